@@ -1,0 +1,538 @@
+// capi.cu -- the C ABI declared in include/gala_b200.h.
+//
+// Host side of the drop-in boundary: turns a gb_potential (the flat mirror of the reference's
+// CPotential, potential/potential/src/cpotential.h:10-36) into the constant-bank DevPot, resolves
+// the composite signature, stages HOST buffers through device memory when asked to, launches the
+// kernels on the caller's stream and maps failures to the error codes of the header.
+// No CPU fallback exists: without a CUDA device every compute entry point returns -10.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/gala_b200.h"
+#include "kernels.h"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long> g_launches{0};
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(-10, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(e__, #call); } while (0)
+
+// expected parameter counts ([G, ...]) of each type for the compile-time signatures
+int expected_npar(int type) {
+    switch (type) {
+        case GB_POT_NULL: return 1;
+        case GB_POT_HERNQUIST: return 3;
+        case GB_POT_NFW_SPHERICAL: case GB_POT_NFW_FLATTENED: case GB_POT_NFW_TRIAXIAL: return 6;
+        case GB_POT_MIYAMOTONAGAI: return 4;
+        case GB_POT_MN3: return 13;
+        case GB_POT_LONGMURALIBAR: return 6;
+        case GB_POT_KEPLER: return 2;
+        case GB_POT_PLUMMER: case GB_POT_ISOCHRONE: case GB_POT_JAFFE: return 3;
+        default: return -1;
+    }
+}
+int min_npar(int type) {
+    switch (type) {
+        case GB_POT_NULL: return 0;
+        case GB_POT_MN3: return 10;
+        case GB_POT_NFW_SPHERICAL: return 3;
+        case GB_POT_SCF: return 5;
+        default: return expected_npar(type);
+    }
+}
+
+struct Resolved {
+    DevPot P;
+    std::vector<double> ext;   // host copy of large parameter blocks (SCF coefficients)
+    double* d_ext = nullptr;   // device copy (owned)
+    ~Resolved() { if (d_ext) cudaFree(d_ext); }
+};
+
+bool sig_matches(const gb_potential* pot, std::initializer_list<int> types) {
+    if ((size_t)pot->n_components != types.size()) return false;
+    int i = 0;
+    for (int t : types) {
+        const gb_component& c = pot->comp[i++];
+        if (c.type_id != t || c.do_shift_rotate || c.n_params != expected_npar(t)) return false;
+    }
+    return true;
+}
+
+// Build the DevPot from the spec: the equivalent of CPotentialWrapper.init +
+// CCompositePotentialWrapper.__init__ (cpotential.pyx:57-102, ccompositepotential.pyx:27-70).
+int resolve(const gb_potential* pot, Resolved& r, cudaStream_t stream) {
+    if (!pot || !pot->comp) return fail(-12, "null potential spec");
+    if (pot->n_dim != 3) return fail(-11, "only n_dim = 3 potentials are supported");
+    if (pot->n_components < 1 || pot->n_components > GB_MAXC)
+        return fail(-11, "number of potential components must be in 1.." + std::to_string(GB_MAXC));
+    DevPot& P = r.P;
+    memset(&P, 0, sizeof(P));
+    P.n = pot->n_components;
+    int off = 0;
+    for (int i = 0; i < P.n; i++) {
+        const gb_component& c = pot->comp[i];
+        if (c.type_id < 0 || c.type_id >= GB_POT_NTYPES) return fail(-11, "unknown potential type id");
+        if (c.type_id == GB_POT_SCF) {
+#if !GB_HAVE_SCF
+            return fail(-11, "SCF potential is not available in this build");
+#endif
+        }
+        if (c.n_params < min_npar(c.type_id) || (c.n_params > 0 && !c.params))
+            return fail(-12, "component " + std::to_string(i) + ": too few parameters for its type");
+        DevComp& d = P.c[i];
+        d.type = c.type_id;
+        d.shift = c.do_shift_rotate ? 1 : 0;
+        d.poff = off;
+        d.eoff = (int)r.ext.size();
+        int nsmall = c.n_params;
+        if (c.type_id == GB_POT_SCF) {
+            nsmall = 5;
+            const int nmax = (int)c.params[1], lmax = (int)c.params[2];
+            const int ncoef = (nmax + 1) * (lmax + 1) * (lmax + 1);
+            if (c.n_params < 5 + 2 * ncoef) return fail(-12, "SCF: parameter vector shorter than 5 + 2*(nmax+1)(lmax+1)^2");
+            if (lmax > 15 || nmax > 63) return fail(-11, "SCF: lmax <= 15 and nmax <= 63 supported");
+            r.ext.insert(r.ext.end(), c.params + 5, c.params + 5 + 2 * ncoef);
+        }
+        d.npar = nsmall;
+        if (off + nsmall > GB_MAXP) return fail(-11, "too many potential parameters for the constant bank");
+        for (int k = 0; k < nsmall; k++) P.par[off + k] = c.params[k];
+        off += nsmall;
+        for (int k = 0; k < 3; k++) d.q0[k] = c.q0[k];
+        for (int k = 0; k < 9; k++) d.R[k] = c.R[k];
+    }
+    // signature resolution
+    P.sig = SIG_GENERIC;
+    if (sig_matches(pot, {GB_POT_NFW_SPHERICAL})) P.sig = SIG_NFW;
+    else if (sig_matches(pot, {GB_POT_HERNQUIST})) P.sig = SIG_HERNQUIST;
+    else if (sig_matches(pot, {GB_POT_MN3, GB_POT_HERNQUIST, GB_POT_HERNQUIST, GB_POT_NFW_SPHERICAL})) P.sig = SIG_MW2022;
+    else if (sig_matches(pot, {GB_POT_LONGMURALIBAR, GB_POT_MN3, GB_POT_HERNQUIST, GB_POT_HERNQUIST, GB_POT_NFW_SPHERICAL})) P.sig = SIG_BAR_MW2022;
+    else if (sig_matches(pot, {GB_POT_MN3, GB_POT_HERNQUIST, GB_POT_HERNQUIST, GB_POT_NFW_SPHERICAL, GB_POT_LONGMURALIBAR})) P.sig = SIG_MW2022_BAR;
+    else if (pot->n_components == 1 && pot->comp[0].type_id == GB_POT_SCF && !pot->comp[0].do_shift_rotate) P.sig = SIG_SCF;
+    if (getenv("GB_FORCE_GENERIC")) P.sig = SIG_GENERIC;
+
+    if (!r.ext.empty()) {
+        CU(cudaMalloc(&r.d_ext, r.ext.size() * sizeof(double)));
+        CU(cudaMemcpyAsync(r.d_ext, r.ext.data(), r.ext.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+        P.ext = r.d_ext;
+    }
+    return 0;
+}
+
+int resolve_frame(const gb_frame* fr, DevFrame& F) {
+    memset(&F, 0, sizeof(F));
+    if (!fr) { F.type = GB_FRAME_STATIC; return 0; }
+    if (fr->type_id != GB_FRAME_STATIC && fr->type_id != GB_FRAME_ROTATING_3D)
+        return fail(-11, "unsupported frame type");
+    F.type = fr->type_id;
+    for (int k = 0; k < 3; k++) F.om[k] = fr->omega[k];
+    return 0;
+}
+
+// Device staging for GB_MEM_HOST calls.  A small grow-only cache per (device, slot) avoids paying
+// cudaMalloc/cudaFree on every call of a time-stepping loop written on the Python side.
+struct Scratch {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    int dev = -1;
+};
+constexpr int NSLOT = 8;
+std::mutex g_scratch_mu;
+Scratch g_scratch[NSLOT];
+
+cudaError_t scratch_get(int slot, size_t bytes, void** out) {
+    int dev;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    Scratch& s = g_scratch[slot];
+    if (s.ptr && (s.dev != dev || s.cap < bytes)) {
+        int cur = dev;
+        if (s.dev != dev) cudaSetDevice(s.dev);
+        cudaFree(s.ptr);
+        if (s.dev != cur) cudaSetDevice(cur);
+        s.ptr = nullptr; s.cap = 0;
+    }
+    if (!s.ptr) {
+        if (bytes == 0) bytes = 8;
+        e = cudaMalloc(&s.ptr, bytes);
+        if (e != cudaSuccess) { s.ptr = nullptr; return e; }
+        s.cap = bytes; s.dev = dev;
+    }
+    *out = s.ptr;
+    return cudaSuccess;
+}
+
+struct Ctx {
+    cudaStream_t stream = nullptr;
+    bool host = true;
+    bool strict = false;
+    int block = 0;
+    int prev_dev = -1;
+    std::unique_lock<std::mutex> lock;   // held for HOST-staged calls (they share the scratch cache)
+    ~Ctx() { if (prev_dev >= 0) cudaSetDevice(prev_dev); }
+};
+
+int open_ctx(const gb_launch* opt, Ctx& c) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(-10, std::string("no CUDA device available (this engine has no CPU fallback): ") +
+                             (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (opt) {
+        c.stream = (cudaStream_t)opt->stream;
+        c.host = opt->mem == GB_MEM_HOST;
+        c.strict = opt->strict_math != 0;
+        c.block = opt->block_threads;
+        if (opt->device >= 0) {
+            int cur; CU(cudaGetDevice(&cur));
+            if (cur != opt->device) { c.prev_dev = cur; CU(cudaSetDevice(opt->device)); }
+        }
+    }
+    if (c.host) c.lock = std::unique_lock<std::mutex>(g_scratch_mu);
+    return 0;
+}
+
+// input staging: returns a device pointer for `p` (copying when the call is HOST-staged)
+int stage_in(Ctx& c, int slot, const void* p, size_t bytes, const void** dptr) {
+    if (!c.host) { *dptr = p; return 0; }
+    void* d; CU(scratch_get(slot, bytes, &d));
+    if (bytes) CU(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, c.stream));
+    *dptr = d;
+    return 0;
+}
+int stage_out_alloc(Ctx& c, int slot, void* p, size_t bytes, void** dptr) {
+    if (!c.host) { *dptr = p; return 0; }
+    CU(scratch_get(slot, bytes, dptr));
+    return 0;
+}
+int stage_out_copy(Ctx& c, void* host, const void* dev, size_t bytes) {
+    if (!c.host || !host || bytes == 0) return 0;
+    CU(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c.stream));
+    return 0;
+}
+int finish(Ctx& c) {
+    // HOST-staged calls return results in caller memory, so they must complete before returning.
+    // DEVICE calls stay asynchronous on the caller's stream (errors surface at the caller's sync).
+    if (c.host) CU(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+#define RET_IF(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
+#define KCALL(c, fn, ...) ((c).strict ? gbk_strict::fn(__VA_ARGS__) : gbk_fast::fn(__VA_ARGS__))
+
+// Ruth4 coefficients exactly as the reference computes them (ruth4.pyx:65-78; numpy float pow ==
+// C pow on the host).
+void ruth4_coeffs(double* cs, double* ds) {
+    const double two_13 = pow(2., 1. / 3.);
+    cs[0] = 1. / (2. * (2. - two_13));
+    cs[1] = (1. - two_13) / (2. * (2. - two_13));
+    cs[2] = (1. - two_13) / (2. * (2. - two_13));
+    cs[3] = 1. / (2. * (2. - two_13));
+    ds[0] = 0.;
+    ds[1] = 1. / (2. - two_13);
+    ds[2] = -two_13 / (2. - two_13);
+    ds[3] = 1. / (2. - two_13);
+}
+
+enum EvalKind { EV_GRAD, EV_ENERGY, EV_DENSITY };
+
+int eval_common(EvalKind kind, const gb_potential* pot, const double* q, double t, size_t N, double* out,
+                const gb_launch* opt) {
+    Ctx c; RET_IF(open_ctx(opt, c));
+    if (N && (!q || !out)) return fail(-12, "null data pointer");
+    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    const int block = c.block > 0 ? c.block : 128;
+    const void* dq; RET_IF(stage_in(c, 0, q, 3 * N * sizeof(double), &dq));
+    const size_t ob = (kind == EV_GRAD ? 3 : 1) * N * sizeof(double);
+    void* dout; RET_IF(stage_out_alloc(c, 1, out, ob, &dout));
+    cudaError_t e;
+    if (kind == EV_GRAD) e = KCALL(c, eval_gradient, r.P, (const double*)dq, t, N, (double*)dout, block, c.stream);
+    else if (kind == EV_ENERGY) e = KCALL(c, eval_energy, r.P, (const double*)dq, t, N, (double*)dout, block, c.stream);
+    else e = KCALL(c, eval_density, r.P, (const double*)dq, t, N, (double*)dout, block, c.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "evaluation kernel launch");
+    if (N) g_launches++;
+    RET_IF(stage_out_copy(c, out, dout, ob));
+    if (r.d_ext) CU(cudaStreamSynchronize(c.stream));   // d_ext is freed when r goes out of scope
+    return finish(c);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gb_last_error(void) { return g_err.c_str(); }
+const char* gb_version(void) { return "gala_b200 0.1 (sm_100a)"; }
+long gb_launch_count(void) { return g_launches.load(); }
+int gb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int gb_gradient(const gb_potential* pot, const double* q, double t, size_t N, double* grad, const gb_launch* opt) {
+    return eval_common(EV_GRAD, pot, q, t, N, grad, opt);
+}
+int gb_energy(const gb_potential* pot, const double* q, double t, size_t N, double* out, const gb_launch* opt) {
+    return eval_common(EV_ENERGY, pot, q, t, N, out, opt);
+}
+int gb_density(const gb_potential* pot, const double* q, double t, size_t N, double* out, const gb_launch* opt) {
+    return eval_common(EV_DENSITY, pot, q, t, N, out, opt);
+}
+
+int gb_hamiltonian_energy(const gb_potential* pot, const gb_frame* fr, const double* w, double t, size_t N,
+                          double* out, const gb_launch* opt) {
+    Ctx c; RET_IF(open_ctx(opt, c));
+    if (N && (!w || !out)) return fail(-12, "null data pointer");
+    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    DevFrame F; RET_IF(resolve_frame(fr, F));
+    const int block = c.block > 0 ? c.block : 128;
+    const void* dw; RET_IF(stage_in(c, 0, w, 6 * N * sizeof(double), &dw));
+    void* dout; RET_IF(stage_out_alloc(c, 1, out, N * sizeof(double), &dout));
+    cudaError_t e = KCALL(c, ham_energy, r.P, F, (const double*)dw, t, N, (double*)dout, block, c.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "ham_energy launch");
+    if (N) g_launches++;
+    RET_IF(stage_out_copy(c, out, dout, N * sizeof(double)));
+    if (r.d_ext) CU(cudaStreamSynchronize(c.stream));
+    return finish(c);
+}
+
+int gb_hamiltonian_gradient(const gb_potential* pot, const gb_frame* fr, const double* w, double t, size_t N,
+                            double* f, const gb_launch* opt) {
+    Ctx c; RET_IF(open_ctx(opt, c));
+    if (N && (!w || !f)) return fail(-12, "null data pointer");
+    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    DevFrame F; RET_IF(resolve_frame(fr, F));
+    const int block = c.block > 0 ? c.block : 128;
+    const void* dw; RET_IF(stage_in(c, 0, w, 6 * N * sizeof(double), &dw));
+    void* dout; RET_IF(stage_out_alloc(c, 1, f, 6 * N * sizeof(double), &dout));
+    cudaError_t e = KCALL(c, ham_gradient, r.P, F, (const double*)dw, t, N, (double*)dout, block, c.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "ham_gradient launch");
+    if (N) g_launches++;
+    RET_IF(stage_out_copy(c, f, dout, 6 * N * sizeof(double)));
+    if (r.d_ext) CU(cudaStreamSynchronize(c.stream));
+    return finish(c);
+}
+
+static int fixed_step_common(bool is_ruth4, const gb_potential* pot, const gb_frame* fr, const double* w0, size_t N,
+                             const double* t, int ntimes, int save_all, double* w_out, const gb_launch* opt) {
+    Ctx c; RET_IF(open_ctx(opt, c));
+    if (ntimes < 2) return fail(-12, "the time grid needs at least 2 entries");
+    if (!t || (N && (!w0 || !w_out))) return fail(-12, "null data pointer");
+    DevFrame F; RET_IF(resolve_frame(fr, F));
+    if (!is_ruth4 && F.type != GB_FRAME_STATIC)
+        return fail(-13, "Leapfrog integration is currently only supported for StaticFrame");
+    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    const int block = c.block > 0 ? c.block : 128;
+    // t is always read on the host for dt (it is tiny); the kernels take dt by value
+    std::vector<double> th;
+    double dt;
+    const double* dt_dev = nullptr;
+    if (c.host) { dt = t[1] - t[0]; }
+    else {
+        double two[2];
+        CU(cudaMemcpyAsync(two, t, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        CU(cudaStreamSynchronize(c.stream));
+        dt = two[1] - two[0];
+    }
+    const void* dw0; RET_IF(stage_in(c, 0, w0, 6 * N * sizeof(double), &dw0));
+    const void* dtg; RET_IF(stage_in(c, 2, t, (size_t)ntimes * sizeof(double), &dtg));
+    dt_dev = (const double*)dtg;
+    const size_t ob = (save_all ? (size_t)ntimes : 1) * 6 * N * sizeof(double);
+    void* dout; RET_IF(stage_out_alloc(c, 1, w_out, ob, &dout));
+    cudaError_t e;
+    if (!is_ruth4) {
+        e = KCALL(c, leapfrog, r.P, (const double*)dw0, N, dt_dev, ntimes, dt, save_all, (double*)dout, block, c.stream);
+    } else {
+        double cs[4], ds[4];
+        ruth4_coeffs(cs, ds);
+        e = KCALL(c, ruth4, r.P, F, (const double*)dw0, N, dt_dev, ntimes, dt, cs, ds, save_all, (double*)dout, block, c.stream);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "integrator kernel launch");
+    if (N) g_launches++;
+    RET_IF(stage_out_copy(c, w_out, dout, ob));
+    if (r.d_ext) CU(cudaStreamSynchronize(c.stream));
+    return finish(c);
+}
+
+int gb_leapfrog(const gb_potential* pot, const gb_frame* fr, const double* w0, size_t N, const double* t,
+                int ntimes, int save_all, double* w_out, const gb_launch* opt) {
+    return fixed_step_common(false, pot, fr, w0, N, t, ntimes, save_all, w_out, opt);
+}
+int gb_ruth4(const gb_potential* pot, const gb_frame* fr, const double* w0, size_t N, const double* t, int ntimes,
+             int save_all, double* w_out, const gb_launch* opt) {
+    return fixed_step_common(true, pot, fr, w0, N, t, ntimes, save_all, w_out, opt);
+}
+
+// dop853() front-end defaults (dopri/dop853.cpp:673-788)
+static int dop853_defaults(Dop853Args& a, double atol, double rtol, long nmax, double dt_max, long nstiff,
+                           double uround, double h0) {
+    a.atol = atol; a.rtol = rtol;
+    if (!nmax) nmax = 1000000;
+    else if (nmax < 0) return fail(-1, "dop853: wrong input, nmax < 0");
+    a.nmax = nmax;
+    if (!nstiff) nstiff = 1000;
+    else if (nstiff < 0) nstiff = nmax + 10;
+    a.nstiff = nstiff;
+    if (uround == 0.0) uround = 2.3E-16;
+    else if (uround <= 1.0E-35 || uround >= 1.0) return fail(-1, "dop853: bad uround");
+    a.uround = uround;
+    a.hmax = dt_max;
+    a.h0 = h0;
+    return 0;
+}
+
+static int worst_status(Ctx& c, const int32_t* dstatus, size_t N, int32_t* host_status, int* worst) {
+    // the per-orbit codes decide the return value, so they are always brought to the host
+    std::vector<int32_t> tmp;
+    int32_t* hs = host_status;
+    if (!c.host || !hs) { tmp.resize(N); hs = tmp.data(); }
+    if (!c.host || !host_status) {
+        CU(cudaMemcpyAsync(hs, dstatus, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+    }
+    CU(cudaStreamSynchronize(c.stream));
+    int w = 0;
+    for (size_t i = 0; i < N; i++) if (hs[i] < w) w = hs[i];
+    *worst = w;
+    return 0;
+}
+
+int gb_dop853(const gb_potential* pot, const gb_frame* fr, const double* w0, size_t N, const double* t, int ntimes,
+              double atol, double rtol, long nmax, double dt_max, long nstiff, int save_all, double* w_out,
+              int32_t* status, const gb_dop853_stats* stats, const gb_launch* opt) {
+    Ctx c; RET_IF(open_ctx(opt, c));
+    if (ntimes < 2) return fail(-12, "the time grid needs at least 2 entries");
+    if (!t || (N && (!w0 || !w_out))) return fail(-12, "null data pointer");
+    DevFrame F; RET_IF(resolve_frame(fr, F));
+    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    const int block = c.block > 0 ? c.block : 64;
+    double two[2];
+    if (c.host) { two[0] = t[0]; two[1] = t[1]; }
+    else {
+        CU(cudaMemcpyAsync(two, t, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        CU(cudaStreamSynchronize(c.stream));
+    }
+    Dop853Args a;
+    // dop853_helper passes uround = np.finfo(float).eps and h = t[1]-t[0] (dop853.pyx:157-182)
+    RET_IF(dop853_defaults(a, atol, rtol, nmax, dt_max, nstiff, 2.220446049250313e-16, two[1] - two[0]));
+    const void* dw0; RET_IF(stage_in(c, 0, w0, 6 * N * sizeof(double), &dw0));
+    const void* dtg; RET_IF(stage_in(c, 2, t, (size_t)ntimes * sizeof(double), &dtg));
+    const size_t ob = (save_all ? (size_t)ntimes : 1) * 6 * N * sizeof(double);
+    void* dout; RET_IF(stage_out_alloc(c, 1, w_out, ob, &dout));
+    // status + optional stats
+    void* dstat;
+    if (c.host || !status) CU(scratch_get(3, N * sizeof(int32_t), &dstat)); else dstat = status;
+    int32_t* dst[4] = {nullptr, nullptr, nullptr, nullptr};
+    int32_t* hst[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (stats) { hst[0] = stats->nstep; hst[1] = stats->naccpt; hst[2] = stats->nrejct; hst[3] = stats->nfcn; }
+    for (int k = 0; k < 4; k++) {
+        if (!hst[k]) continue;
+        if (c.host) { void* d; CU(scratch_get(4 + k, N * sizeof(int32_t), &d)); dst[k] = (int32_t*)d; }
+        else dst[k] = hst[k];
+    }
+    cudaError_t e = (F.type == GB_FRAME_STATIC)
+        ? KCALL(c, dop853_static, r.P, F, (const double*)dw0, N, (const double*)dtg, ntimes, a, save_all,
+                (double*)dout, (int32_t*)dstat, dst[0], dst[1], dst[2], dst[3], block, c.stream)
+        : KCALL(c, dop853_rotating, r.P, F, (const double*)dw0, N, (const double*)dtg, ntimes, a, save_all,
+                (double*)dout, (int32_t*)dstat, dst[0], dst[1], dst[2], dst[3], block, c.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "dop853 kernel launch");
+    if (N) g_launches++;
+    RET_IF(stage_out_copy(c, w_out, dout, ob));
+    if (c.host) {
+        if (status) RET_IF(stage_out_copy(c, status, dstat, N * sizeof(int32_t)));
+        for (int k = 0; k < 4; k++) if (hst[k]) RET_IF(stage_out_copy(c, hst[k], dst[k], N * sizeof(int32_t)));
+    }
+    int worst = 0;
+    if (N) RET_IF(worst_status(c, (const int32_t*)dstat, N, c.host ? status : nullptr, &worst));
+    RET_IF(finish(c));
+    if (worst < 0) return fail(worst, "Integration failed with code " + std::to_string(worst));
+    return 0;
+}
+
+int gb_fardal_release(const gb_potential* pot, double G, const double* prog_w, const double* prog_t,
+                      const double* prog_m, int ntimes, const int32_t* prog_idx, const double* sign,
+                      const double* normals, size_t Np, int gala_modified, double* stream_w0,
+                      const gb_launch* opt) {
+    Ctx c; RET_IF(open_ctx(opt, c));
+    if (ntimes < 1 || !prog_w || !prog_t || !prog_m) return fail(-12, "null progenitor arrays");
+    if (Np && (!prog_idx || !sign || !normals || !stream_w0)) return fail(-12, "null data pointer");
+    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    const int block = c.block > 0 ? c.block : 128;
+    const void *dpw, *dpt, *dpm, *dpi, *dsg, *dnr;
+    RET_IF(stage_in(c, 0, prog_w, (size_t)ntimes * 6 * sizeof(double), &dpw));
+    RET_IF(stage_in(c, 2, prog_t, (size_t)ntimes * sizeof(double), &dpt));
+    RET_IF(stage_in(c, 3, prog_m, (size_t)ntimes * sizeof(double), &dpm));
+    RET_IF(stage_in(c, 4, prog_idx, Np * sizeof(int32_t), &dpi));
+    RET_IF(stage_in(c, 5, sign, Np * sizeof(double), &dsg));
+    RET_IF(stage_in(c, 6, normals, Np * 4 * sizeof(double), &dnr));
+    void* dout; RET_IF(stage_out_alloc(c, 1, stream_w0, Np * 6 * sizeof(double), &dout));
+    cudaError_t e = KCALL(c, fardal_release, r.P, G, (const double*)dpw, (const double*)dpt, (const double*)dpm, ntimes,
+                          (const int32_t*)dpi, (const double*)dsg, (const double*)dnr, Np, gala_modified,
+                          (double*)dout, block, c.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "fardal_release launch");
+    if (Np) g_launches++;
+    RET_IF(stage_out_copy(c, stream_w0, dout, Np * 6 * sizeof(double)));
+    if (r.d_ext) CU(cudaStreamSynchronize(c.stream));
+    return finish(c);
+}
+
+int gb_mockstream_dop853(const gb_potential* pot, const gb_frame* fr, const double* stream_w0, const double* t1,
+                         size_t Np, double tfinal, double dt0, double atol, double rtol, long nmax,
+                         double* stream_w, int32_t* status, const gb_launch* opt) {
+    Ctx c; RET_IF(open_ctx(opt, c));
+    if (Np && (!stream_w0 || !t1 || !stream_w)) return fail(-12, "null data pointer");
+    DevFrame F; RET_IF(resolve_frame(fr, F));
+    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    const int block = c.block > 0 ? c.block : 64;
+    Dop853Args a;
+    // dop853_step (dop853.pyx:45-69): uround 0 -> 2.3e-16, hmax 0, nstiff hard-coded to 1
+    RET_IF(dop853_defaults(a, atol, rtol, nmax, 0.0, 1, 0.0, dt0));
+    const void *dw0, *dt1;
+    RET_IF(stage_in(c, 0, stream_w0, Np * 6 * sizeof(double), &dw0));
+    RET_IF(stage_in(c, 2, t1, Np * sizeof(double), &dt1));
+    void* dout; RET_IF(stage_out_alloc(c, 1, stream_w, Np * 6 * sizeof(double), &dout));
+    void* dstat;
+    if (c.host || !status) CU(scratch_get(3, Np * sizeof(int32_t), &dstat)); else dstat = status;
+    cudaError_t e = KCALL(c, mock_dop853, r.P, F, (const double*)dw0, (const double*)dt1, Np, tfinal, a,
+                          (double*)dout, (int32_t*)dstat, block, c.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "mock_dop853 launch");
+    if (Np) g_launches++;
+    RET_IF(stage_out_copy(c, stream_w, dout, Np * 6 * sizeof(double)));
+    if (c.host && status) RET_IF(stage_out_copy(c, status, dstat, Np * sizeof(int32_t)));
+    int worst = 0;
+    if (Np) RET_IF(worst_status(c, (const int32_t*)dstat, Np, c.host ? status : nullptr, &worst));
+    RET_IF(finish(c));
+    if (worst < 0) return fail(worst, "Integration failed with code " + std::to_string(worst));
+    return 0;
+}
+
+int gb_mockstream_leapfrog(const gb_potential* pot, const double* stream_w0, const double* t1, size_t Np,
+                           double tfinal, double dt, double* stream_w, const gb_launch* opt) {
+    Ctx c; RET_IF(open_ctx(opt, c));
+    if (Np && (!stream_w0 || !t1 || !stream_w)) return fail(-12, "null data pointer");
+    if (dt == 0.0) return fail(-12, "dt must be non-zero");
+    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    const int block = c.block > 0 ? c.block : 128;
+    const void *dw0, *dt1;
+    RET_IF(stage_in(c, 0, stream_w0, Np * 6 * sizeof(double), &dw0));
+    RET_IF(stage_in(c, 2, t1, Np * sizeof(double), &dt1));
+    void* dout; RET_IF(stage_out_alloc(c, 1, stream_w, Np * 6 * sizeof(double), &dout));
+    cudaError_t e = KCALL(c, mock_leapfrog, r.P, (const double*)dw0, (const double*)dt1, Np, tfinal, dt,
+                          (double*)dout, block, c.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "mock_leapfrog launch");
+    if (Np) g_launches++;
+    RET_IF(stage_out_copy(c, stream_w, dout, Np * 6 * sizeof(double)));
+    if (r.d_ext) CU(cudaStreamSynchronize(c.stream));
+    return finish(c);
+}
+
+}  // extern "C"

@@ -1,0 +1,164 @@
+// composite.cuh -- composite-potential dispatch.
+//
+// Replaces c_gradient / c_potential / c_density (reference potential/potential/src/
+// cpotential.cpp:170-287), which loop over components calling host function pointers.
+// Two forms:
+//   Composite<SIG_GENERIC>  a loop with a warp-uniform switch on the component type id; handles
+//                           any component list incl. per-component shift/rotate (cpotential.cpp:
+//                           246-277, apply_shift_rotate_N + apply_rotate_T transpose).
+//   Composite<SIG_xxx>      a compile-time component list (variadic template): no loop, no switch,
+//                           parameter offsets are immediates into the constant bank.
+#pragma once
+#include "potentials.cuh"
+#include "scf.cuh"
+
+template <int T> struct PotOf;
+template <> struct PotOf<GB_POT_NULL>          { using type = PotNull;          static constexpr int NP = 1; };
+template <> struct PotOf<GB_POT_HERNQUIST>     { using type = PotHernquist;     static constexpr int NP = 3; };
+template <> struct PotOf<GB_POT_NFW_SPHERICAL> { using type = PotNFWSpherical;  static constexpr int NP = 6; };
+template <> struct PotOf<GB_POT_NFW_FLATTENED> { using type = PotNFWFlattened;  static constexpr int NP = 6; };
+template <> struct PotOf<GB_POT_NFW_TRIAXIAL>  { using type = PotNFWTriaxial;   static constexpr int NP = 6; };
+template <> struct PotOf<GB_POT_MIYAMOTONAGAI> { using type = PotMiyamotoNagai; static constexpr int NP = 4; };
+template <> struct PotOf<GB_POT_MN3>           { using type = PotMN3;           static constexpr int NP = 13; };
+template <> struct PotOf<GB_POT_LONGMURALIBAR> { using type = PotLongMuraliBar; static constexpr int NP = 6; };
+template <> struct PotOf<GB_POT_KEPLER>        { using type = PotKepler;        static constexpr int NP = 2; };
+template <> struct PotOf<GB_POT_PLUMMER>       { using type = PotPlummer;       static constexpr int NP = 3; };
+template <> struct PotOf<GB_POT_ISOCHRONE>     { using type = PotIsochrone;     static constexpr int NP = 3; };
+template <> struct PotOf<GB_POT_JAFFE>         { using type = PotJaffe;         static constexpr int NP = 3; };
+
+// ---- runtime (generic) component dispatch -----------------------------------------------------
+#define GB_FOR_EACH_SIMPLE_TYPE(X) \
+    X(GB_POT_NULL) X(GB_POT_HERNQUIST) X(GB_POT_NFW_SPHERICAL) X(GB_POT_NFW_FLATTENED) X(GB_POT_NFW_TRIAXIAL) \
+    X(GB_POT_MIYAMOTONAGAI) X(GB_POT_MN3) X(GB_POT_LONGMURALIBAR) X(GB_POT_KEPLER) X(GB_POT_PLUMMER) \
+    X(GB_POT_ISOCHRONE) X(GB_POT_JAFFE)
+
+GB_DEV void gb_comp_gradient(int type, const double* p, const double* e, double x, double y, double z,
+                             double& gx, double& gy, double& gz) {
+    switch (type) {
+#define X(T) case T: PotOf<T>::type::gradient(p, x, y, z, gx, gy, gz); break;
+        GB_FOR_EACH_SIMPLE_TYPE(X)
+#undef X
+        case GB_POT_SCF: PotSCF::gradient(p, e, x, y, z, gx, gy, gz); break;
+        default: break;
+    }
+}
+GB_DEV double gb_comp_value(int type, const double* p, const double* e, double x, double y, double z) {
+    switch (type) {
+#define X(T) case T: return PotOf<T>::type::value(p, x, y, z);
+        GB_FOR_EACH_SIMPLE_TYPE(X)
+#undef X
+        case GB_POT_SCF: return PotSCF::value(p, e, x, y, z);
+        default: return 0.;
+    }
+}
+GB_DEV double gb_comp_density(int type, const double* p, const double* e, double x, double y, double z) {
+    switch (type) {
+#define X(T) case T: return PotOf<T>::type::density(p, x, y, z);
+        GB_FOR_EACH_SIMPLE_TYPE(X)
+#undef X
+        case GB_POT_SCF: return PotSCF::density(p, e, x, y, z);
+        default: return 0.;
+    }
+}
+
+// shift to the component origin and rotate (cpotential.cpp:151-167 + apply_rotate_T :113-131)
+GB_DEV void gb_shift_rotate(const DevComp& c, double x, double y, double z, double& X, double& Y, double& Z) {
+    const double sx = x - c.q0[0], sy = y - c.q0[1], sz = z - c.q0[2];
+    X = c.R[0] * sx + c.R[1] * sy + c.R[2] * sz;
+    Y = c.R[3] * sx + c.R[4] * sy + c.R[5] * sz;
+    Z = c.R[6] * sx + c.R[7] * sy + c.R[8] * sz;
+}
+
+template <int SIG> struct Composite;
+
+template <> struct Composite<SIG_GENERIC> {
+    GB_DEV static void gradient(const DevPot& P, double t, double x, double y, double z,
+                                double& gx, double& gy, double& gz) {
+        gx = 0.; gy = 0.; gz = 0.;
+        for (int i = 0; i < P.n; i++) {
+            const DevComp& c = P.c[i];
+            const double* p = &P.par[c.poff];
+            const double* e = P.ext + c.eoff;
+            if (!c.shift) {
+                gb_comp_gradient(c.type, p, e, x, y, z, gx, gy, gz);
+            } else {
+                double X, Y, Z, ax = 0., ay = 0., az = 0.;
+                gb_shift_rotate(c, x, y, z, X, Y, Z);
+                gb_comp_gradient(c.type, p, e, X, Y, Z, ax, ay, az);
+                // rotate back with R^T and accumulate (cpotential.cpp:263-277)
+                gx += c.R[0] * ax + c.R[3] * ay + c.R[6] * az;
+                gy += c.R[1] * ax + c.R[4] * ay + c.R[7] * az;
+                gz += c.R[2] * ax + c.R[5] * ay + c.R[8] * az;
+            }
+        }
+    }
+    GB_DEV static double value(const DevPot& P, double t, double x, double y, double z) {
+        double v = 0.;
+        for (int i = 0; i < P.n; i++) {
+            const DevComp& c = P.c[i];
+            double X = x, Y = y, Z = z;
+            if (c.shift) gb_shift_rotate(c, x, y, z, X, Y, Z);
+            v = v + gb_comp_value(c.type, &P.par[c.poff], P.ext + c.eoff, X, Y, Z);
+        }
+        return v;
+    }
+    GB_DEV static double density(const DevPot& P, double t, double x, double y, double z) {
+        double v = 0.;
+        for (int i = 0; i < P.n; i++) {
+            const DevComp& c = P.c[i];
+            double X = x, Y = y, Z = z;
+            if (c.shift) gb_shift_rotate(c, x, y, z, X, Y, Z);
+            v = v + gb_comp_density(c.type, &P.par[c.poff], P.ext + c.eoff, X, Y, Z);
+        }
+        return v;
+    }
+};
+
+// ---- compile-time component lists ------------------------------------------------------------
+template <int OFF, int... Ts> struct SeqImpl;
+template <int OFF> struct SeqImpl<OFF> {
+    GB_DEV static void gradient(const DevPot&, double, double, double, double&, double&, double&) {}
+    GB_DEV static double value(const DevPot&, double, double, double, double v) { return v; }
+    GB_DEV static double density(const DevPot&, double, double, double, double v) { return v; }
+};
+template <int OFF, int T0, int... Ts> struct SeqImpl<OFF, T0, Ts...> {
+    using Pt = typename PotOf<T0>::type;
+    using Next = SeqImpl<OFF + PotOf<T0>::NP, Ts...>;
+    GB_DEV static void gradient(const DevPot& P, double x, double y, double z, double& gx, double& gy, double& gz) {
+        Pt::gradient(&P.par[OFF], x, y, z, gx, gy, gz);
+        Next::gradient(P, x, y, z, gx, gy, gz);
+    }
+    GB_DEV static double value(const DevPot& P, double x, double y, double z, double v) {
+        return Next::value(P, x, y, z, v + Pt::value(&P.par[OFF], x, y, z));
+    }
+    GB_DEV static double density(const DevPot& P, double x, double y, double z, double v) {
+        return Next::density(P, x, y, z, v + Pt::density(&P.par[OFF], x, y, z));
+    }
+};
+template <int... Ts> struct Seq {
+    GB_DEV static void gradient(const DevPot& P, double t, double x, double y, double z,
+                                double& gx, double& gy, double& gz) {
+        gx = 0.; gy = 0.; gz = 0.;
+        SeqImpl<0, Ts...>::gradient(P, x, y, z, gx, gy, gz);
+    }
+    GB_DEV static double value(const DevPot& P, double t, double x, double y, double z) {
+        return SeqImpl<0, Ts...>::value(P, x, y, z, 0.);
+    }
+    GB_DEV static double density(const DevPot& P, double t, double x, double y, double z) {
+        return SeqImpl<0, Ts...>::density(P, x, y, z, 0.);
+    }
+};
+
+template <> struct Composite<SIG_NFW>        : Seq<GB_POT_NFW_SPHERICAL> {};
+template <> struct Composite<SIG_HERNQUIST>  : Seq<GB_POT_HERNQUIST> {};
+template <> struct Composite<SIG_MW2022>     : Seq<GB_POT_MN3, GB_POT_HERNQUIST, GB_POT_HERNQUIST, GB_POT_NFW_SPHERICAL> {};
+template <> struct Composite<SIG_BAR_MW2022> : Seq<GB_POT_LONGMURALIBAR, GB_POT_MN3, GB_POT_HERNQUIST, GB_POT_HERNQUIST, GB_POT_NFW_SPHERICAL> {};
+template <> struct Composite<SIG_MW2022_BAR> : Seq<GB_POT_MN3, GB_POT_HERNQUIST, GB_POT_HERNQUIST, GB_POT_NFW_SPHERICAL, GB_POT_LONGMURALIBAR> {};
+template <> struct Composite<SIG_SCF> {
+    GB_DEV static void gradient(const DevPot& P, double t, double x, double y, double z, double& gx, double& gy, double& gz) {
+        gx = 0.; gy = 0.; gz = 0.;
+        PotSCF::gradient(&P.par[0], P.ext, x, y, z, gx, gy, gz);
+    }
+    GB_DEV static double value(const DevPot& P, double t, double x, double y, double z) { return PotSCF::value(&P.par[0], P.ext, x, y, z); }
+    GB_DEV static double density(const DevPot& P, double t, double x, double y, double z) { return PotSCF::density(&P.par[0], P.ext, x, y, z); }
+};

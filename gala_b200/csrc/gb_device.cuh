@@ -1,0 +1,76 @@
+// gb_device.cuh -- device-side potential description and small math helpers.
+//
+// The potential arrives in a kernel as ONE __grid_constant__ struct (DevPot): it lives in the
+// constant bank, every thread of a warp reads the same word, so parameter loads are uniform
+// constant-cache operands of the FP64 instructions rather than register-file traffic.
+// It replaces struct _CPotential (reference potential/potential/src/cpotential.h:10-36):
+// type ids instead of host function pointers, all parameter vectors packed into one array.
+#pragma once
+#include <stdint.h>
+#include "../../include/gala_b200.h"
+
+#define GB_HAVE_SCF 0   // flipped to 1 when scf.cuh carries the recurrence implementation
+#define GB_MAXC 8      // components per composite held in the constant bank
+#define GB_MAXP 120    // packed doubles of "small" parameters ([G, ...] of every component)
+
+struct DevComp {
+    int32_t type;      // gb_pot_type
+    int32_t shift;     // do_shift_rotate
+    int32_t poff;      // offset of this component's [G, ...] in DevPot::par
+    int32_t npar;
+    int32_t eoff;      // offset of this component's large-parameter block in DevPot::ext
+    int32_t _pad;
+    double q0[3];
+    double R[9];
+};
+
+struct DevPot {
+    int32_t n;                 // n_components
+    int32_t sig;               // GbSig the host resolved (informational on device)
+    DevComp c[GB_MAXC];
+    double par[GB_MAXP];
+    const double* ext;         // device-global parameters of "large" components (SCF coefficients)
+};
+
+struct DevFrame {
+    int32_t type;              // gb_frame_type
+    int32_t _pad;
+    double om[3];
+};
+
+// Compile-time composite signatures the host can resolve a gb_potential to.  Everything else
+// runs through SIG_GENERIC (a warp-uniform switch per component).
+enum GbSig {
+    SIG_GENERIC = 0,
+    SIG_NFW,            // [SphericalNFW]
+    SIG_HERNQUIST,      // [Hernquist]
+    SIG_MW2022,         // [MN3, Hernquist, Hernquist, SphericalNFW]  (special.py:221-271 order)
+    SIG_BAR_MW2022,     // [LongMuraliBar, MN3, Hernquist, Hernquist, SphericalNFW]
+    SIG_MW2022_BAR,     // [MN3, Hernquist, Hernquist, SphericalNFW, LongMuraliBar]
+    SIG_SCF,            // [SCF]
+    SIG_COUNT
+};
+
+#ifdef __CUDACC__
+#define GB_DEV __device__ __forceinline__
+
+// ---- math helpers -------------------------------------------------------------------------
+// GB_STRICT=1: IEEE sqrt/div and libm pow/log in the reference's operation order, compiled with
+// -fmad=false.  GB_STRICT=0: same formulas, FMA contraction allowed, x^-1.5 via rsqrt,
+// reciprocals shared where the reference divides repeatedly.
+#ifndef GB_STRICT
+#define GB_STRICT 0
+#endif
+
+GB_DEV double gb_pow_m1p5(double x) {
+#if GB_STRICT
+    return pow(x, -1.5);
+#else
+    const double r = rsqrt(x);
+    return r * r * r;
+#endif
+}
+
+GB_DEV double gb_norm3(double x, double y, double z) { return sqrt(x * x + y * y + z * z); }
+
+#endif  // __CUDACC__

@@ -1,0 +1,294 @@
+// kernels.cu -- sm_100a FP64 kernels of the orbit-integration hot path.
+//
+// One thread = one orbit; phase-space state lives in registers for the whole time loop; global
+// memory is touched only for the initial load, the (optional) per-step trajectory store and the
+// final state.  All arrays are structure-of-arrays (6,N) / (6,ntimes,N) like the reference
+// (integrate/cyintegrators/leapfrog.pyx:57-59,92), so a warp's load/store of one phase-space
+// component is one contiguous 256-byte segment.
+//
+// Compiled twice (see kernels.h): GB_NS = gbk_fast | gbk_strict.
+#include <math_constants.h>
+#include "kernels.h"
+
+#ifndef GB_NS
+#error "GB_NS must be defined (gbk_fast or gbk_strict)"
+#endif
+
+// Everything below -- device functions included -- lives in the per-build namespace, so the
+// strict and the fast translation units never share a (weak) template symbol.
+namespace GB_NS {
+#include "composite.cuh"
+#include "hamiltonian.cuh"
+#include "dop853.cuh"
+#include "mockstream.cuh"
+
+#if GB_PART == 1
+// ------------------------------------------------------------------------------------------------
+// batched evaluation kernels (CPotentialWrapper.gradient/energy/density, cpotential.pyx:104-162;
+// Hamiltonian.energy/gradient, hamiltonian/src/chamiltonian.cpp:7-57)
+// ------------------------------------------------------------------------------------------------
+template <class C>
+__global__ void k_eval_gradient(const __grid_constant__ DevPot P, const double* __restrict__ q, double t,
+                                size_t N, double* __restrict__ g) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double gx, gy, gz;
+    C::gradient(P, t, q[i], q[N + i], q[2 * N + i], gx, gy, gz);
+    g[i] = gx; g[N + i] = gy; g[2 * N + i] = gz;
+}
+template <class C, int WHAT>
+__global__ void k_eval_scalar(const __grid_constant__ DevPot P, const double* __restrict__ q, double t,
+                              size_t N, double* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    out[i] = (WHAT == 0) ? C::value(P, t, q[i], q[N + i], q[2 * N + i])
+                         : C::density(P, t, q[i], q[N + i], q[2 * N + i]);
+}
+
+template <class C>
+__global__ void k_ham_energy(const __grid_constant__ DevPot P, const __grid_constant__ DevFrame F,
+                             const double* __restrict__ w, double t, size_t N, double* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double x = w[i], y = w[N + i], z = w[2 * N + i];
+    out[i] = C::value(P, t, x, y, z) + frame_energy(F, x, y, z, w[3 * N + i], w[4 * N + i], w[5 * N + i]);
+}
+template <class C, bool ROT>
+__global__ void k_ham_gradient(const __grid_constant__ DevPot P, const __grid_constant__ DevFrame F,
+                               const double* __restrict__ w, double t, size_t N, double* __restrict__ f) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double ww[6], ff[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) ww[k] = w[k * N + i];
+    ham_rhs<C, ROT>(P, F, t, ww, ff);
+#pragma unroll
+    for (int k = 0; k < 6; k++) f[k * N + i] = ff[k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Leapfrog (leapfrog_integrate_hamiltonian, integrate/cyintegrators/leapfrog.pyx:54-121;
+// c_init_velocity :24-32; c_leapfrog_step :35-51).  Stored state at step j is (x, v) with the
+// synchronised velocity; the half-step velocity v12 is carried in registers.
+// Trajectory rows are written with streaming stores: each warp store is 256 contiguous bytes of
+// out[k][j][i0..i0+31], never re-read by the kernel, so it should not occupy L2.
+// ------------------------------------------------------------------------------------------------
+template <class C, bool SAVE>
+__global__ void __launch_bounds__(256)
+k_leapfrog(const __grid_constant__ DevPot P, const double* __restrict__ w0, size_t N,
+           const double* __restrict__ t, int ntimes, double dt, double* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double x = w0[i], y = w0[N + i], z = w0[2 * N + i];
+    double vx = w0[3 * N + i], vy = w0[4 * N + i], vz = w0[5 * N + i];
+    const size_t TS = (size_t)ntimes * N;  // stride between phase-space components when SAVE
+    if (SAVE) {
+        __stcs(out + i, x); __stcs(out + TS + i, y); __stcs(out + 2 * TS + i, z);
+        __stcs(out + 3 * TS + i, vx); __stcs(out + 4 * TS + i, vy); __stcs(out + 5 * TS + i, vz);
+    }
+    double gx, gy, gz;
+    C::gradient(P, t[0], x, y, z, gx, gy, gz);
+    double hx = vx - gx * dt / 2., hy = vy - gy * dt / 2., hz = vz - gz * dt / 2.;
+    for (int j = 1; j < ntimes; j++) {
+        x = x + hx * dt; y = y + hy * dt; z = z + hz * dt;
+        C::gradient(P, 0., x, y, z, gx, gy, gz);
+        vx = hx - gx * dt / 2.; vy = hy - gy * dt / 2.; vz = hz - gz * dt / 2.;
+        hx = hx - gx * dt; hy = hy - gy * dt; hz = hz - gz * dt;
+        if (SAVE) {
+            double* o = out + (size_t)j * N + i;
+            __stcs(o, x); __stcs(o + TS, y); __stcs(o + 2 * TS, z);
+            __stcs(o + 3 * TS, vx); __stcs(o + 4 * TS, vy); __stcs(o + 5 * TS, vz);
+        }
+    }
+    if (!SAVE) {
+        out[i] = x; out[N + i] = y; out[2 * N + i] = z;
+        out[3 * N + i] = vx; out[4 * N + i] = vy; out[5 * N + i] = vz;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ruth4 (ruth4_integrate_hamiltonian, integrate/cyintegrators/ruth4.pyx:37-113; step :24-35).
+// ROT=true reproduces the reference's Python Ruth4Integrator in a ConstantRotatingFrame
+// (integrate/pyintegrators/ruth4.py:106-124 with F = Hamiltonian._gradient,
+// hamiltonian/chamiltonian.pyx:88-99): only F[3:] = -(grad + Omega x p) is used.
+// Sub-stage 0 has d_0 = 0: its gradient is multiplied by zero in the reference, so it is not
+// evaluated here (3 gradient evaluations per step).
+// ------------------------------------------------------------------------------------------------
+struct Ruth4Coef { double c[4], d[4]; };
+
+template <class C, bool ROT, bool SAVE>
+__global__ void __launch_bounds__(256)
+k_ruth4(const __grid_constant__ DevPot P, const __grid_constant__ DevFrame F, const __grid_constant__ Ruth4Coef K,
+        const double* __restrict__ w0, size_t N, int ntimes, double dt, double* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double x = w0[i], y = w0[N + i], z = w0[2 * N + i];
+    double vx = w0[3 * N + i], vy = w0[4 * N + i], vz = w0[5 * N + i];
+    const size_t TS = (size_t)ntimes * N;
+    if (SAVE) {
+        __stcs(out + i, x); __stcs(out + TS + i, y); __stcs(out + 2 * TS + i, z);
+        __stcs(out + 3 * TS + i, vx); __stcs(out + 4 * TS + i, vy); __stcs(out + 5 * TS + i, vz);
+    }
+    for (int j = 1; j < ntimes; j++) {
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            if (s > 0) {
+                double gx, gy, gz;
+                C::gradient(P, 0., x, y, z, gx, gy, gz);
+                if (!ROT) {
+                    vx = vx - K.d[s] * gx * dt; vy = vy - K.d[s] * gy * dt; vz = vz - K.d[s] * gz * dt;
+                } else {
+                    const double Cx = F.om[1] * vz - F.om[2] * vy;
+                    const double Cy = -F.om[0] * vz + F.om[2] * vx;
+                    const double Cz = F.om[0] * vy - F.om[1] * vx;
+                    const double ax = -(gx + Cx), ay = -(gy + Cy), az = -(gz + Cz);
+                    vx = vx + K.d[s] * ax * dt; vy = vy + K.d[s] * ay * dt; vz = vz + K.d[s] * az * dt;
+                }
+            }
+            x = x + K.c[s] * vx * dt; y = y + K.c[s] * vy * dt; z = z + K.c[s] * vz * dt;
+        }
+        if (SAVE) {
+            double* o = out + (size_t)j * N + i;
+            __stcs(o, x); __stcs(o + TS, y); __stcs(o + 2 * TS, z);
+            __stcs(o + 3 * TS, vx); __stcs(o + 4 * TS, vy); __stcs(o + 5 * TS, vz);
+        }
+    }
+    if (!SAVE) {
+        out[i] = x; out[N + i] = y; out[2 * N + i] = z;
+        out[3 * N + i] = vx; out[4 * N + i] = vy; out[5 * N + i] = vz;
+    }
+}
+
+#endif  // GB_PART == 1
+
+// ------------------------------------------------------------------------------------------------
+// host launchers.  GB_PART splits this file into translation units that compile in parallel:
+//   1 = evaluation + leapfrog + ruth4, 2 = dop853 static frame, 3 = dop853 rotating frame,
+//   4 = mock-stream kernels.
+// ------------------------------------------------------------------------------------------------
+static inline unsigned nblocks(size_t N, int block) { return (unsigned)((N + block - 1) / block); }
+
+#define GB_SIG_SWITCH(sig, CALL)                                  \
+    switch (sig) {                                                \
+        case SIG_NFW:        { using C = Composite<SIG_NFW>;        CALL; } break; \
+        case SIG_HERNQUIST:  { using C = Composite<SIG_HERNQUIST>;  CALL; } break; \
+        case SIG_MW2022:     { using C = Composite<SIG_MW2022>;     CALL; } break; \
+        case SIG_BAR_MW2022: { using C = Composite<SIG_BAR_MW2022>; CALL; } break; \
+        case SIG_MW2022_BAR: { using C = Composite<SIG_MW2022_BAR>; CALL; } break; \
+        case SIG_SCF:        { using C = Composite<SIG_SCF>;        CALL; } break; \
+        default:             { using C = Composite<SIG_GENERIC>;    CALL; } break; \
+    }
+
+#if GB_PART == 1
+cudaError_t eval_gradient(const DevPot& P, const double* q, double t, size_t N, double* g, int block, cudaStream_t s) {
+    if (N == 0) return cudaSuccess;
+    GB_SIG_SWITCH(P.sig, (k_eval_gradient<C><<<nblocks(N, block), block, 0, s>>>(P, q, t, N, g)));
+    return cudaGetLastError();
+}
+cudaError_t eval_energy(const DevPot& P, const double* q, double t, size_t N, double* out, int block, cudaStream_t s) {
+    if (N == 0) return cudaSuccess;
+    GB_SIG_SWITCH(P.sig, (k_eval_scalar<C, 0><<<nblocks(N, block), block, 0, s>>>(P, q, t, N, out)));
+    return cudaGetLastError();
+}
+cudaError_t eval_density(const DevPot& P, const double* q, double t, size_t N, double* out, int block, cudaStream_t s) {
+    if (N == 0) return cudaSuccess;
+    GB_SIG_SWITCH(P.sig, (k_eval_scalar<C, 1><<<nblocks(N, block), block, 0, s>>>(P, q, t, N, out)));
+    return cudaGetLastError();
+}
+cudaError_t ham_energy(const DevPot& P, const DevFrame& F, const double* w, double t, size_t N, double* out,
+                       int block, cudaStream_t s) {
+    if (N == 0) return cudaSuccess;
+    GB_SIG_SWITCH(P.sig, (k_ham_energy<C><<<nblocks(N, block), block, 0, s>>>(P, F, w, t, N, out)));
+    return cudaGetLastError();
+}
+cudaError_t ham_gradient(const DevPot& P, const DevFrame& F, const double* w, double t, size_t N, double* f,
+                         int block, cudaStream_t s) {
+    if (N == 0) return cudaSuccess;
+    if (F.type == GB_FRAME_STATIC) {
+        GB_SIG_SWITCH(P.sig, (k_ham_gradient<C, false><<<nblocks(N, block), block, 0, s>>>(P, F, w, t, N, f)));
+    } else {
+        GB_SIG_SWITCH(P.sig, (k_ham_gradient<C, true><<<nblocks(N, block), block, 0, s>>>(P, F, w, t, N, f)));
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t leapfrog(const DevPot& P, const double* w0, size_t N, const double* t, int ntimes, double dt,
+                     int save_all, double* out, int block, cudaStream_t s) {
+    if (N == 0) return cudaSuccess;
+    if (save_all) {
+        GB_SIG_SWITCH(P.sig, (k_leapfrog<C, true><<<nblocks(N, block), block, 0, s>>>(P, w0, N, t, ntimes, dt, out)));
+    } else {
+        GB_SIG_SWITCH(P.sig, (k_leapfrog<C, false><<<nblocks(N, block), block, 0, s>>>(P, w0, N, t, ntimes, dt, out)));
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t ruth4(const DevPot& P, const DevFrame& F, const double* w0, size_t N, const double* t, int ntimes,
+                  double dt, const double* cs, const double* ds, int save_all, double* out, int block,
+                  cudaStream_t s) {
+    if (N == 0) return cudaSuccess;
+    Ruth4Coef K;
+    for (int k = 0; k < 4; k++) { K.c[k] = cs[k]; K.d[k] = ds[k]; }
+    const bool rot = F.type != GB_FRAME_STATIC;
+#define GB_R4(ROT, SAVE) GB_SIG_SWITCH(P.sig, (k_ruth4<C, ROT, SAVE><<<nblocks(N, block), block, 0, s>>>(P, F, K, w0, N, ntimes, dt, out)))
+    if (rot) { if (save_all) { GB_R4(true, true); } else { GB_R4(true, false); } }
+    else     { if (save_all) { GB_R4(false, true); } else { GB_R4(false, false); } }
+#undef GB_R4
+    return cudaGetLastError();
+}
+
+#endif  // GB_PART == 1
+
+#if GB_PART == 2 || GB_PART == 3
+#if GB_PART == 2
+#define GB_D8_NAME dop853_static
+#define GB_D8_ROT false
+#else
+#define GB_D8_NAME dop853_rotating
+#define GB_D8_ROT true
+#endif
+cudaError_t GB_D8_NAME(const DevPot& P, const DevFrame& F, const double* w0, size_t N, const double* t, int ntimes,
+                       const Dop853Args& a, int save_all, double* out, int32_t* status, int32_t* nstep,
+                       int32_t* naccpt, int32_t* nrejct, int32_t* nfcn, int block, cudaStream_t s) {
+    if (N == 0) return cudaSuccess;
+    Dop853Stats st{status, nstep, naccpt, nrejct, nfcn};
+#define GB_D8(DENSE) GB_SIG_SWITCH(P.sig, (k_dop853<C, GB_D8_ROT, DENSE><<<nblocks(N, block), block, 0, s>>>(P, F, a, w0, N, t, ntimes, out, st)))
+    if (save_all) { GB_D8(true); } else { GB_D8(false); }
+#undef GB_D8
+    return cudaGetLastError();
+}
+#endif  // GB_PART == 2 || 3
+
+#if GB_PART == 4
+cudaError_t mock_dop853(const DevPot& P, const DevFrame& F, const double* w0_rows, const double* t1, size_t Np,
+                        double tfinal, const Dop853Args& a, double* out_rows, int32_t* status, int block,
+                        cudaStream_t s) {
+    if (Np == 0) return cudaSuccess;
+    const bool rot = F.type != GB_FRAME_STATIC;
+    if (rot) {
+        GB_SIG_SWITCH(P.sig, (k_mock_dop853<C, true><<<nblocks(Np, block), block, 0, s>>>(P, F, a, w0_rows, t1, Np, tfinal, out_rows, status)));
+    } else {
+        GB_SIG_SWITCH(P.sig, (k_mock_dop853<C, false><<<nblocks(Np, block), block, 0, s>>>(P, F, a, w0_rows, t1, Np, tfinal, out_rows, status)));
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t mock_leapfrog(const DevPot& P, const double* w0_rows, const double* t1, size_t Np, double tfinal,
+                          double dt, double* out_rows, int block, cudaStream_t s) {
+    if (Np == 0) return cudaSuccess;
+    GB_SIG_SWITCH(P.sig, (k_mock_leapfrog<C><<<nblocks(Np, block), block, 0, s>>>(P, w0_rows, t1, Np, tfinal, dt, out_rows)));
+    return cudaGetLastError();
+}
+
+cudaError_t fardal_release(const DevPot& P, double G, const double* prog_w, const double* prog_t,
+                           const double* prog_m, int ntimes, const int32_t* prog_idx, const double* sign,
+                           const double* normals, size_t Np, int gala_modified, double* out_rows, int block,
+                           cudaStream_t s) {
+    if (Np == 0) return cudaSuccess;
+    GB_SIG_SWITCH(P.sig, (k_fardal_release<C><<<nblocks(Np, block), block, 0, s>>>(P, G, prog_w, prog_t, prog_m, ntimes, prog_idx, sign, normals, Np, gala_modified, out_rows)));
+    return cudaGetLastError();
+}
+
+#endif  // GB_PART == 4
+
+}  // namespace GB_NS

@@ -1,0 +1,55 @@
+// kernels.h -- host-callable launchers of the sm_100a kernels.  kernels.cu is compiled twice:
+//   -DGB_STRICT=0 (namespace gbk_fast):   default nvcc FP contraction, rsqrt-based x^-1.5
+//   -DGB_STRICT=1 -fmad=false (gbk_strict): reference operation order, IEEE div/sqrt, libm pow
+// capi.cu picks one per call from gb_launch.strict_math.
+#pragma once
+#include <cuda_runtime.h>
+#include "gb_device.cuh"
+
+struct Dop853Args {
+    double atol, rtol;
+    long nmax;        // already defaulted (0 -> 1e6)
+    long nstiff;      // already defaulted (0 -> 1000, <0 -> nmax+10)
+    double hmax;      // 0 -> |xend-x| per orbit
+    double uround;
+    double h0;        // initial step (t[1]-t[0]); 0 -> hinit
+};
+
+#define GB_DECLARE_KERNEL_API(NS)                                                                          \
+    namespace NS {                                                                                         \
+    cudaError_t eval_gradient(const DevPot& P, const double* q, double t, size_t N, double* g,            \
+                              int block, cudaStream_t s);                                                  \
+    cudaError_t eval_energy(const DevPot& P, const double* q, double t, size_t N, double* out,            \
+                            int block, cudaStream_t s);                                                    \
+    cudaError_t eval_density(const DevPot& P, const double* q, double t, size_t N, double* out,           \
+                             int block, cudaStream_t s);                                                   \
+    cudaError_t ham_energy(const DevPot& P, const DevFrame& F, const double* w, double t, size_t N,       \
+                           double* out, int block, cudaStream_t s);                                        \
+    cudaError_t ham_gradient(const DevPot& P, const DevFrame& F, const double* w, double t, size_t N,     \
+                             double* f, int block, cudaStream_t s);                                        \
+    cudaError_t leapfrog(const DevPot& P, const double* w0, size_t N, const double* t, int ntimes,        \
+                         double dt, int save_all, double* out, int block, cudaStream_t s);                 \
+    cudaError_t ruth4(const DevPot& P, const DevFrame& F, const double* w0, size_t N, const double* t,    \
+                      int ntimes, double dt, const double* cs, const double* ds, int save_all,             \
+                      double* out, int block, cudaStream_t s);                                             \
+    cudaError_t dop853_static(const DevPot& P, const DevFrame& F, const double* w0, size_t N,             \
+                              const double* t, int ntimes, const Dop853Args& a, int save_all, double* out, \
+                              int32_t* status, int32_t* nstep, int32_t* naccpt, int32_t* nrejct,           \
+                              int32_t* nfcn, int block, cudaStream_t s);                                   \
+    cudaError_t dop853_rotating(const DevPot& P, const DevFrame& F, const double* w0, size_t N,           \
+                                const double* t, int ntimes, const Dop853Args& a, int save_all,            \
+                                double* out, int32_t* status, int32_t* nstep, int32_t* naccpt,             \
+                                int32_t* nrejct, int32_t* nfcn, int block, cudaStream_t s);                \
+    cudaError_t mock_dop853(const DevPot& P, const DevFrame& F, const double* w0_rows, const double* t1,  \
+                            size_t Np, double tfinal, const Dop853Args& a, double* out_rows,               \
+                            int32_t* status, int block, cudaStream_t s);                                   \
+    cudaError_t mock_leapfrog(const DevPot& P, const double* w0_rows, const double* t1, size_t Np,        \
+                              double tfinal, double dt, double* out_rows, int block, cudaStream_t s);      \
+    cudaError_t fardal_release(const DevPot& P, double G, const double* prog_w, const double* prog_t,     \
+                               const double* prog_m, int ntimes, const int32_t* prog_idx,                  \
+                               const double* sign, const double* normals, size_t Np, int gala_modified,   \
+                               double* out_rows, int block, cudaStream_t s);                               \
+    }
+
+GB_DECLARE_KERNEL_API(gbk_fast)
+GB_DECLARE_KERNEL_API(gbk_strict)

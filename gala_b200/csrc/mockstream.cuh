@@ -1,0 +1,130 @@
+// mockstream.cuh -- mock-stream kernels: particle release (Fardal+15 DF) and the batched
+// integration of all released particles to the final time, one particle per thread.
+//
+// Reference: dynamics/mockstream/df.pyx:61-106 (get_rj_vj_R, transform_from_sat), :363-456
+// (FardalStreamDF._sample), dynamics/mockstream/_coord.pyx:23-48, c_d2_dr2
+// (potential/potential/src/cpotential.cpp:346-371), mockstream_dop853 / mockstream_leapfrog
+// (dynamics/mockstream/mockstream.pyx:176-303, 442-620) for the case without massive bodies:
+// every stream particle is then an independent test particle, which is what makes the
+// one-thread-per-particle batch valid.  Rows are AoS (Np,6) as in the reference.
+#pragma once
+
+// One thread per stream particle.  normals row = [kx, z, vt, vz] drawn on the host in the
+// reference's RNG order; sign = +1 trailing / -1 leading (df.pyx:393-454).
+template <class C>
+__global__ void k_fardal_release(const __grid_constant__ DevPot P, double G, const double* __restrict__ prog_w,
+                                 const double* __restrict__ prog_t, const double* __restrict__ prog_m, int ntimes,
+                                 const int32_t* __restrict__ prog_idx, const double* __restrict__ sign,
+                                 const double* __restrict__ normals, size_t Np, int gala_modified,
+                                 double* __restrict__ out) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Np) return;
+    const int it = prog_idx[p];
+    const double* pw = prog_w + (size_t)it * 6;
+    const double px[3] = {pw[0], pw[1], pw[2]}, pv[3] = {pw[3], pw[4], pw[5]};
+    const double t = prog_t[it], m = prog_m[it];
+
+    // get_rj_vj_R (df.pyx:61-92)
+    double val = 0.;
+    val += px[0] * px[0]; val += px[1] * px[1]; val += px[2] * px[2];
+    const double dist = sqrt(val);
+    double L[3];
+    L[0] = px[1] * pv[2] - px[2] * pv[1];
+    L[1] = -px[0] * pv[2] + px[2] * pv[0];
+    L[2] = px[0] * pv[1] - px[1] * pv[0];
+    val = 0.;
+    val += L[0] * L[0]; val += L[1] * L[1]; val += L[2] * L[2];
+    const double Lnorm = sqrt(val);
+    double R[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { R[0][i] = px[i] / dist; R[2][i] = L[i] / Lnorm; }
+    const double Om = Lnorm / (dist * dist);
+    // c_d2_dr2 (cpotential.cpp:346-371), h = 1e-2
+    double d2r;
+    {
+        const double h = 1E-2;
+        double r2 = 0;
+        r2 = r2 + px[0] * px[0]; r2 = r2 + px[1] * px[1]; r2 = r2 + px[2] * px[2];
+        const double r = sqrt(r2);
+        double e[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) e[j] = px[j] + h * px[j] / r;
+        d2r = C::value(P, t, e[0], e[1], e[2]);
+        d2r = d2r - 2. * C::value(P, t, px[0], px[1], px[2]);
+#pragma unroll
+        for (int j = 0; j < 3; j++) e[j] = px[j] - h * px[j] / r;
+        d2r = d2r + C::value(P, t, e[0], e[1], e[2]);
+        d2r = d2r / (h * h);
+    }
+    const double rj = pow(G * m / (Om * Om - d2r), 1 / 3.);
+    const double vj = Om * rj;
+    // R[1] = -(R[0] x R[2])
+    R[1][0] = -(R[0][1] * R[2][2] - R[0][2] * R[2][1]);
+    R[1][1] = -(-R[0][0] * R[2][2] + R[0][2] * R[2][0]);
+    R[1][2] = -(R[0][0] * R[2][1] - R[0][1] * R[2][0]);
+
+    // FardalStreamDF._sample body (df.pyx:405-454)
+    const double sg = sign[p];
+    const double srj = (sg < 0) ? -rj : rj, svj = (sg < 0) ? -vj : vj;
+    const double* nr = normals + p * 4;
+    const double kx = nr[0];
+    double tx[3] = {kx * srj, 0., nr[1] * srj};
+    double tv[3] = {0., nr[2] * svj, nr[3] * svj};
+    if (gala_modified) tv[1] *= kx;
+    // transform_from_sat (df.pyx:94-106): R^T . x + prog
+    double* o = out + p * 6;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        double ox = R[0][i] * tx[0] + R[1][i] * tx[1] + R[2][i] * tx[2];
+        double ov = R[0][i] * tv[0] + R[1][i] * tv[1] + R[2][i] * tv[2];
+        ox += px[i]; ov += pv[i];
+        o[i] = ox; o[3 + i] = ov;
+    }
+}
+
+// mockstream_dop853 without massive bodies (mockstream.pyx:259-283): particle p integrates from
+// t1[p] to tfinal with dop853_step's settings (dop853.pyx:27-75; set by the host in `a`).
+template <class C, bool ROT>
+__global__ void __launch_bounds__(128)
+k_mock_dop853(const __grid_constant__ DevPot P, const __grid_constant__ DevFrame F,
+              const __grid_constant__ Dop853Args a, const double* __restrict__ w0, const double* __restrict__ t1,
+              size_t Np, double tfinal, double* __restrict__ out, int32_t* __restrict__ status) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Np) return;
+    double y[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) y[k] = w0[p * 6 + k];
+    auto rhs = [&](double tt, const double (&w)[6], double (&f)[6]) { ham_rhs<C, ROT>(P, F, tt, w, f); };
+    auto emit = [&](int, const double (&)[6]) {};
+    int out_idx = 0, nstep, naccpt, nrejct, nfcn;
+    const int code = dop853_integrate<false>(rhs, emit, a, t1[p], tfinal, y, a.h0, nullptr, 0, out_idx, nstep,
+                                             naccpt, nrejct, nfcn);
+#pragma unroll
+    for (int k = 0; k < 6; k++) out[p * 6 + k] = y[k];
+    if (status) status[p] = code;
+}
+
+// mockstream_leapfrog without massive bodies (mockstream.pyx:556-590 with c_init_velocity_nbody /
+// c_leapfrog_step_nbody, integrate/cyintegrators/leapfrog.pyx:126-158).
+template <class C>
+__global__ void __launch_bounds__(256)
+k_mock_leapfrog(const __grid_constant__ DevPot P, const double* __restrict__ w0, const double* __restrict__ t1,
+                size_t Np, double tfinal, double dt, double* __restrict__ out) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Np) return;
+    double x = w0[p * 6], y = w0[p * 6 + 1], z = w0[p * 6 + 2];
+    double vx = w0[p * 6 + 3], vy = w0[p * 6 + 4], vz = w0[p * 6 + 5];
+    const double ts = t1[p];
+    const int n_steps = (int)((tfinal - ts) / dt + 0.5);
+    double gx, gy, gz;
+    C::gradient(P, ts, x, y, z, gx, gy, gz);
+    double hx = vx - gx * dt / 2., hy = vy - gy * dt / 2., hz = vz - gz * dt / 2.;
+    for (int j = 0; j < n_steps; j++) {
+        x = x + hx * dt; y = y + hy * dt; z = z + hz * dt;
+        C::gradient(P, ts + (j + 1) * dt, x, y, z, gx, gy, gz);
+        vx = hx - gx * dt / 2.; vy = hy - gy * dt / 2.; vz = hz - gz * dt / 2.;
+        hx = hx - gx * dt; hy = hy - gy * dt; hz = hz - gz * dt;
+    }
+    double* o = out + p * 6;
+    o[0] = x; o[1] = y; o[2] = z; o[3] = vx; o[4] = vy; o[5] = vz;
+}

@@ -1,0 +1,195 @@
+/*
+ * gala_b200.h -- C ABI of the B200 (sm_100a) orbit-integration engine.
+ *
+ * This is the drop-in boundary for ONE path of adrn/gala: many independent
+ * test-particle orbits advanced through an analytic potential.  Every entry
+ * point replaces one reference function (cited as path:line relative to the
+ * reference's src/gala/).  Plain pointers and sizes only; no torch types.
+ *
+ * Layouts are the reference's own:
+ *   w0      (6, N)          C-contiguous  (leapfrog.pyx:54-59)
+ *   w_out   (6, ntimes, N)  if save_all, else (6, N)   (leapfrog.pyx:92,118-121)
+ *   q       (3, N)          for gradient/energy/density (cpotential.pyx:144-162)
+ *   stream  (Np, 6)         AoS rows for mock streams  (mockstream.pyx:176-184)
+ *
+ * Pointer location: every data pointer may be a HOST pointer or a DEVICE
+ * pointer; gb_launch.mem says which (GB_MEM_HOST: the library stages through
+ * device memory itself, copies are part of the call; GB_MEM_DEVICE: pointers
+ * are device memory on the current CUDA device, no copies are made).
+ * The potential / frame specs are always host structs; they are copied to the
+ * device at call time and the library keeps no reference to them
+ * (cf. cpotential.pyx:60-92 where the wrapper owns the arrays).
+ *
+ * Return value: 0 on success, <0 on failure; gb_last_error() gives the text.
+ *   -1..-4   : DOP853 codes as in dopri/dop853.h:157-164 (worst over orbits)
+ *   -10      : CUDA runtime error          -11 : unsupported potential/frame
+ *   -12      : invalid argument (shape etc; the Python shim raises ValueError)
+ *   -13      : integrator does not support this frame (TypeError in the
+ *              reference: leapfrog.pyx:64-68, ruth4.pyx:49-52)
+ */
+#ifndef GALA_B200_H
+#define GALA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Potential component type ids.  One per *Wrapper class of the reference
+ * (potential/potential/builtin/cybuiltin.pyx:99-122); the parameter vector of
+ * each is exactly CPotentialWrapper._params = [G, c_only..., params...]
+ * (cpotential.pyx:281-316). */
+enum gb_pot_type {
+    GB_POT_NULL             = 0,  /* NullWrapper            cybuiltin.pyx:362  [G]                       */
+    GB_POT_HERNQUIST        = 1,  /* HernquistWrapper       :165  [G, m, c]                              */
+    GB_POT_NFW_SPHERICAL    = 2,  /* SphericalNFWWrapper    :292  [G, m, r_s, a, b, c] (a,b,c ignored)   */
+    GB_POT_NFW_FLATTENED    = 3,  /* FlattenedNFWWrapper    :303  [G, m, r_s, a, b, c] (c used)          */
+    GB_POT_NFW_TRIAXIAL     = 4,  /* TriaxialNFWWrapper     :313  [G, m, r_s, a, b, c]                   */
+    GB_POT_MIYAMOTONAGAI    = 5,  /* MiyamotoNagaiWrapper   :264  [G, m, a, b]                           */
+    GB_POT_MN3              = 6,  /* MN3ExponentialDiskWrapper :276 [G, m1,a1,b1, m2,a2,b2, m3,a3,b3, ...] */
+    GB_POT_LONGMURALIBAR    = 7,  /* LongMuraliBarWrapper   :347  [G, m, a, b, c, alpha]                 */
+    GB_POT_SCF              = 8,  /* SCFWrapper scf/bfe_class.pyx:38 [G, nmax, lmax, m, r_s, S.., T..]   */
+    GB_POT_KEPLER           = 9,  /* KeplerWrapper          :141  [G, m]                                 */
+    GB_POT_PLUMMER          = 10, /* PlummerWrapper         :177  [G, m, b]                              */
+    GB_POT_ISOCHRONE        = 11, /* IsochroneWrapper       :153  [G, m, b]                              */
+    GB_POT_JAFFE            = 12, /* JaffeWrapper           :189  [G, m, c]                              */
+    GB_POT_NTYPES
+};
+
+/* One component of a (composite) potential; mirrors struct _CPotential per
+ * index i (potential/potential/src/cpotential.h:10-36) with a type id in the
+ * place of the four host function pointers. */
+typedef struct {
+    int32_t type_id;          /* enum gb_pot_type                                   */
+    int32_t n_params;         /* length of params (n_params[i])                     */
+    int32_t do_shift_rotate;  /* do_shift_rotate[i]: 0 => q0 and R are ignored      */
+    int32_t _pad;
+    const double* params;     /* parameters[i]: [G, ...]                            */
+    double q0[3];             /* q0[i]: origin                                      */
+    double R[9];              /* R[i]: row-major 3x3 rotation                       */
+} gb_component;
+
+typedef struct {
+    int32_t n_components;     /* n_components                                       */
+    int32_t n_dim;            /* n_dim; only 3 is supported                         */
+    const gb_component* comp;
+} gb_potential;
+
+/* Reference frame; mirrors CFrameType (potential/frame/src/cframe.h:7-17). */
+enum gb_frame_type {
+    GB_FRAME_STATIC      = 0, /* StaticFrameWrapper            frame/builtin/frames.pyx:37-50   */
+    GB_FRAME_ROTATING_3D = 1  /* ConstantRotatingFrameWrapper3D frame/builtin/frames.pyx:90-106 */
+};
+typedef struct {
+    int32_t type_id;
+    int32_t _pad;
+    double omega[3];          /* frame.c_parameters for the rotating frame          */
+} gb_frame;
+
+enum gb_mem { GB_MEM_HOST = 0, GB_MEM_DEVICE = 1 };
+
+/* Launch options.  Zero-initialise for defaults. */
+typedef struct {
+    int32_t mem;              /* enum gb_mem for ALL data pointers of the call      */
+    int32_t device;           /* CUDA device ordinal, -1 = current                  */
+    void*   stream;           /* cudaStream_t to launch on, NULL = default stream   */
+    int32_t strict_math;      /* 1 = strict-IEEE kernels (reference operation order,
+                                 no FMA contraction, libm pow/log); 0 = fast kernels */
+    int32_t block_threads;    /* 0 = library default                                */
+} gb_launch;
+
+/* Per-orbit DOP853 statistics (dopcor's nstep/naccpt/nrejct/nfcn,
+ * dopri/dop853.cpp:115-118); each pointer may be NULL. */
+typedef struct {
+    int32_t* nstep;
+    int32_t* naccpt;
+    int32_t* nrejct;
+    int32_t* nfcn;
+} gb_dop853_stats;
+
+/* ---- potential evaluation (cpotential.cpp:170-287; cpotential.pyx:104-162) ---- */
+int gb_gradient(const gb_potential* pot, const double* q, double t, size_t N,
+                double* grad /* (3,N) */, const gb_launch* opt);
+int gb_energy  (const gb_potential* pot, const double* q, double t, size_t N,
+                double* out /* (N) */, const gb_launch* opt);
+int gb_density (const gb_potential* pot, const double* q, double t, size_t N,
+                double* out /* (N) */, const gb_launch* opt);
+/* Hamiltonian.energy: potential + frame energy, w is (6,N)
+ * (hamiltonian/src/chamiltonian.cpp:7-19; frame/builtin/builtin_frames.cpp:8-16,73-92) */
+int gb_hamiltonian_energy(const gb_potential* pot, const gb_frame* fr, const double* w,
+                          double t, size_t N, double* out /* (N) */, const gb_launch* opt);
+/* Hamiltonian gradient f = [dH/dp ; -dH/dq] for (6,N)
+ * (hamiltonian/src/chamiltonian.cpp:38-57) */
+int gb_hamiltonian_gradient(const gb_potential* pot, const gb_frame* fr, const double* w,
+                            double t, size_t N, double* f /* (6,N) */, const gb_launch* opt);
+
+/* ---- fixed-step integrators ---------------------------------------------------
+ * leapfrog_integrate_hamiltonian (integrate/cyintegrators/leapfrog.pyx:54-121)
+ * ruth4_integrate_hamiltonian    (integrate/cyintegrators/ruth4.pyx:37-113)
+ * dt = t[1]-t[0]; step j uses time t[j].  save_all=1: w_out is (6,ntimes,N) with
+ * w_out[:,0,:]=w0; save_all=0: w_out is (6,N), the state at t[ntimes-1].
+ * gb_leapfrog requires a static frame (-13 otherwise).  gb_ruth4 accepts the
+ * rotating frame with the semantics of the reference's Python Ruth4Integrator
+ * driven by Hamiltonian._gradient (integrate/pyintegrators/ruth4.py:106-124,
+ * hamiltonian/chamiltonian.pyx:88-99): p += d_j*(-Omega x p - grad)*dt; q += c_j*p*dt. */
+int gb_leapfrog(const gb_potential* pot, const gb_frame* fr, const double* w0, size_t N,
+                const double* t, int ntimes, int save_all, double* w_out,
+                const gb_launch* opt);
+int gb_ruth4   (const gb_potential* pot, const gb_frame* fr, const double* w0, size_t N,
+                const double* t, int ntimes, int save_all, double* w_out,
+                const gb_launch* opt);
+
+/* ---- adaptive DOP853 -----------------------------------------------------------
+ * dop853_integrate_hamiltonian (integrate/cyintegrators/dop853.pyx:196-250) with
+ * per-orbit step control (the reference's nbatch=1).  Dense output
+ * onto t[] when save_all=1 (dopri/dop853.cpp:584-612,869-904).
+ * status: per-orbit dop853 return code (1 ok, -2 nmax, -3 step too small, -4 stiff),
+ * may be NULL.  The function returns the most negative per-orbit code, or 0. */
+int gb_dop853(const gb_potential* pot, const gb_frame* fr, const double* w0, size_t N,
+              const double* t, int ntimes, double atol, double rtol, long nmax,
+              double dt_max, long nstiff, int save_all, double* w_out,
+              int32_t* status, const gb_dop853_stats* stats, const gb_launch* opt);
+
+/* ---- mock streams ----------------------------------------------------------------
+ * Particle release: FardalStreamDF._sample + BaseStreamDF.get_rj_vj_R +
+ * transform_from_sat (dynamics/mockstream/df.pyx:61-106,363-456).  The normal
+ * deviates are drawn on the host (numpy RNG, reference order) and passed in:
+ * normals is (Np,4) rows [kx, z, vt, vz] already scaled to N(mean,disp).
+ * prog_idx[p] = progenitor timestep of particle p; sign[p] = +1 trailing, -1 leading. */
+int gb_fardal_release(const gb_potential* pot, double G,
+                      const double* prog_w /* (ntimes,6) */, const double* prog_t,
+                      const double* prog_m, int ntimes,
+                      const int32_t* prog_idx, const double* sign, const double* normals,
+                      size_t Np, int gala_modified,
+                      double* stream_w0 /* (Np,6) */, const gb_launch* opt);
+
+/* mockstream_dop853 (dynamics/mockstream/mockstream.pyx:176-303), no massive
+ * bodies: every stream particle p is integrated from t1[p] to tfinal as its own
+ * n=6 DOP853 system with dop853_step's settings (dop853.pyx:27-75: uround default,
+ * initial step dt0, stiffness test after every accepted step). */
+int gb_mockstream_dop853(const gb_potential* pot, const gb_frame* fr,
+                         const double* stream_w0 /* (Np,6) */, const double* t1 /* (Np) */,
+                         size_t Np, double tfinal, double dt0,
+                         double atol, double rtol, long nmax,
+                         double* stream_w /* (Np,6) */, int32_t* status,
+                         const gb_launch* opt);
+/* mockstream_leapfrog (mockstream.pyx:442-620), no massive bodies: particle p takes
+ * n_steps = (int)((tfinal-t1[p])/dt+0.5) leapfrog steps of size dt. */
+int gb_mockstream_leapfrog(const gb_potential* pot,
+                           const double* stream_w0, const double* t1, size_t Np,
+                           double tfinal, double dt,
+                           double* stream_w, const gb_launch* opt);
+
+/* ---- misc ------------------------------------------------------------------------ */
+const char* gb_last_error(void);
+int  gb_device_count(void);
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+long gb_launch_count(void);
+const char* gb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GALA_B200_H */

@@ -1,0 +1,370 @@
+// oracle/ref_driver.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT.
+//
+// C-ABI driver that links the reference's OWN C++ objects (compiled in place from
+// /root/reference/src/gala by oracle/Makefile into oracle/_ref/) and restates only the
+// Cython time loops that cannot be imported here (they import astropy at module load).
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+// legs may load the resulting library.
+//
+// Each function cites the reference lines it follows (paths relative to src/gala/).
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "potential/src/cpotential.h"
+#include "potential/builtin/builtin_potentials.h"
+#include "frame/src/cframe.h"
+#include "frame/builtin/builtin_frames.h"
+#include "hamiltonian/src/chamiltonian.h"
+#include "dopri/dop853.h"
+#if GB_REF_HAVE_SCF
+#include "scf/src/bfe.h"
+#endif
+
+#include "gala_b200.h"
+
+extern void Fwrapper_T(unsigned full_ndim, double t, double *w, double *f, CPotential *p,
+                       CFrameType *fr, unsigned norbits, unsigned na, void *args);
+extern void Fwrapper_direct_nbody(unsigned full_ndim, double t, double *w, double *f,
+                                  CPotential *p, CFrameType *fr, unsigned norbits,
+                                  unsigned nbody, void *args);
+
+namespace {
+
+// Owns a CPotential built from a gb_potential spec.  Follows CPotentialWrapper.init
+// (potential/potential/cpotential.pyx:57-102) and the *Wrapper.__init__ bodies
+// (potential/potential/builtin/cybuiltin.pyx:126-376): one function-pointer set per type.
+struct RefPotential {
+    CPotential *cp = nullptr;
+    std::vector<std::vector<double>> pars, q0, R;
+    ~RefPotential() { if (cp) free_cpotential(cp); }
+};
+
+#if GB_REF_HAVE_SCF
+// scf_value / scf_density take 4 arguments in the reference (scf/src/bfe.h); the Cython
+// wrapper casts them to energyfunc (scf/bfe_class.pyx).  Adapt explicitly here.
+double scf_value5(double t, double *pars, double *q, int n_dim, void *) { return scf_value(t, pars, q, n_dim); }
+double scf_density5(double t, double *pars, double *q, int n_dim, void *) { return scf_density(t, pars, q, n_dim); }
+#endif
+
+bool fill_component(CPotential *cp, int i, int type_id) {
+    switch (type_id) {
+    case GB_POT_NULL:
+        cp->value[i] = null_value; cp->density[i] = null_density;
+        cp->gradient[i] = null_gradient; cp->hessian[i] = null_hessian; return true;
+    case GB_POT_HERNQUIST:
+        cp->value[i] = hernquist_value; cp->density[i] = hernquist_density;
+        cp->gradient[i] = hernquist_gradient; cp->hessian[i] = hernquist_hessian; return true;
+    case GB_POT_NFW_SPHERICAL:
+        cp->value[i] = sphericalnfw_value; cp->density[i] = sphericalnfw_density;
+        cp->gradient[i] = sphericalnfw_gradient; cp->hessian[i] = sphericalnfw_hessian; return true;
+    case GB_POT_NFW_FLATTENED:   // FlattenedNFWWrapper has no density (cybuiltin.pyx:303-311 uses nan_density)
+        cp->value[i] = flattenednfw_value; cp->density[i] = nan_density;
+        cp->gradient[i] = flattenednfw_gradient; cp->hessian[i] = flattenednfw_hessian; return true;
+    case GB_POT_NFW_TRIAXIAL:
+        cp->value[i] = triaxialnfw_value; cp->density[i] = nan_density;
+        cp->gradient[i] = triaxialnfw_gradient; cp->hessian[i] = triaxialnfw_hessian; return true;
+    case GB_POT_MIYAMOTONAGAI:
+        cp->value[i] = miyamotonagai_value; cp->density[i] = miyamotonagai_density;
+        cp->gradient[i] = miyamotonagai_gradient; cp->hessian[i] = miyamotonagai_hessian; return true;
+    case GB_POT_MN3:
+        cp->value[i] = mn3_value; cp->density[i] = mn3_density;
+        cp->gradient[i] = mn3_gradient; cp->hessian[i] = mn3_hessian; return true;
+    case GB_POT_LONGMURALIBAR:
+        cp->value[i] = longmuralibar_value; cp->density[i] = longmuralibar_density;
+        cp->gradient[i] = longmuralibar_gradient; cp->hessian[i] = longmuralibar_hessian; return true;
+    case GB_POT_KEPLER:
+        cp->value[i] = kepler_value; cp->density[i] = kepler_density;
+        cp->gradient[i] = kepler_gradient; cp->hessian[i] = kepler_hessian; return true;
+    case GB_POT_PLUMMER:
+        cp->value[i] = plummer_value; cp->density[i] = plummer_density;
+        cp->gradient[i] = plummer_gradient; cp->hessian[i] = plummer_hessian; return true;
+    case GB_POT_ISOCHRONE:
+        cp->value[i] = isochrone_value; cp->density[i] = isochrone_density;
+        cp->gradient[i] = isochrone_gradient; cp->hessian[i] = isochrone_hessian; return true;
+    case GB_POT_JAFFE:
+        cp->value[i] = jaffe_value; cp->density[i] = jaffe_density;
+        cp->gradient[i] = jaffe_gradient; cp->hessian[i] = jaffe_hessian; return true;
+#if GB_REF_HAVE_SCF
+    case GB_POT_SCF:
+        cp->value[i] = scf_value5; cp->density[i] = scf_density5;
+        cp->gradient[i] = scf_gradient; cp->hessian[i] = null_hessian; return true;
+#endif
+    default: return false;
+    }
+}
+
+bool build(const gb_potential *spec, RefPotential &out) {
+    int nc = spec->n_components;
+    out.cp = allocate_cpotential(nc);
+    out.cp->n_dim = spec->n_dim;
+    out.pars.resize(nc); out.q0.resize(nc); out.R.resize(nc);
+    int all_null = 1;
+    for (int i = 0; i < nc; i++) {
+        const gb_component &c = spec->comp[i];
+        if (!fill_component(out.cp, i, c.type_id)) return false;
+        if (c.type_id != GB_POT_NULL) all_null = 0;
+        out.pars[i].assign(c.params, c.params + c.n_params);
+        if (out.pars[i].empty()) out.pars[i].push_back(0.);
+        out.q0[i].assign(c.q0, c.q0 + 3);
+        out.R[i].assign(c.R, c.R + 9);
+        out.cp->n_params[i] = c.n_params;
+        out.cp->parameters[i] = out.pars[i].data();
+        out.cp->q0[i] = out.q0[i].data();
+        out.cp->R[i] = out.R[i].data();
+        out.cp->state[i] = NULL;
+        out.cp->do_shift_rotate[i] = c.do_shift_rotate;
+    }
+    out.cp->null = all_null;
+    return true;
+}
+
+// Frame wrappers: potential/frame/builtin/frames.pyx:37-50 (static), :90-106 (rotating 3D).
+struct RefFrame {
+    CFrameType cf;
+    double omega[3];
+};
+void build_frame(const gb_frame *fr, RefFrame &out) {
+    memset(&out.cf, 0, sizeof(out.cf));
+    if (!fr || fr->type_id == GB_FRAME_STATIC) {
+        out.cf.energy = (energyfunc)static_frame_hamiltonian;
+        out.cf.gradient = (gradientfunc)static_frame_gradient;
+        out.cf.hessian = (hessianfunc)static_frame_hessian;
+        out.cf.n_params = 0;
+        out.cf.parameters = NULL;
+    } else {
+        for (int k = 0; k < 3; k++) out.omega[k] = fr->omega[k];
+        out.cf.energy = (energyfunc)constant_rotating_frame_3d_hamiltonian;
+        out.cf.gradient = (gradientfunc)constant_rotating_frame_3d_gradient;
+        out.cf.hessian = (hessianfunc)constant_rotating_frame_3d_hessian;
+        out.cf.n_params = 3;
+        out.cf.parameters = out.omega;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// CPotentialWrapper.gradient (cpotential.pyx:144-162): one c_gradient(N) call.
+int ref_gradient(const gb_potential *spec, const double *q, double t, size_t N, double *grad) {
+    RefPotential rp; if (!build(spec, rp)) return -11;
+    c_gradient(rp.cp, N, t, const_cast<double *>(q), grad);
+    return 0;
+}
+
+// CPotentialWrapper.energy / density (cpotential.pyx:104-142): per-point c_potential /
+// c_density on an AoS copy of each point.  q here is (3,N) like everywhere else in the ABI.
+int ref_energy(const gb_potential *spec, const double *q, double t, size_t N, double *out) {
+    RefPotential rp; if (!build(spec, rp)) return -11;
+    for (size_t i = 0; i < N; i++) {
+        double p[3] = {q[i], q[N + i], q[2 * N + i]};
+        out[i] = c_potential(rp.cp, t, p);
+    }
+    return 0;
+}
+int ref_density(const gb_potential *spec, const double *q, double t, size_t N, double *out) {
+    RefPotential rp; if (!build(spec, rp)) return -11;
+    for (size_t i = 0; i < N; i++) {
+        double p[3] = {q[i], q[N + i], q[2 * N + i]};
+        out[i] = c_density(rp.cp, t, p);
+    }
+    return 0;
+}
+
+// Hamiltonian.energy (hamiltonian/chamiltonian.pyx:107-128): potential energy via
+// c_potential + frame energy (frame_hamiltonian), per point.
+int ref_hamiltonian_energy(const gb_potential *spec, const gb_frame *fr, const double *w, double t,
+                           size_t N, double *out) {
+    RefPotential rp; if (!build(spec, rp)) return -11;
+    RefFrame rf; build_frame(fr, rf);
+    for (size_t i = 0; i < N; i++) {
+        double p[6];
+        for (int k = 0; k < 6; k++) p[k] = w[k * N + i];
+        out[i] = c_potential(rp.cp, t, p) + frame_hamiltonian(&rf.cf, t, p, 3);
+    }
+    return 0;
+}
+
+int ref_hamiltonian_gradient(const gb_potential *spec, const gb_frame *fr, const double *w, double t,
+                             size_t N, double *f) {
+    RefPotential rp; if (!build(spec, rp)) return -11;
+    RefFrame rf; build_frame(fr, rf);
+    hamiltonian_gradient_T(rp.cp, &rf.cf, N, t, const_cast<double *>(w), f);
+    return 0;
+}
+
+// leapfrog_integrate_hamiltonian (integrate/cyintegrators/leapfrog.pyx:54-121) with
+// c_init_velocity (:24-32) and c_leapfrog_step (:35-51).
+int ref_leapfrog(const gb_potential *spec, const double *w0, size_t N, const double *t, int ntimes,
+                 int save_all, double *w_out) {
+    RefPotential rp; if (!build(spec, rp)) return -11;
+    const size_t n = N;
+    const double dt = t[1] - t[0];
+    std::vector<double> tmp_w(w0, w0 + 6 * n), v12(3 * n, 0.), grad(3 * n, 0.);
+    double *x = tmp_w.data(), *v = tmp_w.data() + 3 * n;
+    if (save_all)
+        for (int k = 0; k < 6; k++) memcpy(w_out + (size_t)k * ntimes * n, w0 + k * n, n * sizeof(double));
+
+    c_gradient(rp.cp, n, t[0], x, grad.data());
+    for (int k = 0; k < 3; k++)
+        for (size_t i = 0; i < n; i++) v12[i + k * n] = v[i + k * n] - grad[i + k * n] * dt / 2.;
+
+    for (int j = 1; j < ntimes; j++) {
+        for (int k = 0; k < 3; k++)
+            for (size_t i = 0; i < n; i++) x[i + k * n] = x[i + k * n] + v12[i + k * n] * dt;
+        c_gradient(rp.cp, n, t[j], x, grad.data());
+        for (int k = 0; k < 3; k++)
+            for (size_t i = 0; i < n; i++) {
+                v[i + k * n] = v12[i + k * n] - grad[i + k * n] * dt / 2.;
+                v12[i + k * n] = v12[i + k * n] - grad[i + k * n] * dt;
+            }
+        if (save_all)
+            for (int k = 0; k < 6; k++)
+                memcpy(w_out + ((size_t)k * ntimes + j) * n, tmp_w.data() + k * n, n * sizeof(double));
+    }
+    if (!save_all) memcpy(w_out, tmp_w.data(), 6 * n * sizeof(double));
+    return 0;
+}
+
+// Ruth4 coefficients: integrate/cyintegrators/ruth4.pyx:65-78.
+static void ruth4_coeffs(double *cs, double *ds) {
+    const double two_13 = pow(2., 1. / 3.);
+    cs[0] = 1. / (2. * (2. - two_13));
+    cs[1] = (1. - two_13) / (2. * (2. - two_13));
+    cs[2] = (1. - two_13) / (2. * (2. - two_13));
+    cs[3] = 1. / (2. * (2. - two_13));
+    ds[0] = 0.;
+    ds[1] = 1. / (2. - two_13);
+    ds[2] = -two_13 / (2. - two_13);
+    ds[3] = 1. / (2. - two_13);
+}
+
+// ruth4_integrate_hamiltonian (integrate/cyintegrators/ruth4.pyx:37-113, step :24-35) for the
+// static frame.  For the rotating frame the reference only runs through the Python
+// Ruth4Integrator (integrate/pyintegrators/ruth4.py:106-124) with
+// F = Hamiltonian._gradient (hamiltonian/chamiltonian.pyx:88-99), i.e. F = hamiltonian_gradient_T;
+// the integrator uses only a = F[3:]:  p += d_j*a*dt ; q += c_j*p*dt.
+int ref_ruth4(const gb_potential *spec, const gb_frame *fr, const double *w0, size_t N, const double *t,
+              int ntimes, int save_all, double *w_out) {
+    RefPotential rp; if (!build(spec, rp)) return -11;
+    RefFrame rf; build_frame(fr, rf);
+    const bool rotating = fr && fr->type_id == GB_FRAME_ROTATING_3D;
+    const size_t n = N;
+    const double dt = t[1] - t[0];
+    double cs[4], ds[4];
+    ruth4_coeffs(cs, ds);
+    std::vector<double> w(w0, w0 + 6 * n), grad(3 * n, 0.), F(6 * n, 0.);
+    if (save_all)
+        for (int k = 0; k < 6; k++) memcpy(w_out + (size_t)k * ntimes * n, w0 + k * n, n * sizeof(double));
+    for (int j = 1; j < ntimes; j++) {
+        for (int s = 0; s < 4; s++) {
+            if (!rotating) {
+                c_gradient(rp.cp, n, t[j], w.data(), grad.data());
+                for (int k = 0; k < 3; k++)
+                    for (size_t i = 0; i < n; i++) {
+                        w[(3 + k) * n + i] = w[(3 + k) * n + i] - ds[s] * grad[k * n + i] * dt;
+                        w[k * n + i] = w[k * n + i] + cs[s] * w[(3 + k) * n + i] * dt;
+                    }
+            } else {
+                // pyintegrators/ruth4.py:110-122: a_i = F(t, w)[ndim:]; p = p + d*a_i*dt; q = q + c*p*dt
+                // step() is called with times[ii] (ruth4.py:141), the same t[j] the Cython loop uses.
+                hamiltonian_gradient_T(rp.cp, &rf.cf, n, t[j], w.data(), F.data());
+                for (int k = 0; k < 3; k++)
+                    for (size_t i = 0; i < n; i++) {
+                        w[(3 + k) * n + i] = w[(3 + k) * n + i] + ds[s] * F[(3 + k) * n + i] * dt;
+                        w[k * n + i] = w[k * n + i] + cs[s] * w[(3 + k) * n + i] * dt;
+                    }
+            }
+        }
+        if (save_all)
+            for (int k = 0; k < 6; k++)
+                memcpy(w_out + ((size_t)k * ntimes + j) * n, w.data() + k * n, n * sizeof(double));
+    }
+    if (!save_all) memcpy(w_out, w.data(), 6 * n * sizeof(double));
+    return 0;
+}
+
+// dop853_integrate_hamiltonian (integrate/cyintegrators/dop853.pyx:196-250) calling
+// dop853_helper (:90-193) per batch of `nbatch` orbits.  status[i] = dop853 return code of the
+// batch orbit i belongs to.  Returns the most negative code, or 0.
+int ref_dop853(const gb_potential *spec, const gb_frame *fr, const double *w0, size_t N, const double *t,
+               int ntimes, double atol, double rtol, long nmax, double dt_max, long nstiff, int save_all,
+               int nbatch, double *w_out, int32_t *status) {
+    RefPotential rp; if (!build(spec, rp)) return -11;
+    RefFrame rf; build_frame(fr, rf);
+    if (ntimes < 1) return -12;
+    int worst = 0;
+    for (size_t i0 = 0; i0 < N; i0 += nbatch) {
+        size_t nb = (i0 + nbatch <= N) ? nbatch : N - i0;
+        unsigned size = 6 * nb;
+        std::vector<double> w(size), out((size_t)ntimes * size);
+        for (int k = 0; k < 6; k++)
+            for (size_t i = 0; i < nb; i++) w[k * nb + i] = w0[k * N + i0 + i];
+        Dop853DenseState *state = save_all ? dop853_dense_state_alloc(size, size) : NULL;
+        double rt = rtol, at = atol;
+        int res = dop853(size, (FcnEqDiff)Fwrapper_T, rp.cp, &rf.cf, nb, 0, NULL, t[0], w.data(),
+                         t[ntimes - 1], &rt, &at, 0, NULL, 0, NULL,
+                         2.220446049250313e-16,  // np.finfo(float).eps (dop853.pyx:165)
+                         0.0, 0.0, 0.0, 0.0, dt_max, t[1] - t[0], nmax, 1, nstiff,
+                         save_all ? size : 0, NULL, 0, state, const_cast<double *>(t), ntimes,
+                         save_all ? out.data() : NULL);
+        if (state) dop853_dense_state_free(state, size);
+        if (res < worst) worst = res;
+        for (size_t i = 0; i < nb; i++) if (status) status[i0 + i] = res;
+        if (save_all) {
+            // wres[:, :, i:j] = wbatchout.transpose(1,0,2)   (dop853.pyx:242-243)
+            for (int j = 0; j < ntimes; j++)
+                for (int k = 0; k < 6; k++)
+                    for (size_t i = 0; i < nb; i++)
+                        w_out[((size_t)k * ntimes + j) * N + i0 + i] = out[(size_t)j * size + k * nb + i];
+        } else {
+            for (int k = 0; k < 6; k++)
+                for (size_t i = 0; i < nb; i++) w_out[k * N + i0 + i] = w[k * nb + i];
+        }
+    }
+    return worst;
+}
+
+// One (Np,6)-row-per-particle integration with dop853_step's settings
+// (integrate/cyintegrators/dop853.pyx:27-75): uround=0 (-> 2.3e-16), nstiff hard-coded 1,
+// no dense output, F = Fwrapper_direct_nbody with nbody=0 bodies carrying mass, i.e. the
+// no-self-gravity case of mockstream_dop853 (dynamics/mockstream/mockstream.pyx:259-283).
+// group=1 integrates each particle as its own n=6 system (the per-lane definition used by the
+// GPU engine); group=0 integrates ALL given particles as one coupled system of 6*Np.
+int ref_dop853_step_rows(const gb_potential *spec, const gb_frame *fr, double *w_rows, size_t Np, double t1,
+                         double t2, double dt0, double atol, double rtol, long nmax, int group,
+                         int32_t *status) {
+    RefPotential rp; if (!build(spec, rp)) return -11;
+    RefFrame rf; build_frame(fr, rf);
+    int worst = 0;
+    double rt = rtol, at = atol;
+    if (!group) {
+        int res = dop853(6 * Np, (FcnEqDiff)Fwrapper_direct_nbody, rp.cp, &rf.cf, Np, 0, NULL, t1, w_rows, t2,
+                         &rt, &at, 0, NULL, 0, NULL, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, dt0, nmax, 0, 1, 0, NULL, 0,
+                         NULL, NULL, 0, NULL);
+        for (size_t i = 0; i < Np; i++) if (status) status[i] = res;
+        return res < 0 ? res : 0;
+    }
+    for (size_t i = 0; i < Np; i++) {
+        int res = dop853(6, (FcnEqDiff)Fwrapper_direct_nbody, rp.cp, &rf.cf, 1, 0, NULL, t1, w_rows + 6 * i, t2,
+                         &rt, &at, 0, NULL, 0, NULL, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, dt0, nmax, 0, 1, 0, NULL, 0,
+                         NULL, NULL, 0, NULL);
+        if (status) status[i] = res;
+        if (res < worst) worst = res;
+    }
+    return worst;
+}
+
+// c_d2_dr2 (potential/potential/src/cpotential.cpp:346-371) exposed for the release tests.
+double ref_d2_dr2(const gb_potential *spec, double t, const double *q3) {
+    RefPotential rp; if (!build(spec, rp)) return NAN;
+    double eps[3], q[3] = {q3[0], q3[1], q3[2]};
+    return c_d2_dr2(rp.cp, t, q, eps);
+}
+
+const char *ref_build_flags(void) { return GB_REF_FLAGS; }
+
+}  // extern "C"
