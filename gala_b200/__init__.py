@@ -1,0 +1,19 @@
+"""gala_b200 -- B200-native (sm_100a) engine for gala's orbit-integration hot path.
+
+Mirrors the reference API for that path only: potentials with the ``CPotential`` parameter
+layout, ``StaticFrame`` / ``ConstantRotatingFrame``, ``Hamiltonian.integrate_orbit`` with
+Leapfrog / Ruth4 / DOPRI853, and ``MockStreamGenerator`` with ``FardalStreamDF``.
+All arithmetic runs in hand-written CUDA kernels behind the C ABI of ``include/gala_b200.h``.
+"""
+from . import _abi
+from .units import galactic, dimensionless, G_GALACTIC, KMS_TO_KPC_MYR
+from .potential import *          # noqa: F401,F403
+from .frame import StaticFrame, ConstantRotatingFrame
+from .dynamics import PhaseSpacePosition, Orbit, MockStream
+from .integrate import (parse_time_specification, LeapfrogIntegrator, Ruth4Integrator, DOPRI853Integrator,
+                        leapfrog_integrate_hamiltonian, ruth4_integrate_hamiltonian,
+                        dop853_integrate_hamiltonian)
+from .hamiltonian import Hamiltonian
+from .mockstream import FardalStreamDF, MockStreamGenerator, mockstream_dop853, mockstream_leapfrog
+
+__version__ = "0.1.0"

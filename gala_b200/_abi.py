@@ -1,0 +1,159 @@
+"""ctypes binding of the C ABI in ``include/gala_b200.h``.
+
+The shared library ``gala_b200/libgala_b200.so`` is built in-tree by
+``__graft_entry__.build()`` (``make -C gala_b200/csrc``).  There is no CPU
+fallback: if the library is missing, loading raises; if no CUDA device is
+present, every compute entry point returns -10 and the wrappers raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgala_b200.so")
+
+# enum gb_pot_type
+POT_NULL, POT_HERNQUIST, POT_NFW_SPHERICAL, POT_NFW_FLATTENED, POT_NFW_TRIAXIAL = 0, 1, 2, 3, 4
+POT_MIYAMOTONAGAI, POT_MN3, POT_LONGMURALIBAR, POT_SCF = 5, 6, 7, 8
+POT_KEPLER, POT_PLUMMER, POT_ISOCHRONE, POT_JAFFE = 9, 10, 11, 12
+FRAME_STATIC, FRAME_ROTATING_3D = 0, 1
+MEM_HOST, MEM_DEVICE = 0, 1
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+
+
+class gb_component(C.Structure):
+    _fields_ = [("type_id", C.c_int32), ("n_params", C.c_int32), ("do_shift_rotate", C.c_int32),
+                ("_pad", C.c_int32), ("params", c_double_p), ("q0", C.c_double * 3), ("R", C.c_double * 9)]
+
+
+class gb_potential(C.Structure):
+    _fields_ = [("n_components", C.c_int32), ("n_dim", C.c_int32), ("comp", C.POINTER(gb_component))]
+
+
+class gb_frame(C.Structure):
+    _fields_ = [("type_id", C.c_int32), ("_pad", C.c_int32), ("omega", C.c_double * 3)]
+
+
+class gb_launch(C.Structure):
+    _fields_ = [("mem", C.c_int32), ("device", C.c_int32), ("stream", C.c_void_p),
+                ("strict_math", C.c_int32), ("block_threads", C.c_int32)]
+
+
+class gb_dop853_stats(C.Structure):
+    _fields_ = [("nstep", c_int32_p), ("naccpt", c_int32_p), ("nrejct", c_int32_p), ("nfcn", c_int32_p)]
+
+
+P = C.POINTER
+# name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
+SIGNATURES = {
+    "gb_gradient": (C.c_int, [P(gb_potential), C.c_void_p, C.c_double, C.c_size_t, C.c_void_p, P(gb_launch)]),
+    "gb_energy": (C.c_int, [P(gb_potential), C.c_void_p, C.c_double, C.c_size_t, C.c_void_p, P(gb_launch)]),
+    "gb_density": (C.c_int, [P(gb_potential), C.c_void_p, C.c_double, C.c_size_t, C.c_void_p, P(gb_launch)]),
+    "gb_hamiltonian_energy": (C.c_int, [P(gb_potential), P(gb_frame), C.c_void_p, C.c_double, C.c_size_t,
+                                        C.c_void_p, P(gb_launch)]),
+    "gb_hamiltonian_gradient": (C.c_int, [P(gb_potential), P(gb_frame), C.c_void_p, C.c_double, C.c_size_t,
+                                          C.c_void_p, P(gb_launch)]),
+    "gb_leapfrog": (C.c_int, [P(gb_potential), P(gb_frame), C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
+                              C.c_int, C.c_void_p, P(gb_launch)]),
+    "gb_ruth4": (C.c_int, [P(gb_potential), P(gb_frame), C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
+                           C.c_int, C.c_void_p, P(gb_launch)]),
+    "gb_dop853": (C.c_int, [P(gb_potential), P(gb_frame), C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
+                            C.c_double, C.c_double, C.c_long, C.c_double, C.c_long, C.c_int, C.c_void_p,
+                            C.c_void_p, P(gb_dop853_stats), P(gb_launch)]),
+    "gb_fardal_release": (C.c_int, [P(gb_potential), C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
+                                    P(gb_launch)]),
+    "gb_mockstream_dop853": (C.c_int, [P(gb_potential), P(gb_frame), C.c_void_p, C.c_void_p, C.c_size_t,
+                                       C.c_double, C.c_double, C.c_double, C.c_double, C.c_long, C.c_void_p,
+                                       C.c_void_p, P(gb_launch)]),
+    "gb_mockstream_leapfrog": (C.c_int, [P(gb_potential), C.c_void_p, C.c_void_p, C.c_size_t, C.c_double,
+                                         C.c_double, C.c_void_p, P(gb_launch)]),
+    "gb_last_error": (C.c_char_p, []),
+    "gb_device_count": (C.c_int, []),
+    "gb_launch_count": (C.c_long, []),
+    "gb_version": (C.c_char_p, []),
+    "gb_fp64_peak_tflops": (C.c_double, [C.c_int]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the C-ABI library.  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C gala_b200/csrc`.  gala_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+class GalaB200Error(RuntimeError):
+    pass
+
+
+def check(rc: int):
+    """Map a C-ABI return code to the exception type the reference raises on that condition."""
+    if rc == 0:
+        return
+    msg = lib().gb_last_error().decode()
+    if rc == -12:
+        raise ValueError(msg)                      # dop853.pyx:143-152
+    if rc == -13:
+        raise TypeError(msg)                       # leapfrog.pyx:64-68, ruth4.pyx:49-52
+    if rc in (-1, -2, -3, -4):
+        raise RuntimeError(msg)                    # dop853.pyx:184-185
+    raise GalaB200Error(f"[{rc}] {msg}")
+
+
+def device_count() -> int:
+    return lib().gb_device_count()
+
+
+def launch_count() -> int:
+    return lib().gb_launch_count()
+
+
+def _is_torch_cuda(x) -> bool:
+    return type(x).__module__.startswith("torch") and getattr(x, "is_cuda", False)
+
+
+class Buf:
+    """A host (numpy) or device (torch.cuda tensor) float64/int32 buffer seen as a raw pointer."""
+
+    def __init__(self, arr):
+        self.arr = arr
+        self.device = _is_torch_cuda(arr)
+        if self.device:
+            if not arr.is_contiguous():
+                raise ValueError("device tensors must be contiguous")
+            self.ptr = arr.data_ptr()
+        else:
+            self.ptr = arr.ctypes.data
+
+
+def launch_opts(device_mem: bool, strict: bool = False, stream=None, block: int = 0, device: int = -1):
+    o = gb_launch()
+    o.mem = MEM_DEVICE if device_mem else MEM_HOST
+    o.device = device
+    o.stream = stream
+    o.strict_math = 1 if strict else 0
+    o.block_threads = block
+    return o
+
+
+def as_f64(a, shape_ndim=None):
+    """C-contiguous float64 view/copy of a numpy-like array (host path)."""
+    return np.ascontiguousarray(a, dtype=np.float64)

@@ -1,0 +1,103 @@
+"""Thin containers standing in for ``gala.dynamics.PhaseSpacePosition`` / ``Orbit``
+(reference ``dynamics/core.py:57``, ``dynamics/orbit.py:22``) in the unit system of the
+Hamiltonian: plain arrays, no astropy.  Only the touch points of the hot path exist:
+``w()`` (``dynamics/core.py:476-525``), ``from_w``, slicing by orbit, and ``energy``."""
+from __future__ import annotations
+
+import numpy as np
+
+__all__ = ["PhaseSpacePosition", "Orbit", "MockStream"]
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+class PhaseSpacePosition:
+    def __init__(self, pos, vel, frame=None):
+        self.pos = pos if _is_torch(pos) else np.asarray(pos, dtype=np.float64)
+        self.vel = vel if _is_torch(vel) else np.asarray(vel, dtype=np.float64)
+        if tuple(self.pos.shape) != tuple(self.vel.shape):
+            raise ValueError("pos and vel must have the same shape")
+        self.frame = frame
+
+    @property
+    def ndim(self):
+        return self.pos.shape[0]
+
+    @property
+    def shape(self):
+        return tuple(self.pos.shape[1:])
+
+    xyz = property(lambda self: self.pos)
+    v_xyz = property(lambda self: self.vel)
+
+    def w(self, units=None):
+        """(2*ndim, ...) array [pos; vel]."""
+        if _is_torch(self.pos):
+            import torch
+            return torch.cat([self.pos, self.vel], dim=0)
+        return np.vstack([self.pos, self.vel])
+
+    @classmethod
+    def from_w(cls, w, units=None, **kw):
+        n = w.shape[0] // 2
+        return cls(pos=w[:n], vel=w[n:], **kw)
+
+    def __getitem__(self, key):
+        if not isinstance(key, tuple):
+            key = (key,)
+        return self.__class__(pos=self.pos[(slice(None),) + key], vel=self.vel[(slice(None),) + key],
+                              frame=self.frame)
+
+
+class Orbit(PhaseSpacePosition):
+    """pos, vel of shape (3, ntimes[, norbits]) plus the time grid."""
+
+    def __init__(self, pos, vel, t=None, hamiltonian=None, frame=None):
+        super().__init__(pos, vel, frame=frame if frame is not None else getattr(hamiltonian, "frame", None))
+        self.t = t
+        self.hamiltonian = hamiltonian
+
+    @property
+    def ntimes(self):
+        return self.pos.shape[1]
+
+    @property
+    def norbits(self):
+        return 1 if self.pos.ndim < 3 else self.pos.shape[2]
+
+    @classmethod
+    def from_w(cls, w, units=None, t=None, hamiltonian=None, **kw):
+        n = w.shape[0] // 2
+        return cls(pos=w[:n], vel=w[n:], t=t, hamiltonian=hamiltonian, **kw)
+
+    def __getitem__(self, key):
+        if not isinstance(key, tuple):
+            key = (key,)
+        t = self.t
+        if t is not None and len(key) >= 1 and not isinstance(key[0], (int, np.integer)):
+            t = t[key[0]]
+        elif t is not None and len(key) >= 1:
+            return PhaseSpacePosition(pos=self.pos[(slice(None),) + key], vel=self.vel[(slice(None),) + key],
+                                      frame=self.frame)
+        return Orbit(pos=self.pos[(slice(None),) + key], vel=self.vel[(slice(None),) + key], t=t,
+                     hamiltonian=self.hamiltonian, frame=self.frame)
+
+    def energy(self, hamiltonian=None):
+        """Hamiltonian value along the orbit, shape (ntimes[, norbits]) -- evaluated on the GPU."""
+        H = hamiltonian or self.hamiltonian
+        if H is None:
+            raise ValueError("an Orbit without a hamiltonian needs one passed in")
+        w = self.w()
+        flat = w.reshape(w.shape[0], -1)
+        return H.energy(flat).reshape(tuple(w.shape[1:]))
+
+
+class MockStream(PhaseSpacePosition):
+    """reference ``dynamics/mockstream/core.py`` MockStream: adds release_time and lead_trail."""
+
+    def __init__(self, pos, vel, release_time=None, lead_trail=None, frame=None):
+        super().__init__(pos, vel, frame=frame)
+        self.release_time = release_time
+        self.lead_trail = lead_trail

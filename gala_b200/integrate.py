@@ -1,0 +1,225 @@
+"""Integrator front-ends and the three functions at the reference's Cython boundary.
+
+``leapfrog_integrate_hamiltonian``, ``ruth4_integrate_hamiltonian`` and
+``dop853_integrate_hamiltonian`` keep the reference's names, argument meaning, return shapes and
+error behaviour (``integrate/cyintegrators/leapfrog.pyx:54-121``, ``ruth4.pyx:37-113``,
+``dop853.pyx:196-250``) and forward to the C ABI.  ``w0`` may be a numpy array (host buffers,
+copies inside the call) or a float64 ``torch.cuda`` tensor (device buffers, no copies, result
+stays on the device).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+
+import numpy as np
+
+from . import _abi
+from .frame import StaticFrame
+from .units import strip
+
+__all__ = ["parse_time_specification", "LeapfrogIntegrator", "Ruth4Integrator", "DOPRI853Integrator",
+           "get_integrator", "leapfrog_integrate_hamiltonian", "ruth4_integrate_hamiltonian",
+           "dop853_integrate_hamiltonian"]
+
+
+def parse_time_specification(units=None, dt=None, n_steps=None, t1=None, t2=None, t=None):
+    """Restates ``integrate/timespec.py:10-147`` (same accepted combinations, same arithmetic:
+    ``dt, n_steps`` -> ``t1 + cumsum`` of n_steps+1 entries)."""
+    if n_steps is not None:
+        n_steps = int(n_steps)
+    dt, t1, t2, t = strip(dt), strip(t1), strip(t2), strip(t)
+    if t is not None:
+        return np.asarray(t).astype(np.float64)
+    if dt is None and (t1 is None or t2 is None or n_steps is None):
+        raise ValueError("Invalid specification of integration time. See docstring for more information.")
+    if dt is not None and n_steps is not None:
+        if t1 is None:
+            t1 = 0.0
+        times = parse_time_specification(units, dt=np.ones(n_steps + 1) * dt, t1=t1)
+    elif dt is not None and t1 is not None and t2 is not None:
+        if t2 < t1 and dt < 0:
+            t_i, times = t1, []
+            while t_i > t2 and len(times) < 1e6:
+                times.append(t_i)
+                t_i += dt
+            if times[-1] != t2:
+                times.append(t2)
+            return np.array(times, dtype=np.float64)
+        if t2 > t1 and dt > 0:
+            t_i, times = t1, []
+            while t_i < t2 and len(times) < 1e6:
+                times.append(t_i)
+                t_i += dt
+            return np.array(times, dtype=np.float64)
+        if dt == 0:
+            raise ValueError("dt must be non-zero.")
+        raise ValueError("If t2 < t1, dt must be negative. If t1 < t2, dt must be positive.")
+    elif isinstance(dt, np.ndarray) and t1 is not None:
+        times = np.cumsum(np.append([0.0], dt)) + t1
+        times = times[:-1]
+    elif dt is None and not (t1 is None or t2 is None or n_steps is None):
+        times = np.linspace(t1, t2, n_steps, endpoint=True)
+    else:
+        raise ValueError("Invalid options. See docstring.")
+    return times.astype(np.float64)
+
+
+# ---- buffers ------------------------------------------------------------------------------------
+def _prep_w0(w0):
+    if _abi._is_torch_cuda(w0):
+        import torch
+        if w0.dtype != torch.float64 or w0.ndim != 2 or w0.shape[0] != 6:
+            raise ValueError("w0 must be a float64 tensor of shape (6, N)")
+        return _abi.Buf(w0.contiguous())
+    a = np.ascontiguousarray(w0, dtype=np.float64)
+    if a.ndim != 2 or a.shape[0] != 6:
+        raise ValueError(f"w0 must have shape (6, N), got {a.shape}")
+    return _abi.Buf(a)
+
+
+def _prep_t(t, like):
+    th = np.ascontiguousarray(strip(t) if not _abi._is_torch_cuda(t) else t.cpu().numpy(), dtype=np.float64)
+    if th.ndim != 1:
+        raise ValueError("t must be one-dimensional")
+    if like.device:
+        import torch
+        return th, _abi.Buf(torch.as_tensor(th, device=like.arr.device))
+    return th, _abi.Buf(th)
+
+
+def _alloc(like, shape, dtype="f8"):
+    if like.device:
+        import torch
+        return torch.empty(shape, dtype=torch.float64 if dtype == "f8" else torch.int32, device=like.arr.device)
+    return np.empty(shape, dtype=np.float64 if dtype == "f8" else np.int32)
+
+
+def _opts(like, hamiltonian, block=0):
+    stream, dev = None, -1
+    if like.device:
+        import torch
+        stream = torch.cuda.current_stream(like.arr.device).cuda_stream
+        dev = like.arr.device.index
+    strict = bool(getattr(hamiltonian, "strict_math", False) or getattr(hamiltonian.potential, "strict_math", False))
+    return _abi.launch_opts(like.device, strict, stream, block=block, device=dev)
+
+
+def _check_c_enabled(hamiltonian):
+    if not getattr(hamiltonian, "c_enabled", False):
+        raise TypeError("Input Hamiltonian object does not support C-level access.")
+
+
+# ---- the boundary functions -----------------------------------------------------------------------
+def _fixed_step(fn_name, hamiltonian, w0, t, save_all):
+    _check_c_enabled(hamiltonian)
+    w = _prep_w0(w0)
+    th, tb = _prep_t(t, w)
+    N, ntimes = w.arr.shape[1], th.size
+    out = _alloc(w, (6, ntimes, N) if save_all else (6, N))
+    opt = _opts(w, hamiltonian)
+    fr = hamiltonian.frame.spec()
+    fn = getattr(_abi.lib(), fn_name)
+    _abi.check(fn(hamiltonian.potential.spec().ptr(), C.byref(fr), w.ptr, N, tb.ptr, ntimes, int(bool(save_all)),
+                  _abi.Buf(out).ptr, C.byref(opt)))
+    return (th, out) if save_all else (th[-1:], out)
+
+
+def leapfrog_integrate_hamiltonian(hamiltonian, w0, t, save_all=1):
+    """w0 (6,N) -> (t, w[6, ntimes, N]) or (t[-1:], w[6, N]); StaticFrame only (TypeError otherwise),
+    like ``leapfrog.pyx:54-121``."""
+    if not isinstance(hamiltonian.frame, StaticFrame):
+        _check_c_enabled(hamiltonian)
+        raise TypeError("Leapfrog integration is currently only supported for StaticFrame, "
+                        f"not {hamiltonian.frame.__class__.__name__}")
+    return _fixed_step("gb_leapfrog", hamiltonian, w0, t, save_all)
+
+
+def ruth4_integrate_hamiltonian(hamiltonian, w0, t, save_all=1, allow_rotating_frame=False):
+    """``ruth4.pyx:37-113``.  The Cython function raises TypeError for a non-static frame; pass
+    ``allow_rotating_frame=True`` to run the reference's *Python* Ruth4 semantics in a
+    ConstantRotatingFrame on the GPU (what ``cython_if_possible=False`` executes in the reference)."""
+    if not isinstance(hamiltonian.frame, StaticFrame) and not allow_rotating_frame:
+        _check_c_enabled(hamiltonian)
+        raise TypeError("Leapfrog integration is currently only supported for StaticFrame, not "
+                        f"{hamiltonian.frame.__class__.__name__}.")
+    return _fixed_step("gb_ruth4", hamiltonian, w0, t, save_all)
+
+
+def dop853_integrate_hamiltonian(hamiltonian, w0, t, atol=1e-10, rtol=1e-10, nmax=0, dt_max=0.0, nstiff=0,
+                                 save_all=1, err_if_fail=1, log_output=0, nbatch=100, return_status=False):
+    """``dop853.pyx:196-250``.  Step-size control is per orbit (the reference's ``nbatch=1``); the
+    ``nbatch`` argument is accepted and ignored.  With ``err_if_fail`` a failed orbit raises
+    ``RuntimeError("Integration failed with code ...")`` like ``dop853.pyx:184-185``."""
+    _check_c_enabled(hamiltonian)
+    w = _prep_w0(w0)
+    th, tb = _prep_t(t, w)
+    N, ntimes = w.arr.shape[1], th.size
+    if ntimes < 1:
+        raise ValueError("ntimes must be greater than 1")
+    out = _alloc(w, (6, ntimes, N) if save_all else (6, N))
+    status = _alloc(w, (N,), "i4")
+    stats = None
+    stats_struct = None
+    if return_status:
+        stats = {k: _alloc(w, (N,), "i4") for k in ("nstep", "naccpt", "nrejct", "nfcn")}
+        stats_struct = _abi.gb_dop853_stats(*[C.cast(_abi.Buf(stats[k]).ptr, _abi.c_int32_p)
+                                              for k in ("nstep", "naccpt", "nrejct", "nfcn")])
+    opt = _opts(w, hamiltonian)
+    fr = hamiltonian.frame.spec()
+    rc = _abi.lib().gb_dop853(hamiltonian.potential.spec().ptr(), C.byref(fr), w.ptr, N, tb.ptr, ntimes,
+                              float(atol), float(rtol), int(nmax), float(dt_max), int(nstiff), int(bool(save_all)),
+                              _abi.Buf(out).ptr, _abi.Buf(status).ptr,
+                              C.byref(stats_struct) if stats_struct is not None else None, C.byref(opt))
+    if rc in (-1, -2, -3, -4):
+        if err_if_fail:
+            _abi.check(rc)
+    else:
+        _abi.check(rc)
+    res = (th, out) if save_all else (th[-1:], out)
+    if return_status:
+        stats["status"] = status
+        return res + (stats,)
+    return res
+
+
+# ---- integrator classes (names for Hamiltonian.integrate_orbit dispatch; integrate/__init__.py) ---
+class _IntegratorBase:
+    name = None
+
+    def __init__(self, func=None, func_args=(), func_units=None, progress=False, save_all=True, **kwargs):
+        self.F = func
+        self.save_all = save_all
+        self.kwargs = kwargs
+
+
+class LeapfrogIntegrator(_IntegratorBase):
+    name = "leapfrog"
+
+
+class Ruth4Integrator(_IntegratorBase):
+    name = "ruth4"
+
+
+class DOPRI853Integrator(_IntegratorBase):
+    name = "dopri853"
+
+
+_LOOKUP = {"leapfrog": LeapfrogIntegrator, "ruth4": Ruth4Integrator, "dopri853": DOPRI853Integrator,
+           "dop853": DOPRI853Integrator}
+
+
+def get_integrator(Integrator):
+    """``integrate/lookup.py``: accept a class or a (case-insensitive) name."""
+    if isinstance(Integrator, str):
+        try:
+            return _LOOKUP[Integrator.lower()]
+        except KeyError:
+            raise ValueError(f"Unknown integrator name '{Integrator}'. Available: {sorted(_LOOKUP)}")
+    if isinstance(Integrator, type) and issubclass(Integrator, _IntegratorBase):
+        return Integrator
+    name = getattr(Integrator, "__name__", "")
+    for cls in (LeapfrogIntegrator, Ruth4Integrator, DOPRI853Integrator):     # real gala classes by name
+        if name == cls.__name__:
+            return cls
+    raise ValueError(f"Integrator {Integrator!r} is not supported by the B200 engine")

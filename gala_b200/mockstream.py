@@ -1,0 +1,303 @@
+"""Mock stellar streams: ``FardalStreamDF``, ``MockStreamGenerator`` and the two functions at the
+reference's Cython boundary, ``mockstream_dop853`` / ``mockstream_leapfrog``
+(reference ``dynamics/mockstream/df.pyx``, ``mockstream_generator.py``, ``mockstream.pyx``).
+
+Scope: no massive bodies other than the (massless-for-dynamics)
+progenitor -- i.e. ``progenitor_potential=None`` and no extra ``nbody`` -- in a StaticFrame.  Then
+every stream particle is an independent test particle and the whole stream is integrated by ONE
+batched kernel launch (one thread per particle) instead of the reference's sequential loop over
+release groups.  Random deviates are drawn on the host with the caller's numpy RNG in exactly the
+reference's order (``df.pyx:393-454``), so sampling is bit-reproducible; the GPU does the geometry.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from .dynamics import MockStream, Orbit, PhaseSpacePosition
+from .frame import StaticFrame
+from .hamiltonian import Hamiltonian
+from .integrate import (DOPRI853Integrator, LeapfrogIntegrator, dop853_integrate_hamiltonian, get_integrator,
+                        leapfrog_integrate_hamiltonian, parse_time_specification)
+from .units import strip
+
+__all__ = ["FardalStreamDF", "MockStreamGenerator", "DirectNBody", "mockstream_dop853", "mockstream_leapfrog"]
+
+
+def _opts(H):
+    return _abi.launch_opts(False, bool(getattr(H, "strict_math", False) or H.potential.strict_math))
+
+
+class FardalStreamDF:
+    """Fardal, Huang & Weinberg (2015) particle-release distribution function
+    (``df.pyx:320-456``).  ``random_state`` may be a ``numpy.random.RandomState`` or ``Generator``;
+    only ``.normal(loc, scale)`` is used."""
+
+    def __init__(self, gala_modified=True, lead=True, trail=True, random_state=None):
+        self._lead, self._trail = int(bool(lead)), int(bool(trail))
+        if not self._lead and not self._trail:
+            raise ValueError("You must generate either leading or trailing tails (or both!)")
+        self.random_state = np.random.RandomState() if random_state is None else random_state
+        self._gala_modified = int(bool(gala_modified))
+
+    lead = property(lambda self: self._lead)
+    trail = property(lambda self: self._trail)
+
+    def _plan(self, prog_m, nparticles):
+        """Particle bookkeeping in the reference's emission order: per timestep (skipping
+        prog_m == 0), all trailing particles, then all leading particles (``df.pyx:393-454``)."""
+        idx, sign = [], []
+        for i in range(len(prog_m)):
+            if prog_m[i] == 0:
+                continue
+            n = int(nparticles[i])
+            if self._trail:
+                idx.append(np.full(n, i, dtype=np.int32)); sign.append(np.full(n, 1.0))
+            if self._lead:
+                idx.append(np.full(n, i, dtype=np.int32)); sign.append(np.full(n, -1.0))
+        if not idx:
+            return np.zeros(0, np.int32), np.zeros(0)
+        return np.concatenate(idx), np.concatenate(sign)
+
+    def _sample(self, potential, prog_x, prog_v, prog_t, prog_m, nparticles):
+        """(ntimes,3) progenitor positions / velocities -> particle_x (Np,3), particle_v, particle_t1."""
+        prog_idx, sign = self._plan(prog_m, nparticles)
+        Np = prog_idx.size
+        # k_mean / k_disp of df.pyx:378-391; draws per particle in the order kx, z, vt, vz
+        kvt_fardal = 0.4
+        loc = np.array([2.0, 0.0, 0.3, 0.0])
+        scale = np.array([0.5 if self._gala_modified else 0.4, 0.5,
+                          0.5 if self._gala_modified else kvt_fardal, 0.5])
+        normals = np.ascontiguousarray(
+            self.random_state.normal(np.broadcast_to(loc, (Np, 4)), np.broadcast_to(scale, (Np, 4))), dtype=np.float64)
+        prog_w = np.ascontiguousarray(np.hstack([prog_x, prog_v]), dtype=np.float64)
+        prog_t = np.ascontiguousarray(prog_t, dtype=np.float64)
+        prog_m = np.ascontiguousarray(prog_m, dtype=np.float64)
+        out = np.empty((Np, 6))
+        opt = _abi.launch_opts(False, bool(potential.strict_math))
+        _abi.check(_abi.lib().gb_fardal_release(
+            potential.spec().ptr(), float(potential.G), prog_w.ctypes.data, prog_t.ctypes.data, prog_m.ctypes.data,
+            len(prog_t), prog_idx.ctypes.data, sign.ctypes.data, normals.ctypes.data, Np, self._gala_modified,
+            out.ctypes.data, C.byref(opt)))
+        return out[:, :3].copy(), out[:, 3:].copy(), prog_t[prog_idx]
+
+    def sample(self, prog_orbit, prog_mass, hamiltonian=None, release_every=1, n_particles=1):
+        """``BaseStreamDF.sample`` (``df.pyx:125-238``): returns a ``MockStream`` of initial conditions."""
+        H = prog_orbit.hamiltonian if getattr(prog_orbit, "hamiltonian", None) is not None else (
+            Hamiltonian(hamiltonian) if hamiltonian is not None else None)
+        if H is None:
+            raise ValueError("a hamiltonian is required to sample the DF")
+        if not isinstance(H.frame, StaticFrame):
+            raise NotImplementedError("mock streams are implemented for StaticFrame only")
+        prog_x = np.ascontiguousarray(np.asarray(prog_orbit.pos).T)
+        prog_v = np.ascontiguousarray(np.asarray(prog_orbit.vel).T)
+        prog_t = np.asarray(prog_orbit.t, dtype=np.float64)
+        prog_m = np.squeeze(np.asarray(strip(prog_mass), dtype=np.float64))
+        if prog_m.shape == ():
+            prog_m = np.full_like(prog_t, prog_m)
+        if np.iterable(n_particles):
+            n_particles = np.array(n_particles).astype("i4")
+            if len(n_particles) != len(prog_t):
+                raise ValueError("If passing in an array n_particles, its shape must match the number of "
+                                 "timesteps in the progenitor orbit.")
+        else:
+            N = int(n_particles)
+            n_particles = np.zeros(len(prog_t), dtype="i4")
+            n_particles[::release_every] = N
+        x, v, t1 = self._sample(H.potential, prog_x, prog_v, prog_t, prog_m, n_particles)
+        lt = np.empty(len(t1), dtype="U1")
+        i = 0
+        for k, n in enumerate(n_particles):
+            if prog_m[k] == 0:
+                continue
+            if self._trail:
+                lt[i:i + n] = "t"; i += n
+            if self._lead:
+                lt[i:i + n] = "l"; i += n
+        return MockStream(pos=x.T, vel=v.T, release_time=t1, lead_trail=lt, frame=H.frame)
+
+
+class DirectNBody:
+    """The slice of ``gala.dynamics.nbody.DirectNBody`` the mock-stream path touches
+    (``dynamics/nbody/core.py``): initial conditions of the bodies + per-body potentials + the external
+    Hamiltonian.  Only massless bodies (particle potential ``None``) are supported."""
+
+    def __init__(self, w0, particle_potentials, external_potential=None, frame=None, units=None, save_all=True):
+        w = w0.w() if isinstance(w0, PhaseSpacePosition) else np.asarray(w0, dtype=np.float64)
+        w = w.reshape(6, -1)
+        self._c_w0 = np.ascontiguousarray(w.T)            # (nbodies, 6) like the reference
+        self.particle_potentials = list(particle_potentials)
+        if any(p is not None and p.__class__.__name__ != "NullPotential" for p in self.particle_potentials):
+            raise NotImplementedError("massive bodies (self-gravity / perturbers) are not implemented yet")
+        if len(self.particle_potentials) != self._c_w0.shape[0]:
+            raise ValueError("one particle potential per body is required")
+        self.H = Hamiltonian(external_potential, frame)
+        self.external_potential, self.frame, self.units = self.H.potential, self.H.frame, self.H.units
+        self.save_all = save_all
+
+    def integrate_orbit(self, Integrator=None, Integrator_kwargs=None, **time_spec):
+        """``nbody/core.py:166-282`` for massless bodies: DOPRI853 runs with the stiffness test disabled
+        (``nbody.pyx:106``), i.e. as independent n=6 systems here."""
+        Integrator = get_integrator(Integrator or DOPRI853Integrator)
+        kw = dict(Integrator_kwargs or {})
+        t = parse_time_specification(self.units, **time_spec)
+        w0 = np.ascontiguousarray(self._c_w0.T)
+        if Integrator is LeapfrogIntegrator:
+            _, w = leapfrog_integrate_hamiltonian(self.H, w0, t, save_all=int(self.save_all))
+        elif Integrator is DOPRI853Integrator:
+            kw = {k: kw[k] for k in ("atol", "rtol", "nmax", "dt_max", "err_if_fail") if k in kw}
+            _, w = dop853_integrate_hamiltonian(self.H, w0, t, nstiff=-1, save_all=int(self.save_all), **kw)
+        else:
+            raise NotImplementedError(f"N-body integration is not supported with {Integrator}")
+        if self.save_all:
+            return Orbit.from_w(w, t=t, hamiltonian=self.H)
+        return PhaseSpacePosition.from_w(w, frame=self.frame)
+
+
+def _validate_time_arrays(ntimes, n_t1, n_nstream):
+    if n_t1 != ntimes or n_nstream != ntimes:
+        raise ValueError("time, stream_t1 and nstream must have the same length")
+
+
+def mockstream_dop853(nbody, time, stream_w0, stream_t1, tfinal, nstream, atol=1e-10, rtol=1e-10, nmax=0,
+                      dt_max=0.0, nstiff=-1, progress=0, err_if_fail=1, log_output=0):
+    """``mockstream.pyx:176-303``.  Returns ``(nbody_w (nbodies,6), stream_w (Np,6))``.
+    Deviation from the reference (documented in DESIGN.md): the members of a release group do not
+    share one DOP853 step size; each particle is its own n=6 system."""
+    time = np.ascontiguousarray(time, dtype=np.float64)
+    stream_w0 = np.ascontiguousarray(stream_w0, dtype=np.float64)
+    stream_t1 = np.ascontiguousarray(stream_t1, dtype=np.float64)
+    nstream = np.asarray(nstream)
+    ntimes = time.shape[0]
+    _validate_time_arrays(ntimes, stream_t1.shape[0], nstream.shape[0])
+    if stream_w0.shape != (int(nstream.sum()), 6):
+        raise ValueError("stream_w0 must have shape (sum(nstream), 6)")
+    H = nbody.H
+    nbodies = nbody._c_w0.shape[0]
+    dt0 = time[1] - time[0]
+    # 1) the bodies at every release time: dense output of one DOP853 run (mockstream.pyx:247-255)
+    _, nbody_w = dop853_integrate_hamiltonian(H, np.ascontiguousarray(nbody._c_w0.T), time, atol=atol, rtol=rtol,
+                                              nmax=nmax, dt_max=dt_max, nstiff=nstiff, save_all=1,
+                                              err_if_fail=err_if_fail)
+    # 2) every stream particle from its release time to tfinal, plus the bodies from the LAST group's
+    #    release time (that is what w_tmp[:nbodies] holds when the reference's loop ends, :285-290)
+    groups = np.nonzero(nstream)[0]
+    last = groups[-1] if groups.size else ntimes - 1
+    rows = np.vstack([stream_w0, nbody_w[:, last, :].T])
+    t1 = np.concatenate([np.repeat(stream_t1, nstream), np.full(nbodies, stream_t1[last])])
+    out = np.empty_like(rows)
+    status = np.empty(rows.shape[0], dtype=np.int32)
+    opt = _opts(H)
+    fr = H.frame.spec()
+    rc = _abi.lib().gb_mockstream_dop853(H.potential.spec().ptr(), C.byref(fr), rows.ctypes.data, t1.ctypes.data,
+                                         rows.shape[0], float(tfinal), float(dt0), float(atol), float(rtol),
+                                         int(nmax), out.ctypes.data, status.ctypes.data, C.byref(opt))
+    if rc in (-1, -2, -3, -4):
+        if err_if_fail:
+            _abi.check(rc)
+    else:
+        _abi.check(rc)
+    Np = stream_w0.shape[0]
+    return out[Np:].copy(), out[:Np].copy()
+
+
+def mockstream_leapfrog(nbody, full_time, spawn_time, stream_w0, stream_t1, tfinal, nstream, progress=0,
+                        err_if_fail=1):
+    """``mockstream.pyx:442-620``: fixed-step version; particle p takes
+    ``int((tfinal - t1)/dt + 0.5)`` steps of ``dt = full_time[1]-full_time[0]``."""
+    full_time = np.ascontiguousarray(full_time, dtype=np.float64)
+    stream_w0 = np.ascontiguousarray(stream_w0, dtype=np.float64)
+    stream_t1 = np.ascontiguousarray(stream_t1, dtype=np.float64)
+    nstream = np.asarray(nstream)
+    ntimes = len(spawn_time)
+    _validate_time_arrays(ntimes, stream_t1.shape[0], nstream.shape[0])
+    H = nbody.H
+    nbodies = nbody._c_w0.shape[0]
+    dt = full_time[1] - full_time[0]
+    _, traj = leapfrog_integrate_hamiltonian(H, np.ascontiguousarray(nbody._c_w0.T), full_time, save_all=1)
+    groups = np.nonzero(nstream)[0]
+    last = groups[-1] if groups.size else ntimes - 1
+    idx = int((stream_t1[last] - full_time[0]) / dt + 0.5)          # mockstream.pyx:548
+    rows = np.vstack([stream_w0, traj[:, idx, :].T])
+    t1 = np.concatenate([np.repeat(stream_t1, nstream), np.full(nbodies, stream_t1[last])])
+    out = np.empty_like(rows)
+    opt = _opts(H)
+    _abi.check(_abi.lib().gb_mockstream_leapfrog(H.potential.spec().ptr(), rows.ctypes.data, t1.ctypes.data,
+                                                 rows.shape[0], float(tfinal), float(dt), out.ctypes.data,
+                                                 C.byref(opt)))
+    Np = stream_w0.shape[0]
+    return out[Np:].copy(), out[:Np].copy()
+
+
+class MockStreamGenerator:
+    """``dynamics/mockstream/mockstream_generator.py``: orchestration is unchanged; the three heavy
+    steps (progenitor orbit, particle release, stream integration) each run as one GPU call."""
+
+    def __init__(self, df, hamiltonian, progenitor_potential=None):
+        if not hasattr(df, "sample"):
+            raise TypeError("The input distribution function (DF) instance must be a stream DF")
+        self.df = df
+        self.hamiltonian = Hamiltonian(hamiltonian)
+        if progenitor_potential is not None:
+            raise NotImplementedError("progenitor self-gravity (massive bodies) is not implemented yet")
+        self.progenitor_potential = None
+        self.self_gravity = False
+
+    def _get_nbody(self, prog_w0, nbody):
+        if nbody is not None:
+            raise NotImplementedError("additional N-body perturbers are not implemented yet")
+        return DirectNBody(prog_w0, [None], external_potential=self.hamiltonian.potential,
+                           frame=self.hamiltonian.frame, units=self.hamiltonian.units)
+
+    def run(self, prog_w0, prog_mass, nbody=None, release_every=1, n_particles=1, output_every=None,
+            output_filename=None, check_filesize=True, overwrite=False, progress=False, Integrator=None,
+            Integrator_kwargs=None, **time_spec):
+        """``mockstream_generator.py:119-372``.  Returns ``(stream: MockStream, prog: PhaseSpacePosition)``."""
+        if output_every is not None:
+            raise NotImplementedError("snapshot output (output_every) is not implemented")
+        Integrator_kwargs = dict(Integrator_kwargs or {})
+        Integrator = get_integrator(Integrator or DOPRI853Integrator)
+        units = self.hamiltonian.units
+        t = parse_time_specification(units, **time_spec)
+        prog_nbody = self._get_nbody(prog_w0, nbody)
+        nbody_orbits = prog_nbody.integrate_orbit(t=t, Integrator=Integrator, Integrator_kwargs=Integrator_kwargs)
+        if t[1] < t[0]:
+            # initial conditions are at the END time: flip, restart from the earliest state (:237-250)
+            nbody_orbits = Orbit(pos=nbody_orbits.pos[:, ::-1], vel=nbody_orbits.vel[:, ::-1], t=nbody_orbits.t[::-1],
+                                 hamiltonian=self.hamiltonian)
+            nbody0 = DirectNBody(nbody_orbits[0], prog_nbody.particle_potentials,
+                                 external_potential=self.hamiltonian.potential, frame=self.hamiltonian.frame,
+                                 units=units)
+        else:
+            nbody0 = prog_nbody
+        prog_orbit = Orbit(pos=nbody_orbits.pos[:, :, 0], vel=nbody_orbits.vel[:, :, 0], t=nbody_orbits.t,
+                           hamiltonian=self.hamiltonian)
+        orbit_t = np.asarray(prog_orbit.t, dtype=np.float64)
+        stream_w0 = self.df.sample(prog_orbit, prog_mass, hamiltonian=self.hamiltonian,
+                                   release_every=release_every, n_particles=n_particles)
+        w0 = np.ascontiguousarray(np.vstack((stream_w0.pos, stream_w0.vel)).T)
+        unq_t1s, nstream = np.unique(stream_w0.release_time, return_counts=True)
+        all_nstream = np.zeros(prog_orbit.ntimes, dtype=int)
+        for t1, n in zip(unq_t1s, nstream):
+            all_nstream[np.isclose(orbit_t, t1)] = n
+        nstream_idx = np.where(all_nstream != 0)[0]
+        if 0 not in nstream_idx:
+            nstream_idx = np.insert(nstream_idx, 0, 0)
+            unq_t1s = np.insert(unq_t1s, 0, orbit_t[0])
+        if Integrator is DOPRI853Integrator:
+            raw_nbody, raw_stream = mockstream_dop853(nbody0, orbit_t[nstream_idx], w0, unq_t1s, orbit_t[-1],
+                                                      all_nstream[nstream_idx].astype("i4"), progress=int(progress),
+                                                      **Integrator_kwargs)
+        elif Integrator is LeapfrogIntegrator:
+            raw_nbody, raw_stream = mockstream_leapfrog(nbody0, orbit_t, orbit_t[nstream_idx], w0, unq_t1s,
+                                                        orbit_t[-1], all_nstream[nstream_idx].astype("i4"),
+                                                        progress=int(progress))
+        else:
+            raise ValueError("Currently, only the DOPRI853Integrator and LeapfrogIntegrator are supported for "
+                             "mock stream generation.")
+        stream = MockStream(pos=raw_stream[:, :3].T, vel=raw_stream[:, 3:].T, release_time=stream_w0.release_time,
+                            lead_trail=stream_w0.lead_trail, frame=self.hamiltonian.frame)
+        prog = PhaseSpacePosition(pos=raw_nbody[:, :3].T, vel=raw_nbody[:, 3:].T, frame=self.hamiltonian.frame)
+        return stream, prog

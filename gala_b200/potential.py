@@ -1,0 +1,412 @@
+"""Host-side mirror of the reference's potential classes for the hot path.
+
+Class names, parameter names and the C parameter layout follow the reference
+(``potential/potential/builtin/core.py``, ``special.py``, ``cybuiltin.pyx``,
+``ccompositepotential.pyx``): every object exposes ``G``, ``c_parameters`` (so that
+``[G] + c_parameters`` is exactly ``CPotentialWrapper._params``, ``cpotential.pyx:306-316``),
+``origin`` and ``R``, and ``spec()`` turns it into the flat ``gb_potential`` of the C ABI.
+All numerics run in the CUDA library; nothing here evaluates a potential on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+
+from . import _abi
+from .units import galactic, strip
+
+__all__ = [
+    "PotentialBase", "CCompositePotential", "NullPotential", "KeplerPotential", "HernquistPotential",
+    "PlummerPotential", "IsochronePotential", "JaffePotential", "NFWPotential", "MiyamotoNagaiPotential",
+    "MN3ExponentialDiskPotential", "LongMuraliBarPotential", "SCFPotential", "MilkyWayPotential",
+    "MilkyWayPotential2022",
+]
+
+
+class _Spec:
+    """Owns the ctypes structs + parameter arrays of one gb_potential (kept alive with it)."""
+
+    def __init__(self, components):
+        self.n = len(components)
+        self._arrays = []
+        self.comps = (_abi.gb_component * self.n)()
+        for i, (type_id, params, origin, R) in enumerate(components):
+            p = np.ascontiguousarray(params, dtype=np.float64)
+            self._arrays.append(p)
+            c = self.comps[i]
+            c.type_id = type_id
+            c.n_params = p.size
+            c.params = p.ctypes.data_as(_abi.c_double_p)
+            origin = np.zeros(3) if origin is None else np.asarray(origin, dtype=np.float64)
+            R = np.eye(3) if R is None else np.asarray(R, dtype=np.float64)
+            # do_shift_rotate = not (q0 == 0 and R == I)   (cpotential.pyx:79-92)
+            c.do_shift_rotate = int(not (np.all(origin == 0.0) and np.array_equal(R, np.eye(3))))
+            for k in range(3):
+                c.q0[k] = origin[k]
+            for k in range(9):
+                c.R[k] = R.ravel()[k]
+        self.pot = _abi.gb_potential(self.n, 3, C.cast(self.comps, C.POINTER(_abi.gb_component)))
+
+    def ptr(self):
+        return C.byref(self.pot)
+
+
+def _prep_q(q):
+    """(3,) or (3,N) host array / device tensor -> (Buf of shape (3,N), orig_shape)."""
+    if _abi._is_torch_cuda(q):
+        import torch
+        if q.dtype != torch.float64:
+            raise TypeError("device tensors must be float64")
+        shape = tuple(q.shape)
+        q2 = q.reshape(shape[0], -1).contiguous()
+        return _abi.Buf(q2), shape
+    a = np.asarray(strip(q), dtype=np.float64)
+    shape = a.shape
+    a2 = np.ascontiguousarray(a.reshape(shape[0], -1))
+    return _abi.Buf(a2), shape
+
+
+def _alloc_like(buf, shape, dtype="f8"):
+    if buf.device:
+        import torch
+        return torch.empty(shape, dtype=torch.float64 if dtype == "f8" else torch.int32, device=buf.arr.device)
+    return np.empty(shape, dtype=np.float64 if dtype == "f8" else np.int32)
+
+
+def _stream_of(buf):
+    if buf.device:
+        import torch
+        return torch.cuda.current_stream(buf.arr.device).cuda_stream, buf.arr.device.index
+    return None, -1
+
+
+class PotentialBase:
+    """Common behaviour (reference ``potential/potential/core.py`` PotentialBase, C-enabled subset)."""
+
+    ndim = 3
+    _type_id = None
+    _param_names = ()
+
+    def __init__(self, *, units=galactic, origin=None, R=None, **params):
+        self.units = units
+        self.G = units.G if units is not None else 1.0
+        self.origin = np.zeros(3) if origin is None else np.asarray(strip(origin), dtype=np.float64)
+        self.R = None if R is None else np.asarray(R, dtype=np.float64)
+        if self.R is not None and self.R.shape != (3, 3):
+            raise ValueError("Rotation matrix must be 3x3")
+        self.parameters = OrderedDict((k, float(strip(params[k]))) for k in self._param_names)
+        self.c_parameters = self._c_parameters()
+        self._spec = None
+        self.strict_math = False
+
+    # -- C parameter vector (without G), in the order the reference's wrapper receives it
+    def _c_parameters(self):
+        return np.array([self.parameters[k] for k in self._param_names], dtype=np.float64)
+
+    @property
+    def _R(self):
+        return np.eye(3) if self.R is None else self.R
+
+    def _components(self):
+        return [(self._type_id, np.concatenate([[self.G], self.c_parameters]), self.origin, self.R)]
+
+    def spec(self):
+        if self._spec is None:
+            self._spec = _Spec(self._components())
+        return self._spec
+
+    c_enabled = True
+
+    # -- evaluation ---------------------------------------------------------------------------
+    def _eval(self, fn_name, q, t, out_rows):
+        buf, shape = _prep_q(q)
+        if shape[0] != 3:
+            raise ValueError(f"position array must have shape (3, ...), got {shape}")
+        N = buf.arr.shape[1]
+        out = _alloc_like(buf, (out_rows, N) if out_rows > 1 else (N,))
+        stream, dev = _stream_of(buf)
+        opt = _abi.launch_opts(buf.device, self.strict_math, stream, device=dev)
+        fn = getattr(_abi.lib(), fn_name)
+        _abi.check(fn(self.spec().ptr(), buf.ptr, float(strip(t)), N, _abi.Buf(out).ptr, C.byref(opt)))
+        if out_rows > 1:
+            return out.reshape((out_rows,) + tuple(shape[1:]))
+        return out.reshape(tuple(shape[1:]))
+
+    def gradient(self, q, t=0.0):
+        """dPhi/dq at q (3,N); mirrors ``PotentialBase.gradient`` (core.py:425-479)."""
+        return self._eval("gb_gradient", q, t, 3)
+
+    def acceleration(self, q, t=0.0):
+        return -self.gradient(q, t)
+
+    def energy(self, q, t=0.0):
+        return self._eval("gb_energy", q, t, 1)
+
+    def density(self, q, t=0.0):
+        return self._eval("gb_density", q, t, 1)
+
+    def __call__(self, q, t=0.0):
+        return self.energy(q, t)
+
+    # -- orbit integration (core.py:1150-1184 -> Hamiltonian.integrate_orbit) --------------------
+    def integrate_orbit(self, w0, Integrator=None, Integrator_kwargs=None, cython_if_possible=True,
+                        save_all=True, **time_spec):
+        from .hamiltonian import Hamiltonian
+        return Hamiltonian(self).integrate_orbit(w0, Integrator=Integrator, Integrator_kwargs=Integrator_kwargs,
+                                                 cython_if_possible=cython_if_possible, save_all=save_all,
+                                                 **time_spec)
+
+    def __add__(self, other):
+        new = CCompositePotential()
+        for i, p in enumerate((self, other)):
+            if isinstance(p, CCompositePotential):
+                for k, v in p.items():
+                    new[k] = v
+            else:
+                new[f"c{len(new)}"] = p
+        return new
+
+    def __repr__(self):
+        pars = ", ".join(f"{k}={v:g}" for k, v in self.parameters.items())
+        return f"<{self.__class__.__name__}: {pars}>"
+
+
+class NullPotential(PotentialBase):
+    _type_id = _abi.POT_NULL
+
+
+class KeplerPotential(PotentialBase):
+    _type_id = _abi.POT_KEPLER
+    _param_names = ("m",)
+
+    def __init__(self, m, **kw):
+        super().__init__(m=m, **kw)
+
+
+class HernquistPotential(PotentialBase):
+    _type_id = _abi.POT_HERNQUIST
+    _param_names = ("m", "c")
+
+    def __init__(self, m, c, **kw):
+        super().__init__(m=m, c=c, **kw)
+
+
+class PlummerPotential(PotentialBase):
+    _type_id = _abi.POT_PLUMMER
+    _param_names = ("m", "b")
+
+    def __init__(self, m, b, **kw):
+        super().__init__(m=m, b=b, **kw)
+
+
+class IsochronePotential(PotentialBase):
+    _type_id = _abi.POT_ISOCHRONE
+    _param_names = ("m", "b")
+
+    def __init__(self, m, b, **kw):
+        super().__init__(m=m, b=b, **kw)
+
+
+class JaffePotential(PotentialBase):
+    _type_id = _abi.POT_JAFFE
+    _param_names = ("m", "c")
+
+    def __init__(self, m, c, **kw):
+        super().__init__(m=m, c=c, **kw)
+
+
+class NFWPotential(PotentialBase):
+    """NFW; wrapper chosen like ``NFWPotential._setup_potential`` (builtin/core.py:722-741)."""
+    _param_names = ("m", "r_s", "a", "b", "c")
+
+    def __init__(self, m, r_s, a=1.0, b=1.0, c=1.0, **kw):
+        super().__init__(m=m, r_s=r_s, a=a, b=b, c=c, **kw)
+        a, b, c = (self.parameters[k] for k in "abc")
+        if np.allclose([a, b, c], 1.0):
+            self._type_id = _abi.POT_NFW_SPHERICAL
+        elif np.allclose([a, b], 1.0):
+            self._type_id = _abi.POT_NFW_FLATTENED
+        else:
+            self._type_id = _abi.POT_NFW_TRIAXIAL
+
+    @classmethod
+    def from_circular_velocity(cls, v_c, r_s, a=1.0, b=1.0, c=1.0, r_ref=None, units=galactic, **kw):
+        """builtin/core.py ``NFWPotential.from_circular_velocity``: v_c in kpc/Myr at r_ref (default r_s)."""
+        v_c, r_s = float(strip(v_c)), float(strip(r_s))
+        r_ref = r_s if r_ref is None else float(strip(r_ref))
+        uu = r_ref / r_s
+        vs2 = v_c ** 2 / uu / (np.log(1 + uu) / uu ** 2 - 1 / (uu * (1 + uu)))
+        m = vs2 * r_s / units.G
+        return cls(m=m, r_s=r_s, a=a, b=b, c=c, units=units, **kw)
+
+
+class MiyamotoNagaiPotential(PotentialBase):
+    _type_id = _abi.POT_MIYAMOTONAGAI
+    _param_names = ("m", "a", "b")
+
+    def __init__(self, m, a, b, **kw):
+        super().__init__(m=m, a=a, b=b, **kw)
+
+
+class MN3ExponentialDiskPotential(PotentialBase):
+    """Three Miyamoto-Nagai disks approximating an exponential disk (Smith et al. 2015, MNRAS 448,
+    2934, tables 1 and 2).  Parameter precompute restates builtin/core.py:607-666; the C vector is
+    ``[m1,a1,b1, m2,a2,b2, m3,a3,b3, m, h_R, h_z]`` (c_only first, cpotential.pyx:289-303)."""
+    _type_id = _abi.POT_MN3
+    _param_names = ("m", "h_R", "h_z")
+
+    # Smith+2015 fitting-coefficient tables (positive-density and negative-density variants)
+    _K_pos_dens = np.array([
+        [0.0036, -0.0330, 0.1117, -0.1335, 0.1749],
+        [-0.0131, 0.1090, -0.3035, 0.2921, -5.7976],
+        [-0.0048, 0.0454, -0.1425, 0.1012, 6.7120],
+        [-0.0158, 0.0993, -0.2070, -0.7089, 0.6445],
+        [-0.0319, 0.1514, -0.1279, -0.9325, 2.6836],
+        [-0.0326, 0.1816, -0.2943, -0.6329, 2.3193]])
+    _K_neg_dens = np.array([
+        [-0.0090, 0.0640, -0.1653, 0.1164, 1.9487],
+        [0.0173, -0.0903, 0.0877, 0.2029, -1.3077],
+        [-0.0051, 0.0287, -0.0361, -0.0544, 0.2242],
+        [-0.0358, 0.2610, -0.6987, -0.1193, 2.0074],
+        [-0.0830, 0.4992, -0.7967, -1.2966, 4.4441],
+        [-0.0247, 0.1718, -0.4124, -0.5944, 0.7333]])
+
+    def __init__(self, m, h_R, h_z, positive_density=True, sech2_z=True, **kw):
+        self.positive_density = positive_density
+        self.sech2_z = sech2_z
+        super().__init__(m=m, h_R=h_R, h_z=h_z, **kw)
+
+    def _c_parameters(self):
+        m, h_R, h_z = (self.parameters[k] for k in ("m", "h_R", "h_z"))
+        hzR = h_z / h_R
+        K = self._K_pos_dens if self.positive_density else self._K_neg_dens
+        if self.sech2_z:
+            b_hR = -0.033 * hzR ** 3 + 0.262 * hzR ** 2 + 0.659 * hzR
+        else:
+            b_hR = -0.269 * hzR ** 3 + 1.08 * hzR ** 2 + 1.092 * hzR
+        x = np.vander([b_hR], N=5)[0]
+        param_vec = K @ x
+        self._ms = param_vec[:3] * m
+        self._as = param_vec[3:] * h_R
+        self._b = b_hR * h_R
+        c_only = []
+        for i in range(3):
+            c_only += [self._ms[i], self._as[i], self._b]
+        return np.array(c_only + [m, h_R, h_z], dtype=np.float64)
+
+    def get_three_potentials(self):
+        return {f"disk{i + 1}": MiyamotoNagaiPotential(m=self._ms[i], a=self._as[i], b=self._b, units=self.units,
+                                                       origin=self.origin, R=self.R) for i in range(3)}
+
+
+class LongMuraliBarPotential(PotentialBase):
+    """Long & Murali (1992) bar; ``alpha`` in radians (builtin/core.py LongMuraliBarPotential)."""
+    _type_id = _abi.POT_LONGMURALIBAR
+    _param_names = ("m", "a", "b", "c", "alpha")
+
+    def __init__(self, m, a, b, c, alpha=0.0, **kw):
+        super().__init__(m=m, a=a, b=b, c=c, alpha=alpha, **kw)
+
+
+class SCFPotential(PotentialBase):
+    """Hernquist-Ostriker basis-function expansion (reference potential/scf/core.py SCFPotential):
+    ``Snlm``/``Tnlm`` have shape (nmax+1, lmax+1, lmax+1); the C vector is
+    ``[nmax, lmax, m, r_s, Snlm.ravel(), Tnlm.ravel()]`` (scf/bfe.cpp:229-258)."""
+    _type_id = _abi.POT_SCF
+    _param_names = ("m", "r_s")
+
+    def __init__(self, m, r_s, Snlm, Tnlm=None, **kw):
+        self.Snlm = np.ascontiguousarray(Snlm, dtype=np.float64)
+        self.Tnlm = np.zeros_like(self.Snlm) if Tnlm is None else np.ascontiguousarray(Tnlm, dtype=np.float64)
+        if self.Snlm.ndim != 3 or self.Snlm.shape[1] != self.Snlm.shape[2] or self.Tnlm.shape != self.Snlm.shape:
+            raise ValueError("Snlm/Tnlm must have shape (nmax+1, lmax+1, lmax+1)")
+        self.nmax = self.Snlm.shape[0] - 1
+        self.lmax = self.Snlm.shape[1] - 1
+        super().__init__(m=m, r_s=r_s, **kw)
+
+    def _c_parameters(self):
+        return np.concatenate([[self.nmax, self.lmax, self.parameters["m"], self.parameters["r_s"]],
+                               self.Snlm.ravel(), self.Tnlm.ravel()])
+
+
+class CCompositePotential(PotentialBase, OrderedDict):
+    """Ordered collection of C-enabled potentials (reference ``ccompositepotential.pyx:27-86``);
+    components are evaluated and summed in insertion order."""
+
+    def __init__(self, **potentials):
+        OrderedDict.__init__(self)
+        self.units = galactic
+        self.G = galactic.G
+        self.origin = np.zeros(3)
+        self.R = None
+        self.parameters = OrderedDict()
+        self.c_parameters = np.array([])
+        self._spec = None
+        self.strict_math = False
+        self.lock = False
+        for k, v in potentials.items():
+            self[k] = v
+
+    def __setitem__(self, key, value):
+        if getattr(self, "lock", False):
+            raise ValueError("Potential object is locked - new components can only be added to unlocked potentials.")
+        if not isinstance(value, PotentialBase) or isinstance(value, CCompositePotential):
+            raise TypeError("components must be (non-composite) C-enabled potentials")
+        OrderedDict.__setitem__(self, key, value)
+        self.units = value.units
+        self.G = value.G
+        self._spec = None
+
+    def _components(self):
+        comps = []
+        for p in self.values():
+            comps += p._components()
+        return comps
+
+    def __repr__(self):
+        return "<CCompositePotential " + ",".join(self.keys()) + ">"
+
+    # OrderedDict defines __eq__/__hash__ semantics we do not want to inherit for hashing
+    __hash__ = object.__hash__
+
+
+class MilkyWayPotential(CCompositePotential):
+    """v1 Milky Way model (builtin/special.py:88-124 defaults): MN disk, two Hernquist spheres, NFW."""
+
+    def __init__(self, units=galactic, disk=None, halo=None, bulge=None, nucleus=None, version="v1"):
+        super().__init__()
+        if version in ("v2", "latest"):
+            _setup_mwp_2022(self, units, disk, halo, bulge, nucleus)
+        else:
+            d = dict(m=6.8e10, a=3.0, b=0.28); d.update(disk or {})
+            b = dict(m=5e9, c=1.0); b.update(bulge or {})
+            n = dict(m=1.71e9, c=0.07); n.update(nucleus or {})
+            h = dict(m=5.4e11, r_s=15.62); h.update(halo or {})
+            self["disk"] = MiyamotoNagaiPotential(units=units, **d)
+            self["bulge"] = HernquistPotential(units=units, **b)
+            self["nucleus"] = HernquistPotential(units=units, **n)
+            self["halo"] = NFWPotential(units=units, **h)
+        self.lock = True
+
+
+def _setup_mwp_2022(obj, units, disk=None, halo=None, bulge=None, nucleus=None):
+    # defaults and component order: builtin/special.py:127-153
+    d = dict(m=4.7717e10, h_R=2.6, h_z=0.3); d.update(disk or {})
+    b = dict(m=5e9, c=1.0); b.update(bulge or {})
+    n = dict(m=1.8142e9, c=0.0688867); n.update(nucleus or {})
+    h = dict(m=5.5427e11, r_s=15.626); h.update(halo or {})
+    obj["disk"] = MN3ExponentialDiskPotential(units=units, **d)
+    obj["bulge"] = HernquistPotential(units=units, **b)
+    obj["nucleus"] = HernquistPotential(units=units, **n)
+    obj["halo"] = NFWPotential(units=units, **h)
+
+
+class MilkyWayPotential2022(CCompositePotential):
+    """builtin/special.py:221-271: MN3 disk + Hernquist bulge + Hernquist nucleus + NFW halo."""
+
+    def __init__(self, units=galactic, disk=None, halo=None, bulge=None, nucleus=None):
+        super().__init__()
+        _setup_mwp_2022(self, units, disk, halo, bulge, nucleus)
+        self.lock = True

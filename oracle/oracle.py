@@ -1,0 +1,214 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE, NOT PRODUCT.
+
+ctypes front-end of the CPU checkers built by ``oracle/Makefile``:
+
+* ``Ref("strict")``  -> ``oracle/_ref/libgala_ref.so``: the reference's own C++ compiled unmodified
+  with strict-IEEE flags + the restated Cython loops of ``oracle/ref_driver.cpp``.  THE parity oracle.
+* ``Ref("fast")``    -> ``oracle/_ref/libgala_ref_fast.so``: same sources with the reference's shipped
+  flags (``-Ofast -march=x86-64-v3``); used for CPU timing and for reference-vs-reference floors.
+* ``Port()`` / ``Port(long_double=True)`` -> ``oracle/_ref/libgala_port*.so``: our plain-C restatement
+  (``oracle/port.c``), validated against ``Ref`` in tests/test_oracle_cpu.py.
+
+Only tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs
+may import this module.  Potentials / frames are passed as gala_b200 host objects; only their
+``spec()`` (the C-ABI structs) is used.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REF_DIR = os.path.join(_HERE, "_ref")
+
+
+def build(quiet=True):
+    """Run oracle/Makefile (builds the port always, the reference libs when /root/reference exists)."""
+    r = subprocess.run(["make", "-C", _HERE, "all"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+    return r.stdout
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class _Lib:
+    prefix = "ref_"
+
+    def __init__(self, path):
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} not built; run `make -C oracle`")
+        self.path = path
+        self.L = C.CDLL(path)
+
+    def _fn(self, name, restype=C.c_int):
+        f = getattr(self.L, self.prefix + name)
+        f.restype = restype
+        return f
+
+    # ---- potential evaluation ----------------------------------------------------------------
+    def gradient(self, pot, q, t=0.0):
+        q = _f64(q); N = q.shape[1]
+        out = np.empty((3, N))
+        rc = self._fn("gradient")(pot.spec().ptr(), q.ctypes.data_as(C.c_void_p), C.c_double(t), C.c_size_t(N),
+                                  out.ctypes.data_as(C.c_void_p))
+        assert rc == 0, rc
+        return out
+
+    def _scalar(self, name, pot, q, t):
+        q = _f64(q); N = q.shape[1]
+        out = np.empty(N)
+        rc = self._fn(name)(pot.spec().ptr(), q.ctypes.data_as(C.c_void_p), C.c_double(t), C.c_size_t(N),
+                            out.ctypes.data_as(C.c_void_p))
+        assert rc == 0, rc
+        return out
+
+    def energy(self, pot, q, t=0.0):
+        return self._scalar("energy", pot, q, t)
+
+    def density(self, pot, q, t=0.0):
+        return self._scalar("density", pot, q, t)
+
+    def hamiltonian_energy(self, H, w, t=0.0):
+        w = _f64(w); N = w.shape[1]
+        out = np.empty(N)
+        fr = H.frame.spec()
+        rc = self._fn("hamiltonian_energy")(H.potential.spec().ptr(), C.byref(fr), w.ctypes.data_as(C.c_void_p),
+                                            C.c_double(t), C.c_size_t(N), out.ctypes.data_as(C.c_void_p))
+        assert rc == 0, rc
+        return out
+
+    def hamiltonian_gradient(self, H, w, t=0.0):
+        w = _f64(w); N = w.shape[1]
+        out = np.empty((6, N))
+        fr = H.frame.spec()
+        rc = self._fn("hamiltonian_gradient")(H.potential.spec().ptr(), C.byref(fr), w.ctypes.data_as(C.c_void_p),
+                                              C.c_double(t), C.c_size_t(N), out.ctypes.data_as(C.c_void_p))
+        assert rc == 0, rc
+        return out
+
+    # ---- integrators ---------------------------------------------------------------------------
+    def leapfrog(self, pot, w0, t, save_all=True):
+        w0 = _f64(w0); t = _f64(t); N = w0.shape[1]
+        out = np.empty((6, t.size, N) if save_all else (6, N))
+        rc = self._fn("leapfrog")(pot.spec().ptr(), w0.ctypes.data_as(C.c_void_p), C.c_size_t(N),
+                                  t.ctypes.data_as(C.c_void_p), C.c_int(t.size), C.c_int(int(save_all)),
+                                  out.ctypes.data_as(C.c_void_p))
+        assert rc == 0, rc
+        return out
+
+    def ruth4(self, H, w0, t, save_all=True):
+        w0 = _f64(w0); t = _f64(t); N = w0.shape[1]
+        out = np.empty((6, t.size, N) if save_all else (6, N))
+        fr = H.frame.spec()
+        rc = self._fn("ruth4")(H.potential.spec().ptr(), C.byref(fr), w0.ctypes.data_as(C.c_void_p), C.c_size_t(N),
+                               t.ctypes.data_as(C.c_void_p), C.c_int(t.size), C.c_int(int(save_all)),
+                               out.ctypes.data_as(C.c_void_p))
+        assert rc == 0, rc
+        return out
+
+    def dop853(self, H, w0, t, atol=1e-10, rtol=1e-10, nmax=0, dt_max=0.0, nstiff=0, save_all=True, nbatch=1):
+        w0 = _f64(w0); t = _f64(t); N = w0.shape[1]
+        out = np.empty((6, t.size, N) if save_all else (6, N))
+        status = np.empty(N, dtype=np.int32)
+        fr = H.frame.spec()
+        rc = self._fn("dop853")(H.potential.spec().ptr(), C.byref(fr), w0.ctypes.data_as(C.c_void_p), C.c_size_t(N),
+                                t.ctypes.data_as(C.c_void_p), C.c_int(t.size), C.c_double(atol), C.c_double(rtol),
+                                C.c_long(nmax), C.c_double(dt_max), C.c_long(nstiff), C.c_int(int(save_all)),
+                                C.c_int(nbatch), out.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p))
+        return out, status, rc
+
+    def dop853_step_rows(self, H, rows, t1, t2, dt0, atol=1e-10, rtol=1e-10, nmax=0, group=True):
+        """rows (Np,6) integrated t1->t2 with dop853_step's settings; group=True: each row alone."""
+        rows = _f64(rows).copy(); Np = rows.shape[0]
+        status = np.empty(Np, dtype=np.int32)
+        fr = H.frame.spec()
+        rc = self._fn("dop853_step_rows")(H.potential.spec().ptr(), C.byref(fr), rows.ctypes.data_as(C.c_void_p),
+                                          C.c_size_t(Np), C.c_double(t1), C.c_double(t2), C.c_double(dt0),
+                                          C.c_double(atol), C.c_double(rtol), C.c_long(nmax), C.c_int(int(group)),
+                                          status.ctypes.data_as(C.c_void_p))
+        return rows, status, rc
+
+    def d2_dr2(self, pot, q3, t=0.0):
+        q3 = _f64(q3)
+        return self._fn("d2_dr2", C.c_double)(pot.spec().ptr(), C.c_double(t), q3.ctypes.data_as(C.c_void_p))
+
+
+class Ref(_Lib):
+    def __init__(self, flavor="strict"):
+        name = {"strict": "libgala_ref.so", "fast": "libgala_ref_fast.so"}[flavor]
+        super().__init__(os.path.join(_REF_DIR, name))
+        self.flavor = flavor
+
+    def build_flags(self):
+        return self._fn("build_flags", C.c_char_p)().decode()
+
+
+def have_ref(flavor="strict"):
+    name = {"strict": "libgala_ref.so", "fast": "libgala_ref_fast.so"}[flavor]
+    return os.path.exists(os.path.join(_REF_DIR, name))
+
+
+# ---- pure-numpy restatements of the Python-level pieces of the path (no C needed) -------------------
+def fardal_release_numpy(ref, pot, prog_x, prog_v, prog_t, prog_m, nparticles, random_state, gala_modified=True,
+                         lead=True, trail=True):
+    """FardalStreamDF._sample + get_rj_vj_R + transform_from_sat restated in numpy scalars
+    (dynamics/mockstream/df.pyx:61-106, 363-456), drawing the RNG exactly like the reference: four
+    scalar ``random_state.normal`` calls per particle.  ``ref`` supplies c_d2_dr2 from the compiled
+    reference (cpotential.cpp:346-371)."""
+    G = pot.G
+    k_mean = np.zeros(6); k_disp = np.zeros(6)
+    k_mean[0] = 2.; k_disp[0] = 0.5 if gala_modified else 0.4
+    k_mean[2] = 0.; k_disp[2] = 0.5
+    k_mean[4] = 0.3; k_disp[4] = 0.5 if gala_modified else 0.4
+    k_mean[5] = 0.; k_disp[5] = 0.5
+    X, V, T1 = [], [], []
+    for i in range(len(prog_t)):
+        if prog_m[i] == 0:
+            continue
+        px, pv = prog_x[i], prog_v[i]
+        dist = np.sqrt(px[0] ** 2 + px[1] ** 2 + px[2] ** 2)
+        L = np.array([px[1] * pv[2] - px[2] * pv[1], -px[0] * pv[2] + px[2] * pv[0], px[0] * pv[1] - px[1] * pv[0]])
+        Lnorm = np.sqrt(L[0] ** 2 + L[1] ** 2 + L[2] ** 2)
+        R = np.zeros((3, 3))
+        R[0] = px / dist
+        R[2] = L / Lnorm
+        Om = Lnorm / dist ** 2
+        d2r = ref.d2_dr2(pot, px, prog_t[i])
+        rj = (G * prog_m[i] / (Om * Om - d2r)) ** (1 / 3.)
+        vj = Om * rj
+        a, b = R[0], R[2]
+        R[1] = -np.array([a[1] * b[2] - a[2] * b[1], -a[0] * b[2] + a[2] * b[0], a[0] * b[1] - a[1] * b[0]])
+        for sgn, on in ((1.0, trail), (-1.0, lead)):
+            if not on:
+                continue
+            for _ in range(int(nparticles[i])):
+                tmp_x = np.zeros(3); tmp_v = np.zeros(3)
+                kx = random_state.normal(k_mean[0], k_disp[0])
+                tmp_x[0] = kx * (sgn * rj)
+                tmp_x[2] = random_state.normal(k_mean[2], k_disp[2]) * (sgn * rj)
+                tmp_v[1] = random_state.normal(k_mean[4], k_disp[4]) * (sgn * vj)
+                if gala_modified:
+                    tmp_v[1] *= kx
+                tmp_v[2] = random_state.normal(k_mean[5], k_disp[5]) * (sgn * vj)
+                ox = np.array([R[0, k] * tmp_x[0] + R[1, k] * tmp_x[1] + R[2, k] * tmp_x[2] for k in range(3)]) + px
+                ov = np.array([R[0, k] * tmp_v[0] + R[1, k] * tmp_v[1] + R[2, k] * tmp_v[2] for k in range(3)]) + pv
+                X.append(ox); V.append(ov); T1.append(prog_t[i])
+    return np.array(X).reshape(-1, 3), np.array(V).reshape(-1, 3), np.array(T1)
+
+
+class Port(_Lib):
+    """oracle/port.c restatement (double, or long double with ``long_double=True``)."""
+    prefix = "port_"
+
+    def __init__(self, long_double=False):
+        super().__init__(os.path.join(_REF_DIR, "libgala_port_ld.so" if long_double else "libgala_port.so"))
+        self.long_double = long_double
+
+    def build_flags(self):
+        return "gcc -std=c11 -O2 -ffp-contract=off (oracle/port.c)"

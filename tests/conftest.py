@@ -1,0 +1,58 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def make_ic(pot_gradient, N, seed, rmin=4.0, rmax=50.0):
+    """Seeded bound orbits: r = exp(U[ln rmin, ln rmax]) kpc with isotropic direction; speed =
+    f * v_circ(r), f ~ U[0.5, 1.0]; velocity direction mostly tangential (radial direction cosine
+    mu ~ U[-0.5, 0.5]).  SURVEY.md 8d proposed a fully isotropic velocity direction; that produces
+    plunging orbits (pericentre < 0.3 kpc through the 0.07-kpc nucleus) on which the reference does
+    not reproduce ITSELF between its -O2 and -Ofast builds after 1000 steps (differences of order
+    unity), so parity there measures chaos, not the implementation.  ``pot_gradient(q)`` -> (3,N)."""
+    rng = np.random.default_rng(seed)
+    r = np.exp(rng.uniform(np.log(rmin), np.log(rmax), N))
+    mu = rng.uniform(-1, 1, N); ph = rng.uniform(0, 2 * np.pi, N)
+    s = np.sqrt(1 - mu * mu)
+    rhat = np.vstack([s * np.cos(ph), s * np.sin(ph), mu])
+    q = r * rhat
+    # two unit vectors orthogonal to rhat
+    e1 = np.vstack([-np.sin(ph), np.cos(ph), np.zeros(N)])
+    e2 = np.cross(rhat.T, e1.T).T
+    psi = rng.uniform(0, 2 * np.pi, N)
+    cr = rng.uniform(-0.5, 0.5, N)
+    vhat = cr * rhat + np.sqrt(1 - cr * cr) * (np.cos(psi) * e1 + np.sin(psi) * e2)
+    g = pot_gradient(np.ascontiguousarray(q))
+    vc = np.sqrt(r * np.sqrt((g * g).sum(0)))
+    v = rng.uniform(0.5, 1.0, N) * vc * vhat
+    return np.ascontiguousarray(np.vstack([q, v]))
+
+
+def relnorm(a, b):
+    """Per-orbit norm-relative difference of positions and of velocities: arrays (6, ..., N) -> (2, ..., N)."""
+    dp = np.sqrt(((a[:3] - b[:3]) ** 2).sum(0)) / np.sqrt((b[:3] ** 2).sum(0))
+    dv = np.sqrt(((a[3:] - b[3:]) ** 2).sum(0)) / np.sqrt((b[3:] ** 2).sum(0))
+    return np.stack([dp, dv])
+
+
+@pytest.fixture(scope="session")
+def ref():
+    from oracle import oracle
+    if not oracle.have_ref("strict"):
+        try:
+            oracle.build()
+        except Exception as e:  # pragma: no cover
+            pytest.skip(f"reference oracle not available: {e}")
+    if not oracle.have_ref("strict"):
+        pytest.skip("oracle/_ref/libgala_ref.so missing (needs /root/reference at build time)")
+    return oracle.Ref("strict")

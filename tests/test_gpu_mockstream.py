@@ -1,0 +1,114 @@
+"""GPU parity of the mock-stream path (config C3 at reduced size) against the compiled reference +
+the numpy restatement of the Python-level DF code (oracle/oracle.py)."""
+import numpy as np
+import pytest
+
+import gala_b200 as gb
+from gala_b200.mockstream import DirectNBody
+from conftest import relnorm
+
+pytestmark = pytest.mark.gpu
+
+KMS = gb.KMS_TO_KPC_MYR
+PROG_W0 = np.array([13.0, 0.0, 20.0, 0.0, 130.0 * KMS, 50.0 * KMS])   # tests/dynamics/mockstream/test_mockstream.py:676-678
+
+
+def _prog_orbit(H, n_steps=200, dt=-1.0):
+    t = gb.parse_time_specification(None, dt=dt, n_steps=n_steps)
+    nb = DirectNBody(PROG_W0, [None], external_potential=H.potential, frame=H.frame)
+    return nb.integrate_orbit(t=t, Integrator="dopri853"), t
+
+
+@pytest.mark.parametrize("rng_kind", ["RandomState", "Generator"])
+@pytest.mark.parametrize("gala_modified", [True, False])
+def test_fardal_release_parity(ref, rng_kind, gala_modified):
+    from oracle import oracle
+    pot = gb.MilkyWayPotential2022()
+    H = gb.Hamiltonian(pot)
+    orb, t = _prog_orbit(H, 64)
+    prog = gb.Orbit(pos=orb.pos[:, ::-1, 0], vel=orb.vel[:, ::-1, 0], t=t[::-1], hamiltonian=H)
+    mk = (lambda: np.random.RandomState(42)) if rng_kind == "RandomState" else (lambda: np.random.default_rng(42))
+    npart = np.zeros(65, dtype="i4"); npart[::2] = 3
+    prog_m = np.full(65, 2.5e4); prog_m[10] = 0.0
+    df = gb.FardalStreamDF(gala_modified=gala_modified, random_state=mk())
+    pot.strict_math = True
+    s = df.sample(prog, prog_m, n_particles=npart)
+    x0, v0, t10 = oracle.fardal_release_numpy(ref, pot, prog.pos.T, prog.vel.T, prog.t, prog_m, npart, mk(),
+                                              gala_modified=gala_modified)
+    assert s.pos.shape == (3, x0.shape[0])
+    assert np.array_equal(s.release_time, t10)
+    # rj = (...)**(1/3) goes through libm pow on both sides: agreement to a few ulp of the offsets
+    off = np.sqrt(((x0 - prog.pos.T[np.searchsorted(prog.t, t10)]) ** 2).sum(1))
+    assert np.max(np.abs(s.pos.T - x0) / off[:, None]) < 1e-12
+    assert np.max(np.abs(s.vel.T - v0)) / np.abs(v0).max() < 1e-13
+    assert list(s.lead_trail[:6]) == ["t", "t", "t", "l", "l", "l"]
+
+
+def test_mockstream_dop853_parity(ref):
+    pot = gb.MilkyWayPotential2022()
+    H = gb.Hamiltonian(pot)
+    gen = gb.MockStreamGenerator(gb.FardalStreamDF(gala_modified=True, random_state=np.random.RandomState(42)), H)
+    stream, prog = gen.run(PROG_W0, 2.5e4, dt=-1.0, n_steps=120, n_particles=4, release_every=1)
+    assert stream.pos.shape == (3, 2 * 4 * 121)
+    # oracle: same ICs (re-sampled with the same seed), each particle its own n=6 dop853_step run
+    orb, t = _prog_orbit(H, 120)
+    prog_orb = gb.Orbit(pos=orb.pos[:, ::-1, 0], vel=orb.vel[:, ::-1, 0], t=t[::-1], hamiltonian=H)
+    s0 = gb.FardalStreamDF(gala_modified=True, random_state=np.random.RandomState(42)).sample(
+        prog_orb, 2.5e4, n_particles=4)
+    w0 = np.vstack([s0.pos, s0.vel]).T
+    tf = prog_orb.t[-1]
+    dt0 = prog_orb.t[1] - prog_orb.t[0]
+    out = np.empty_like(w0)
+    for t1 in np.unique(s0.release_time):
+        m = s0.release_time == t1
+        rows, st, rc = ref.dop853_step_rows(H, w0[m], t1, tf, dt0, group=True)
+        assert rc >= 0
+        out[m] = rows
+    got = np.vstack([stream.pos, stream.vel])
+    d = relnorm(got, out.T)
+    print(f"\n[mockstream dop853] median={np.median(d):.2e} max={d.max():.2e}")
+    assert d.max() < 1e-9
+    # the reference's grouped integration (one shared step size per release group) -- measured, not asserted tight
+    outg = np.empty_like(w0)
+    for t1 in np.unique(s0.release_time):
+        m = s0.release_time == t1
+        rows, st, rc = ref.dop853_step_rows(H, w0[m], t1, tf, dt0, group=False)
+        outg[m] = rows
+    dg = relnorm(got, outg.T)
+    print(f"[mockstream dop853 vs reference GROUPED stepping] median={np.median(dg):.2e} max={dg.max():.2e}")
+    assert np.median(dg) < 1e-6
+    # progenitor end state == direct orbit integration (tests/dynamics/mockstream/test_mockstream.py:663-805)
+    direct = H.integrate_orbit(prog_orb[0].w(), t=prog_orb.t, Integrator="dopri853")
+    assert np.allclose(prog.w()[:, 0], direct.w()[:, -1], rtol=1e-10)
+    assert np.allclose(prog.w()[:, 0], PROG_W0, rtol=1e-7)      # integrated back and forth
+
+
+def test_mockstream_leapfrog_parity(ref):
+    pot = gb.MilkyWayPotential2022()
+    H = gb.Hamiltonian(pot)
+    gen = gb.MockStreamGenerator(gb.FardalStreamDF(gala_modified=True, random_state=np.random.RandomState(1)), H)
+    stream, prog = gen.run(PROG_W0, 2.5e4, dt=-1.0, n_steps=150, n_particles=2, Integrator="leapfrog")
+    t = gb.parse_time_specification(None, dt=-1.0, n_steps=150)
+    nb = DirectNBody(PROG_W0, [None], external_potential=pot)
+    orb = nb.integrate_orbit(t=t, Integrator="leapfrog")
+    prog_orb = gb.Orbit(pos=orb.pos[:, ::-1, 0], vel=orb.vel[:, ::-1, 0], t=t[::-1], hamiltonian=H)
+    s0 = gb.FardalStreamDF(gala_modified=True, random_state=np.random.RandomState(1)).sample(prog_orb, 2.5e4, n_particles=2)
+    w0 = np.vstack([s0.pos, s0.vel])
+    tf = prog_orb.t[-1]
+    out = np.empty_like(w0)
+    for t1 in np.unique(s0.release_time):
+        m = s0.release_time == t1
+        n_steps = int((tf - t1) / 1.0 + 0.5)
+        if n_steps == 0:
+            out[:, m] = w0[:, m]
+            continue
+        tt = t1 + np.arange(n_steps + 1) * 1.0
+        out[:, m] = ref.leapfrog(pot, np.ascontiguousarray(w0[:, m]), tt, save_all=False)
+    got = np.vstack([stream.pos, stream.vel])
+    d = relnorm(got, out)
+    print(f"\n[mockstream leapfrog] median={np.median(d):.2e} max={d.max():.2e}")
+    assert d.max() < 1e-12
+    # leapfrog vs dop853 streams are close (tests/dynamics/mockstream/test_mockstream.py:361-412)
+    gen2 = gb.MockStreamGenerator(gb.FardalStreamDF(gala_modified=True, random_state=np.random.RandomState(1)), H)
+    s2, _ = gen2.run(PROG_W0, 2.5e4, dt=-1.0, n_steps=150, n_particles=2)
+    assert np.mean(np.sqrt(((s2.pos - stream.pos) ** 2).sum(0))) < 2.0
