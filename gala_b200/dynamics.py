@@ -37,7 +37,7 @@ class PhaseSpacePosition:
         if _is_torch(self.pos):
             import torch
             return torch.cat([self.pos, self.vel], dim=0)
-        return np.vstack([self.pos, self.vel])
+        return np.concatenate([self.pos, self.vel], axis=0)
 
     @classmethod
     def from_w(cls, w, units=None, **kw):

@@ -188,6 +188,9 @@ int  gb_device_count(void);
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 long gb_launch_count(void);
 const char* gb_version(void);
+/* FP64 DFMA throughput (TFLOP/s, 2 flops per FMA) measured on the current device: the roofline
+ * denominator bench.py reports against (MEASURED_PEAKS.json carries no FP64 figure). */
+double gb_fp64_peak_tflops(int reps);
 
 #ifdef __cplusplus
 }

@@ -56,3 +56,21 @@ def ref():
     if not oracle.have_ref("strict"):
         pytest.skip("oracle/_ref/libgala_ref.so missing (needs /root/reference at build time)")
     return oracle.Ref("strict")
+
+
+def assert_within_floor(d, floor, abs_tol, label="", qs=(0.5, 0.9, 0.99, 1.0), factor=10.0):
+    """Parity assertion anchored on the reference's own reproducibility floor: each quantile of the
+    GPU-vs-reference difference ``d`` must be below ``abs_tol`` or below ``factor`` x the same quantile
+    of ``floor`` (reference built -Ofast vs reference built -O2 -ffp-contract=off, same inputs)."""
+    dq = np.quantile(d, qs)
+    fq = np.quantile(floor, qs) if floor is not None else np.zeros(len(qs))
+    print(f"\n[{label}] GPU-vs-ref q50/90/99/max = " + " ".join(f"{x:.2e}" for x in dq)
+          + (" | ref(-Ofast)-vs-ref(-O2) = " + " ".join(f"{x:.2e}" for x in fq) if floor is not None else ""))
+    for q, a, b in zip(qs, dq, fq):
+        assert a <= max(abs_tol, factor * b), f"{label}: q{q} = {a:.3e} exceeds max({abs_tol:.1e}, {factor}x floor {b:.3e})"
+
+
+@pytest.fixture(scope="session")
+def ref_fast():
+    from oracle import oracle
+    return oracle.Ref("fast") if oracle.have_ref("fast") else None

@@ -1,0 +1,61 @@
+"""`-m "not gpu"`: the C-ABI library loads, exports every symbol include/gala_b200.h declares, and
+its compute entry points fail loudly without a CUDA device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gala_b200 as gb
+from gala_b200 import _abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    txt = open(os.path.join(ROOT, "include", "gala_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(gb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_built_and_exports_header_symbols():
+    L = _abi.lib()
+    names = header_functions()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/gala_b200.h but not exported"
+        assert n in _abi.SIGNATURES, f"{n} has no ctypes signature in gala_b200/_abi.py"
+    for n in _abi.SIGNATURES:
+        assert n in names, f"{n} bound in _abi.py but not declared in the header"
+
+
+def test_struct_layouts_match_header():
+    # sizes implied by the header on LP64: gb_component 4*4 + 8 + 3*8 + 9*8 = 120
+    assert ctypes.sizeof(_abi.gb_component) == 120
+    assert ctypes.sizeof(_abi.gb_potential) == 16
+    assert ctypes.sizeof(_abi.gb_frame) == 32
+    assert ctypes.sizeof(_abi.gb_launch) == 24
+    assert ctypes.sizeof(_abi.gb_dop853_stats) == 32
+
+
+def test_version_and_counters():
+    L = _abi.lib()
+    assert b"sm_100a" in L.gb_version()
+    assert _abi.launch_count() >= 0
+
+
+@pytest.mark.skipif(_abi.device_count() > 0, reason="a CUDA device is present")
+def test_no_cpu_fallback():
+    """Without a GPU every compute call must raise, never silently compute on the CPU."""
+    pot = gb.MilkyWayPotential2022()
+    H = gb.Hamiltonian(pot)
+    q = np.ones((3, 4))
+    w0 = np.ones((6, 4))
+    t = np.arange(4.0)
+    for call in (lambda: pot.gradient(q), lambda: pot.energy(q), lambda: pot.density(q), lambda: H.energy(w0),
+                 lambda: gb.leapfrog_integrate_hamiltonian(H, w0, t),
+                 lambda: gb.ruth4_integrate_hamiltonian(H, w0, t),
+                 lambda: gb.dop853_integrate_hamiltonian(H, w0, t)):
+        with pytest.raises(_abi.GalaB200Error, match="no CUDA device"):
+            call()

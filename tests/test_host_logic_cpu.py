@@ -1,0 +1,138 @@
+"""`-m "not gpu"`: host-side mirror of the reference interface (no compute)."""
+import numpy as np
+import pytest
+
+import gala_b200 as gb
+from gala_b200 import _abi
+from gala_b200.dist import deal_by_work, shard_bounds
+
+
+def test_parse_time_specification_matches_reference_semantics():
+    # integrate/timespec.py:102,137-139: dt, n_steps -> t1 + cumsum, n_steps + 1 entries
+    t = gb.parse_time_specification(None, dt=0.5, n_steps=4)
+    assert np.array_equal(t, [0.0, 0.5, 1.0, 1.5, 2.0])
+    t = gb.parse_time_specification(None, dt=-1.0, n_steps=3, t1=10.0)
+    assert np.array_equal(t, [10.0, 9.0, 8.0, 7.0])
+    t = gb.parse_time_specification(None, dt=0.25, t1=0.0, t2=1.0)
+    assert np.array_equal(t, [0.0, 0.25, 0.5, 0.75])          # forward: t2 not appended (timespec.py:121-129)
+    t = gb.parse_time_specification(None, dt=-0.25, t1=1.0, t2=0.0)
+    assert np.array_equal(t, [1.0, 0.75, 0.5, 0.25, 0.0])     # backward: t2 appended (:109-119)
+    t = gb.parse_time_specification(None, n_steps=5, t1=0.0, t2=1.0)
+    assert np.array_equal(t, np.linspace(0, 1, 5))
+    t = gb.parse_time_specification(None, t=np.array([0, 1, 3]))
+    assert t.dtype == np.float64 and np.array_equal(t, [0.0, 1.0, 3.0])
+    t = gb.parse_time_specification(None, dt=np.array([1.0, 2.0, 3.0]), t1=5.0)
+    assert np.array_equal(t, [5.0, 6.0, 8.0])
+    for bad in (dict(), dict(dt=1.0), dict(dt=1.0, t1=0.0, t2=-1.0), dict(dt=0.0, t1=0.0, t2=1.0)):
+        with pytest.raises(ValueError):
+            gb.parse_time_specification(None, **bad)
+
+
+def test_mw2022_parameter_layout():
+    """MN3 precompute (builtin/core.py:639-666) and component order
+    (builtin/special.py:127-153); [G] + c_parameters is CPotentialWrapper._params."""
+    pot = gb.MilkyWayPotential2022()
+    assert list(pot.keys()) == ["disk", "bulge", "nucleus", "halo"]
+    d = pot["disk"].c_parameters
+    assert np.allclose(d[[0, 3, 6]], [7872306998.700792, -275625221944.33154, 320618418897.9487], rtol=1e-12)
+    assert np.allclose(d[[1, 4, 7]], [1.5259431976529216, 6.782764436261113, 5.894799616164217], rtol=1e-12)
+    assert np.allclose(d[[2, 5, 8]], 0.20663742603550295, rtol=1e-12)
+    assert np.array_equal(d[9:], [4.7717e10, 2.6, 0.3])
+    s = pot.spec()
+    assert s.n == 4
+    assert [s.comps[i].type_id for i in range(4)] == [_abi.POT_MN3, _abi.POT_HERNQUIST, _abi.POT_HERNQUIST,
+                                                      _abi.POT_NFW_SPHERICAL]
+    assert [s.comps[i].n_params for i in range(4)] == [13, 3, 3, 6]
+    assert s.comps[0].params[0] == gb.G_GALACTIC
+    assert all(s.comps[i].do_shift_rotate == 0 for i in range(4))
+    assert np.array_equal([s.comps[3].params[k] for k in range(6)], [gb.G_GALACTIC, 5.5427e11, 15.626, 1, 1, 1])
+
+
+def test_nfw_wrapper_choice_and_shift_rotate_flag():
+    assert gb.NFWPotential(1e11, 12.0)._type_id == _abi.POT_NFW_SPHERICAL          # builtin/core.py:722-741
+    assert gb.NFWPotential(1e11, 12.0, c=0.8)._type_id == _abi.POT_NFW_FLATTENED
+    assert gb.NFWPotential(1e11, 12.0, b=0.9)._type_id == _abi.POT_NFW_TRIAXIAL
+    p = gb.HernquistPotential(1e10, 1.0, origin=[1.0, 0, 0])
+    assert p.spec().comps[0].do_shift_rotate == 1                                   # cpotential.pyx:79-92
+    R = np.array([[0., 1, 0], [-1, 0, 0], [0, 0, 1]])
+    p = gb.HernquistPotential(1e10, 1.0, R=R)
+    c = p.spec().comps[0]
+    assert c.do_shift_rotate == 1 and [c.R[k] for k in range(9)] == list(R.ravel())
+    assert gb.HernquistPotential(1e10, 1.0).spec().comps[0].do_shift_rotate == 0
+    m = gb.NFWPotential.from_circular_velocity(0.2, 15.0).parameters["m"]
+    uu = 1.0
+    assert np.isclose(m, 0.2 ** 2 / uu / (np.log(2) - 0.5) * 15.0 / gb.G_GALACTIC)
+
+
+def test_composite_rules():
+    c = gb.CCompositePotential()
+    c["a"] = gb.HernquistPotential(1e10, 1.0)
+    c["b"] = gb.NFWPotential(1e11, 12.0)
+    assert c.spec().n == 2
+    with pytest.raises(TypeError):
+        c["c"] = c
+    mw = gb.MilkyWayPotential2022()
+    with pytest.raises(ValueError):
+        mw["x"] = gb.HernquistPotential(1e10, 1.0)        # locked (special.py:271)
+    s = gb.HernquistPotential(1e10, 1.0) + gb.NFWPotential(1e11, 12.0)
+    assert isinstance(s, gb.CCompositePotential) and len(s) == 2
+
+
+def test_scf_parameter_vector():
+    S = np.zeros((3, 2, 2)); S[0, 0, 0] = 1.0
+    p = gb.SCFPotential(m=1e12, r_s=20.0, Snlm=S)
+    v = np.concatenate([[p.G], p.c_parameters])
+    assert v[1] == 2 and v[2] == 1 and v[3] == 1e12 and v[4] == 20.0       # scf/bfe.cpp:229-258
+    assert v.size == 5 + 2 * 12 and v[5] == 1.0
+
+
+def test_hamiltonian_dispatch_and_errors():
+    pot = gb.NFWPotential(1e11, 12.0)
+    H = gb.Hamiltonian(pot)
+    assert isinstance(H.frame, gb.StaticFrame) and H.c_enabled
+    Hr = gb.Hamiltonian(pot, gb.ConstantRotatingFrame([0, 0, 0.03]))
+    w0 = np.ones((6, 2))
+    with pytest.raises(TypeError):                      # leapfrog.pyx:64-68
+        gb.leapfrog_integrate_hamiltonian(Hr, w0, np.arange(3.0))
+    with pytest.raises(TypeError):                      # ruth4.pyx:49-52
+        gb.ruth4_integrate_hamiltonian(Hr, w0, np.arange(3.0))
+    with pytest.raises(ValueError):
+        gb.leapfrog_integrate_hamiltonian(H, np.ones((5, 2)), np.arange(3.0))
+    with pytest.raises(ValueError):
+        gb.ConstantRotatingFrame([0.03])
+    with pytest.raises(ValueError):
+        H.integrate_orbit(w0, Integrator="rk5", dt=1.0, n_steps=2)
+
+
+def test_fardal_plan_order():
+    """df.pyx:393-454: per timestep all trailing particles, then all leading; prog_m == 0 skipped."""
+    df = gb.FardalStreamDF(gala_modified=True, random_state=np.random.RandomState(0))
+    idx, sign = df._plan(np.array([1.0, 0.0, 1.0]), np.array([2, 5, 1]))
+    assert list(idx) == [0, 0, 0, 0, 2, 2] and list(sign) == [1, 1, -1, -1, 1, -1]
+    df = gb.FardalStreamDF(gala_modified=True, lead=False)
+    idx, sign = df._plan(np.ones(2), np.array([1, 2]))
+    assert list(idx) == [0, 1, 1] and list(sign) == [1, 1, 1]
+    with pytest.raises(ValueError):
+        gb.FardalStreamDF(lead=False, trail=False)
+
+
+def test_rng_broadcast_draw_equals_scalar_draws():
+    """One broadcast normal(loc[Np,4], scale[Np,4]) consumes the RNG stream exactly like the
+    reference's 4 scalar draws per particle (df.pyx:419-425), for both RNG flavours."""
+    loc = np.broadcast_to([2.0, 0.0, 0.3, 0.0], (50, 4)); scale = np.broadcast_to([0.5, 0.5, 0.5, 0.5], (50, 4))
+    for mk in (lambda: np.random.RandomState(42), lambda: np.random.default_rng(42)):
+        a = mk().normal(loc, scale)
+        r = mk()
+        b = np.array([[r.normal(loc[i, k], scale[i, k]) for k in range(4)] for i in range(50)])
+        assert np.array_equal(a, b)
+
+
+def test_shard_bounds_and_work_dealing():
+    b = shard_bounds(10, 4)
+    assert b == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert shard_bounds(0, 2) == [(0, 0), (0, 0)]
+    work = np.arange(100)[::-1]
+    parts = deal_by_work(work, 8)
+    assert sorted(np.concatenate(parts)) == list(range(100))
+    loads = [work[p].sum() for p in parts]
+    assert max(loads) - min(loads) <= 100

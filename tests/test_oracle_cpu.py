@@ -1,0 +1,292 @@
+"""`-m "not gpu"`: pins the ORACLES before anything is compared with them.
+
+* oracle/_ref/libgala_ref.so  = the reference's own C++ (compiled unmodified) + restated Cython loops
+* oracle/_ref/libgala_port.so = oracle/port.c, our plain-C restatement
+
+against the reference's own known answers that need no astropy: the sympy closed forms of
+builtin/core.py (tests/potential/potential/potential_helpers.py:409-503), the NFW enclosed-mass
+identity (test_all_builtin.py:328-341), Kepler / co-rotating-frame / Jacobi-constant tests
+(tests/potential/hamiltonian/test_with_frame_potential.py:130-177), SCF == Hernquist
+(tests/potential/scf/test_class.py:27-57), the Fortran SCF golden vectors
+(tests/potential/scf/test_accp_fortran.py) and the Plummer doctest numbers
+(docs/dynamics/orbits-in-detail.rst:321-330).  The port is then pinned against the compiled reference.
+"""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gala_b200 as gb
+from conftest import make_ic, relnorm
+from oracle import oracle
+
+G = gb.G_GALACTIC
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def port():
+    if not os.path.exists(os.path.join(oracle._REF_DIR, "libgala_port.so")):
+        oracle.build()
+    return oracle.Port()
+
+
+def checkers(ref, port):
+    return [("ref", ref), ("port", port)]
+
+
+# ---- closed forms (the reference's to_sympy expressions, builtin/core.py) -----------------------------
+def sympy_case(name):
+    import sympy as sy
+    x, y, z = sy.symbols("x y z", real=True)
+    if name == "hernquist":       # builtin/core.py:235-242
+        pot = gb.HernquistPotential(m=1e11, c=0.5); m, c = 1e11, 0.5
+        expr = -G * m / (sy.sqrt(x ** 2 + y ** 2 + z ** 2) + c)
+    elif name == "mn":            # :554-563
+        pot = gb.MiyamotoNagaiPotential(m=6.8e10, a=3.0, b=0.28); m, a, b = 6.8e10, 3.0, 0.28
+        expr = -G * m / sy.sqrt(x ** 2 + y ** 2 + (a + sy.sqrt(z ** 2 + b ** 2)) ** 2)
+    elif name == "nfw":           # :743-756
+        pot = gb.NFWPotential(m=6e11, r_s=15.0, a=1.0, b=0.9, c=0.8); m, rs = 6e11, 15.0
+        uu = sy.sqrt((x / 1.0) ** 2 + (y / 0.9) ** 2 + (z / 0.8) ** 2) / rs
+        expr = -G * m / rs * sy.log(1 + uu) / uu
+    elif name == "bar":           # :1049-1072
+        al = 0.4
+        pot = gb.LongMuraliBarPotential(m=1e10, a=4.0, b=0.8, c=0.25, alpha=al); m, a, b, c = 1e10, 4.0, 0.8, 0.25
+        xx = x * sy.cos(al) + y * sy.sin(al); yy = -x * sy.sin(al) + y * sy.cos(al)
+        Tm = sy.sqrt((a - xx) ** 2 + yy ** 2 + (b + sy.sqrt(c ** 2 + z ** 2)) ** 2)
+        Tp = sy.sqrt((a + xx) ** 2 + yy ** 2 + (b + sy.sqrt(c ** 2 + z ** 2)) ** 2)
+        expr = G * m / (2 * a) * sy.log((xx - a + Tm) / (xx + a + Tp))
+    elif name == "plummer":
+        pot = gb.PlummerPotential(m=1e11, b=1.5)
+        expr = -G * 1e11 / sy.sqrt(x ** 2 + y ** 2 + z ** 2 + 1.5 ** 2)
+    elif name == "isochrone":
+        pot = gb.IsochronePotential(m=1e11, b=1.5)
+        expr = -G * 1e11 / (1.5 + sy.sqrt(x ** 2 + y ** 2 + z ** 2 + 1.5 ** 2))
+    elif name == "jaffe":
+        pot = gb.JaffePotential(m=1e11, c=2.0)
+        r = sy.sqrt(x ** 2 + y ** 2 + z ** 2)
+        expr = -G * 1e11 / 2.0 * sy.log(1 + 2.0 / r)
+    elif name == "kepler":
+        pot = gb.KeplerPotential(m=1e11)
+        expr = -G * 1e11 / sy.sqrt(x ** 2 + y ** 2 + z ** 2)
+    f = sy.lambdify((x, y, z), expr, "numpy")
+    g = sy.lambdify((x, y, z), [sy.diff(expr, v) for v in (x, y, z)], "numpy")
+    lap = sy.lambdify((x, y, z), sum(sy.diff(expr, v, 2) for v in (x, y, z)), "numpy")
+    return pot, f, g, lap
+
+
+@pytest.mark.parametrize("name", ["hernquist", "mn", "nfw", "bar", "plummer", "isochrone", "jaffe", "kepler"])
+def test_against_sympy_closed_forms(ref, port, name):
+    """Energy, gradient and density (via Poisson) of both oracles against the reference's sympy
+    definitions at 64 random points (potential_helpers.py:409-503 uses rtol 1e-5; here 1e-9)."""
+    pot, f, g, lap = sympy_case(name)
+    q = np.random.default_rng(42).uniform(-10, 10, (3, 64)) + 0.1
+    for label, chk in checkers(ref, port):
+        assert np.allclose(chk.energy(pot, q), f(*q), rtol=1e-11), (label, name)
+        assert np.allclose(chk.gradient(pot, q), np.array(g(*q)), rtol=1e-9, atol=1e-30), (label, name)
+        if name not in ("nfw", "kepler"):      # triaxial NFW has no density in the reference (nan_density)
+            dens = lap(*q) / (4 * np.pi * G)
+            assert np.allclose(chk.density(pot, q), dens, rtol=2e-6, atol=1e-8 * np.abs(dens).max()), (label, name)
+
+
+def test_nfw_enclosed_mass_identity(ref, port):
+    """tests/potential/potential/test_all_builtin.py:328-341: M(<r) from dPhi/dr vs the analytic NFW mass."""
+    m, rs = 6e11, 15.0
+    pot = gb.NFWPotential(m=m, r_s=rs)
+    r = np.geomspace(0.1, 300, 50)
+    q = np.vstack([r, 0 * r, 0 * r])
+    analytic = m * (np.log(1 + r / rs) - (r / rs) / (1 + r / rs))
+    for label, chk in checkers(ref, port):
+        menc = r ** 2 * chk.gradient(pot, q)[0] / G
+        assert np.allclose(menc, analytic, rtol=1e-12), label
+
+
+def test_mw2022_is_sum_of_components(ref, port):
+    pot = gb.MilkyWayPotential2022()
+    q = np.random.default_rng(1).normal(0, 10, (3, 100))
+    for label, chk in checkers(ref, port):
+        tot = chk.gradient(pot, q)
+        parts = sum(chk.gradient(p, q) for p in pot.values())
+        assert np.allclose(tot, parts, rtol=1e-13)
+        three = sum(chk.gradient(p, q) for p in pot["disk"].get_three_potentials().values())
+        assert np.allclose(chk.gradient(pot["disk"], q), three, rtol=1e-13)
+
+
+def test_kepler_orbit_closes(ref, port):
+    """tests/integrate/test_pyintegrators.py:96-104: a Kepler orbit returns to its start after one period."""
+    M = 1e11
+    pot = gb.KeplerPotential(m=M)
+    H = gb.Hamiltonian(pot)
+    a = 10.0
+    vc = np.sqrt(G * M / a)
+    w0 = np.array([[a, 0, 0, 0, 0.8 * vc, 0.0]]).T          # eccentric, still bound
+    E = 0.5 * (0.8 * vc) ** 2 - G * M / a
+    a_orb = -G * M / (2 * E)
+    T = 2 * np.pi * np.sqrt(a_orb ** 3 / (G * M))
+    for label, chk in checkers(ref, port):
+        t = np.linspace(0, T, 20001)
+        w = chk.leapfrog(pot, w0, t, save_all=False)
+        assert np.allclose(w[:, 0], w0[:, 0], atol=1e-5 * a), label
+        w = chk.ruth4(H, w0, t[::10].copy(), save_all=False)
+        assert np.allclose(w[:, 0], w0[:, 0], atol=1e-6 * a), label
+        wd, st, rc = chk.dop853(H, w0, np.array([0.0, T / 2, T]), atol=1e-12, rtol=1e-12, nbatch=1)
+        assert rc >= 0 and np.all(st == 1)
+        assert np.allclose(wd[:, -1, 0], w0[:, 0], atol=1e-8 * a), label
+
+
+def test_rotating_frame_known_answers(ref, port):
+    """tests/potential/hamiltonian/test_with_frame_potential.py:130-177: a circular Kepler orbit is
+    stationary in the co-rotating frame (atol 1e-7) and the Jacobi constant is conserved (< 1e-9 at
+    DOP853 rtol=atol=1e-12)."""
+    M = 1e11
+    pot = gb.KeplerPotential(m=M)
+    r0 = 8.0
+    vc = np.sqrt(G * M / r0)
+    Om = vc / r0
+    H = gb.Hamiltonian(pot, gb.ConstantRotatingFrame([0.0, 0.0, Om]))
+    w0 = np.array([[r0, 0, 0, 0, vc, 0.0]]).T            # canonical momentum p = v_inertial
+    t = np.linspace(0, 1000, 201)
+    for label, chk in checkers(ref, port):
+        w, st, rc = chk.dop853(H, w0, t, atol=1e-12, rtol=1e-12, nbatch=1)
+        assert rc >= 0
+        assert np.allclose(w[:3, :, 0], w0[:3], atol=1e-7), label
+    pot2 = gb.MilkyWayPotential2022()
+    H2 = gb.Hamiltonian(pot2, gb.ConstantRotatingFrame([0.0, 0.0, 0.030681]))
+    w0 = make_ic(lambda q: ref.gradient(pot2, q), 16, seed=3)
+    for label, chk in checkers(ref, port):
+        w, st, rc = chk.dop853(H2, w0, t, atol=1e-12, rtol=1e-12, nbatch=1)
+        EJ = chk.hamiltonian_energy(H2, w.reshape(6, -1)).reshape(len(t), -1)
+        assert np.max(np.abs(EJ / EJ[0] - 1)) < 1e-9, label
+
+
+def test_plummer_doctest_numbers(ref, port):
+    """docs/dynamics/orbits-in-detail.rst:240-243,321-330: Plummer(m=1e10, b=1), w0 = [10,0,0] kpc,
+    [0,75,0] km/s, default (leapfrog) integrator, dt=0.1, 1e5 steps: <Lz> = 0.76703412 kpc^2/Myr,
+    pericentre 10.00000005952518 kpc, apocentre 19.390916871970223 kpc, e = 0.31951765618193967."""
+    pot = gb.PlummerPotential(m=1e10, b=1.0)
+    w0 = np.array([[10.0, 0, 0, 0, 75 * gb.KMS_TO_KPC_MYR, 0]]).T
+    t = 0.1 * np.arange(100001)
+    for label, chk in checkers(ref, port):
+        w = chk.leapfrog(pot, w0, t, save_all=True)
+        r = np.sqrt((w[:3, :, 0] ** 2).sum(0))
+        # parabolic refinement of the extrema like Orbit.pericenter()/apocenter() do by interpolation
+        def extremum(sign):
+            i = np.argmax(sign * r[1:-1]) + 1
+            y0, y1, y2 = r[i - 1], r[i], r[i + 1]
+            return y1 - 0.125 * (y2 - y0) ** 2 / (y2 - 2 * y1 + y0)
+        peri, apo = r.min(), extremum(+1)
+        assert abs(peri - 10.00000005952518) < 1e-6, (label, peri)
+        assert abs(apo - 19.390916871970223) < 2e-5, (label, apo)
+        assert abs((apo - peri) / (apo + peri) - 0.31951765618193967) < 2e-6, label
+        Lz = w[0, :, 0] * w[4, :, 0] - w[1, :, 0] * w[3, :, 0]
+        assert np.allclose(Lz, Lz[0], rtol=1e-12)
+        assert abs(Lz.mean() - 0.76703412) < 1e-8
+
+
+# ---- SCF ------------------------------------------------------------------------------------------------
+SCF_SETS = ["simple_hernquist", "multi_hernquist", "simple_nonsph", "random", "wang_zhao"]
+
+
+@pytest.mark.parametrize("name", SCF_SETS)
+def test_scf_fortran_golden_vectors(ref, port, name):
+    """tests/potential/scf/test_accp_fortran.py:77-156 on the committed fixture
+    (tests/golden/scf_fortran.npz, made by tests/golden/make_scf_golden.py): potential and gradient at
+    rtol 1e-6 with G = M = r_s = 1."""
+    d = np.load(os.path.join(GOLD, "scf_fortran.npz"))
+    pot = gb.SCFPotential(m=1.0, r_s=1.0, Snlm=d[name + "_S"], Tnlm=d[name + "_T"], units=gb.dimensionless)
+    assert pot.G == 1.0
+    q = np.ascontiguousarray(d["xyz"].T)
+    for label, chk in checkers(ref, port):
+        np.testing.assert_allclose(chk.energy(pot, q), d[name + "_pot"], rtol=1e-6, err_msg=label)
+        np.testing.assert_allclose(chk.gradient(pot, q).T, d[name + "_grad"], rtol=1e-6, err_msg=label)
+
+
+def test_scf_s000_is_hernquist(ref, port):
+    """tests/potential/scf/test_class.py:27-57: SCF with S000 = 1 is the Hernquist sphere."""
+    S = np.zeros((4, 3, 3)); S[0, 0, 0] = 1.0
+    scf = gb.SCFPotential(m=1e10, r_s=3.0, Snlm=S)
+    hern = gb.HernquistPotential(m=1e10, c=3.0)
+    r = np.geomspace(0.05, 100, 128)
+    rng = np.random.default_rng(0)
+    n = rng.normal(size=(3, 128)); n /= np.sqrt((n ** 2).sum(0))
+    q = r * n
+    for label, chk in checkers(ref, port):
+        np.testing.assert_allclose(chk.energy(scf, q), chk.energy(hern, q), rtol=1e-12, err_msg=label)
+        np.testing.assert_allclose(chk.gradient(scf, q), chk.gradient(hern, q), rtol=1e-9, atol=1e-25, err_msg=label)
+        np.testing.assert_allclose(chk.density(scf, q), chk.density(hern, q), rtol=1e-11, err_msg=label)
+
+
+# ---- the port against the compiled reference -------------------------------------------------------------
+def all_potentials():
+    from test_gpu_parity import potentials
+    return potentials()
+
+
+def test_port_equals_reference_evaluation(ref, port):
+    rng = np.random.default_rng(7)
+    q = rng.normal(0, 10.0, (3, 2000))
+    for name, pot in all_potentials().items():
+        g, g0 = port.gradient(pot, q), ref.gradient(pot, q)
+        assert np.max(np.sqrt(((g - g0) ** 2).sum(0)) / np.sqrt((g0 ** 2).sum(0))) < 4e-16, name
+        assert np.allclose(port.energy(pot, q), ref.energy(pot, q), rtol=1e-15, atol=0), name
+        d, d0 = port.density(pot, q), ref.density(pot, q)
+        ok = np.isfinite(d0)
+        assert np.array_equal(np.isfinite(d), ok)
+        if ok.any():
+            tol = 1e-8 if "bar" in name else 1e-14
+            assert np.max(np.abs(d[ok] - d0[ok])) <= tol * np.abs(d0[ok]).max(), name
+    H = gb.Hamiltonian(all_potentials()["bar_mw2022"], gb.ConstantRotatingFrame([0.001, 0.002, 0.03]))
+    w = rng.normal(0, 8.0, (6, 500)); w[3:] *= 0.02
+    assert np.allclose(port.hamiltonian_energy(H, w), ref.hamiltonian_energy(H, w), rtol=1e-15)
+    assert np.allclose(port.hamiltonian_gradient(H, w), ref.hamiltonian_gradient(H, w), rtol=1e-13, atol=1e-18)
+    assert np.isclose(port.d2_dr2(H.potential, w[:3, 0]), ref.d2_dr2(H.potential, w[:3, 0]), rtol=1e-12)
+
+
+def test_port_equals_reference_integrators(ref, port):
+    pots = all_potentials()
+    pot = pots["mw2022"]
+    w0 = make_ic(lambda q: ref.gradient(pot, q), 300, seed=1, rmin=15.0)
+    t = np.arange(1001, dtype=float)
+    d = relnorm(port.leapfrog(pot, w0, t), ref.leapfrog(pot, w0, t))
+    assert d.max() < 1e-12 and np.median(d) < 1e-15
+    for frame in (gb.StaticFrame(), gb.ConstantRotatingFrame([0, 0, 0.030681])):
+        H = gb.Hamiltonian(pots["bar_mw2022"], frame)
+        d = relnorm(port.ruth4(H, w0, t * 0.5, save_all=False), ref.ruth4(H, w0, t * 0.5, save_all=False))
+        assert d.max() < 1e-12
+        H = gb.Hamiltonian(pot, frame)
+        tt = np.linspace(0, 1000, 200)
+        wp, sp, rcp = port.dop853(H, w0[:, :100], tt, nbatch=1)
+        wr, sr, rcr = ref.dop853(H, w0[:, :100], tt, nbatch=1)
+        assert rcp >= 0 and rcr >= 0 and np.array_equal(sp, sr)
+        assert relnorm(wp, wr).max() < 1e-10
+        rows = np.ascontiguousarray(w0[:, :50].T)
+        a, sa, _ = port.dop853_step_rows(H, rows, 0.0, 800.0, 1.0)
+        b, sb, _ = ref.dop853_step_rows(H, rows, 0.0, 800.0, 1.0, group=True)
+        assert np.array_equal(sa, sb) and relnorm(a.T, b.T).max() < 1e-10
+
+
+def test_long_double_truth_run(ref):
+    """The long-double build of the port arbitrates FP64 differences: the strict reference stays
+    within ~1e-12 of it over 1000 MW2022 leapfrog steps on regular orbits."""
+    ld = oracle.Port(long_double=True)
+    pot = gb.MilkyWayPotential2022()
+    w0 = make_ic(lambda q: ref.gradient(pot, q), 200, seed=5, rmin=15.0)
+    t = np.arange(1001, dtype=float)
+    d = relnorm(ref.leapfrog(pot, w0, t, save_all=False), ld.leapfrog(pot, w0, t, save_all=False))
+    assert np.median(d) < 1e-13 and d.max() < 1e-10
+
+
+def test_dop853_coefficients_match_reference():
+    """Our device / port coefficient tables against the numbers in the reference source, numerically."""
+    ref_src = "/root/reference/src/gala/integrate/cyintegrators/dopri/dop853.cpp"
+    if not os.path.exists(ref_src):
+        pytest.skip("reference tree not present")
+    txt = open(ref_src).read()
+    txt = txt[txt.index("case 1:"):txt.index("facold = 1.0E-4")]
+    refc = {k: float(v) for k, v in re.findall(r"\b([a-z]+[0-9]+)\s*=\s*([-+0-9.Ee]+);", txt)}
+    root = os.path.dirname(GOLD.rstrip("/")).rsplit("/tests", 1)[0]
+    for path in ("gala_b200/csrc/dop853_coeffs.cuh", "oracle/port_dop853_coeffs.h"):
+        mine = {k: float(v) for k, v in re.findall(r"\b([a-z]+[0-9]+)\s*=\s*([-+0-9.Ee]+)", open(os.path.join(root, path)).read())}
+        assert set(mine) == set(refc) and len(refc) == 154
+        assert all(mine[k] == refc[k] for k in refc), path
