@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 SM_FILL = 148 * 2048          # resident threads of one B200 at full occupancy
 
 # algorithmic flops per orbit-step (source-level op counts)
-FLOPS = {"headline": 146, "c1": 46, "c4": 666, "c2": 3970}
+FLOPS = {"headline": 146, "c1": 46, "c4": 666, "c2": 3970, "c5": 3400}
 
 
 def make_ic(N, seed, pot_gradient, rmin=4.0, rmax=50.0):
@@ -105,6 +105,24 @@ def workload(name, n_orbits):
         def units(N_, out):
             ns = stats["nstep"]
             return int(ns.sum().item() if hasattr(ns, "cpu") else ns.sum())
+    elif name == "c5":
+        rng = np.random.default_rng(5)
+        nmax, lmax = 10, 6
+        S = np.zeros((nmax + 1, lmax + 1, lmax + 1)); T = np.zeros_like(S)
+        for n in range(nmax + 1):
+            for l in range(lmax + 1):
+                for m in range(l + 1):
+                    sig = 0.05 / (1 + n + l) ** 2
+                    S[n, l, m] = rng.normal(0, sig)
+                    if m > 0:
+                        T[n, l, m] = rng.normal(0, sig)
+        S[0, 0, 0] = 1.0
+        H = gb.Hamiltonian(gb.SCFPotential(m=1e12, r_s=20.0, Snlm=S, Tnlm=T))
+        t = np.arange(1001, dtype=float)
+        N = n_orbits or 1_250_000           # 10^7 orbits / 8 GPUs
+        desc = f"C5: SCFPotential(nmax=10,lmax=6) leapfrog dt=1Myr 1000 steps final-state-only, {N} orbits/GPU"
+        run = lambda w0, tt: gb.leapfrog_integrate_hamiltonian(H, w0, tt, save_all=0)[1]
+        units = lambda N_, out: N_ * 1000
     else:
         raise SystemExit(f"unknown workload {name}")
     return H, t, N, desc, run, units

@@ -59,6 +59,28 @@ struct Resolved {
     ~Resolved() { if (d_ext) cudaFree(d_ext); }
 };
 
+// SCF coefficients for the device (scf.cuh): (S,T) pairs in [l][m<=l][n] order with the spherical-
+// harmonic normalisation sqrt((2l+1)/(4 pi) (l-m)!/(l+m)!) (what gsl_sf_legendre_sphPlm and the
+// gamma-function ratio of reference bfe_helper.cpp:21,42,72-74 apply per term) folded in.
+// Input layout: params = [G, nmax, lmax, m, r_s, S[n][l][m]..., T[n][l][m]...] (bfe.cpp:229-258,
+// index i = m + (lmax+1)(l + (lmax+1) n), bfe.cpp:160).
+void scf_pack(const double* params, int nmax, int lmax, std::vector<double>& ext) {
+    const int L1 = lmax + 1, ncoef = (nmax + 1) * L1 * L1;
+    const double* S = params + 5;
+    const double* T = params + 5 + ncoef;
+    for (int l = 0; l <= lmax; l++)
+        for (int m = 0; m <= l; m++) {
+            double ratio = 1.;                        // (l-m)!/(l+m)!
+            for (int k = l - m + 1; k <= l + m; k++) ratio /= (double)k;
+            const double nlm = sqrt((2. * l + 1.) / (4. * M_PI) * ratio);
+            for (int n = 0; n <= nmax; n++) {
+                const int i = m + L1 * (l + L1 * n);
+                ext.push_back(S[i] * nlm);
+                ext.push_back(T[i] * nlm);
+            }
+        }
+}
+
 bool sig_matches(const gb_potential* pot, std::initializer_list<int> types) {
     if ((size_t)pot->n_components != types.size()) return false;
     int i = 0;
@@ -102,7 +124,7 @@ int resolve(const gb_potential* pot, Resolved& r, cudaStream_t stream) {
             const int ncoef = (nmax + 1) * (lmax + 1) * (lmax + 1);
             if (c.n_params < 5 + 2 * ncoef) return fail(-12, "SCF: parameter vector shorter than 5 + 2*(nmax+1)(lmax+1)^2");
             if (lmax > 15 || nmax > 63) return fail(-11, "SCF: lmax <= 15 and nmax <= 63 supported");
-            r.ext.insert(r.ext.end(), c.params + 5, c.params + 5 + 2 * ncoef);
+            scf_pack(c.params, nmax, lmax, r.ext);
         }
         d.npar = nsmall;
         if (off + nsmall > GB_MAXP) return fail(-11, "too many potential parameters for the constant bank");

@@ -9,7 +9,7 @@
 #include <stdint.h>
 #include "../../include/gala_b200.h"
 
-#define GB_HAVE_SCF 0   // flipped to 1 when scf.cuh carries the recurrence implementation
+#define GB_HAVE_SCF 1   // flipped to 1 when scf.cuh carries the recurrence implementation
 #define GB_MAXC 8      // components per composite held in the constant bank
 #define GB_MAXP 120    // packed doubles of "small" parameters ([G, ...] of every component)
 
