@@ -78,6 +78,7 @@ SIGNATURES = {
     "gb_launch_count": (C.c_long, []),
     "gb_version": (C.c_char_p, []),
     "gb_fp64_peak_tflops": (C.c_double, [C.c_int]),
+    "gb_math_probe": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, P(gb_launch)]),
 }
 
 _lib = None
@@ -124,6 +125,16 @@ def device_count() -> int:
 
 def launch_count() -> int:
     return lib().gb_launch_count()
+
+
+def math_probe(which: int, x, strict: bool = False):
+    """y = f(x) with the math primitive the selected build uses inside its kernels
+    (0: 1/x, 1: x^-1/2, 2: x^-3/2, 3: ln x); host arrays.  Diagnostic for the test suite."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    o = launch_opts(False, strict=strict)
+    check(lib().gb_math_probe(which, x.ctypes.data, x.size, y.ctypes.data, C.byref(o)))
+    return y
 
 
 def _is_torch_cuda(x) -> bool:

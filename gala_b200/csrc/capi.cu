@@ -52,6 +52,28 @@ int min_npar(int type) {
     }
 }
 
+// Host-derived constants of one component for the fast build (layout: gb_nderived() in
+// gb_device.cuh; consumers: the accum() functions of potentials.cuh).  Pure functions of the
+// parameter vector, evaluated once per call in IEEE double.
+void gb_derive(int type, const double* p, double* d) {
+    switch (type) {
+        case GB_POT_HERNQUIST: case GB_POT_KEPLER: case GB_POT_JAFFE:
+            d[0] = p[0] * p[1]; break;
+        case GB_POT_NFW_SPHERICAL:
+            d[0] = p[0] * p[1]; d[1] = 1. / p[2]; break;
+        case GB_POT_MIYAMOTONAGAI:
+            d[0] = p[0] * p[1]; d[1] = p[3] * p[3]; break;
+        case GB_POT_PLUMMER: case GB_POT_ISOCHRONE:
+            d[0] = p[0] * p[1]; d[1] = p[2] * p[2]; break;
+        case GB_POT_MN3:
+            for (int i = 0; i < 3; i++) { d[i] = p[0] * p[1 + 3 * i]; d[3 + i] = p[3 + 3 * i] * p[3 + 3 * i]; }
+            break;
+        case GB_POT_LONGMURALIBAR:
+            d[0] = p[0] * p[1]; d[1] = sin(p[5]); d[2] = cos(p[5]); d[3] = p[4] * p[4]; break;
+        default: break;
+    }
+}
+
 struct Resolved {
     DevPot P;
     std::vector<double> ext;   // host copy of large parameter blocks (SCF coefficients)
@@ -87,6 +109,8 @@ bool sig_matches(const gb_potential* pot, std::initializer_list<int> types) {
     for (int t : types) {
         const gb_component& c = pot->comp[i++];
         if (c.type_id != t || c.do_shift_rotate || c.n_params != expected_npar(t)) return false;
+        // the compile-time MN3 evaluates sqrt(z^2+b^2) once for the three discs (potentials.cuh)
+        if (t == GB_POT_MN3 && !(c.params[3] == c.params[6] && c.params[6] == c.params[9])) return false;
     }
     return true;
 }
@@ -101,7 +125,7 @@ int resolve(const gb_potential* pot, Resolved& r, cudaStream_t stream) {
     DevPot& P = r.P;
     memset(&P, 0, sizeof(P));
     P.n = pot->n_components;
-    int off = 0;
+    int off = 0, doff = 0;
     for (int i = 0; i < P.n; i++) {
         const gb_component& c = pot->comp[i];
         if (c.type_id < 0 || c.type_id >= GB_POT_NTYPES) return fail(-11, "unknown potential type id");
@@ -130,6 +154,10 @@ int resolve(const gb_potential* pot, Resolved& r, cudaStream_t stream) {
         if (off + nsmall > GB_MAXP) return fail(-11, "too many potential parameters for the constant bank");
         for (int k = 0; k < nsmall; k++) P.par[off + k] = c.params[k];
         off += nsmall;
+        d.doff = doff;
+        if (doff + gb_nderived(c.type_id) > GB_MAXD) return fail(-11, "too many potential components for the constant bank");
+        gb_derive(c.type_id, c.params, &P.drv[doff]);
+        doff += gb_nderived(c.type_id);
         for (int k = 0; k < 3; k++) d.q0[k] = c.q0[k];
         for (int k = 0; k < 9; k++) d.R[k] = c.R[k];
     }
@@ -309,6 +337,19 @@ int gb_energy(const gb_potential* pot, const double* q, double t, size_t N, doub
 }
 int gb_density(const gb_potential* pot, const double* q, double t, size_t N, double* out, const gb_launch* opt) {
     return eval_common(EV_DENSITY, pot, q, t, N, out, opt);
+}
+
+int gb_math_probe(int which, const double* x, size_t N, double* y, const gb_launch* opt) {
+    Ctx c; RET_IF(open_ctx(opt, c));
+    if (which < 0 || which > 3) return fail(-12, "gb_math_probe: which must be 0..3");
+    if (N && (!x || !y)) return fail(-12, "null data pointer");
+    const void* dx; RET_IF(stage_in(c, 0, x, N * sizeof(double), &dx));
+    void* dy; RET_IF(stage_out_alloc(c, 1, y, N * sizeof(double), &dy));
+    cudaError_t e = KCALL(c, math_probe, which, (const double*)dx, N, (double*)dy, c.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "math_probe launch");
+    if (N) g_launches++;
+    RET_IF(stage_out_copy(c, y, dy, N * sizeof(double)));
+    return finish(c);
 }
 
 int gb_hamiltonian_energy(const gb_potential* pot, const gb_frame* fr, const double* w, double t, size_t N,

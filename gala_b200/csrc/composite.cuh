@@ -42,6 +42,18 @@ GB_DEV void gb_comp_gradient(int type, const double* p, const double* e, double 
         default: break;
     }
 }
+#if !GB_STRICT
+template <class Ctx>
+GB_DEV void gb_comp_accum(int type, const double* p, const double* d, const double* e, Ctx& c) {
+    switch (type) {
+#define X(T) case T: PotOf<T>::type::accum(p, d, c); break;
+        GB_FOR_EACH_SIMPLE_TYPE(X)
+#undef X
+        case GB_POT_SCF: PotSCF::gradient(p, e, c.x, c.y, c.z, c.gx, c.gy, c.gz); break;
+        default: break;
+    }
+}
+#endif
 GB_DEV double gb_comp_value(int type, const double* p, const double* e, double x, double y, double z) {
     switch (type) {
 #define X(T) case T: return PotOf<T>::type::value(p, x, y, z);
@@ -74,6 +86,7 @@ template <int SIG> struct Composite;
 template <> struct Composite<SIG_GENERIC> {
     GB_DEV static void gradient(const DevPot& P, double t, double x, double y, double z,
                                 double& gx, double& gy, double& gz) {
+#if GB_STRICT
         gx = 0.; gy = 0.; gz = 0.;
         for (int i = 0; i < P.n; i++) {
             const DevComp& c = P.c[i];
@@ -91,6 +104,30 @@ template <> struct Composite<SIG_GENERIC> {
                 gz += c.R[2] * ax + c.R[5] * ay + c.R[8] * az;
             }
         }
+#else
+        // fast build: unshifted components share one evaluation context (r, 1/r computed once);
+        // a shifted/rotated component gets its own context in its own coordinates.
+        FastCtx<GB_USE_ALL> ctx(x, y, z);
+        for (int i = 0; i < P.n; i++) {
+            const DevComp& c = P.c[i];
+            const double* p = &P.par[c.poff];
+            const double* d = &P.drv[c.doff];
+            const double* e = P.ext + c.eoff;
+            if (!c.shift) {
+                gb_comp_accum(c.type, p, d, e, ctx);
+            } else {
+                double X, Y, Z, ax, ay, az;
+                gb_shift_rotate(c, x, y, z, X, Y, Z);
+                FastCtx<GB_USE_ALL> c2(X, Y, Z);
+                gb_comp_accum(c.type, p, d, e, c2);
+                c2.finish(ax, ay, az);
+                ctx.gx += c.R[0] * ax + c.R[3] * ay + c.R[6] * az;
+                ctx.gy += c.R[1] * ax + c.R[4] * ay + c.R[7] * az;
+                ctx.gz += c.R[2] * ax + c.R[5] * ay + c.R[8] * az;
+            }
+        }
+        ctx.finish(gx, gy, gz);
+#endif
     }
     GB_DEV static double value(const DevPot& P, double t, double x, double y, double z) {
         double v = 0.;
@@ -115,15 +152,27 @@ template <> struct Composite<SIG_GENERIC> {
 };
 
 // ---- compile-time component lists ------------------------------------------------------------
-template <int OFF, int... Ts> struct SeqImpl;
-template <int OFF> struct SeqImpl<OFF> {
+template <int OFF, int DOFF, int... Ts> struct SeqImpl;
+template <int OFF, int DOFF> struct SeqImpl<OFF, DOFF> {
+#if !GB_STRICT
+    static constexpr int USE = 0;
+    template <class Ctx> GB_DEV static void accum(const DevPot&, Ctx&) {}
+#endif
     GB_DEV static void gradient(const DevPot&, double, double, double, double&, double&, double&) {}
     GB_DEV static double value(const DevPot&, double, double, double, double v) { return v; }
     GB_DEV static double density(const DevPot&, double, double, double, double v) { return v; }
 };
-template <int OFF, int T0, int... Ts> struct SeqImpl<OFF, T0, Ts...> {
+template <int OFF, int DOFF, int T0, int... Ts> struct SeqImpl<OFF, DOFF, T0, Ts...> {
     using Pt = typename PotOf<T0>::type;
-    using Next = SeqImpl<OFF + PotOf<T0>::NP, Ts...>;
+    using Next = SeqImpl<OFF + PotOf<T0>::NP, DOFF + gb_nderived(T0), Ts...>;
+#if !GB_STRICT
+    static constexpr int USE = Pt::USE | Next::USE;
+    template <class Ctx> GB_DEV static void accum(const DevPot& P, Ctx& c) {
+        if constexpr (T0 == GB_POT_MN3) PotMN3::template accum_mn3<true>(&P.par[OFF], &P.drv[DOFF], c);   // host verified b1==b2==b3
+        else Pt::accum(&P.par[OFF], &P.drv[DOFF], c);
+        Next::accum(P, c);
+    }
+#endif
     GB_DEV static void gradient(const DevPot& P, double x, double y, double z, double& gx, double& gy, double& gz) {
         Pt::gradient(&P.par[OFF], x, y, z, gx, gy, gz);
         Next::gradient(P, x, y, z, gx, gy, gz);
@@ -138,14 +187,20 @@ template <int OFF, int T0, int... Ts> struct SeqImpl<OFF, T0, Ts...> {
 template <int... Ts> struct Seq {
     GB_DEV static void gradient(const DevPot& P, double t, double x, double y, double z,
                                 double& gx, double& gy, double& gz) {
+#if GB_STRICT
         gx = 0.; gy = 0.; gz = 0.;
-        SeqImpl<0, Ts...>::gradient(P, x, y, z, gx, gy, gz);
+        SeqImpl<0, 0, Ts...>::gradient(P, x, y, z, gx, gy, gz);
+#else
+        FastCtx<SeqImpl<0, 0, Ts...>::USE> c(x, y, z);
+        SeqImpl<0, 0, Ts...>::accum(P, c);
+        c.finish(gx, gy, gz);
+#endif
     }
     GB_DEV static double value(const DevPot& P, double t, double x, double y, double z) {
-        return SeqImpl<0, Ts...>::value(P, x, y, z, 0.);
+        return SeqImpl<0, 0, Ts...>::value(P, x, y, z, 0.);
     }
     GB_DEV static double density(const DevPot& P, double t, double x, double y, double z) {
-        return SeqImpl<0, Ts...>::density(P, x, y, z, 0.);
+        return SeqImpl<0, 0, Ts...>::density(P, x, y, z, 0.);
     }
 };
 

@@ -12,6 +12,7 @@
 #define GB_HAVE_SCF 1   // flipped to 1 when scf.cuh carries the recurrence implementation
 #define GB_MAXC 8      // components per composite held in the constant bank
 #define GB_MAXP 120    // packed doubles of "small" parameters ([G, ...] of every component)
+#define GB_MAXD 40     // packed doubles of host-derived constants (G*m, b^2, 1/r_s, ...) for the fast build
 
 struct DevComp {
     int32_t type;      // gb_pot_type
@@ -19,7 +20,7 @@ struct DevComp {
     int32_t poff;      // offset of this component's [G, ...] in DevPot::par
     int32_t npar;
     int32_t eoff;      // offset of this component's large-parameter block in DevPot::ext
-    int32_t _pad;
+    int32_t doff;      // offset of this component's derived constants in DevPot::drv
     double q0[3];
     double R[9];
 };
@@ -29,6 +30,7 @@ struct DevPot {
     int32_t sig;               // GbSig the host resolved (informational on device)
     DevComp c[GB_MAXC];
     double par[GB_MAXP];
+    double drv[GB_MAXD];       // per component: gb_nderived(type) doubles, see gb_derive() in capi.cu
     const double* ext;         // device-global parameters of "large" components (SCF coefficients)
 };
 
@@ -51,6 +53,19 @@ enum GbSig {
     SIG_COUNT
 };
 
+// Number of host-derived constants per potential type (filled by capi.cu:gb_derive, read by the
+// fast build's accum() functions in potentials.cuh; the strict build ignores them):
+//   Hernquist/Kepler/Jaffe [G m] ; NFW spherical [G m, 1/r_s] ; MiyamotoNagai/Plummer/Isochrone [G m, b^2] ;
+//   MN3 [G m1, G m2, G m3, b1^2, b2^2, b3^2] ; LongMuraliBar [G m, sin(alpha), cos(alpha), c^2].
+constexpr int gb_nderived(int type) {
+    return (type == GB_POT_HERNQUIST || type == GB_POT_KEPLER || type == GB_POT_JAFFE) ? 1
+         : (type == GB_POT_NFW_SPHERICAL || type == GB_POT_MIYAMOTONAGAI || type == GB_POT_PLUMMER ||
+            type == GB_POT_ISOCHRONE) ? 2
+         : (type == GB_POT_MN3) ? 6
+         : (type == GB_POT_LONGMURALIBAR) ? 4
+         : 0;
+}
+
 #ifdef __CUDACC__
 #define GB_DEV __device__ __forceinline__
 
@@ -62,14 +77,10 @@ enum GbSig {
 #define GB_STRICT 0
 #endif
 
-GB_DEV double gb_pow_m1p5(double x) {
+#include "fastmath.cuh"
 #if GB_STRICT
-    return pow(x, -1.5);
-#else
-    const double r = rsqrt(x);
-    return r * r * r;
+GB_DEV double gb_pow_m1p5(double x) { return pow(x, -1.5); }
 #endif
-}
 
 GB_DEV double gb_norm3(double x, double y, double z) { return sqrt(x * x + y * y + z * z); }
 

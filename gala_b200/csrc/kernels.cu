@@ -45,6 +45,18 @@ __global__ void k_eval_scalar(const __grid_constant__ DevPot P, const double* __
                          : C::density(P, t, q[i], q[N + i], q[2 * N + i]);
 }
 
+// diagnostic: the math primitives of this build, one per `which` (tests/test_gpu_fastmath.py)
+__global__ void k_math_probe(int which, const double* __restrict__ x, size_t N, double* __restrict__ y) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double v = x[i];
+#if GB_STRICT
+    y[i] = which == 0 ? 1.0 / v : which == 1 ? 1.0 / sqrt(v) : which == 2 ? gb_pow_m1p5(v) : log(v);
+#else
+    y[i] = which == 0 ? gb_rcp(v) : which == 1 ? gb_rsqrt(v) : which == 2 ? gb_pow_m1p5(v) : gb_log(v);
+#endif
+}
+
 template <class C>
 __global__ void k_ham_energy(const __grid_constant__ DevPot P, const __grid_constant__ DevFrame F,
                              const double* __restrict__ w, double t, size_t N, double* __restrict__ out) {
@@ -89,10 +101,13 @@ k_leapfrog(const __grid_constant__ DevPot P, const double* __restrict__ w0, size
     double gx, gy, gz;
     C::gradient(P, t[0], x, y, z, gx, gy, gz);
     double hx = vx - gx * dt / 2., hy = vy - gy * dt / 2., hz = vz - gz * dt / 2.;
+    // The synchronised velocity is only formed where it is read: every step when SAVE, else on the
+    // last step (same expression, same operands as c_leapfrog_step, leapfrog.pyx:35-51).
+#pragma unroll 1
     for (int j = 1; j < ntimes; j++) {
         x = x + hx * dt; y = y + hy * dt; z = z + hz * dt;
         C::gradient(P, 0., x, y, z, gx, gy, gz);
-        vx = hx - gx * dt / 2.; vy = hy - gy * dt / 2.; vz = hz - gz * dt / 2.;
+        if (SAVE || j == ntimes - 1) { vx = hx - gx * dt / 2.; vy = hy - gy * dt / 2.; vz = hz - gz * dt / 2.; }
         hx = hx - gx * dt; hy = hy - gy * dt; hz = hz - gz * dt;
         if (SAVE) {
             double* o = out + (size_t)j * N + i;
@@ -183,6 +198,11 @@ static inline unsigned nblocks(size_t N, int block) { return (unsigned)((N + blo
 cudaError_t eval_gradient(const DevPot& P, const double* q, double t, size_t N, double* g, int block, cudaStream_t s) {
     if (N == 0) return cudaSuccess;
     GB_SIG_SWITCH(P.sig, (k_eval_gradient<C><<<nblocks(N, block), block, 0, s>>>(P, q, t, N, g)));
+    return cudaGetLastError();
+}
+cudaError_t math_probe(int which, const double* x, size_t N, double* y, cudaStream_t s) {
+    if (N == 0) return cudaSuccess;
+    k_math_probe<<<nblocks(N, 128), 128, 0, s>>>(which, x, N, y);
     return cudaGetLastError();
 }
 cudaError_t eval_energy(const DevPot& P, const double* q, double t, size_t N, double* out, int block, cudaStream_t s) {

@@ -19,6 +19,7 @@ struct Dop853Args {
     namespace NS {                                                                                         \
     cudaError_t eval_gradient(const DevPot& P, const double* q, double t, size_t N, double* g,            \
                               int block, cudaStream_t s);                                                  \
+    cudaError_t math_probe(int which, const double* x, size_t N, double* y, cudaStream_t s);              \
     cudaError_t eval_energy(const DevPot& P, const double* q, double t, size_t N, double* out,            \
                             int block, cudaStream_t s);                                                    \
     cudaError_t eval_density(const DevPot& P, const double* q, double t, size_t N, double* out,           \

@@ -11,11 +11,60 @@
 
 #define GB_PI 3.14159265358979323846
 
+#if !GB_STRICT
+// ---- fast build: fused gradient accumulation ------------------------------------------------------
+// Every potential adds its contribution to ONE evaluation context instead of to (gx,gy,gz):
+//   spherical terms   grad = F(r) q            -> Fs (direct) or Sir (still to be multiplied by 1/r)
+//   axisymmetric disc grad = (Fd x, Fd y, Fdz z)
+//   anything else     -> (gx, gy, gz)
+// so r, 1/r and the final multiplications by (x,y,z) are done once per evaluation, not once per
+// component, and the seeds/refinements of fastmath.cuh replace the library div/sqrt/log.  Same
+// formulas as the reference; only the association of the sums and the rounding of the primitives
+// differ ("two math modes").  `d` points at the component's host-derived
+// constants (gb_nderived()).
+enum { GB_USE_SIR = 1, GB_USE_FS = 2, GB_USE_DISC = 4, GB_USE_GEN = 8, GB_USE_ALL = 15 };
+
+template <int USE> struct FastCtx {
+    double x, y, z, R2, z2, r2, ir, r;
+    double Sir, Fs, Fd, Fdz, gx, gy, gz;
+    GB_DEV FastCtx(double x_, double y_, double z_) : x(x_), y(y_), z(z_) {
+        R2 = fma(y, y, x * x);
+        z2 = z * z;
+        r2 = R2 + z2;
+        ir = gb_rsqrt(r2);      // dead-code-eliminated when no component reads it
+        r = r2 * ir;
+        Sir = 0.; Fs = 0.; Fd = 0.; Fdz = 0.; gx = 0.; gy = 0.; gz = 0.;
+    }
+    GB_DEV void finish(double& ox, double& oy, double& oz) const {
+        double s = 0.;
+        if (USE & GB_USE_SIR) s = (USE & GB_USE_FS) ? fma(Sir, ir, Fs) : Sir * ir;
+        else if (USE & GB_USE_FS) s = Fs;
+        constexpr bool SPH = (USE & (GB_USE_SIR | GB_USE_FS)) != 0;
+        double fxy, fz;
+        if (USE & GB_USE_DISC) { fxy = SPH ? s + Fd : Fd; fz = SPH ? s + Fdz : Fdz; }
+        else { fxy = s; fz = s; }
+        if (USE & GB_USE_GEN) { ox = fma(fxy, x, gx); oy = fma(fxy, y, gy); oz = fma(fz, z, gz); }
+        else { ox = fxy * x; oy = fxy * y; oz = fz * z; }
+    }
+};
+#define GB_ACCUM_VIA_GRADIENT                                                                      \
+    static constexpr int USE = GB_USE_GEN;                                                         \
+    template <class Ctx> GB_DEV static void accum(const double* p, const double*, Ctx& c) {        \
+        gradient(p, c.x, c.y, c.z, c.gx, c.gy, c.gz);                                              \
+    }
+#else
+#define GB_ACCUM_VIA_GRADIENT
+#endif
+
 // ---- Null (builtin_potentials.cpp:18-21) -----------------------------------------------------
 struct PotNull {
     GB_DEV static void gradient(const double*, double, double, double, double&, double&, double&) {}
     GB_DEV static double value(const double*, double, double, double) { return 0.; }
     GB_DEV static double density(const double*, double, double, double) { return 0.; }
+#if !GB_STRICT
+    static constexpr int USE = 0;
+    template <class Ctx> GB_DEV static void accum(const double*, const double*, Ctx&) {}
+#endif
 };
 
 // ---- Kepler (builtin_potentials.cpp:56-85): [G, m] -------------------------------------------
@@ -33,6 +82,12 @@ struct PotKepler {
     GB_DEV static double density(const double*, double x, double y, double z) {
         return (x * x + y * y + z * z == 0.) ? CUDART_INF : 0.;
     }
+#if !GB_STRICT
+    static constexpr int USE = GB_USE_SIR;
+    template <class Ctx> GB_DEV static void accum(const double*, const double* d, Ctx& c) {
+        c.Sir = fma(d[0], c.ir * c.ir, c.Sir);                  // G m / r^3
+    }
+#endif
 };
 
 // ---- Isochrone (builtin_potentials.cpp:128-160): [G, m, b] -----------------------------------
@@ -53,6 +108,15 @@ struct PotIsochrone {
         const double a = sqrt(b * b + r2);
         return p[1] * (3 * (b + a) * a * a - r2 * (b + 3 * a)) / (4 * GB_PI * pow(b + a, 3.) * a * a * a);
     }
+#if !GB_STRICT
+    static constexpr int USE = GB_USE_FS;
+    template <class Ctx> GB_DEV static void accum(const double* p, const double* d, Ctx& c) {
+        const double s2 = c.r2 + d[1];
+        const double is = gb_rsqrt(s2);
+        const double isb = gb_rcp(fma(s2, is, p[2]));           // 1 / (s + b)
+        c.Fs = fma(d[0] * is, isb * isb, c.Fs);                  // G m / (s (s+b)^2)
+    }
+#endif
 };
 
 // ---- Hernquist (builtin_potentials.cpp:211-244): [G, m, c] -----------------------------------
@@ -70,6 +134,13 @@ struct PotHernquist {
         const double rho0 = p[1] / (2 * GB_PI * p[2] * p[2] * p[2]);
         return rho0 / ((r / p[2]) * pow(1 + r / p[2], 3.));
     }
+#if !GB_STRICT
+    static constexpr int USE = GB_USE_SIR;
+    template <class Ctx> GB_DEV static void accum(const double* p, const double* d, Ctx& c) {
+        const double ia = gb_rcp(c.r + p[2]);
+        c.Sir = fma(d[0], ia * ia, c.Sir);                      // G m / ((r+c)^2 r)
+    }
+#endif
 };
 
 // ---- Plummer (builtin_potentials.cpp:292-320): [G, m, b] -------------------------------------
@@ -86,6 +157,12 @@ struct PotPlummer {
         const double r2 = x * x + y * y + z * z;
         return 3 * p[1] / (4 * GB_PI * p[2] * p[2] * p[2]) * pow(1 + r2 / (p[2] * p[2]), -2.5);
     }
+#if !GB_STRICT
+    static constexpr int USE = GB_USE_FS;
+    template <class Ctx> GB_DEV static void accum(const double*, const double* d, Ctx& c) {
+        c.Fs = fma(d[0], gb_pow_m1p5(c.r2 + d[1]), c.Fs);       // G m (r^2+b^2)^-3/2
+    }
+#endif
 };
 
 // ---- Jaffe (builtin_potentials.cpp:365-393): [G, m, c] ---------------------------------------
@@ -105,6 +182,12 @@ struct PotJaffe {
         const double u = r / p[2];
         return rho0 / ((u * u) * ((1 + u) * (1 + u)));
     }
+#if !GB_STRICT
+    static constexpr int USE = GB_USE_SIR;
+    template <class Ctx> GB_DEV static void accum(const double* p, const double* d, Ctx& c) {
+        c.Sir = fma(d[0] * c.ir, gb_rcp(p[2] + c.r), c.Sir);    // G m / (r^2 (c+r))
+    }
+#endif
 };
 
 // ---- NFW family (builtin_potentials.cpp:819-864 spherical, 925-962 flattened, 1028-1072
@@ -133,6 +216,15 @@ struct PotNFWSpherical {
         const double u = r / p[2];
         return rho0 / (u * ((1 + u) * (1 + u)));
     }
+#if !GB_STRICT
+    static constexpr int USE = GB_USE_SIR;
+    // G m [ln(1+u) - u/(1+u)] / r^3, u = r/r_s (same expression as gb_nfw_fac, v_h2/(u^3 r_s^2) = G m/r^3)
+    template <class Ctx> GB_DEV static void accum(const double* p, const double* d, Ctx& c) {
+        const double L = gb_log(fma(c.r, d[1], 1.0));
+        const double h = fma(-c.r, gb_rcp(c.r + p[2]), L);
+        c.Sir = fma(d[0], (c.ir * c.ir) * h, c.Sir);
+    }
+#endif
 };
 struct PotNFWFlattened {
     GB_DEV static double u_of(const double* p, double x, double y, double z) {
@@ -144,6 +236,7 @@ struct PotNFWFlattened {
     }
     GB_DEV static double value(const double* p, double x, double y, double z) { return gb_nfw_value(p, u_of(p, x, y, z)); }
     GB_DEV static double density(const double*, double, double, double) { return CUDART_NAN; }  // nan_density (cybuiltin.pyx:303-311)
+    GB_ACCUM_VIA_GRADIENT
 };
 struct PotNFWTriaxial {
     GB_DEV static double u_of(const double* p, double x, double y, double z) {
@@ -155,6 +248,7 @@ struct PotNFWTriaxial {
     }
     GB_DEV static double value(const double* p, double x, double y, double z) { return gb_nfw_value(p, u_of(p, x, y, z)); }
     GB_DEV static double density(const double*, double, double, double) { return CUDART_NAN; }
+    GB_ACCUM_VIA_GRADIENT
 };
 
 // ---- Miyamoto-Nagai (builtin_potentials.cpp:1287-1332): [G, m, a, b] --------------------------
@@ -178,12 +272,29 @@ GB_DEV double gb_mn_density(double M, double a, double b, double x, double y, do
     const double denom = pow(R2 + (a + sqrt_zb) * (a + sqrt_zb), 2.5) * sqrt_zb * sqrt_zb * sqrt_zb;
     return numer / denom;
 }
+#if !GB_STRICT
+// one Miyamoto-Nagai disc given sq = sqrt(z^2+b^2) and isq = 1/sq: 12 FP64 instructions
+template <class Ctx> GB_DEV void gb_mn_accum(double Gm, double a, double sq, double isq, Ctx& c) {
+    const double zd = a + sq;
+    const double f = gb_pow_m1p5(fma(zd, zd, c.R2));
+    c.Fd = fma(Gm, f, c.Fd);
+    c.Fdz = fma(Gm, f * fma(a, isq, 1.0), c.Fdz);
+}
+#endif
 struct PotMiyamotoNagai {
     GB_DEV static void gradient(const double* p, double x, double y, double z, double& gx, double& gy, double& gz) {
         gb_mn_gradient(p[0], p[1], p[2], p[3], x, y, z, gx, gy, gz);
     }
     GB_DEV static double value(const double* p, double x, double y, double z) { return gb_mn_value(p[0], p[1], p[2], p[3], x, y, z); }
     GB_DEV static double density(const double* p, double x, double y, double z) { return gb_mn_density(p[1], p[2], p[3], x, y, z); }
+#if !GB_STRICT
+    static constexpr int USE = GB_USE_DISC;
+    template <class Ctx> GB_DEV static void accum(const double* p, const double* d, Ctx& c) {
+        const double s2 = c.z2 + d[1];
+        const double isq = gb_rsqrt(s2);
+        gb_mn_accum(d[0], p[2], s2 * isq, isq, c);
+    }
+#endif
 };
 
 // ---- MN3 exponential disk (builtin_potentials.cpp:1390-1441): [G, m1,a1,b1, m2,a2,b2, m3,a3,b3, ...]
@@ -204,6 +315,25 @@ struct PotMN3 {
         for (int i = 0; i < 3; i++) val += gb_mn_density(p[1 + 3 * i], p[2 + 3 * i], p[3 + 3 * i], x, y, z);
         return val;
     }
+#if !GB_STRICT
+    static constexpr int USE = GB_USE_DISC;
+    // SHARED_B: the three discs have the same b (always true for MN3ExponentialDiskPotential,
+    // builtin/core.py:658-664; the host verifies it before resolving a compile-time signature), so
+    // sqrt(z^2+b^2) is evaluated once.
+    template <bool SHARED_B, class Ctx> GB_DEV static void accum_mn3(const double* p, const double* d, Ctx& c) {
+        double sq = 0., isq = 0.;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            if (i == 0 || !SHARED_B) {
+                const double s2 = c.z2 + d[3 + i];
+                isq = gb_rsqrt(s2);
+                sq = s2 * isq;
+            }
+            gb_mn_accum(d[i], p[2 + 3 * i], sq, isq, c);
+        }
+    }
+    template <class Ctx> GB_DEV static void accum(const double* p, const double* d, Ctx& c) { accum_mn3<false>(p, d, c); }
+#endif
 };
 
 // ---- Long & Murali bar (builtin_potentials.cpp:1681-1739): [G, m, a, b, c, alpha] --------------
@@ -242,6 +372,36 @@ struct PotLongMuraliBar {
         const double Tp = sqrt((a + x) * (a + x) + y * y + bcz * bcz);
         return p[0] * p[1] / (2 * a) * log((x - a + Tm) / (x + a + Tp));
     }
+#if !GB_STRICT
+    static constexpr int USE = GB_USE_GEN;
+    // same closed form as gradient() above with sin/cos(alpha) and c^2 from the host-derived block,
+    // 3 rsqrt + 2 rcp seeds instead of 5 sqrt + 5 div
+    template <class Ctx> GB_DEV static void accum(const double* p, const double* d, Ctx& c) {
+        const double sa = d[1], ca = d[2];
+        const double x = fma(c.y, sa, c.x * ca);
+        const double y = fma(c.y, ca, -(c.x * sa));
+        const double a = p[2], b = p[3];
+        const double zc2 = c.z2 + d[3];
+        const double izc = gb_rsqrt(zc2);
+        const double bcz = fma(zc2, izc, b);
+        const double S = fma(bcz, bcz, y * y);
+        const double am = a - x, ap = a + x;
+        const double Tm2 = fma(am, am, S), Tp2 = fma(ap, ap, S);
+        const double iTm = gb_rsqrt(Tm2), iTp = gb_rsqrt(Tp2);
+        const double T = fma(Tm2, iTm, Tp2 * iTp);               // Tp + Tm
+        const double iT = gb_rcp(T);
+        const double fac1 = (0.5 * d[0]) * (iTm * iTp);
+        const double fac2 = gb_rcp(S);
+        const double x4 = 4. * x;
+        const double fac3 = fma(-(x4 * x), iT, T);
+        const double gx = fac1 * (x4 * iT);
+        const double f123 = fac1 * (fac2 * fac3);
+        const double gy = f123 * y;
+        c.gx += fma(gx, ca, -(gy * sa));
+        c.gy += fma(gx, sa, gy * ca);
+        c.gz = fma(f123 * c.z, bcz * izc, c.gz);
+    }
+#endif
     // Density: the reference uses a sympy-generated expression (builtin_potentials.cpp:1741-1811);
     // here it is derived independently as rho = Laplacian(Phi)/(4 pi G) from the closed-form second
     // derivatives of Phi = GM/(2a) * ln((x-a+Tm)/(x+a+Tp)); see DESIGN.md.

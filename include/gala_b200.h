@@ -192,6 +192,12 @@ const char* gb_version(void);
  * denominator bench.py reports against (MEASURED_PEAKS.json carries no FP64 figure). */
 double gb_fp64_peak_tflops(int reps);
 
+/* Diagnostic: y[i] = f(x[i]) with the math primitive the selected build (opt->strict_math) uses
+ * inside the kernels: which = 0: 1/x, 1: x^-1/2, 2: x^-3/2, 3: ln x.  The fast build replaces the
+ * CUDA library expansions by seed + fixed refinement (csrc/fastmath.cuh); this entry lets the test
+ * suite measure their error in ulp on the device. */
+int gb_math_probe(int which, const double* x, size_t N, double* y, const gb_launch* opt);
+
 #ifdef __cplusplus
 }
 #endif

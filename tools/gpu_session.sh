@@ -1,0 +1,22 @@
+#!/bin/bash
+# One GPU-box session: parity tests, the bench lines, launch list and ncu captures -> gpurun_out/<tag>/
+# usage: tools/gpu_session.sh <tag> [steps...]   steps: tests bench ncu_lf ncu_d8 launches
+TAG=${1:-s}; shift
+STEPS=${@:-tests bench ncu_lf ncu_d8 launches}
+OUT=gpurun_out/$TAG; mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.txt 2>&1
+for s in $STEPS; do
+case $s in
+tests)   timeout 1500 python -m pytest tests -m gpu -x -q -s > $OUT/pytest.log 2>&1; echo "pytest exit $?" >> $OUT/pytest.log; tail -5 $OUT/pytest.log ;;
+bench)   for w in headline c1 c2 c4 c5; do
+            extra="--no-cpu-baseline"; [ $w = headline ] && extra=""
+            timeout 900 python bench.py --workload $w --steps 3 --warmup 3 $extra > $OUT/bench_$w.json 2> $OUT/bench_$w.err; tail -1 $OUT/bench_$w.json | cut -c1-400
+         done ;;
+launches) ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/launches_bench.log 2>&1 ;;
+ncu_lf)  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_leapfrog -s 3 -c 1 -o $OUT/prof_leapfrog -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_lf.log 2>&1; tail -2 $OUT/ncu_lf.log ;;
+ncu_d8)  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_dop853 -s 3 -c 1 -o $OUT/prof_dop853 -f python bench.py --workload c2 --orbits 75776 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_d8.log 2>&1; tail -2 $OUT/ncu_d8.log ;;
+ncu_r4)  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_ruth4 -s 3 -c 1 -o $OUT/prof_ruth4 -f python bench.py --workload c4 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_r4.log 2>&1; tail -2 $OUT/ncu_r4.log ;;
+ncu_scf) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_leapfrog -s 3 -c 1 -o $OUT/prof_scf -f python bench.py --workload c5 --orbits 303104 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_scf.log 2>&1; tail -2 $OUT/ncu_scf.log ;;
+*) echo "unknown step $s" ;;
+esac
+done
