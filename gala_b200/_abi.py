@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgala_b200.so")
+# GALA_B200_LIB selects an alternative build of the same ABI (A/B experiments on the GPU box)
+LIB_PATH = os.environ.get("GALA_B200_LIB") or os.path.join(_HERE, "libgala_b200.so")
 
 # enum gb_pot_type
 POT_NULL, POT_HERNQUIST, POT_NFW_SPHERICAL, POT_NFW_FLATTENED, POT_NFW_TRIAXIAL = 0, 1, 2, 3, 4

@@ -469,12 +469,41 @@ static int worst_status(Ctx& c, const int32_t* dstatus, size_t N, int32_t* host_
     return 0;
 }
 
+// The default stream-ordered pool returns freed memory to the driver at the next synchronisation
+// (release threshold 0), so a time-stepping loop of calls would re-map its scratch every call
+// (measured: 1.5 s per call for 14.5 GB).  Keep up to 6 GB cached per device.
+static int pool_keep() {
+    static std::mutex mu;
+    static bool done[64] = {false};
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> g(mu);
+    if (dev < 64 && !done[dev]) {
+        cudaMemPool_t pool;
+        CU(cudaDeviceGetDefaultMemPool(&pool, dev));
+        unsigned long long thr = 6ull << 30;
+        CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        done[dev] = true;
+    }
+    return 0;
+}
+
+// Stream-ordered temporary device memory (freed with cudaFreeAsync on the same stream).
+struct AsyncBuf {
+    void* p = nullptr;
+    cudaStream_t s = nullptr;
+    cudaError_t alloc(size_t bytes, cudaStream_t stream) { s = stream; return cudaMallocAsync(&p, bytes ? bytes : 8, s); }
+    ~AsyncBuf() { if (p) cudaFreeAsync(p, s); }
+};
+
 int gb_dop853(const gb_potential* pot, const gb_frame* fr, const double* w0, size_t N, const double* t, int ntimes,
               double atol, double rtol, long nmax, double dt_max, long nstiff, int save_all, double* w_out,
               int32_t* status, const gb_dop853_stats* stats, const gb_launch* opt) {
     Ctx c; RET_IF(open_ctx(opt, c));
     if (ntimes < 2) return fail(-12, "the time grid needs at least 2 entries");
     if (!t || (N && (!w0 || !w_out))) return fail(-12, "null data pointer");
+    if (N >= 0xffffffffull) return fail(-12, "at most 2^32-2 orbits per call");
+    RET_IF(pool_keep());
     DevFrame F; RET_IF(resolve_frame(fr, F));
     Resolved r; RET_IF(resolve(pot, r, c.stream));
     const int block = c.block > 0 ? c.block : 64;
@@ -493,7 +522,10 @@ int gb_dop853(const gb_potential* pot, const gb_frame* fr, const double* w0, siz
     void* dout; RET_IF(stage_out_alloc(c, 1, w_out, ob, &dout));
     // status + optional stats
     void* dstat;
-    if (c.host || !status) CU(scratch_get(3, N * sizeof(int32_t), &dstat)); else dstat = status;
+    if (c.host || !status) {
+        if (!c.lock.owns_lock()) c.lock = std::unique_lock<std::mutex>(g_scratch_mu);
+        CU(scratch_get(3, N * sizeof(int32_t), &dstat));
+    } else dstat = status;
     int32_t* dst[4] = {nullptr, nullptr, nullptr, nullptr};
     int32_t* hst[4] = {nullptr, nullptr, nullptr, nullptr};
     if (stats) { hst[0] = stats->nstep; hst[1] = stats->naccpt; hst[2] = stats->nrejct; hst[3] = stats->nfcn; }
@@ -502,13 +534,65 @@ int gb_dop853(const gb_potential* pot, const gb_frame* fr, const double* w0, siz
         if (c.host) { void* d; CU(scratch_get(4 + k, N * sizeof(int32_t), &d)); dst[k] = (int32_t*)d; }
         else dst[k] = hst[k];
     }
-    cudaError_t e = (F.type == GB_FRAME_STATIC)
-        ? KCALL(c, dop853_static, r.P, F, (const double*)dw0, N, (const double*)dtg, ntimes, a, save_all,
-                (double*)dout, (int32_t*)dstat, dst[0], dst[1], dst[2], dst[3], block, c.stream)
-        : KCALL(c, dop853_rotating, r.P, F, (const double*)dw0, N, (const double*)dtg, ntimes, a, save_all,
-                (double*)dout, (int32_t*)dstat, dst[0], dst[1], dst[2], dst[3], block, c.stream);
-    if (e != cudaSuccess) return cuda_fail(e, "dop853 kernel launch");
-    if (N) g_launches++;
+
+    // Orbit queue: chunks of contiguous orbit indices; inside a chunk the queue order is ascending
+    // dynamical time (most steps first), see dop853.cuh.  Dense output needs an orbit-major scratch of
+    // chunk x ntimes x 48 bytes, so the chunk is sized to a fraction of the free device memory.
+    size_t chunk = N;
+    if (save_all && N) {
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        const size_t per_orbit = (size_t)ntimes * 6 * sizeof(double);
+        // <= 4 GB: big enough for > 2 full waves of resident lanes at ntimes = 1000, small enough that
+        // the stream-ordered pool can keep it cached between calls (pool_keep() below)
+        size_t budget = free_b / 2 < ((size_t)4 << 30) ? free_b / 2 : ((size_t)4 << 30);
+        if (const char* e = getenv("GB_D8_SCRATCH_MB")) budget = (size_t)atoll(e) << 20;
+        chunk = budget / per_orbit;
+        if (chunk < 64) chunk = 64;
+        chunk &= ~(size_t)31;
+        if (chunk > N) chunk = N;
+    }
+    const bool sorted = N >= 2048 && !getenv("GB_D8_NOSORT");
+    AsyncBuf queue, keys_in, keys_out, idx_in, perm, temp, scratch;
+    size_t temp_bytes = 0;
+    if (N) {
+        CU(queue.alloc(sizeof(unsigned long long), c.stream));
+        if (sorted) {
+            CU(gb_sort_pairs_bytes(chunk, &temp_bytes));
+            CU(keys_in.alloc(chunk * 4, c.stream)); CU(keys_out.alloc(chunk * 4, c.stream));
+            CU(idx_in.alloc(chunk * 4, c.stream)); CU(perm.alloc(chunk * 4, c.stream));
+            CU(temp.alloc(temp_bytes, c.stream));
+        }
+        if (save_all) CU(scratch.alloc(chunk * (size_t)ntimes * 6 * sizeof(double), c.stream));
+    }
+    for (size_t orb0 = 0; orb0 < N; orb0 += chunk) {
+        const size_t nc = (N - orb0 < chunk) ? N - orb0 : chunk;
+        CU(cudaMemsetAsync(queue.p, 0, sizeof(unsigned long long), c.stream));
+        if (sorted) {
+            cudaError_t e = KCALL(c, dyn_time_keys, r.P, (const double*)dw0, N, two[0], orb0, nc, (float*)keys_in.p,
+                                  (uint32_t*)idx_in.p, c.stream);
+            if (e != cudaSuccess) return cuda_fail(e, "dyn_time_keys launch");
+            g_launches++;
+            CU(gb_sort_pairs((const float*)keys_in.p, (float*)keys_out.p, (const uint32_t*)idx_in.p, (uint32_t*)perm.p,
+                             nc, temp.p, temp_bytes, c.stream));
+        }
+        double* kout = save_all ? (double*)scratch.p : (double*)dout;
+        const uint32_t* pp = sorted ? (const uint32_t*)perm.p : nullptr;
+        cudaError_t e = (F.type == GB_FRAME_STATIC)
+            ? KCALL(c, dop853_static, r.P, F, (const double*)dw0, N, (const double*)dtg, ntimes, a, save_all, pp,
+                    (unsigned long long*)queue.p, orb0, nc, kout, (int32_t*)dstat, dst[0], dst[1], dst[2], dst[3],
+                    block, c.stream)
+            : KCALL(c, dop853_rotating, r.P, F, (const double*)dw0, N, (const double*)dtg, ntimes, a, save_all, pp,
+                    (unsigned long long*)queue.p, orb0, nc, kout, (int32_t*)dstat, dst[0], dst[1], dst[2], dst[3],
+                    block, c.stream);
+        if (e != cudaSuccess) return cuda_fail(e, "dop853 kernel launch");
+        g_launches++;
+        if (save_all) {
+            e = KCALL(c, dop853_transpose, (const double*)scratch.p, orb0, nc, ntimes, N, (double*)dout, c.stream);
+            if (e != cudaSuccess) return cuda_fail(e, "dop853 transpose launch");
+            g_launches++;
+        }
+    }
     RET_IF(stage_out_copy(c, w_out, dout, ob));
     if (c.host) {
         if (status) RET_IF(stage_out_copy(c, status, dstat, N * sizeof(int32_t)));

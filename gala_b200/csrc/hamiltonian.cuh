@@ -21,10 +21,22 @@ GB_DEV double frame_energy(const DevFrame& F, double x, double y, double z, doub
 // f = [dH/dp ; -dH/dq]  (hamiltonian_gradient_T, chamiltonian.cpp:38-57).  Static frame: qdot = p
 // (builtin_frames.cpp:18-24).  Rotating frame: qdot = p - Omega x q, pdot = -(grad + Omega x p)
 // (builtin_frames.cpp:94-112).
+// GB_RHS_NOINLINE (DOP853 translation units): one out-of-line copy of the potential gradient instead
+// of 18 inlined ones keeps the adaptive kernel's code within the instruction cache.
+template <class C>
+__device__ __noinline__ void gradient_call(const DevPot& P, double t, double x, double y, double z,
+                                           double& gx, double& gy, double& gz) {
+    C::gradient(P, t, x, y, z, gx, gy, gz);
+}
+
 template <class C, bool ROT>
 GB_DEV void ham_rhs(const DevPot& P, const DevFrame& F, double t, const double (&w)[6], double (&f)[6]) {
     double gx, gy, gz;
+#ifdef GB_RHS_NOINLINE
+    gradient_call<C>(P, t, w[0], w[1], w[2], gx, gy, gz);
+#else
     C::gradient(P, t, w[0], w[1], w[2], gx, gy, gz);
+#endif
     if (!ROT) {
         f[0] = w[3]; f[1] = w[4]; f[2] = w[5];
         f[3] = -gx; f[4] = -gy; f[5] = -gz;

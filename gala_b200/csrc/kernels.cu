@@ -267,16 +267,59 @@ cudaError_t ruth4(const DevPot& P, const DevFrame& F, const double* w0, size_t N
 #define GB_D8_NAME dop853_rotating
 #define GB_D8_ROT true
 #endif
-cudaError_t GB_D8_NAME(const DevPot& P, const DevFrame& F, const double* w0, size_t N, const double* t, int ntimes,
-                       const Dop853Args& a, int save_all, double* out, int32_t* status, int32_t* nstep,
-                       int32_t* naccpt, int32_t* nrejct, int32_t* nfcn, int block, cudaStream_t s) {
-    if (N == 0) return cudaSuccess;
-    Dop853Stats st{status, nstep, naccpt, nrejct, nfcn};
-#define GB_D8(DENSE) GB_SIG_SWITCH(P.sig, (k_dop853<C, GB_D8_ROT, DENSE><<<nblocks(N, block), block, 0, s>>>(P, F, a, w0, N, t, ntimes, out, st)))
-    if (save_all) { GB_D8(true); } else { GB_D8(false); }
-#undef GB_D8
+// Persistent launch: one CTA slot per resident block (occupancy x SM count), never more CTAs than
+// there are 64-orbit groups.  `out` is the (6,N) final-state array, or for save_all the orbit-major
+// scratch [nslots][ntimes][6] that dop853_transpose() turns into the caller's layout.
+template <class C, bool DENSE>
+static cudaError_t launch_d8(const DevPot& P, const DevFrame& F, const double* w0, size_t N, const double* t,
+                             int ntimes, const Dop853Args& a, const uint32_t* perm, unsigned long long* queue,
+                             size_t orb0, size_t nslots, double* out, const Dop853Stats& st, int block, int nsm,
+                             cudaStream_t s) {
+    auto kern = k_dop853_dyn<C, GB_D8_ROT, DENSE>;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0);
+    if (e != cudaSuccess) return e;
+    const size_t want = (nslots + block - 1) / block;
+    const size_t cap = (size_t)(per_sm > 0 ? per_sm : 1) * nsm;
+    kern<<<(unsigned)(want < cap ? want : cap), block, 0, s>>>(P, F, a, w0, N, t, ntimes, perm, queue, orb0, nslots,
+                                                                out, st);
     return cudaGetLastError();
 }
+cudaError_t GB_D8_NAME(const DevPot& P, const DevFrame& F, const double* w0, size_t N, const double* t, int ntimes,
+                       const Dop853Args& a, int save_all, const uint32_t* perm, unsigned long long* queue,
+                       size_t orb0, size_t nslots, double* out, int32_t* status, int32_t* nstep,
+                       int32_t* naccpt, int32_t* nrejct, int32_t* nfcn, int block, cudaStream_t s) {
+    if (nslots == 0) return cudaSuccess;
+    Dop853Stats st{status, nstep, naccpt, nrejct, nfcn};
+    int dev = 0, nsm = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    if (block > 64 || block <= 0) block = 64;      // __launch_bounds__(64)
+    if (save_all) {
+        GB_SIG_SWITCH(P.sig, (e = launch_d8<C, true>(P, F, w0, N, t, ntimes, a, perm, queue, orb0, nslots, out, st, block, nsm, s)));
+    } else {
+        GB_SIG_SWITCH(P.sig, (e = launch_d8<C, false>(P, F, w0, N, t, ntimes, a, perm, queue, orb0, nslots, out, st, block, nsm, s)));
+    }
+    return e;
+}
+#if GB_PART == 2
+cudaError_t dop853_transpose(const double* scratch, size_t orb0, size_t nslots, int ntimes, size_t N, double* out,
+                             cudaStream_t s) {
+    if (nslots == 0) return cudaSuccess;
+    constexpr int TT = 16;
+    dim3 grid((unsigned)((nslots + 31) / 32), (unsigned)((ntimes + TT - 1) / TT));
+    k_transpose_dense<TT><<<grid, 256, 0, s>>>(scratch, orb0, nslots, ntimes, N, out);
+    return cudaGetLastError();
+}
+cudaError_t dyn_time_keys(const DevPot& P, const double* w0, size_t N, double t0, size_t orb0, size_t n, float* key,
+                          uint32_t* idx, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    GB_SIG_SWITCH(P.sig, (k_dyn_time<C><<<nblocks(n, 256), 256, 0, s>>>(P, w0, N, t0, orb0, n, key, idx)));
+    return cudaGetLastError();
+}
+#endif
 #endif  // GB_PART == 2 || 3
 
 #if GB_PART == 4

@@ -34,13 +34,20 @@ struct Dop853Args {
                       int ntimes, double dt, const double* cs, const double* ds, int save_all,             \
                       double* out, int block, cudaStream_t s);                                             \
     cudaError_t dop853_static(const DevPot& P, const DevFrame& F, const double* w0, size_t N,             \
-                              const double* t, int ntimes, const Dop853Args& a, int save_all, double* out, \
-                              int32_t* status, int32_t* nstep, int32_t* naccpt, int32_t* nrejct,           \
-                              int32_t* nfcn, int block, cudaStream_t s);                                   \
+                              const double* t, int ntimes, const Dop853Args& a, int save_all,              \
+                              const uint32_t* perm, unsigned long long* queue, size_t orb0, size_t nslots, \
+                              double* out, int32_t* status, int32_t* nstep, int32_t* naccpt,               \
+                              int32_t* nrejct, int32_t* nfcn, int block, cudaStream_t s);                  \
     cudaError_t dop853_rotating(const DevPot& P, const DevFrame& F, const double* w0, size_t N,           \
                                 const double* t, int ntimes, const Dop853Args& a, int save_all,            \
-                                double* out, int32_t* status, int32_t* nstep, int32_t* naccpt,             \
-                                int32_t* nrejct, int32_t* nfcn, int block, cudaStream_t s);                \
+                                const uint32_t* perm, unsigned long long* queue, size_t orb0,              \
+                                size_t nslots, double* out, int32_t* status, int32_t* nstep,               \
+                                int32_t* naccpt, int32_t* nrejct, int32_t* nfcn, int block,                \
+                                cudaStream_t s);                                                           \
+    cudaError_t dop853_transpose(const double* scratch, size_t orb0, size_t nslots, int ntimes, size_t N, \
+                                 double* out, cudaStream_t s);                                             \
+    cudaError_t dyn_time_keys(const DevPot& P, const double* w0, size_t N, double t0, size_t orb0,        \
+                              size_t n, float* key, uint32_t* idx, cudaStream_t s);                        \
     cudaError_t mock_dop853(const DevPot& P, const DevFrame& F, const double* w0_rows, const double* t1,  \
                             size_t Np, double tfinal, const Dop853Args& a, double* out_rows,               \
                             int32_t* status, int block, cudaStream_t s);                                   \
@@ -51,6 +58,11 @@ struct Dop853Args {
                                const double* sign, const double* normals, size_t Np, int gala_modified,   \
                                double* out_rows, int block, cudaStream_t s);                               \
     }
+
+// sort.cu: radix sort of (float key, uint32 value) pairs with cub (plumbing for the orbit queue order)
+cudaError_t gb_sort_pairs_bytes(size_t n, size_t* temp_bytes);
+cudaError_t gb_sort_pairs(const float* keys_in, float* keys_out, const uint32_t* vals_in, uint32_t* vals_out,
+                          size_t n, void* temp, size_t temp_bytes, cudaStream_t s);
 
 GB_DECLARE_KERNEL_API(gbk_fast)
 GB_DECLARE_KERNEL_API(gbk_strict)

@@ -58,16 +58,22 @@ def ref():
     return oracle.Ref("strict")
 
 
-def assert_within_floor(d, floor, abs_tol, label="", qs=(0.5, 0.9, 0.99, 1.0), factor=10.0):
+def assert_within_floor(d, floor, abs_tol, label="", qs=(0.5, 0.9, 0.99, 1.0), factor=10.0, max_factor=None):
     """Parity assertion anchored on the reference's own reproducibility floor: each quantile of the
     GPU-vs-reference difference ``d`` must be below ``abs_tol`` or below ``factor`` x the same quantile
-    of ``floor`` (reference built -Ofast vs reference built -O2 -ffp-contract=off, same inputs)."""
+    of ``floor`` (reference built -Ofast vs reference built -O2 -ffp-contract=off, same inputs).
+    ``max_factor`` (default = factor) applies to the q = 1.0 entry only: the maximum over N orbits is
+    a single-orbit statistic, and for chaotic orbits (10^4 leapfrog steps through the MW2022 disc) two
+    rounding-level perturbations of the same orbit set differ there by more than 10x between
+    themselves (measured: strict GPU 2.3e-4, fast GPU 1.0e-3, reference -Ofast 7.7e-5 for the same
+    2000 orbits whose q50/q90/q99 agree to 10 %)."""
     dq = np.quantile(d, qs)
     fq = np.quantile(floor, qs) if floor is not None else np.zeros(len(qs))
     print(f"\n[{label}] GPU-vs-ref q50/90/99/max = " + " ".join(f"{x:.2e}" for x in dq)
           + (" | ref(-Ofast)-vs-ref(-O2) = " + " ".join(f"{x:.2e}" for x in fq) if floor is not None else ""))
     for q, a, b in zip(qs, dq, fq):
-        assert a <= max(abs_tol, factor * b), f"{label}: q{q} = {a:.3e} exceeds max({abs_tol:.1e}, {factor}x floor {b:.3e})"
+        f = max_factor if (max_factor is not None and q == 1.0) else factor
+        assert a <= max(abs_tol, f * b), f"{label}: q{q} = {a:.3e} exceeds max({abs_tol:.1e}, {f}x floor {b:.3e})"
 
 
 @pytest.fixture(scope="session")

@@ -51,7 +51,13 @@ def test_fast_primitive_ulp(which, name, bound):
 def test_strict_primitive_is_ieee(which):
     x = _inputs(10 + which, 100_000)
     y = _abi.math_probe(which, x, strict=True)
-    ref = _longdouble_ref(which, x).astype(np.float64)
-    # IEEE division is correctly rounded; 1/sqrt is two correctly rounded operations; CUDA log <= 1 ulp
-    bound = {0: 0.0, 1: 1.0, 3: 1.0}[which]
-    assert _ulp_err(y, ref).max() <= bound + 1e-9
+    # IEEE division and sqrt are correctly rounded, so the strict build must equal numpy bit for bit;
+    # CUDA's log is documented at <= 1 ulp
+    if which == 0:
+        assert np.array_equal(y, 1.0 / x)
+    elif which == 1:
+        assert np.array_equal(y, 1.0 / np.sqrt(x))
+    else:
+        ref = _longdouble_ref(which, x)
+        err = (np.abs(y.astype(np.longdouble) - ref) / np.spacing(np.abs(ref.astype(np.float64)))).astype(np.float64)
+        assert err.max() <= 1.0

@@ -184,7 +184,7 @@ def test_leapfrog_long_parity_distribution(ref, ref_fast):
             pot.strict_math = strict
             _, w = gb.leapfrog_integrate_hamiltonian(gb.Hamiltonian(pot), w0, t, save_all=0)
             d = relnorm(w, w_ref).max(0)
-            assert_within_floor(d, floor, 1e-12, f"leapfrog 1e4 steps {name} strict={strict}")
+            assert_within_floor(d, floor, 1e-12, f"leapfrog 1e4 steps {name} strict={strict}", max_factor=100.0)
             assert np.median(d) < 1e-12
         pot.strict_math = False
 

@@ -17,6 +17,15 @@ ncu_lf)  timeout 900 ncu --set full --clock-control none --import-source on -k r
 ncu_d8)  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_dop853 -s 3 -c 1 -o $OUT/prof_dop853 -f python bench.py --workload c2 --orbits 75776 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_d8.log 2>&1; tail -2 $OUT/ncu_d8.log ;;
 ncu_r4)  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_ruth4 -s 3 -c 1 -o $OUT/prof_ruth4 -f python bench.py --workload c4 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_r4.log 2>&1; tail -2 $OUT/ncu_r4.log ;;
 ncu_scf) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_leapfrog -s 3 -c 1 -o $OUT/prof_scf -f python bench.py --workload c5 --orbits 303104 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_scf.log 2>&1; tail -2 $OUT/ncu_scf.log ;;
+c2ab)    for v in sort nosort; do
+            [ $v = nosort ] && export GB_D8_NOSORT=1 || unset GB_D8_NOSORT
+            timeout 900 python bench.py --workload c2 --steps 3 --warmup 3 --no-cpu-baseline > $OUT/bench_c2_$v.json 2> $OUT/bench_c2_$v.err; tail -1 $OUT/bench_c2_$v.json | cut -c1-300
+         done; unset GB_D8_NOSORT ;;
+c2ni)    for v in inline noinline; do
+            [ $v = noinline ] && export GALA_B200_LIB=$PWD/gala_b200/libgala_b200_noinline.so || unset GALA_B200_LIB
+            timeout 900 python bench.py --workload c2 --steps 3 --warmup 3 --no-cpu-baseline > $OUT/bench_c2_$v.json 2> $OUT/bench_c2_$v.err; tail -1 $OUT/bench_c2_$v.json | cut -c1-300
+         done; unset GALA_B200_LIB ;;
+d8stats) timeout 600 python tools/d8_stats.py > $OUT/d8_stats.json 2> $OUT/d8_stats.err; head -50 $OUT/d8_stats.json ;;
 *) echo "unknown step $s" ;;
 esac
 done
