@@ -70,14 +70,14 @@ def workload(name, n_orbits):
         t = np.arange(1001, dtype=float)
         N = n_orbits or 10 * SM_FILL
         desc = f"MilkyWayPotential2022 leapfrog dt=1Myr 1000 steps final-state-only, {N} orbits/GPU"
-        run = lambda w0, tt: gb.leapfrog_integrate_hamiltonian(H, w0, tt, save_all=0)[1]
+        run = lambda w0, tt, out=None: gb.leapfrog_integrate_hamiltonian(H, w0, tt, save_all=0, out=out)[1]
         units = lambda N_, out: N_ * 1000
     elif name == "c1":
         H = gb.Hamiltonian(gb.NFWPotential(m=1e11, r_s=12.0))
         t = np.arange(1001, dtype=float)
         N = n_orbits or 10_000
         desc = f"C1: NFWPotential(m=1e11,r_s=12) leapfrog dt=1Myr 1000 steps save_all, {N} orbits/GPU"
-        run = lambda w0, tt: gb.leapfrog_integrate_hamiltonian(H, w0, tt, save_all=1)[1]
+        run = lambda w0, tt, out=None: gb.leapfrog_integrate_hamiltonian(H, w0, tt, save_all=1, out=out)[1]
         units = lambda N_, out: N_ * 1000
     elif name == "c4":
         pot = gb.CCompositePotential()
@@ -88,7 +88,7 @@ def workload(name, n_orbits):
         t = np.arange(1001) * 0.5
         N = n_orbits or 4 * SM_FILL
         desc = f"C4: LongMuraliBar+MW2022 Ruth4 dt=0.5Myr 1000 steps ConstantRotatingFrame final-state, {N} orbits/GPU"
-        run = lambda w0, tt: gb.ruth4_integrate_hamiltonian(H, w0, tt, save_all=0, allow_rotating_frame=True)[1]
+        run = lambda w0, tt, out=None: gb.ruth4_integrate_hamiltonian(H, w0, tt, save_all=0, allow_rotating_frame=True, out=out)[1]
         units = lambda N_, out: N_ * 1000
     elif name == "c2":
         H = gb.Hamiltonian(gb.MilkyWayPotential2022())
@@ -97,7 +97,7 @@ def workload(name, n_orbits):
         desc = f"C2: MW2022 DOP853 atol=rtol=1e-10, 1000 dense-output times, {N} orbits/GPU (chunk of the 1e6)"
         stats = {}
 
-        def run(w0, tt):
+        def run(w0, tt, out=None):
             res = gb.dop853_integrate_hamiltonian(H, w0, tt, save_all=1, return_status=True)
             stats["nstep"] = res[2]["nstep"]
             return res[1]
@@ -121,7 +121,7 @@ def workload(name, n_orbits):
         t = np.arange(1001, dtype=float)
         N = n_orbits or 1_250_000           # 10^7 orbits / 8 GPUs
         desc = f"C5: SCFPotential(nmax=10,lmax=6) leapfrog dt=1Myr 1000 steps final-state-only, {N} orbits/GPU"
-        run = lambda w0, tt: gb.leapfrog_integrate_hamiltonian(H, w0, tt, save_all=0)[1]
+        run = lambda w0, tt, out=None: gb.leapfrog_integrate_hamiltonian(H, w0, tt, save_all=0, out=out)[1]
         units = lambda N_, out: N_ * 1000
     else:
         raise SystemExit(f"unknown workload {name}")
@@ -324,13 +324,16 @@ def main():
         pin = torch.empty(w0_host.shape, dtype=torch.float64).pin_memory()
         pin.numpy()[...] = w0_host
         w0_pinned = pin.numpy()
-        for _ in range(2):
-            out_h = run(w0_pinned, t)
+        out_h = run(w0_pinned, t)
+        # the result lands in a caller-provided page-locked array (gb.pinned_empty), as the inputs do:
+        # with pageable arrays the driver stages every copy and page-faults the fresh result buffer
+        out_pin = gb.pinned_empty(np.asarray(out_h).shape) if args.workload != "c2" else None
+        out_h = run(w0_pinned, t, out_pin)
         e2e_units = 0
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            out_h = run(w0_pinned, t)          # returns after the D2H copy completed
+            out_h = run(w0_pinned, t, out_pin)   # returns after the D2H copy completed
             e2e_units += units(N, out_h)
         torch.cuda.synchronize()
         el = time.perf_counter() - t0

@@ -10,7 +10,7 @@ from .units import galactic, dimensionless, G_GALACTIC, KMS_TO_KPC_MYR
 from .potential import *          # noqa: F401,F403
 from .frame import StaticFrame, ConstantRotatingFrame
 from .dynamics import PhaseSpacePosition, Orbit, MockStream
-from .integrate import (parse_time_specification, LeapfrogIntegrator, Ruth4Integrator, DOPRI853Integrator,
+from .integrate import (pinned_empty, parse_time_specification, LeapfrogIntegrator, Ruth4Integrator, DOPRI853Integrator,
                         leapfrog_integrate_hamiltonian, ruth4_integrate_hamiltonian,
                         dop853_integrate_hamiltonian)
 from .hamiltonian import Hamiltonian

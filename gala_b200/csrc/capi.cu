@@ -196,7 +196,7 @@ struct Scratch {
     size_t cap = 0;
     int dev = -1;
 };
-constexpr int NSLOT = 8;
+constexpr int NSLOT = 16;
 std::mutex g_scratch_mu;
 Scratch g_scratch[NSLOT];
 
@@ -386,6 +386,34 @@ int gb_hamiltonian_gradient(const gb_potential* pot, const gb_frame* fr, const d
     return finish(c);
 }
 
+// Two side streams per device for the chunked HOST pipeline (created once, never destroyed).
+struct SideStreams { cudaStream_t s[2] = {nullptr, nullptr}; cudaEvent_t ev[3] = {nullptr, nullptr, nullptr}; };
+static int side_streams(SideStreams** out) {
+    static std::mutex mu;
+    static SideStreams tab[64];
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    if (dev >= 64) return fail(-10, "device ordinal >= 64");
+    std::lock_guard<std::mutex> g(mu);
+    SideStreams& S = tab[dev];
+    if (!S.s[0]) {
+        for (int k = 0; k < 2; k++) CU(cudaStreamCreateWithFlags(&S.s[k], cudaStreamNonBlocking));
+        for (int k = 0; k < 3; k++) CU(cudaEventCreateWithFlags(&S.ev[k], cudaEventDisableTiming));
+    }
+    *out = &S;
+    return 0;
+}
+
+static cudaError_t launch_fixed(Ctx& c, bool is_ruth4, const DevPot& P, const DevFrame& F, const double* dw0, size_t n,
+                                const double* dt_dev, int ntimes, double dt, int save_all, double* dout, int block,
+                                cudaStream_t st) {
+    if (!is_ruth4)
+        return KCALL(c, leapfrog, P, dw0, n, dt_dev, ntimes, dt, save_all, dout, block, st);
+    double cs[4], ds[4];
+    ruth4_coeffs(cs, ds);
+    return KCALL(c, ruth4, P, F, dw0, n, dt_dev, ntimes, dt, cs, ds, save_all, dout, block, st);
+}
+
 static int fixed_step_common(bool is_ruth4, const gb_potential* pot, const gb_frame* fr, const double* w0, size_t N,
                              const double* t, int ntimes, int save_all, double* w_out, const gb_launch* opt) {
     Ctx c; RET_IF(open_ctx(opt, c));
@@ -397,9 +425,7 @@ static int fixed_step_common(bool is_ruth4, const gb_potential* pot, const gb_fr
     Resolved r; RET_IF(resolve(pot, r, c.stream));
     const int block = c.block > 0 ? c.block : 128;
     // t is always read on the host for dt (it is tiny); the kernels take dt by value
-    std::vector<double> th;
     double dt;
-    const double* dt_dev = nullptr;
     if (c.host) { dt = t[1] - t[0]; }
     else {
         double two[2];
@@ -407,19 +433,53 @@ static int fixed_step_common(bool is_ruth4, const gb_potential* pot, const gb_fr
         CU(cudaStreamSynchronize(c.stream));
         dt = two[1] - two[0];
     }
-    const void* dw0; RET_IF(stage_in(c, 0, w0, 6 * N * sizeof(double), &dw0));
     const void* dtg; RET_IF(stage_in(c, 2, t, (size_t)ntimes * sizeof(double), &dtg));
-    dt_dev = (const double*)dtg;
-    const size_t ob = (save_all ? (size_t)ntimes : 1) * 6 * N * sizeof(double);
-    void* dout; RET_IF(stage_out_alloc(c, 1, w_out, ob, &dout));
-    cudaError_t e;
-    if (!is_ruth4) {
-        e = KCALL(c, leapfrog, r.P, (const double*)dw0, N, dt_dev, ntimes, dt, save_all, (double*)dout, block, c.stream);
-    } else {
-        double cs[4], ds[4];
-        ruth4_coeffs(cs, ds);
-        e = KCALL(c, ruth4, r.P, F, (const double*)dw0, N, dt_dev, ntimes, dt, cs, ds, save_all, (double*)dout, block, c.stream);
+    const double* dt_dev = (const double*)dtg;
+    const size_t rows = save_all ? (size_t)ntimes : 1;       // output rows per phase-space component
+
+    // HOST buffers, many orbits: orbit-index chunks pipelined over two streams, so the H2D copy of
+    // chunk k+1 and the D2H copy of chunk k-1 overlap the kernel of chunk k (the (6,N) layout makes a
+    // chunk of orbits a 2-D copy: 6 [x ntimes] rows of nb doubles with a pitch of N doubles).
+    const size_t kPipeMin = 1 << 16;
+    if (c.host && N >= kPipeMin && !getenv("GB_NO_PIPELINE")) {
+        SideStreams* S; RET_IF(side_streams(&S));
+        size_t nb = (N + 7) / 8;                                   // ~8 chunks
+        const size_t cap = ((size_t)256 << 20) / (rows * 6 * sizeof(double));   // <= 256 MB of output per chunk
+        if (nb > cap) nb = cap;
+        if (nb < 16384) nb = 16384;
+        nb = (nb + 127) & ~(size_t)127;
+        void *din[2], *dou[2];
+        for (int k = 0; k < 2; k++) {
+            CU(scratch_get(8 + k, 6 * nb * sizeof(double), &din[k]));
+            CU(scratch_get(10 + k, rows * 6 * nb * sizeof(double), &dou[k]));
+        }
+        CU(cudaEventRecord(S->ev[2], c.stream));                   // t grid (and SCF coefficients) staged
+        for (int k = 0; k < 2; k++) CU(cudaStreamWaitEvent(S->s[k], S->ev[2], 0));
+        int k = 0;
+        for (size_t a0 = 0; a0 < N; a0 += nb, k ^= 1) {
+            const size_t n = (N - a0 < nb) ? N - a0 : nb;
+            cudaStream_t st = S->s[k];
+            CU(cudaMemcpy2DAsync(din[k], n * sizeof(double), w0 + a0, N * sizeof(double), n * sizeof(double), 6,
+                                 cudaMemcpyHostToDevice, st));
+            cudaError_t e = launch_fixed(c, is_ruth4, r.P, F, (const double*)din[k], n, dt_dev, ntimes, dt, save_all,
+                                         (double*)dou[k], block, st);
+            if (e != cudaSuccess) return cuda_fail(e, "integrator kernel launch");
+            g_launches++;
+            CU(cudaMemcpy2DAsync(w_out + a0, N * sizeof(double), dou[k], n * sizeof(double), n * sizeof(double),
+                                 6 * rows, cudaMemcpyDeviceToHost, st));
+        }
+        for (int q = 0; q < 2; q++) {
+            CU(cudaEventRecord(S->ev[q], S->s[q]));
+            CU(cudaStreamWaitEvent(c.stream, S->ev[q], 0));
+        }
+        return finish(c);       // synchronises c.stream, which now depends on both side streams
     }
+
+    const void* dw0; RET_IF(stage_in(c, 0, w0, 6 * N * sizeof(double), &dw0));
+    const size_t ob = rows * 6 * N * sizeof(double);
+    void* dout; RET_IF(stage_out_alloc(c, 1, w_out, ob, &dout));
+    cudaError_t e = launch_fixed(c, is_ruth4, r.P, F, (const double*)dw0, N, dt_dev, ntimes, dt, save_all,
+                                 (double*)dout, block, c.stream);
     if (e != cudaSuccess) return cuda_fail(e, "integrator kernel launch");
     if (N) g_launches++;
     RET_IF(stage_out_copy(c, w_out, dout, ob));

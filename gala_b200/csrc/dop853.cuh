@@ -320,11 +320,11 @@ GB_DEV int dop853_integrate(const RHS& rhs, const OUT& emit, const Dop853Args& a
 // the algorithmic DRAM traffic in the first version.)
 // ------------------------------------------------------------------------------------------------
 template <class C, bool ROT, bool DENSE>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(256)
 k_dop853_dyn(const __grid_constant__ DevPot P, const __grid_constant__ DevFrame F, const __grid_constant__ Dop853Args a,
              const double* __restrict__ w0, size_t N, const double* __restrict__ t, int ntimes,
              const uint32_t* __restrict__ perm, unsigned long long* __restrict__ queue,
-             size_t orb0, size_t nslots, double* __restrict__ out, Dop853Stats st) {
+             size_t orb0, size_t nslots, double* __restrict__ out, Dop853Stats st, int block_sync) {
     // This launch integrates the orbits [orb0, orb0 + nslots); perm (length nslots, global orbit
     // indices of that range in queue order) may be null = natural order.
     auto rhs = [&](double tt, const double (&w)[6], double (&f)[6]) { ham_rhs<C, ROT>(P, F, tt, w, f); };
@@ -359,7 +359,11 @@ k_dop853_dyn(const __grid_constant__ DevPot P, const __grid_constant__ DevFrame 
                 }
             }
         }
-        if (!__any_sync(0xffffffffu, active)) break;
+        // block_sync: the warps of a CTA start every attempted step together, so they walk the same
+        // ~90 KB of straight-line code at the same time and share its instruction-cache misses
+        // (the L1.5 I-cache is 32 KB; unsynchronised warps each stream the whole loop body from L2).
+        if (block_sync) { if (!__syncthreads_or(active)) break; }
+        else if (!__any_sync(0xffffffffu, active)) break;
         if (active) {
             const int code = L.step(rhs, emit, a, t, ntimes);
             if (code != 0) {

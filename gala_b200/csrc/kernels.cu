@@ -8,6 +8,7 @@
 //
 // Compiled twice (see kernels.h): GB_NS = gbk_fast | gbk_strict.
 #include <math_constants.h>
+#include <stdlib.h>
 #include "kernels.h"
 
 #ifndef GB_NS
@@ -274,7 +275,7 @@ template <class C, bool DENSE>
 static cudaError_t launch_d8(const DevPot& P, const DevFrame& F, const double* w0, size_t N, const double* t,
                              int ntimes, const Dop853Args& a, const uint32_t* perm, unsigned long long* queue,
                              size_t orb0, size_t nslots, double* out, const Dop853Stats& st, int block, int nsm,
-                             cudaStream_t s) {
+                             int block_sync, cudaStream_t s) {
     auto kern = k_dop853_dyn<C, GB_D8_ROT, DENSE>;
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0);
@@ -282,7 +283,7 @@ static cudaError_t launch_d8(const DevPot& P, const DevFrame& F, const double* w
     const size_t want = (nslots + block - 1) / block;
     const size_t cap = (size_t)(per_sm > 0 ? per_sm : 1) * nsm;
     kern<<<(unsigned)(want < cap ? want : cap), block, 0, s>>>(P, F, a, w0, N, t, ntimes, perm, queue, orb0, nslots,
-                                                                out, st);
+                                                                out, st, block_sync);
     return cudaGetLastError();
 }
 cudaError_t GB_D8_NAME(const DevPot& P, const DevFrame& F, const double* w0, size_t N, const double* t, int ntimes,
@@ -296,11 +297,14 @@ cudaError_t GB_D8_NAME(const DevPot& P, const DevFrame& F, const double* w0, siz
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
-    if (block > 64 || block <= 0) block = 64;      // __launch_bounds__(64)
+    if (const char* eb = getenv("GB_D8_BLOCK")) block = atoi(eb);
+    if (block > 256 || block <= 0 || (block & 31)) block = 64;      // __launch_bounds__(256)
+    const char* bs = getenv("GB_D8_BLOCKSYNC");
+    const int block_sync = bs ? atoi(bs) : 0;
     if (save_all) {
-        GB_SIG_SWITCH(P.sig, (e = launch_d8<C, true>(P, F, w0, N, t, ntimes, a, perm, queue, orb0, nslots, out, st, block, nsm, s)));
+        GB_SIG_SWITCH(P.sig, (e = launch_d8<C, true>(P, F, w0, N, t, ntimes, a, perm, queue, orb0, nslots, out, st, block, nsm, block_sync, s)));
     } else {
-        GB_SIG_SWITCH(P.sig, (e = launch_d8<C, false>(P, F, w0, N, t, ntimes, a, perm, queue, orb0, nslots, out, st, block, nsm, s)));
+        GB_SIG_SWITCH(P.sig, (e = launch_d8<C, false>(P, F, w0, N, t, ntimes, a, perm, queue, orb0, nslots, out, st, block, nsm, block_sync, s)));
     }
     return e;
 }

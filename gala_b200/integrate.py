@@ -18,7 +18,7 @@ from . import _abi
 from .frame import StaticFrame
 from .units import strip
 
-__all__ = ["parse_time_specification", "LeapfrogIntegrator", "Ruth4Integrator", "DOPRI853Integrator",
+__all__ = ["pinned_empty", "parse_time_specification", "LeapfrogIntegrator", "Ruth4Integrator", "DOPRI853Integrator",
            "get_integrator", "leapfrog_integrate_hamiltonian", "ruth4_integrate_hamiltonian",
            "dop853_integrate_hamiltonian"]
 
@@ -66,6 +66,28 @@ def parse_time_specification(units=None, dt=None, n_steps=None, t1=None, t2=None
 
 
 # ---- buffers ------------------------------------------------------------------------------------
+def pinned_empty(shape, dtype=np.float64):
+    """Page-locked host array (numpy view of a pinned torch tensor).  Passing pinned ``w0`` / ``out``
+    arrays lets the chunked host pipeline of the C ABI overlap its H2D/D2H copies with the kernels;
+    pageable arrays work too, the copies are then staged by the driver."""
+    import torch
+    tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.int32): torch.int32}[np.dtype(dtype)]
+    return torch.empty(tuple(np.atleast_1d(shape)), dtype=tdt).pin_memory().numpy()
+
+
+def _check_out(out, like, shape):
+    if like.device:
+        ok = _abi._is_torch_cuda(out) and tuple(out.shape) == tuple(shape) and out.is_contiguous() \
+            and str(out.dtype) == "torch.float64"
+    else:
+        ok = isinstance(out, np.ndarray) and out.shape == tuple(shape) and out.dtype == np.float64 \
+            and out.flags.c_contiguous and out.flags.writeable
+    if not ok:
+        raise ValueError(f"out must be a C-contiguous float64 array of shape {tuple(shape)} on the same side "
+                         "(host/device) as w0")
+    return out
+
+
 def _prep_w0(w0):
     if _abi._is_torch_cuda(w0):
         import torch
@@ -111,12 +133,13 @@ def _check_c_enabled(hamiltonian):
 
 
 # ---- the boundary functions -----------------------------------------------------------------------
-def _fixed_step(fn_name, hamiltonian, w0, t, save_all):
+def _fixed_step(fn_name, hamiltonian, w0, t, save_all, out=None):
     _check_c_enabled(hamiltonian)
     w = _prep_w0(w0)
     th, tb = _prep_t(t, w)
     N, ntimes = w.arr.shape[1], th.size
-    out = _alloc(w, (6, ntimes, N) if save_all else (6, N))
+    shape = (6, ntimes, N) if save_all else (6, N)
+    out = _alloc(w, shape) if out is None else _check_out(out, w, shape)
     opt = _opts(w, hamiltonian)
     fr = hamiltonian.frame.spec()
     fn = getattr(_abi.lib(), fn_name)
@@ -125,17 +148,17 @@ def _fixed_step(fn_name, hamiltonian, w0, t, save_all):
     return (th, out) if save_all else (th[-1:], out)
 
 
-def leapfrog_integrate_hamiltonian(hamiltonian, w0, t, save_all=1):
+def leapfrog_integrate_hamiltonian(hamiltonian, w0, t, save_all=1, out=None):
     """w0 (6,N) -> (t, w[6, ntimes, N]) or (t[-1:], w[6, N]); StaticFrame only (TypeError otherwise),
-    like ``leapfrog.pyx:54-121``."""
+    like ``leapfrog.pyx:54-121``.  ``out`` (extension): preallocated result array, e.g. ``pinned_empty``."""
     if not isinstance(hamiltonian.frame, StaticFrame):
         _check_c_enabled(hamiltonian)
         raise TypeError("Leapfrog integration is currently only supported for StaticFrame, "
                         f"not {hamiltonian.frame.__class__.__name__}")
-    return _fixed_step("gb_leapfrog", hamiltonian, w0, t, save_all)
+    return _fixed_step("gb_leapfrog", hamiltonian, w0, t, save_all, out)
 
 
-def ruth4_integrate_hamiltonian(hamiltonian, w0, t, save_all=1, allow_rotating_frame=False):
+def ruth4_integrate_hamiltonian(hamiltonian, w0, t, save_all=1, allow_rotating_frame=False, out=None):
     """``ruth4.pyx:37-113``.  The Cython function raises TypeError for a non-static frame; pass
     ``allow_rotating_frame=True`` to run the reference's *Python* Ruth4 semantics in a
     ConstantRotatingFrame on the GPU (what ``cython_if_possible=False`` executes in the reference)."""
@@ -143,7 +166,7 @@ def ruth4_integrate_hamiltonian(hamiltonian, w0, t, save_all=1, allow_rotating_f
         _check_c_enabled(hamiltonian)
         raise TypeError("Leapfrog integration is currently only supported for StaticFrame, not "
                         f"{hamiltonian.frame.__class__.__name__}.")
-    return _fixed_step("gb_ruth4", hamiltonian, w0, t, save_all)
+    return _fixed_step("gb_ruth4", hamiltonian, w0, t, save_all, out)
 
 
 def dop853_integrate_hamiltonian(hamiltonian, w0, t, atol=1e-10, rtol=1e-10, nmax=0, dt_max=0.0, nstiff=0,

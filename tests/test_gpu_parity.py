@@ -325,6 +325,33 @@ def test_device_buffers_roundtrip(ref):
     assert np.array_equal(w_dev.cpu().numpy(), w_host)
 
 
+@pytest.mark.parametrize("save_all", [0, 1])
+def test_host_pipeline_equals_device(save_all):
+    """HOST calls with >= 65536 orbits run as orbit-index chunks pipelined over two streams
+    (capi.cu:fixed_step_common); the result must be bit-identical to the single-launch device path,
+    for pageable and for page-locked (pinned_empty) buffers, ragged last chunk included."""
+    import torch
+    pot = POTS["mw2022"]; H = gb.Hamiltonian(pot)
+    N = 70_001 if save_all else 200_003
+    w0 = make_ic(lambda q: pot.gradient(q), N, seed=17)
+    t = np.arange(9 if save_all else 33, dtype=float)
+    _, wd = gb.leapfrog_integrate_hamiltonian(H, torch.as_tensor(w0, device="cuda"), t, save_all=save_all)
+    wd = wd.cpu().numpy()
+    _, wh = gb.leapfrog_integrate_hamiltonian(H, w0, t, save_all=save_all)
+    assert np.array_equal(wh, wd)
+    w0p = gb.pinned_empty(w0.shape); w0p[...] = w0
+    outp = gb.pinned_empty(wd.shape); outp[...] = np.nan
+    _, wp = gb.leapfrog_integrate_hamiltonian(H, w0p, t, save_all=save_all, out=outp)
+    assert wp is outp and np.array_equal(wp, wd)
+    Hr = gb.Hamiltonian(POTS["bar_mw2022"], gb.ConstantRotatingFrame([0., 0., 0.03]))
+    _, rd = gb.ruth4_integrate_hamiltonian(Hr, torch.as_tensor(w0, device="cuda"), t, save_all=save_all,
+                                           allow_rotating_frame=True)
+    _, rh = gb.ruth4_integrate_hamiltonian(Hr, w0, t, save_all=save_all, allow_rotating_frame=True)
+    assert np.array_equal(rh, rd.cpu().numpy())
+    with pytest.raises(ValueError):
+        gb.leapfrog_integrate_hamiltonian(H, w0, t, save_all=save_all, out=np.empty((6, 3)))
+
+
 def test_edge_cases():
     pot = POTS["nfw"]
     H = gb.Hamiltonian(pot)
