@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("GALA_B200_LIB") or os.path.join(_HERE, "libgala_b200.
 # enum gb_pot_type
 POT_NULL, POT_HERNQUIST, POT_NFW_SPHERICAL, POT_NFW_FLATTENED, POT_NFW_TRIAXIAL = 0, 1, 2, 3, 4
 POT_MIYAMOTONAGAI, POT_MN3, POT_LONGMURALIBAR, POT_SCF = 5, 6, 7, 8
-POT_KEPLER, POT_PLUMMER, POT_ISOCHRONE, POT_JAFFE = 9, 10, 11, 12
+POT_KEPLER, POT_PLUMMER, POT_ISOCHRONE, POT_JAFFE, POT_MULTIPOLE = 9, 10, 11, 12, 13
 FRAME_STATIC, FRAME_ROTATING_3D = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 

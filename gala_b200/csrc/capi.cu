@@ -48,6 +48,7 @@ int min_npar(int type) {
         case GB_POT_MN3: return 10;
         case GB_POT_NFW_SPHERICAL: return 3;
         case GB_POT_SCF: return 5;
+        case GB_POT_MULTIPOLE: return 6;
         default: return expected_npar(type);
     }
 }
@@ -103,6 +104,21 @@ void scf_pack(const double* params, int nmax, int lmax, std::vector<double>& ext
         }
 }
 
+// Multipole coefficients for the device (multipole.cuh): (S,T) pairs in the reference's (l, m<=l)
+// order with the spherical-harmonic normalisation folded in (gsl_sf_legendre_sphPlm and the factor A
+// of multipole.cpp:106-111).  Input: params = [G, lmax, num_coeff, inner, m, r_s, S00, T00, S10, ...].
+void mp_pack(const double* params, int lmax, std::vector<double>& ext) {
+    int i = 0;
+    for (int l = 0; l <= lmax; l++)
+        for (int m = 0; m <= l; m++, i++) {
+            double ratio = 1.;
+            for (int k = l - m + 1; k <= l + m; k++) ratio /= (double)k;
+            const double nlm = sqrt((2. * l + 1.) / (4. * M_PI) * ratio);
+            ext.push_back(params[6 + 2 * i] * nlm);
+            ext.push_back(params[7 + 2 * i] * nlm);
+        }
+}
+
 bool sig_matches(const gb_potential* pot, std::initializer_list<int> types) {
     if ((size_t)pot->n_components != types.size()) return false;
     int i = 0;
@@ -149,6 +165,16 @@ int resolve(const gb_potential* pot, Resolved& r, cudaStream_t stream) {
             if (c.n_params < 5 + 2 * ncoef) return fail(-12, "SCF: parameter vector shorter than 5 + 2*(nmax+1)(lmax+1)^2");
             if (lmax > 15 || nmax > 63) return fail(-11, "SCF: lmax <= 15 and nmax <= 63 supported");
             scf_pack(c.params, nmax, lmax, r.ext);
+        }
+        if (c.type_id == GB_POT_MULTIPOLE) {
+            nsmall = 6;
+            const int lmax = (int)c.params[1], ncoef = (int)c.params[2];
+            if (lmax < 0 || lmax > GB_MP_LMAX) return fail(-11, "Multipole: 0 <= lmax <= 15 supported");
+            if (ncoef != (lmax + 1) * (lmax + 2) / 2 || c.n_params < 6 + 2 * ncoef)
+                return fail(-12, "Multipole: num_coeff must be (lmax+1)(lmax+2)/2 and the parameter vector 6 + 2*num_coeff long");
+            if (r.ext.size() & 1) r.ext.push_back(0.);     // keep (S,T) pairs 16-byte aligned
+            d.eoff = (int)r.ext.size();
+            mp_pack(c.params, lmax, r.ext);
         }
         d.npar = nsmall;
         if (off + nsmall > GB_MAXP) return fail(-11, "too many potential parameters for the constant bank");

@@ -11,6 +11,7 @@
 #pragma once
 #include "potentials.cuh"
 #include "scf.cuh"
+#include "multipole.cuh"
 
 template <int T> struct PotOf;
 template <> struct PotOf<GB_POT_NULL>          { using type = PotNull;          static constexpr int NP = 1; };
@@ -39,6 +40,7 @@ GB_DEV void gb_comp_gradient(int type, const double* p, const double* e, double 
         GB_FOR_EACH_SIMPLE_TYPE(X)
 #undef X
         case GB_POT_SCF: PotSCF::gradient(p, e, x, y, z, gx, gy, gz); break;
+        case GB_POT_MULTIPOLE: PotMultipole::gradient(p, e, x, y, z, gx, gy, gz); break;
         default: break;
     }
 }
@@ -50,6 +52,7 @@ GB_DEV void gb_comp_accum(int type, const double* p, const double* d, const doub
         GB_FOR_EACH_SIMPLE_TYPE(X)
 #undef X
         case GB_POT_SCF: PotSCF::gradient(p, e, c.x, c.y, c.z, c.gx, c.gy, c.gz); break;
+        case GB_POT_MULTIPOLE: PotMultipole::gradient(p, e, c.x, c.y, c.z, c.gx, c.gy, c.gz); break;
         default: break;
     }
 }
@@ -60,6 +63,7 @@ GB_DEV double gb_comp_value(int type, const double* p, const double* e, double x
         GB_FOR_EACH_SIMPLE_TYPE(X)
 #undef X
         case GB_POT_SCF: return PotSCF::value(p, e, x, y, z);
+        case GB_POT_MULTIPOLE: return PotMultipole::value(p, e, x, y, z);
         default: return 0.;
     }
 }
@@ -69,6 +73,7 @@ GB_DEV double gb_comp_density(int type, const double* p, const double* e, double
         GB_FOR_EACH_SIMPLE_TYPE(X)
 #undef X
         case GB_POT_SCF: return PotSCF::density(p, e, x, y, z);
+        case GB_POT_MULTIPOLE: return PotMultipole::density(p, e, x, y, z);
         default: return 0.;
     }
 }

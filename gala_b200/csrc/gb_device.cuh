@@ -10,6 +10,7 @@
 #include "../../include/gala_b200.h"
 
 #define GB_HAVE_SCF 1   // flipped to 1 when scf.cuh carries the recurrence implementation
+#define GB_MP_LMAX 15  // largest multipole order the device evaluates
 #define GB_MAXC 8      // components per composite held in the constant bank
 #define GB_MAXP 120    // packed doubles of "small" parameters ([G, ...] of every component)
 #define GB_MAXD 40     // packed doubles of host-derived constants (G*m, b^2, 1/r_s, ...) for the fast build

@@ -20,7 +20,7 @@ from .units import galactic, strip
 __all__ = [
     "PotentialBase", "CCompositePotential", "NullPotential", "KeplerPotential", "HernquistPotential",
     "PlummerPotential", "IsochronePotential", "JaffePotential", "NFWPotential", "MiyamotoNagaiPotential",
-    "MN3ExponentialDiskPotential", "LongMuraliBarPotential", "SCFPotential", "MilkyWayPotential",
+    "MN3ExponentialDiskPotential", "LongMuraliBarPotential", "SCFPotential", "MultipolePotential", "MilkyWayPotential",
     "MilkyWayPotential2022",
 ]
 
@@ -329,6 +329,42 @@ class SCFPotential(PotentialBase):
     def _c_parameters(self):
         return np.concatenate([[self.nmax, self.lmax, self.parameters["m"], self.parameters["r_s"]],
                                self.Snlm.ravel(), self.Tnlm.ravel()])
+
+
+class MultipolePotential(PotentialBase):
+    """Inner / outer multipole expansion (reference ``builtin/core.py:1101-1239`` MultipolePotential,
+    ``builtin/multipole.cpp``).  ``MultipolePotential(lmax=2, m=..., r_s=..., inner=False, S10=5., T21=...)``:
+    unspecified ``S{l}{m}`` / ``T{l}{m}`` default to 0, unknown names raise.  The C vector is
+    ``[lmax, n_coeffs, inner, m, r_s, S00, T00, S10, T10, S11, T11, ...]`` (c-only parameters first,
+    ``core.py:1220-1222``; then declaration order ``:1122-1146``)."""
+    _type_id = _abi.POT_MULTIPOLE
+    _param_names = ("m", "r_s")
+
+    def __init__(self, *args, lmax=None, m=1.0, r_s=1.0, inner=False, **kw):
+        if lmax is None:
+            raise TypeError("Can't initialize a MultipolePotential without specifying the `lmax` keyword argument.")
+        if args:
+            m = args[0]
+            if len(args) > 1:
+                r_s = args[1]
+        self.lmax = int(lmax)
+        self.inner = bool(inner)
+        self.coeffs = OrderedDict()
+        for l in range(self.lmax + 1):
+            for mm in range(l + 1):
+                self.coeffs[f"S{l}{mm}"] = float(kw.pop(f"S{l}{mm}", 0.0))
+                self.coeffs[f"T{l}{mm}"] = float(kw.pop(f"T{l}{mm}", 0.0))
+        bad = [k for k in kw if k[:1] in "ST" and k[1:].isdigit()]
+        if bad:
+            raise ValueError(f"coefficient(s) {bad} not allowed for lmax={self.lmax}")
+        super().__init__(m=m, r_s=r_s, **kw)
+        self.parameters["inner"] = self.inner
+        self.parameters.update(self.coeffs)
+
+    def _c_parameters(self):
+        n_coeffs = (self.lmax + 1) * (self.lmax + 2) // 2
+        return np.concatenate([[self.lmax, n_coeffs, float(self.inner), self.parameters["m"], self.parameters["r_s"]],
+                               np.array(list(self.coeffs.values()), dtype=np.float64)])
 
 
 class CCompositePotential(PotentialBase, OrderedDict):

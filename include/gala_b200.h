@@ -55,6 +55,8 @@ enum gb_pot_type {
     GB_POT_PLUMMER          = 10, /* PlummerWrapper         :177  [G, m, b]                              */
     GB_POT_ISOCHRONE        = 11, /* IsochroneWrapper       :153  [G, m, b]                              */
     GB_POT_JAFFE            = 12, /* JaffeWrapper           :189  [G, m, c]                              */
+    GB_POT_MULTIPOLE        = 13, /* MultipoleWrapper       :378  [G, lmax, n_coeff, inner, m, r_s, (S_lm,T_lm)..]
+                                     (builtin/multipole.cpp:247-262); lmax <= 15                        */
     GB_POT_NTYPES
 };
 

@@ -301,6 +301,55 @@ static void scf_grad(const double *p, const REAL *q, REAL *g) {   /* scf_gradien
     g[0] += gx * sc; g[1] += gy * sc; g[2] += gz * sc;
 }
 
+/* ---- Multipole (potential/potential/builtin/multipole.cpp:30-301), term by term like the reference:
+ * p = [G, lmax, num_coeff, inner, m, r_s, S00, T00, S10, T10, S11, T11, ...] (:247-262) */
+static REAL mp_phi_l(REAL s, int l, int inner) { return inner ? POW(s, l) : POW(s, -(l + 1)); }   /* :50-56 */
+static void mp_sph_grad_phi_lm(REAL s, REAL X, int l, int m, int inner, REAL *sg) {             /* :69-138 */
+    REAL sintheta = SQRT(1 - X * X);
+    REAL Ylm = sphplm(l, m, X), Plm = (m <= l) ? plm(l, m, X) : 0, Phi_l = mp_phi_l(s, l, inner), dPhil_dr, dY = 0;
+    if (inner) dPhil_dr = l * POW(s, l - 1) * Ylm; else dPhil_dr = -(l + 1) * POW(s, -l - 2) * Ylm;
+    if (l != 0) {
+        REAL Pl1m = (m <= l - 1) ? plm(l - 1, m, X) : 0;
+        REAL A = SQRT((REAL)(2 * l + 1)) / SQRT_FOURPI * SQRT(fact_ratio(l, m));
+        dY = (sintheta != 0) ? A / sintheta * (l * X * Plm - (l + m) * Pl1m) : 0;
+    }
+    if (s > 0) { sg[0] = dPhil_dr; sg[1] = dY * Phi_l / s; sg[2] = ((m == 0) ? 0 : (REAL)m) * Ylm * Phi_l; }
+    else { sg[0] = sg[1] = sg[2] = 0; }
+}
+static REAL mp_value(const double *p, const REAL *q) {       /* mp_potential_helper :185-226 */
+    int lmax = (int)p[1], inner = (int)p[3];
+    REAL r = norm3(q), s = r / p[5], X = q[2] / r, phi = ATAN2(q[1], q[0]), val = 0;
+    int i = 0;
+    for (int l = 0; l <= lmax; l++) for (int m = 0; m <= l; m++, i++) {
+        double S = p[6 + 2 * i], T = p[7 + 2 * i];
+        if (S == 0. && T == 0.) continue;
+        val += mp_phi_l(s, l, inner) * sphplm(l, m, X) * (S * COS(m * phi) + T * SIN(m * phi));
+    }
+    if (r == 0 && inner) val = 0;
+    return val * p[0] * p[4] / p[5];
+}
+static void mp_grad(const double *p, const REAL *q, REAL *g) {    /* mp_gradient_helper :228-301 */
+    int lmax = (int)p[1], inner = (int)p[3];
+    REAL r = norm3(q), s = r / p[5], X = q[2] / r, phi = ATAN2(q[1], q[0]);
+    REAL sintheta = SQRT(1 - X * X), cosphi = COS(phi), sinphi = SIN(phi);
+    REAL t2[3] = {0, 0, 0}, sg[3];
+    int i = 0;
+    for (int l = 0; l <= lmax; l++) for (int m = 0; m <= l; m++, i++) {
+        double S = p[6 + 2 * i], T = p[7 + 2 * i];
+        if (S == 0. && T == 0.) continue;
+        REAL cm = COS(m * phi), sm = SIN(m * phi), tmp = S * cm + T * sm;
+        mp_sph_grad_phi_lm(s, X, l, m, inner, sg);
+        t2[0] += sg[0] * tmp;
+        t2[1] += sg[1] * tmp;
+        if (sintheta != 0) t2[2] += sg[2] * (T * cm - S * sm) / (s * sintheta); else t2[2] = 0;
+    }
+    REAL gx = sintheta * cosphi * t2[0] + X * cosphi * t2[1] - sinphi * t2[2];
+    REAL gy = sintheta * sinphi * t2[0] + X * sinphi * t2[1] + cosphi * t2[2];
+    REAL gz = X * t2[0] - sintheta * t2[1];
+    REAL sc = (REAL)p[0] * p[4] / ((REAL)p[5] * p[5]);
+    g[0] += gx * sc; g[1] += gy * sc; g[2] += gz * sc;
+}
+
 /* ---- per-component dispatch ------------------------------------------------------------------- */
 static void comp_grad(int type, const double *p, const REAL *q, REAL *g) {
     switch (type) {
@@ -310,6 +359,7 @@ static void comp_grad(int type, const double *p, const REAL *q, REAL *g) {
         case GB_POT_MN3: for (int i = 0; i < 3; i++) mn_grad(p[0], p[1 + 3 * i], p[2 + 3 * i], p[3 + 3 * i], q, g); break; /* :1404-1414 */
         case GB_POT_LONGMURALIBAR: lmbar_grad(p, q, g); break;
         case GB_POT_SCF: scf_grad(p, q, g); break;
+        case GB_POT_MULTIPOLE: mp_grad(p, q, g); break;
         case GB_POT_KEPLER: kepler_grad(p, q, g); break;
         case GB_POT_PLUMMER: plummer_grad(p, q, g); break;
         case GB_POT_ISOCHRONE: isochrone_grad(p, q, g); break;
@@ -325,6 +375,7 @@ static REAL comp_value(int type, const double *p, const REAL *q) {
         case GB_POT_MN3: { REAL v = 0; for (int i = 0; i < 3; i++) v += mn_value(p[0], p[1 + 3 * i], p[2 + 3 * i], p[3 + 3 * i], q); return v; }
         case GB_POT_LONGMURALIBAR: return lmbar_value(p, q);
         case GB_POT_SCF: return scf_value(p, q);
+        case GB_POT_MULTIPOLE: return mp_value(p, q);
         case GB_POT_KEPLER: return kepler_value(p, q);
         case GB_POT_PLUMMER: return plummer_value(p, q);
         case GB_POT_ISOCHRONE: return isochrone_value(p, q);
@@ -340,6 +391,7 @@ static REAL comp_density(int type, const double *p, const REAL *q) {
         case GB_POT_MN3: { REAL v = 0; for (int i = 0; i < 3; i++) v += mn_density(p[1 + 3 * i], p[2 + 3 * i], p[3 + 3 * i], q); return v; }
         case GB_POT_LONGMURALIBAR: return lmbar_density(p, q);
         case GB_POT_SCF: return scf_density(p, q);
+        case GB_POT_MULTIPOLE: return 0;      /* mp_density :404-420 returns 0 */
         case GB_POT_KEPLER: return kepler_density(p, q);
         case GB_POT_PLUMMER: return plummer_density(p, q);
         case GB_POT_ISOCHRONE: return isochrone_density(p, q);

@@ -21,6 +21,7 @@
 #include "dopri/dop853.h"
 #if GB_REF_HAVE_SCF
 #include "scf/src/bfe.h"
+#include "potential/builtin/multipole.h"
 #endif
 
 #include "gala_b200.h"
@@ -47,6 +48,9 @@ struct RefPotential {
 // wrapper casts them to energyfunc (scf/bfe_class.pyx).  Adapt explicitly here.
 double scf_value5(double t, double *pars, double *q, int n_dim, void *) { return scf_value(t, pars, q, n_dim); }
 double scf_density5(double t, double *pars, double *q, int n_dim, void *) { return scf_density(t, pars, q, n_dim); }
+// same for the multipole functions (builtin/multipole.h:3-5; cybuiltin.pyx:385-388)
+double mp_potential5(double t, double *pars, double *q, int n_dim, void *) { return mp_potential(t, pars, q, n_dim); }
+double mp_density5(double t, double *pars, double *q, int n_dim, void *) { return mp_density(t, pars, q, n_dim); }
 #endif
 
 bool fill_component(CPotential *cp, int i, int type_id) {
@@ -91,6 +95,9 @@ bool fill_component(CPotential *cp, int i, int type_id) {
     case GB_POT_SCF:
         cp->value[i] = scf_value5; cp->density[i] = scf_density5;
         cp->gradient[i] = scf_gradient; cp->hessian[i] = null_hessian; return true;
+    case GB_POT_MULTIPOLE:
+        cp->value[i] = mp_potential5; cp->density[i] = mp_density5;
+        cp->gradient[i] = mp_gradient; cp->hessian[i] = null_hessian; return true;
 #endif
     default: return false;
     }

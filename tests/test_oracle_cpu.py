@@ -228,8 +228,8 @@ def test_port_equals_reference_evaluation(ref, port):
     q = rng.normal(0, 10.0, (3, 2000))
     for name, pot in all_potentials().items():
         g, g0 = port.gradient(pot, q), ref.gradient(pot, q)
-        assert np.max(np.sqrt(((g - g0) ** 2).sum(0)) / np.sqrt((g0 ** 2).sum(0))) < (1e-13 if name.startswith('scf') else 4e-16), name
-        assert np.allclose(port.energy(pot, q), ref.energy(pot, q), rtol=(1e-13 if name.startswith('scf') else 1e-15), atol=0), name
+        assert np.max(np.sqrt(((g - g0) ** 2).sum(0)) / np.sqrt((g0 ** 2).sum(0))) < (1e-13 if name.startswith(('scf', 'multipole')) else 4e-16), name
+        assert np.allclose(port.energy(pot, q), ref.energy(pot, q), rtol=(1e-12 if name.startswith(('scf', 'multipole')) else 1e-15), atol=0), name
         d, d0 = port.density(pot, q), ref.density(pot, q)
         ok = np.isfinite(d0)
         assert np.array_equal(np.isfinite(d), ok)
@@ -290,3 +290,63 @@ def test_dop853_coefficients_match_reference():
         mine = {k: float(v) for k, v in re.findall(r"\b([a-z]+[0-9]+)\s*=\s*([-+0-9.Ee]+)", open(os.path.join(root, path)).read())}
         assert set(mine) == set(refc) and len(refc) == 154
         assert all(mine[k] == refc[k] for k in refc), path
+
+
+# ---- multipole expansion (builtin/multipole.cpp) ---------------------------------------------------
+def _mp_random(lmax, inner, seed):
+    rng = np.random.default_rng(seed)
+    kw = {}
+    for l in range(lmax + 1):
+        for m in range(l + 1):
+            kw[f"S{l}{m}"] = rng.normal()
+            if m > 0:
+                kw[f"T{l}{m}"] = rng.normal()
+    return gb.MultipolePotential(lmax=lmax, inner=inner, m=3e10, r_s=7.0, **kw)
+
+
+def test_multipole_closed_forms(ref, port):
+    """Known answers for the lowest orders, derived from Y_lm with the Condon-Shortley phase:
+    outer l=0 with S00 = -sqrt(4 pi) is a Kepler potential; inner (l,m)=(1,0) is a uniform field along z;
+    inner (2,2) is proportional to x^2 - y^2."""
+    rng = np.random.default_rng(3)
+    q = rng.normal(0, 9.0, (3, 257))
+    M, rs = 3e10, 7.0
+    kep = gb.KeplerPotential(m=M)
+    mp0 = gb.MultipolePotential(lmax=0, inner=False, m=M, r_s=rs, S00=-np.sqrt(4 * np.pi))
+    mp10 = gb.MultipolePotential(lmax=1, inner=True, m=M, r_s=rs, S10=1.0)
+    mp22 = gb.MultipolePotential(lmax=2, inner=True, m=M, r_s=rs, S22=1.0)
+    for _, chk in checkers(ref, port):
+        assert np.allclose(chk.energy(mp0, q), chk.energy(kep, q), rtol=1e-13)
+        assert np.allclose(chk.gradient(mp0, q), chk.gradient(kep, q), rtol=1e-12, atol=1e-18)
+        g = chk.gradient(mp10, q)
+        assert np.allclose(g[2], G * M / rs ** 2 * np.sqrt(3 / (4 * np.pi)), rtol=1e-12)
+        assert np.abs(g[:2]).max() < 1e-12 * np.abs(g[2]).max()
+        c22 = G * M / rs ** 3 * np.sqrt(5 / (4 * np.pi) / 24.0) * 3.0
+        assert np.allclose(chk.energy(mp22, q), c22 * (q[0] ** 2 - q[1] ** 2), rtol=1e-11, atol=1e-12 * c22 * 81)
+        g = chk.gradient(mp22, q)
+        scale = np.abs(g).max()
+        assert np.allclose(g[0], 2 * c22 * q[0], atol=1e-11 * scale)
+        assert np.allclose(g[1], -2 * c22 * q[1], atol=1e-11 * scale)
+        assert np.abs(g[2]).max() < 1e-11 * scale
+        assert np.all(chk.density(mp22, q) == 0.0)      # mp_density returns 0 (multipole.cpp:404-420)
+
+
+@pytest.mark.parametrize("inner", [True, False])
+def test_multipole_port_equals_reference_and_is_a_gradient(ref, port, inner):
+    pot = _mp_random(5, inner, 40 + inner)
+    rng = np.random.default_rng(8)
+    q = rng.normal(0, 9.0, (3, 513))
+    g_ref, g_port = ref.gradient(pot, q), port.gradient(pot, q)
+    scale = np.sqrt((g_ref ** 2).sum(0))
+    assert np.max(np.sqrt(((g_ref - g_port) ** 2).sum(0)) / scale) < 1e-12
+    assert np.allclose(ref.energy(pot, q), port.energy(pot, q), rtol=1e-12)
+    # the gradient is the derivative of the value (the reference's own generic potential test,
+    # tests/potential/potential/potential_helpers.py numerical-gradient check)
+    h = 1e-5
+    for k in range(3):
+        dq = np.zeros((3, 1)); dq[k] = h
+        num = (port.energy(pot, q + dq) - port.energy(pot, q - dq)) / (2 * h)
+        assert np.max(np.abs(num - g_port[k]) / scale) < 1e-7
+    # on the z axis the theta and phi components are dropped (multipole.cpp:117-121, 281-283)
+    qz = np.array([[0.0], [0.0], [5.0]])
+    assert np.allclose(ref.gradient(pot, qz), port.gradient(pot, qz), rtol=1e-12, atol=1e-30)
