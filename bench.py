@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 SM_FILL = 148 * 2048          # resident threads of one B200 at full occupancy
 
 # algorithmic flops per orbit-step (source-level op counts)
-FLOPS = {"headline": 146, "c1": 46, "c4": 666, "c2": 3970, "c5": 3400}
+FLOPS = {"headline": 146, "c1": 46, "c4": 666, "c2": 3970, "c5": 3400, "c3": 146, "c3d": 0}
 
 
 def make_ic(N, seed, pot_gradient, rmin=4.0, rmax=50.0):
@@ -105,6 +105,26 @@ def workload(name, n_orbits):
         def units(N_, out):
             ns = stats["nstep"]
             return int(ns.sum().item() if hasattr(ns, "cpu") else ns.sum())
+    elif name in ("c3", "c3d"):
+        # C3: 10^5-particle Fardal stream in MW2022 (tests/dynamics/mockstream/test_mockstream.py:676-678
+        # progenitor); c3 = LeapfrogIntegrator (exact orbit-step count), c3d = DOPRI853 (reference default)
+        H = gb.Hamiltonian(gb.MilkyWayPotential2022())
+        prog = gb.PhaseSpacePosition(pos=[13.0, 0.0, 20.0], vel=np.array([0.0, 130.0, 50.0]) * gb.KMS_TO_KPC_MYR)
+        n_steps, n_part = 5000, 10
+        t = np.arange(n_steps + 1) * -1.0
+        N = 2 * n_part * (n_steps + 1)
+        integ = gb.LeapfrogIntegrator if name == "c3" else gb.DOPRI853Integrator
+        desc = (f"C3: FardalStreamDF(gala_modified, RandomState(42)) in MW2022, dt=-1Myr x {n_steps}, {n_part} particles "
+                f"per tail per step = {N} particles, {integ.__name__}, whole MockStreamGenerator.run per step")
+
+        def run(w0, tt, out=None):
+            gen = gb.MockStreamGenerator(gb.FardalStreamDF(gala_modified=True, random_state=np.random.RandomState(42)), H)
+            stream, _ = gen.run(prog, 2.5e4, dt=-1.0, n_steps=n_steps, n_particles=n_part, release_every=1,
+                                Integrator=integ)
+            return stream.w()
+
+        # fixed-step count: particle released at step k takes k steps (+ the progenitor orbit itself)
+        units = lambda N_, out: 2 * n_part * (n_steps * (n_steps + 1) // 2) + n_steps
     elif name == "c5":
         rng = np.random.default_rng(5)
         nmax, lmax = 10, 6

@@ -79,6 +79,7 @@ SIGNATURES = {
     "gb_launch_count": (C.c_long, []),
     "gb_version": (C.c_char_p, []),
     "gb_fp64_peak_tflops": (C.c_double, [C.c_int]),
+    "gb_release_scratch": (C.c_int, []),
     "gb_math_probe": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, P(gb_launch)]),
 }
 
@@ -126,6 +127,11 @@ def device_count() -> int:
 
 def launch_count() -> int:
     return lib().gb_launch_count()
+
+
+def release_scratch():
+    """Free the device buffers the library caches between calls (see ``gb_release_scratch``)."""
+    check(lib().gb_release_scratch())
 
 
 def math_probe(which: int, x, strict: bool = False):

@@ -71,9 +71,15 @@ void gb_derive(int type, const double* p, double* d) {
             break;
         case GB_POT_LONGMURALIBAR:
             d[0] = p[0] * p[1]; d[1] = sin(p[5]); d[2] = cos(p[5]); d[3] = p[4] * p[4]; break;
+        case GB_POT_SCF:
+            d[0] = p[0] * p[3] / (p[4] * p[4]); d[1] = 1. / p[4]; break;
         default: break;
     }
 }
+
+#define GB_SCF_NMAX_CONST 10
+#define GB_SCF_LMAX_CONST 6
+static_assert(GB_CEXT == 2 * (GB_SCF_NMAX_CONST + 1) * ((GB_SCF_LMAX_CONST + 1) * (GB_SCF_LMAX_CONST + 2) / 2), "cext layout");
 
 struct Resolved {
     DevPot P;
@@ -196,6 +202,21 @@ int resolve(const gb_potential* pot, Resolved& r, cudaStream_t stream) {
     else if (sig_matches(pot, {GB_POT_MN3, GB_POT_HERNQUIST, GB_POT_HERNQUIST, GB_POT_NFW_SPHERICAL, GB_POT_LONGMURALIBAR})) P.sig = SIG_MW2022_BAR;
     else if (pot->n_components == 1 && pot->comp[0].type_id == GB_POT_SCF && !pot->comp[0].do_shift_rotate) P.sig = SIG_SCF;
     if (getenv("GB_FORCE_GENERIC")) P.sig = SIG_GENERIC;
+    if (P.sig == SIG_SCF && !getenv("GB_SCF_NO_CONST")) {
+        // small expansions also go to the constant bank in the fixed (10,6) layout of scf_fast_gradient
+        const double* p = pot->comp[0].params;
+        const int nmax = (int)p[1], lmax = (int)p[2];
+        if (nmax <= GB_SCF_NMAX_CONST && lmax <= GB_SCF_LMAX_CONST) {
+            size_t k = 0;                                   // r.ext is [l][m][n] with this nmax
+            for (int l = 0; l <= lmax; l++)
+                for (int m = 0; m <= l; m++)
+                    for (int n = 0; n <= nmax; n++, k += 2) {
+                        const int i = 2 * (((l * (l + 1)) / 2 + m) * (GB_SCF_NMAX_CONST + 1) + n);
+                        P.cext[i] = r.ext[k]; P.cext[i + 1] = r.ext[k + 1];
+                    }
+            P.cext_ok = 1;
+        }
+    }
 
     if (!r.ext.empty()) {
         CU(cudaMalloc(&r.d_ext, r.ext.size() * sizeof(double)));
@@ -365,6 +386,22 @@ int gb_density(const gb_potential* pot, const double* q, double t, size_t N, dou
     return eval_common(EV_DENSITY, pot, q, t, N, out, opt);
 }
 
+int gb_release_scratch(void) {
+    std::lock_guard<std::mutex> g(g_scratch_mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int k = 0; k < NSLOT; k++) {
+        Scratch& sc = g_scratch[k];
+        if (!sc.ptr) continue;
+        if (sc.dev != cur) cudaSetDevice(sc.dev);
+        cudaDeviceSynchronize();
+        cudaFree(sc.ptr);
+        if (sc.dev != cur) cudaSetDevice(cur);
+        sc.ptr = nullptr; sc.cap = 0; sc.dev = -1;
+    }
+    return 0;
+}
+
 int gb_math_probe(int which, const double* x, size_t N, double* y, const gb_launch* opt) {
     Ctx c; RET_IF(open_ctx(opt, c));
     if (which < 0 || which > 3) return fail(-12, "gb_math_probe: which must be 0..3");
@@ -413,6 +450,8 @@ int gb_hamiltonian_gradient(const gb_potential* pot, const gb_frame* fr, const d
 }
 
 // Two side streams per device for the chunked HOST pipeline (created once, never destroyed).
+// The streams and events are shared by every call on a device, so a call that uses them holds g_side_mu.
+std::mutex g_side_mu;
 struct SideStreams { cudaStream_t s[2] = {nullptr, nullptr}; cudaEvent_t ev[3] = {nullptr, nullptr, nullptr}; };
 static int side_streams(SideStreams** out) {
     static std::mutex mu;
@@ -468,6 +507,7 @@ static int fixed_step_common(bool is_ruth4, const gb_potential* pot, const gb_fr
     // chunk of orbits a 2-D copy: 6 [x ntimes] rows of nb doubles with a pitch of N doubles).
     const size_t kPipeMin = 1 << 16;
     if (c.host && N >= kPipeMin && !getenv("GB_NO_PIPELINE")) {
+        std::lock_guard<std::mutex> side_lock(g_side_mu);
         SideStreams* S; RET_IF(side_streams(&S));
         size_t nb = (N + 7) / 8;                                   // ~8 chunks
         const size_t cap = ((size_t)256 << 20) / (rows * 6 * sizeof(double));   // <= 256 MB of output per chunk
@@ -576,6 +616,8 @@ static int pool_keep() {
 
 // Stream-ordered temporary device memory (freed with cudaFreeAsync on the same stream).
 struct AsyncBuf {
+    void* p_cached = nullptr;    // alternatively a pointer owned by the scratch cache (not freed here)
+    void* get() const { return p ? p : p_cached; }
     void* p = nullptr;
     cudaStream_t s = nullptr;
     cudaError_t alloc(size_t bytes, cudaStream_t stream) { s = stream; return cudaMallocAsync(&p, bytes ? bytes : 8, s); }
@@ -592,7 +634,7 @@ int gb_dop853(const gb_potential* pot, const gb_frame* fr, const double* w0, siz
     RET_IF(pool_keep());
     DevFrame F; RET_IF(resolve_frame(fr, F));
     Resolved r; RET_IF(resolve(pot, r, c.stream));
-    const int block = c.block > 0 ? c.block : 64;
+    const int block = c.block > 0 ? c.block : 128;     // 4 warps per CTA, step-synchronised (dop853.cuh)
     double two[2];
     if (c.host) { two[0] = t[0]; two[1] = t[1]; }
     else {
@@ -629,9 +671,12 @@ int gb_dop853(const gb_potential* pot, const gb_frame* fr, const double* w0, siz
         size_t free_b = 0, total_b = 0;
         CU(cudaMemGetInfo(&free_b, &total_b));
         const size_t per_orbit = (size_t)ntimes * 6 * sizeof(double);
-        // <= 4 GB: big enough for > 2 full waves of resident lanes at ntimes = 1000, small enough that
-        // the stream-ordered pool can keep it cached between calls (pool_keep() below)
-        size_t budget = free_b / 2 < ((size_t)4 << 30) ? free_b / 2 : ((size_t)4 << 30);
+        // As many orbits per persistent launch as memory allows: a launch cannot end before its longest
+        // orbit does (~1000 sequential steps), so the work per resident lane must be several times
+        // that, i.e. >> 38k orbits per launch.  Up to half of the free memory (counting what the
+        // scratch cache already holds); the buffer stays cached until gb_release_scratch().
+        if (!c.lock.owns_lock()) c.lock = std::unique_lock<std::mutex>(g_scratch_mu);
+        size_t budget = (free_b + g_scratch[14].cap) / 2;
         if (const char* e = getenv("GB_D8_SCRATCH_MB")) budget = (size_t)atoll(e) << 20;
         chunk = budget / per_orbit;
         if (chunk < 64) chunk = 64;
@@ -639,44 +684,75 @@ int gb_dop853(const gb_potential* pot, const gb_frame* fr, const double* w0, siz
         if (chunk > N) chunk = N;
     }
     const bool sorted = N >= 2048 && !getenv("GB_D8_NOSORT");
-    AsyncBuf queue, keys_in, keys_out, idx_in, perm, temp, scratch;
-    size_t temp_bytes = 0;
-    if (N) {
-        CU(queue.alloc(sizeof(unsigned long long), c.stream));
-        if (sorted) {
-            CU(gb_sort_pairs_bytes(chunk, &temp_bytes));
-            CU(keys_in.alloc(chunk * 4, c.stream)); CU(keys_out.alloc(chunk * 4, c.stream));
-            CU(idx_in.alloc(chunk * 4, c.stream)); CU(perm.alloc(chunk * 4, c.stream));
-            CU(temp.alloc(temp_bytes, c.stream));
-        }
-        if (save_all) CU(scratch.alloc(chunk * (size_t)ntimes * 6 * sizeof(double), c.stream));
+    // More than one chunk: chunks alternate between two side streams (each with its own queue
+    // counter, sort buffers and scratch), so the tail of one persistent kernel -- a few long orbits
+    // on a mostly idle GPU -- overlaps the start of the next chunk.
+    // (measured: slower than one stream with a larger chunk -- each persistent grid fills the GPU, so the
+    // second launch only becomes resident as the first one drains; kept as an opt-in experiment.)
+    const int nstreams = (N > chunk && getenv("GB_D8_TWO_STREAMS")) ? 2 : 1;
+    if (nstreams == 2 && save_all) {
+        chunk = (chunk / 2) & ~(size_t)31;
+        if (chunk < 64) chunk = 64;
     }
-    for (size_t orb0 = 0; orb0 < N; orb0 += chunk) {
+    std::unique_lock<std::mutex> side_lock;
+    if (nstreams == 2) side_lock = std::unique_lock<std::mutex>(g_side_mu);
+    AsyncBuf queue[2], keys_in[2], keys_out[2], idx_in[2], perm[2], temp[2], scratch[2];
+    size_t temp_bytes = 0;
+    cudaStream_t st[2] = {c.stream, c.stream};
+    SideStreams* S = nullptr;
+    if (N) {
+        if (sorted) CU(gb_sort_pairs_bytes(chunk, &temp_bytes));
+        for (int k = 0; k < nstreams; k++) {
+            CU(queue[k].alloc(sizeof(unsigned long long), c.stream));
+            if (sorted) {
+                CU(keys_in[k].alloc(chunk * 4, c.stream)); CU(keys_out[k].alloc(chunk * 4, c.stream));
+                CU(idx_in[k].alloc(chunk * 4, c.stream)); CU(perm[k].alloc(chunk * 4, c.stream));
+                CU(temp[k].alloc(temp_bytes, c.stream));
+            }
+            if (save_all) {
+                const size_t sb = chunk * (size_t)ntimes * 6 * sizeof(double);
+                if (nstreams == 1) CU(scratch_get(14, sb, &scratch[k].p_cached)); else CU(scratch[k].alloc(sb, c.stream));
+            }
+        }
+        if (nstreams == 2) {
+            RET_IF(side_streams(&S));
+            CU(cudaEventRecord(S->ev[2], c.stream));       // inputs staged, buffers allocated
+            for (int k = 0; k < 2; k++) { st[k] = S->s[k]; CU(cudaStreamWaitEvent(st[k], S->ev[2], 0)); }
+        }
+    }
+    int k = 0;
+    for (size_t orb0 = 0; orb0 < N; orb0 += chunk, k = (k + 1) % nstreams) {
         const size_t nc = (N - orb0 < chunk) ? N - orb0 : chunk;
-        CU(cudaMemsetAsync(queue.p, 0, sizeof(unsigned long long), c.stream));
+        CU(cudaMemsetAsync(queue[k].p, 0, sizeof(unsigned long long), st[k]));
         if (sorted) {
-            cudaError_t e = KCALL(c, dyn_time_keys, r.P, (const double*)dw0, N, two[0], orb0, nc, (float*)keys_in.p,
-                                  (uint32_t*)idx_in.p, c.stream);
+            cudaError_t e = KCALL(c, dyn_time_keys, r.P, (const double*)dw0, N, two[0], orb0, nc, (float*)keys_in[k].p,
+                                  (uint32_t*)idx_in[k].p, st[k]);
             if (e != cudaSuccess) return cuda_fail(e, "dyn_time_keys launch");
             g_launches++;
-            CU(gb_sort_pairs((const float*)keys_in.p, (float*)keys_out.p, (const uint32_t*)idx_in.p, (uint32_t*)perm.p,
-                             nc, temp.p, temp_bytes, c.stream));
+            CU(gb_sort_pairs((const float*)keys_in[k].p, (float*)keys_out[k].p, (const uint32_t*)idx_in[k].p,
+                             (uint32_t*)perm[k].p, nc, temp[k].p, temp_bytes, st[k]));
         }
-        double* kout = save_all ? (double*)scratch.p : (double*)dout;
-        const uint32_t* pp = sorted ? (const uint32_t*)perm.p : nullptr;
+        double* kout = save_all ? (double*)scratch[k].get() : (double*)dout;
+        const uint32_t* pp = sorted ? (const uint32_t*)perm[k].p : nullptr;
         cudaError_t e = (F.type == GB_FRAME_STATIC)
             ? KCALL(c, dop853_static, r.P, F, (const double*)dw0, N, (const double*)dtg, ntimes, a, save_all, pp,
-                    (unsigned long long*)queue.p, orb0, nc, kout, (int32_t*)dstat, dst[0], dst[1], dst[2], dst[3],
-                    block, c.stream)
+                    (unsigned long long*)queue[k].p, orb0, nc, kout, (int32_t*)dstat, dst[0], dst[1], dst[2], dst[3],
+                    block, st[k])
             : KCALL(c, dop853_rotating, r.P, F, (const double*)dw0, N, (const double*)dtg, ntimes, a, save_all, pp,
-                    (unsigned long long*)queue.p, orb0, nc, kout, (int32_t*)dstat, dst[0], dst[1], dst[2], dst[3],
-                    block, c.stream);
+                    (unsigned long long*)queue[k].p, orb0, nc, kout, (int32_t*)dstat, dst[0], dst[1], dst[2], dst[3],
+                    block, st[k]);
         if (e != cudaSuccess) return cuda_fail(e, "dop853 kernel launch");
         g_launches++;
         if (save_all) {
-            e = KCALL(c, dop853_transpose, (const double*)scratch.p, orb0, nc, ntimes, N, (double*)dout, c.stream);
+            e = KCALL(c, dop853_transpose, (const double*)scratch[k].get(), orb0, nc, ntimes, N, (double*)dout, st[k]);
             if (e != cudaSuccess) return cuda_fail(e, "dop853 transpose launch");
             g_launches++;
+        }
+    }
+    if (nstreams == 2) {
+        for (int q = 0; q < 2; q++) {
+            CU(cudaEventRecord(S->ev[q], S->s[q]));
+            CU(cudaStreamWaitEvent(c.stream, S->ev[q], 0));
         }
     }
     RET_IF(stage_out_copy(c, w_out, dout, ob));

@@ -216,6 +216,9 @@ template <> struct Composite<SIG_BAR_MW2022> : Seq<GB_POT_LONGMURALIBAR, GB_POT_
 template <> struct Composite<SIG_MW2022_BAR> : Seq<GB_POT_MN3, GB_POT_HERNQUIST, GB_POT_HERNQUIST, GB_POT_NFW_SPHERICAL, GB_POT_LONGMURALIBAR> {};
 template <> struct Composite<SIG_SCF> {
     GB_DEV static void gradient(const DevPot& P, double t, double x, double y, double z, double& gx, double& gy, double& gz) {
+#if !GB_STRICT
+        if (P.cext_ok) { scf_fast_gradient(P, &P.drv[0], x, y, z, gx, gy, gz); return; }   // warp-uniform
+#endif
         gx = 0.; gy = 0.; gz = 0.;
         PotSCF::gradient(&P.par[0], P.ext, x, y, z, gx, gy, gz);
     }

@@ -13,6 +13,7 @@
 #define GB_MP_LMAX 15  // largest multipole order the device evaluates
 #define GB_MAXC 8      // components per composite held in the constant bank
 #define GB_MAXP 120    // packed doubles of "small" parameters ([G, ...] of every component)
+#define GB_CEXT 616    // 2 x 11 x 28 doubles: (S,T) pairs of SCF(nmax=10,lmax=6), [l][m][n]
 #define GB_MAXD 40     // packed doubles of host-derived constants (G*m, b^2, 1/r_s, ...) for the fast build
 
 struct DevComp {
@@ -32,6 +33,9 @@ struct DevPot {
     DevComp c[GB_MAXC];
     double par[GB_MAXP];
     double drv[GB_MAXD];       // per component: gb_nderived(type) doubles, see gb_derive() in capi.cu
+    int32_t cext_ok;           // 1: cext holds the SCF coefficients of component 0 in the (10,6) padded layout
+    int32_t _pad2;
+    double cext[GB_CEXT];      // constant-bank copy of a small `ext` block (scf.cuh: scf_fast_gradient)
     const double* ext;         // device-global parameters of "large" components (SCF coefficients)
 };
 
@@ -57,13 +61,15 @@ enum GbSig {
 // Number of host-derived constants per potential type (filled by capi.cu:gb_derive, read by the
 // fast build's accum() functions in potentials.cuh; the strict build ignores them):
 //   Hernquist/Kepler/Jaffe [G m] ; NFW spherical [G m, 1/r_s] ; MiyamotoNagai/Plummer/Isochrone [G m, b^2] ;
-//   MN3 [G m1, G m2, G m3, b1^2, b2^2, b3^2] ; LongMuraliBar [G m, sin(alpha), cos(alpha), c^2].
+//   MN3 [G m1, G m2, G m3, b1^2, b2^2, b3^2] ; LongMuraliBar [G m, sin(alpha), cos(alpha), c^2] ;
+//   SCF [G m / r_s^2, 1 / r_s].
 constexpr int gb_nderived(int type) {
     return (type == GB_POT_HERNQUIST || type == GB_POT_KEPLER || type == GB_POT_JAFFE) ? 1
          : (type == GB_POT_NFW_SPHERICAL || type == GB_POT_MIYAMOTONAGAI || type == GB_POT_PLUMMER ||
             type == GB_POT_ISOCHRONE) ? 2
          : (type == GB_POT_MN3) ? 6
          : (type == GB_POT_LONGMURALIBAR) ? 4
+         : (type == GB_POT_SCF) ? 2
          : 0;
 }
 

@@ -300,7 +300,7 @@ cudaError_t GB_D8_NAME(const DevPot& P, const DevFrame& F, const double* w0, siz
     if (const char* eb = getenv("GB_D8_BLOCK")) block = atoi(eb);
     if (block > 256 || block <= 0 || (block & 31)) block = 64;      // __launch_bounds__(256)
     const char* bs = getenv("GB_D8_BLOCKSYNC");
-    const int block_sync = bs ? atoi(bs) : 0;
+    const int block_sync = bs ? atoi(bs) : (block > 32);
     if (save_all) {
         GB_SIG_SWITCH(P.sig, (e = launch_d8<C, true>(P, F, w0, N, t, ntimes, a, perm, queue, orb0, nslots, out, st, block, nsm, block_sync, s)));
     } else {

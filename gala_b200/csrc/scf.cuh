@@ -173,6 +173,133 @@ __device__ __noinline__ void scf_eval(const double* __restrict__ p, const double
     out[0] += gx * sc; out[1] += gy * sc; out[2] += gz * sc;
 }
 
+#if !GB_STRICT
+// ------------------------------------------------------------------------------------------------
+// Fast-build gradient for nmax <= 10, lmax <= 6 (BASELINE config C5) with everything resolved at
+// compile time.  Differences from scf_eval<10,6,0> above (same series, same recurrences):
+//   * the (S,T) pairs come from DevPot::cext -- the kernel-parameter constant bank -- in a fixed
+//     [l][m][n] layout padded to (10,6), so each of the 4 x 308 coefficient FMAs takes its coefficient
+//     as a constant-bank operand: no load instruction, no address arithmetic;
+//   * l, m, n loops are fully unrolled, so every recurrence coefficient ((2l-1)/(l-m), 2(n+lam-1)/n ...)
+//     is a literal: the first version spent ~1700 of its 4600 FP64 instructions per evaluation on ~150
+//     divisions by small integers (profiles/ncu_r1_leapfrog_scf_v0.txt);
+//   * the radial prefactors are applied to the (l) partial sums, not to each Phi_nl;
+//   * n is the outer loop of each l: one recurrence step feeds 4 (l+1) independent FMAs.
+// ~2300 FP64 instructions per evaluation.
+// ------------------------------------------------------------------------------------------------
+#define GB_SCF_NM 10
+#define GB_SCF_LM 6
+GB_DEV void scf_fast_gradient(const DevPot& P, const double* __restrict__ d, double x, double y, double z,
+                              double& ogx, double& ogy, double& ogz) {
+    constexpr int NM = GB_SCF_NM, LM = GB_SCF_LM;
+    const double* __restrict__ co = P.cext;
+    const double R2 = fma(y, y, x * x);
+    const double r2 = fma(z, z, R2);
+    const double ir = gb_rsqrt(r2);
+    const double r = r2 * ir;
+    const double s = r * d[1];                     // r / r_s
+    const double X = z * ir;                       // cos(theta)
+    const bool offaxis = R2 > 0.;
+    const double iR = gb_rsqrt(offaxis ? R2 : 1.);
+    const double cphi = offaxis ? x * iR : 1., sphi = offaxis ? y * iR : 0.;
+    const double sintheta = offaxis ? (R2 * iR) * ir : 0.;
+
+    double cm[LM + 1], sm[LM + 1];
+    cm[0] = 1.; sm[0] = 0.;
+#pragma unroll
+    for (int m = 1; m <= LM; m++) {
+        cm[m] = fma(cm[m - 1], cphi, -(sm[m - 1] * sphi));
+        sm[m] = fma(sm[m - 1], cphi, cm[m - 1] * sphi);
+    }
+    const double ops = 1. + s;
+    const double iops = gb_rcp(ops);
+    const double is = gb_rcp(s);
+    const double xi = (s - 1.) * iops;
+    const double rfac = s * (iops * iops);         // ratio of s^l (1+s)^(-2l-1) between consecutive l
+    double radial = iops;                          // s^0 (1+s)^(-1)
+    const double dscale = is * (iops * iops);      // dPhi prefactor relative to radial: 1/(s (1+s)^2)
+
+    double gr = 0., gt = 0., gp = 0.;
+    double Pl[LM + 1], Pm1[LM + 1], Pm2[LM + 1];
+#pragma unroll
+    for (int m = 0; m <= LM; m++) { Pl[m] = 0.; Pm1[m] = 0.; Pm2[m] = 0.; }
+    double pmm = 1.;
+#pragma unroll
+    for (int l = 0; l <= LM; l++) {
+        // ---- Legendre row l (Condon-Shortley phase) ----------------------------------------------
+#pragma unroll
+        for (int m = 0; m <= LM; m++) { Pm2[m] = Pm1[m]; Pm1[m] = Pl[m]; }
+        if (l > 0) pmm *= -(2. * l - 1.) * sintheta;
+#pragma unroll
+        for (int m = 0; m <= l; m++) {
+            if (m < l - 1) {
+                const double a = (2. * l - 1.) / (double)(l - m), b = (l + m - 1.) / (double)(l - m);   // literals
+                Pl[m] = fma(a, X * Pm1[m], -(b * Pm2[m]));
+            } else if (m == l - 1) {
+                Pl[m] = (X * (2. * m + 1.)) * Pm1[m];
+            } else {
+                Pl[m] = pmm;
+            }
+        }
+        // ---- Gegenbauer recurrences in n, accumulating the four sums of every m <= l -----------------
+        const double lam = 2. * l + 1.5, lam1 = lam + 1.;
+        double A0[LM + 1], B0[LM + 1], AD[LM + 1], BD[LM + 1];
+#pragma unroll
+        for (int m = 0; m <= LM; m++) { A0[m] = 0.; B0[m] = 0.; AD[m] = 0.; BD[m] = 0.; }
+        double ca = 0., cb = 0., da = 0., db = 0.;
+#pragma unroll
+        for (int n = 0; n <= NM; n++) {
+            double Cn, Dn;
+            if (n == 0) { Cn = 1.; Dn = 0.; }
+            else if (n == 1) { Cn = (2. * lam) * xi; Dn = 1.; }
+            else {
+                const double an = 2. * (n + lam - 1.) / n, bn = (n + 2. * lam - 2.) / n;               // literals
+                Cn = fma(an * xi, cb, -(bn * ca));
+                const int k = n - 1;
+                if (k == 1) Dn = (2. * lam1) * xi;
+                else {
+                    const double ak = 2. * (k + lam1 - 1.) / k, bk = (k + 2. * lam1 - 2.) / k;
+                    Dn = fma(ak * xi, db, -(bk * da));
+                }
+            }
+            ca = cb; cb = Cn; da = db; db = Dn;
+#pragma unroll
+            for (int m = 0; m <= l; m++) {
+                const int i = 2 * (((l * (l + 1)) / 2 + m) * (NM + 1) + n);
+                const double S = co[i], T = co[i + 1];
+                A0[m] = fma(Cn, S, A0[m]); B0[m] = fma(Cn, T, B0[m]);
+                if (n > 0) { AD[m] = fma(Dn, S, AD[m]); BD[m] = fma(Dn, T, BD[m]); }
+            }
+        }
+        // ---- angular sums of this l; radial prefactors applied once per l -------------------------------
+        const double poly = ops * fma((double)l, s - 1., s);
+        const double dcoef = (-2. * (3. + 4. * l)) * s;
+        double gr_l = 0., gt_l = 0., gp_l = 0.;
+#pragma unroll
+        for (int m = 0; m <= l; m++) {
+            const double CS0 = fma(cm[m], A0[m], sm[m] * B0[m]);
+            const double CSD = fma(cm[m], AD[m], sm[m] * BD[m]);
+            gr_l = fma(Pl[m], fma(dcoef, CSD, poly * CS0), gr_l);
+            if (l > 0) gt_l = fma(fma((double)l * X, Pl[m], -((double)(l + m) * Pm1[m])), CS0, gt_l);
+            if (m > 0) gp_l = fma((double)m * Pl[m], fma(cm[m], B0[m], -(sm[m] * A0[m])), gp_l);
+        }
+        const double pre = -GB_SQRT_FOURPI * radial;          // Phi_nl  = pre * C_n
+        const double dpre = (GB_SQRT_FOURPI * radial) * dscale;   // dPhi_nl = dpre * (dcoef D_n + poly C_n)
+        gr = fma(dpre, gr_l, gr);
+        gt = fma(pre, gt_l, gt);
+        gp = fma(pre, gp_l, gp);
+        radial *= rfac;
+    }
+    // common factors of the theta and phi components (bfe_helper.cpp:76-87, bfe.cpp:168-170)
+    const double ist = gb_rcp(sintheta * s);
+    gt *= ist; gp *= ist;
+    const double gx = fma(sintheta * cphi, gr, fma(X * cphi, gt, -(sphi * gp)));
+    const double gy = fma(sintheta * sphi, gr, fma(X * sphi, gt, cphi * gp));
+    const double gz = fma(X, gr, -(sintheta * gt));
+    ogx = gx * d[0]; ogy = gy * d[0]; ogz = gz * d[0];
+}
+#endif
+
 struct PotSCF {
     GB_DEV static void gradient(const double* p, const double* e, double x, double y, double z,
                                 double& gx, double& gy, double& gz) {

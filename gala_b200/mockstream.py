@@ -48,18 +48,17 @@ class FardalStreamDF:
     def _plan(self, prog_m, nparticles):
         """Particle bookkeeping in the reference's emission order: per timestep (skipping
         prog_m == 0), all trailing particles, then all leading particles (``df.pyx:393-454``)."""
-        idx, sign = [], []
-        for i in range(len(prog_m)):
-            if prog_m[i] == 0:
-                continue
-            n = int(nparticles[i])
-            if self._trail:
-                idx.append(np.full(n, i, dtype=np.int32)); sign.append(np.full(n, 1.0))
-            if self._lead:
-                idx.append(np.full(n, i, dtype=np.int32)); sign.append(np.full(n, -1.0))
-        if not idx:
+        prog_m = np.asarray(prog_m)
+        n = np.where(prog_m == 0, 0, np.asarray(nparticles, dtype=np.int64))
+        steps = np.nonzero(n)[0]
+        if steps.size == 0:
             return np.zeros(0, np.int32), np.zeros(0)
-        return np.concatenate(idx), np.concatenate(sign)
+        # per timestep: n trailing (+1) then n leading (-1) entries -- vectorised form of the loop
+        tails = ([1.0] if self._trail else []) + ([-1.0] if self._lead else [])
+        step_rep = np.repeat(steps, len(tails))                 # timestep of each (timestep, tail) block
+        sign_rep = np.tile(np.array(tails), steps.size)
+        counts = n[step_rep]
+        return np.repeat(step_rep, counts).astype(np.int32), np.repeat(sign_rep, counts)
 
     def _sample(self, potential, prog_x, prog_v, prog_t, prog_m, nparticles):
         """(ntimes,3) progenitor positions / velocities -> particle_x (Np,3), particle_v, particle_t1."""
@@ -107,15 +106,8 @@ class FardalStreamDF:
             n_particles = np.zeros(len(prog_t), dtype="i4")
             n_particles[::release_every] = N
         x, v, t1 = self._sample(H.potential, prog_x, prog_v, prog_t, prog_m, n_particles)
-        lt = np.empty(len(t1), dtype="U1")
-        i = 0
-        for k, n in enumerate(n_particles):
-            if prog_m[k] == 0:
-                continue
-            if self._trail:
-                lt[i:i + n] = "t"; i += n
-            if self._lead:
-                lt[i:i + n] = "l"; i += n
+        _, sign = self._plan(prog_m, n_particles)
+        lt = np.where(sign > 0, "t", "l").astype("U1")
         return MockStream(pos=x.T, vel=v.T, release_time=t1, lead_trail=lt, frame=H.frame)
 
 
@@ -231,6 +223,27 @@ def mockstream_leapfrog(nbody, full_time, spawn_time, stream_w0, stream_t1, tfin
     return out[Np:].copy(), out[:Np].copy()
 
 
+def _scatter_isclose(orbit_t, unq_t1s, nstream):
+    """``all_nstream[np.isclose(orbit_t, t1)] = n`` for every (t1, n) (mockstream_generator.py:297-299)
+    without the O(ntimes^2) loop: candidates come from a sorted search, the same ``np.isclose`` predicate
+    (rtol 1e-5, atol 1e-8, relative to t1) decides, later t1 overwrite earlier ones as in the loop."""
+    all_nstream = np.zeros(len(orbit_t), dtype=int)
+    order = np.argsort(orbit_t, kind="stable")
+    ts = orbit_t[order]
+    tol = 1e-8 + 1e-5 * np.abs(unq_t1s)
+    lo = np.searchsorted(ts, unq_t1s - tol, side="left")
+    hi = np.searchsorted(ts, unq_t1s + tol, side="right")
+    if np.all(hi - lo <= 1):
+        hit = hi > lo
+        cand = order[lo[hit]]
+        ok = np.isclose(orbit_t[cand], unq_t1s[hit])
+        all_nstream[cand[ok]] = nstream[hit][ok]
+        return all_nstream
+    for t1, n in zip(unq_t1s, nstream):          # overlapping tolerance windows: keep the loop's semantics
+        all_nstream[np.isclose(orbit_t, t1)] = n
+    return all_nstream
+
+
 class MockStreamGenerator:
     """``dynamics/mockstream/mockstream_generator.py``: orchestration is unchanged; the three heavy
     steps (progenitor orbit, particle release, stream integration) each run as one GPU call."""
@@ -279,9 +292,7 @@ class MockStreamGenerator:
                                    release_every=release_every, n_particles=n_particles)
         w0 = np.ascontiguousarray(np.vstack((stream_w0.pos, stream_w0.vel)).T)
         unq_t1s, nstream = np.unique(stream_w0.release_time, return_counts=True)
-        all_nstream = np.zeros(prog_orbit.ntimes, dtype=int)
-        for t1, n in zip(unq_t1s, nstream):
-            all_nstream[np.isclose(orbit_t, t1)] = n
+        all_nstream = _scatter_isclose(orbit_t, unq_t1s, nstream)
         nstream_idx = np.where(all_nstream != 0)[0]
         if 0 not in nstream_idx:
             nstream_idx = np.insert(nstream_idx, 0, 0)

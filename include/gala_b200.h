@@ -194,6 +194,11 @@ const char* gb_version(void);
  * denominator bench.py reports against (MEASURED_PEAKS.json carries no FP64 figure). */
 double gb_fp64_peak_tflops(int reps);
 
+/* Frees the device staging / scratch buffers the library keeps cached between calls (HOST-mode staging
+ * of inputs and outputs; the orbit-major dense-output scratch of gb_dop853, up to half of the free
+ * device memory).  Safe to call at any time from the thread that made the calls. */
+int gb_release_scratch(void);
+
 /* Diagnostic: y[i] = f(x[i]) with the math primitive the selected build (opt->strict_math) uses
  * inside the kernels: which = 0: 1/x, 1: x^-1/2, 2: x^-3/2, 3: ln x.  The fast build replaces the
  * CUDA library expansions by seed + fixed refinement (csrc/fastmath.cuh); this entry lets the test

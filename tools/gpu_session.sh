@@ -30,6 +30,8 @@ c2bs)    for v in "64 0" "128 1" "256 1" "128 0"; do
             timeout 900 python bench.py --workload c2 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/bench_c2_b$1_s$2.json 2> $OUT/bench_c2_b$1_s$2.err; echo "block $1 sync $2: $(tail -1 $OUT/bench_c2_b$1_s$2.json | cut -c1-120)"
          done; unset GB_D8_BLOCK GB_D8_BLOCKSYNC ;;
 launches_c2) ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches_c2.csv python bench.py --workload c2 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/launches_c2.log 2>&1; grep -c k_ $OUT/launches_c2.csv ;;
+c3)      for w in c3 c3d; do timeout 900 python bench.py --workload $w --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/bench_$w.json 2> $OUT/bench_$w.err; tail -1 $OUT/bench_$w.json | cut -c1-200; tail -2 $OUT/bench_$w.err; done ;;
+b1)      w=$B1W; timeout 900 python bench.py --workload $w --steps 3 --warmup 3 --no-cpu-baseline > $OUT/bench_$w.json 2> $OUT/bench_$w.err; tail -1 $OUT/bench_$w.json | cut -c1-220; tail -2 $OUT/bench_$w.err ;;
 d8stats) timeout 600 python tools/d8_stats.py > $OUT/d8_stats.json 2> $OUT/d8_stats.err; head -50 $OUT/d8_stats.json ;;
 *) echo "unknown step $s" ;;
 esac
