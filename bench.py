@@ -98,7 +98,7 @@ def workload(name, n_orbits):
         stats = {}
 
         def run(w0, tt, out=None):
-            res = gb.dop853_integrate_hamiltonian(H, w0, tt, save_all=1, return_status=True)
+            res = gb.dop853_integrate_hamiltonian(H, w0, tt, save_all=1, return_status=True, out=out)
             stats["nstep"] = res[2]["nstep"]
             return res[1]
 
@@ -149,16 +149,53 @@ def workload(name, n_orbits):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md clocks line).  Sampled
+    in-process through NVML every 20 ms: a polling `nvidia-smi -lms` child serialises against this
+    process's own driver calls (measured: it stretched a 34 ms C2 step to 108 ms); nvidia-smi is only the
+    fallback when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, force_smi=False):
         self.rows, self.proc, self.idx = [], None, gpu_index
+        self.nv, self.h, self.stop_flag, self.thread = None, None, False, None
+        self.sm, self.smax, self.reasons, self.how = [], None, set(), None
+        if not force_smi:
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+                self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+                self.nv = pynvml
+            except Exception:
+                self.nv = None
+
+    def _poll_nvml(self):
+        nv = self.nv
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, nm in names.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def start(self):
+        if self.nv is not None:
+            self.how = "nvml 20ms"
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
         try:
+            self.how = "nvidia-smi -lms 100"
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
@@ -170,6 +207,11 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(1.0)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smax,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "how": self.how}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -185,7 +227,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "how": self.how}
 
 
 def cpu_reference_rate(name, H, t, seconds_target=12.0, threads=None):
@@ -247,6 +289,7 @@ def main():
     ap.add_argument("--strict", action="store_true", help="use the strict-IEEE kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--smi-clocks", action="store_true", help="sample clocks with an nvidia-smi child (A/B only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -310,7 +353,7 @@ def main():
     torch.cuda.synchronize()
 
     clocks = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
-                          int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+                          int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]), force_smi=args.smi_clocks)
     if rank == 0:
         clocks.start()
     n0 = gb._abi.launch_count()
@@ -344,10 +387,10 @@ def main():
         pin = torch.empty(w0_host.shape, dtype=torch.float64).pin_memory()
         pin.numpy()[...] = w0_host
         w0_pinned = pin.numpy()
-        out_h = run(w0_pinned, t)
+        out_shape = (6, len(t), N) if args.workload == "c2" else np.asarray(run(w0_pinned, t)).shape
         # the result lands in a caller-provided page-locked array (gb.pinned_empty), as the inputs do:
         # with pageable arrays the driver stages every copy and page-faults the fresh result buffer
-        out_pin = gb.pinned_empty(np.asarray(out_h).shape) if args.workload != "c2" else None
+        out_pin = gb.pinned_empty(out_shape)
         out_h = run(w0_pinned, t, out_pin)
         e2e_units = 0
         barrier()

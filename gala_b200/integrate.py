@@ -170,17 +170,19 @@ def ruth4_integrate_hamiltonian(hamiltonian, w0, t, save_all=1, allow_rotating_f
 
 
 def dop853_integrate_hamiltonian(hamiltonian, w0, t, atol=1e-10, rtol=1e-10, nmax=0, dt_max=0.0, nstiff=0,
-                                 save_all=1, err_if_fail=1, log_output=0, nbatch=100, return_status=False):
+                                 save_all=1, err_if_fail=1, log_output=0, nbatch=100, return_status=False, out=None):
     """``dop853.pyx:196-250``.  Step-size control is per orbit (the reference's ``nbatch=1``); the
     ``nbatch`` argument is accepted and ignored.  With ``err_if_fail`` a failed orbit raises
-    ``RuntimeError("Integration failed with code ...")`` like ``dop853.pyx:184-185``."""
+    ``RuntimeError("Integration failed with code ...")`` like ``dop853.pyx:184-185``.  ``out`` (extension):
+    preallocated result array, e.g. ``pinned_empty`` for the host-buffer path."""
     _check_c_enabled(hamiltonian)
     w = _prep_w0(w0)
     th, tb = _prep_t(t, w)
     N, ntimes = w.arr.shape[1], th.size
     if ntimes < 1:
         raise ValueError("ntimes must be greater than 1")
-    out = _alloc(w, (6, ntimes, N) if save_all else (6, N))
+    shape = (6, ntimes, N) if save_all else (6, N)
+    out = _alloc(w, shape) if out is None else _check_out(out, w, shape)
     status = _alloc(w, (N,), "i4")
     stats = None
     stats_struct = None

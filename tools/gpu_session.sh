@@ -33,6 +33,14 @@ launches_c2) ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --
 c3)      for w in c3 c3d; do timeout 900 python bench.py --workload $w --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/bench_$w.json 2> $OUT/bench_$w.err; tail -1 $OUT/bench_$w.json | cut -c1-200; tail -2 $OUT/bench_$w.err; done ;;
 b1)      w=$B1W; timeout 900 python bench.py --workload $w --steps 3 --warmup 3 --no-cpu-baseline > $OUT/bench_$w.json 2> $OUT/bench_$w.err; tail -1 $OUT/bench_$w.json | cut -c1-220; tail -2 $OUT/bench_$w.err ;;
 d8stats) timeout 600 python tools/d8_stats.py > $OUT/d8_stats.json 2> $OUT/d8_stats.err; head -50 $OUT/d8_stats.json ;;
+d8ab)    for v in default loop loop2 noinline; do
+            [ $v = default ] && unset GALA_B200_LIB || export GALA_B200_LIB=$PWD/gala_b200/libgala_b200_$v.so
+            timeout 600 python tools/c2_phases.py 303104 1 > $OUT/phases_$v.json 2> $OUT/phases_$v.err; python -c "
+import json,sys; d=json.load(open('$OUT/phases_$v.json')); r=d['rows'][-1]; print('$v dense', {k:round(x,2) for k,x in r.items()})"
+            timeout 600 python tools/c2_phases.py 303104 0 > $OUT/phases_fs_$v.json 2> $OUT/phases_fs_$v.err; python -c "
+import json,sys; d=json.load(open('$OUT/phases_fs_$v.json')); r=d['rows'][-1]; print('$v final', {k:round(x,2) for k,x in r.items()})"
+            [ $v != default ] && { timeout 900 python -m pytest tests -m gpu -x -q -k "dop853 or mockstream" > $OUT/pytest_$v.log 2>&1; tail -1 $OUT/pytest_$v.log; }
+         done; unset GALA_B200_LIB ;;
 *) echo "unknown step $s" ;;
 esac
 done
