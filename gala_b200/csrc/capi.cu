@@ -39,6 +39,10 @@ int expected_npar(int type) {
         case GB_POT_LONGMURALIBAR: return 6;
         case GB_POT_KEPLER: return 2;
         case GB_POT_PLUMMER: case GB_POT_ISOCHRONE: case GB_POT_JAFFE: return 3;
+        case GB_POT_STONE: case GB_POT_SATOH: case GB_POT_POWERLAWCUTOFF: return 4;
+        case GB_POT_BURKERT: case GB_POT_KUZMIN: return 3;
+        case GB_POT_LOGARITHMIC: return 7;
+        case GB_POT_LEESUTO: return 6;
         default: return -1;
     }
 }

@@ -26,12 +26,20 @@ template <> struct PotOf<GB_POT_KEPLER>        { using type = PotKepler;        
 template <> struct PotOf<GB_POT_PLUMMER>       { using type = PotPlummer;       static constexpr int NP = 3; };
 template <> struct PotOf<GB_POT_ISOCHRONE>     { using type = PotIsochrone;     static constexpr int NP = 3; };
 template <> struct PotOf<GB_POT_JAFFE>         { using type = PotJaffe;         static constexpr int NP = 3; };
+template <> struct PotOf<GB_POT_STONE>         { using type = PotStone;         static constexpr int NP = 4; };
+template <> struct PotOf<GB_POT_BURKERT>       { using type = PotBurkert;       static constexpr int NP = 3; };
+template <> struct PotOf<GB_POT_SATOH>         { using type = PotSatoh;         static constexpr int NP = 4; };
+template <> struct PotOf<GB_POT_KUZMIN>        { using type = PotKuzmin;        static constexpr int NP = 3; };
+template <> struct PotOf<GB_POT_LOGARITHMIC>   { using type = PotLogarithmic;   static constexpr int NP = 7; };
+template <> struct PotOf<GB_POT_LEESUTO>       { using type = PotLeeSuto;       static constexpr int NP = 6; };
+template <> struct PotOf<GB_POT_POWERLAWCUTOFF>{ using type = PotPowerLawCutoff;static constexpr int NP = 4; };
 
 // ---- runtime (generic) component dispatch -----------------------------------------------------
 #define GB_FOR_EACH_SIMPLE_TYPE(X) \
     X(GB_POT_NULL) X(GB_POT_HERNQUIST) X(GB_POT_NFW_SPHERICAL) X(GB_POT_NFW_FLATTENED) X(GB_POT_NFW_TRIAXIAL) \
     X(GB_POT_MIYAMOTONAGAI) X(GB_POT_MN3) X(GB_POT_LONGMURALIBAR) X(GB_POT_KEPLER) X(GB_POT_PLUMMER) \
-    X(GB_POT_ISOCHRONE) X(GB_POT_JAFFE)
+    X(GB_POT_ISOCHRONE) X(GB_POT_JAFFE) X(GB_POT_STONE) X(GB_POT_BURKERT) X(GB_POT_SATOH) X(GB_POT_KUZMIN) \
+    X(GB_POT_LOGARITHMIC) X(GB_POT_LEESUTO) X(GB_POT_POWERLAWCUTOFF)
 
 GB_DEV void gb_comp_gradient(int type, const double* p, const double* e, double x, double y, double z,
                              double& gx, double& gy, double& gz) {

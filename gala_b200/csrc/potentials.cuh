@@ -434,3 +434,276 @@ struct PotLongMuraliBar {
         return p[1] / (8. * GB_PI * a) * (Pxx + Pyy + Pzz);
     }
 };
+
+// ================================================================================================
+// Remaining analytic builtins.  All of them accumulate through the generic
+// (gx,gy,gz) path in the fast build; strict mode mirrors the reference's statements.
+// ================================================================================================
+
+// ---- Stone & Ostriker 2015 (builtin_potentials.cpp:662-719): [G, m, r_c, r_h] ------------------
+struct PotStone {
+    GB_DEV static void gradient(const double* p, double x, double y, double z, double& gx, double& gy, double& gz) {
+        const double r = gb_norm3(x, y, z);
+        const double u_c = r / p[2];
+        const double u_h = r / p[3];
+        const double fac = 2 * p[0] * p[1] / (GB_PI * r * r * r) / (p[2] - p[3]);
+        const double dphi_dr = fac * (p[2] * atan(u_c) - p[3] * atan(u_h));
+        gx = gx + dphi_dr * x; gy = gy + dphi_dr * y; gz = gz + dphi_dr * z;
+    }
+    GB_DEV static double value(const double* p, double x, double y, double z) {
+        const double r = gb_norm3(x, y, z);
+        const double u_c = r / p[2];
+        const double u_h = r / p[3];
+        const double fac = 2 * p[0] * p[1] / GB_PI / (p[3] - p[2]);
+        if (r == 0) return -fac * 0.5 * log(p[3] * p[3] / (p[2] * p[2]));
+        return -fac * (atan(u_h) / u_h - atan(u_c) / u_c + 0.5 * log((r * r + p[3] * p[3]) / (r * r + p[2] * p[2])));
+    }
+    GB_DEV static double density(const double* p, double x, double y, double z) {
+        const double r = gb_norm3(x, y, z);
+        const double rho = p[1] * (p[2] + p[3]) / (2 * GB_PI * GB_PI * p[2] * p[2] * p[3] * p[3]);
+        const double u_c = r / p[2];
+        const double u_t = r / p[3];
+        return rho / ((1 + u_c * u_c) * (1 + u_t * u_t));
+    }
+    GB_ACCUM_VIA_GRADIENT
+};
+
+// ---- Burkert (builtin_potentials.cpp:2238-2279): [G, rho, r0] ----------------------------------
+struct PotBurkert {
+    GB_DEV static void gradient(const double* p, double x, double y, double z, double& gx, double& gy, double& gz) {
+        const double r = gb_norm3(x, y, z);
+        const double u = r / p[2];
+        const double dphi_dr = -GB_PI * p[0] * p[1] * p[2] / (u * u) * (2 * atan(u) - 2 * log(1 + u) - log(1 + u * u));
+        gx = gx + dphi_dr * x / r; gy = gy + dphi_dr * y / r; gz = gz + dphi_dr * z / r;
+    }
+    GB_DEV static double value(const double* p, double x, double y, double z) {
+        const double r = gb_norm3(x, y, z);
+        const double u = r / p[2];
+        return -GB_PI * p[0] * p[1] * p[2] * p[2] *
+               (GB_PI - 2 * (1 + 1 / u) * atan(u) + 2 * (1 + 1 / u) * log(1 + u) - (1 - 1 / u) * log(1 + u * u));
+    }
+    GB_DEV static double density(const double* p, double x, double y, double z) {
+        const double u = gb_norm3(x, y, z) / p[2];
+        return p[1] / ((1 + u) * (1 + u * u));
+    }
+    GB_ACCUM_VIA_GRADIENT
+};
+
+// ---- Satoh (builtin_potentials.cpp:1147-1186): [G, m, a, b] ------------------------------------
+struct PotSatoh {
+    GB_DEV static void gradient(const double* p, double x, double y, double z, double& gx, double& gy, double& gz) {
+        const double zb = sqrt(z * z + p[3] * p[3]);
+        const double S2 = (x * x + y * y + z * z) + p[2] * (p[2] + 2 * zb);
+        const double dPhi_dS = p[0] * p[1] / S2;
+        const double S = sqrt(S2);
+        gx = gx + dPhi_dS * x / S;
+        gy = gy + dPhi_dS * y / S;
+        gz = gz + dPhi_dS / S * z * (1 + p[2] / zb);
+    }
+    GB_DEV static double value(const double* p, double x, double y, double z) {
+        const double S2 = (x * x + y * y + z * z) + p[2] * (p[2] + 2 * sqrt(z * z + p[3] * p[3]));
+        return -p[0] * p[1] / sqrt(S2);
+    }
+    GB_DEV static double density(const double* p, double x, double y, double z) {
+        const double z2b2 = z * z + p[3] * p[3];
+        const double xyz2 = x * x + y * y + z * z;
+        const double S2 = xyz2 + p[2] * (p[2] + 2 * sqrt(z2b2));
+        const double A = p[1] * p[2] * p[3] * p[3] / (4 * GB_PI * S2 * sqrt(S2) * z2b2);
+        return A * (1 / sqrt(z2b2) + 3 / p[2] * (1 - xyz2 / S2));
+    }
+    GB_ACCUM_VIA_GRADIENT
+};
+
+// ---- Kuzmin disc (builtin_potentials.cpp:1235-1283): [G, m, a] ---------------------------------
+struct PotKuzmin {
+    GB_DEV static void gradient(const double* p, double x, double y, double z, double& gx, double& gy, double& gz) {
+        const double az = p[2] + fabs(z);
+        const double S2 = x * x + y * y + az * az;
+        const double fac = p[0] * p[1] * gb_pow_m1p5(S2);
+        const double zsign = (z > 0) ? 1. : ((z < 0) ? -1. : 0.);
+        gx = gx + fac * x; gy = gy + fac * y; gz = gz + fac * zsign * az;
+    }
+    GB_DEV static double value(const double* p, double x, double y, double z) {
+        const double az = p[2] + fabs(z);
+        return -p[0] * p[1] / sqrt(x * x + y * y + az * az);
+    }
+    GB_DEV static double density(const double* p, double x, double y, double z) {
+        if (z != 0.) return 0.;
+        return p[1] * p[2] / (2 * GB_PI) * pow(x * x + y * y + p[2] * p[2], -1.5);
+    }
+    GB_ACCUM_VIA_GRADIENT
+};
+
+// ---- Logarithmic, triaxial, rotated by phi about z (builtin_potentials.cpp:1560-1625):
+//      [G, v_c, r_h, q1, q2, q3, phi] ------------------------------------------------------------
+struct PotLogarithmic {
+    GB_DEV static void gradient(const double* p, double qx, double qy, double qz, double& gx, double& gy, double& gz) {
+        double sp, cp;
+        sincos(p[6], &sp, &cp);
+        const double x = qx * cp + qy * sp;
+        const double y = -qx * sp + qy * cp;
+        const double z = qz;
+        const double fac = p[1] * p[1] / (p[2] * p[2] + x * x / (p[3] * p[3]) + y * y / (p[4] * p[4]) + z * z / (p[5] * p[5]));
+        const double ax = fac * x / (p[3] * p[3]);
+        const double ay = fac * y / (p[4] * p[4]);
+        const double az = fac * z / (p[5] * p[5]);
+        gx = gx + (ax * cp - ay * sp);
+        gy = gy + (ax * sp + ay * cp);
+        gz = gz + az;
+    }
+    GB_DEV static double value(const double* p, double qx, double qy, double qz) {
+        double sp, cp;
+        sincos(p[6], &sp, &cp);
+        const double x = qx * cp + qy * sp;
+        const double y = -qx * sp + qy * cp;
+        return 0.5 * p[1] * p[1] * log(p[2] * p[2] + x * x / (p[3] * p[3]) + y * y / (p[4] * p[4]) + qz * qz / (p[5] * p[5]));
+    }
+    // the reference's density ignores phi (it uses q directly, :1579-1601); reproduced as coded
+    GB_DEV static double density(const double* p, double x, double y, double z) {
+        const double q1s = p[3] * p[3], q2s = p[4] * p[4], q3s = p[5] * p[5];
+        const double t2 = q1s * q2s;
+        const double t3 = t2 * (z * z);
+        const double t5 = q1s * q3s;
+        const double t6 = t5 * (y * y);
+        const double t7 = q2s * q3s;
+        const double t8 = t7 * (x * x);
+        const double t9 = p[2] * p[2] * t2 * q3s;
+        const double t10 = t6 + t8 + t9;
+        const double t11 = t3 + t9;
+        const double den = t10 + t3;
+        return p[1] * p[1] * (t2 * (t10 - t3) + t5 * (t11 - t6 + t8) + t7 * (t11 + t6 - t8)) / (den * den) / (4 * GB_PI * p[0]);
+    }
+    GB_ACCUM_VIA_GRADIENT
+};
+
+// ---- Lee & Suto 2003 triaxial NFW (builtin_potentials.cpp:1446-1558): [G, v_c, r_s, a, b, c] ----
+struct PotLeeSuto {
+    GB_DEV static double vh2(const double* p, double& e_b2, double& e_c2) {
+        const double ba = p[4] / p[3], ca = p[5] / p[3];
+        e_b2 = 1 - ba * ba;
+        e_c2 = 1 - ca * ca;
+        const double ln2 = 0.6931471805599453;
+        return p[1] * p[1] / (ln2 - 0.5 + (ln2 - 0.75) * e_b2 + (ln2 - 0.75) * e_c2);
+    }
+    GB_DEV static void gradient(const double* p, double x, double y, double z, double& gx, double& gy, double& gz) {
+        double e_b2, e_c2;
+        const double v_h2 = vh2(p, e_b2, e_c2);
+        const double rs = p[2];
+        const double r2 = x * x + y * y + z * z;
+        const double r = sqrt(r2);
+        const double r4 = r2 * r2;
+        const double x0 = r + rs;
+        const double x1 = x0 * x0;
+        const double x2 = v_h2 / (12. * r4 * r2 * r * x1);
+        const double x10 = log(x0 / rs);
+        const double x13 = r * 3. * rs;
+        const double x15 = x13 - r2;
+        const double x16 = x15 + 6. * (rs * rs);
+        const double x17 = 6. * rs * x0 * (r * x16 - x0 * x10 * 6. * (rs * rs));
+        const double x20 = x0 * r2;
+        const double x21 = 2. * r * x0;
+        const double x7 = e_b2 * y * y + e_c2 * z * z;
+        const double x22 = -12. * r4 * r * rs * x0 + 12. * r4 * rs * x1 * x10 +
+                           3. * rs * x7 * (x16 * r2 - 18. * x1 * x10 * (rs * rs) + x20 * (2. * r - 3. * rs) + x21 * (x15 + 9. * (rs * rs))) -
+                           x20 * (e_b2 + e_c2) * (-6. * r * rs * (r2 - (rs * rs)) + 6. * rs * x0 * x10 * (r2 - 3. * (rs * rs)) +
+                                                  x20 * (-4. * r + 3. * rs) + x21 * (-x13 + 2. * r2 + 6. * (rs * rs)));
+        gx = gx + x2 * x * (x17 * x7 + x22);
+        gy = gy + x2 * y * (x17 * (x7 - r2 * e_b2) + x22);
+        gz = gz + x2 * z * (x17 * (x7 - r2 * e_c2) + x22);
+    }
+    GB_DEV static double value(const double* p, double x, double y, double z) {
+        double e_b2, e_c2;
+        const double phi0 = vh2(p, e_b2, e_c2);
+        const double r = sqrt(x * x + y * y + z * z);
+        const double u = r / p[2];
+        if (u == 0) return phi0;
+        const double l1u = log(1 + u);
+        const double F1 = -l1u / u;
+        const double F2 = -1 / 3. + (2 * u * u - 3 * u + 6) / (6 * u * u) + (1 / u - pow(u, -3.)) * l1u;
+        const double F3 = (u * u - 3 * u - 6) / (2 * u * u * (1 + u)) + 3 * pow(u, -3.) * l1u;
+        const double costh2 = z * z / (r * r);
+        const double sinth2 = 1 - costh2;
+        const double sinph2 = y * y / (x * x + y * y);
+        return phi0 * (F1 + (e_b2 + e_c2) / 2. * F2 + (e_b2 * sinth2 * sinph2 + e_c2 * costh2) / 2. * F3);
+    }
+    GB_DEV static double density(const double* p, double x, double y, double z) {
+        const double b_a2 = p[4] * p[4] / (p[3] * p[3]);
+        const double c_a2 = p[5] * p[5] / (p[3] * p[3]);
+        double e_b2, e_c2;
+        const double v_h2 = vh2(p, e_b2, e_c2);
+        const double u = sqrt(x * x + y * y / b_a2 + z * z / c_a2) / p[2];
+        return v_h2 / (u * (1 + u) * (1 + u)) / (4. * GB_PI * p[2] * p[2] * p[0]);
+    }
+    GB_ACCUM_VIA_GRADIENT
+};
+
+// ---- Power law with exponential cutoff (builtin_potentials.cpp:465-554): [G, m, alpha, r_c] -----
+// The reference calls GSL (gsl_sf_gamma_inc_P, gsl_sf_gamma; system library, absent here).  The
+// regularised lower incomplete gamma function P(a,x) is evaluated from its published series
+// (x < a+1) and Lentz continued fraction (otherwise), both to double-precision convergence.
+GB_DEV double gb_gamma_inc_P(double a, double x) {
+    if (!(x > 0.)) return 0.;
+    const double lead = exp(a * log(x) - x - lgamma(a));
+    if (x < a + 1.) {
+        double ap = a, del = 1. / a, sum = del;
+        for (int n = 0; n < 500; n++) {
+            ap += 1.;
+            del *= x / ap;
+            sum += del;
+            if (fabs(del) < fabs(sum) * 1e-17) break;
+        }
+        return sum * lead;
+    }
+    const double tiny = 1e-300;
+    double b = x + 1. - a, c = 1. / tiny, d = 1. / b, h = d;
+    for (int i = 1; i < 500; i++) {
+        const double an = -(double)i * ((double)i - a);
+        b += 2.;
+        d = an * d + b; if (fabs(d) < tiny) d = tiny;
+        c = b + an / c; if (fabs(c) < tiny) c = tiny;
+        d = 1. / d;
+        const double del = d * c;
+        h *= del;
+        if (fabs(del - 1.) < 1e-16) break;
+    }
+    return 1. - lead * h;
+}
+// lower incomplete gamma for any real a (safe_gamma_inc, :467-489): recurrence down from a+N > 0
+GB_DEV double gb_safe_gamma_inc(double a, double x) {
+    if (a > 0) return gb_gamma_inc_P(a, x) * tgamma(a);
+    const int N = (int)ceil(-a);
+    double A = 1., B = 0.;
+    for (int n = 0; n < N; n++) {
+        A = A * (a + n);
+        double tmp = 1.;
+        for (int m = N - 1; m > n; m--) tmp = tmp * (a + m);
+        B = B + pow(x, a + n) * exp(-x) * tmp;
+    }
+    return (B + gb_gamma_inc_P(a + N, x) * tgamma(a + N)) / A;
+}
+struct PotPowerLawCutoff {
+    GB_DEV static void gradient(const double* p, double x, double y, double z, double& gx, double& gy, double& gz) {
+        const double r = gb_norm3(x, y, z);
+        const double dPhi_dr = p[0] * p[1] / (r * r * r) * gb_gamma_inc_P(0.5 * (3 - p[2]), r * r / (p[3] * p[3]));
+        gx = gx + dPhi_dr * x; gy = gy + dPhi_dr * y; gz = gz + dPhi_dr * z;
+    }
+    GB_DEV static double value(const double* p, double x, double y, double z) {
+        const double r = gb_norm3(x, y, z);
+        if (r == 0.) return -CUDART_INF;
+        const double t0 = p[2] / 2.0, t1 = -t0, t2 = t1 + 1.5;
+        const double t3 = r * r;
+        const double t4 = t3 / (p[3] * p[3]);
+        const double t5 = p[0] * p[1];
+        const double t6 = t5 * gb_safe_gamma_inc(t2, t4) / (sqrt(t3) * tgamma(t1 + 2.5));
+        const double phi_r = t0 * t6 - 3.0 / 2.0 * t6 + t5 * gb_safe_gamma_inc(t1 + 1, t4) / (p[3] * tgamma(t2));
+        double phi_inf = 0.0;
+        if (t2 > 0) phi_inf = t5 * tgamma(t1 + 1) / (p[3] * tgamma(t2));
+        return phi_r - phi_inf;
+    }
+    GB_DEV static double density(const double* p, double x, double y, double z) {
+        const double r = gb_norm3(x, y, z);
+        const double A = p[1] / (2 * GB_PI) * pow(p[3], p[2] - 3) / tgamma(0.5 * (3 - p[2]));
+        return A * pow(r, -p[2]) * exp(-r * r / (p[3] * p[3]));
+    }
+    GB_ACCUM_VIA_GRADIENT
+};

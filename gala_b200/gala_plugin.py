@@ -29,7 +29,9 @@ WRAPPER_TO_TYPE = {           # potential/potential/builtin/cybuiltin.pyx:99-122
     "MN3ExponentialDiskWrapper": _abi.POT_MN3, "LongMuraliBarWrapper": _abi.POT_LONGMURALIBAR,
     "SCFWrapper": _abi.POT_SCF, "KeplerWrapper": _abi.POT_KEPLER, "PlummerWrapper": _abi.POT_PLUMMER,
     "IsochroneWrapper": _abi.POT_ISOCHRONE, "JaffeWrapper": _abi.POT_JAFFE,
-    "MultipoleWrapper": _abi.POT_MULTIPOLE,
+    "MultipoleWrapper": _abi.POT_MULTIPOLE, "StoneWrapper": _abi.POT_STONE, "BurkertWrapper": _abi.POT_BURKERT,
+    "SatohWrapper": _abi.POT_SATOH, "KuzminWrapper": _abi.POT_KUZMIN, "LogarithmicWrapper": _abi.POT_LOGARITHMIC,
+    "LeeSutoTriaxialNFWWrapper": _abi.POT_LEESUTO, "PowerLawCutoffWrapper": _abi.POT_POWERLAWCUTOFF,
 }
 
 

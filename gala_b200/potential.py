@@ -15,13 +15,15 @@ from collections import OrderedDict
 import numpy as np
 
 from . import _abi
-from .units import galactic, strip
+from .units import galactic, strip, KMS_TO_KPC_MYR
 
 __all__ = [
     "PotentialBase", "CCompositePotential", "NullPotential", "KeplerPotential", "HernquistPotential",
     "PlummerPotential", "IsochronePotential", "JaffePotential", "NFWPotential", "MiyamotoNagaiPotential",
     "MN3ExponentialDiskPotential", "LongMuraliBarPotential", "SCFPotential", "MultipolePotential", "MilkyWayPotential",
-    "MilkyWayPotential2022",
+    "MilkyWayPotential2022", "StonePotential", "BurkertPotential", "SatohPotential", "KuzminPotential",
+    "LogarithmicPotential", "LeeSutoTriaxialNFWPotential", "PowerLawCutoffPotential", "LM10Potential",
+    "BovyMWPotential2014",
 ]
 
 
@@ -310,6 +312,67 @@ class LongMuraliBarPotential(PotentialBase):
         super().__init__(m=m, a=a, b=b, c=c, alpha=alpha, **kw)
 
 
+class StonePotential(PotentialBase):
+    """Stone & Ostriker (2015) (builtin/core.py:306-328); C vector [m, r_c, r_h]."""
+    _type_id = _abi.POT_STONE
+    _param_names = ("m", "r_c", "r_h")
+
+    def __init__(self, m, r_c, r_h, **kw):
+        super().__init__(m=m, r_c=r_c, r_h=r_h, **kw)
+
+
+class BurkertPotential(PotentialBase):
+    """Burkert (builtin/core.py:415-432); C vector [rho, r0]."""
+    _type_id = _abi.POT_BURKERT
+    _param_names = ("rho", "r0")
+
+    def __init__(self, rho, r0, **kw):
+        super().__init__(rho=rho, r0=r0, **kw)
+
+
+class SatohPotential(PotentialBase):
+    _type_id = _abi.POT_SATOH
+    _param_names = ("m", "a", "b")
+
+    def __init__(self, m, a, b, **kw):
+        super().__init__(m=m, a=a, b=b, **kw)
+
+
+class KuzminPotential(PotentialBase):
+    _type_id = _abi.POT_KUZMIN
+    _param_names = ("m", "a")
+
+    def __init__(self, m, a, **kw):
+        super().__init__(m=m, a=a, **kw)
+
+
+class LogarithmicPotential(PotentialBase):
+    """Triaxial logarithmic halo (builtin/core.py:937-968); C vector [v_c, r_h, q1, q2, q3, phi]."""
+    _type_id = _abi.POT_LOGARITHMIC
+    _param_names = ("v_c", "r_h", "q1", "q2", "q3", "phi")
+
+    def __init__(self, v_c, r_h, q1=1.0, q2=1.0, q3=1.0, phi=0.0, **kw):
+        super().__init__(v_c=v_c, r_h=r_h, q1=q1, q2=q2, q3=q3, phi=phi, **kw)
+
+
+class LeeSutoTriaxialNFWPotential(PotentialBase):
+    """Lee & Suto (2003) (builtin/core.py:983-1013); C vector [v_c, r_s, a, b, c]."""
+    _type_id = _abi.POT_LEESUTO
+    _param_names = ("v_c", "r_s", "a", "b", "c")
+
+    def __init__(self, v_c, r_s, a=1.0, b=1.0, c=1.0, **kw):
+        super().__init__(v_c=v_c, r_s=r_s, a=a, b=b, c=c, **kw)
+
+
+class PowerLawCutoffPotential(PotentialBase):
+    """Power law with exponential cutoff (builtin/core.py:347-374); C vector [m, alpha, r_c], alpha < 3."""
+    _type_id = _abi.POT_POWERLAWCUTOFF
+    _param_names = ("m", "alpha", "r_c")
+
+    def __init__(self, m, alpha, r_c, **kw):
+        super().__init__(m=m, alpha=alpha, r_c=r_c, **kw)
+
+
 class SCFPotential(PotentialBase):
     """Hernquist-Ostriker basis-function expansion (reference potential/scf/core.py SCFPotential):
     ``Snlm``/``Tnlm`` have shape (nmax+1, lmax+1, lmax+1); the C vector is
@@ -445,4 +508,35 @@ class MilkyWayPotential2022(CCompositePotential):
     def __init__(self, units=galactic, disk=None, halo=None, bulge=None, nucleus=None):
         super().__init__()
         _setup_mwp_2022(self, units, disk, halo, bulge, nucleus)
+        self.lock = True
+
+
+class LM10Potential(CCompositePotential):
+    """Law & Majewski (2010) (builtin/special.py:26-87): MiyamotoNagai disk + Hernquist bulge + triaxial
+    Logarithmic halo, in that order; v_c = sqrt(2) * 121.858 km/s in kpc/Myr."""
+
+    def __init__(self, units=galactic, disk=None, bulge=None, halo=None):
+        super().__init__()
+        d = dict(m=1e11, a=6.5, b=0.26); d.update(disk or {})
+        b = dict(m=3.4e10, c=0.7); b.update(bulge or {})
+        h = dict(q1=1.38, q2=1.0, q3=1.36, r_h=12.0, phi=np.deg2rad(97.0),
+                 v_c=np.sqrt(2) * 121.858 * KMS_TO_KPC_MYR); h.update(halo or {})
+        self["disk"] = MiyamotoNagaiPotential(units=units, **d)
+        self["bulge"] = HernquistPotential(units=units, **b)
+        self["halo"] = LogarithmicPotential(units=units, **h)
+        self.lock = True
+
+
+class BovyMWPotential2014(CCompositePotential):
+    """galpy's MWPotential2014 (builtin/special.py:274-347): MiyamotoNagai disk + PowerLawCutoff bulge +
+    NFW halo, in that order."""
+
+    def __init__(self, units=galactic, disk=None, halo=None, bulge=None):
+        super().__init__()
+        d = dict(m=68193902782.346756, a=3.0, b=0.28); d.update(disk or {})
+        b = dict(m=4501365375.06545, alpha=1.8, r_c=1.9); b.update(bulge or {})
+        h = dict(m=4.3683325e11, r_s=16.0); h.update(halo or {})
+        self["disk"] = MiyamotoNagaiPotential(units=units, **d)
+        self["bulge"] = PowerLawCutoffPotential(units=units, **b)
+        self["halo"] = NFWPotential(units=units, **h)
         self.lock = True

@@ -57,6 +57,13 @@ enum gb_pot_type {
     GB_POT_JAFFE            = 12, /* JaffeWrapper           :189  [G, m, c]                              */
     GB_POT_MULTIPOLE        = 13, /* MultipoleWrapper       :378  [G, lmax, n_coeff, inner, m, r_s, (S_lm,T_lm)..]
                                      (builtin/multipole.cpp:247-262); lmax <= 15                        */
+    GB_POT_STONE            = 14, /* StoneWrapper           :201  [G, m, r_c, r_h]                       */
+    GB_POT_BURKERT          = 15, /* BurkertWrapper         :226  [G, rho, r0]                           */
+    GB_POT_SATOH            = 16, /* SatohWrapper           :240  [G, m, a, b]                           */
+    GB_POT_KUZMIN           = 17, /* KuzminWrapper          :252  [G, m, a]                              */
+    GB_POT_LOGARITHMIC      = 18, /* LogarithmicWrapper     :324  [G, v_c, r_h, q1, q2, q3, phi]         */
+    GB_POT_LEESUTO          = 19, /* LeeSutoTriaxialNFWWrapper :336 [G, v_c, r_s, a, b, c]               */
+    GB_POT_POWERLAWCUTOFF   = 20, /* PowerLawCutoffWrapper  :213  [G, m, alpha, r_c] (alpha < 3)         */
     GB_POT_NTYPES
 };
 

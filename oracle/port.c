@@ -28,6 +28,11 @@ typedef long double REAL;
 #define COS cosl
 #define FABS fabsl
 #define ATAN2 atan2l
+#define ATAN atanl
+#define EXP expl
+#define LGAMMA lgammal
+#define TGAMMA tgammal
+#define CEIL ceill
 #else
 typedef double REAL;
 #define SQRT sqrt
@@ -37,6 +42,11 @@ typedef double REAL;
 #define COS cos
 #define FABS fabs
 #define ATAN2 atan2
+#define ATAN atan
+#define EXP exp
+#define LGAMMA lgamma
+#define TGAMMA tgamma
+#define CEIL ceil
 #endif
 #define PI_R ((REAL)3.14159265358979323846264338327950288L)
 
@@ -350,6 +360,187 @@ static void mp_grad(const double *p, const REAL *q, REAL *g) {    /* mp_gradient
     g[0] += gx * sc; g[1] += gy * sc; g[2] += gz * sc;
 }
 
+/* ---- remaining analytic builtins ------------------------------------------------- */
+/* Stone :662-719  [G, m, r_c, r_h] */
+static REAL stone_value(const double *p, const REAL *q) {
+    REAL r = norm3(q), u_c = r / p[2], u_h = r / p[3];
+    REAL fac = 2 * (REAL)p[0] * p[1] / PI_R / ((REAL)p[3] - p[2]);
+    if (r == 0) return -fac * 0.5 * LOG((REAL)p[3] * p[3] / ((REAL)p[2] * p[2]));
+    return -fac * (ATAN(u_h) / u_h - ATAN(u_c) / u_c + 0.5 * LOG((r * r + (REAL)p[3] * p[3]) / (r * r + (REAL)p[2] * p[2])));
+}
+static void stone_grad(const double *p, const REAL *q, REAL *g) {
+    REAL r = norm3(q), u_c = r / p[2], u_h = r / p[3];
+    REAL fac = 2 * (REAL)p[0] * p[1] / (PI_R * r * r * r) / ((REAL)p[2] - p[3]);
+    REAL d = fac * (p[2] * ATAN(u_c) - p[3] * ATAN(u_h));
+    g[0] += d * q[0]; g[1] += d * q[1]; g[2] += d * q[2];
+}
+static REAL stone_density(const double *p, const REAL *q) {
+    REAL r = norm3(q);
+    REAL rho = (REAL)p[1] * ((REAL)p[2] + p[3]) / (2 * PI_R * PI_R * p[2] * p[2] * p[3] * p[3]);
+    REAL u_c = r / p[2], u_t = r / p[3];
+    return rho / ((1 + u_c * u_c) * (1 + u_t * u_t));
+}
+/* Burkert :2238-2279  [G, rho, r0] */
+static REAL burkert_value(const double *p, const REAL *q) {
+    REAL x = norm3(q) / p[2];
+    return -PI_R * p[0] * p[1] * p[2] * p[2] *
+           (PI_R - 2 * (1 + 1 / x) * ATAN(x) + 2 * (1 + 1 / x) * LOG(1 + x) - (1 - 1 / x) * LOG(1 + x * x));
+}
+static void burkert_grad(const double *p, const REAL *q, REAL *g) {
+    REAL r = norm3(q), x = r / p[2];
+    REAL d = -PI_R * p[0] * p[1] * p[2] / (x * x) * (2 * ATAN(x) - 2 * LOG(1 + x) - LOG(1 + x * x));
+    g[0] += d * q[0] / r; g[1] += d * q[1] / r; g[2] += d * q[2] / r;
+}
+static REAL burkert_density(const double *p, const REAL *q) {
+    REAL x = norm3(q) / p[2];
+    return p[1] / ((1 + x) * (1 + x * x));
+}
+/* Satoh :1147-1186  [G, m, a, b] */
+static REAL satoh_S2(const double *p, const REAL *q) {
+    return (q[0] * q[0] + q[1] * q[1] + q[2] * q[2]) + p[2] * (p[2] + 2 * SQRT(q[2] * q[2] + (REAL)p[3] * p[3]));
+}
+static REAL satoh_value(const double *p, const REAL *q) { return -(REAL)p[0] * p[1] / SQRT(satoh_S2(p, q)); }
+static void satoh_grad(const double *p, const REAL *q, REAL *g) {
+    REAL S2 = satoh_S2(p, q), dS = (REAL)p[0] * p[1] / S2, S = SQRT(S2);
+    g[0] += dS * q[0] / S; g[1] += dS * q[1] / S;
+    g[2] += dS / S * q[2] * (1 + p[2] / SQRT(q[2] * q[2] + (REAL)p[3] * p[3]));
+}
+static REAL satoh_density(const double *p, const REAL *q) {
+    REAL z2b2 = q[2] * q[2] + (REAL)p[3] * p[3], xyz2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
+    REAL S2 = xyz2 + p[2] * (p[2] + 2 * SQRT(z2b2));
+    REAL A = (REAL)p[1] * p[2] * p[3] * p[3] / (4 * PI_R * S2 * SQRT(S2) * z2b2);
+    return A * (1 / SQRT(z2b2) + 3 / p[2] * (1 - xyz2 / S2));
+}
+/* Kuzmin :1235-1283  [G, m, a] */
+static REAL kuzmin_value(const double *p, const REAL *q) {
+    REAL az = p[2] + FABS(q[2]);
+    return -(REAL)p[0] * p[1] / SQRT(q[0] * q[0] + q[1] * q[1] + az * az);
+}
+static void kuzmin_grad(const double *p, const REAL *q, REAL *g) {
+    REAL az = p[2] + FABS(q[2]);
+    REAL fac = (REAL)p[0] * p[1] * POW(q[0] * q[0] + q[1] * q[1] + az * az, -1.5);
+    REAL zs = (q[2] > 0) ? 1 : ((q[2] < 0) ? -1 : 0);
+    g[0] += fac * q[0]; g[1] += fac * q[1]; g[2] += fac * zs * az;
+}
+static REAL kuzmin_density(const double *p, const REAL *q) {
+    if (q[2] != 0) return 0;
+    return (REAL)p[1] * p[2] / (2 * PI_R) * POW(q[0] * q[0] + q[1] * q[1] + (REAL)p[2] * p[2], -1.5);
+}
+/* Logarithmic :1560-1625  [G, v_c, r_h, q1, q2, q3, phi] */
+static REAL log_value(const double *p, const REAL *q) {
+    REAL cp = COS(p[6]), sp = SIN(p[6]);
+    REAL x = q[0] * cp + q[1] * sp, y = -q[0] * sp + q[1] * cp, z = q[2];
+    return 0.5 * p[1] * p[1] * LOG((REAL)p[2] * p[2] + x * x / ((REAL)p[3] * p[3]) + y * y / ((REAL)p[4] * p[4]) + z * z / ((REAL)p[5] * p[5]));
+}
+static void log_grad(const double *p, const REAL *q, REAL *g) {
+    REAL cp = COS(p[6]), sp = SIN(p[6]);
+    REAL x = q[0] * cp + q[1] * sp, y = -q[0] * sp + q[1] * cp, z = q[2];
+    REAL fac = (REAL)p[1] * p[1] / ((REAL)p[2] * p[2] + x * x / ((REAL)p[3] * p[3]) + y * y / ((REAL)p[4] * p[4]) + z * z / ((REAL)p[5] * p[5]));
+    REAL ax = fac * x / ((REAL)p[3] * p[3]), ay = fac * y / ((REAL)p[4] * p[4]), az = fac * z / ((REAL)p[5] * p[5]);
+    g[0] += ax * cp - ay * sp; g[1] += ax * sp + ay * cp; g[2] += az;
+}
+static REAL log_density(const double *p, const REAL *q) {   /* ignores phi, as coded :1579-1601 */
+    REAL q1s = (REAL)p[3] * p[3], q2s = (REAL)p[4] * p[4], q3s = (REAL)p[5] * p[5];
+    REAL t2 = q1s * q2s, t3 = t2 * (q[2] * q[2]), t5 = q1s * q3s, t6 = t5 * (q[1] * q[1]);
+    REAL t7 = q2s * q3s, t8 = t7 * (q[0] * q[0]), t9 = (REAL)p[2] * p[2] * t2 * q3s;
+    REAL t10 = t6 + t8 + t9, t11 = t3 + t9, den = t10 + t3;
+    return (REAL)p[1] * p[1] * (t2 * (t10 - t3) + t5 * (t11 - t6 + t8) + t7 * (t11 + t6 - t8)) / (den * den) / (4 * PI_R * p[0]);
+}
+/* Lee & Suto :1446-1558  [G, v_c, r_s, a, b, c] */
+static REAL ls_vh2(const double *p, REAL *eb, REAL *ec) {
+    REAL ba = (REAL)p[4] / p[3], ca = (REAL)p[5] / p[3];
+    *eb = 1 - ba * ba; *ec = 1 - ca * ca;
+    REAL ln2 = LOG((REAL)2);
+    return (REAL)p[1] * p[1] / (ln2 - 0.5 + (ln2 - 0.75) * *eb + (ln2 - 0.75) * *ec);
+}
+static REAL ls_value(const double *p, const REAL *q) {
+    REAL eb, ec, phi0 = ls_vh2(p, &eb, &ec);
+    REAL x = q[0], y = q[1], z = q[2], r = SQRT(x * x + y * y + z * z), u = r / p[2];
+    if (u == 0) return phi0;
+    REAL l1u = LOG(1 + u);
+    REAL F1 = -l1u / u;
+    REAL F2 = -1 / (REAL)3 + (2 * u * u - 3 * u + 6) / (6 * u * u) + (1 / u - POW(u, -3)) * l1u;
+    REAL F3 = (u * u - 3 * u - 6) / (2 * u * u * (1 + u)) + 3 * POW(u, -3) * l1u;
+    REAL c2 = z * z / (r * r), s2 = 1 - c2, sp2 = y * y / (x * x + y * y);
+    return phi0 * (F1 + (eb + ec) / 2 * F2 + (eb * s2 * sp2 + ec * c2) / 2 * F3);
+}
+static void ls_grad(const double *p, const REAL *q, REAL *g) {
+    REAL eb, ec, vh2 = ls_vh2(p, &eb, &ec), rs = p[2];
+    REAL x = q[0], y = q[1], z = q[2];
+    REAL r2 = x * x + y * y + z * z, r = SQRT(r2), r4 = r2 * r2;
+    REAL x0 = r + rs, x1 = x0 * x0, x2 = vh2 / (12 * r4 * r2 * r * x1), x10 = LOG(x0 / rs);
+    REAL x13 = r * 3 * rs, x15 = x13 - r2, x16 = x15 + 6 * (rs * rs);
+    REAL x17 = 6 * rs * x0 * (r * x16 - x0 * x10 * 6 * (rs * rs));
+    REAL x20 = x0 * r2, x21 = 2 * r * x0, x7 = eb * y * y + ec * z * z;
+    REAL x22 = -12 * r4 * r * rs * x0 + 12 * r4 * rs * x1 * x10
+             + 3 * rs * x7 * (x16 * r2 - 18 * x1 * x10 * (rs * rs) + x20 * (2 * r - 3 * rs) + x21 * (x15 + 9 * (rs * rs)))
+             - x20 * (eb + ec) * (-6 * r * rs * (r2 - (rs * rs)) + 6 * rs * x0 * x10 * (r2 - 3 * (rs * rs))
+                                  + x20 * (-4 * r + 3 * rs) + x21 * (-x13 + 2 * r2 + 6 * (rs * rs)));
+    g[0] += x2 * x * (x17 * x7 + x22);
+    g[1] += x2 * y * (x17 * (x7 - r2 * eb) + x22);
+    g[2] += x2 * z * (x17 * (x7 - r2 * ec) + x22);
+}
+static REAL ls_density(const double *p, const REAL *q) {
+    REAL ba2 = (REAL)p[4] * p[4] / ((REAL)p[3] * p[3]), ca2 = (REAL)p[5] * p[5] / ((REAL)p[3] * p[3]);
+    REAL eb, ec, vh2 = ls_vh2(p, &eb, &ec);
+    REAL u = SQRT(q[0] * q[0] + q[1] * q[1] / ba2 + q[2] * q[2] / ca2) / p[2];
+    return vh2 / (u * (1 + u) * (1 + u)) / (4 * PI_R * p[2] * p[2] * p[0]);
+}
+/* PowerLawCutoff :465-554  [G, m, alpha, r_c].  gsl_sf_gamma_inc_P (GSL, absent) restated from the
+ * published series / continued fraction of the regularised incomplete gamma function. */
+static REAL gamma_inc_P(REAL a, REAL x) {
+    if (!(x > 0)) return 0;
+    REAL lead = EXP(a * LOG(x) - x - LGAMMA(a));
+    if (x < a + 1) {
+        REAL ap = a, del = 1 / a, sum = del;
+        for (int n = 0; n < 500; n++) { ap += 1; del *= x / ap; sum += del; if (FABS(del) < FABS(sum) * 1e-19) break; }
+        return sum * lead;
+    }
+    REAL tiny = 1e-300, b = x + 1 - a, c = 1 / tiny, d = 1 / b, h = d;
+    for (int i = 1; i < 500; i++) {
+        REAL an = -(REAL)i * ((REAL)i - a);
+        b += 2;
+        d = an * d + b; if (FABS(d) < tiny) d = tiny;
+        c = b + an / c; if (FABS(c) < tiny) c = tiny;
+        d = 1 / d;
+        REAL del = d * c; h *= del;
+        if (FABS(del - 1) < 1e-19) break;
+    }
+    return 1 - lead * h;
+}
+static REAL safe_gamma_inc_r(REAL a, REAL x) {
+    if (a > 0) return gamma_inc_P(a, x) * TGAMMA(a);
+    int N = (int)CEIL(-a);
+    REAL A = 1, B = 0;
+    for (int n = 0; n < N; n++) {
+        A = A * (a + n);
+        REAL tmp = 1;
+        for (int m = N - 1; m > n; m--) tmp = tmp * (a + m);
+        B = B + POW(x, a + n) * EXP(-x) * tmp;
+    }
+    return (B + gamma_inc_P(a + N, x) * TGAMMA(a + N)) / A;
+}
+static REAL plc_value(const double *p, const REAL *q) {
+    REAL r = norm3(q);
+    if (r == 0) return -INFINITY;
+    REAL t0 = (REAL)p[2] / 2, t1 = -t0, t2 = t1 + 1.5, t3 = r * r, t4 = t3 / ((REAL)p[3] * p[3]), t5 = (REAL)p[0] * p[1];
+    REAL t6 = t5 * safe_gamma_inc_r(t2, t4) / (SQRT(t3) * TGAMMA(t1 + 2.5));
+    REAL phi_r = t0 * t6 - 3.0 / 2.0 * t6 + t5 * safe_gamma_inc_r(t1 + 1, t4) / (p[3] * TGAMMA(t2));
+    REAL phi_inf = 0;
+    if (t2 > 0) phi_inf = t5 * TGAMMA(t1 + 1) / (p[3] * TGAMMA(t2));
+    return phi_r - phi_inf;
+}
+static void plc_grad(const double *p, const REAL *q, REAL *g) {
+    REAL r = norm3(q);
+    REAL d = (REAL)p[0] * p[1] / (r * r * r) * gamma_inc_P(0.5 * (3 - (REAL)p[2]), r * r / ((REAL)p[3] * p[3]));
+    g[0] += d * q[0]; g[1] += d * q[1]; g[2] += d * q[2];
+}
+static REAL plc_density(const double *p, const REAL *q) {
+    REAL r = norm3(q);
+    REAL A = p[1] / (2 * PI_R) * POW(p[3], (REAL)p[2] - 3) / TGAMMA(0.5 * (3 - (REAL)p[2]));
+    return A * POW(r, -(REAL)p[2]) * EXP(-r * r / ((REAL)p[3] * p[3]));
+}
+
 /* ---- per-component dispatch ------------------------------------------------------------------- */
 static void comp_grad(int type, const double *p, const REAL *q, REAL *g) {
     switch (type) {
@@ -364,6 +555,13 @@ static void comp_grad(int type, const double *p, const REAL *q, REAL *g) {
         case GB_POT_PLUMMER: plummer_grad(p, q, g); break;
         case GB_POT_ISOCHRONE: isochrone_grad(p, q, g); break;
         case GB_POT_JAFFE: jaffe_grad(p, q, g); break;
+        case GB_POT_STONE: stone_grad(p, q, g); break;
+        case GB_POT_BURKERT: burkert_grad(p, q, g); break;
+        case GB_POT_SATOH: satoh_grad(p, q, g); break;
+        case GB_POT_KUZMIN: kuzmin_grad(p, q, g); break;
+        case GB_POT_LOGARITHMIC: log_grad(p, q, g); break;
+        case GB_POT_LEESUTO: ls_grad(p, q, g); break;
+        case GB_POT_POWERLAWCUTOFF: plc_grad(p, q, g); break;
         default: break;
     }
 }
@@ -380,6 +578,13 @@ static REAL comp_value(int type, const double *p, const REAL *q) {
         case GB_POT_PLUMMER: return plummer_value(p, q);
         case GB_POT_ISOCHRONE: return isochrone_value(p, q);
         case GB_POT_JAFFE: return jaffe_value(p, q);
+        case GB_POT_STONE: return stone_value(p, q);
+        case GB_POT_BURKERT: return burkert_value(p, q);
+        case GB_POT_SATOH: return satoh_value(p, q);
+        case GB_POT_KUZMIN: return kuzmin_value(p, q);
+        case GB_POT_LOGARITHMIC: return log_value(p, q);
+        case GB_POT_LEESUTO: return ls_value(p, q);
+        case GB_POT_POWERLAWCUTOFF: return plc_value(p, q);
         default: return 0;
     }
 }
@@ -396,6 +601,13 @@ static REAL comp_density(int type, const double *p, const REAL *q) {
         case GB_POT_PLUMMER: return plummer_density(p, q);
         case GB_POT_ISOCHRONE: return isochrone_density(p, q);
         case GB_POT_JAFFE: return jaffe_density(p, q);
+        case GB_POT_STONE: return stone_density(p, q);
+        case GB_POT_BURKERT: return burkert_density(p, q);
+        case GB_POT_SATOH: return satoh_density(p, q);
+        case GB_POT_KUZMIN: return kuzmin_density(p, q);
+        case GB_POT_LOGARITHMIC: return log_density(p, q);
+        case GB_POT_LEESUTO: return ls_density(p, q);
+        case GB_POT_POWERLAWCUTOFF: return plc_density(p, q);
         default: return 0;
     }
 }

@@ -91,7 +91,29 @@ bool fill_component(CPotential *cp, int i, int type_id) {
     case GB_POT_JAFFE:
         cp->value[i] = jaffe_value; cp->density[i] = jaffe_density;
         cp->gradient[i] = jaffe_gradient; cp->hessian[i] = jaffe_hessian; return true;
+    case GB_POT_STONE:
+        cp->value[i] = stone_value;      // the header declares stone_density as void (builtin_potentials.h:95); the definition returns double
+        cp->density[i] = reinterpret_cast<densityfunc>(stone_density);
+        cp->gradient[i] = stone_gradient; cp->hessian[i] = stone_hessian; return true;
+    case GB_POT_BURKERT:         // BurkertWrapper sets no hessian (cybuiltin.pyx:226-234)
+        cp->value[i] = burkert_value; cp->density[i] = burkert_density;
+        cp->gradient[i] = burkert_gradient; cp->hessian[i] = null_hessian; return true;
+    case GB_POT_SATOH:
+        cp->value[i] = satoh_value; cp->density[i] = satoh_density;
+        cp->gradient[i] = satoh_gradient; cp->hessian[i] = satoh_hessian; return true;
+    case GB_POT_KUZMIN:
+        cp->value[i] = kuzmin_value; cp->density[i] = kuzmin_density;
+        cp->gradient[i] = kuzmin_gradient; cp->hessian[i] = null_hessian; return true;
+    case GB_POT_LOGARITHMIC:
+        cp->value[i] = logarithmic_value; cp->density[i] = logarithmic_density;
+        cp->gradient[i] = logarithmic_gradient; cp->hessian[i] = logarithmic_hessian; return true;
+    case GB_POT_LEESUTO:
+        cp->value[i] = leesuto_value; cp->density[i] = leesuto_density;
+        cp->gradient[i] = leesuto_gradient; cp->hessian[i] = null_hessian; return true;
 #if GB_REF_HAVE_SCF
+    case GB_POT_POWERLAWCUTOFF:  // compiled only with USE_GSL == 1 (builtin_potentials.cpp:465)
+        cp->value[i] = powerlawcutoff_value; cp->density[i] = powerlawcutoff_density;
+        cp->gradient[i] = powerlawcutoff_gradient; cp->hessian[i] = powerlawcutoff_hessian; return true;
     case GB_POT_SCF:
         cp->value[i] = scf_value5; cp->density[i] = scf_density5;
         cp->gradient[i] = scf_gradient; cp->hessian[i] = null_hessian; return true;

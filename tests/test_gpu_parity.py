@@ -67,6 +67,15 @@ def potentials():
         "plummer": gb.PlummerPotential(m=1e11, b=1.5),
         "isochrone": gb.IsochronePotential(m=1e11, b=1.5),
         "jaffe": gb.JaffePotential(m=1e11, c=2.0),
+        "stone": gb.StonePotential(m=1e11, r_c=0.5, r_h=20.0),
+        "burkert": gb.BurkertPotential(rho=2.3e7, r0=4.0),
+        "satoh": gb.SatohPotential(m=8e10, a=3.0, b=0.4),
+        "kuzmin": gb.KuzminPotential(m=8e10, a=3.0),
+        "logarithmic": gb.LogarithmicPotential(v_c=0.2, r_h=12.0, q1=1.38, q2=1.0, q3=1.36, phi=np.deg2rad(97.0)),
+        "leesuto": gb.LeeSutoTriaxialNFWPotential(v_c=0.2, r_s=15.0, a=1.0, b=0.85, c=0.7),
+        "powerlawcutoff": gb.PowerLawCutoffPotential(m=4.5e9, alpha=1.8, r_c=1.9),
+        "lm10": gb.LM10Potential(),
+        "bovy2014": gb.BovyMWPotential2014(),
         "scf_c5": scf_c5(),
         "scf_small": scf_c5(nmax=3, lmax=2, seed=6),
         "scf_big": scf_c5(nmax=12, lmax=8, seed=7),
@@ -100,9 +109,16 @@ def test_gradient_energy_density(ref, name, strict):
     # SCF: the reference sums 308 terms of per-term GSL evaluations, the device uses recurrences
     # multipole: same situation at lmax <= 5 (a handful of terms)
     gtol = 2e-11 if name.startswith("scf") else 1e-12 if name.startswith("multipole") else (5e-15 if strict else 2e-14)
+    if name in ("powerlawcutoff", "bovy2014"):
+        gtol = 1e-13      # incomplete gamma function: series / continued fraction on both sides, different libm
+    if name == "leesuto":
+        gtol = 1e-11      # the reference's expanded polynomial form cancels ~3 digits (builtin_potentials.cpp:1518)
     assert np.max(np.sqrt(((g - g0) ** 2).sum(0)) / scale) < gtol
     e = pot.energy(q); e0 = ref.energy(pot, q)
-    assert rel(e, e0) < (1e-11 if name.startswith("scf") else 1e-10 if name.startswith("multipole") else 1e-13)
+    etol = 1e-11 if name.startswith("scf") else 1e-10 if name.startswith("multipole") else 1e-13
+    if name in ("powerlawcutoff", "bovy2014", "burkert", "leesuto"):
+        etol = 1e-11      # differences of O(1) terms (atan/log/gamma) that cancel at large or small radius
+    assert rel(e, e0) < etol
     d0 = ref.density(pot, q)
     d = pot.density(q)
     ok = np.isfinite(d0)
