@@ -350,6 +350,7 @@ def main():
 
     for _ in range(args.warmup):
         out = run(w0_dev, t)
+        units(N, out)      # also warms the unit count (C2 sums per-orbit step counts with a lazily loaded torch kernel)
     torch.cuda.synchronize()
 
     clocks = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
@@ -362,14 +363,20 @@ def main():
     barrier()
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_start.record()
+    trace = []
     for k in range(args.steps):
+        ta = time.perf_counter()
         ev[k][0].record()
         out = run(w0_dev, t)
         ev[k][1].record()
+        tb = time.perf_counter()
         tot_units += units(N, out)
+        trace.append((tb - ta, time.perf_counter() - tb))
     e_stop.record()
     barrier()
     launches = gb._abi.launch_count() - n0
+    if os.environ.get("BENCH_TRACE"):
+        print("trace (call s, units s):", [(round(a * 1e3, 2), round(b * 1e3, 2)) for a, b in trace], file=sys.stderr)
     clk = clocks.stop() if rank == 0 else None
     ms_total = e_start.elapsed_time(e_stop)
     kern_ms = [a.elapsed_time(b) for a, b in ev]
