@@ -46,6 +46,10 @@ class gb_launch(C.Structure):
                 ("strict_math", C.c_int32), ("block_threads", C.c_int32)]
 
 
+class gb_bodies(C.Structure):
+    _fields_ = [("n_bodies", C.c_int32), ("_pad", C.c_int32), ("body_pot", C.POINTER(gb_potential))]
+
+
 class gb_dop853_stats(C.Structure):
     _fields_ = [("nstep", c_int32_p), ("naccpt", c_int32_p), ("nrejct", c_int32_p), ("nfcn", c_int32_p)]
 
@@ -75,6 +79,13 @@ SIGNATURES = {
                                        C.c_void_p, P(gb_launch)]),
     "gb_mockstream_leapfrog": (C.c_int, [P(gb_potential), C.c_void_p, C.c_void_p, C.c_size_t, C.c_double,
                                          C.c_double, C.c_void_p, P(gb_launch)]),
+    "gb_nbody_leapfrog": (C.c_int, [P(gb_potential), P(gb_bodies), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_size_t, C.c_double, C.c_double, C.c_int, C.c_double,
+                                    C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, P(gb_launch)]),
+    "gb_nbody_dop853": (C.c_int, [P(gb_potential), P(gb_bodies), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double,
+                                  C.c_double, C.c_long, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
+                                  C.c_void_p, C.c_void_p, P(gb_launch)]),
     "gb_last_error": (C.c_char_p, []),
     "gb_device_count": (C.c_int, []),
     "gb_launch_count": (C.c_long, []),

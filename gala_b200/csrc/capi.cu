@@ -848,4 +848,132 @@ int gb_mockstream_leapfrog(const gb_potential* pot, const double* stream_w0, con
     return finish(c);
 }
 
+// ---- massive bodies ------------------------------------------------------------------
+// Flattens the per-body potentials into DevBodies (gb_device.cuh).  A body is a force source unless its
+// potential is all-Null (CPotential::null, set by CPotentialWrapper.init when every component is a
+// NullWrapper; cpotential.cpp:397-399 skips those).
+static int resolve_bodies(const gb_bodies* bodies, DevBodies& B) {
+    memset(&B, 0, sizeof(B));
+    if (!bodies || bodies->n_bodies < 1 || bodies->n_bodies > GB_MAXB)
+        return fail(-11, "the N-body kernels carry 1.." + std::to_string(GB_MAXB) + " bodies per system");
+    B.nb = bodies->n_bodies;
+    int nc = 0, off = 0;
+    for (int b = 0; b < B.nb; b++) {
+        const gb_potential* bp = bodies->body_pot ? &bodies->body_pot[b] : nullptr;
+        B.cbeg[b] = nc;
+        int massive = 0;
+        if (bp) for (int i = 0; i < bp->n_components; i++) {
+            const gb_component& c = bp->comp[i];
+            if (c.type_id == GB_POT_NULL) continue;
+            if (c.type_id < 0 || c.type_id >= GB_POT_NTYPES || c.type_id == GB_POT_SCF || c.type_id == GB_POT_MULTIPOLE)
+                return fail(-11, "body potentials must be analytic builtin types");
+            if (c.n_params < min_npar(c.type_id) || !c.params) return fail(-12, "body potential: too few parameters");
+            if (nc >= GB_MAXBC || off + c.n_params > GB_MAXBP) return fail(-11, "too many body-potential components/parameters");
+            B.type[nc] = c.type_id; B.poff[nc] = off;
+            for (int k = 0; k < c.n_params; k++) B.par[off + k] = c.params[k];
+            off += c.n_params;
+            for (int k = 0; k < 9; k++) B.R[nc][k] = c.R[k];
+            nc++; massive = 1;
+        }
+        B.null_[b] = !massive;
+    }
+    B.cbeg[B.nb] = nc; B.nc = nc;
+    return 0;
+}
+
+struct DevTmp {                      // stream-ordered device temporary with optional H2D fill
+    void* p = nullptr; cudaStream_t s = nullptr;
+    cudaError_t put(const void* host, size_t bytes, cudaStream_t st) {
+        s = st;
+        cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 8, s);
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        if (host && bytes) e = cudaMemcpyAsync(p, host, bytes, cudaMemcpyHostToDevice, s);
+        return e;
+    }
+    ~DevTmp() { if (p) cudaFreeAsync(p, s); }
+};
+
+int gb_nbody_leapfrog(const gb_potential* pot, const gb_bodies* bodies, const double* body_w0, int ngroups,
+                      const int32_t* group, const double* w0_rows, const double* t1, size_t Np, double t0,
+                      double tfinal, int nsteps, double dt, double* out_particles, double* out_bodies,
+                      size_t body_writer, double* traj, const gb_launch* opt) {
+    Ctx c; RET_IF(open_ctx(opt, c));
+    if (!c.host) return fail(-12, "gb_nbody_leapfrog takes host buffers");
+    if (!body_w0 || ngroups < 1 || (Np && !w0_rows)) return fail(-12, "null data pointer");
+    if (dt == 0.0) return fail(-12, "dt must be non-zero");
+    RET_IF(pool_keep());
+    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    DevBodies B; RET_IF(resolve_bodies(bodies, B));
+    const size_t nb = B.nb, ntot = nb + Np;
+    if (body_writer >= (Np ? Np : 1)) return fail(-12, "body_writer out of range");
+    DevTmp dbw, dgrp, dw0, dt1, dop, dob, dtr;
+    CU(dbw.put(body_w0, (size_t)ngroups * nb * 6 * sizeof(double), c.stream));
+    if (group) CU(dgrp.put(group, Np * sizeof(int32_t), c.stream));
+    CU(dw0.put(w0_rows, Np * 6 * sizeof(double), c.stream));
+    if (t1) CU(dt1.put(t1, Np * sizeof(double), c.stream));
+    if (out_particles) CU(dop.put(nullptr, Np * 6 * sizeof(double), c.stream));
+    if (out_bodies) CU(dob.put(nullptr, nb * 6 * sizeof(double), c.stream));
+    const size_t tb = traj ? (size_t)(nsteps + 1) * ntot * 6 * sizeof(double) : 0;
+    if (traj) { if (t1) return fail(-12, "trajectories need a common start time"); CU(dtr.put(nullptr, tb, c.stream)); }
+    cudaError_t e = KCALL(c, nbody_leapfrog, r.P, B, (const double*)dbw.p, (const int32_t*)dgrp.p, (const double*)dw0.p,
+                          (const double*)dt1.p, Np, t0, tfinal, nsteps, dt, (double*)dop.p, (double*)dob.p, body_writer,
+                          (double*)dtr.p, ntot, c.block, c.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "nbody_leapfrog launch");
+    g_launches++;
+    if (out_particles && Np) CU(cudaMemcpyAsync(out_particles, dop.p, Np * 6 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    if (out_bodies) CU(cudaMemcpyAsync(out_bodies, dob.p, nb * 6 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    if (traj) CU(cudaMemcpyAsync(traj, dtr.p, tb, cudaMemcpyDeviceToHost, c.stream));
+    return finish(c);
+}
+
+int gb_nbody_dop853(const gb_potential* pot, const gb_bodies* bodies, const double* body_w0, int ngroups,
+                    const int32_t* group, const double* w0_rows, const double* t1, size_t Np,
+                    const double* tgrid, int ntimes, double tfinal, double dt0, double atol, double rtol, long nmax,
+                    double dt_max, int step_mode, double* out_particles, double* out_bodies, size_t body_writer,
+                    double* traj, int32_t* status, const gb_launch* opt) {
+    Ctx c; RET_IF(open_ctx(opt, c));
+    if (!c.host) return fail(-12, "gb_nbody_dop853 takes host buffers");
+    if (!body_w0 || ngroups < 1 || (Np && !w0_rows)) return fail(-12, "null data pointer");
+    if (traj && (!tgrid || ntimes < 2 || t1)) return fail(-12, "dense output needs a time grid and a common start time");
+    RET_IF(pool_keep());
+    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    DevBodies B; RET_IF(resolve_bodies(bodies, B));
+    const size_t nb = B.nb, ntot = nb + Np;
+    if (nb + (Np ? 1 : 0) > 4) return fail(-11, "DOP853 N-body systems carry at most 4 points per lane (3 bodies + the particle)");
+    if (body_writer >= (Np ? Np : 1)) return fail(-12, "body_writer out of range");
+    Dop853Args a;
+    // step_mode 0: dop853_helper (dop853.pyx:157-182: uround = eps, nstiff = -1 from direct_nbody_dop853, nbody.pyx:106);
+    // step_mode 1: dop853_step (dop853.pyx:45-69: uround 0 -> 2.3e-16, hmax 0, nstiff hard-coded to 1)
+    if (step_mode == 0) RET_IF(dop853_defaults(a, atol, rtol, nmax, dt_max, -1, 2.220446049250313e-16, dt0));
+    else RET_IF(dop853_defaults(a, atol, rtol, nmax, 0.0, 1, 0.0, dt0));
+    const size_t nthreads = Np ? Np : 1;
+    DevTmp dbw, dgrp, dw0, dt1, dtg, dop, dob, dtr, dst;
+    CU(dbw.put(body_w0, (size_t)ngroups * nb * 6 * sizeof(double), c.stream));
+    if (group) CU(dgrp.put(group, Np * sizeof(int32_t), c.stream));
+    CU(dw0.put(w0_rows, Np * 6 * sizeof(double), c.stream));
+    if (t1) CU(dt1.put(t1, Np * sizeof(double), c.stream));
+    if (tgrid) CU(dtg.put(tgrid, (size_t)ntimes * sizeof(double), c.stream));
+    if (out_particles) CU(dop.put(nullptr, Np * 6 * sizeof(double), c.stream));
+    if (out_bodies) CU(dob.put(nullptr, nb * 6 * sizeof(double), c.stream));
+    const size_t tb = traj ? (size_t)ntimes * ntot * 6 * sizeof(double) : 0;
+    if (traj) { CU(dtr.put(nullptr, tb, c.stream)); CU(cudaMemsetAsync(dtr.p, 0xff, tb, c.stream)); }   // NaN where an orbit failed
+    CU(dst.put(nullptr, nthreads * sizeof(int32_t), c.stream));
+    const double t0 = tgrid ? tgrid[0] : 0.0;
+    cudaError_t e = KCALL(c, nbody_dop853, r.P, B, a, (const double*)dbw.p, (const int32_t*)dgrp.p, (const double*)dw0.p,
+                          (const double*)dt1.p, Np, (const double*)dtg.p, ntimes, t0, tfinal, (double*)dop.p, (double*)dob.p,
+                          body_writer, (double*)dtr.p, ntot, (int32_t*)dst.p, c.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "nbody_dop853 launch");
+    g_launches++;
+    if (out_particles && Np) CU(cudaMemcpyAsync(out_particles, dop.p, Np * 6 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    if (out_bodies) CU(cudaMemcpyAsync(out_bodies, dob.p, nb * 6 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    if (traj) CU(cudaMemcpyAsync(traj, dtr.p, tb, cudaMemcpyDeviceToHost, c.stream));
+    std::vector<int32_t> hs(nthreads);
+    CU(cudaMemcpyAsync(hs.data(), dst.p, nthreads * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+    CU(cudaStreamSynchronize(c.stream));
+    int worst = 0;
+    for (size_t i = 0; i < nthreads; i++) { if (hs[i] < worst) worst = hs[i]; if (status) status[i] = hs[i]; }
+    if (worst < 0) return fail(worst, "Integration failed with code " + std::to_string(worst));
+    return 0;
+}
+
 }  // extern "C"

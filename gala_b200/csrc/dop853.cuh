@@ -43,9 +43,12 @@ GB_DEV double gb_pow_eighth(double err) {
 //   init(): dop853() front-end + the first RHS evaluation + hinit (dop853.cpp:18-86, 361-366)
 //   step(): one attempted step of the dopcor loop (dop853.cpp:367-650); returns 0 to continue or
 //           the dop853 code: 1 ok, -2 nmax exceeded, -3 step too small, -4 stiff.
-template <bool DENSE>
+template <bool DENSE, int NDIM = 6>
 struct Dop853Lane {
-    static constexpr int n = 6;
+    static constexpr int n = NDIM;
+    // loops over the n components: fully unrolled (state in registers) for one orbit, rolled (state in
+    // local memory, small code) for the N-body systems of nbody.cuh
+    static constexpr int GB_NU = (NDIM <= 6) ? NDIM : 1;   // 6 for one orbit; 6 (nb + 1) when a lane carries nb massive bodies (nbody.cuh)
     double y[n], k1[n];
     double x, xend, h, posneg, hmax, facold, hlamb;
     int last, reject, nstep, naccpt, nrejct, nfcn, out_idx;
@@ -66,7 +69,7 @@ struct Dop853Lane {
             // hinit (dop853.cpp:18-86), iord = 8
             double k2[n], k3[n];
             double dnf = 0.0, dny = 0.0;
-#pragma unroll
+#pragma unroll(GB_NU)
             for (int i = 0; i < n; i++) {
                 const double sk = atoli + rtoli * fabs(y[i]);
                 double sqr = k1[i] / sk; dnf += sqr * sqr;
@@ -75,11 +78,11 @@ struct Dop853Lane {
             double hh = ((dnf <= 1.0E-10) || (dny <= 1.0E-10)) ? 1.0E-6 : sqrt(dny / dnf) * 0.01;
             hh = gb_min(hh, hmax);
             hh = gb_sign(hh, posneg);
-#pragma unroll
+#pragma unroll(GB_NU)
             for (int i = 0; i < n; i++) k3[i] = y[i] + hh * k1[i];
             rhs(x + hh, k3, k2);
             double der2 = 0.0;
-#pragma unroll
+#pragma unroll(GB_NU)
             for (int i = 0; i < n; i++) {
                 const double sk = atoli + rtoli * fabs(y[i]);
                 const double sqr = (k2[i] - k1[i]) / sk; der2 += sqr * sqr;
@@ -109,50 +112,50 @@ struct Dop853Lane {
             nstep++;
 
             // the twelve stages (dop853.cpp:369-409)
-    #pragma unroll
+#pragma unroll(GB_NU)
             for (int i = 0; i < n; i++) yy1[i] = y[i] + h * a21 * k1[i];
             rhs(x + c2 * h, yy1, k2);
-    #pragma unroll
+#pragma unroll(GB_NU)
             for (int i = 0; i < n; i++) yy1[i] = y[i] + h * (a31 * k1[i] + a32 * k2[i]);
             rhs(x + c3 * h, yy1, k3);
-    #pragma unroll
+#pragma unroll(GB_NU)
             for (int i = 0; i < n; i++) yy1[i] = y[i] + h * (a41 * k1[i] + a43 * k3[i]);
             rhs(x + c4 * h, yy1, k4);
-    #pragma unroll
+#pragma unroll(GB_NU)
             for (int i = 0; i < n; i++) yy1[i] = y[i] + h * (a51 * k1[i] + a53 * k3[i] + a54 * k4[i]);
             rhs(x + c5 * h, yy1, k5);
-    #pragma unroll
+#pragma unroll(GB_NU)
             for (int i = 0; i < n; i++) yy1[i] = y[i] + h * (a61 * k1[i] + a64 * k4[i] + a65 * k5[i]);
             rhs(x + c6 * h, yy1, k6);
-    #pragma unroll
+#pragma unroll(GB_NU)
             for (int i = 0; i < n; i++) yy1[i] = y[i] + h * (a71 * k1[i] + a74 * k4[i] + a75 * k5[i] + a76 * k6[i]);
             rhs(x + c7 * h, yy1, k7);
-    #pragma unroll
+#pragma unroll(GB_NU)
             for (int i = 0; i < n; i++)
                 yy1[i] = y[i] + h * (a81 * k1[i] + a84 * k4[i] + a85 * k5[i] + a86 * k6[i] + a87 * k7[i]);
             rhs(x + c8 * h, yy1, k8);
-    #pragma unroll
+#pragma unroll(GB_NU)
             for (int i = 0; i < n; i++)
                 yy1[i] = y[i] + h * (a91 * k1[i] + a94 * k4[i] + a95 * k5[i] + a96 * k6[i] + a97 * k7[i] + a98 * k8[i]);
             rhs(x + c9 * h, yy1, k9);
-    #pragma unroll
+#pragma unroll(GB_NU)
             for (int i = 0; i < n; i++)
                 yy1[i] = y[i] + h * (a101 * k1[i] + a104 * k4[i] + a105 * k5[i] + a106 * k6[i] + a107 * k7[i] +
                                      a108 * k8[i] + a109 * k9[i]);
             rhs(x + c10 * h, yy1, k10);
-    #pragma unroll
+#pragma unroll(GB_NU)
             for (int i = 0; i < n; i++)
                 yy1[i] = y[i] + h * (a111 * k1[i] + a114 * k4[i] + a115 * k5[i] + a116 * k6[i] + a117 * k7[i] +
                                      a118 * k8[i] + a119 * k9[i] + a1110 * k10[i]);
             rhs(x + c11 * h, yy1, k2);
             const double xph = x + h;
-    #pragma unroll
+#pragma unroll(GB_NU)
             for (int i = 0; i < n; i++)
                 yy1[i] = y[i] + h * (a121 * k1[i] + a124 * k4[i] + a125 * k5[i] + a126 * k6[i] + a127 * k7[i] +
                                      a128 * k8[i] + a129 * k9[i] + a1210 * k10[i] + a1211 * k2[i]);
             rhs(xph, yy1, k3);
             nfcn += 11;
-    #pragma unroll
+#pragma unroll(GB_NU)
             for (int i = 0; i < n; i++) {
                 k4[i] = b1 * k1[i] + b6 * k6[i] + b7 * k7[i] + b8 * k8[i] + b9 * k9[i] + b10 * k10[i] + b11 * k2[i] +
                         b12 * k3[i];
@@ -161,7 +164,7 @@ struct Dop853Lane {
 
             // error estimation (dop853.cpp:416-444), scalar tolerances, norm over this orbit's 6 components
             double err = 0.0, err2 = 0.0;
-    #pragma unroll
+#pragma unroll(GB_NU)
             for (int i = 0; i < n; i++) {
                 const double sk = atoli + rtoli * gb_max(fabs(y[i]), fabs(k5[i]));
                 double erri = k4[i] - bhh1 * k1[i] - bhh2 * k9[i] - bhh3 * k3[i];
@@ -192,7 +195,7 @@ struct Dop853Lane {
                 // stiffness detection as coded in the reference (dop853.cpp:460-485)
                 if (!(naccpt % a.nstiff)) {
                     double stnum = 0.0, stden = 0.0;
-    #pragma unroll
+#pragma unroll(GB_NU)
                     for (int i = 0; i < n; i++) {
                         double sqr = k4[i] - k3[i]; stnum += sqr * sqr;
                         sqr = k5[i] - yy1[i]; stden += sqr * sqr;
@@ -203,7 +206,7 @@ struct Dop853Lane {
 
                 if (DENSE) {
                     // dense-output preparation (dop853.cpp:492-582)
-    #pragma unroll
+#pragma unroll(GB_NU)
                     for (int i = 0; i < n; i++) {
                         rc1[i] = y[i];
                         const double ydiff = k5[i] - y[i];
@@ -220,23 +223,23 @@ struct Dop853Lane {
                         rc8[i] = d71 * k1[i] + d76 * k6[i] + d77 * k7[i] + d78 * k8[i] + d79 * k9[i] + d710 * k10[i] +
                                  d711 * k2[i] + d712 * k3[i];
                     }
-    #pragma unroll
+#pragma unroll(GB_NU)
                     for (int i = 0; i < n; i++)
                         yy1[i] = y[i] + h * (a141 * k1[i] + a147 * k7[i] + a148 * k8[i] + a149 * k9[i] + a1410 * k10[i] +
                                              a1411 * k2[i] + a1412 * k3[i] + a1413 * k4[i]);
                     rhs(x + c14 * h, yy1, k10);
-    #pragma unroll
+#pragma unroll(GB_NU)
                     for (int i = 0; i < n; i++)
                         yy1[i] = y[i] + h * (a151 * k1[i] + a156 * k6[i] + a157 * k7[i] + a158 * k8[i] + a1511 * k2[i] +
                                              a1512 * k3[i] + a1513 * k4[i] + a1514 * k10[i]);
                     rhs(x + c15 * h, yy1, k2);
-    #pragma unroll
+#pragma unroll(GB_NU)
                     for (int i = 0; i < n; i++)
                         yy1[i] = y[i] + h * (a161 * k1[i] + a166 * k6[i] + a167 * k7[i] + a168 * k8[i] + a169 * k9[i] +
                                              a1613 * k4[i] + a1614 * k10[i] + a1615 * k2[i]);
                     rhs(x + c16 * h, yy1, k3);
                     nfcn += 3;
-    #pragma unroll
+#pragma unroll(GB_NU)
                     for (int i = 0; i < n; i++) {
                         rc5[i] = h * (rc5[i] + d413 * k4[i] + d414 * k10[i] + d415 * k2[i] + d416 * k3[i]);
                         rc6[i] = h * (rc6[i] + d513 * k4[i] + d514 * k10[i] + d515 * k2[i] + d516 * k3[i]);
@@ -251,7 +254,7 @@ struct Dop853Lane {
                             const double s = (t_out - x0) / h;
                             const double s1 = 1.0 - s;
                             double v[n];
-    #pragma unroll
+#pragma unroll(GB_NU)
                             for (int i = 0; i < n; i++)
                                 v[i] = rc1[i] + s * (rc2[i] + s1 * (rc3[i] + s * (rc4[i] + s1 * (rc5[i] + s * (rc6[i] + s1 * (rc7[i] + s * rc8[i]))))));
                             emit(out_idx, v);
@@ -262,7 +265,7 @@ struct Dop853Lane {
                     }
                 }
 
-    #pragma unroll
+#pragma unroll(GB_NU)
                 for (int i = 0; i < n; i++) { k1[i] = k4[i]; y[i] = k5[i]; }
                 x = xph;
                 if (last) return 1;
@@ -284,18 +287,18 @@ struct Dop853Lane {
 
 // Thread-per-orbit driver (used by the mock-stream kernel and as the reference semantics of the
 // persistent kernel): run one lane to completion.
-template <bool DENSE, class RHS, class OUT>
+template <bool DENSE, int NDIM = 6, class RHS, class OUT>
 GB_DEV int dop853_integrate(const RHS& rhs, const OUT& emit, const Dop853Args& a, double x, double xend,
-                            double (&y)[6], double h, const double* __restrict__ tout, int ntout,
+                            double (&y)[NDIM], double h, const double* __restrict__ tout, int ntout,
                             int& out_idx, int& nstep_, int& naccpt_, int& nrejct_, int& nfcn_) {
-    Dop853Lane<DENSE> L;
+    Dop853Lane<DENSE, NDIM> L;
 #pragma unroll
-    for (int i = 0; i < 6; i++) L.y[i] = y[i];
+    for (int i = 0; i < NDIM; i++) L.y[i] = y[i];
     L.init(rhs, a, x, xend, h);
     int code;
     do { code = L.step(rhs, emit, a, tout, ntout); } while (code == 0);
 #pragma unroll
-    for (int i = 0; i < 6; i++) y[i] = L.y[i];
+    for (int i = 0; i < NDIM; i++) y[i] = L.y[i];
     out_idx = L.out_idx; nstep_ = L.nstep; naccpt_ = L.naccpt; nrejct_ = L.nrejct; nfcn_ = L.nfcn;
     return code;
 }

@@ -39,6 +39,23 @@ struct DevPot {
     const double* ext;         // device-global parameters of "large" components (SCF coefficients)
 };
 
+// Massive bodies carried by every lane of the N-body kernels (nbody.cuh): each body owns a small potential
+// (its components are evaluated about the body's current position: c_nbody_acceleration /
+// c_nbody_gradient_symplectic set do_shift_rotate = 1 and q0 = &w[body], cpotential.cpp:389-442).
+#define GB_MAXB 4      // massive bodies per system
+#define GB_MAXBC 8     // potential components over all bodies
+#define GB_MAXBP 48    // packed parameters over all body components
+struct DevBodies {
+    int32_t nb;                   // bodies (massive or Null) at the front of the system
+    int32_t nc;
+    int32_t null_[GB_MAXB];       // CPotential::null of body b (skipped as a force source)
+    int32_t cbeg[GB_MAXB + 1];    // components of body b: [cbeg[b], cbeg[b+1])
+    int32_t type[GB_MAXBC];
+    int32_t poff[GB_MAXBC];
+    double R[GB_MAXBC][9];
+    double par[GB_MAXBP];
+};
+
 struct DevFrame {
     int32_t type;              // gb_frame_type
     int32_t _pad;

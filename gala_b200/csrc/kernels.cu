@@ -22,6 +22,9 @@ namespace GB_NS {
 #include "hamiltonian.cuh"
 #include "dop853.cuh"
 #include "mockstream.cuh"
+#if GB_PART == 5 || GB_PART == 6
+#include "nbody.cuh"
+#endif
 
 #if GB_PART == 1
 // ------------------------------------------------------------------------------------------------
@@ -180,7 +183,7 @@ k_ruth4(const __grid_constant__ DevPot P, const __grid_constant__ DevFrame F, co
 // ------------------------------------------------------------------------------------------------
 // host launchers.  GB_PART splits this file into translation units that compile in parallel:
 //   1 = evaluation + leapfrog + ruth4, 2 = dop853 static frame, 3 = dop853 rotating frame,
-//   4 = mock-stream kernels.
+//   4 = mock-stream kernels, 5 = N-body (massive bodies) kernels.
 // ------------------------------------------------------------------------------------------------
 static inline unsigned nblocks(size_t N, int block) { return (unsigned)((N + block - 1) / block); }
 
@@ -357,5 +360,79 @@ cudaError_t fardal_release(const DevPot& P, double G, const double* prog_w, cons
 }
 
 #endif  // GB_PART == 4
+
+#if GB_PART == 5 || GB_PART == 6
+// Two composite forms are instantiated for the N-body kernels: the compile-time MW2022 list and the
+// generic loop (which evaluates any component list).
+#define GB_SIG_SWITCH2(sig, CALL)                                 \
+    switch (sig) {                                                \
+        case SIG_MW2022:     { using C = Composite<SIG_MW2022>;     CALL; } break; \
+        default:             { using C = Composite<SIG_GENERIC>;    CALL; } break; \
+    }
+#if GB_PART == 5
+cudaError_t nbody_leapfrog(const DevPot& P, const DevBodies& B, const double* body_w0, const int32_t* group,
+                           const double* w0, const double* t1, size_t Np, double t0, double tfinal, int nsteps_fixed,
+                           double dt, double* out_p, double* out_b, size_t body_writer, double* traj, size_t ntot,
+                           int block, cudaStream_t s) {
+    const int hasp = Np > 0;
+    const size_t nthreads = hasp ? Np : 1;
+    if (block > 128 || block <= 0) block = 128;
+    GB_SIG_SWITCH2(P.sig, (k_nbody_leapfrog<C><<<nblocks(nthreads, block), block, 0, s>>>(
+        P, B, body_w0, group, w0, t1, Np, hasp, t0, tfinal, nsteps_fixed, dt, out_p, out_b, body_writer, traj, ntot)));
+    return cudaGetLastError();
+}
+#endif
+
+template <class C, int NDIM>
+static void launch_nbody_d8(const DevPot& P, const DevBodies& B, const Dop853Args& a, const double* body_w0,
+                            const int32_t* group, const double* w0, const double* t1, size_t Np, int hasp,
+                            const double* tgrid, int ntimes, double t0, double tfinal, double* out_p, double* out_b,
+                            size_t body_writer, double* traj, size_t ntot, int32_t* status, cudaStream_t s) {
+    const size_t nthreads = hasp ? Np : 1;
+    const int block = 64;
+    if (traj)
+        k_nbody_dop853<C, NDIM, true><<<nblocks(nthreads, block), block, 0, s>>>(
+            P, B, a, body_w0, group, w0, t1, Np, hasp, tgrid, ntimes, t0, tfinal, out_p, out_b, body_writer, traj, ntot, status);
+    else
+        k_nbody_dop853<C, NDIM, false><<<nblocks(nthreads, block), block, 0, s>>>(
+            P, B, a, body_w0, group, w0, t1, Np, hasp, tgrid, ntimes, t0, tfinal, out_p, out_b, body_writer, traj, ntot, status);
+}
+// systems of 1-2 points (n = 6, 12: unrolled, state in registers) compile in part 5, 3-4 points in part 6
+#if GB_PART == 5
+#define GB_ND_NAME nbody_dop853_small
+#else
+#define GB_ND_NAME nbody_dop853_big
+#endif
+cudaError_t GB_ND_NAME(const DevPot& P, const DevBodies& B, const Dop853Args& a, const double* body_w0,
+                         const int32_t* group, const double* w0, const double* t1, size_t Np,
+                         const double* tgrid, int ntimes, double t0, double tfinal, double* out_p, double* out_b,
+                         size_t body_writer, double* traj, size_t ntot, int32_t* status, cudaStream_t s) {
+    const int hasp = Np > 0;
+    const int npts = B.nb + hasp;
+#define GB_ND(N) GB_SIG_SWITCH2(P.sig, (launch_nbody_d8<C, N>(P, B, a, body_w0, group, w0, t1, Np, hasp, tgrid, ntimes, t0, tfinal, out_p, out_b, body_writer, traj, ntot, status, s)))
+    switch (npts) {
+#if GB_PART == 5
+        case 1: GB_ND(6); break;
+        case 2: GB_ND(12); break;
+#else
+        case 3: GB_ND(18); break;
+        case 4: GB_ND(24); break;
+#endif
+        default: return cudaErrorInvalidValue;
+    }
+#undef GB_ND
+    return cudaGetLastError();
+}
+#if GB_PART == 5
+cudaError_t nbody_dop853(const DevPot& P, const DevBodies& B, const Dop853Args& a, const double* body_w0,
+                         const int32_t* group, const double* w0, const double* t1, size_t Np,
+                         const double* tgrid, int ntimes, double t0, double tfinal, double* out_p, double* out_b,
+                         size_t body_writer, double* traj, size_t ntot, int32_t* status, cudaStream_t s) {
+    return (B.nb + (Np > 0) <= 2)
+        ? nbody_dop853_small(P, B, a, body_w0, group, w0, t1, Np, tgrid, ntimes, t0, tfinal, out_p, out_b, body_writer, traj, ntot, status, s)
+        : nbody_dop853_big(P, B, a, body_w0, group, w0, t1, Np, tgrid, ntimes, t0, tfinal, out_p, out_b, body_writer, traj, ntot, status, s);
+}
+#endif
+#endif  // GB_PART == 5 || 6
 
 }  // namespace GB_NS

@@ -15,6 +15,12 @@ struct Dop853Args {
     double h0;        // initial step (t[1]-t[0]); 0 -> hinit
 };
 
+#define GB_DECL_ND(NAME)                                                                                   \
+    cudaError_t NAME(const DevPot& P, const DevBodies& B, const Dop853Args& a, const double* body_w0,     \
+                     const int32_t* group, const double* w0, const double* t1, size_t Np,                  \
+                     const double* tgrid, int ntimes, double t0, double tfinal, double* out_p,             \
+                     double* out_b, size_t body_writer, double* traj, size_t ntot, int32_t* status,        \
+                     cudaStream_t s);
 #define GB_DECLARE_KERNEL_API(NS)                                                                          \
     namespace NS {                                                                                         \
     cudaError_t eval_gradient(const DevPot& P, const double* q, double t, size_t N, double* g,            \
@@ -53,6 +59,16 @@ struct Dop853Args {
                             int32_t* status, int block, cudaStream_t s);                                   \
     cudaError_t mock_leapfrog(const DevPot& P, const double* w0_rows, const double* t1, size_t Np,        \
                               double tfinal, double dt, double* out_rows, int block, cudaStream_t s);      \
+    cudaError_t nbody_leapfrog(const DevPot& P, const DevBodies& B, const double* body_w0, const int32_t* group, \
+                               const double* w0, const double* t1, size_t Np, double t0, double tfinal,   \
+                               int nsteps_fixed, double dt, double* out_p, double* out_b,                  \
+                               size_t body_writer, double* traj, size_t ntot, int block, cudaStream_t s);  \
+    GB_DECL_ND(nbody_dop853_small) GB_DECL_ND(nbody_dop853_big)                                            \
+    cudaError_t nbody_dop853(const DevPot& P, const DevBodies& B, const Dop853Args& a,                    \
+                             const double* body_w0, const int32_t* group, const double* w0,                \
+                             const double* t1, size_t Np, const double* tgrid, int ntimes, double t0,      \
+                             double tfinal, double* out_p, double* out_b, size_t body_writer,              \
+                             double* traj, size_t ntot, int32_t* status, cudaStream_t s);                  \
     cudaError_t fardal_release(const DevPot& P, double G, const double* prog_w, const double* prog_t,     \
                                const double* prog_m, int ntimes, const int32_t* prog_idx,                  \
                                const double* sign, const double* normals, size_t Np, int gala_modified,   \

@@ -111,38 +111,160 @@ class FardalStreamDF:
         return MockStream(pos=x.T, vel=v.T, release_time=t1, lead_trail=lt, frame=H.frame)
 
 
+def _same_potential(a, b):
+    if a is b:
+        return True
+    ca, cb = a._components(), b._components()
+    return len(ca) == len(cb) and all(
+        x[0] == y[0] and np.array_equal(x[1], y[1]) and np.array_equal(np.zeros(3) if x[2] is None else x[2],
+                                                                       np.zeros(3) if y[2] is None else y[2])
+        for x, y in zip(ca, cb))
+
+
+def _is_null(pp):
+    return pp is None or pp.__class__.__name__ == "NullPotential"
+
+
+class _BodySpec:
+    """ctypes view of the per-body potentials (``gb_bodies``); bodies at index >= ``n_sources`` are passed
+    as massless (``leapfrog_integrate_nbody`` only loops over the first ``nbody`` = number-of-non-Null
+    potentials as force sources, leapfrog.pyx:200-202,236-247)."""
+
+    def __init__(self, particle_potentials, n_sources=None):
+        nb = len(particle_potentials)
+        if nb < 1 or nb > 4:
+            raise NotImplementedError("the B200 N-body kernels carry 1..4 bodies (massive or massless) per system")
+        self._keep = []
+        self.pots = (_abi.gb_potential * nb)()
+        for b, pp in enumerate(particle_potentials):
+            if _is_null(pp) or (n_sources is not None and b >= n_sources):
+                self.pots[b].n_components = 0
+                self.pots[b].n_dim = 3
+                continue
+            sp = pp.spec()
+            self._keep.append(sp)
+            self.pots[b] = sp.pot
+        self.struct = _abi.gb_bodies(nb, 0, C.cast(self.pots, C.POINTER(_abi.gb_potential)))
+
+    def ptr(self):
+        return C.byref(self.struct)
+
+
+def _nbody_leapfrog(H, pps, body_w0, t0, tfinal, nsteps, dt, w0_rows=None, t1=None, group=None, body_writer=0,
+                    save_all=False, n_sources=None):
+    """One ``gb_nbody_leapfrog`` call.  Returns (particles (Np,6) | None, bodies (nb,6), traj | None)."""
+    bs = _BodySpec(pps, n_sources)
+    body_w0 = np.ascontiguousarray(body_w0, dtype=np.float64).reshape(-1, len(pps), 6)
+    Np = 0 if w0_rows is None else w0_rows.shape[0]
+    rows = np.ascontiguousarray(w0_rows, dtype=np.float64) if Np else None
+    out_p = np.empty((Np, 6)) if Np else None
+    out_b = np.empty((len(pps), 6))
+    traj = np.empty((nsteps + 1, len(pps) + Np, 6)) if save_all else None
+    t1a = None if t1 is None else np.ascontiguousarray(t1, dtype=np.float64)
+    grp = None if group is None else np.ascontiguousarray(group, dtype=np.int32)
+    opt = _opts(H)
+    ptr = lambda a: None if a is None else a.ctypes.data
+    _abi.check(_abi.lib().gb_nbody_leapfrog(H.potential.spec().ptr(), bs.ptr(), body_w0.ctypes.data, body_w0.shape[0],
+                                            ptr(grp), ptr(rows), ptr(t1a), Np, float(t0), float(tfinal), int(nsteps),
+                                            float(dt), ptr(out_p), out_b.ctypes.data, int(body_writer), ptr(traj),
+                                            C.byref(opt)))
+    return out_p, out_b, traj
+
+
+def _nbody_dop853(H, pps, body_w0, tgrid, tfinal, dt0, step_mode, w0_rows=None, t1=None, group=None, body_writer=0,
+                  save_all=False, atol=1e-10, rtol=1e-10, nmax=0, dt_max=0.0, err_if_fail=1):
+    """One ``gb_nbody_dop853`` call.  Returns (particles | None, bodies, traj | None, status)."""
+    bs = _BodySpec(pps)
+    body_w0 = np.ascontiguousarray(body_w0, dtype=np.float64).reshape(-1, len(pps), 6)
+    Np = 0 if w0_rows is None else w0_rows.shape[0]
+    if len(pps) + (1 if Np else 0) > 4:
+        raise NotImplementedError("DOP853 N-body systems carry at most 4 points per lane (3 bodies + the test particle)")
+    rows = np.ascontiguousarray(w0_rows, dtype=np.float64) if Np else None
+    out_p = np.empty((Np, 6)) if Np else None
+    out_b = np.empty((len(pps), 6))
+    tg = None if tgrid is None else np.ascontiguousarray(tgrid, dtype=np.float64)
+    traj = np.empty((tg.size, len(pps) + Np, 6)) if save_all else None
+    status = np.empty(max(Np, 1), dtype=np.int32)
+    t1a = None if t1 is None else np.ascontiguousarray(t1, dtype=np.float64)
+    grp = None if group is None else np.ascontiguousarray(group, dtype=np.int32)
+    opt = _opts(H)
+    ptr = lambda a: None if a is None else a.ctypes.data
+    rc = _abi.lib().gb_nbody_dop853(H.potential.spec().ptr(), bs.ptr(), body_w0.ctypes.data, body_w0.shape[0], ptr(grp),
+                                    ptr(rows), ptr(t1a), Np, ptr(tg), 0 if tg is None else tg.size, float(tfinal),
+                                    float(dt0), float(atol), float(rtol), int(nmax), float(dt_max), int(step_mode),
+                                    ptr(out_p), out_b.ctypes.data, int(body_writer), ptr(traj), status.ctypes.data,
+                                    C.byref(opt))
+    if rc in (-1, -2, -3, -4):
+        if err_if_fail:
+            _abi.check(rc)
+    else:
+        _abi.check(rc)
+    return out_p, out_b, traj, status
+
+
 class DirectNBody:
-    """The slice of ``gala.dynamics.nbody.DirectNBody`` the mock-stream path touches
-    (``dynamics/nbody/core.py``): initial conditions of the bodies + per-body potentials + the external
-    Hamiltonian.  Only massless bodies (particle potential ``None``) are supported."""
+    """``gala.dynamics.nbody.DirectNBody`` (``dynamics/nbody/core.py``): initial conditions of the bodies,
+    one potential per body (``None`` = test particle) and the external Hamiltonian.  Up to 4 massive
+    bodies plus any number of test particles run on the device (one lane = the massive bodies + one test
+    particle, ``csrc/nbody.cuh``); without massive bodies every body is an independent orbit."""
 
     def __init__(self, w0, particle_potentials, external_potential=None, frame=None, units=None, save_all=True):
         w = w0.w() if isinstance(w0, PhaseSpacePosition) else np.asarray(w0, dtype=np.float64)
         w = w.reshape(6, -1)
         self._c_w0 = np.ascontiguousarray(w.T)            # (nbodies, 6) like the reference
-        self.particle_potentials = list(particle_potentials)
-        if any(p is not None and p.__class__.__name__ != "NullPotential" for p in self.particle_potentials):
-            raise NotImplementedError("massive bodies (self-gravity / perturbers) are not implemented yet")
+        self.particle_potentials = [None if _is_null(p) else p for p in particle_potentials]
         if len(self.particle_potentials) != self._c_w0.shape[0]:
-            raise ValueError("one particle potential per body is required")
+            raise ValueError("The number of initial conditions in `w0` must match the number of particle "
+                             "potentials passed in with `particle_potentials`.")
+        if external_potential is None:
+            from .potential import NullPotential
+            external_potential = NullPotential()
         self.H = Hamiltonian(external_potential, frame)
         self.external_potential, self.frame, self.units = self.H.potential, self.H.frame, self.H.units
         self.save_all = save_all
 
+    @property
+    def n_massive(self):
+        return sum(p is not None for p in self.particle_potentials)
+
     def integrate_orbit(self, Integrator=None, Integrator_kwargs=None, **time_spec):
-        """``nbody/core.py:166-282`` for massless bodies: DOPRI853 runs with the stiffness test disabled
-        (``nbody.pyx:106``), i.e. as independent n=6 systems here."""
+        """``nbody/core.py:166-282``: massive bodies are moved to the front, integrated together with the
+        test particles, and the original order is restored.  DOPRI853 runs with the stiffness test
+        disabled (``nbody.pyx:106``)."""
         Integrator = get_integrator(Integrator or DOPRI853Integrator)
         kw = dict(Integrator_kwargs or {})
         t = parse_time_specification(self.units, **time_spec)
-        w0 = np.ascontiguousarray(self._c_w0.T)
-        if Integrator is LeapfrogIntegrator:
-            _, w = leapfrog_integrate_hamiltonian(self.H, w0, t, save_all=int(self.save_all))
-        elif Integrator is DOPRI853Integrator:
-            kw = {k: kw[k] for k in ("atol", "rtol", "nmax", "dt_max", "err_if_fail") if k in kw}
-            _, w = dop853_integrate_hamiltonian(self.H, w0, t, nstiff=-1, save_all=int(self.save_all), **kw)
+        if Integrator not in (LeapfrogIntegrator, DOPRI853Integrator):
+            raise NotImplementedError(f"N-body integration is not supported with {Integrator} on the B200 engine")
+        kw = {k: kw[k] for k in ("atol", "rtol", "nmax", "dt_max", "err_if_fail") if k in kw}
+        if self.n_massive == 0:
+            w0 = np.ascontiguousarray(self._c_w0.T)
+            if Integrator is LeapfrogIntegrator:
+                _, w = leapfrog_integrate_hamiltonian(self.H, w0, t, save_all=int(self.save_all))
+            else:
+                _, w = dop853_integrate_hamiltonian(self.H, w0, t, nstiff=-1, save_all=int(self.save_all), **kw)
         else:
-            raise NotImplementedError(f"N-body integration is not supported with {Integrator}")
+            if not isinstance(self.frame, StaticFrame):
+                raise TypeError("N-body integration with massive bodies is only supported for StaticFrame")
+            front = [i for i, pp in enumerate(self.particle_potentials) if pp is not None]
+            end = [i for i, pp in enumerate(self.particle_potentials) if pp is None]
+            idx = np.array(front + end)
+            pps = [self.particle_potentials[i] for i in front]
+            body_w0 = self._c_w0[front]
+            rows = self._c_w0[end] if end else None
+            dt = t[1] - t[0]
+            if Integrator is LeapfrogIntegrator:
+                out_p, out_b, traj = _nbody_leapfrog(self.H, pps, body_w0, t[0], t[-1], len(t) - 1, dt, w0_rows=rows,
+                                                     save_all=self.save_all)
+            else:
+                out_p, out_b, traj, _ = _nbody_dop853(self.H, pps, body_w0, t, t[-1], dt, 0, w0_rows=rows,
+                                                      save_all=self.save_all, **kw)
+            undo = np.argsort(idx)
+            if self.save_all:
+                w = np.ascontiguousarray(traj[:, undo, :].transpose(2, 0, 1))      # (6, ntimes, N)
+            else:
+                ws = out_b if out_p is None else np.vstack([out_b, out_p])
+                w = np.ascontiguousarray(ws[undo].T)
         if self.save_all:
             return Orbit.from_w(w, t=t, hamiltonian=self.H)
         return PhaseSpacePosition.from_w(w, frame=self.frame)
@@ -169,6 +291,20 @@ def mockstream_dop853(nbody, time, stream_w0, stream_t1, tfinal, nstream, atol=1
     H = nbody.H
     nbodies = nbody._c_w0.shape[0]
     dt0 = time[1] - time[0]
+    if nbody.n_massive:
+        # massive bodies: every lane integrates [the bodies, one stream particle] (csrc/nbody.cuh)
+        pps = nbody.particle_potentials
+        _, _, traj, _ = _nbody_dop853(H, pps, nbody._c_w0, time, time[-1], dt0, 0, save_all=True, atol=atol, rtol=rtol,
+                                      nmax=nmax, dt_max=dt_max, err_if_fail=err_if_fail)      # mockstream.pyx:247-255
+        groups = np.nonzero(nstream)[0]
+        if groups.size == 0:
+            return traj[-1].copy(), np.empty((0, 6))
+        group = np.repeat(np.arange(ntimes, dtype=np.int32), nstream)
+        t1 = np.repeat(stream_t1, nstream)
+        writer = int(np.nonzero(group == groups[-1])[0][0])
+        out_p, out_b, _, _ = _nbody_dop853(H, pps, traj, None, tfinal, dt0, 1, w0_rows=stream_w0, t1=t1, group=group,
+                                           body_writer=writer, atol=atol, rtol=rtol, nmax=nmax, err_if_fail=err_if_fail)
+        return out_b, out_p
     # 1) the bodies at every release time: dense output of one DOP853 run (mockstream.pyx:247-255)
     _, nbody_w = dop853_integrate_hamiltonian(H, np.ascontiguousarray(nbody._c_w0.T), time, atol=atol, rtol=rtol,
                                               nmax=nmax, dt_max=dt_max, nstiff=nstiff, save_all=1,
@@ -208,6 +344,23 @@ def mockstream_leapfrog(nbody, full_time, spawn_time, stream_w0, stream_t1, tfin
     H = nbody.H
     nbodies = nbody._c_w0.shape[0]
     dt = full_time[1] - full_time[0]
+    if nbody.n_massive:
+        pps = nbody.particle_potentials
+        # leapfrog_integrate_nbody over the full grid (mockstream.pyx:528-531); only the first n_massive
+        # potentials act as sources there (leapfrog.pyx:200-202)
+        _, _, full = _nbody_leapfrog(H, pps, nbody._c_w0, full_time[0], full_time[-1], len(full_time) - 1, dt,
+                                     save_all=True, n_sources=nbody.n_massive)
+        idx = ((stream_t1 - full_time[0]) / dt + 0.5).astype(np.int64)              # mockstream.pyx:548
+        nbody_w = full[idx]                                                         # (ntimes, nbodies, 6)
+        groups = np.nonzero(nstream)[0]
+        if groups.size == 0:
+            raise ValueError("no stream particles to integrate")
+        group = np.repeat(np.arange(ntimes, dtype=np.int32), nstream)
+        t1 = np.repeat(stream_t1, nstream)
+        writer = int(np.nonzero(group == groups[-1])[0][0])
+        out_p, out_b, _ = _nbody_leapfrog(H, pps, nbody_w, 0.0, tfinal, 0, dt, w0_rows=stream_w0, t1=t1, group=group,
+                                          body_writer=writer)
+        return out_b, out_p
     _, traj = leapfrog_integrate_hamiltonian(H, np.ascontiguousarray(nbody._c_w0.T), full_time, save_all=1)
     groups = np.nonzero(nstream)[0]
     last = groups[-1] if groups.size else ntimes - 1
@@ -253,16 +406,26 @@ class MockStreamGenerator:
             raise TypeError("The input distribution function (DF) instance must be a stream DF")
         self.df = df
         self.hamiltonian = Hamiltonian(hamiltonian)
-        if progenitor_potential is not None:
-            raise NotImplementedError("progenitor self-gravity (massive bodies) is not implemented yet")
-        self.progenitor_potential = None
-        self.self_gravity = False
+        if progenitor_potential is not None and not hasattr(progenitor_potential, "spec"):
+            raise TypeError("If specified, the progenitor_potential must be a gala.potential class instance.")
+        self.progenitor_potential = progenitor_potential
+        self.self_gravity = progenitor_potential is not None
 
     def _get_nbody(self, prog_w0, nbody):
+        """``mockstream_generator.py:79-117``: the progenitor becomes body 0 of a DirectNBody, followed by
+        the bodies of the caller's ``nbody`` (perturbers)."""
+        pw = prog_w0.w() if isinstance(prog_w0, PhaseSpacePosition) else np.asarray(prog_w0, dtype=np.float64)
+        pw = pw.reshape(6, -1)
+        pps = [self.progenitor_potential]
         if nbody is not None:
-            raise NotImplementedError("additional N-body perturbers are not implemented yet")
-        return DirectNBody(prog_w0, [None], external_potential=self.hamiltonian.potential,
-                           frame=self.hamiltonian.frame, units=self.hamiltonian.units)
+            if not _same_potential(nbody.external_potential, self.hamiltonian.potential):
+                raise ValueError("The external potential of the input nbody instance must match the potential of the "
+                                 "mock stream input hamiltonian!")
+            pw = np.hstack([pw, nbody._c_w0.T])
+            pps = pps + list(nbody.particle_potentials)
+        return DirectNBody(PhaseSpacePosition.from_w(pw, frame=self.hamiltonian.frame), pps,
+                           external_potential=self.hamiltonian.potential, frame=self.hamiltonian.frame,
+                           units=self.hamiltonian.units)
 
     def run(self, prog_w0, prog_mass, nbody=None, release_every=1, n_particles=1, output_every=None,
             output_filename=None, check_filesize=True, overwrite=False, progress=False, Integrator=None,

@@ -191,6 +191,48 @@ int gb_mockstream_leapfrog(const gb_potential* pot,
                            double tfinal, double dt,
                            double* stream_w, const gb_launch* opt);
 
+/* ---- massive bodies (direct N-body) --------------------------------------------------
+ * Replaces, for systems of a few massive bodies plus any number of TEST particles:
+ *   leapfrog_integrate_nbody   integrate/cyintegrators/leapfrog.pyx:161-257
+ *   direct_nbody_dop853        dynamics/nbody/nbody.pyx:30-115
+ *   the massive-body branches of mockstream_leapfrog / mockstream_dop853
+ *                              dynamics/mockstream/mockstream.pyx:442-620, 176-303
+ * (c_nbody_gradient_symplectic / c_nbody_acceleration, potential/potential/src/cpotential.cpp:389-442).
+ * body_pot[b] is body b's own potential (the reference's particle_potentials[b]; n_components == 0 or
+ * all-Null components = a massless body), evaluated about the body's current position.  Every device
+ * lane integrates [the bodies, ONE test particle]; test particles never act on anything.  Host buffers
+ * only.  Rows are AoS: body_w0 (ngroups, n_bodies, 6) -- particle p starts with the bodies in state
+ * body_w0[group[p]] (group == NULL: state 0) at time t1[p] (t1 == NULL: the common start time);
+ * w0_rows (Np, 6); out_particles (Np, 6); out_bodies (n_bodies, 6) = the bodies as integrated by lane
+ * `body_writer` (Np == 0: the single bodies-only lane); traj (ntimes, n_bodies + Np, 6) or NULL. */
+#define GB_MAX_BODIES 4
+typedef struct {
+    int32_t n_bodies;              /* 1..GB_MAX_BODIES */
+    int32_t _pad;
+    const gb_potential* body_pot;  /* [n_bodies] */
+} gb_bodies;
+
+/* fixed step: particle p takes int((tfinal - t1[p])/dt + 0.5) steps (mockstream.pyx:571), or `nsteps`
+ * when t1 == NULL.  StaticFrame only, like the reference (leapfrog.pyx:172-176). */
+int gb_nbody_leapfrog(const gb_potential* pot, const gb_bodies* bodies,
+                      const double* body_w0, int ngroups, const int32_t* group,
+                      const double* w0_rows, const double* t1, size_t Np,
+                      double t0, double tfinal, int nsteps, double dt,
+                      double* out_particles, double* out_bodies, size_t body_writer,
+                      double* traj, const gb_launch* opt);
+
+/* DOP853: step_mode 0 = dop853_helper's settings with nstiff = -1 (direct_nbody_dop853), tgrid/ntimes
+ * = the caller's output grid (dense output when traj != NULL); step_mode 1 = dop853_step's settings
+ * (mockstream_dop853).  At most 4 points per lane (n_bodies + 1 <= 4 with test particles).  status:
+ * one dop853 code per lane (Np entries, or 1). */
+int gb_nbody_dop853(const gb_potential* pot, const gb_bodies* bodies,
+                    const double* body_w0, int ngroups, const int32_t* group,
+                    const double* w0_rows, const double* t1, size_t Np,
+                    const double* tgrid, int ntimes, double tfinal, double dt0,
+                    double atol, double rtol, long nmax, double dt_max, int step_mode,
+                    double* out_particles, double* out_bodies, size_t body_writer,
+                    double* traj, int32_t* status, const gb_launch* opt);
+
 /* ---- misc ------------------------------------------------------------------------ */
 const char* gb_last_error(void);
 int  gb_device_count(void);

@@ -134,6 +134,46 @@ class _Lib:
                                           status.ctypes.data_as(C.c_void_p))
         return rows, status, rc
 
+    # ---- massive bodies (reference c_nbody_* + Fwrapper_direct_nbody; ref_driver.cpp) -------------------
+    @staticmethod
+    def _body_specs(pps):
+        import gala_b200 as gb
+        null = gb.NullPotential()
+        keep = [null.spec()] + [(null if p is None else p).spec() for p in pps]
+        arr = (type(keep[0].pot) * len(pps))()
+        for b in range(len(pps)):
+            arr[b] = keep[b + 1].pot
+        return keep, arr
+
+    def nbody_leapfrog(self, H, pps, w_rows, t0, nsteps, dt, nsrc=None, save_all=False):
+        """rows (n,6): bodies (one potential each in ``pps``, None = massless) then test particles.
+        Returns (final rows, traj (nsteps+1, n, 6) | None)."""
+        keep, arr = self._body_specs(pps)
+        rows = _f64(w_rows).copy(); n = rows.shape[0]
+        traj = np.empty((nsteps + 1, n, 6)) if save_all else None
+        rc = self._fn("nbody_leapfrog")(H.potential.spec().ptr(), arr, C.c_int(len(pps)), keep[0].ptr(),
+                                        rows.ctypes.data_as(C.c_void_p), C.c_size_t(n),
+                                        C.c_int(len(pps) if nsrc is None else nsrc), C.c_double(t0), C.c_int(nsteps),
+                                        C.c_double(dt), None if traj is None else traj.ctypes.data_as(C.c_void_p))
+        assert rc == 0, rc
+        return rows, traj
+
+    def nbody_dop853(self, H, pps, w_rows, tgrid=None, t1=0.0, t2=0.0, dt0=0.0, atol=1e-10, rtol=1e-10, nmax=0,
+                     dt_max=0.0, mode=0, save_all=False):
+        """mode 0: direct_nbody_dop853 over ``tgrid`` (dense output when save_all); mode 1: dop853_step t1->t2."""
+        keep, arr = self._body_specs(pps)
+        rows = _f64(w_rows).copy(); n = rows.shape[0]
+        tg = None if tgrid is None else _f64(tgrid)
+        traj = np.empty((tg.size, n, 6)) if (save_all and tg is not None) else None
+        rc = self._fn("nbody_dop853")(H.potential.spec().ptr(), arr, C.c_int(len(pps)), keep[0].ptr(),
+                                      rows.ctypes.data_as(C.c_void_p), C.c_size_t(n),
+                                      None if tg is None else tg.ctypes.data_as(C.c_void_p),
+                                      C.c_int(0 if tg is None else tg.size), C.c_double(t1), C.c_double(t2),
+                                      C.c_double(dt0), C.c_double(atol), C.c_double(rtol), C.c_long(nmax),
+                                      C.c_double(dt_max), C.c_int(mode),
+                                      None if traj is None else traj.ctypes.data_as(C.c_void_p))
+        return rows, traj, rc
+
     def d2_dr2(self, pot, q3, t=0.0):
         q3 = _f64(q3)
         return self._fn("d2_dr2", C.c_double)(pot.spec().ptr(), C.c_double(t), q3.ctypes.data_as(C.c_void_p))

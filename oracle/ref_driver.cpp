@@ -394,6 +394,87 @@ double ref_d2_dr2(const gb_potential *spec, double t, const double *q3) {
     return c_d2_dr2(rp.cp, t, q, eps);
 }
 
+// ---- massive bodies -----------------------------------------------------------------------------------
+// System rows (n, 6): the first `nbodies` rows are bodies with their own potentials body_specs[b]
+// (a Null-type spec = massless), the rest are test particles (Null potentials, as
+// _setup_particle_potentials does, dynamics/mockstream/mockstream.pyx:49-77).
+struct RefBodies {
+    std::vector<RefPotential> pots;       // one per row of the system
+    std::vector<CPotential *> ptrs;
+    bool build_all(const gb_potential *body_specs, int nbodies, size_t n, const gb_potential *null_spec) {
+        pots.resize(n); ptrs.resize(n);
+        for (size_t i = 0; i < n; i++) {
+            if (!build(i < (size_t)nbodies ? &body_specs[i] : null_spec, pots[i])) return false;
+            ptrs[i] = pots[i].cp;
+        }
+        return true;
+    }
+};
+
+// leapfrog_integrate_nbody (integrate/cyintegrators/leapfrog.pyx:161-257) == the per-group loop of
+// mockstream_leapfrog (dynamics/mockstream/mockstream.pyx:556-590): c_init_velocity_nbody for every row,
+// then nsteps of c_leapfrog_step_nbody over the rows IN ORDER, in place.  `nsrc` is the `nbody` argument
+// handed to c_nbody_gradient_symplectic (sources = rows j < nsrc).  traj: (nsteps+1, n, 6) or NULL.
+int ref_nbody_leapfrog(const gb_potential *spec, const gb_potential *body_specs, int nbodies,
+                       const gb_potential *null_spec, double *w_rows, size_t n, int nsrc, double t0, int nsteps,
+                       double dt, double *traj) {
+    RefPotential rp; if (!build(spec, rp)) return -11;
+    RefBodies rb; if (!rb.build_all(body_specs, nbodies, n, null_spec)) return -11;
+    std::vector<double> v12(3 * n, 0.);
+    double grad[3];
+    if (traj) memcpy(traj, w_rows, n * 6 * sizeof(double));
+    for (size_t i = 0; i < n; i++) {
+        double *x = w_rows + 6 * i, *v = x + 3;
+        grad[0] = grad[1] = grad[2] = 0.;
+        c_gradient(rp.cp, 1, t0, x, grad);                                               // leapfrog.pyx:134
+        c_nbody_gradient_symplectic(rb.ptrs.data(), t0, x, w_rows, nsrc, (int)i, 3, grad);
+        for (int k = 0; k < 3; k++) v12[3 * i + k] = v[k] - grad[k] * dt / 2.;
+    }
+    for (int j = 0; j < nsteps; j++) {
+        const double tj = t0 + (j + 1) * dt;
+        for (size_t i = 0; i < n; i++) {
+            double *x = w_rows + 6 * i, *v = x + 3;
+            grad[0] = grad[1] = grad[2] = 0.;
+            for (int k = 0; k < 3; k++) x[k] = x[k] + v12[3 * i + k] * dt;                 // leapfrog.pyx:147-148
+            c_gradient(rp.cp, 1, tj, x, grad);
+            c_nbody_gradient_symplectic(rb.ptrs.data(), tj, x, w_rows, nsrc, (int)i, 3, grad);
+            for (int k = 0; k < 3; k++) {
+                v[k] = v12[3 * i + k] - grad[k] * dt / 2.;
+                v12[3 * i + k] = v12[3 * i + k] - grad[k] * dt;
+            }
+        }
+        if (traj) memcpy(traj + (size_t)(j + 1) * n * 6, w_rows, n * 6 * sizeof(double));
+    }
+    return 0;
+}
+
+// dop853 over the whole system with Fwrapper_direct_nbody (dop853.cpp:990-1006).
+// mode 0: dop853_helper's call (dop853.pyx:157-182) as used by direct_nbody_dop853 (nbody.pyx:96-110,
+//         nstiff = -1) with dense output at tgrid -> traj (ntimes, n, 6) when traj != NULL;
+// mode 1: dop853_step's call (dop853.pyx:45-69) from t1 to t2, final state only.
+int ref_nbody_dop853(const gb_potential *spec, const gb_potential *body_specs, int nbodies,
+                     const gb_potential *null_spec, double *w_rows, size_t n, const double *tgrid, int ntimes,
+                     double t1, double t2, double dt0, double atol, double rtol, long nmax, double dt_max, int mode,
+                     double *traj) {
+    RefPotential rp; if (!build(spec, rp)) return -11;
+    RefFrame rf; build_frame(NULL, rf);
+    RefBodies rb; if (!rb.build_all(body_specs, nbodies, n, null_spec)) return -11;
+    double rt = rtol, at = atol;
+    const unsigned size = 6 * n;
+    void *args = (void *)rb.ptrs.data();
+    if (mode == 1)
+        return dop853(size, (FcnEqDiff)Fwrapper_direct_nbody, rp.cp, &rf.cf, n, nbodies, args, t1, w_rows, t2,
+                      &rt, &at, 0, NULL, 0, NULL, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, dt0, nmax, 0, 1, 0, NULL, 0,
+                      NULL, NULL, 0, NULL);
+    Dop853DenseState *state = traj ? dop853_dense_state_alloc(size, size) : NULL;
+    int res = dop853(size, (FcnEqDiff)Fwrapper_direct_nbody, rp.cp, &rf.cf, n, nbodies, args, tgrid[0], w_rows,
+                     tgrid[ntimes - 1], &rt, &at, 0, NULL, 0, NULL, 2.220446049250313e-16, 0.0, 0.0, 0.0, 0.0,
+                     dt_max, tgrid[1] - tgrid[0], nmax, 1, -1, traj ? size : 0, NULL, 0, state,
+                     const_cast<double *>(tgrid), ntimes, traj);
+    if (state) dop853_dense_state_free(state, size);
+    return res;
+}
+
 const char *ref_build_flags(void) { return GB_REF_FLAGS; }
 
 }  // extern "C"

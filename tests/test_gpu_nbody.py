@@ -1,0 +1,196 @@
+"""GPU parity of the massive-body (direct N-body) path -- SURVEY section 8 row f-2 -- against the reference's
+own ``c_nbody_gradient_symplectic`` / ``Fwrapper_direct_nbody`` + ``dop853`` compiled into
+oracle/_ref/libgala_ref.so, driven by the restated Cython loops of oracle/ref_driver.cpp
+(leapfrog.pyx:126-257, nbody.pyx:30-115, mockstream.pyx:176-303,442-620)."""
+import numpy as np
+import pytest
+
+import gala_b200 as gb
+from gala_b200.mockstream import DirectNBody, mockstream_dop853, mockstream_leapfrog
+from conftest import relnorm
+
+pytestmark = pytest.mark.gpu
+
+KMS = gb.KMS_TO_KPC_MYR
+PROG_W0 = np.array([13.0, 0.0, 20.0, 0.0, 130.0 * KMS, 50.0 * KMS])   # tests/dynamics/mockstream/test_mockstream.py:676-678
+
+
+def _system(n_test=64, seed=3):
+    """two massive satellites (Hernquist, Plummer) + test particles scattered around the first one"""
+    rng = np.random.default_rng(seed)
+    b0 = PROG_W0
+    b1 = np.array([-25.0, 8.0, 5.0, 0.02, -0.15, 0.03])
+    tp = b0[None, :] + np.hstack([rng.normal(0, 1.5, (n_test, 3)), rng.normal(0, 0.004, (n_test, 3))])
+    pps = [gb.HernquistPotential(m=2e9, c=0.8), gb.PlummerPotential(m=5e9, b=1.2)]
+    return np.vstack([b0, b1]), tp, pps
+
+
+@pytest.mark.parametrize("strict", [True, False])
+def test_direct_nbody_leapfrog_matches_reference(ref, strict):
+    pot = gb.MilkyWayPotential2022(); pot.strict_math = strict
+    H = gb.Hamiltonian(pot)
+    bodies, tp, pps = _system()
+    # test particles first, massive bodies in the middle/end: integrate_orbit must reorder and restore
+    w_all = np.vstack([tp[:10], bodies[:1], tp[10:], bodies[1:]])
+    ppl = [None] * 10 + [pps[0]] + [None] * (len(tp) - 10) + [pps[1]]
+    nb = DirectNBody(gb.PhaseSpacePosition.from_w(np.ascontiguousarray(w_all.T)), ppl, external_potential=pot)
+    t = np.arange(0, 301.0) * 1.0
+    orb = nb.integrate_orbit(t=t, Integrator="leapfrog")
+    got = np.vstack([orb.pos, orb.vel])                                  # (6, ntimes, N)
+    # reference: ONE system, massive bodies first (nbody/core.py:213-227), sequential in-place update
+    rows = np.vstack([bodies, tp])
+    fin, traj = ref.nbody_leapfrog(H, pps, rows, t[0], len(t) - 1, 1.0, save_all=True)
+    order = [len(bodies) + i for i in range(10)] + [0] + [len(bodies) + i for i in range(10, len(tp))] + [1]
+    want = traj[:, order, :].transpose(2, 0, 1)
+    d = relnorm(got[:, -1], want[:, -1])
+    print(f"\n[nbody leapfrog strict={strict}] final-state q50/max = {np.median(d):.2e} {d.max():.2e}")
+    assert d.max() < (1e-13 if strict else 1e-11)
+    assert relnorm(got[:, 150], want[:, 150]).max() < (1e-13 if strict else 1e-11)
+    nb.save_all = False
+    fin_g = nb.integrate_orbit(t=t, Integrator="leapfrog")
+    assert np.allclose(np.vstack([fin_g.pos, fin_g.vel]), got[:, -1], rtol=0, atol=0)
+    pot.strict_math = False
+
+
+def test_direct_nbody_massive_only_and_momentum(ref):
+    """Two Kepler point masses, no external field: the system is run by a single lane; total momentum is
+    conserved and the result equals the reference's."""
+    pps = [gb.KeplerPotential(m=1e10), gb.KeplerPotential(m=3e10)]
+    G = gb.G_GALACTIC
+    sep = 10.0
+    vrel = np.sqrt(G * 4e10 / sep)
+    w = np.array([[-7.5, 0, 0, 0, -0.75 * vrel, 0], [2.5, 0, 0, 0, 0.25 * vrel, 0]])
+    nb = DirectNBody(gb.PhaseSpacePosition.from_w(np.ascontiguousarray(w.T)), pps)
+    t = np.linspace(0, 2000.0, 401)
+    for integ in ("leapfrog", "dopri853"):
+        orb = nb.integrate_orbit(t=t, Integrator=integ)
+        p_tot = 1e10 * orb.vel[:, :, 0] + 3e10 * orb.vel[:, :, 1]
+        assert np.abs(p_tot).max() < 1e-9 * 3e10 * vrel, integ
+        r = np.sqrt(((orb.pos[:, :, 0] - orb.pos[:, :, 1]) ** 2).sum(0))
+        assert np.abs(r / sep - 1).max() < (2e-3 if integ == "leapfrog" else 1e-7), integ      # circular orbit
+    H = nb.H
+    fin, traj, rc = ref.nbody_dop853(H, pps, w, tgrid=t, mode=0, save_all=True)
+    assert rc >= 0
+    got = np.vstack([orb.pos, orb.vel]).transpose(1, 2, 0)               # (ntimes, N, 6)
+    assert np.max(np.abs(got - traj)) / sep < 1e-9
+
+
+def test_direct_nbody_dop853_per_lane_matches_reference(ref):
+    pot = gb.MilkyWayPotential2022()
+    H = gb.Hamiltonian(pot)
+    bodies, tp, pps = _system(n_test=24)
+    nb = DirectNBody(gb.PhaseSpacePosition.from_w(np.ascontiguousarray(np.vstack([bodies, tp]).T)), pps + [None] * len(tp),
+                     external_potential=pot)
+    t = np.linspace(0, 400.0, 81)
+    orb = nb.integrate_orbit(t=t, Integrator="dopri853")
+    got = np.vstack([orb.pos, orb.vel]).transpose(1, 2, 0)               # (ntimes, N, 6)
+    # the device definition: every lane = [bodies, ONE particle] with its own step size
+    worst = 0.0
+    for p in range(len(tp)):
+        fin, traj, rc = ref.nbody_dop853(H, pps, np.vstack([bodies, tp[p:p + 1]]), tgrid=t, mode=0, save_all=True)
+        assert rc >= 0
+        d = relnorm(got[:, 2 + p, :].T, traj[:, 2, :].T)
+        worst = max(worst, d.max())
+    print(f"\n[nbody dop853 per-lane] max over particles/times = {worst:.2e}")
+    assert worst < 1e-9
+    # the reference's own definition (ONE step size for the whole system): measured
+    fin, traj, rc = ref.nbody_dop853(H, pps, np.vstack([bodies, tp]), tgrid=t, mode=0, save_all=True)
+    dg = relnorm(got[-1].T, traj[-1].T)
+    print(f"[nbody dop853 vs whole-system stepping] median={np.median(dg):.2e} max={dg.max():.2e}")
+    assert np.median(dg) < 1e-7
+
+
+def _release(H, n_steps, n_particles, seed=42):
+    t = gb.parse_time_specification(None, dt=1.0, n_steps=n_steps)
+    nb0 = DirectNBody(PROG_W0, [None], external_potential=H.potential)
+    orb = nb0.integrate_orbit(t=t, Integrator="leapfrog")
+    prog = gb.Orbit(pos=orb.pos[:, :, 0], vel=orb.vel[:, :, 0], t=t, hamiltonian=H)
+    s0 = gb.FardalStreamDF(gala_modified=True, random_state=np.random.RandomState(seed)).sample(
+        prog, 5e8, n_particles=n_particles)
+    return t, np.ascontiguousarray(np.vstack([s0.pos, s0.vel]).T), np.asarray(s0.release_time)
+
+
+@pytest.mark.parametrize("with_perturber", [False, True])
+def test_mockstream_leapfrog_self_gravity(ref, with_perturber):
+    """mockstream_leapfrog with a massive progenitor (and optionally a massive perturber): every release
+    group is re-integrated from the bodies' state at the release time (mockstream.pyx:548-590)."""
+    pot = gb.MilkyWayPotential2022(); pot.strict_math = True
+    H = gb.Hamiltonian(pot)
+    n_steps = 80
+    t, w0, rel_t = _release(H, n_steps, 3)
+    pps = [gb.PlummerPotential(m=5e8, b=0.3)]
+    body_w0 = PROG_W0[None, :]
+    if with_perturber:
+        pps.append(gb.HernquistPotential(m=1e10, c=1.0))
+        body_w0 = np.vstack([body_w0, [15.0, 3.0, 17.0, -0.05, 0.1, 0.08]])
+    nb = DirectNBody(gb.PhaseSpacePosition.from_w(np.ascontiguousarray(body_w0.T)), pps, external_potential=pot)
+    unq, nstream = np.unique(rel_t, return_counts=True)
+    got_b, got_s = mockstream_leapfrog(nb, t, unq, w0, unq, t[-1], nstream.astype("i4"))
+    # reference loop
+    _, full = ref.nbody_leapfrog(H, pps, body_w0, t[0], n_steps, 1.0, nsrc=len(pps), save_all=True)
+    want = np.empty_like(w0)
+    n = 0
+    for i, t1 in enumerate(unq):
+        idx = int((t1 - t[0]) / 1.0 + 0.5)
+        rows = np.vstack([full[idx], w0[n:n + nstream[i]]])
+        ns = int((t[-1] - t1) / 1.0 + 0.5)
+        fin, _ = ref.nbody_leapfrog(H, pps, rows, t1, ns, 1.0)
+        want[n:n + nstream[i]] = fin[len(pps):]
+        last_b = fin[:len(pps)]
+        n += nstream[i]
+    d = relnorm(got_s.T, want.T)
+    print(f"\n[mockstream leapfrog self-gravity perturber={with_perturber}] q50/max = {np.median(d):.2e} {d.max():.2e}")
+    assert d.max() < 1e-12
+    assert relnorm(got_b.T, last_b.T).max() < 1e-13
+    pot.strict_math = False
+
+
+def test_mockstream_dop853_self_gravity(ref):
+    pot = gb.MilkyWayPotential2022()
+    H = gb.Hamiltonian(pot)
+    n_steps = 60
+    t, w0, rel_t = _release(H, n_steps, 2)
+    pps = [gb.PlummerPotential(m=5e8, b=0.3)]
+    body_w0 = PROG_W0[None, :]
+    nb = DirectNBody(gb.PhaseSpacePosition.from_w(np.ascontiguousarray(body_w0.T)), pps, external_potential=pot)
+    unq, nstream = np.unique(rel_t, return_counts=True)
+    got_b, got_s = mockstream_dop853(nb, unq, w0, unq, t[-1], nstream.astype("i4"))
+    _, traj, rc = ref.nbody_dop853(H, pps, body_w0, tgrid=unq, mode=0, save_all=True)
+    assert rc >= 0
+    want = np.empty_like(w0)
+    wantg = np.empty_like(w0)
+    n = 0
+    for i, t1 in enumerate(unq):
+        for p in range(n, n + nstream[i]):            # device definition: [bodies, one particle]
+            fin, _, rc = ref.nbody_dop853(H, pps, np.vstack([traj[i], w0[p:p + 1]]), t1=t1, t2=t[-1], dt0=unq[1] - unq[0], mode=1)
+            assert rc >= 0
+            want[p] = fin[1]
+        fin, _, rc = ref.nbody_dop853(H, pps, np.vstack([traj[i], w0[n:n + nstream[i]]]), t1=t1, t2=t[-1],
+                                      dt0=unq[1] - unq[0], mode=1)      # the reference's group
+        wantg[n:n + nstream[i]] = fin[1:]
+        n += nstream[i]
+    keep = rel_t < t[-1]                  # the last group starts at tfinal: nothing to integrate
+    d = relnorm(got_s[keep].T, want[keep].T)
+    dg = relnorm(got_s[keep].T, wantg[keep].T)
+    print(f"\n[mockstream dop853 self-gravity] per-lane q50/max = {np.median(d):.2e} {d.max():.2e}; "
+          f"vs grouped stepping q50/max = {np.median(dg):.2e} {dg.max():.2e}")
+    assert d.max() < 1e-9
+    assert np.median(dg) < 1e-7
+
+
+def test_generator_with_progenitor_potential_changes_the_stream():
+    """End to end through MockStreamGenerator (mockstream_generator.py:119-372) with self-gravity."""
+    pot = gb.MilkyWayPotential2022()
+    H = gb.Hamiltonian(pot)
+    mk = lambda: gb.FardalStreamDF(gala_modified=True, random_state=np.random.RandomState(42))
+    s0, p0 = gb.MockStreamGenerator(mk(), H).run(PROG_W0, 5e8, dt=-1.0, n_steps=300, n_particles=2)
+    for integ in ("leapfrog", "dopri853"):
+        gen = gb.MockStreamGenerator(mk(), H, progenitor_potential=gb.PlummerPotential(m=5e8, b=0.3))
+        s1, p1 = gen.run(PROG_W0, 5e8, dt=-1.0, n_steps=300, n_particles=2, Integrator=integ)
+        assert s1.pos.shape == s0.pos.shape and np.all(np.isfinite(s1.pos))
+        # the progenitor only feels the external field: same end state as without self-gravity
+        assert np.allclose(p1.pos, p0.pos, rtol=1e-6) and np.allclose(p1.vel, p0.vel, rtol=1e-6)
+        # recently released particles linger near the progenitor and feel it: the stream must differ
+        assert np.abs(s1.pos - s0.pos).max() > 1e-3
+        late = np.asarray(s1.release_time) > -5
+        assert np.sqrt(((s1.pos[:, late] - p1.pos.reshape(3, 1)) ** 2).sum(0)).max() < 5.0
