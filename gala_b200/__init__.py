@@ -14,6 +14,7 @@ from .integrate import (pinned_empty, parse_time_specification, LeapfrogIntegrat
                         leapfrog_integrate_hamiltonian, ruth4_integrate_hamiltonian,
                         dop853_integrate_hamiltonian)
 from .hamiltonian import Hamiltonian
-from .mockstream import FardalStreamDF, MockStreamGenerator, mockstream_dop853, mockstream_leapfrog
+from .mockstream import (BaseStreamDF, FardalStreamDF, StreaklineStreamDF, LagrangeCloudStreamDF, ChenStreamDF,
+                         MockStreamGenerator, DirectNBody, mockstream_dop853, mockstream_leapfrog)
 
 __version__ = "0.1.0"

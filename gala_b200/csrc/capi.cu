@@ -771,13 +771,16 @@ int gb_dop853(const gb_potential* pot, const gb_frame* fr, const double* w0, siz
     return 0;
 }
 
-int gb_fardal_release(const gb_potential* pot, double G, const double* prog_w, const double* prog_t,
+int gb_stream_release(const gb_potential* pot, double G, const double* prog_w, const double* prog_t,
                       const double* prog_m, int ntimes, const int32_t* prog_idx, const double* sign,
-                      const double* normals, size_t Np, int gala_modified, double* stream_w0,
+                      const double* draws, int ncols, size_t Np, int df_kind, int flags, double* stream_w0,
                       const gb_launch* opt) {
     Ctx c; RET_IF(open_ctx(opt, c));
     if (ntimes < 1 || !prog_w || !prog_t || !prog_m) return fail(-12, "null progenitor arrays");
-    if (Np && (!prog_idx || !sign || !normals || !stream_w0)) return fail(-12, "null data pointer");
+    if (df_kind < 0 || df_kind > 3) return fail(-12, "unknown stream DF kind");
+    static const int need[4] = {4, 0, 3, 6};
+    if (ncols < need[df_kind]) return fail(-12, "too few random deviates per particle for this DF");
+    if (Np && (!prog_idx || !sign || !stream_w0 || (need[df_kind] && !draws))) return fail(-12, "null data pointer");
     Resolved r; RET_IF(resolve(pot, r, c.stream));
     const int block = c.block > 0 ? c.block : 128;
     const void *dpw, *dpt, *dpm, *dpi, *dsg, *dnr;
@@ -786,16 +789,24 @@ int gb_fardal_release(const gb_potential* pot, double G, const double* prog_w, c
     RET_IF(stage_in(c, 3, prog_m, (size_t)ntimes * sizeof(double), &dpm));
     RET_IF(stage_in(c, 4, prog_idx, Np * sizeof(int32_t), &dpi));
     RET_IF(stage_in(c, 5, sign, Np * sizeof(double), &dsg));
-    RET_IF(stage_in(c, 6, normals, Np * 4 * sizeof(double), &dnr));
+    RET_IF(stage_in(c, 6, draws, draws ? Np * (size_t)ncols * sizeof(double) : 0, &dnr));
     void* dout; RET_IF(stage_out_alloc(c, 1, stream_w0, Np * 6 * sizeof(double), &dout));
     cudaError_t e = KCALL(c, fardal_release, r.P, G, (const double*)dpw, (const double*)dpt, (const double*)dpm, ntimes,
-                          (const int32_t*)dpi, (const double*)dsg, (const double*)dnr, Np, gala_modified,
+                          (const int32_t*)dpi, (const double*)dsg, (const double*)dnr, ncols, Np, df_kind, flags,
                           (double*)dout, block, c.stream);
-    if (e != cudaSuccess) return cuda_fail(e, "fardal_release launch");
+    if (e != cudaSuccess) return cuda_fail(e, "stream release launch");
     if (Np) g_launches++;
     RET_IF(stage_out_copy(c, stream_w0, dout, Np * 6 * sizeof(double)));
     if (r.d_ext) CU(cudaStreamSynchronize(c.stream));
     return finish(c);
+}
+
+int gb_fardal_release(const gb_potential* pot, double G, const double* prog_w, const double* prog_t,
+                      const double* prog_m, int ntimes, const int32_t* prog_idx, const double* sign,
+                      const double* normals, size_t Np, int gala_modified, double* stream_w0,
+                      const gb_launch* opt) {
+    return gb_stream_release(pot, G, prog_w, prog_t, prog_m, ntimes, prog_idx, sign, normals, 4, Np, 0, gala_modified,
+                             stream_w0, opt);
 }
 
 int gb_mockstream_dop853(const gb_potential* pot, const gb_frame* fr, const double* stream_w0, const double* t1,

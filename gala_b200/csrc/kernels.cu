@@ -352,10 +352,10 @@ cudaError_t mock_leapfrog(const DevPot& P, const double* w0_rows, const double* 
 
 cudaError_t fardal_release(const DevPot& P, double G, const double* prog_w, const double* prog_t,
                            const double* prog_m, int ntimes, const int32_t* prog_idx, const double* sign,
-                           const double* normals, size_t Np, int gala_modified, double* out_rows, int block,
-                           cudaStream_t s) {
+                           const double* normals, int ncols, size_t Np, int kind, int gala_modified, double* out_rows,
+                           int block, cudaStream_t s) {
     if (Np == 0) return cudaSuccess;
-    GB_SIG_SWITCH(P.sig, (k_fardal_release<C><<<nblocks(Np, block), block, 0, s>>>(P, G, prog_w, prog_t, prog_m, ntimes, prog_idx, sign, normals, Np, gala_modified, out_rows)));
+    GB_SIG_SWITCH(P.sig, (k_fardal_release<C><<<nblocks(Np, block), block, 0, s>>>(P, G, prog_w, prog_t, prog_m, ntimes, prog_idx, sign, normals, ncols, Np, kind, gala_modified, out_rows)));
     return cudaGetLastError();
 }
 

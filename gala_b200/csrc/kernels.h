@@ -71,8 +71,8 @@ struct Dop853Args {
                              double* traj, size_t ntot, int32_t* status, cudaStream_t s);                  \
     cudaError_t fardal_release(const DevPot& P, double G, const double* prog_w, const double* prog_t,     \
                                const double* prog_m, int ntimes, const int32_t* prog_idx,                  \
-                               const double* sign, const double* normals, size_t Np, int gala_modified,   \
-                               double* out_rows, int block, cudaStream_t s);                               \
+                               const double* sign, const double* normals, int ncols, size_t Np, int kind, \
+                               int gala_modified, double* out_rows, int block, cudaStream_t s);            \
     }
 
 // sort.cu: radix sort of (float key, uint32 value) pairs with cub (plumbing for the orbit queue order)

@@ -9,13 +9,17 @@
 // one-thread-per-particle batch valid.  Rows are AoS (Np,6) as in the reference.
 #pragma once
 
-// One thread per stream particle.  normals row = [kx, z, vt, vz] drawn on the host in the
-// reference's RNG order; sign = +1 trailing / -1 leading (df.pyx:393-454).
+// One thread per stream particle.  The random deviates of particle p are the row normals[p * ncols ..]
+// drawn on the host in the reference's RNG order; sign = +1 trailing / -1 leading.  kind selects the DF:
+//   0 Fardal+15      (df.pyx:363-456)  row [kx, z, vt, vz] ~ N(k_mean, k_disp); flag = gala_modified
+//   1 Streakline     (df.pyx:242-318)  no deviates: released at +-rj with +-vj
+//   2 LagrangeCloud  (df.pyx:460-552)  row [vx, vy, vz] ~ N(0, v_disp)
+//   3 Chen+24        (df.pyx:556-702)  row [r, phi, theta, v, alpha, beta] ~ N(mean, cov), angles in degrees
 template <class C>
 __global__ void k_fardal_release(const __grid_constant__ DevPot P, double G, const double* __restrict__ prog_w,
                                  const double* __restrict__ prog_t, const double* __restrict__ prog_m, int ntimes,
                                  const int32_t* __restrict__ prog_idx, const double* __restrict__ sign,
-                                 const double* __restrict__ normals, size_t Np, int gala_modified,
+                                 const double* __restrict__ normals, int ncols, size_t Np, int kind, int gala_modified,
                                  double* __restrict__ out) {
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= Np) return;
@@ -66,11 +70,28 @@ __global__ void k_fardal_release(const __grid_constant__ DevPot P, double G, con
     // FardalStreamDF._sample body (df.pyx:405-454)
     const double sg = sign[p];
     const double srj = (sg < 0) ? -rj : rj, svj = (sg < 0) ? -vj : vj;
-    const double* nr = normals + p * 4;
-    const double kx = nr[0];
-    double tx[3] = {kx * srj, 0., nr[1] * srj};
-    double tv[3] = {0., nr[2] * svj, nr[3] * svj};
-    if (gala_modified) tv[1] *= kx;
+    const double* nr = normals + p * (size_t)ncols;
+    double tx[3] = {0., 0., 0.}, tv[3] = {0., 0., 0.};
+    if (kind == 0) {
+        const double kx = nr[0];
+        tx[0] = kx * srj; tx[2] = nr[1] * srj;
+        tv[1] = nr[2] * svj; tv[2] = nr[3] * svj;
+        if (gala_modified) tv[1] *= kx;
+    } else if (kind == 1) {
+        tx[0] = srj; tv[1] = svj;
+    } else if (kind == 2) {
+        tx[0] = srj;
+        tv[0] = nr[0]; tv[1] = nr[1]; tv[2] = nr[2];
+    } else {
+        // ChenStreamDF (df.pyx:631-697): leading particles are rotated by pi in phi and alpha
+        const double Dr = nr[0] * rj;
+        const double Dv = nr[3] * sqrt(2 * G * m / Dr);
+        double a1 = nr[1] * (GB_PI / 180), a4 = nr[4] * (GB_PI / 180);
+        if (sg < 0) { a1 = a1 + GB_PI; a4 = a4 + GB_PI; }
+        const double a2 = nr[2] * (GB_PI / 180), a5 = nr[5] * (GB_PI / 180);
+        tx[0] = Dr * cos(a2) * cos(a1); tx[1] = Dr * cos(a2) * sin(a1); tx[2] = Dr * sin(a2);
+        tv[0] = Dv * cos(a5) * cos(a4); tv[1] = Dv * cos(a5) * sin(a4); tv[2] = Dv * sin(a5);
+    }
     // transform_from_sat (df.pyx:94-106): R^T . x + prog
     double* o = out + p * 6;
 #pragma unroll

@@ -23,27 +23,33 @@ from .integrate import (DOPRI853Integrator, LeapfrogIntegrator, dop853_integrate
                         leapfrog_integrate_hamiltonian, parse_time_specification)
 from .units import strip
 
-__all__ = ["FardalStreamDF", "MockStreamGenerator", "DirectNBody", "mockstream_dop853", "mockstream_leapfrog"]
+__all__ = ["BaseStreamDF", "FardalStreamDF", "StreaklineStreamDF", "LagrangeCloudStreamDF", "ChenStreamDF",
+           "MockStreamGenerator", "DirectNBody", "mockstream_dop853", "mockstream_leapfrog"]
 
 
 def _opts(H):
     return _abi.launch_opts(False, bool(getattr(H, "strict_math", False) or H.potential.strict_math))
 
 
-class FardalStreamDF:
-    """Fardal, Huang & Weinberg (2015) particle-release distribution function
-    (``df.pyx:320-456``).  ``random_state`` may be a ``numpy.random.RandomState`` or ``Generator``;
-    only ``.normal(loc, scale)`` is used."""
+class BaseStreamDF:
+    """``BaseStreamDF`` (``df.pyx:28-238``): bookkeeping shared by the stream distribution functions.  A
+    subclass provides ``_kind`` (the device DF id), and ``_draws(Np)`` = the random deviates of all
+    particles drawn with the caller's numpy RNG in exactly the reference's order (per timestep all
+    trailing particles, then all leading ones; per particle the DF's own draw order)."""
+    _kind = None
+    _flags = 0
 
-    def __init__(self, gala_modified=True, lead=True, trail=True, random_state=None):
+    def __init__(self, lead=True, trail=True, random_state=None):
         self._lead, self._trail = int(bool(lead)), int(bool(trail))
         if not self._lead and not self._trail:
             raise ValueError("You must generate either leading or trailing tails (or both!)")
         self.random_state = np.random.RandomState() if random_state is None else random_state
-        self._gala_modified = int(bool(gala_modified))
 
     lead = property(lambda self: self._lead)
     trail = property(lambda self: self._trail)
+
+    def _draws(self, Np, potential):
+        return None
 
     def _plan(self, prog_m, nparticles):
         """Particle bookkeeping in the reference's emission order: per timestep (skipping
@@ -64,22 +70,17 @@ class FardalStreamDF:
         """(ntimes,3) progenitor positions / velocities -> particle_x (Np,3), particle_v, particle_t1."""
         prog_idx, sign = self._plan(prog_m, nparticles)
         Np = prog_idx.size
-        # k_mean / k_disp of df.pyx:378-391; draws per particle in the order kx, z, vt, vz
-        kvt_fardal = 0.4
-        loc = np.array([2.0, 0.0, 0.3, 0.0])
-        scale = np.array([0.5 if self._gala_modified else 0.4, 0.5,
-                          0.5 if self._gala_modified else kvt_fardal, 0.5])
-        normals = np.ascontiguousarray(
-            self.random_state.normal(np.broadcast_to(loc, (Np, 4)), np.broadcast_to(scale, (Np, 4))), dtype=np.float64)
+        draws = self._draws(Np, potential)
+        ncols = 0 if draws is None else draws.shape[1]
         prog_w = np.ascontiguousarray(np.hstack([prog_x, prog_v]), dtype=np.float64)
         prog_t = np.ascontiguousarray(prog_t, dtype=np.float64)
         prog_m = np.ascontiguousarray(prog_m, dtype=np.float64)
         out = np.empty((Np, 6))
         opt = _abi.launch_opts(False, bool(potential.strict_math))
-        _abi.check(_abi.lib().gb_fardal_release(
+        _abi.check(_abi.lib().gb_stream_release(
             potential.spec().ptr(), float(potential.G), prog_w.ctypes.data, prog_t.ctypes.data, prog_m.ctypes.data,
-            len(prog_t), prog_idx.ctypes.data, sign.ctypes.data, normals.ctypes.data, Np, self._gala_modified,
-            out.ctypes.data, C.byref(opt)))
+            len(prog_t), prog_idx.ctypes.data, sign.ctypes.data, None if draws is None else draws.ctypes.data, ncols,
+            Np, int(self._kind), int(self._flags), out.ctypes.data, C.byref(opt)))
         return out[:, :3].copy(), out[:, 3:].copy(), prog_t[prog_idx]
 
     def sample(self, prog_orbit, prog_mass, hamiltonian=None, release_every=1, n_particles=1):
@@ -109,6 +110,65 @@ class FardalStreamDF:
         _, sign = self._plan(prog_m, n_particles)
         lt = np.where(sign > 0, "t", "l").astype("U1")
         return MockStream(pos=x.T, vel=v.T, release_time=t1, lead_trail=lt, frame=H.frame)
+
+
+class FardalStreamDF(BaseStreamDF):
+    """Fardal, Huang & Weinberg (2015) particle-release distribution function
+    (``df.pyx:320-456``).  ``random_state`` may be a ``numpy.random.RandomState`` or ``Generator``;
+    only ``.normal(loc, scale)`` is used: four draws per particle in the order kx, z, vt, vz."""
+    _kind = 0
+
+    def __init__(self, gala_modified=True, lead=True, trail=True, random_state=None):
+        super().__init__(lead=lead, trail=trail, random_state=random_state)
+        self._gala_modified = int(bool(gala_modified))
+        self._flags = self._gala_modified
+
+    def _draws(self, Np, potential):
+        # k_mean / k_disp of df.pyx:378-391; one broadcast call consumes the bit stream in the scalar order
+        kvt_fardal = 0.4
+        loc = np.array([2.0, 0.0, 0.3, 0.0])
+        scale = np.array([0.5 if self._gala_modified else 0.4, 0.5,
+                          0.5 if self._gala_modified else kvt_fardal, 0.5])
+        return np.ascontiguousarray(
+            self.random_state.normal(np.broadcast_to(loc, (Np, 4)), np.broadcast_to(scale, (Np, 4))), dtype=np.float64)
+
+
+class StreaklineStreamDF(BaseStreamDF):
+    """Kuepper et al. (2012) "streakline" DF (``df.pyx:242-318``): particles leave exactly at the Lagrange
+    radius with the progenitor's angular velocity; no random numbers."""
+    _kind = 1
+
+
+class LagrangeCloudStreamDF(BaseStreamDF):
+    """Gibbons et al. (2014) Lagrange-cloud stripping (``df.pyx:460-552``): released at the Lagrange radius
+    with an isotropic Gaussian velocity offset of dispersion ``v_disp`` (kpc/Myr here; the reference converts
+    an astropy speed to the potential's units); three ``normal(0, v_disp)`` draws per particle."""
+    _kind = 2
+
+    def __init__(self, v_disp, lead=True, trail=True, random_state=None):
+        super().__init__(lead=lead, trail=trail, random_state=random_state)
+        self.v_disp = float(strip(v_disp))
+
+    def _draws(self, Np, potential):
+        return np.ascontiguousarray(self.random_state.normal(np.zeros((Np, 3)), np.full((Np, 3), self.v_disp)),
+                                    dtype=np.float64)
+
+
+class ChenStreamDF(BaseStreamDF):
+    """Chen et al. (2024) DF (``df.pyx:556-702``): per particle one ``multivariate_normal(mean, cov)`` draw of
+    (r, phi, theta, v, alpha, beta).  The reference calls it once per particle (one SVD of ``cov`` per call);
+    a single ``size=Np`` call consumes the same standard normals in the same order and applies the same
+    factorisation, so the rows agree with the per-particle loop to 1 ulp (matrix-matrix instead of
+    matrix-vector product inside numpy; ``tests/test_host_logic_cpu.py``)."""
+    _kind = 3
+    mean = np.array([1.6, -30.0, 0.0, 1.0, 20.0, 0.0])
+    cov = np.diag([0.1225, 529.0, 144.0, 0.0, 400.0, 484.0])
+    cov[0, 4] = cov[4, 0] = -4.9
+
+    def _draws(self, Np, potential):
+        if Np == 0:
+            return np.zeros((0, 6))
+        return np.ascontiguousarray(self.random_state.multivariate_normal(self.mean, self.cov, size=Np), dtype=np.float64)
 
 
 def _same_potential(a, b):

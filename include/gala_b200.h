@@ -174,6 +174,17 @@ int gb_fardal_release(const gb_potential* pot, double G,
                       size_t Np, int gala_modified,
                       double* stream_w0 /* (Np,6) */, const gb_launch* opt);
 
+/* The same release step for every builtin stream DF (dynamics/mockstream/df.pyx): df_kind 0 = Fardal
+ * (draws (Np,4), flags = gala_modified), 1 = Streakline (:242-318, no draws), 2 = LagrangeCloud
+ * (:460-552, draws (Np,3) = N(0, v_disp) velocity offsets), 3 = Chen+24 (:556-702, draws (Np,6) =
+ * multivariate_normal(mean, cov) rows [r, phi, theta, v, alpha, beta], angles in degrees). */
+int gb_stream_release(const gb_potential* pot, double G,
+                      const double* prog_w /* (ntimes,6) */, const double* prog_t,
+                      const double* prog_m, int ntimes,
+                      const int32_t* prog_idx, const double* sign, const double* draws, int ncols,
+                      size_t Np, int df_kind, int flags,
+                      double* stream_w0 /* (Np,6) */, const gb_launch* opt);
+
 /* mockstream_dop853 (dynamics/mockstream/mockstream.pyx:176-303), no massive
  * bodies: every stream particle p is integrated from t1[p] to tfinal as its own
  * n=6 DOP853 system with dop853_step's settings (dop853.pyx:27-75: uround default,

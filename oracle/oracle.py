@@ -195,51 +195,95 @@ def have_ref(flavor="strict"):
 
 
 # ---- pure-numpy restatements of the Python-level pieces of the path (no C needed) -------------------
-def fardal_release_numpy(ref, pot, prog_x, prog_v, prog_t, prog_m, nparticles, random_state, gala_modified=True,
-                         lead=True, trail=True):
-    """FardalStreamDF._sample + get_rj_vj_R + transform_from_sat restated in numpy scalars
-    (dynamics/mockstream/df.pyx:61-106, 363-456), drawing the RNG exactly like the reference: four
-    scalar ``random_state.normal`` calls per particle.  ``ref`` supplies c_d2_dr2 from the compiled
-    reference (cpotential.cpp:346-371)."""
+def _sat_frame(ref, pot, px, pv, m, t):
+    """get_rj_vj_R (df.pyx:61-92) in numpy scalars; c_d2_dr2 from the compiled reference."""
+    G = pot.G
+    dist = np.sqrt(px[0] ** 2 + px[1] ** 2 + px[2] ** 2)
+    L = np.array([px[1] * pv[2] - px[2] * pv[1], -px[0] * pv[2] + px[2] * pv[0], px[0] * pv[1] - px[1] * pv[0]])
+    Lnorm = np.sqrt(L[0] ** 2 + L[1] ** 2 + L[2] ** 2)
+    R = np.zeros((3, 3))
+    R[0] = px / dist
+    R[2] = L / Lnorm
+    Om = Lnorm / dist ** 2
+    d2r = ref.d2_dr2(pot, px, t)
+    rj = (G * m / (Om * Om - d2r)) ** (1 / 3.)
+    vj = Om * rj
+    a, b = R[0], R[2]
+    R[1] = -np.array([a[1] * b[2] - a[2] * b[1], -a[0] * b[2] + a[2] * b[0], a[0] * b[1] - a[1] * b[0]])
+    return rj, vj, R
+
+
+def stream_release_numpy(ref, pot, kind, prog_x, prog_v, prog_t, prog_m, nparticles, random_state, gala_modified=True,
+                         lead=True, trail=True, v_disp=0.0):
+    """``*StreamDF._sample`` + get_rj_vj_R + transform_from_sat restated in numpy scalars
+    (dynamics/mockstream/df.pyx:61-106 and :242-318 streakline, :363-456 fardal, :460-552 lagrange,
+    :556-702 chen), drawing the RNG exactly like the reference (scalar ``normal`` calls, or one
+    ``multivariate_normal(mean, cov)`` call per particle).  ``ref`` supplies c_d2_dr2
+    (cpotential.cpp:346-371)."""
     G = pot.G
     k_mean = np.zeros(6); k_disp = np.zeros(6)
     k_mean[0] = 2.; k_disp[0] = 0.5 if gala_modified else 0.4
     k_mean[2] = 0.; k_disp[2] = 0.5
     k_mean[4] = 0.3; k_disp[4] = 0.5 if gala_modified else 0.4
     k_mean[5] = 0.; k_disp[5] = 0.5
+    mean = np.array([1.6, -30., 0., 1., 20., 0.])
+    cov = np.zeros((6, 6))
+    cov[0, 0] = 0.1225; cov[1, 1] = 529.; cov[2, 2] = 144.; cov[3, 3] = 0.; cov[4, 4] = 400.; cov[5, 5] = 484.
+    cov[0, 4] = -4.9; cov[4, 0] = -4.9
     X, V, T1 = [], [], []
     for i in range(len(prog_t)):
         if prog_m[i] == 0:
             continue
         px, pv = prog_x[i], prog_v[i]
-        dist = np.sqrt(px[0] ** 2 + px[1] ** 2 + px[2] ** 2)
-        L = np.array([px[1] * pv[2] - px[2] * pv[1], -px[0] * pv[2] + px[2] * pv[0], px[0] * pv[1] - px[1] * pv[0]])
-        Lnorm = np.sqrt(L[0] ** 2 + L[1] ** 2 + L[2] ** 2)
-        R = np.zeros((3, 3))
-        R[0] = px / dist
-        R[2] = L / Lnorm
-        Om = Lnorm / dist ** 2
-        d2r = ref.d2_dr2(pot, px, prog_t[i])
-        rj = (G * prog_m[i] / (Om * Om - d2r)) ** (1 / 3.)
-        vj = Om * rj
-        a, b = R[0], R[2]
-        R[1] = -np.array([a[1] * b[2] - a[2] * b[1], -a[0] * b[2] + a[2] * b[0], a[0] * b[1] - a[1] * b[0]])
+        rj, vj, R = _sat_frame(ref, pot, px, pv, prog_m[i], prog_t[i])
         for sgn, on in ((1.0, trail), (-1.0, lead)):
             if not on:
                 continue
             for _ in range(int(nparticles[i])):
                 tmp_x = np.zeros(3); tmp_v = np.zeros(3)
-                kx = random_state.normal(k_mean[0], k_disp[0])
-                tmp_x[0] = kx * (sgn * rj)
-                tmp_x[2] = random_state.normal(k_mean[2], k_disp[2]) * (sgn * rj)
-                tmp_v[1] = random_state.normal(k_mean[4], k_disp[4]) * (sgn * vj)
-                if gala_modified:
-                    tmp_v[1] *= kx
-                tmp_v[2] = random_state.normal(k_mean[5], k_disp[5]) * (sgn * vj)
+                if kind == "fardal":
+                    kx = random_state.normal(k_mean[0], k_disp[0])
+                    tmp_x[0] = kx * (sgn * rj)
+                    tmp_x[2] = random_state.normal(k_mean[2], k_disp[2]) * (sgn * rj)
+                    tmp_v[1] = random_state.normal(k_mean[4], k_disp[4]) * (sgn * vj)
+                    if gala_modified:
+                        tmp_v[1] *= kx
+                    tmp_v[2] = random_state.normal(k_mean[5], k_disp[5]) * (sgn * vj)
+                elif kind == "streakline":
+                    tmp_x[0] = sgn * rj
+                    tmp_v[1] = sgn * vj
+                elif kind == "lagrange":
+                    tmp_x[0] = sgn * rj
+                    tmp_v[0] = random_state.normal(0, v_disp)
+                    tmp_v[1] = random_state.normal(0, v_disp)
+                    tmp_v[2] = random_state.normal(0, v_disp)
+                elif kind == "chen":
+                    pvl = np.array(random_state.multivariate_normal(mean, cov))
+                    Dr = pvl[0] * rj
+                    Dv = pvl[3] * np.sqrt(2 * G * prog_m[i] / Dr)
+                    off = np.pi if sgn < 0 else 0.0
+                    pvl[1] = pvl[1] * (np.pi / 180) + off if sgn < 0 else pvl[1] * (np.pi / 180)
+                    pvl[2] = pvl[2] * (np.pi / 180)
+                    pvl[4] = pvl[4] * (np.pi / 180) + off if sgn < 0 else pvl[4] * (np.pi / 180)
+                    pvl[5] = pvl[5] * (np.pi / 180)
+                    tmp_x[0] = Dr * np.cos(pvl[2]) * np.cos(pvl[1])
+                    tmp_x[1] = Dr * np.cos(pvl[2]) * np.sin(pvl[1])
+                    tmp_x[2] = Dr * np.sin(pvl[2])
+                    tmp_v[0] = Dv * np.cos(pvl[5]) * np.cos(pvl[4])
+                    tmp_v[1] = Dv * np.cos(pvl[5]) * np.sin(pvl[4])
+                    tmp_v[2] = Dv * np.sin(pvl[5])
+                else:
+                    raise ValueError(kind)
                 ox = np.array([R[0, k] * tmp_x[0] + R[1, k] * tmp_x[1] + R[2, k] * tmp_x[2] for k in range(3)]) + px
                 ov = np.array([R[0, k] * tmp_v[0] + R[1, k] * tmp_v[1] + R[2, k] * tmp_v[2] for k in range(3)]) + pv
                 X.append(ox); V.append(ov); T1.append(prog_t[i])
     return np.array(X).reshape(-1, 3), np.array(V).reshape(-1, 3), np.array(T1)
+
+
+def fardal_release_numpy(ref, pot, prog_x, prog_v, prog_t, prog_m, nparticles, random_state, gala_modified=True,
+                         lead=True, trail=True):
+    return stream_release_numpy(ref, pot, "fardal", prog_x, prog_v, prog_t, prog_m, nparticles, random_state,
+                                gala_modified=gala_modified, lead=lead, trail=trail)
 
 
 class Port(_Lib):

@@ -44,6 +44,36 @@ def test_fardal_release_parity(ref, rng_kind, gala_modified):
     assert list(s.lead_trail[:6]) == ["t", "t", "t", "l", "l", "l"]
 
 
+@pytest.mark.parametrize("kind", ["streakline", "lagrange", "chen"])
+def test_other_stream_dfs_release_parity(ref, kind):
+    """StreaklineStreamDF / LagrangeCloudStreamDF / ChenStreamDF (df.pyx:242-318, 460-552, 556-702) against the
+    numpy-scalar restatement drawing the RNG call by call like the reference."""
+    from oracle import oracle
+    pot = gb.MilkyWayPotential2022()
+    H = gb.Hamiltonian(pot)
+    orb, t = _prog_orbit(H, 48)
+    prog = gb.Orbit(pos=orb.pos[:, ::-1, 0], vel=orb.vel[:, ::-1, 0], t=t[::-1], hamiltonian=H)
+    npart = np.zeros(49, dtype="i4"); npart[::3] = 4
+    prog_m = np.full(49, 2.5e4)
+    for mk in (lambda: np.random.RandomState(5), lambda: np.random.default_rng(5)):
+        df = {"streakline": lambda: gb.StreaklineStreamDF(random_state=mk()),
+              "lagrange": lambda: gb.LagrangeCloudStreamDF(v_disp=1.2e-3, random_state=mk()),
+              "chen": lambda: gb.ChenStreamDF(random_state=mk())}[kind]()
+        pot.strict_math = True
+        s = df.sample(prog, prog_m, n_particles=npart)
+        x0, v0, t10 = oracle.stream_release_numpy(ref, pot, kind, prog.pos.T, prog.vel.T, prog.t, prog_m, npart, mk(),
+                                                  v_disp=1.2e-3)
+        pot.strict_math = False
+        assert s.pos.shape == (3, x0.shape[0]) and np.array_equal(s.release_time, t10)
+        off = np.sqrt(((x0 - prog.pos.T[np.searchsorted(prog.t, t10)]) ** 2).sum(1))
+        assert np.max(np.abs(s.pos.T - x0) / off[:, None]) < 1e-11
+        assert np.max(np.abs(s.vel.T - v0)) / np.abs(v0).max() < 1e-13
+    # a whole stream through the generator with each DF
+    gen = gb.MockStreamGenerator(df, H)
+    stream, _ = gen.run(PROG_W0, 2.5e4, dt=-1.0, n_steps=60, n_particles=2, Integrator="leapfrog")
+    assert stream.pos.shape == (3, 2 * 2 * 61) and np.all(np.isfinite(stream.pos))
+
+
 def test_mockstream_dop853_parity(ref):
     pot = gb.MilkyWayPotential2022()
     H = gb.Hamiltonian(pot)

@@ -127,6 +127,25 @@ def test_rng_broadcast_draw_equals_scalar_draws():
         assert np.array_equal(a, b)
 
 
+def test_chen_batched_draw_matches_per_particle_calls():
+    """ChenStreamDF: one multivariate_normal(mean, cov, size=Np) consumes the RNG like the reference's
+    per-particle calls (df.pyx:632, 663) and agrees with them to 1 ulp; LagrangeCloud: one broadcast
+    normal(0, v_disp) call == three scalar draws per particle (df.pyx:520-522)."""
+    for mk in (lambda: np.random.RandomState(7), lambda: np.random.default_rng(7)):
+        df = gb.ChenStreamDF(random_state=mk())
+        a = df._draws(500, None)
+        r = mk()
+        b = np.array([r.multivariate_normal(gb.ChenStreamDF.mean, gb.ChenStreamDF.cov) for _ in range(500)])
+        assert np.max(np.abs(a - b)) < 1e-14
+        assert np.all(a[:, 3] == 1.0)                      # cov[3,3] = 0: v is exactly the mean
+        df = gb.LagrangeCloudStreamDF(v_disp=0.002, random_state=mk())
+        a = df._draws(100, None)
+        r = mk()
+        b = np.array([[r.normal(0, 0.002) for _ in range(3)] for _ in range(100)])
+        assert np.array_equal(a, b)
+    assert gb.StreaklineStreamDF()._draws(10, None) is None
+
+
 def test_shard_bounds_and_work_dealing():
     b = shard_bounds(10, 4)
     assert b == [(0, 3), (3, 6), (6, 8), (8, 10)]
