@@ -906,10 +906,13 @@ struct DevTmp {                      // stream-ordered device temporary with opt
 
 int gb_nbody_leapfrog(const gb_potential* pot, const gb_bodies* bodies, const double* body_w0, int ngroups,
                       const int32_t* group, const double* w0_rows, const double* t1, size_t Np, double t0,
-                      double tfinal, int nsteps, double dt, double* out_particles, double* out_bodies,
+                      double tfinal, int nsteps, double dt, int scheme, double* out_particles, double* out_bodies,
                       size_t body_writer, double* traj, const gb_launch* opt) {
     Ctx c; RET_IF(open_ctx(opt, c));
     if (!c.host) return fail(-12, "gb_nbody_leapfrog takes host buffers");
+    if (scheme != 0 && scheme != 1) return fail(-12, "scheme must be 0 (leapfrog) or 1 (ruth4)");
+    double cs[4], ds[4];
+    ruth4_coeffs(cs, ds);
     if (!body_w0 || ngroups < 1 || (Np && !w0_rows)) return fail(-12, "null data pointer");
     if (dt == 0.0) return fail(-12, "dt must be non-zero");
     RET_IF(pool_keep());
@@ -926,7 +929,7 @@ int gb_nbody_leapfrog(const gb_potential* pot, const gb_bodies* bodies, const do
     if (out_bodies) CU(dob.put(nullptr, nb * 6 * sizeof(double), c.stream));
     const size_t tb = traj ? (size_t)(nsteps + 1) * ntot * 6 * sizeof(double) : 0;
     if (traj) { if (t1) return fail(-12, "trajectories need a common start time"); CU(dtr.put(nullptr, tb, c.stream)); }
-    cudaError_t e = KCALL(c, nbody_leapfrog, r.P, B, (const double*)dbw.p, (const int32_t*)dgrp.p, (const double*)dw0.p,
+    cudaError_t e = KCALL(c, nbody_leapfrog, r.P, B, scheme, cs, ds, (const double*)dbw.p, (const int32_t*)dgrp.p, (const double*)dw0.p,
                           (const double*)dt1.p, Np, t0, tfinal, nsteps, dt, (double*)dop.p, (double*)dob.p, body_writer,
                           (double*)dtr.p, ntot, c.block, c.stream);
     if (e != cudaSuccess) return cuda_fail(e, "nbody_leapfrog launch");

@@ -370,15 +370,18 @@ cudaError_t fardal_release(const DevPot& P, double G, const double* prog_w, cons
         default:             { using C = Composite<SIG_GENERIC>;    CALL; } break; \
     }
 #if GB_PART == 5
-cudaError_t nbody_leapfrog(const DevPot& P, const DevBodies& B, const double* body_w0, const int32_t* group,
+cudaError_t nbody_leapfrog(const DevPot& P, const DevBodies& B, int scheme, const double* cs, const double* ds,
+                           const double* body_w0, const int32_t* group,
                            const double* w0, const double* t1, size_t Np, double t0, double tfinal, int nsteps_fixed,
                            double dt, double* out_p, double* out_b, size_t body_writer, double* traj, size_t ntot,
                            int block, cudaStream_t s) {
     const int hasp = Np > 0;
     const size_t nthreads = hasp ? Np : 1;
     if (block > 128 || block <= 0) block = 128;
+    Ruth4Coef rc;
+    for (int k = 0; k < 4; k++) { rc.cs[k] = cs ? cs[k] : 0.; rc.ds[k] = ds ? ds[k] : 0.; }
     GB_SIG_SWITCH2(P.sig, (k_nbody_leapfrog<C><<<nblocks(nthreads, block), block, 0, s>>>(
-        P, B, body_w0, group, w0, t1, Np, hasp, t0, tfinal, nsteps_fixed, dt, out_p, out_b, body_writer, traj, ntot)));
+        P, B, rc, scheme, body_w0, group, w0, t1, Np, hasp, t0, tfinal, nsteps_fixed, dt, out_p, out_b, body_writer, traj, ntot)));
     return cudaGetLastError();
 }
 #endif

@@ -59,7 +59,8 @@ struct Dop853Args {
                             int32_t* status, int block, cudaStream_t s);                                   \
     cudaError_t mock_leapfrog(const DevPot& P, const double* w0_rows, const double* t1, size_t Np,        \
                               double tfinal, double dt, double* out_rows, int block, cudaStream_t s);      \
-    cudaError_t nbody_leapfrog(const DevPot& P, const DevBodies& B, const double* body_w0, const int32_t* group, \
+    cudaError_t nbody_leapfrog(const DevPot& P, const DevBodies& B, int scheme, const double* cs,          \
+                               const double* ds, const double* body_w0, const int32_t* group,              \
                                const double* w0, const double* t1, size_t Np, double t0, double tfinal,   \
                                int nsteps_fixed, double dt, double* out_p, double* out_b,                  \
                                size_t body_writer, double* traj, size_t ntot, int block, cudaStream_t s);  \

@@ -52,9 +52,14 @@ GB_DEV void gb_nbody_grad_symplectic(const DevPot& P, const DevBodies& B, double
 // state body_w0[group[p]] and takes nsteps = int((tfinal - t1)/dt + 0.5) steps (mockstream.pyx:571) or
 // `nsteps_fixed` (leapfrog_integrate_nbody).  traj != null: every step is stored as rows of
 // (ntimes, ntot, 6) (leapfrog.pyx:249-252), the bodies by lane `body_writer`.
+struct Ruth4Coef { double cs[4], ds[4]; };   // ruth4.pyx:166-178, computed on the host
+
+// scheme 0: leapfrog (above).  scheme 1: Ruth4 (c_ruth4_step_nbody, ruth4.pyx:116-136): no half-step
+// velocity; every point takes its four sub-stages in one go while the others stay where they are.
 template <class C>
 __global__ void __launch_bounds__(128)
 k_nbody_leapfrog(const __grid_constant__ DevPot P, const __grid_constant__ DevBodies B,
+                 const __grid_constant__ Ruth4Coef rc, int scheme,
                  const double* __restrict__ body_w0, const int32_t* __restrict__ group,
                  const double* __restrict__ w0, const double* __restrict__ t1, size_t Np, int has_particle,
                  double t0, double tfinal, int nsteps_fixed, double dt,
@@ -77,11 +82,11 @@ k_nbody_leapfrog(const __grid_constant__ DevPot P, const __grid_constant__ DevBo
     const bool wb = (p == body_writer);
     double gx, gy, gz;
     // c_init_velocity_nbody for the bodies in order, then the particle (mockstream.pyx:556-566)
-    for (int b = 0; b < nb; b++) {
+    if (scheme == 0) for (int b = 0; b < nb; b++) {
         gb_nbody_grad_symplectic<C>(P, B, ts, bq, b, bq[b][0], bq[b][1], bq[b][2], gx, gy, gz);
         bh[b][0] = bv[b][0] - gx * dt / 2.; bh[b][1] = bv[b][1] - gy * dt / 2.; bh[b][2] = bv[b][2] - gz * dt / 2.;
     }
-    if (has_particle) {
+    if (scheme == 0 && has_particle) {
         gb_nbody_grad_symplectic<C>(P, B, ts, bq, nb, x, y, z, gx, gy, gz);
         hx = vx - gx * dt / 2.; hy = vy - gy * dt / 2.; hz = vz - gz * dt / 2.;
     }
@@ -94,14 +99,28 @@ k_nbody_leapfrog(const __grid_constant__ DevPot P, const __grid_constant__ DevBo
     }
     for (int j = 0; j < n_steps; j++) {
         const double tj = ts + (j + 1) * dt;
+        if (scheme == 1) {
+            for (int b = 0; b < nb; b++)
+                for (int q = 0; q < 4; q++) {
+                    gb_nbody_grad_symplectic<C>(P, B, tj, bq, b, bq[b][0], bq[b][1], bq[b][2], gx, gy, gz);
+                    bv[b][0] = bv[b][0] - rc.ds[q] * gx * dt; bv[b][1] = bv[b][1] - rc.ds[q] * gy * dt; bv[b][2] = bv[b][2] - rc.ds[q] * gz * dt;
+                    bq[b][0] = bq[b][0] + rc.cs[q] * bv[b][0] * dt; bq[b][1] = bq[b][1] + rc.cs[q] * bv[b][1] * dt; bq[b][2] = bq[b][2] + rc.cs[q] * bv[b][2] * dt;
+                }
+            if (has_particle)
+                for (int q = 0; q < 4; q++) {
+                    gb_nbody_grad_symplectic<C>(P, B, tj, bq, nb, x, y, z, gx, gy, gz);
+                    vx = vx - rc.ds[q] * gx * dt; vy = vy - rc.ds[q] * gy * dt; vz = vz - rc.ds[q] * gz * dt;
+                    x = x + rc.cs[q] * vx * dt; y = y + rc.cs[q] * vy * dt; z = z + rc.cs[q] * vz * dt;
+                }
+        }
         // bodies one after the other, each seeing the others where they are NOW (in-place update)
-        for (int b = 0; b < nb; b++) {
+        if (scheme == 0) for (int b = 0; b < nb; b++) {
             bq[b][0] = bq[b][0] + bh[b][0] * dt; bq[b][1] = bq[b][1] + bh[b][1] * dt; bq[b][2] = bq[b][2] + bh[b][2] * dt;
             gb_nbody_grad_symplectic<C>(P, B, tj, bq, b, bq[b][0], bq[b][1], bq[b][2], gx, gy, gz);
             bv[b][0] = bh[b][0] - gx * dt / 2.; bv[b][1] = bh[b][1] - gy * dt / 2.; bv[b][2] = bh[b][2] - gz * dt / 2.;
             bh[b][0] = bh[b][0] - gx * dt; bh[b][1] = bh[b][1] - gy * dt; bh[b][2] = bh[b][2] - gz * dt;
         }
-        if (has_particle) {
+        if (scheme == 0 && has_particle) {
             x = x + hx * dt; y = y + hy * dt; z = z + hz * dt;
             gb_nbody_grad_symplectic<C>(P, B, tj, bq, nb, x, y, z, gx, gy, gz);
             vx = hx - gx * dt / 2.; vy = hy - gy * dt / 2.; vz = hz - gz * dt / 2.;

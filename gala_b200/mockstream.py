@@ -211,7 +211,7 @@ class _BodySpec:
 
 
 def _nbody_leapfrog(H, pps, body_w0, t0, tfinal, nsteps, dt, w0_rows=None, t1=None, group=None, body_writer=0,
-                    save_all=False, n_sources=None):
+                    save_all=False, n_sources=None, scheme=0):
     """One ``gb_nbody_leapfrog`` call.  Returns (particles (Np,6) | None, bodies (nb,6), traj | None)."""
     bs = _BodySpec(pps, n_sources)
     body_w0 = np.ascontiguousarray(body_w0, dtype=np.float64).reshape(-1, len(pps), 6)
@@ -226,7 +226,7 @@ def _nbody_leapfrog(H, pps, body_w0, t0, tfinal, nsteps, dt, w0_rows=None, t1=No
     ptr = lambda a: None if a is None else a.ctypes.data
     _abi.check(_abi.lib().gb_nbody_leapfrog(H.potential.spec().ptr(), bs.ptr(), body_w0.ctypes.data, body_w0.shape[0],
                                             ptr(grp), ptr(rows), ptr(t1a), Np, float(t0), float(tfinal), int(nsteps),
-                                            float(dt), ptr(out_p), out_b.ctypes.data, int(body_writer), ptr(traj),
+                                            float(dt), int(scheme), ptr(out_p), out_b.ctypes.data, int(body_writer), ptr(traj),
                                             C.byref(opt)))
     return out_p, out_b, traj
 
@@ -294,13 +294,17 @@ class DirectNBody:
         Integrator = get_integrator(Integrator or DOPRI853Integrator)
         kw = dict(Integrator_kwargs or {})
         t = parse_time_specification(self.units, **time_spec)
-        if Integrator not in (LeapfrogIntegrator, DOPRI853Integrator):
-            raise NotImplementedError(f"N-body integration is not supported with {Integrator} on the B200 engine")
+        from .integrate import Ruth4Integrator, ruth4_integrate_hamiltonian
+        if Integrator not in (LeapfrogIntegrator, DOPRI853Integrator, Ruth4Integrator):
+            raise NotImplementedError(f"N-body integration is currently not supported with the {Integrator} "
+                                      "integrator class")
         kw = {k: kw[k] for k in ("atol", "rtol", "nmax", "dt_max", "err_if_fail") if k in kw}
         if self.n_massive == 0:
             w0 = np.ascontiguousarray(self._c_w0.T)
             if Integrator is LeapfrogIntegrator:
                 _, w = leapfrog_integrate_hamiltonian(self.H, w0, t, save_all=int(self.save_all))
+            elif Integrator is Ruth4Integrator:
+                _, w = ruth4_integrate_hamiltonian(self.H, w0, t, save_all=int(self.save_all))
             else:
                 _, w = dop853_integrate_hamiltonian(self.H, w0, t, nstiff=-1, save_all=int(self.save_all), **kw)
         else:
@@ -313,9 +317,9 @@ class DirectNBody:
             body_w0 = self._c_w0[front]
             rows = self._c_w0[end] if end else None
             dt = t[1] - t[0]
-            if Integrator is LeapfrogIntegrator:
+            if Integrator in (LeapfrogIntegrator, Ruth4Integrator):
                 out_p, out_b, traj = _nbody_leapfrog(self.H, pps, body_w0, t[0], t[-1], len(t) - 1, dt, w0_rows=rows,
-                                                     save_all=self.save_all)
+                                                     save_all=self.save_all, scheme=int(Integrator is Ruth4Integrator))
             else:
                 out_p, out_b, traj, _ = _nbody_dop853(self.H, pps, body_w0, t, t[-1], dt, 0, w0_rows=rows,
                                                       save_all=self.save_all, **kw)

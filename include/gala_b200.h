@@ -224,11 +224,12 @@ typedef struct {
 } gb_bodies;
 
 /* fixed step: particle p takes int((tfinal - t1[p])/dt + 0.5) steps (mockstream.pyx:571), or `nsteps`
- * when t1 == NULL.  StaticFrame only, like the reference (leapfrog.pyx:172-176). */
+ * when t1 == NULL.  scheme 0 = leapfrog; 1 = Ruth4 (ruth4_integrate_nbody,
+ * integrate/cyintegrators/ruth4.pyx:116-241).  StaticFrame only, like the reference (leapfrog.pyx:172-176). */
 int gb_nbody_leapfrog(const gb_potential* pot, const gb_bodies* bodies,
                       const double* body_w0, int ngroups, const int32_t* group,
                       const double* w0_rows, const double* t1, size_t Np,
-                      double t0, double tfinal, int nsteps, double dt,
+                      double t0, double tfinal, int nsteps, double dt, int scheme,
                       double* out_particles, double* out_bodies, size_t body_writer,
                       double* traj, const gb_launch* opt);
 

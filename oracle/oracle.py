@@ -145,13 +145,16 @@ class _Lib:
             arr[b] = keep[b + 1].pot
         return keep, arr
 
-    def nbody_leapfrog(self, H, pps, w_rows, t0, nsteps, dt, nsrc=None, save_all=False):
+    def nbody_ruth4(self, H, pps, w_rows, t0, nsteps, dt, nsrc=None, save_all=False):
+        return self.nbody_leapfrog(H, pps, w_rows, t0, nsteps, dt, nsrc, save_all, fn="nbody_ruth4")
+
+    def nbody_leapfrog(self, H, pps, w_rows, t0, nsteps, dt, nsrc=None, save_all=False, fn="nbody_leapfrog"):
         """rows (n,6): bodies (one potential each in ``pps``, None = massless) then test particles.
         Returns (final rows, traj (nsteps+1, n, 6) | None)."""
         keep, arr = self._body_specs(pps)
         rows = _f64(w_rows).copy(); n = rows.shape[0]
         traj = np.empty((nsteps + 1, n, 6)) if save_all else None
-        rc = self._fn("nbody_leapfrog")(H.potential.spec().ptr(), arr, C.c_int(len(pps)), keep[0].ptr(),
+        rc = self._fn(fn)(H.potential.spec().ptr(), arr, C.c_int(len(pps)), keep[0].ptr(),
                                         rows.ctypes.data_as(C.c_void_p), C.c_size_t(n),
                                         C.c_int(len(pps) if nsrc is None else nsrc), C.c_double(t0), C.c_int(nsteps),
                                         C.c_double(dt), None if traj is None else traj.ctypes.data_as(C.c_void_p))

@@ -448,6 +448,34 @@ int ref_nbody_leapfrog(const gb_potential *spec, const gb_potential *body_specs,
     return 0;
 }
 
+// ruth4_integrate_nbody (integrate/cyintegrators/ruth4.pyx:139-241) with c_ruth4_step_nbody (:116-136).
+int ref_nbody_ruth4(const gb_potential *spec, const gb_potential *body_specs, int nbodies,
+                    const gb_potential *null_spec, double *w_rows, size_t n, int nsrc, double t0, int nsteps,
+                    double dt, double *traj) {
+    RefPotential rp; if (!build(spec, rp)) return -11;
+    RefBodies rb; if (!rb.build_all(body_specs, nbodies, n, null_spec)) return -11;
+    double cs[4], ds[4], grad[3];
+    ruth4_coeffs(cs, ds);
+    if (traj) memcpy(traj, w_rows, n * 6 * sizeof(double));
+    for (int j = 0; j < nsteps; j++) {
+        const double tj = t0 + (j + 1) * dt;
+        for (size_t i = 0; i < n; i++) {
+            double *w = w_rows + 6 * i;
+            for (int q = 0; q < 4; q++) {
+                grad[0] = grad[1] = grad[2] = 0.;
+                c_gradient(rp.cp, 1, tj, w, grad);
+                c_nbody_gradient_symplectic(rb.ptrs.data(), tj, w, w_rows, nsrc, (int)i, 3, grad);
+                for (int k = 0; k < 3; k++) {
+                    w[3 + k] = w[3 + k] - ds[q] * grad[k] * dt;
+                    w[k] = w[k] + cs[q] * w[3 + k] * dt;
+                }
+            }
+        }
+        if (traj) memcpy(traj + (size_t)(j + 1) * n * 6, w_rows, n * 6 * sizeof(double));
+    }
+    return 0;
+}
+
 // dop853 over the whole system with Fwrapper_direct_nbody (dop853.cpp:990-1006).
 // mode 0: dop853_helper's call (dop853.pyx:157-182) as used by direct_nbody_dop853 (nbody.pyx:96-110,
 //         nstiff = -1) with dense output at tgrid -> traj (ntimes, n, 6) when traj != NULL;
