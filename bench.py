@@ -273,7 +273,7 @@ def cpu_reference_rate(name, H, t, seconds_target=12.0, threads=None):
         unit = "orbit-output-samples/s"
     else:
         total = sum(units); unit = "orbit-steps/s"
-    return {"value": total / best, "unit": unit, "cores": threads, "kind": kind,
+    return {"value": total / best, "unit": unit, "cores": threads, "kind": kind, "sample_seconds": best,
             "sample": f"{threads} threads x {per_thread} orbits x {len(t) - 1} steps, best of 2, "
                       f"{chk.build_flags() if kind == 'reference' else 'port -O2'}"}
 
@@ -317,7 +317,8 @@ def main():
         cb = dict(vals[-1]); cb["value"] = v
         line = {"impl": "reference", "metric": "FP64 orbit-steps/sec", "value": v, "unit": cb["unit"],
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": float(np.mean([r["sample_seconds"] for r in vals])) * 1e3 if vals else None,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": {"workload": desc},
                 "cpu_baseline": cb,
                 "e2e": {"value": v, "unit": cb["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
