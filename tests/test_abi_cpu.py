@@ -56,6 +56,30 @@ def test_no_cpu_fallback():
     for call in (lambda: pot.gradient(q), lambda: pot.energy(q), lambda: pot.density(q), lambda: H.energy(w0),
                  lambda: gb.leapfrog_integrate_hamiltonian(H, w0, t),
                  lambda: gb.ruth4_integrate_hamiltonian(H, w0, t),
-                 lambda: gb.dop853_integrate_hamiltonian(H, w0, t)):
+                 lambda: gb.dop853_integrate_hamiltonian(H, w0, t),
+                 lambda: gb.DirectNBody(w0[:, :2], [gb.PlummerPotential(m=1e9, b=0.1), None],
+                                        external_potential=pot).integrate_orbit(t=t, Integrator="leapfrog"),
+                 lambda: gb.DirectNBody(w0[:, :2], [gb.PlummerPotential(m=1e9, b=0.1), None],
+                                        external_potential=pot).integrate_orbit(t=t, Integrator="dopri853"),
+                 lambda: gb.StreaklineStreamDF()._sample(pot, np.ones((4, 3)), np.ones((4, 3)), t, np.ones(4),
+                                                         np.ones(4, dtype="i4"))):
         with pytest.raises(_abi.GalaB200Error, match="no CUDA device"):
             call()
+
+
+def test_nbody_host_validation():
+    """Argument checks that happen before any device work (DirectNBody / _BodySpec)."""
+    from gala_b200.mockstream import _BodySpec
+    assert ctypes.sizeof(_abi.gb_bodies) == 16
+    pp = gb.PlummerPotential(m=1e9, b=0.1)
+    bs = _BodySpec([pp, None, pp], n_sources=2)          # third body is beyond the source count: massless
+    assert bs.struct.n_bodies == 3 and bs.pots[0].n_components == 1 and bs.pots[1].n_components == 0
+    assert bs.pots[2].n_components == 0
+    with pytest.raises(NotImplementedError):
+        _BodySpec([pp] * 5)
+    with pytest.raises(ValueError):
+        gb.DirectNBody(np.ones((6, 2)), [pp])
+    nb = gb.DirectNBody(np.ones((6, 3)), [None, pp, None], external_potential=gb.MilkyWayPotential2022())
+    assert nb.n_massive == 1
+    with pytest.raises(TypeError):
+        gb.MockStreamGenerator(gb.FardalStreamDF(), gb.Hamiltonian(gb.MilkyWayPotential2022()), progenitor_potential=3.0)

@@ -5,6 +5,8 @@ TAG=${1:-s}; shift
 STEPS=${@:-tests bench ncu_lf ncu_d8 launches}
 OUT=gpurun_out/$TAG; mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.txt 2>&1
+# the .ncu-rep files (with source) exceed gpurun's 64 MiB return limit: summarise on the box, keep the text
+summ() { python tools/ncu_summary.py $OUT/$1.ncu-rep "$2" > $OUT/$1.txt 2> $OUT/$1.summ.err; ls -la $OUT/$1.ncu-rep | awk '{print "rep bytes", $5}'; [ -z "$KEEP_REP" ] && rm -f $OUT/$1.ncu-rep; grep -E "gpu__time_duration|pipe_fp64_cycles_active|registers_per_thread|warps_active|dram__bytes" $OUT/$1.txt | head -8; }
 for s in $STEPS; do
 case $s in
 tests)   timeout 1500 python -m pytest tests -m gpu -x -q -s > $OUT/pytest.log 2>&1; echo "pytest exit $?" >> $OUT/pytest.log; tail -5 $OUT/pytest.log ;;
@@ -13,10 +15,10 @@ bench)   for w in headline c1 c2 c4 c5; do
             timeout 900 python bench.py --workload $w --steps 3 --warmup 3 $extra > $OUT/bench_$w.json 2> $OUT/bench_$w.err; tail -1 $OUT/bench_$w.json | cut -c1-400
          done ;;
 launches) ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/launches_bench.log 2>&1 ;;
-ncu_lf)  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_leapfrog -s 3 -c 1 -o $OUT/prof_leapfrog -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_lf.log 2>&1; tail -2 $OUT/ncu_lf.log ;;
-ncu_d8)  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_dop853 -s 3 -c 1 -o $OUT/prof_dop853 -f python bench.py --workload c2 --orbits 75776 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_d8.log 2>&1; tail -2 $OUT/ncu_d8.log ;;
-ncu_r4)  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_ruth4 -s 3 -c 1 -o $OUT/prof_ruth4 -f python bench.py --workload c4 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_r4.log 2>&1; tail -2 $OUT/ncu_r4.log ;;
-ncu_scf) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_leapfrog -s 3 -c 1 -o $OUT/prof_scf -f python bench.py --workload c5 --orbits 303104 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_scf.log 2>&1; tail -2 $OUT/ncu_scf.log ;;
+ncu_lf)  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_leapfrog -s 3 -c 1 -o $OUT/prof_leapfrog -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_lf.log 2>&1; summ prof_leapfrog "ncu --set full --clock-control none, k_leapfrog<MW2022, final-state>, bench headline size ($TAG)" ;;
+ncu_d8)  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_dop853 -s 3 -c 1 -o $OUT/prof_dop853 -f python bench.py --workload c2 --orbits 75776 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_d8.log 2>&1; summ prof_dop853 "ncu --set full --clock-control none, k_dop853_dyn<MW2022, static, dense>, 75,776 orbits x 1000 output times ($TAG)" ;;
+ncu_r4)  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_ruth4 -s 3 -c 1 -o $OUT/prof_ruth4 -f python bench.py --workload c4 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_r4.log 2>&1; summ prof_ruth4 "ncu --set full --clock-control none, k_ruth4<bar+MW2022, rotating, final-state>, C4 bench size ($TAG)" ;;
+ncu_scf) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_leapfrog -s 3 -c 1 -o $OUT/prof_scf -f python bench.py --workload c5 --orbits 303104 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_scf.log 2>&1; summ prof_scf "ncu --set full --clock-control none, k_leapfrog<SCF(10,6), final-state>, 303,104 orbits x 1000 steps ($TAG)" ;;
 c2ab)    for v in sort nosort; do
             [ $v = nosort ] && export GB_D8_NOSORT=1 || unset GB_D8_NOSORT
             timeout 900 python bench.py --workload c2 --steps 3 --warmup 3 --no-cpu-baseline > $OUT/bench_c2_$v.json 2> $OUT/bench_c2_$v.err; tail -1 $OUT/bench_c2_$v.json | cut -c1-300
