@@ -43,12 +43,15 @@ GB_DEV double gb_pow_eighth(double err) {
 //   init(): dop853() front-end + the first RHS evaluation + hinit (dop853.cpp:18-86, 361-366)
 //   step(): one attempted step of the dopcor loop (dop853.cpp:367-650); returns 0 to continue or
 //           the dop853 code: 1 ok, -2 nmax exceeded, -3 step too small, -4 stiff.
+#ifndef GB_D8_UNROLL_MAX
+#define GB_D8_UNROLL_MAX 12
+#endif
 template <bool DENSE, int NDIM = 6>
 struct Dop853Lane {
     static constexpr int n = NDIM;
-    // loops over the n components: fully unrolled (state in registers) for one orbit, rolled (state in
-    // local memory, small code) for the N-body systems of nbody.cuh
-    static constexpr int GB_NU = (NDIM <= 6) ? NDIM : 1;   // 6 for one orbit; 6 (nb + 1) when a lane carries nb massive bodies (nbody.cuh)
+    // loops over the n components: fully unrolled (state in registers, the compiler spills what does not
+    // fit) up to n = 12 = one massive body + one particle; rolled (state in local memory, small code) beyond
+    static constexpr int GB_NU = (NDIM <= GB_D8_UNROLL_MAX) ? NDIM : 1;   // 6 for one orbit; 6 (nb + 1) when a lane carries nb massive bodies (nbody.cuh)
     double y[n], k1[n];
     double x, xend, h, posneg, hmax, facold, hlamb;
     int last, reject, nstep, naccpt, nrejct, nfcn, out_idx;

@@ -148,7 +148,40 @@ k_nbody_leapfrog(const __grid_constant__ DevPot P, const __grid_constant__ DevBo
 // frame), then c_nbody_acceleration (sources j < nb non-Null acting on every i != j, cpotential.cpp:389-415).
 // One step size per lane: the reference shares it across a whole release group / the whole system
 // (deviation 1).  DENSE: samples at the caller's times as rows of (ntimes, ntot, 6).
-// one out-of-line copy of the right-hand side per kernel (the integrator calls it at 16 sites)
+// Right-hand side.  n > 12: ONE out-of-line copy per kernel (the integrator calls it at 16 sites; the state
+// lives in local memory anyway).  n <= 12: inlined so that the state can stay in registers, with the two
+// expensive leaves -- the external gradient and the body gradient -- as out-of-line calls on scalars.
+template <class C>
+static __device__ __noinline__ void gb_ext_gradient_call(const DevPot& P, double t, double x, double y, double z,
+                                                         double& gx, double& gy, double& gz) {
+    C::gradient(P, t, x, y, z, gx, gy, gz);
+}
+template <class C, int NDIM>
+struct NbodyRhsInline {
+    const DevPot& P;
+    const DevBodies& B;
+    __device__ __forceinline__ void operator()(double tt, const double (&w)[NDIM], double (&f)[NDIM]) const {
+        constexpr int npts = NDIM / 6;
+#pragma unroll
+        for (int i = 0; i < npts; i++) {
+            double gx, gy, gz;
+            gb_ext_gradient_call<C>(P, tt, w[6 * i], w[6 * i + 1], w[6 * i + 2], gx, gy, gz);
+            f[6 * i] = w[6 * i + 3]; f[6 * i + 1] = w[6 * i + 4]; f[6 * i + 2] = w[6 * i + 5];
+            f[6 * i + 3] = -gx; f[6 * i + 4] = -gy; f[6 * i + 5] = -gz;
+        }
+#pragma unroll
+        for (int j = 0; j < npts; j++) {
+            if (j >= B.nb || B.null_[j]) continue;
+#pragma unroll
+            for (int i = 0; i < npts; i++) {
+                if (i == j) continue;
+                double fx, fy, fz;
+                gb_body_gradient(B, j, w[6 * j], w[6 * j + 1], w[6 * j + 2], w[6 * i], w[6 * i + 1], w[6 * i + 2], fx, fy, fz);
+                f[6 * i + 3] += -fx; f[6 * i + 4] += -fy; f[6 * i + 5] += -fz;
+            }
+        }
+    }
+};
 template <class C, int NDIM>
 struct NbodyRhs {
     const DevPot& P;
@@ -187,20 +220,27 @@ k_nbody_dop853(const __grid_constant__ DevPot P, const __grid_constant__ DevBodi
     const int npts = NDIM / 6;
     double y[NDIM];
     const double* bw = body_w0 + (group ? (size_t)group[p] : 0) * (size_t)nb * 6;
-    for (int i = 0; i < nb * 6; i++) y[i] = bw[i];
-    if (has_particle) for (int k = 0; k < 6; k++) y[nb * 6 + k] = w0[p * 6 + k];
-    const NbodyRhs<C, NDIM> rhs{P, B};
+    // NDIM == 6 (nb + has_particle): rows [bodies..., particle] -- static indices so y can live in registers
+#pragma unroll
+    for (int i = 0; i < NDIM; i++) y[i] = (i < nb * 6) ? bw[i] : w0[p * 6 + (i - nb * 6)];
+    const typename std::conditional<(NDIM <= GB_D8_UNROLL_MAX), NbodyRhsInline<C, NDIM>, NbodyRhs<C, NDIM>>::type rhs{P, B};
     const bool wb = (p == body_writer);
     auto emit = [&](int idx, const double (&v)[NDIM]) {
         double* row = traj + (size_t)idx * ntot * 6;
-        if (wb) for (int i = 0; i < nb * 6; i++) row[i] = v[i];
-        if (has_particle) for (int k = 0; k < 6; k++) row[((size_t)nb + p) * 6 + k] = v[nb * 6 + k];
+#pragma unroll
+        for (int i = 0; i < NDIM; i++) {
+            if (i < nb * 6) { if (wb) row[i] = v[i]; }
+            else row[((size_t)nb + p) * 6 + (i - nb * 6)] = v[i];
+        }
     };
     int out_idx = 0, nstep, naccpt, nrejct, nfcn;
     const double ts = t1 ? t1[p] : t0;
     const int code = dop853_integrate<DENSE, NDIM>(rhs, emit, a, ts, tfinal, y, a.h0, tgrid, ntimes, out_idx, nstep,
                                                    naccpt, nrejct, nfcn);
-    if (has_particle && out_p) for (int k = 0; k < 6; k++) out_p[p * 6 + k] = y[nb * 6 + k];
-    if (wb && out_b) for (int i = 0; i < nb * 6; i++) out_b[i] = y[i];
+#pragma unroll
+    for (int i = 0; i < NDIM; i++) {
+        if (i < nb * 6) { if (wb && out_b) out_b[i] = y[i]; }
+        else if (out_p) out_p[p * 6 + (i - nb * 6)] = y[i];
+    }
     if (status) status[p] = code;
 }
