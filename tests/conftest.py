@@ -80,3 +80,13 @@ def assert_within_floor(d, floor, abs_tol, label="", qs=(0.5, 0.9, 0.99, 1.0), f
 def ref_fast():
     from oracle import oracle
     return oracle.Ref("fast") if oracle.have_ref("fast") else None
+
+
+@pytest.fixture(scope="session")
+def port_lib():
+    """oracle/port.c (plain-C restatement; fast enough for SCF samples at full problem sizes)."""
+    import os
+    from oracle import oracle
+    if not os.path.exists(os.path.join(oracle._REF_DIR, "libgala_port.so")):
+        oracle.build()
+    return oracle.Port()
