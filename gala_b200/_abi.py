@@ -60,6 +60,7 @@ SIGNATURES = {
     "gb_gradient": (C.c_int, [P(gb_potential), C.c_void_p, C.c_double, C.c_size_t, C.c_void_p, P(gb_launch)]),
     "gb_energy": (C.c_int, [P(gb_potential), C.c_void_p, C.c_double, C.c_size_t, C.c_void_p, P(gb_launch)]),
     "gb_density": (C.c_int, [P(gb_potential), C.c_void_p, C.c_double, C.c_size_t, C.c_void_p, P(gb_launch)]),
+    "gb_hessian": (C.c_int, [P(gb_potential), C.c_void_p, C.c_double, C.c_size_t, C.c_void_p, P(gb_launch)]),
     "gb_hamiltonian_energy": (C.c_int, [P(gb_potential), P(gb_frame), C.c_void_p, C.c_double, C.c_size_t,
                                         C.c_void_p, P(gb_launch)]),
     "gb_hamiltonian_gradient": (C.c_int, [P(gb_potential), P(gb_frame), C.c_void_p, C.c_double, C.c_size_t,
@@ -129,6 +130,8 @@ def check(rc: int):
     msg = lib().gb_last_error().decode()
     if rc == -12:
         raise ValueError(msg)                      # dop853.pyx:143-152
+    if rc == -14:
+        raise NotImplementedError(msg)             # potential/potential/core.py:572-575
     if rc == -13:
         raise TypeError(msg)                       # leapfrog.pyx:64-68, ruth4.pyx:49-52
     if rc in (-1, -2, -3, -4):

@@ -390,6 +390,33 @@ int gb_density(const gb_potential* pot, const double* q, double t, size_t N, dou
     return eval_common(EV_DENSITY, pot, q, t, N, out, opt);
 }
 
+int gb_hessian(const gb_potential* pot, const double* q, double t, size_t N, double* hess, const gb_launch* opt) {
+    Ctx c; RET_IF(open_ctx(opt, c));
+    if (N && (!q || !hess)) return fail(-12, "null data pointer");
+    if (!pot) return fail(-12, "null potential");
+    for (int i = 0; i < pot->n_components; i++) {
+        const gb_component& cc = pot->comp[i];
+        if (cc.type_id == GB_POT_SCF || cc.type_id == GB_POT_MULTIPOLE)
+            return fail(-11, "no Hessian for basis-function expansions (the reference has none either)");
+        if (cc.do_shift_rotate) {
+            static const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+            for (int k = 0; k < 9; k++)
+                if (cc.R[k] != I3[k])
+                    return fail(-14, "Computing Hessian matrices for rotated potentials is currently not supported.");
+        }
+    }
+    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    const int block = c.block > 0 ? c.block : 128;
+    const void* dq; RET_IF(stage_in(c, 0, q, 3 * N * sizeof(double), &dq));
+    void* dout; RET_IF(stage_out_alloc(c, 1, hess, 9 * N * sizeof(double), &dout));
+    cudaError_t e = KCALL(c, eval_hessian, r.P, (const double*)dq, N, (double*)dout, block, c.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "hessian kernel launch");
+    if (N) g_launches++;
+    RET_IF(stage_out_copy(c, hess, dout, 9 * N * sizeof(double)));
+    (void)t;
+    return finish(c);
+}
+
 int gb_release_scratch(void) {
     std::lock_guard<std::mutex> g(g_scratch_mu);
     int cur = 0;

@@ -22,6 +22,9 @@ namespace GB_NS {
 #include "hamiltonian.cuh"
 #include "dop853.cuh"
 #include "mockstream.cuh"
+#if GB_PART == 4
+#include "hessian.cuh"
+#endif
 #if GB_PART == 5 || GB_PART == 6
 #include "nbody.cuh"
 #endif
@@ -359,6 +362,11 @@ cudaError_t fardal_release(const DevPot& P, double G, const double* prog_w, cons
     return cudaGetLastError();
 }
 
+cudaError_t eval_hessian(const DevPot& P, const double* q, size_t N, double* hess, int block, cudaStream_t s) {
+    if (N == 0) return cudaSuccess;
+    k_eval_hessian<<<nblocks(N, block), block, 0, s>>>(P, q, N, hess);
+    return cudaGetLastError();
+}
 #endif  // GB_PART == 4
 
 #if GB_PART == 5 || GB_PART == 6

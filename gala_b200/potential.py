@@ -149,6 +149,12 @@ class PotentialBase:
     def density(self, q, t=0.0):
         return self._eval("gb_density", q, t, 1)
 
+    def hessian(self, q, t=0.0):
+        """d2Phi/dq_i dq_j at q (3,N) -> (3,3,N); mirrors ``PotentialBase.hessian`` (core.py:535-600).
+        Rotated potentials raise ``NotImplementedError`` like the reference."""
+        h = self._eval("gb_hessian", q, t, 9)
+        return h.reshape((3, 3) + tuple(h.shape[1:]))
+
     def __call__(self, q, t=0.0):
         return self.energy(q, t)
 

@@ -125,6 +125,12 @@ int gb_energy  (const gb_potential* pot, const double* q, double t, size_t N,
                 double* out /* (N) */, const gb_launch* opt);
 int gb_density (const gb_potential* pot, const double* q, double t, size_t N,
                 double* out /* (N) */, const gb_launch* opt);
+/* CPotentialWrapper.hessian -> c_hessian (potential/potential/cpotential.pyx:164-182,
+ * potential/potential/src/cpotential.cpp:290-314): hess (3,3,N), H[i][j][n] = d2Phi/dq_i dq_j.  Evaluated by
+ * forward-mode differentiation of the gradient on the device (csrc/hessian.cuh).  -14 for a rotated
+ * component (NotImplementedError in the reference, core.py:572-575); -11 for SCF / multipole. */
+int gb_hessian(const gb_potential* pot, const double* q, double t, size_t N, double* hess, const gb_launch* opt);
+
 /* Hamiltonian.energy: potential + frame energy, w is (6,N)
  * (hamiltonian/src/chamiltonian.cpp:7-19; frame/builtin/builtin_frames.cpp:8-16,73-92) */
 int gb_hamiltonian_energy(const gb_potential* pot, const gb_frame* fr, const double* w,

@@ -74,6 +74,14 @@ class _Lib:
     def density(self, pot, q, t=0.0):
         return self._scalar("density", pot, q, t)
 
+    def hessian(self, pot, q, t=0.0):
+        q = _f64(q); N = q.shape[1]
+        out = np.empty((3, 3, N))
+        rc = self._fn("hessian")(pot.spec().ptr(), q.ctypes.data_as(C.c_void_p), C.c_double(t), C.c_size_t(N),
+                                 out.ctypes.data_as(C.c_void_p))
+        assert rc == 0, rc
+        return out
+
     def hamiltonian_energy(self, H, w, t=0.0):
         w = _f64(w); N = w.shape[1]
         out = np.empty(N)

@@ -387,6 +387,18 @@ int ref_dop853_step_rows(const gb_potential *spec, const gb_frame *fr, double *w
     return worst;
 }
 
+// CPotentialWrapper.hessian (potential/potential/cpotential.pyx:164-182): c_hessian per point; q (3,N) SoA
+// in, hess (3,3,N) out (the layout PotentialBase.hessian returns, core.py:535-600).
+int ref_hessian(const gb_potential *spec, const double *q, double t, size_t N, double *hess) {
+    RefPotential rp; if (!build(spec, rp)) return -11;
+    for (size_t n = 0; n < N; n++) {
+        double qq[3] = {q[n], q[N + n], q[2 * N + n]}, h[9];
+        c_hessian(rp.cp, t, qq, h);
+        for (int k = 0; k < 9; k++) hess[(size_t)k * N + n] = h[k];
+    }
+    return 0;
+}
+
 // c_d2_dr2 (potential/potential/src/cpotential.cpp:346-371) exposed for the release tests.
 double ref_d2_dr2(const gb_potential *spec, double t, const double *q3) {
     RefPotential rp; if (!build(spec, rp)) return NAN;

@@ -404,3 +404,57 @@ def test_edge_cases():
         w0 = np.tile(one[:, None], (1, N)) * (1 + 1e-3 * np.arange(N))
         _, w = gb.leapfrog_integrate_hamiltonian(H, np.ascontiguousarray(w0), t, save_all=0)
         assert np.isfinite(w).all() and w.shape == (6, N)
+
+
+HESS_REF = ["nfw", "nfw_flat", "nfw_triax", "hernquist", "mn", "mn3", "bar", "kepler", "plummer", "isochrone", "jaffe",
+            "stone", "satoh", "powerlawcutoff", "mw2022", "mw_v1", "bar_mw2022", "bovy2014"]
+HESS_FD = ["burkert", "kuzmin", "leesuto", "logarithmic", "lm10"]
+
+
+@pytest.mark.parametrize("name", HESS_REF + HESS_FD)
+def test_hessian(ref, name):
+    """gb_hessian (forward-mode differentiation of the gradient on the device) against the reference's
+    sympy-generated `*_hessian` functions through c_hessian (cpotential.cpp:290-314) where the reference has
+    one; for Burkert / Kuzmin / LeeSuto (no Hessian in cybuiltin.pyx) and for the Logarithmic potential with
+    phi != 0 (logarithmic_hessian, builtin_potentials.cpp:1627-1679, ignores the rotation its own gradient
+    applies -- 9 % off its own finite differences) the check is central differences of the gradient."""
+    pot = POTS[name]
+    q = np.random.default_rng(11).normal(0, 9.0, (3, 513))
+    if name == "kuzmin":
+        q[2] = np.abs(q[2]) + 0.3                     # stay off the z = 0 sheet
+    H = pot.hessian(q)
+    assert H.shape == (3, 3, 513)
+    scale = np.sqrt((H ** 2).sum((0, 1)))
+    assert np.max(np.abs(H - H.transpose(1, 0, 2)).sum((0, 1)) / scale) < 1e-12       # symmetric
+    if name in HESS_REF:
+        H0 = ref.hessian(pot, q)
+        tol = 1e-10 if name in ("powerlawcutoff", "bovy2014") else 1e-12
+        assert np.max(np.sqrt(((H - H0) ** 2).sum((0, 1))) / np.sqrt((H0 ** 2).sum((0, 1)))) < tol
+    else:
+        h = 1e-5
+        fd = np.zeros_like(H)
+        for j in range(3):
+            dq = np.zeros_like(q); dq[j] = h
+            fd[:, j] = (ref.gradient(pot, q + dq) - ref.gradient(pot, q - dq)) / (2 * h)
+        assert np.max(np.sqrt(((H - fd) ** 2).sum((0, 1))) / np.sqrt((fd ** 2).sum((0, 1)))) < 1e-7
+    # trace of the Hessian = 4 pi G rho (Poisson) wherever the density is defined and smooth
+    if name in ("hernquist", "plummer", "mn", "mn3", "satoh", "stone", "burkert", "mw2022"):
+        rho = pot.density(q)
+        tr = H[0, 0] + H[1, 1] + H[2, 2]
+        assert np.allclose(tr, 4 * np.pi * pot.G * rho, rtol=1e-8, atol=1e-10 * np.abs(tr).max())
+
+
+def test_hessian_errors_and_shift(ref):
+    shifted = gb.HernquistPotential(m=3e10, c=2.0, origin=[1.0, -2.0, 0.5])
+    q = np.random.default_rng(3).normal(0, 5.0, (3, 64))
+    H0 = ref.hessian(shifted, q)
+    assert np.max(np.abs(shifted.hessian(q) - H0)) / np.abs(H0).max() < 1e-13
+    with pytest.raises(NotImplementedError):
+        POTS["shifted_composite"].hessian(q)          # one component carries a rotation
+    with pytest.raises(gb._abi.GalaB200Error):
+        POTS["scf_small"].hessian(q)
+    # device buffers
+    import torch
+    Hd = POTS["mw2022"].hessian(torch.as_tensor(q, device="cuda"))
+    assert tuple(Hd.shape) == (3, 3, 64)
+    assert np.allclose(Hd.cpu().numpy(), POTS["mw2022"].hessian(q), rtol=0, atol=0)
