@@ -980,7 +980,6 @@ int gb_nbody_dop853(const gb_potential* pot, const gb_bodies* bodies, const doub
     Resolved r; RET_IF(resolve(pot, r, c.stream));
     DevBodies B; RET_IF(resolve_bodies(bodies, B));
     const size_t nb = B.nb, ntot = nb + Np;
-    if (nb + (Np ? 1 : 0) > 4) return fail(-11, "DOP853 N-body systems carry at most 4 points per lane (3 bodies + the particle)");
     if (body_writer >= (Np ? Np : 1)) return fail(-12, "body_writer out of range");
     Dop853Args a;
     // step_mode 0: dop853_helper (dop853.pyx:157-182: uround = eps, nstiff = -1 from direct_nbody_dop853, nbody.pyx:106);

@@ -53,11 +53,13 @@ struct Dop853Lane {
     // fit) up to n = 12 = one massive body + one particle; rolled (state in local memory, small code) beyond
     static constexpr int GB_NU = (NDIM <= GB_D8_UNROLL_MAX) ? NDIM : 1;   // 6 for one orbit; 6 (nb + 1) when a lane carries nb massive bodies (nbody.cuh)
     double y[n], k1[n];
+    int nrun = NDIM;   // number of components in use (n > GB_D8_UNROLL_MAX: a system of nrun <= NDIM equations)
     double x, xend, h, posneg, hmax, facold, hlamb;
     int last, reject, nstep, naccpt, nrejct, nfcn, out_idx;
 
     template <class RHS>
     GB_DEV void init(const RHS& rhs, const Dop853Args& a, double x0, double xend_, double h0) {
+        const int nn = (NDIM <= GB_D8_UNROLL_MAX) ? NDIM : nrun;
         x = x0; xend = xend_; h = h0;
         posneg = gb_sign(1.0, xend - x);
         hmax = (a.hmax == 0.0) ? (xend - x) : a.hmax;   // dop853.cpp:787-788
@@ -73,7 +75,7 @@ struct Dop853Lane {
             double k2[n], k3[n];
             double dnf = 0.0, dny = 0.0;
 #pragma unroll(GB_NU)
-            for (int i = 0; i < n; i++) {
+            for (int i = 0; i < nn; i++) {
                 const double sk = atoli + rtoli * fabs(y[i]);
                 double sqr = k1[i] / sk; dnf += sqr * sqr;
                 sqr = y[i] / sk; dny += sqr * sqr;
@@ -82,11 +84,11 @@ struct Dop853Lane {
             hh = gb_min(hh, hmax);
             hh = gb_sign(hh, posneg);
 #pragma unroll(GB_NU)
-            for (int i = 0; i < n; i++) k3[i] = y[i] + hh * k1[i];
+            for (int i = 0; i < nn; i++) k3[i] = y[i] + hh * k1[i];
             rhs(x + hh, k3, k2);
             double der2 = 0.0;
 #pragma unroll(GB_NU)
-            for (int i = 0; i < n; i++) {
+            for (int i = 0; i < nn; i++) {
                 const double sk = atoli + rtoli * fabs(y[i]);
                 const double sqr = (k2[i] - k1[i]) / sk; der2 += sqr * sqr;
             }
@@ -102,6 +104,7 @@ struct Dop853Lane {
     template <class RHS, class OUT>
     GB_DEV int step(const RHS& rhs, const OUT& emit, const Dop853Args& a, const double* __restrict__ tout, int ntout) {
         using namespace dp8;
+        const int nn = (NDIM <= GB_D8_UNROLL_MAX) ? NDIM : nrun;
         double k2[n], k3[n], k4[n], k5[n], k6[n], k7[n], k8[n], k9[n], k10[n], yy1[n];
         double rc1[n], rc2[n], rc3[n], rc4[n], rc5[n], rc6[n], rc7[n], rc8[n];
         const double safe = 0.9, fac1 = 0.333, fac2 = 6.0;     // dop853.cpp:755-768 defaults
@@ -116,50 +119,50 @@ struct Dop853Lane {
 
             // the twelve stages (dop853.cpp:369-409)
 #pragma unroll(GB_NU)
-            for (int i = 0; i < n; i++) yy1[i] = y[i] + h * a21 * k1[i];
+            for (int i = 0; i < nn; i++) yy1[i] = y[i] + h * a21 * k1[i];
             rhs(x + c2 * h, yy1, k2);
 #pragma unroll(GB_NU)
-            for (int i = 0; i < n; i++) yy1[i] = y[i] + h * (a31 * k1[i] + a32 * k2[i]);
+            for (int i = 0; i < nn; i++) yy1[i] = y[i] + h * (a31 * k1[i] + a32 * k2[i]);
             rhs(x + c3 * h, yy1, k3);
 #pragma unroll(GB_NU)
-            for (int i = 0; i < n; i++) yy1[i] = y[i] + h * (a41 * k1[i] + a43 * k3[i]);
+            for (int i = 0; i < nn; i++) yy1[i] = y[i] + h * (a41 * k1[i] + a43 * k3[i]);
             rhs(x + c4 * h, yy1, k4);
 #pragma unroll(GB_NU)
-            for (int i = 0; i < n; i++) yy1[i] = y[i] + h * (a51 * k1[i] + a53 * k3[i] + a54 * k4[i]);
+            for (int i = 0; i < nn; i++) yy1[i] = y[i] + h * (a51 * k1[i] + a53 * k3[i] + a54 * k4[i]);
             rhs(x + c5 * h, yy1, k5);
 #pragma unroll(GB_NU)
-            for (int i = 0; i < n; i++) yy1[i] = y[i] + h * (a61 * k1[i] + a64 * k4[i] + a65 * k5[i]);
+            for (int i = 0; i < nn; i++) yy1[i] = y[i] + h * (a61 * k1[i] + a64 * k4[i] + a65 * k5[i]);
             rhs(x + c6 * h, yy1, k6);
 #pragma unroll(GB_NU)
-            for (int i = 0; i < n; i++) yy1[i] = y[i] + h * (a71 * k1[i] + a74 * k4[i] + a75 * k5[i] + a76 * k6[i]);
+            for (int i = 0; i < nn; i++) yy1[i] = y[i] + h * (a71 * k1[i] + a74 * k4[i] + a75 * k5[i] + a76 * k6[i]);
             rhs(x + c7 * h, yy1, k7);
 #pragma unroll(GB_NU)
-            for (int i = 0; i < n; i++)
+            for (int i = 0; i < nn; i++)
                 yy1[i] = y[i] + h * (a81 * k1[i] + a84 * k4[i] + a85 * k5[i] + a86 * k6[i] + a87 * k7[i]);
             rhs(x + c8 * h, yy1, k8);
 #pragma unroll(GB_NU)
-            for (int i = 0; i < n; i++)
+            for (int i = 0; i < nn; i++)
                 yy1[i] = y[i] + h * (a91 * k1[i] + a94 * k4[i] + a95 * k5[i] + a96 * k6[i] + a97 * k7[i] + a98 * k8[i]);
             rhs(x + c9 * h, yy1, k9);
 #pragma unroll(GB_NU)
-            for (int i = 0; i < n; i++)
+            for (int i = 0; i < nn; i++)
                 yy1[i] = y[i] + h * (a101 * k1[i] + a104 * k4[i] + a105 * k5[i] + a106 * k6[i] + a107 * k7[i] +
                                      a108 * k8[i] + a109 * k9[i]);
             rhs(x + c10 * h, yy1, k10);
 #pragma unroll(GB_NU)
-            for (int i = 0; i < n; i++)
+            for (int i = 0; i < nn; i++)
                 yy1[i] = y[i] + h * (a111 * k1[i] + a114 * k4[i] + a115 * k5[i] + a116 * k6[i] + a117 * k7[i] +
                                      a118 * k8[i] + a119 * k9[i] + a1110 * k10[i]);
             rhs(x + c11 * h, yy1, k2);
             const double xph = x + h;
 #pragma unroll(GB_NU)
-            for (int i = 0; i < n; i++)
+            for (int i = 0; i < nn; i++)
                 yy1[i] = y[i] + h * (a121 * k1[i] + a124 * k4[i] + a125 * k5[i] + a126 * k6[i] + a127 * k7[i] +
                                      a128 * k8[i] + a129 * k9[i] + a1210 * k10[i] + a1211 * k2[i]);
             rhs(xph, yy1, k3);
             nfcn += 11;
 #pragma unroll(GB_NU)
-            for (int i = 0; i < n; i++) {
+            for (int i = 0; i < nn; i++) {
                 k4[i] = b1 * k1[i] + b6 * k6[i] + b7 * k7[i] + b8 * k8[i] + b9 * k9[i] + b10 * k10[i] + b11 * k2[i] +
                         b12 * k3[i];
                 k5[i] = y[i] + h * k4[i];
@@ -168,7 +171,7 @@ struct Dop853Lane {
             // error estimation (dop853.cpp:416-444), scalar tolerances, norm over this orbit's 6 components
             double err = 0.0, err2 = 0.0;
 #pragma unroll(GB_NU)
-            for (int i = 0; i < n; i++) {
+            for (int i = 0; i < nn; i++) {
                 const double sk = atoli + rtoli * gb_max(fabs(y[i]), fabs(k5[i]));
                 double erri = k4[i] - bhh1 * k1[i] - bhh2 * k9[i] - bhh3 * k3[i];
                 double sqr = erri / sk;
@@ -180,7 +183,7 @@ struct Dop853Lane {
             }
             double deno = err + 0.01 * err2;
             if (deno <= 0.0) deno = 1.0;
-            err = fabs(h) * err * sqrt(1.0 / (deno * (double)n));
+            err = fabs(h) * err * sqrt(1.0 / (deno * (double)nn));
 
             // step-size controller (dop853.cpp:446-452), beta = 0 => pow(facold, beta) == 1
             const double fac11 = gb_pow_eighth(err);
@@ -199,7 +202,7 @@ struct Dop853Lane {
                 if (!(naccpt % a.nstiff)) {
                     double stnum = 0.0, stden = 0.0;
 #pragma unroll(GB_NU)
-                    for (int i = 0; i < n; i++) {
+                    for (int i = 0; i < nn; i++) {
                         double sqr = k4[i] - k3[i]; stnum += sqr * sqr;
                         sqr = k5[i] - yy1[i]; stden += sqr * sqr;
                     }
@@ -210,7 +213,7 @@ struct Dop853Lane {
                 if (DENSE) {
                     // dense-output preparation (dop853.cpp:492-582)
 #pragma unroll(GB_NU)
-                    for (int i = 0; i < n; i++) {
+                    for (int i = 0; i < nn; i++) {
                         rc1[i] = y[i];
                         const double ydiff = k5[i] - y[i];
                         rc2[i] = ydiff;
@@ -227,23 +230,23 @@ struct Dop853Lane {
                                  d711 * k2[i] + d712 * k3[i];
                     }
 #pragma unroll(GB_NU)
-                    for (int i = 0; i < n; i++)
+                    for (int i = 0; i < nn; i++)
                         yy1[i] = y[i] + h * (a141 * k1[i] + a147 * k7[i] + a148 * k8[i] + a149 * k9[i] + a1410 * k10[i] +
                                              a1411 * k2[i] + a1412 * k3[i] + a1413 * k4[i]);
                     rhs(x + c14 * h, yy1, k10);
 #pragma unroll(GB_NU)
-                    for (int i = 0; i < n; i++)
+                    for (int i = 0; i < nn; i++)
                         yy1[i] = y[i] + h * (a151 * k1[i] + a156 * k6[i] + a157 * k7[i] + a158 * k8[i] + a1511 * k2[i] +
                                              a1512 * k3[i] + a1513 * k4[i] + a1514 * k10[i]);
                     rhs(x + c15 * h, yy1, k2);
 #pragma unroll(GB_NU)
-                    for (int i = 0; i < n; i++)
+                    for (int i = 0; i < nn; i++)
                         yy1[i] = y[i] + h * (a161 * k1[i] + a166 * k6[i] + a167 * k7[i] + a168 * k8[i] + a169 * k9[i] +
                                              a1613 * k4[i] + a1614 * k10[i] + a1615 * k2[i]);
                     rhs(x + c16 * h, yy1, k3);
                     nfcn += 3;
 #pragma unroll(GB_NU)
-                    for (int i = 0; i < n; i++) {
+                    for (int i = 0; i < nn; i++) {
                         rc5[i] = h * (rc5[i] + d413 * k4[i] + d414 * k10[i] + d415 * k2[i] + d416 * k3[i]);
                         rc6[i] = h * (rc6[i] + d513 * k4[i] + d514 * k10[i] + d515 * k2[i] + d516 * k3[i]);
                         rc7[i] = h * (rc7[i] + d613 * k4[i] + d614 * k10[i] + d615 * k2[i] + d616 * k3[i]);
@@ -258,7 +261,7 @@ struct Dop853Lane {
                             const double s1 = 1.0 - s;
                             double v[n];
 #pragma unroll(GB_NU)
-                            for (int i = 0; i < n; i++)
+                            for (int i = 0; i < nn; i++)
                                 v[i] = rc1[i] + s * (rc2[i] + s1 * (rc3[i] + s * (rc4[i] + s1 * (rc5[i] + s * (rc6[i] + s1 * (rc7[i] + s * rc8[i]))))));
                             emit(out_idx, v);
                             out_idx++;
@@ -269,7 +272,7 @@ struct Dop853Lane {
                 }
 
 #pragma unroll(GB_NU)
-                for (int i = 0; i < n; i++) { k1[i] = k4[i]; y[i] = k5[i]; }
+                for (int i = 0; i < nn; i++) { k1[i] = k4[i]; y[i] = k5[i]; }
                 x = xph;
                 if (last) return 1;
                 if (fabs(hnew) > hmax) hnew = posneg * hmax;
@@ -293,14 +296,16 @@ struct Dop853Lane {
 template <bool DENSE, int NDIM = 6, class RHS, class OUT>
 GB_DEV int dop853_integrate(const RHS& rhs, const OUT& emit, const Dop853Args& a, double x, double xend,
                             double (&y)[NDIM], double h, const double* __restrict__ tout, int ntout,
-                            int& out_idx, int& nstep_, int& naccpt_, int& nrejct_, int& nfcn_) {
+                            int& out_idx, int& nstep_, int& naccpt_, int& nrejct_, int& nfcn_, int nrun = NDIM) {
     Dop853Lane<DENSE, NDIM> L;
-#pragma unroll
+    constexpr int NU = (NDIM <= GB_D8_UNROLL_MAX) ? NDIM : 1;
+    L.nrun = nrun;
+#pragma unroll(NU)
     for (int i = 0; i < NDIM; i++) L.y[i] = y[i];
     L.init(rhs, a, x, xend, h);
     int code;
     do { code = L.step(rhs, emit, a, tout, ntout); } while (code == 0);
-#pragma unroll
+#pragma unroll(NU)
     for (int i = 0; i < NDIM; i++) y[i] = L.y[i];
     out_idx = L.out_idx; nstep_ = L.nstep; naccpt_ = L.naccpt; nrejct_ = L.nrejct; nfcn_ = L.nfcn;
     return code;

@@ -42,9 +42,10 @@ struct DevPot {
 // Massive bodies carried by every lane of the N-body kernels (nbody.cuh): each body owns a small potential
 // (its components are evaluated about the body's current position: c_nbody_acceleration /
 // c_nbody_gradient_symplectic set do_shift_rotate = 1 and q0 = &w[body], cpotential.cpp:389-442).
-#define GB_MAXB 4      // massive bodies per system
-#define GB_MAXBC 8     // potential components over all bodies
-#define GB_MAXBP 48    // packed parameters over all body components
+#define GB_MAXB 16     // bodies (massive or massless) carried per system
+#define GB_MAXBC 16    // potential components over all bodies
+#define GB_MAXBP 96    // packed parameters over all body components
+#define GB_ND_MAX (6 * (GB_MAXB + 1))   // largest DOP853 system of a lane: all bodies + its particle
 struct DevBodies {
     int32_t nb;                   // bodies (massive or Null) at the front of the system
     int32_t nc;

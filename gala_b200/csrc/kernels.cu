@@ -408,7 +408,8 @@ static void launch_nbody_d8(const DevPot& P, const DevBodies& B, const Dop853Arg
         k_nbody_dop853<C, NDIM, false><<<nblocks(nthreads, block), block, 0, s>>>(
             P, B, a, body_w0, group, w0, t1, Np, hasp, tgrid, ntimes, t0, tfinal, out_p, out_b, body_writer, traj, ntot, status);
 }
-// systems of 1-2 points (n = 6, 12: unrolled, state in registers) compile in part 5, 3-4 points in part 6
+// systems of 1-2 points (n = 6, 12: unrolled, state in registers) compile in part 5; larger ones run ONE
+// kernel sized for GB_ND_MAX equations with a run-time count (rolled loops, state in local memory), part 6
 #if GB_PART == 5
 #define GB_ND_NAME nbody_dop853_small
 #else
@@ -425,11 +426,10 @@ cudaError_t GB_ND_NAME(const DevPot& P, const DevBodies& B, const Dop853Args& a,
 #if GB_PART == 5
         case 1: GB_ND(6); break;
         case 2: GB_ND(12); break;
-#else
-        case 3: GB_ND(18); break;
-        case 4: GB_ND(24); break;
-#endif
         default: return cudaErrorInvalidValue;
+#else
+        default: if (npts < 3 || npts > GB_MAXB + 1) return cudaErrorInvalidValue; GB_ND(GB_ND_MAX); break;
+#endif
     }
 #undef GB_ND
     return cudaGetLastError();

@@ -186,8 +186,9 @@ template <class C, int NDIM>
 struct NbodyRhs {
     const DevPot& P;
     const DevBodies& B;
+    int npts;                      // points in use (bodies + the particle); the arrays are sized for NDIM / 6
     __device__ __noinline__ void operator()(double tt, const double (&w)[NDIM], double (&f)[NDIM]) const {
-        const int nb = B.nb, npts = NDIM / 6;
+        const int nb = B.nb;
         for (int i = 0; i < npts; i++) {
             double gx, gy, gz;
             C::gradient(P, tt, w[6 * i], w[6 * i + 1], w[6 * i + 2], gx, gy, gz);
@@ -217,30 +218,32 @@ k_nbody_dop853(const __grid_constant__ DevPot P, const __grid_constant__ DevBodi
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= (has_particle ? Np : 1)) return;
     const int nb = B.nb;
-    const int npts = NDIM / 6;
+    constexpr bool FIXED = NDIM <= GB_D8_UNROLL_MAX;          // NDIM == 6 (nb + has_particle), state in registers
+    const int nrun = FIXED ? NDIM : 6 * (nb + (has_particle ? 1 : 0));
     double y[NDIM];
     const double* bw = body_w0 + (group ? (size_t)group[p] : 0) * (size_t)nb * 6;
-    // NDIM == 6 (nb + has_particle): rows [bodies..., particle] -- static indices so y can live in registers
-#pragma unroll
-    for (int i = 0; i < NDIM; i++) y[i] = (i < nb * 6) ? bw[i] : w0[p * 6 + (i - nb * 6)];
-    const typename std::conditional<(NDIM <= GB_D8_UNROLL_MAX), NbodyRhsInline<C, NDIM>, NbodyRhs<C, NDIM>>::type rhs{P, B};
+    // rows [bodies..., particle]
+#pragma unroll(FIXED ? NDIM : 1)
+    for (int i = 0; i < NDIM; i++) y[i] = (i < nb * 6) ? bw[i] : ((i < nrun) ? w0[p * 6 + (i - nb * 6)] : 0.);
+    typename std::conditional<FIXED, NbodyRhsInline<C, NDIM>, NbodyRhs<C, NDIM>>::type rhs{P, B};
+    if constexpr (!FIXED) rhs.npts = nrun / 6;
     const bool wb = (p == body_writer);
     auto emit = [&](int idx, const double (&v)[NDIM]) {
         double* row = traj + (size_t)idx * ntot * 6;
-#pragma unroll
+#pragma unroll(FIXED ? NDIM : 1)
         for (int i = 0; i < NDIM; i++) {
             if (i < nb * 6) { if (wb) row[i] = v[i]; }
-            else row[((size_t)nb + p) * 6 + (i - nb * 6)] = v[i];
+            else if (i < nrun) row[((size_t)nb + p) * 6 + (i - nb * 6)] = v[i];
         }
     };
     int out_idx = 0, nstep, naccpt, nrejct, nfcn;
     const double ts = t1 ? t1[p] : t0;
     const int code = dop853_integrate<DENSE, NDIM>(rhs, emit, a, ts, tfinal, y, a.h0, tgrid, ntimes, out_idx, nstep,
-                                                   naccpt, nrejct, nfcn);
-#pragma unroll
+                                                   naccpt, nrejct, nfcn, nrun);
+#pragma unroll(FIXED ? NDIM : 1)
     for (int i = 0; i < NDIM; i++) {
         if (i < nb * 6) { if (wb && out_b) out_b[i] = y[i]; }
-        else if (out_p) out_p[p * 6 + (i - nb * 6)] = y[i];
+        else if (i < nrun && out_p) out_p[p * 6 + (i - nb * 6)] = y[i];
     }
     if (status) status[p] = code;
 }

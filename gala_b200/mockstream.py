@@ -192,8 +192,8 @@ class _BodySpec:
 
     def __init__(self, particle_potentials, n_sources=None):
         nb = len(particle_potentials)
-        if nb < 1 or nb > 4:
-            raise NotImplementedError("the B200 N-body kernels carry 1..4 bodies (massive or massless) per system")
+        if nb < 1 or nb > 16:
+            raise NotImplementedError("the B200 N-body kernels carry 1..16 bodies (massive or massless) per system")
         self._keep = []
         self.pots = (_abi.gb_potential * nb)()
         for b, pp in enumerate(particle_potentials):
@@ -237,8 +237,6 @@ def _nbody_dop853(H, pps, body_w0, tgrid, tfinal, dt0, step_mode, w0_rows=None, 
     bs = _BodySpec(pps)
     body_w0 = np.ascontiguousarray(body_w0, dtype=np.float64).reshape(-1, len(pps), 6)
     Np = 0 if w0_rows is None else w0_rows.shape[0]
-    if len(pps) + (1 if Np else 0) > 4:
-        raise NotImplementedError("DOP853 N-body systems carry at most 4 points per lane (3 bodies + the test particle)")
     rows = np.ascontiguousarray(w0_rows, dtype=np.float64) if Np else None
     out_p = np.empty((Np, 6)) if Np else None
     out_b = np.empty((len(pps), 6))
@@ -264,7 +262,7 @@ def _nbody_dop853(H, pps, body_w0, tgrid, tfinal, dt0, step_mode, w0_rows=None, 
 
 class DirectNBody:
     """``gala.dynamics.nbody.DirectNBody`` (``dynamics/nbody/core.py``): initial conditions of the bodies,
-    one potential per body (``None`` = test particle) and the external Hamiltonian.  Up to 4 massive
+    one potential per body (``None`` = test particle) and the external Hamiltonian.  Up to 16 massive
     bodies plus any number of test particles run on the device (one lane = the massive bodies + one test
     particle, ``csrc/nbody.cuh``); without massive bodies every body is an independent orbit."""
 

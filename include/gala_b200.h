@@ -222,7 +222,7 @@ int gb_mockstream_leapfrog(const gb_potential* pot,
  * body_w0[group[p]] (group == NULL: state 0) at time t1[p] (t1 == NULL: the common start time);
  * w0_rows (Np, 6); out_particles (Np, 6); out_bodies (n_bodies, 6) = the bodies as integrated by lane
  * `body_writer` (Np == 0: the single bodies-only lane); traj (ntimes, n_bodies + Np, 6) or NULL. */
-#define GB_MAX_BODIES 4
+#define GB_MAX_BODIES 16
 typedef struct {
     int32_t n_bodies;              /* 1..GB_MAX_BODIES */
     int32_t _pad;
@@ -241,7 +241,8 @@ int gb_nbody_leapfrog(const gb_potential* pot, const gb_bodies* bodies,
 
 /* DOP853: step_mode 0 = dop853_helper's settings with nstiff = -1 (direct_nbody_dop853), tgrid/ntimes
  * = the caller's output grid (dense output when traj != NULL); step_mode 1 = dop853_step's settings
- * (mockstream_dop853).  At most 4 points per lane (n_bodies + 1 <= 4 with test particles).  status:
+ * (mockstream_dop853).  Systems of 1-2 points keep their state in registers; larger ones (up to
+ * GB_MAX_BODIES + 1 points) run with their state in local memory.  status:
  * one dop853 code per lane (Np entries, or 1). */
 int gb_nbody_dop853(const gb_potential* pot, const gb_bodies* bodies,
                     const double* body_w0, int ngroups, const int32_t* group,

@@ -76,7 +76,7 @@ def test_nbody_host_validation():
     assert bs.struct.n_bodies == 3 and bs.pots[0].n_components == 1 and bs.pots[1].n_components == 0
     assert bs.pots[2].n_components == 0
     with pytest.raises(NotImplementedError):
-        _BodySpec([pp] * 5)
+        _BodySpec([pp] * 17)
     with pytest.raises(ValueError):
         gb.DirectNBody(np.ones((6, 2)), [pp])
     nb = gb.DirectNBody(np.ones((6, 3)), [None, pp, None], external_potential=gb.MilkyWayPotential2022())

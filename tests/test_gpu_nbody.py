@@ -216,3 +216,44 @@ def test_generator_with_progenitor_potential_changes_the_stream():
         assert np.allclose(p1.pos, p0.pos, rtol=1e-6, atol=1e-6) and np.allclose(p1.vel, p0.vel, rtol=1e-6, atol=1e-8)
         # recently released particles linger near the progenitor and feel it: the stream must differ
         assert np.abs(s1.pos - s0.pos).max() > 1e-3
+
+
+@pytest.mark.parametrize("integ", ["dopri853", "leapfrog"])
+def test_nbody_reorder_sixteen_bodies(ref, integ):
+    """tests/dynamics/nbody/test_nbody.py:233-258 (test_nbody_reorder): 16 bodies, about half of them massive
+    Hernquist spheres scattered through the list, in a Hernquist halo.  The first saved row is the input in
+    the caller's order, and every test particle equals the reference run lane by lane ([massive..., it])."""
+    N = 16
+    rng = np.random.default_rng(seed=42)
+    w0 = np.vstack([rng.normal(0, 5, size=(3, N)), rng.normal(0, 50, size=(3, N)) * KMS])
+    # softening 50 pc instead of the reference test's 1 pc: that test only asserts the FIRST row; here the
+    # trajectories themselves are compared, so close passages must stay resolvable in 100 steps of 1 Myr
+    pots = [gb.HernquistPotential(m=1e9, c=0.05) if rng.uniform() > 0.5 else None for _ in range(N)]
+    ext = gb.HernquistPotential(m=1e12, c=10.0)
+    sim = DirectNBody(gb.PhaseSpacePosition.from_w(w0), pots, external_potential=ext)
+    assert 4 < sim.n_massive <= 16
+    t = np.arange(0, 101.0)
+    orb = sim.integrate_orbit(t=t, Integrator=integ)
+    assert np.allclose(orb.pos[:, 0], w0[:3], rtol=0, atol=0)              # test_nbody_reorder's assertion
+    got = np.vstack([orb.pos, orb.vel])                                    # (6, ntimes, N)
+    massive = [i for i, p in enumerate(pots) if p is not None]
+    tests_ = [i for i, p in enumerate(pots) if p is None]
+    pps = [pots[i] for i in massive]
+    H = sim.H
+    rows_b = w0[:, massive].T
+    worst = 0.0
+    for i in tests_:
+        rows = np.vstack([rows_b, w0[:, i:i + 1].T])
+        if integ == "leapfrog":
+            fin, traj = ref.nbody_leapfrog(H, pps, rows, t[0], len(t) - 1, 1.0, save_all=True)
+        else:
+            fin, traj, rc = ref.nbody_dop853(H, pps, rows, tgrid=t, mode=0, save_all=True)
+            assert rc >= 0
+        d = relnorm(got[:, :, i], traj[:, -1, :].T)
+        worst = max(worst, np.median(d))
+        # the massive bodies as integrated by the lane that writes them
+        if i == tests_[0]:
+            db = relnorm(got[:, -1, massive], traj[-1, :len(massive), :].T)
+            assert db.max() < 1e-8
+    print(f"\n[nbody reorder, {sim.n_massive} massive of 16, {integ}] worst per-particle median over time = {worst:.2e}")
+    assert worst < 1e-10
