@@ -81,6 +81,9 @@ SIGNATURES = {
     "gb_mockstream_dop853": (C.c_int, [P(gb_potential), P(gb_frame), C.c_void_p, C.c_void_p, C.c_size_t,
                                        C.c_double, C.c_double, C.c_double, C.c_double, C.c_long, C.c_void_p,
                                        C.c_void_p, P(gb_launch)]),
+    "gb_mockstream_dop853_animate": (C.c_int, [P(gb_potential), P(gb_frame), C.c_void_p, C.c_void_p, C.c_size_t,
+                                               C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_long, C.c_int,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, P(gb_launch)]),
     "gb_mockstream_leapfrog": (C.c_int, [P(gb_potential), C.c_void_p, C.c_void_p, C.c_size_t, C.c_double,
                                          C.c_double, C.c_void_p, P(gb_launch)]),
     "gb_nbody_leapfrog": (C.c_int, [P(gb_potential), P(gb_bodies), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,

@@ -798,6 +798,18 @@ int gb_dop853(const gb_potential* pot, const gb_frame* fr, const double* w0, siz
     return 0;
 }
 
+struct DevTmp {                      // stream-ordered device temporary with optional H2D fill
+    void* p = nullptr; cudaStream_t s = nullptr;
+    cudaError_t put(const void* host, size_t bytes, cudaStream_t st) {
+        s = st;
+        cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 8, s);
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        if (host && bytes) e = cudaMemcpyAsync(p, host, bytes, cudaMemcpyHostToDevice, s);
+        return e;
+    }
+    ~DevTmp() { if (p) cudaFreeAsync(p, s); }
+};
+
 int gb_stream_release(const gb_potential* pot, double G, const double* prog_w, const double* prog_t,
                       const double* prog_m, int ntimes, const int32_t* prog_idx, const double* sign,
                       const double* draws, int ncols, size_t Np, int df_kind, int flags, double* stream_w0,
@@ -866,6 +878,48 @@ int gb_mockstream_dop853(const gb_potential* pot, const gb_frame* fr, const doub
     return 0;
 }
 
+int gb_mockstream_dop853_animate(const gb_potential* pot, const gb_frame* fr, const double* w0_rows,
+                                 const int32_t* release_idx, size_t Np, const double* t, int ntimes, double atol,
+                                 double rtol, long nmax, int output_every, double* snapshots, double* final_w,
+                                 int32_t* status, const gb_launch* opt) {
+    Ctx c; RET_IF(open_ctx(opt, c));
+    if (!c.host) return fail(-12, "gb_mockstream_dop853_animate takes host buffers");
+    if (ntimes < 2 || !t) return fail(-12, "the time grid needs at least 2 entries");
+    if (output_every < 1) return fail(-12, "output_every must be >= 1");
+    if (Np && (!w0_rows || !release_idx || !snapshots || !final_w)) return fail(-12, "null data pointer");
+    RET_IF(pool_keep());
+    DevFrame F; RET_IF(resolve_frame(fr, F));
+    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    int nout = (ntimes - 1) / output_every + 1;
+    if ((ntimes - 1) % output_every != 0) nout += 1;                  // mockstream.pyx:360-363
+    Dop853Args a;
+    RET_IF(dop853_defaults(a, atol, rtol, nmax, 0.0, 1, 0.0, t[1] - t[0]));   // dop853_step's settings
+    DevTmp dw0, dri, dtg, dsn, dou, dst;
+    CU(dw0.put(w0_rows, Np * 6 * sizeof(double), c.stream));
+    CU(dri.put(release_idx, Np * sizeof(int32_t), c.stream));
+    CU(dtg.put(t, (size_t)ntimes * sizeof(double), c.stream));
+    const size_t sb = (size_t)nout * Np * 6 * sizeof(double);
+    CU(dsn.put(nullptr, sb, c.stream));
+    CU(dou.put(nullptr, Np * 6 * sizeof(double), c.stream));
+    CU(dst.put(nullptr, (Np ? Np : 1) * sizeof(int32_t), c.stream));
+    cudaError_t e = KCALL(c, mock_dop853_animate, r.P, F, (const double*)dw0.p, (const int32_t*)dri.p, Np,
+                          (const double*)dtg.p, ntimes, a, output_every, (double*)dsn.p, (double*)dou.p,
+                          (int32_t*)dst.p, c.block, c.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "mock_dop853_animate launch");
+    if (Np) g_launches++;
+    std::vector<int32_t> hs(Np);
+    if (Np) {
+        CU(cudaMemcpyAsync(snapshots, dsn.p, sb, cudaMemcpyDeviceToHost, c.stream));
+        CU(cudaMemcpyAsync(final_w, dou.p, Np * 6 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        CU(cudaMemcpyAsync(hs.data(), dst.p, Np * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+    }
+    CU(cudaStreamSynchronize(c.stream));
+    int worst = 0;
+    for (size_t i = 0; i < Np; i++) { if (hs[i] < worst) worst = hs[i]; if (status) status[i] = hs[i]; }
+    if (worst < 0) return fail(worst, "Integration failed with code " + std::to_string(worst));
+    return 0;
+}
+
 int gb_mockstream_leapfrog(const gb_potential* pot, const double* stream_w0, const double* t1, size_t Np,
                            double tfinal, double dt, double* stream_w, const gb_launch* opt) {
     Ctx c; RET_IF(open_ctx(opt, c));
@@ -919,17 +973,6 @@ static int resolve_bodies(const gb_bodies* bodies, DevBodies& B) {
     return 0;
 }
 
-struct DevTmp {                      // stream-ordered device temporary with optional H2D fill
-    void* p = nullptr; cudaStream_t s = nullptr;
-    cudaError_t put(const void* host, size_t bytes, cudaStream_t st) {
-        s = st;
-        cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 8, s);
-        if (e != cudaSuccess) { p = nullptr; return e; }
-        if (host && bytes) e = cudaMemcpyAsync(p, host, bytes, cudaMemcpyHostToDevice, s);
-        return e;
-    }
-    ~DevTmp() { if (p) cudaFreeAsync(p, s); }
-};
 
 int gb_nbody_leapfrog(const gb_potential* pot, const gb_bodies* bodies, const double* body_w0, int ngroups,
                       const int32_t* group, const double* w0_rows, const double* t1, size_t Np, double t0,

@@ -346,6 +346,20 @@ cudaError_t mock_dop853(const DevPot& P, const DevFrame& F, const double* w0_row
     return cudaGetLastError();
 }
 
+cudaError_t mock_dop853_animate(const DevPot& P, const DevFrame& F, const double* w0_rows, const int32_t* ridx,
+                                size_t Np, const double* t, int ntimes, const Dop853Args& a, int output_every,
+                                double* snap, double* out_rows, int32_t* status, int block, cudaStream_t s) {
+    if (Np == 0) return cudaSuccess;
+    if (block > 128 || block <= 0) block = 64;
+    const bool rot = F.type != GB_FRAME_STATIC;
+    if (rot) {
+        GB_SIG_SWITCH(P.sig, (k_mock_dop853_animate<C, true><<<nblocks(Np, block), block, 0, s>>>(P, F, a, w0_rows, ridx, Np, t, ntimes, output_every, snap, out_rows, status)));
+    } else {
+        GB_SIG_SWITCH(P.sig, (k_mock_dop853_animate<C, false><<<nblocks(Np, block), block, 0, s>>>(P, F, a, w0_rows, ridx, Np, t, ntimes, output_every, snap, out_rows, status)));
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t mock_leapfrog(const DevPot& P, const double* w0_rows, const double* t1, size_t Np, double tfinal,
                           double dt, double* out_rows, int block, cudaStream_t s) {
     if (Np == 0) return cudaSuccess;

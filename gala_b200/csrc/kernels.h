@@ -59,6 +59,10 @@ struct Dop853Args {
     cudaError_t mock_dop853(const DevPot& P, const DevFrame& F, const double* w0_rows, const double* t1,  \
                             size_t Np, double tfinal, const Dop853Args& a, double* out_rows,               \
                             int32_t* status, int block, cudaStream_t s);                                   \
+    cudaError_t mock_dop853_animate(const DevPot& P, const DevFrame& F, const double* w0_rows,            \
+                                    const int32_t* ridx, size_t Np, const double* t, int ntimes,           \
+                                    const Dop853Args& a, int output_every, double* snap, double* out_rows, \
+                                    int32_t* status, int block, cudaStream_t s);                           \
     cudaError_t mock_leapfrog(const DevPot& P, const double* w0_rows, const double* t1, size_t Np,        \
                               double tfinal, double dt, double* out_rows, int block, cudaStream_t s);      \
     cudaError_t nbody_leapfrog(const DevPot& P, const DevBodies& B, int scheme, const double* cs,          \

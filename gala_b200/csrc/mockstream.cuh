@@ -125,6 +125,47 @@ k_mock_dop853(const __grid_constant__ DevPot P, const __grid_constant__ DevFrame
     if (status) status[p] = code;
 }
 
+// mockstream_dop853_animate without massive bodies (mockstream.pyx:306-440): the stream is marched over the
+// caller's time grid one interval at a time -- every interval is a fresh dop853_step call (initial step dt0
+// again, dop853.pyx:27-75) -- and the state of every released particle is stored every `output_every`
+// intervals (and at the end).  ridx[p] = index of particle p's release time in t; before that its snapshot
+// rows are NaN (the HDF5 fill value, mockstream.pyx:133-140).  snap rows: (nout, Np, 6).
+template <class C, bool ROT>
+__global__ void __launch_bounds__(128)
+k_mock_dop853_animate(const __grid_constant__ DevPot P, const __grid_constant__ DevFrame F,
+                      const __grid_constant__ Dop853Args a, const double* __restrict__ w0,
+                      const int32_t* __restrict__ ridx, size_t Np, const double* __restrict__ t, int ntimes,
+                      int output_every, double* __restrict__ snap, double* __restrict__ out,
+                      int32_t* __restrict__ status) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Np) return;
+    double y[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) y[k] = w0[p * 6 + k];
+    auto rhs = [&](double tt, const double (&w)[6], double (&f)[6]) { ham_rhs<C, ROT>(P, F, tt, w, f); };
+    auto emit = [&](int, const double (&)[6]) {};
+    const int k0 = ridx[p];
+    const double nan = CUDART_NAN;
+    int code = 1, j = 0;
+    auto store = [&](int jj, bool live) {
+        double* o = snap + ((size_t)jj * Np + p) * 6;
+#pragma unroll
+        for (int k = 0; k < 6; k++) o[k] = live ? y[k] : nan;
+    };
+    store(0, k0 == 0);
+    for (int i = 1; i < ntimes; i++) {
+        if (i > k0 && code > 0) {
+            int out_idx = 0, nstep, naccpt, nrejct, nfcn;
+            code = dop853_integrate<false>(rhs, emit, a, t[i - 1], t[i], y, a.h0, nullptr, 0, out_idx, nstep, naccpt,
+                                           nrejct, nfcn);
+        }
+        if ((i % output_every) == 0 || i == ntimes - 1) { j++; store(j, i >= k0 && code > 0); }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) out[p * 6 + k] = y[k];
+    if (status) status[p] = code;
+}
+
 // mockstream_leapfrog without massive bodies (mockstream.pyx:556-590 with c_init_velocity_nbody /
 // c_leapfrog_step_nbody, integrate/cyintegrators/leapfrog.pyx:126-158).
 template <class C>

@@ -24,7 +24,7 @@ from .integrate import (DOPRI853Integrator, LeapfrogIntegrator, dop853_integrate
 from .units import strip
 
 __all__ = ["BaseStreamDF", "FardalStreamDF", "StreaklineStreamDF", "LagrangeCloudStreamDF", "ChenStreamDF",
-           "MockStreamGenerator", "DirectNBody", "mockstream_dop853", "mockstream_leapfrog"]
+           "MockStreamGenerator", "DirectNBody", "mockstream_dop853", "mockstream_leapfrog", "mockstream_dop853_animate"]
 
 
 def _opts(H):
@@ -393,6 +393,89 @@ def mockstream_dop853(nbody, time, stream_w0, stream_t1, tfinal, nstream, atol=1
     return out[Np:].copy(), out[:Np].copy()
 
 
+def _write_snapshots(filename, overwrite, groups, units_name):
+    """The reference's on-disk layout (mockstream.pyx:107-173): groups ``stream`` / ``nbody`` with datasets
+    ``pos``, ``vel`` of shape (3, n_out, n) and ``time``.  HDF5 (gzip-9, NaN fill value, ``unit`` attributes)
+    when h5py is importable; otherwise the same arrays go to ``<filename>.npz`` under the keys
+    ``stream/pos`` ... ``nbody/time`` (this image has no h5py)."""
+    import os
+    try:
+        import h5py
+    except ImportError:
+        h5py = None
+    target = str(filename) if h5py is not None else str(filename) + ".npz"
+    if os.path.exists(target) and not overwrite:
+        raise IOError(f"Mockstream output file {target} already exists! Use overwrite=True to overwrite the file.")
+    if h5py is None:
+        np.savez_compressed(target, **{f"{g}/{k}": v for g, d in groups.items() for k, v in d.items()})
+        return target
+    with h5py.File(target, "w") as f:
+        for g, d in groups.items():
+            grp = f.create_group(g)
+            for k, v in d.items():
+                if k == "time":
+                    ds = grp.create_dataset(k, data=v)
+                else:
+                    ds = grp.create_dataset(k, data=v, dtype="f8", fillvalue=np.nan, compression="gzip", compression_opts=9)
+                ds.attrs["unit"] = units_name.get(k, "")
+    return target
+
+
+def mockstream_dop853_animate(nbody, t, stream_w0, nstream, output_every=1, output_filename="", overwrite=False,
+                              check_filesize=True, atol=1e-10, rtol=1e-10, nmax=0, dt_max=0.0, nstiff=-1, progress=0,
+                              err_if_fail=1, log_output=0):
+    """``mockstream.pyx:306-440``: march the stream over ``t`` interval by interval, storing a snapshot every
+    ``output_every`` intervals (and the final state) in ``output_filename``.  Returns
+    ``(nbody_w (nbodies,6), stream_w (Np,6))`` like the reference; the snapshot arrays are also kept on the
+    function object as ``mockstream_dop853_animate.last`` (dict of the two groups).  Massless bodies only."""
+    import warnings
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    stream_w0 = np.ascontiguousarray(stream_w0, dtype=np.float64)
+    nstream = np.asarray(nstream)
+    ntimes = t.shape[0]
+    if nstream.shape[0] != ntimes:
+        raise ValueError("nstream must have one entry per time")
+    if stream_w0.shape != (int(nstream.sum()), 6):
+        raise ValueError("stream_w0 must have shape (sum(nstream), 6)")
+    if nbody.n_massive:
+        raise NotImplementedError("snapshot output with massive bodies is not implemented on the B200 engine")
+    H = nbody.H
+    nbodies = nbody._c_w0.shape[0]
+    Np = stream_w0.shape[0]
+    nout = (ntimes - 1) // output_every + 1 + (1 if (ntimes - 1) % output_every else 0)
+    if Np * nout * 8 >= 8e9 and check_filesize:
+        warnings.warn("Estimated mockstream output file is expected to be >8 GB in size! If you're sure, turn this "
+                      "warning off with `check_filesize=False`")
+    rows = np.vstack([nbody._c_w0, stream_w0])
+    ridx = np.concatenate([np.zeros(nbodies, dtype=np.int32), np.repeat(np.arange(ntimes, dtype=np.int32), nstream)])
+    snap = np.empty((nout, rows.shape[0], 6))
+    fin = np.empty_like(rows)
+    status = np.empty(rows.shape[0], dtype=np.int32)
+    opt = _opts(H)
+    fr = H.frame.spec()
+    rc = _abi.lib().gb_mockstream_dop853_animate(H.potential.spec().ptr(), C.byref(fr), rows.ctypes.data, ridx.ctypes.data,
+                                                 rows.shape[0], t.ctypes.data, ntimes, float(atol), float(rtol), int(nmax),
+                                                 int(output_every), snap.ctypes.data, fin.ctypes.data, status.ctypes.data,
+                                                 C.byref(opt))
+    if rc in (-1, -2, -3, -4):
+        if err_if_fail:
+            _abi.check(rc)
+    else:
+        _abi.check(rc)
+    out_i = [i for i in range(ntimes) if i == 0 or i % output_every == 0 or i == ntimes - 1]
+    times = t[out_i]
+    sw = snap.transpose(2, 0, 1)                                    # (6, nout, n)
+    groups = {"stream": {"pos": np.ascontiguousarray(sw[:3, :, nbodies:]), "vel": np.ascontiguousarray(sw[3:, :, nbodies:]),
+                         "time": times},
+              "nbody": {"pos": np.ascontiguousarray(sw[:3, :, :nbodies]), "vel": np.ascontiguousarray(sw[3:, :, :nbodies]),
+                        "time": times}}
+    mockstream_dop853_animate.last = groups
+    if output_filename:
+        mockstream_dop853_animate.last_file = _write_snapshots(output_filename, overwrite, groups,
+                                                               {"pos": "kpc", "vel": "kpc / Myr", "time": "Myr"})
+    return fin[:nbodies].copy(), fin[nbodies:].copy()
+
+
 def mockstream_leapfrog(nbody, full_time, spawn_time, stream_w0, stream_t1, tfinal, nstream, progress=0,
                         err_if_fail=1):
     """``mockstream.pyx:442-620``: fixed-step version; particle p takes
@@ -493,8 +576,6 @@ class MockStreamGenerator:
             output_filename=None, check_filesize=True, overwrite=False, progress=False, Integrator=None,
             Integrator_kwargs=None, **time_spec):
         """``mockstream_generator.py:119-372``.  Returns ``(stream: MockStream, prog: PhaseSpacePosition)``."""
-        if output_every is not None:
-            raise NotImplementedError("snapshot output (output_every) is not implemented")
         Integrator_kwargs = dict(Integrator_kwargs or {})
         Integrator = get_integrator(Integrator or DOPRI853Integrator)
         units = self.hamiltonian.units
@@ -522,10 +603,19 @@ class MockStreamGenerator:
         if 0 not in nstream_idx:
             nstream_idx = np.insert(nstream_idx, 0, 0)
             unq_t1s = np.insert(unq_t1s, 0, orbit_t[0])
-        if Integrator is DOPRI853Integrator:
+        if output_every is not None and output_filename is None:
+            raise ValueError("If output_every is specified, you must also pass in a filename to store the snapshots in")
+        if Integrator is DOPRI853Integrator and output_every is not None:
+            raw_nbody, raw_stream = mockstream_dop853_animate(nbody0, orbit_t, w0, all_nstream.astype("i4"),
+                                                              output_every=output_every, output_filename=output_filename,
+                                                              check_filesize=check_filesize, overwrite=overwrite,
+                                                              progress=int(progress), **Integrator_kwargs)
+        elif Integrator is DOPRI853Integrator:
             raw_nbody, raw_stream = mockstream_dop853(nbody0, orbit_t[nstream_idx], w0, unq_t1s, orbit_t[-1],
                                                       all_nstream[nstream_idx].astype("i4"), progress=int(progress),
                                                       **Integrator_kwargs)
+        elif Integrator is LeapfrogIntegrator and output_every is not None:
+            raise NotImplementedError("Animation output for LeapfrogIntegrator is not implemented")
         elif Integrator is LeapfrogIntegrator:
             raw_nbody, raw_stream = mockstream_leapfrog(nbody0, orbit_t, orbit_t[nstream_idx], w0, unq_t1s,
                                                         orbit_t[-1], all_nstream[nstream_idx].astype("i4"),

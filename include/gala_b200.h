@@ -208,6 +208,17 @@ int gb_mockstream_leapfrog(const gb_potential* pot,
                            double tfinal, double dt,
                            double* stream_w, const gb_launch* opt);
 
+/* mockstream_dop853_animate (dynamics/mockstream/mockstream.pyx:306-440), no massive bodies: the released
+ * particles are marched over the time grid t interval by interval (one dop853_step call per interval, initial
+ * step t[1]-t[0] each time) and stored every `output_every` intervals and at the end.  release_idx[p] = index
+ * in t of particle p's release time.  snapshots: (nout, Np, 6) rows with
+ * nout = (ntimes-1)/output_every + 1 (+1 when the last interval is not a multiple, :360-363); NaN before release. */
+int gb_mockstream_dop853_animate(const gb_potential* pot, const gb_frame* fr,
+                                 const double* w0_rows /* (Np,6) */, const int32_t* release_idx, size_t Np,
+                                 const double* t, int ntimes, double atol, double rtol, long nmax,
+                                 int output_every, double* snapshots, double* final_w /* (Np,6) */,
+                                 int32_t* status, const gb_launch* opt);
+
 /* ---- massive bodies (direct N-body) --------------------------------------------------
  * Replaces, for systems of a few massive bodies plus any number of TEST particles:
  *   leapfrog_integrate_nbody   integrate/cyintegrators/leapfrog.pyx:161-257

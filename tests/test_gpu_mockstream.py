@@ -142,3 +142,55 @@ def test_mockstream_leapfrog_parity(ref):
     gen2 = gb.MockStreamGenerator(gb.FardalStreamDF(gala_modified=True, random_state=np.random.RandomState(1)), H)
     s2, _ = gen2.run(PROG_W0, 2.5e4, dt=-1.0, n_steps=150, n_particles=2)
     assert np.mean(np.sqrt(((s2.pos - stream.pos) ** 2).sum(0))) < 2.0
+
+
+def test_mockstream_animate_snapshots(ref, tmp_path):
+    """mockstream_dop853_animate (mockstream.pyx:306-440) through MockStreamGenerator.run(output_every=...):
+    snapshot bookkeeping (count, times, NaN before release, first appearance = the release state) and every
+    particle's march -- one dop853_step call per interval -- against the compiled reference."""
+    pot = gb.MilkyWayPotential2022()
+    H = gb.Hamiltonian(pot)
+    fn = tmp_path / "snaps.hdf5"
+    n_steps, oe = 40, 6
+    gen = gb.MockStreamGenerator(gb.FardalStreamDF(gala_modified=True, random_state=np.random.RandomState(42)), H)
+    stream, prog = gen.run(PROG_W0, 2.5e4, dt=1.0, n_steps=n_steps, n_particles=1, release_every=2,
+                           output_every=oe, output_filename=str(fn))
+    from gala_b200.mockstream import mockstream_dop853_animate
+    snaps = mockstream_dop853_animate.last
+    import os
+    assert os.path.exists(mockstream_dop853_animate.last_file)
+    out_i = [i for i in range(n_steps + 1) if i % oe == 0 or i == n_steps]
+    assert snaps["stream"]["pos"].shape == (3, len(out_i), stream.pos.shape[1])
+    assert np.allclose(snaps["stream"]["time"], np.array(out_i, dtype=float))
+    t = np.arange(n_steps + 1.0)
+    rel = np.asarray(stream.release_time)
+    w_snap = np.concatenate([snaps["stream"]["pos"], snaps["stream"]["vel"]])        # (6, nout, Np)
+    # same ICs again (same seed) for the reference march
+    orb, _ = _prog_orbit(H, n_steps, dt=1.0)
+    prog_orb = gb.Orbit(pos=orb.pos[:, :, 0], vel=orb.vel[:, :, 0], t=t, hamiltonian=H)
+    s0 = gb.FardalStreamDF(gala_modified=True, random_state=np.random.RandomState(42)).sample(
+        prog_orb, 2.5e4, n_particles=1, release_every=2)
+    w0 = np.vstack([s0.pos, s0.vel]).T
+    for p in range(0, w0.shape[0], 3):
+        k0 = int(round(rel[p]))
+        y = w0[p:p + 1].copy()
+        j = 0
+        assert np.all(np.isnan(w_snap[:, 0, p])) == (k0 > 0)
+        for i in range(1, n_steps + 1):
+            if i > k0:
+                y, st, rc = ref.dop853_step_rows(H, y, t[i - 1], t[i], 1.0, group=True)
+                assert rc >= 0
+            if i % oe == 0 or i == n_steps:
+                j += 1
+                if i < k0:
+                    assert np.all(np.isnan(w_snap[:, j, p]))
+                else:
+                    assert np.allclose(w_snap[:, j, p], y[0], rtol=1e-11, atol=1e-13), (p, i)
+        assert np.allclose(np.concatenate([stream.pos[:, p], stream.vel[:, p]]), y[0], rtol=1e-11, atol=1e-13)
+    # the progenitor's snapshots follow its orbit
+    assert np.allclose(snaps["nbody"]["pos"][:, -1, 0], prog.pos.ravel())
+    with pytest.raises(IOError):
+        gen.run(PROG_W0, 2.5e4, dt=1.0, n_steps=4, n_particles=1, output_every=2, output_filename=str(fn))
+    with pytest.raises(NotImplementedError):
+        gen.run(PROG_W0, 2.5e4, dt=1.0, n_steps=4, n_particles=1, output_every=2, output_filename=str(fn),
+                Integrator="leapfrog", overwrite=True)
