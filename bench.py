@@ -35,7 +35,8 @@ sys.path.insert(0, ROOT)
 SM_FILL = 148 * 2048          # resident threads of one B200 at full occupancy
 
 # algorithmic flops per orbit-step (source-level op counts)
-FLOPS = {"headline": 146, "c1": 46, "c4": 666, "c2": 3970, "c5": 3400, "c3": 146, "c3d": 0}
+FLOPS = {"headline": 146, "c1": 46, "c4": 666, "c2": 3970, "c5": 3400, "c3": 146, "c3d": 0,
+         "c3sg": 2 * 146 + 20, "c3sgd": 0}      # self-gravity lane: progenitor + particle gradients + one Plummer term
 
 
 def make_ic(N, seed, pot_gradient, rmin=4.0, rmax=50.0):
@@ -105,7 +106,7 @@ def workload(name, n_orbits):
         def units(N_, out):
             ns = stats["nstep"]
             return int(ns.sum().item() if hasattr(ns, "cpu") else ns.sum())
-    elif name in ("c3", "c3d"):
+    elif name in ("c3", "c3d", "c3sg", "c3sgd"):
         # C3: 10^5-particle Fardal stream in MW2022 (tests/dynamics/mockstream/test_mockstream.py:676-678
         # progenitor); c3 = LeapfrogIntegrator (exact orbit-step count), c3d = DOPRI853 (reference default)
         H = gb.Hamiltonian(gb.MilkyWayPotential2022())
@@ -113,14 +114,20 @@ def workload(name, n_orbits):
         n_steps, n_part = 5000, 10
         t = np.arange(n_steps + 1) * -1.0
         N = 2 * n_part * (n_steps + 1)
-        integ = gb.LeapfrogIntegrator if name == "c3" else gb.DOPRI853Integrator
+        integ = gb.LeapfrogIntegrator if name in ("c3", "c3sg") else gb.DOPRI853Integrator
+        # c3sg / c3sgd: the same stream with the progenitor's own gravity (a 2.5e4 Msun Plummer sphere, b = 50 pc):
+        # every device lane integrates [progenitor, one particle] (csrc/nbody.cuh)
+        selfgrav = name in ("c3sg", "c3sgd")
         desc = (f"C3: FardalStreamDF(gala_modified, RandomState(42)) in MW2022, dt=-1Myr x {n_steps}, {n_part} particles "
-                f"per tail per step = {N} particles, {integ.__name__}, whole MockStreamGenerator.run per step")
+                f"per tail per step = {N} particles, {integ.__name__}, "
+                f"{'progenitor self-gravity (Plummer 2.5e4 Msun, b=50pc), ' if selfgrav else ''}"
+                f"whole MockStreamGenerator.run per step")
 
         def run(w0, tt, out=None):
-            gen = gb.MockStreamGenerator(gb.FardalStreamDF(gala_modified=True, random_state=np.random.RandomState(42)), H)
+            gen = gb.MockStreamGenerator(gb.FardalStreamDF(gala_modified=True, random_state=np.random.RandomState(42)), H,
+                                         progenitor_potential=gb.PlummerPotential(m=2.5e4, b=0.05) if selfgrav else None)
             stream, _ = gen.run(prog, 2.5e4, dt=-1.0, n_steps=n_steps, n_particles=n_part, release_every=1,
-                                Integrator=integ)
+                                Integrator=integ, Integrator_kwargs={"err_if_fail": 0} if integ is gb.DOPRI853Integrator else None)
             return stream.w()
 
         # fixed-step count: particle released at step k takes k steps (+ the progenitor orbit itself)
