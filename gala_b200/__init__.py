@@ -17,4 +17,6 @@ from .hamiltonian import Hamiltonian
 from .mockstream import (BaseStreamDF, FardalStreamDF, StreaklineStreamDF, LagrangeCloudStreamDF, ChenStreamDF,
                          MockStreamGenerator, DirectNBody, mockstream_dop853, mockstream_leapfrog)
 
+from .nonlinear import fast_lyapunov_max
+
 __version__ = "0.1.0"

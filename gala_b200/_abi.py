@@ -93,6 +93,9 @@ SIGNATURES = {
                                   C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double,
                                   C.c_double, C.c_long, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
                                   C.c_void_p, C.c_void_p, P(gb_launch)]),
+    "gb_lyapunov_max": (C.c_int, [P(gb_potential), P(gb_frame), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
+                                  C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_long, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, P(gb_launch)]),
     "gb_last_error": (C.c_char_p, []),
     "gb_device_count": (C.c_int, []),
     "gb_launch_count": (C.c_long, []),

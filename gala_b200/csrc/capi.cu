@@ -1059,4 +1059,47 @@ int gb_nbody_dop853(const gb_potential* pot, const gb_bodies* bodies, const doub
     return 0;
 }
 
+int gb_lyapunov_max(const gb_potential* pot, const gb_frame* fr, const double* w0_rows, const double* d0_vec, size_t N,
+                    const double* t, int n_steps, double d0, int n_steps_per_pullback, int noffset_orbits, double atol,
+                    double rtol, long nmax, double* LEs_raw, double* traj, int32_t* status, const gb_launch* opt) {
+    Ctx c; RET_IF(open_ctx(opt, c));
+    if (!c.host) return fail(-12, "gb_lyapunov_max takes host buffers");
+    if (n_steps < 2 || !t) return fail(-12, "the time grid needs at least 2 entries");
+    if (noffset_orbits < 1 || noffset_orbits > GB_MAXB) return fail(-12, "1..16 offset orbits per parent orbit");
+    if (n_steps_per_pullback < 1 || !(d0 > 0.)) return fail(-12, "n_steps_per_pullback >= 1 and d0 > 0 required");
+    if (N && (!w0_rows || !d0_vec || !LEs_raw)) return fail(-12, "null data pointer");
+    RET_IF(pool_keep());
+    DevFrame F; RET_IF(resolve_frame(fr, F));
+    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    Dop853Args a;
+    RET_IF(dop853_defaults(a, atol, rtol, nmax, 0.0, 1, 0.0, t[1] - t[0]));      // dop853_step (dop853.pyx:45-69)
+    const int norb = 1 + noffset_orbits, niter = n_steps / n_steps_per_pullback;
+    DevTmp dw0, dd0, dtg, dle, dtr, dst;
+    CU(dw0.put(w0_rows, N * 6 * sizeof(double), c.stream));
+    CU(dd0.put(d0_vec, N * (size_t)noffset_orbits * 6 * sizeof(double), c.stream));
+    CU(dtg.put(t, (size_t)n_steps * sizeof(double), c.stream));
+    const size_t lb = N * (size_t)niter * noffset_orbits * sizeof(double);
+    CU(dle.put(nullptr, lb, c.stream));
+    CU(cudaMemsetAsync(dle.p, 0, lb ? lb : 8, c.stream));                       // LEs = np.zeros (:44)
+    const size_t tb = traj ? N * (size_t)n_steps * norb * 6 * sizeof(double) : 0;
+    if (traj) { CU(dtr.put(nullptr, tb, c.stream)); CU(cudaMemsetAsync(dtr.p, 0, tb, c.stream)); }
+    CU(dst.put(nullptr, (N ? N : 1) * sizeof(int32_t), c.stream));
+    cudaError_t e = KCALL(c, lyapunov, r.P, F, a, (const double*)dw0.p, (const double*)dd0.p, N, (const double*)dtg.p,
+                          n_steps, d0, n_steps_per_pullback, noffset_orbits, (double*)dle.p, (double*)dtr.p,
+                          (int32_t*)dst.p, c.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "lyapunov launch");
+    if (N) g_launches++;
+    std::vector<int32_t> hs(N);
+    if (N) {
+        if (lb) CU(cudaMemcpyAsync(LEs_raw, dle.p, lb, cudaMemcpyDeviceToHost, c.stream));
+        if (traj) CU(cudaMemcpyAsync(traj, dtr.p, tb, cudaMemcpyDeviceToHost, c.stream));
+        CU(cudaMemcpyAsync(hs.data(), dst.p, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+    }
+    CU(cudaStreamSynchronize(c.stream));
+    int worst = 0;
+    for (size_t i = 0; i < N; i++) { if (hs[i] < worst) worst = hs[i]; if (status) status[i] = hs[i]; }
+    if (worst < 0) return fail(worst, "Integration failed with code " + std::to_string(worst));
+    return 0;
+}
+
 }  // extern "C"

@@ -28,6 +28,9 @@ namespace GB_NS {
 #if GB_PART == 5 || GB_PART == 6
 #include "nbody.cuh"
 #endif
+#if GB_PART == 6
+#include "lyapunov.cuh"
+#endif
 
 #if GB_PART == 1
 // ------------------------------------------------------------------------------------------------
@@ -448,6 +451,20 @@ cudaError_t GB_ND_NAME(const DevPot& P, const DevBodies& B, const Dop853Args& a,
 #undef GB_ND
     return cudaGetLastError();
 }
+#if GB_PART == 6
+cudaError_t lyapunov(const DevPot& P, const DevFrame& F, const Dop853Args& a, const double* w0, const double* d0_vec,
+                     size_t N, const double* t, int n_steps, double d0, int pullback, int noff, double* LEs, double* traj,
+                     int32_t* status, cudaStream_t s) {
+    if (N == 0) return cudaSuccess;
+    const int block = 64;
+    if (F.type != GB_FRAME_STATIC) {
+        GB_SIG_SWITCH2(P.sig, (k_lyapunov<C, true><<<nblocks(N, block), block, 0, s>>>(P, F, a, w0, d0_vec, N, t, n_steps, d0, pullback, noff, LEs, traj, status)));
+    } else {
+        GB_SIG_SWITCH2(P.sig, (k_lyapunov<C, false><<<nblocks(N, block), block, 0, s>>>(P, F, a, w0, d0_vec, N, t, n_steps, d0, pullback, noff, LEs, traj, status)));
+    }
+    return cudaGetLastError();
+}
+#endif
 #if GB_PART == 5
 cudaError_t nbody_dop853(const DevPot& P, const DevBodies& B, const Dop853Args& a, const double* body_w0,
                          const int32_t* group, const double* w0, const double* t1, size_t Np,

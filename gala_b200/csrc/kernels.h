@@ -76,6 +76,10 @@ struct Dop853Args {
                              const double* t1, size_t Np, const double* tgrid, int ntimes, double t0,      \
                              double tfinal, double* out_p, double* out_b, size_t body_writer,              \
                              double* traj, size_t ntot, int32_t* status, cudaStream_t s);                  \
+    cudaError_t lyapunov(const DevPot& P, const DevFrame& F, const Dop853Args& a, const double* w0,       \
+                         const double* d0_vec, size_t N, const double* t, int n_steps, double d0,          \
+                         int pullback, int noff, double* LEs, double* traj, int32_t* status,               \
+                         cudaStream_t s);                                                                  \
     cudaError_t fardal_release(const DevPot& P, double G, const double* prog_w, const double* prog_t,     \
                                const double* prog_m, int ntimes, const int32_t* prog_idx,                  \
                                const double* sign, const double* normals, int ncols, size_t Np, int kind, \

@@ -263,6 +263,18 @@ int gb_nbody_dop853(const gb_potential* pot, const gb_bodies* bodies,
                     double* out_particles, double* out_bodies, size_t body_writer,
                     double* traj, int32_t* status, const gb_launch* opt);
 
+/* ---- chaos indicators ----------------------------------------------------------------
+ * dop853_lyapunov_max(_dont_save) (dynamics/lyapunov/dop853_lyapunov.pyx:22-192) for N parent orbits at once
+ * (the reference takes one per call): lane p integrates parent orbit p and its offset orbits
+ * w0[p] + d0_vec[p][i] as one DOP853 system, interval by interval over t (dop853_step), and every
+ * n_steps_per_pullback intervals stores ln(|d1|/d0) per offset orbit in LEs_raw (N, n_steps / pullback, noff)
+ * and pulls the offset orbit back to distance d0.  traj: (N, n_steps, 1 + noff, 6) or NULL.  Host buffers. */
+int gb_lyapunov_max(const gb_potential* pot, const gb_frame* fr,
+                    const double* w0_rows /* (N,6) */, const double* d0_vec /* (N,noff,6) */, size_t N,
+                    const double* t, int n_steps, double d0, int n_steps_per_pullback, int noffset_orbits,
+                    double atol, double rtol, long nmax,
+                    double* LEs_raw, double* traj, int32_t* status, const gb_launch* opt);
+
 /* ---- misc ------------------------------------------------------------------------ */
 const char* gb_last_error(void);
 int  gb_device_count(void);

@@ -185,6 +185,20 @@ class _Lib:
                                       None if traj is None else traj.ctypes.data_as(C.c_void_p))
         return rows, traj, rc
 
+    def lyapunov(self, H, w0, d0_vec, t, d0, pullback, atol=1e-10, rtol=1e-10, nmax=0, save=False):
+        """dop853_lyapunov_max for ONE parent orbit: returns (LEs_raw (niter, noff), all_w | None, code)."""
+        w0 = _f64(w0); d0_vec = _f64(d0_vec); t = _f64(t)
+        noff = d0_vec.shape[0]; n_steps = t.size
+        LEs = np.zeros((n_steps // pullback, noff))
+        allw = np.zeros((n_steps, 1 + noff, 6)) if save else None
+        fr = H.frame.spec()
+        rc = self._fn("lyapunov")(H.potential.spec().ptr(), C.byref(fr), w0.ctypes.data_as(C.c_void_p),
+                                  d0_vec.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p), C.c_int(n_steps),
+                                  C.c_double(d0), C.c_int(pullback), C.c_int(noff), C.c_double(atol), C.c_double(rtol),
+                                  C.c_long(nmax), LEs.ctypes.data_as(C.c_void_p),
+                                  None if allw is None else allw.ctypes.data_as(C.c_void_p))
+        return LEs, allw, rc
+
     def d2_dr2(self, pot, q3, t=0.0):
         q3 = _f64(q3)
         return self._fn("d2_dr2", C.c_double)(pot.spec().ptr(), C.c_double(t), q3.ctypes.data_as(C.c_void_p))

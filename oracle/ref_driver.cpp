@@ -28,6 +28,9 @@
 
 extern void Fwrapper_T(unsigned full_ndim, double t, double *w, double *f, CPotential *p,
                        CFrameType *fr, unsigned norbits, unsigned na, void *args);
+extern void Fwrapper(unsigned full_ndim, double t, double *w, double *f, CPotential *p,
+                     CFrameType *fr, unsigned norbits, unsigned na, void *args);
+extern double six_norm(double *x);
 extern void Fwrapper_direct_nbody(unsigned full_ndim, double t, double *w, double *f,
                                   CPotential *p, CFrameType *fr, unsigned norbits,
                                   unsigned nbody, void *args);
@@ -385,6 +388,43 @@ int ref_dop853_step_rows(const gb_potential *spec, const gb_frame *fr, double *w
         if (res < worst) worst = res;
     }
     return worst;
+}
+
+// dop853_lyapunov_max (dynamics/lyapunov/dop853_lyapunov.pyx:22-118): parent orbit w0 + noff offset orbits
+// w0 + d0_vec[i] (already of length d0) advanced interval by interval with dop853_step's call
+// (integrate/cyintegrators/dop853.pyx:45-69) over F = Fwrapper, pulled back every `pullback` intervals.
+// LEs_raw (niter, noff) = ln(|d1|/d0); all_w (n_steps, 1+noff, 6) or NULL.  Returns the dop853 code.
+int ref_lyapunov(const gb_potential *spec, const gb_frame *fr, const double *w0, const double *d0_vec,
+                 const double *t, int n_steps, double d0, int pullback, int noff, double atol, double rtol,
+                 long nmax, double *LEs_raw, double *all_w) {
+    RefPotential rp; if (!build(spec, rp)) return -11;
+    RefFrame rf; build_frame(fr, rf);
+    const int norb = 1 + noff;
+    std::vector<double> w(6 * norb), d1(6);
+    for (int k = 0; k < 6; k++) w[k] = w0[k];
+    for (int i = 1; i < norb; i++)
+        for (int k = 0; k < 6; k++) w[6 * i + k] = w0[k] + d0_vec[(i - 1) * 6 + k];
+    if (all_w) memcpy(all_w, w.data(), 6 * norb * sizeof(double));
+    const double dt0 = t[1] - t[0];
+    int jiter = 0;
+    for (int j = 1; j < n_steps; j++) {
+        double rt = rtol, at = atol;
+        int res = dop853(6 * norb, (FcnEqDiff)Fwrapper, rp.cp, &rf.cf, norb, 0, NULL, t[j - 1], w.data(), t[j],
+                         &rt, &at, 0, NULL, 0, NULL, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, dt0, nmax, 0, 1, 0, NULL, 0,
+                         NULL, NULL, 0, NULL);
+        if (res < 0) return res;
+        if (all_w) memcpy(all_w + (size_t)j * 6 * norb, w.data(), 6 * norb * sizeof(double));
+        if ((j % pullback) == 0) {
+            for (int i = 1; i < norb; i++) {
+                for (int k = 0; k < 6; k++) d1[k] = w[6 * i + k] - w[k];
+                const double mag = six_norm(d1.data());
+                LEs_raw[jiter * noff + (i - 1)] = log(mag / d0);
+                for (int k = 0; k < 6; k++) w[6 * i + k] = w[k] + d0 * d1[k] / mag;
+            }
+            jiter++;
+        }
+    }
+    return 1;
 }
 
 // CPotentialWrapper.hessian (potential/potential/cpotential.pyx:164-182): c_hessian per point; q (3,N) SoA
