@@ -94,6 +94,29 @@ def _wrap(fn):
     return inner
 
 
+def adapt_nbody(nbody):
+    """gala ``DirectNBody`` (duck-typed: ``_c_w0`` (nbodies,6), ``particle_potentials``, ``H``) -> ours."""
+    if isinstance(nbody, _ms.DirectNBody):
+        return nbody
+    H = extract_hamiltonian(nbody.H)
+    pps = []
+    for pp in nbody.particle_potentials:
+        if pp is None or type(getattr(pp, "c_instance", None)).__name__ == "NullWrapper":
+            pps.append(None)
+        else:
+            pps.append(extract_potential(pp))
+    return _ms.DirectNBody(np.ascontiguousarray(np.asarray(nbody._c_w0, dtype=np.float64).T), pps,
+                           external_potential=H.potential, frame=H.frame)
+
+
+def _wrap_stream(fn):
+    def inner(nbody, *a, **kw):
+        return fn(adapt_nbody(nbody), *[np.asarray(x) if hasattr(x, "shape") else x for x in a], **kw)
+    inner.__name__ = fn.__name__
+    inner.__doc__ = fn.__doc__
+    return inner
+
+
 def install():
     """Swap gala's Cython boundary functions for the GPU-backed ones.  Raises ImportError if gala
     itself cannot be imported."""
@@ -107,4 +130,14 @@ def install():
     for name in ("leapfrog_integrate_hamiltonian", "ruth4_integrate_hamiltonian", "dop853_integrate_hamiltonian"):
         if hasattr(ch, name):       # chamiltonian.pyx imports them lazily inside integrate_orbit
             setattr(ch, name, _wrap(getattr(_integ, name)))
+    try:        # mock-stream boundary (dynamics/mockstream/mockstream.pyx:176-620)
+        import gala.dynamics.mockstream.mockstream as msx
+        import gala.dynamics.mockstream.mockstream_generator as msg
+        for name in ("mockstream_dop853", "mockstream_leapfrog", "mockstream_dop853_animate"):
+            w = _wrap_stream(getattr(_ms, name))
+            setattr(msx, name, w)
+            if hasattr(msg, name):
+                setattr(msg, name, w)
+    except ImportError:
+        pass
     return True

@@ -155,3 +155,61 @@ def test_shard_bounds_and_work_dealing():
     assert sorted(np.concatenate(parts)) == list(range(100))
     loads = [work[p].sum() for p in parts]
     assert max(loads) - min(loads) <= 100
+
+
+def test_gala_plugin_extracts_duck_typed_gala_objects():
+    """gala_plugin maps real gala objects to the C-ABI spec through exactly what the Cython code reads
+    (type(pot.c_instance).__name__, pot.G, pot.c_parameters, pot.origin, pot._R; frame.c_parameters;
+    cpotential.pyx:281-316, ccompositepotential.pyx:27-86, cframe.pyx:98-112).  gala itself is not importable
+    here, so stand-ins with the same attribute names are used."""
+    from collections import OrderedDict
+    from gala_b200 import gala_plugin as gp, _abi
+
+    def fake(wrapper_name, G, c_parameters, origin=(0, 0, 0), R=None):
+        W = type(wrapper_name, (), {})
+        return type("FakePot", (), {"c_instance": W(), "G": G, "c_parameters": np.asarray(c_parameters, float),
+                                    "origin": np.asarray(origin, float), "_R": R, "units": None})()
+
+    G = gb.G_GALACTIC
+    h = gp.extract_potential(fake("HernquistWrapper", G, [1e11, 0.5], origin=(1, 2, 3)))
+    mine = gb.HernquistPotential(m=1e11, c=0.5, origin=[1, 2, 3])
+    c0, c1 = h._components()[0], mine._components()[0]
+    assert c0[0] == c1[0] == _abi.POT_HERNQUIST and np.array_equal(c0[1], c1[1]) and np.array_equal(c0[2], c1[2])
+
+    class FakeComposite(OrderedDict):
+        c_instance = type("CCompositePotentialWrapper", (), {})()
+    comp = FakeComposite()
+    comp["disk"] = fake("MiyamotoNagaiWrapper", G, [6.8e10, 3.0, 0.28])
+    comp["halo"] = fake("LogarithmicWrapper", G, [0.2, 12.0, 1.38, 1.0, 1.36, 1.7])
+    out = gp.extract_potential(comp)
+    assert list(out.keys()) == ["disk", "halo"]
+    assert [c[0] for c in out._components()] == [_abi.POT_MIYAMOTONAGAI, _abi.POT_LOGARITHMIC]
+    with pytest.raises(TypeError):
+        gp.extract_potential(fake("CylSplineWrapper", G, [1.0]))
+    # every wrapper id of the header has an entry
+    assert set(gp.WRAPPER_TO_TYPE.values()) == set(range(21))
+
+    StaticW = type("StaticFrameWrapper", (), {})
+    RotW = type("ConstantRotatingFrameWrapper3D", (), {})
+    fs = type("F", (), {"c_instance": StaticW(), "c_parameters": np.zeros(0)})()
+    frw = type("F", (), {"c_instance": RotW(), "c_parameters": np.array([0.0, 0.0, 0.03])})()
+    assert isinstance(gp.extract_frame(fs), gb.StaticFrame)
+    rot = gp.extract_frame(frw)
+    assert isinstance(rot, gb.ConstantRotatingFrame) and np.allclose(rot.spec().omega[:], [0, 0, 0.03])
+    Hf = type("H", (), {"potential": comp, "frame": frw})()
+    H = gp.extract_hamiltonian(Hf)
+    assert isinstance(H, gb.Hamiltonian) and H.c_enabled
+
+
+def test_gala_plugin_adapts_nbody():
+    from gala_b200 import gala_plugin as gp
+    G = gb.G_GALACTIC
+    W = type("PlummerWrapper", (), {})
+    N = type("NullWrapper", (), {})
+    pp = type("P", (), {"c_instance": W(), "G": G, "c_parameters": np.array([1e9, 0.1]), "origin": np.zeros(3), "_R": None})()
+    nullp = type("P", (), {"c_instance": N(), "G": G, "c_parameters": np.zeros(0), "origin": np.zeros(3), "_R": None})()
+    Hf = type("H", (), {"potential": gb.MilkyWayPotential2022(), "frame": gb.StaticFrame()})()
+    nb = type("NB", (), {"_c_w0": np.arange(12.0).reshape(2, 6), "particle_potentials": [pp, nullp], "H": Hf})()
+    ours = gp.adapt_nbody(nb)
+    assert ours.n_massive == 1 and ours._c_w0.shape == (2, 6) and np.array_equal(ours._c_w0, nb._c_w0)
+    assert ours.particle_potentials[1] is None
