@@ -330,8 +330,11 @@ GB_DEV int dop853_integrate(const RHS& rhs, const OUT& emit, const Dop853Args& a
 // fully coalesced reads and writes.  (Writing (6,ntimes,N) directly from per-lane cursors cost 8x
 // the algorithmic DRAM traffic in the first version.)
 // ------------------------------------------------------------------------------------------------
+// Register budget (A/B on B200, 303,104 MW2022 orbits, profiles/c2_ab_r1.txt): the dense kernel is fastest
+// with the full 255 registers (2 CTAs of 128 per SM: 34.1 ms; capped at 168 registers / 3 CTAs: 34.8 ms, at
+// 128 / 4 CTAs: 38.9 ms); the final-state kernel gains from 3 CTAs per SM (14.5 -> 13.3 ms).
 template <class C, bool ROT, bool DENSE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(DENSE ? 256 : 128, DENSE ? 1 : 3)
 k_dop853_dyn(const __grid_constant__ DevPot P, const __grid_constant__ DevFrame F, const __grid_constant__ Dop853Args a,
              const double* __restrict__ w0, size_t N, const double* __restrict__ t, int ntimes,
              const uint32_t* __restrict__ perm, unsigned long long* __restrict__ queue,

@@ -307,7 +307,7 @@ cudaError_t GB_D8_NAME(const DevPot& P, const DevFrame& F, const double* w0, siz
     e = cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
     if (const char* eb = getenv("GB_D8_BLOCK")) block = atoi(eb);
-    if (block > 256 || block <= 0 || (block & 31)) block = 64;      // __launch_bounds__(256)
+    if (block > (save_all ? 256 : 128) || block <= 0 || (block & 31)) block = 64;      // __launch_bounds__ of k_dop853_dyn
     const char* bs = getenv("GB_D8_BLOCKSYNC");
     const int block_sync = bs ? atoi(bs) : (block > 32);
     if (save_all) {

@@ -16,7 +16,7 @@ bench)   for w in headline c1 c2 c4 c5; do
          done ;;
 launches) ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/launches_bench.log 2>&1 ;;
 ncu_lf)  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_leapfrog -s 3 -c 1 -o $OUT/prof_leapfrog -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_lf.log 2>&1; summ prof_leapfrog "ncu --set full --clock-control none, k_leapfrog<MW2022, final-state>, bench headline size ($TAG)" ;;
-ncu_d8)  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_dop853 -s 3 -c 1 -o $OUT/prof_dop853 -f python bench.py --workload c2 --orbits 75776 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_d8.log 2>&1; summ prof_dop853 "ncu --set full --clock-control none, k_dop853_dyn<MW2022, static, dense>, 75,776 orbits x 1000 output times ($TAG)" ;;
+ncu_d8)  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_dop853 -s 3 -c 1 -o $OUT/prof_dop853 -f python bench.py --workload c2 --orbits ${D8_ORBITS:-75776} --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_d8.log 2>&1; summ prof_dop853 "ncu --set full --clock-control none, k_dop853_dyn<MW2022, static, dense>, 75,776 orbits x 1000 output times ($TAG)" ;;
 ncu_r4)  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_ruth4 -s 3 -c 1 -o $OUT/prof_ruth4 -f python bench.py --workload c4 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_r4.log 2>&1; summ prof_ruth4 "ncu --set full --clock-control none, k_ruth4<bar+MW2022, rotating, final-state>, C4 bench size ($TAG)" ;;
 ncu_scf) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_leapfrog -s 3 -c 1 -o $OUT/prof_scf -f python bench.py --workload c5 --orbits 303104 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_scf.log 2>&1; summ prof_scf "ncu --set full --clock-control none, k_leapfrog<SCF(10,6), final-state>, 303,104 orbits x 1000 steps ($TAG)" ;;
 c2ab)    for v in sort nosort; do
