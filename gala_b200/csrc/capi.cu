@@ -204,8 +204,16 @@ int resolve(const gb_potential* pot, Resolved& r, cudaStream_t stream) {
     else if (sig_matches(pot, {GB_POT_MN3, GB_POT_HERNQUIST, GB_POT_HERNQUIST, GB_POT_NFW_SPHERICAL})) P.sig = SIG_MW2022;
     else if (sig_matches(pot, {GB_POT_LONGMURALIBAR, GB_POT_MN3, GB_POT_HERNQUIST, GB_POT_HERNQUIST, GB_POT_NFW_SPHERICAL})) P.sig = SIG_BAR_MW2022;
     else if (sig_matches(pot, {GB_POT_MN3, GB_POT_HERNQUIST, GB_POT_HERNQUIST, GB_POT_NFW_SPHERICAL, GB_POT_LONGMURALIBAR})) P.sig = SIG_MW2022_BAR;
+    else if (sig_matches(pot, {GB_POT_MIYAMOTONAGAI, GB_POT_HERNQUIST, GB_POT_HERNQUIST, GB_POT_NFW_SPHERICAL})) P.sig = SIG_MW_V1;
+    else if (sig_matches(pot, {GB_POT_MIYAMOTONAGAI, GB_POT_HERNQUIST, GB_POT_LOGARITHMIC})) P.sig = SIG_LM10;
+    else if (sig_matches(pot, {GB_POT_MIYAMOTONAGAI, GB_POT_POWERLAWCUTOFF, GB_POT_NFW_SPHERICAL})) P.sig = SIG_BOVY2014;
     else if (pot->n_components == 1 && pot->comp[0].type_id == GB_POT_SCF && !pot->comp[0].do_shift_rotate) P.sig = SIG_SCF;
     if (getenv("GB_FORCE_GENERIC")) P.sig = SIG_GENERIC;
+    if (P.sig == SIG_GENERIC && !getenv("GB_FORCE_GENERIC_HEAVY")) {
+        bool heavy = false;
+        for (int i = 0; i < P.n; i++) heavy |= (P.c[i].type == GB_POT_SCF || P.c[i].type == GB_POT_MULTIPOLE);
+        if (!heavy) P.sig = SIG_GENERIC_LIGHT;
+    }
     if (P.sig == SIG_SCF && !getenv("GB_SCF_NO_CONST")) {
         // small expansions also go to the constant bank in the fixed (10,6) layout of scf_fast_gradient
         const double* p = pot->comp[0].params;

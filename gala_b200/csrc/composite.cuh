@@ -41,47 +41,52 @@ template <> struct PotOf<GB_POT_POWERLAWCUTOFF>{ using type = PotPowerLawCutoff;
     X(GB_POT_ISOCHRONE) X(GB_POT_JAFFE) X(GB_POT_STONE) X(GB_POT_BURKERT) X(GB_POT_SATOH) X(GB_POT_KUZMIN) \
     X(GB_POT_LOGARITHMIC) X(GB_POT_LEESUTO) X(GB_POT_POWERLAWCUTOFF)
 
+// HEAVY = false leaves the basis-function expansions (SCF, multipole: 255 registers, 1.7 KB of stack) out of
+// the switch: a kernel instantiated that way keeps the register budget of the analytic potentials.
+template <bool HEAVY = true>
 GB_DEV void gb_comp_gradient(int type, const double* p, const double* e, double x, double y, double z,
                              double& gx, double& gy, double& gz) {
     switch (type) {
 #define X(T) case T: PotOf<T>::type::gradient(p, x, y, z, gx, gy, gz); break;
         GB_FOR_EACH_SIMPLE_TYPE(X)
 #undef X
-        case GB_POT_SCF: PotSCF::gradient(p, e, x, y, z, gx, gy, gz); break;
-        case GB_POT_MULTIPOLE: PotMultipole::gradient(p, e, x, y, z, gx, gy, gz); break;
+        case GB_POT_SCF: if constexpr (HEAVY) PotSCF::gradient(p, e, x, y, z, gx, gy, gz); break;
+        case GB_POT_MULTIPOLE: if constexpr (HEAVY) PotMultipole::gradient(p, e, x, y, z, gx, gy, gz); break;
         default: break;
     }
 }
 #if !GB_STRICT
-template <class Ctx>
+template <bool HEAVY = true, class Ctx>
 GB_DEV void gb_comp_accum(int type, const double* p, const double* d, const double* e, Ctx& c) {
     switch (type) {
 #define X(T) case T: PotOf<T>::type::accum(p, d, c); break;
         GB_FOR_EACH_SIMPLE_TYPE(X)
 #undef X
-        case GB_POT_SCF: PotSCF::gradient(p, e, c.x, c.y, c.z, c.gx, c.gy, c.gz); break;
-        case GB_POT_MULTIPOLE: PotMultipole::gradient(p, e, c.x, c.y, c.z, c.gx, c.gy, c.gz); break;
+        case GB_POT_SCF: if constexpr (HEAVY) PotSCF::gradient(p, e, c.x, c.y, c.z, c.gx, c.gy, c.gz); break;
+        case GB_POT_MULTIPOLE: if constexpr (HEAVY) PotMultipole::gradient(p, e, c.x, c.y, c.z, c.gx, c.gy, c.gz); break;
         default: break;
     }
 }
 #endif
+template <bool HEAVY = true>
 GB_DEV double gb_comp_value(int type, const double* p, const double* e, double x, double y, double z) {
     switch (type) {
 #define X(T) case T: return PotOf<T>::type::value(p, x, y, z);
         GB_FOR_EACH_SIMPLE_TYPE(X)
 #undef X
-        case GB_POT_SCF: return PotSCF::value(p, e, x, y, z);
-        case GB_POT_MULTIPOLE: return PotMultipole::value(p, e, x, y, z);
+        case GB_POT_SCF: if constexpr (HEAVY) return PotSCF::value(p, e, x, y, z); else return 0.;
+        case GB_POT_MULTIPOLE: if constexpr (HEAVY) return PotMultipole::value(p, e, x, y, z); else return 0.;
         default: return 0.;
     }
 }
+template <bool HEAVY = true>
 GB_DEV double gb_comp_density(int type, const double* p, const double* e, double x, double y, double z) {
     switch (type) {
 #define X(T) case T: return PotOf<T>::type::density(p, x, y, z);
         GB_FOR_EACH_SIMPLE_TYPE(X)
 #undef X
-        case GB_POT_SCF: return PotSCF::density(p, e, x, y, z);
-        case GB_POT_MULTIPOLE: return PotMultipole::density(p, e, x, y, z);
+        case GB_POT_SCF: if constexpr (HEAVY) return PotSCF::density(p, e, x, y, z); else return 0.;
+        case GB_POT_MULTIPOLE: if constexpr (HEAVY) return PotMultipole::density(p, e, x, y, z); else return 0.;
         default: return 0.;
     }
 }
@@ -96,7 +101,10 @@ GB_DEV void gb_shift_rotate(const DevComp& c, double x, double y, double z, doub
 
 template <int SIG> struct Composite;
 
-template <> struct Composite<SIG_GENERIC> {
+template <bool HEAVY> struct CompositeGeneric {
+    // the adaptive integrator evaluates the gradient at 15-17 sites per step: ONE out-of-line copy of this
+    // loop-and-switch per kernel instead of 17 inlined ones (hamiltonian.cuh: ham_rhs)
+    static constexpr bool kOutOfLineInRhs = true;
     GB_DEV static void gradient(const DevPot& P, double t, double x, double y, double z,
                                 double& gx, double& gy, double& gz) {
 #if GB_STRICT
@@ -106,11 +114,11 @@ template <> struct Composite<SIG_GENERIC> {
             const double* p = &P.par[c.poff];
             const double* e = P.ext + c.eoff;
             if (!c.shift) {
-                gb_comp_gradient(c.type, p, e, x, y, z, gx, gy, gz);
+                gb_comp_gradient<HEAVY>(c.type, p, e, x, y, z, gx, gy, gz);
             } else {
                 double X, Y, Z, ax = 0., ay = 0., az = 0.;
                 gb_shift_rotate(c, x, y, z, X, Y, Z);
-                gb_comp_gradient(c.type, p, e, X, Y, Z, ax, ay, az);
+                gb_comp_gradient<HEAVY>(c.type, p, e, X, Y, Z, ax, ay, az);
                 // rotate back with R^T and accumulate (cpotential.cpp:263-277)
                 gx += c.R[0] * ax + c.R[3] * ay + c.R[6] * az;
                 gy += c.R[1] * ax + c.R[4] * ay + c.R[7] * az;
@@ -127,12 +135,12 @@ template <> struct Composite<SIG_GENERIC> {
             const double* d = &P.drv[c.doff];
             const double* e = P.ext + c.eoff;
             if (!c.shift) {
-                gb_comp_accum(c.type, p, d, e, ctx);
+                gb_comp_accum<HEAVY>(c.type, p, d, e, ctx);
             } else {
                 double X, Y, Z, ax, ay, az;
                 gb_shift_rotate(c, x, y, z, X, Y, Z);
                 FastCtx<GB_USE_ALL> c2(X, Y, Z);
-                gb_comp_accum(c.type, p, d, e, c2);
+                gb_comp_accum<HEAVY>(c.type, p, d, e, c2);
                 c2.finish(ax, ay, az);
                 ctx.gx += c.R[0] * ax + c.R[3] * ay + c.R[6] * az;
                 ctx.gy += c.R[1] * ax + c.R[4] * ay + c.R[7] * az;
@@ -148,7 +156,7 @@ template <> struct Composite<SIG_GENERIC> {
             const DevComp& c = P.c[i];
             double X = x, Y = y, Z = z;
             if (c.shift) gb_shift_rotate(c, x, y, z, X, Y, Z);
-            v = v + gb_comp_value(c.type, &P.par[c.poff], P.ext + c.eoff, X, Y, Z);
+            v = v + gb_comp_value<HEAVY>(c.type, &P.par[c.poff], P.ext + c.eoff, X, Y, Z);
         }
         return v;
     }
@@ -158,11 +166,13 @@ template <> struct Composite<SIG_GENERIC> {
             const DevComp& c = P.c[i];
             double X = x, Y = y, Z = z;
             if (c.shift) gb_shift_rotate(c, x, y, z, X, Y, Z);
-            v = v + gb_comp_density(c.type, &P.par[c.poff], P.ext + c.eoff, X, Y, Z);
+            v = v + gb_comp_density<HEAVY>(c.type, &P.par[c.poff], P.ext + c.eoff, X, Y, Z);
         }
         return v;
     }
 };
+template <> struct Composite<SIG_GENERIC> : CompositeGeneric<true> {};
+template <> struct Composite<SIG_GENERIC_LIGHT> : CompositeGeneric<false> {};
 
 // ---- compile-time component lists ------------------------------------------------------------
 template <int OFF, int DOFF, int... Ts> struct SeqImpl;
@@ -198,6 +208,7 @@ template <int OFF, int DOFF, int T0, int... Ts> struct SeqImpl<OFF, DOFF, T0, Ts
     }
 };
 template <int... Ts> struct Seq {
+    static constexpr bool kOutOfLineInRhs = false;
     GB_DEV static void gradient(const DevPot& P, double t, double x, double y, double z,
                                 double& gx, double& gy, double& gz) {
 #if GB_STRICT
@@ -222,7 +233,11 @@ template <> struct Composite<SIG_HERNQUIST>  : Seq<GB_POT_HERNQUIST> {};
 template <> struct Composite<SIG_MW2022>     : Seq<GB_POT_MN3, GB_POT_HERNQUIST, GB_POT_HERNQUIST, GB_POT_NFW_SPHERICAL> {};
 template <> struct Composite<SIG_BAR_MW2022> : Seq<GB_POT_LONGMURALIBAR, GB_POT_MN3, GB_POT_HERNQUIST, GB_POT_HERNQUIST, GB_POT_NFW_SPHERICAL> {};
 template <> struct Composite<SIG_MW2022_BAR> : Seq<GB_POT_MN3, GB_POT_HERNQUIST, GB_POT_HERNQUIST, GB_POT_NFW_SPHERICAL, GB_POT_LONGMURALIBAR> {};
+template <> struct Composite<SIG_MW_V1>      : Seq<GB_POT_MIYAMOTONAGAI, GB_POT_HERNQUIST, GB_POT_HERNQUIST, GB_POT_NFW_SPHERICAL> {};
+template <> struct Composite<SIG_LM10>       : Seq<GB_POT_MIYAMOTONAGAI, GB_POT_HERNQUIST, GB_POT_LOGARITHMIC> {};
+template <> struct Composite<SIG_BOVY2014>   : Seq<GB_POT_MIYAMOTONAGAI, GB_POT_POWERLAWCUTOFF, GB_POT_NFW_SPHERICAL> {};
 template <> struct Composite<SIG_SCF> {
+    static constexpr bool kOutOfLineInRhs = true;
     GB_DEV static void gradient(const DevPot& P, double t, double x, double y, double z, double& gx, double& gy, double& gz) {
 #if !GB_STRICT
         if (P.cext_ok) { scf_fast_gradient(P, &P.drv[0], x, y, z, gx, gy, gz); return; }   // warp-uniform

@@ -73,6 +73,10 @@ enum GbSig {
     SIG_BAR_MW2022,     // [LongMuraliBar, MN3, Hernquist, Hernquist, SphericalNFW]
     SIG_MW2022_BAR,     // [MN3, Hernquist, Hernquist, SphericalNFW, LongMuraliBar]
     SIG_SCF,            // [SCF]
+    SIG_MW_V1,          // [MiyamotoNagai, Hernquist, Hernquist, SphericalNFW]   MilkyWayPotential v1 (special.py:88-124)
+    SIG_LM10,           // [MiyamotoNagai, Hernquist, Logarithmic]               LM10Potential (special.py:26-87)
+    SIG_BOVY2014,       // [MiyamotoNagai, PowerLawCutoff, SphericalNFW]         BovyMWPotential2014 (special.py:274-347)
+    SIG_GENERIC_LIGHT,  // any list of analytic components (no SCF / multipole): the generic loop at their register budget
     SIG_COUNT
 };
 

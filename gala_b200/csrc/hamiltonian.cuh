@@ -35,7 +35,8 @@ GB_DEV void ham_rhs(const DevPot& P, const DevFrame& F, double t, const double (
 #ifdef GB_RHS_NOINLINE
     gradient_call<C>(P, t, w[0], w[1], w[2], gx, gy, gz);
 #else
-    C::gradient(P, t, w[0], w[1], w[2], gx, gy, gz);
+    if constexpr (C::kOutOfLineInRhs) gradient_call<C>(P, t, w[0], w[1], w[2], gx, gy, gz);
+    else C::gradient(P, t, w[0], w[1], w[2], gx, gy, gz);
 #endif
     if (!ROT) {
         f[0] = w[3]; f[1] = w[4]; f[2] = w[5];

@@ -201,6 +201,10 @@ static inline unsigned nblocks(size_t N, int block) { return (unsigned)((N + blo
         case SIG_BAR_MW2022: { using C = Composite<SIG_BAR_MW2022>; CALL; } break; \
         case SIG_MW2022_BAR: { using C = Composite<SIG_MW2022_BAR>; CALL; } break; \
         case SIG_SCF:        { using C = Composite<SIG_SCF>;        CALL; } break; \
+        case SIG_MW_V1:      { using C = Composite<SIG_MW_V1>;      CALL; } break; \
+        case SIG_LM10:       { using C = Composite<SIG_LM10>;       CALL; } break; \
+        case SIG_BOVY2014:   { using C = Composite<SIG_BOVY2014>;   CALL; } break; \
+        case SIG_GENERIC_LIGHT: { using C = Composite<SIG_GENERIC_LIGHT>; CALL; } break; \
         default:             { using C = Composite<SIG_GENERIC>;    CALL; } break; \
     }
 
@@ -387,12 +391,13 @@ cudaError_t eval_hessian(const DevPot& P, const double* q, size_t N, double* hes
 #endif  // GB_PART == 4
 
 #if GB_PART == 5 || GB_PART == 6
-// Two composite forms are instantiated for the N-body kernels: the compile-time MW2022 list and the
-// generic loop (which evaluates any component list).
+// Three composite forms are instantiated for the N-body kernels: the compile-time MW2022 list, the generic
+// loop over analytic components, and the generic loop that also knows the basis-function expansions.
 #define GB_SIG_SWITCH2(sig, CALL)                                 \
     switch (sig) {                                                \
         case SIG_MW2022:     { using C = Composite<SIG_MW2022>;     CALL; } break; \
-        default:             { using C = Composite<SIG_GENERIC>;    CALL; } break; \
+        case SIG_GENERIC: case SIG_SCF: { using C = Composite<SIG_GENERIC>; CALL; } break; \
+        default:             { using C = Composite<SIG_GENERIC_LIGHT>; CALL; } break; \
     }
 #if GB_PART == 5
 cudaError_t nbody_leapfrog(const DevPot& P, const DevBodies& B, int scheme, const double* cs, const double* ds,

@@ -157,16 +157,36 @@ def test_c5_scf_leapfrog(ref):
     pot.strict_math = False
 
 
-def test_generic_equals_specialised(monkeypatch):
-    """The compile-time composite (SIG_MW2022) and the generic switch loop give identical bits in
-    strict mode (same operation order, no contraction)."""
-    pot = POTS["mw2022"]; pot.strict_math = True
+@pytest.mark.parametrize("name", ["mw2022", "mw_v1", "lm10", "bovy2014", "bar_mw2022", "nfw", "hernquist"])
+def test_generic_equals_specialised(monkeypatch, ref, name):
+    """The compile-time composites (SIG_MW2022, SIG_MW_V1, SIG_LM10, SIG_BOVY2014, ...) and the two generic
+    switch loops (analytic-only = "light", and the one that also carries SCF / multipole) give identical
+    bits in strict mode (same operation order, no contraction), for evaluation and through 200 leapfrog and
+    40 Ruth4 steps; the fast builds of all three agree with the reference."""
+    pot = POTS[name]; pot.strict_math = True
+    H = gb.Hamiltonian(pot)
     q = np.random.default_rng(3).normal(0, 10.0, (3, 1000))
-    g1 = pot.gradient(q)
+    w0 = make_ic(lambda qq: ref.gradient(pot, qq), 256, seed=12, rmin=8.0)
+    t = np.arange(201.0)
+
+    def run():
+        return (pot.gradient(q), gb.leapfrog_integrate_hamiltonian(H, w0, t, save_all=0)[1],
+                gb.ruth4_integrate_hamiltonian(H, w0, t[:41], save_all=0)[1])
+    a = run()
     monkeypatch.setenv("GB_FORCE_GENERIC", "1")
-    g2 = pot.gradient(q)
+    b = run()
+    monkeypatch.setenv("GB_FORCE_GENERIC_HEAVY", "1")
+    c = run()
     pot.strict_math = False
-    assert np.array_equal(g1, g2)
+    for x, y, z in zip(a, b, c):
+        assert np.array_equal(x, y) and np.array_equal(x, z)
+    wr = ref.leapfrog(pot, w0, t, save_all=False)
+    for env in ({"GB_FORCE_GENERIC": "1", "GB_FORCE_GENERIC_HEAVY": "1"}, {"GB_FORCE_GENERIC": "1"}, {}):
+        monkeypatch.delenv("GB_FORCE_GENERIC", raising=False); monkeypatch.delenv("GB_FORCE_GENERIC_HEAVY", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        d = relnorm(gb.leapfrog_integrate_hamiltonian(H, w0, t, save_all=0)[1], wr)
+        assert np.median(d) < 1e-13 and d.max() < 1e-9, (name, env, d.max())
 
 
 def test_hamiltonian_energy_gradient(ref):
