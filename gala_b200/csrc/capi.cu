@@ -77,6 +77,11 @@ void gb_derive(int type, const double* p, double* d) {
             d[0] = p[0] * p[1]; d[1] = sin(p[5]); d[2] = cos(p[5]); d[3] = p[4] * p[4]; break;
         case GB_POT_SCF:
             d[0] = p[0] * p[3] / (p[4] * p[4]); d[1] = 1. / p[4]; break;
+        case GB_POT_LOGARITHMIC:
+            d[0] = p[1] * p[1]; d[1] = p[2] * p[2]; d[2] = 1. / (p[3] * p[3]); d[3] = 1. / (p[4] * p[4]);
+            d[4] = 1. / (p[5] * p[5]); d[5] = sin(p[6]); d[6] = cos(p[6]); break;
+        case GB_POT_POWERLAWCUTOFF:
+            d[0] = p[0] * p[1]; d[1] = lgamma(0.5 * (3. - p[2])); d[2] = 1. / (p[3] * p[3]); break;
         default: break;
     }
 }
@@ -162,6 +167,8 @@ int resolve(const gb_potential* pot, Resolved& r, cudaStream_t stream) {
         }
         if (c.n_params < min_npar(c.type_id) || (c.n_params > 0 && !c.params))
             return fail(-12, "component " + std::to_string(i) + ": too few parameters for its type");
+        if (c.type_id == GB_POT_POWERLAWCUTOFF && !(c.params[2] < 3.))
+            return fail(-12, "PowerLawCutoff: alpha must be < 3 (gsl_sf_gamma_inc_P needs a > 0)");
         DevComp& d = P.c[i];
         d.type = c.type_id;
         d.shift = c.do_shift_rotate ? 1 : 0;

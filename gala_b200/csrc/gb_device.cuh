@@ -84,7 +84,8 @@ enum GbSig {
 // fast build's accum() functions in potentials.cuh; the strict build ignores them):
 //   Hernquist/Kepler/Jaffe [G m] ; NFW spherical [G m, 1/r_s] ; MiyamotoNagai/Plummer/Isochrone [G m, b^2] ;
 //   MN3 [G m1, G m2, G m3, b1^2, b2^2, b3^2] ; LongMuraliBar [G m, sin(alpha), cos(alpha), c^2] ;
-//   SCF [G m / r_s^2, 1 / r_s].
+//   SCF [G m / r_s^2, 1 / r_s] ; PowerLawCutoff [G m, lgamma((3-alpha)/2), 1/r_c^2] ;
+//   Logarithmic [v_c^2, r_h^2, 1/q1^2, 1/q2^2, 1/q3^2, sin(phi), cos(phi)].
 constexpr int gb_nderived(int type) {
     return (type == GB_POT_HERNQUIST || type == GB_POT_KEPLER || type == GB_POT_JAFFE) ? 1
          : (type == GB_POT_NFW_SPHERICAL || type == GB_POT_MIYAMOTONAGAI || type == GB_POT_PLUMMER ||
@@ -92,6 +93,8 @@ constexpr int gb_nderived(int type) {
          : (type == GB_POT_MN3) ? 6
          : (type == GB_POT_LONGMURALIBAR) ? 4
          : (type == GB_POT_SCF) ? 2
+         : (type == GB_POT_POWERLAWCUTOFF) ? 3
+         : (type == GB_POT_LOGARITHMIC) ? 7
          : 0;
 }
 

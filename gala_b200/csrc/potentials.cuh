@@ -573,7 +573,20 @@ struct PotLogarithmic {
         const double den = t10 + t3;
         return p[1] * p[1] * (t2 * (t10 - t3) + t5 * (t11 - t6 + t8) + t7 * (t11 + t6 - t8)) / (den * den) / (4 * GB_PI * p[0]);
     }
-    GB_ACCUM_VIA_GRADIENT
+    #if !GB_STRICT
+    static constexpr int USE = GB_USE_GEN;
+    // d = [v_c^2, r_h^2, 1/q1^2, 1/q2^2, 1/q3^2, sin(phi), cos(phi)]: one reciprocal instead of seven divisions
+    template <class Ctx> GB_DEV static void accum(const double*, const double* d, Ctx& c) {
+        const double sp = d[5], cp = d[6];
+        const double X = fma(c.y, sp, c.x * cp), Y = fma(c.y, cp, -(c.x * sp));
+        const double Xi = X * d[2], Yi = Y * d[3], zi = c.z * d[4];
+        const double f = d[0] * gb_rcp(fma(X, Xi, fma(Y, Yi, fma(c.z, zi, d[1]))));
+        const double ax = f * Xi, ay = f * Yi;
+        c.gx += fma(ax, cp, -(ay * sp));
+        c.gy += fma(ax, sp, ay * cp);
+        c.gz = fma(f, zi, c.gz);
+    }
+#endif
 };
 
 // ---- Lee & Suto 2003 triaxial NFW (builtin_potentials.cpp:1446-1558): [G, v_c, r_s, a, b, c] ----
@@ -681,6 +694,38 @@ GB_DEV double gb_safe_gamma_inc(double a, double x) {
     }
     return (B + gb_gamma_inc_P(a + N, x) * tgamma(a + N)) / A;
 }
+#if !GB_STRICT
+// fast build: lgamma(a) comes from the host (a is a parameter), reciprocals from the seed+refine primitive,
+// and P = 1 to within 3e-17 once x > 40 (Q(a,x) < x^(a-1) e^-x / Gamma(a), a <= 1.5)
+GB_DEV double gb_gamma_inc_P_fast(double a, double x, double lgam_a) {
+    if (!(x > 0.)) return 0.;
+    if (x > 40.) return 1.;
+    const double lead = exp(a * log(x) - x - lgam_a);
+    if (x < a + 1.) {
+        double ap = a, del = gb_rcp(a), sum = del;
+        for (int n = 0; n < 200; n++) {
+            ap += 1.;
+            del *= x * gb_rcp(ap);
+            sum += del;
+            if (del < sum * 1e-17) break;
+        }
+        return sum * lead;
+    }
+    const double tiny = 1e-300;
+    double b = x + 1. - a, c = 1. / tiny, d = gb_rcp(b), h = d;
+    for (int i = 1; i < 200; i++) {
+        const double an = -(double)i * ((double)i - a);
+        b += 2.;
+        d = fma(an, d, b); if (fabs(d) < tiny) d = tiny;
+        c = fma(an, gb_rcp(c), b); if (fabs(c) < tiny) c = tiny;
+        d = gb_rcp(d);
+        const double del = d * c;
+        h *= del;
+        if (fabs(del - 1.) < 1e-16) break;
+    }
+    return fma(-lead, h, 1.);
+}
+#endif
 struct PotPowerLawCutoff {
     GB_DEV static void gradient(const double* p, double x, double y, double z, double& gx, double& gy, double& gz) {
         const double r = gb_norm3(x, y, z);
@@ -705,5 +750,12 @@ struct PotPowerLawCutoff {
         const double A = p[1] / (2 * GB_PI) * pow(p[3], p[2] - 3) / tgamma(0.5 * (3 - p[2]));
         return A * pow(r, -p[2]) * exp(-r * r / (p[3] * p[3]));
     }
-    GB_ACCUM_VIA_GRADIENT
+    #if !GB_STRICT
+    static constexpr int USE = GB_USE_SIR;
+    // d = [G m, lgamma((3-alpha)/2), 1/r_c^2]
+    template <class Ctx> GB_DEV static void accum(const double* p, const double* d, Ctx& c) {
+        const double P = gb_gamma_inc_P_fast(0.5 * (3 - p[2]), c.r2 * d[2], d[1]);
+        c.Sir = fma(d[0] * P, c.ir * c.ir, c.Sir);              // G m P(a, r^2/r_c^2) / r^3
+    }
+#endif
 };
