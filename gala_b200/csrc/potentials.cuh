@@ -721,7 +721,7 @@ GB_DEV double gb_gamma_inc_P_fast(double a, double x, double lgam_a) {
         d = gb_rcp(d);
         const double del = d * c;
         h *= del;
-        if (fabs(del - 1.) < 1e-16) break;
+        if (fabs(del - 1.) < 2e-15) break;     // the reciprocal seeds carry 2 ulp: del never settles on exactly 1
     }
     return fma(-lead, h, 1.);
 }

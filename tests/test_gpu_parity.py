@@ -110,14 +110,16 @@ def test_gradient_energy_density(ref, name, strict):
     # multipole: same situation at lmax <= 5 (a handful of terms)
     gtol = 2e-11 if name.startswith("scf") else 1e-12 if name.startswith("multipole") else (5e-15 if strict else 2e-14)
     if name in ("powerlawcutoff", "bovy2014"):
-        gtol = 1e-13      # incomplete gamma function: series / continued fraction on both sides, different libm
+        gtol = 1e-13 if strict else 1e-12      # incomplete gamma function: series / continued fraction on both sides
     if name == "leesuto":
         gtol = 1e-11      # the reference's expanded polynomial form cancels ~3 digits (builtin_potentials.cpp:1518)
     assert np.max(np.sqrt(((g - g0) ** 2).sum(0)) / scale) < gtol
     e = pot.energy(q); e0 = ref.energy(pot, q)
     etol = 1e-11 if name.startswith("scf") else 1e-10 if name.startswith("multipole") else 1e-13
-    if name in ("powerlawcutoff", "bovy2014", "burkert", "leesuto"):
-        etol = 1e-11      # differences of O(1) terms (atan/log/gamma) that cancel at large or small radius
+    if name in ("powerlawcutoff", "bovy2014", "burkert", "leesuto", "lm10"):
+        # differences of O(1) terms (atan/log/gamma) that cancel at large or small radius; LM10: a positive
+        # logarithmic halo against a negative disc + bulge, the total passes through zero
+        etol = 1e-11
     assert rel(e, e0) < etol
     d0 = ref.density(pot, q)
     d = pot.density(q)
