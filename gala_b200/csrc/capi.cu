@@ -81,7 +81,8 @@ void gb_derive(int type, const double* p, double* d) {
             d[0] = p[1] * p[1]; d[1] = p[2] * p[2]; d[2] = 1. / (p[3] * p[3]); d[3] = 1. / (p[4] * p[4]);
             d[4] = 1. / (p[5] * p[5]); d[5] = sin(p[6]); d[6] = cos(p[6]); break;
         case GB_POT_POWERLAWCUTOFF:
-            d[0] = p[0] * p[1]; d[1] = lgamma(0.5 * (3. - p[2])); d[2] = 1. / (p[3] * p[3]); break;
+            d[0] = p[0] * p[1]; d[1] = lgamma(0.5 * (3. - p[2])); d[2] = 1. / (p[3] * p[3]); d[3] = 1. / p[3];
+            d[4] = 3. - p[2]; d[5] = -1.; break;     // d[5] = offset of the fit in ext (resolve()); < 0: no fit, use the series
         default: break;
     }
 }
@@ -132,6 +133,34 @@ void mp_pack(const double* params, int lmax, std::vector<double>& ext) {
             ext.push_back(params[6 + 2 * i] * nlm);
             ext.push_back(params[7 + 2 * i] * nlm);
         }
+}
+
+// PowerLawCutoff, fast build: Chebyshev fit of F(s) = gamma*(a, s^2) = P(a, s^2) / s^(2a) (Tricomi's entire
+// incomplete gamma function) on GB_PLC_NINT equal intervals of s in [0, GB_PLC_SMAX], degree GB_PLC_DEG.
+// F(s) = e^-x sum_n x^n / Gamma(a+n+1), x = s^2: all terms positive, summed in long double.
+void plc_pack(double a, std::vector<double>& ext) {
+    const int D = GB_PLC_DEG + 1;
+    const long double h = (long double)GB_PLC_SMAX / GB_PLC_NINT, pi = 3.14159265358979323846264338327950288L;
+    auto F = [&](long double sx) {
+        const long double x = sx * sx;
+        long double term = 1.0L / tgammal((long double)a + 1.0L), sum = term;
+        for (int n = 0; n < 2000; n++) {
+            term *= x / ((long double)a + n + 1.0L);
+            sum += term;
+            if (term < sum * 1e-22L) break;
+        }
+        return expl(-x) * sum;
+    };
+    for (int k = 0; k < GB_PLC_NINT; k++) {
+        const long double mid = (k + 0.5L) * h;
+        long double v[GB_PLC_DEG + 1];
+        for (int j = 0; j < D; j++) v[j] = F(mid + 0.5L * h * cosl(pi * (2 * j + 1) / (2.0L * D)));
+        for (int i = 0; i < D; i++) {
+            long double c = 0;
+            for (int j = 0; j < D; j++) c += v[j] * cosl(pi * i * (2 * j + 1) / (2.0L * D));
+            ext.push_back((double)(2.0L * c / D));
+        }
+    }
 }
 
 bool sig_matches(const gb_potential* pot, std::initializer_list<int> types) {
@@ -193,6 +222,11 @@ int resolve(const gb_potential* pot, Resolved& r, cudaStream_t stream) {
             d.eoff = (int)r.ext.size();
             mp_pack(c.params, lmax, r.ext);
         }
+        if (c.type_id == GB_POT_POWERLAWCUTOFF && !getenv("GB_PLC_NO_TABLE")) {
+            if (r.ext.size() & 1) r.ext.push_back(0.);
+            d.eoff = (int)r.ext.size();
+            plc_pack(0.5 * (3. - c.params[2]), r.ext);
+        }
         d.npar = nsmall;
         if (off + nsmall > GB_MAXP) return fail(-11, "too many potential parameters for the constant bank");
         for (int k = 0; k < nsmall; k++) P.par[off + k] = c.params[k];
@@ -200,6 +234,7 @@ int resolve(const gb_potential* pot, Resolved& r, cudaStream_t stream) {
         d.doff = doff;
         if (doff + gb_nderived(c.type_id) > GB_MAXD) return fail(-11, "too many potential components for the constant bank");
         gb_derive(c.type_id, c.params, &P.drv[doff]);
+        if (c.type_id == GB_POT_POWERLAWCUTOFF && !getenv("GB_PLC_NO_TABLE")) P.drv[doff + 5] = (double)d.eoff;
         doff += gb_nderived(c.type_id);
         for (int k = 0; k < 3; k++) d.q0[k] = c.q0[k];
         for (int k = 0; k < 9; k++) d.R[k] = c.R[k];

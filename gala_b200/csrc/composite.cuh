@@ -129,6 +129,7 @@ template <bool HEAVY> struct CompositeGeneric {
         // fast build: unshifted components share one evaluation context (r, 1/r computed once);
         // a shifted/rotated component gets its own context in its own coordinates.
         FastCtx<GB_USE_ALL> ctx(x, y, z);
+        ctx.ext = P.ext;
         for (int i = 0; i < P.n; i++) {
             const DevComp& c = P.c[i];
             const double* p = &P.par[c.poff];
@@ -140,6 +141,7 @@ template <bool HEAVY> struct CompositeGeneric {
                 double X, Y, Z, ax, ay, az;
                 gb_shift_rotate(c, x, y, z, X, Y, Z);
                 FastCtx<GB_USE_ALL> c2(X, Y, Z);
+                c2.ext = P.ext;
                 gb_comp_accum<HEAVY>(c.type, p, d, e, c2);
                 c2.finish(ax, ay, az);
                 ctx.gx += c.R[0] * ax + c.R[3] * ay + c.R[6] * az;
@@ -216,6 +218,7 @@ template <int... Ts> struct Seq {
         SeqImpl<0, 0, Ts...>::gradient(P, x, y, z, gx, gy, gz);
 #else
         FastCtx<SeqImpl<0, 0, Ts...>::USE> c(x, y, z);
+        c.ext = P.ext;
         SeqImpl<0, 0, Ts...>::accum(P, c);
         c.finish(gx, gy, gz);
 #endif

@@ -14,6 +14,9 @@
 #define GB_MAXC 8      // components per composite held in the constant bank
 #define GB_MAXP 120    // packed doubles of "small" parameters ([G, ...] of every component)
 #define GB_CEXT 616    // 2 x 11 x 28 doubles: (S,T) pairs of SCF(nmax=10,lmax=6), [l][m][n]
+#define GB_PLC_NINT 64   // PowerLawCutoff: Chebyshev fit of gamma*(a, s^2) on [0, GB_PLC_SMAX], s = r/r_c
+#define GB_PLC_DEG 9
+#define GB_PLC_SMAX 6.4
 #define GB_MAXD 40     // packed doubles of host-derived constants (G*m, b^2, 1/r_s, ...) for the fast build
 
 struct DevComp {
@@ -84,7 +87,7 @@ enum GbSig {
 // fast build's accum() functions in potentials.cuh; the strict build ignores them):
 //   Hernquist/Kepler/Jaffe [G m] ; NFW spherical [G m, 1/r_s] ; MiyamotoNagai/Plummer/Isochrone [G m, b^2] ;
 //   MN3 [G m1, G m2, G m3, b1^2, b2^2, b3^2] ; LongMuraliBar [G m, sin(alpha), cos(alpha), c^2] ;
-//   SCF [G m / r_s^2, 1 / r_s] ; PowerLawCutoff [G m, lgamma((3-alpha)/2), 1/r_c^2] ;
+//   SCF [G m / r_s^2, 1 / r_s] ; PowerLawCutoff [G m, lgamma(a), 1/r_c^2, 1/r_c, 2a, ext offset of the gamma* fit], a = (3-alpha)/2 ;
 //   Logarithmic [v_c^2, r_h^2, 1/q1^2, 1/q2^2, 1/q3^2, sin(phi), cos(phi)].
 constexpr int gb_nderived(int type) {
     return (type == GB_POT_HERNQUIST || type == GB_POT_KEPLER || type == GB_POT_JAFFE) ? 1
@@ -93,7 +96,7 @@ constexpr int gb_nderived(int type) {
          : (type == GB_POT_MN3) ? 6
          : (type == GB_POT_LONGMURALIBAR) ? 4
          : (type == GB_POT_SCF) ? 2
-         : (type == GB_POT_POWERLAWCUTOFF) ? 3
+         : (type == GB_POT_POWERLAWCUTOFF) ? 6
          : (type == GB_POT_LOGARITHMIC) ? 7
          : 0;
 }

@@ -27,6 +27,7 @@ enum { GB_USE_SIR = 1, GB_USE_FS = 2, GB_USE_DISC = 4, GB_USE_GEN = 8, GB_USE_AL
 template <int USE> struct FastCtx {
     double x, y, z, R2, z2, r2, ir, r;
     double Sir, Fs, Fd, Fdz, gx, gy, gz;
+    const double* ext = nullptr;    // DevPot::ext (device-global tables: the PowerLawCutoff fit); set by the composites
     GB_DEV FastCtx(double x_, double y_, double z_) : x(x_), y(y_), z(z_) {
         R2 = fma(y, y, x * x);
         z2 = z * z;
@@ -752,9 +753,31 @@ struct PotPowerLawCutoff {
     }
     #if !GB_STRICT
     static constexpr int USE = GB_USE_SIR;
-    // d = [G m, lgamma((3-alpha)/2), 1/r_c^2]
+    // d = [G m, lgamma(a), 1/r_c^2, 1/r_c, 2a, offset of the fit in DevPot::ext], a = (3-alpha)/2.
+    // P(a, x) = x^a gamma*(a, x) with Tricomi's entire function gamma*; the host fits F(s) = gamma*(a, s^2),
+    // s = r/r_c, by Chebyshev polynomials of degree GB_PLC_DEG on GB_PLC_NINT intervals of [0, GB_PLC_SMAX]
+    // (capi.cu:plc_pack; 2e-16 relative), so one evaluation is a 10-term Clenshaw sum + exp(2a ln s)
+    // instead of a 30-term series or continued fraction.  Beyond s = 6.4 (x = 41) P = 1 to 3e-17.
     template <class Ctx> GB_DEV static void accum(const double* p, const double* d, Ctx& c) {
-        const double P = gb_gamma_inc_P_fast(0.5 * (3 - p[2]), c.r2 * d[2], d[1]);
+        double P;
+        const double sr = c.r * d[3];
+        if (c.ext == nullptr || d[5] < 0.) {
+            P = gb_gamma_inc_P_fast(0.5 * (3 - p[2]), c.r2 * d[2], d[1]);
+        } else if (sr >= GB_PLC_SMAX) {
+            P = 1.;
+        } else {
+            const double* tab = c.ext + (int)d[5];
+            const double u = sr * (GB_PLC_NINT / GB_PLC_SMAX);
+            int k = (int)u;
+            k = k < GB_PLC_NINT ? k : GB_PLC_NINT - 1;
+            const double t = 2. * (u - (double)k) - 1.;
+            const double* co = tab + k * (GB_PLC_DEG + 1);
+            double b1 = 0., b2 = 0.;
+#pragma unroll
+            for (int i = GB_PLC_DEG; i >= 1; i--) { const double b0 = fma(2. * t, b1, co[i] - b2); b2 = b1; b1 = b0; }
+            const double F = fma(t, b1, 0.5 * co[0] - b2);
+            P = (sr > 0.) ? exp(d[4] * log(sr)) * F : 0.;
+        }
         c.Sir = fma(d[0] * P, c.ir * c.ir, c.Sir);              // G m P(a, r^2/r_c^2) / r^3
     }
 #endif
