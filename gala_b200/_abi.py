@@ -93,6 +93,9 @@ SIGNATURES = {
                                   C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double,
                                   C.c_double, C.c_long, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
                                   C.c_void_p, C.c_void_p, P(gb_launch)]),
+    "gb_nbody_dop853_animate": (C.c_int, [P(gb_potential), P(gb_bodies), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                          C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_long, C.c_int, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, P(gb_launch)]),
     "gb_lyapunov_max": (C.c_int, [P(gb_potential), P(gb_frame), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
                                   C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_long, C.c_void_p,
                                   C.c_void_p, C.c_void_p, P(gb_launch)]),

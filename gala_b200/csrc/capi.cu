@@ -1109,6 +1109,59 @@ int gb_nbody_dop853(const gb_potential* pot, const gb_bodies* bodies, const doub
     return 0;
 }
 
+int gb_nbody_dop853_animate(const gb_potential* pot, const gb_bodies* bodies, const double* body_w0,
+                            const double* w0_rows, const int32_t* release_idx, size_t Np, const double* t, int ntimes,
+                            double atol, double rtol, long nmax, int output_every, double* snapshots,
+                            double* out_particles, double* out_bodies, int32_t* status, const gb_launch* opt) {
+    Ctx c; RET_IF(open_ctx(opt, c));
+    if (!c.host) return fail(-12, "gb_nbody_dop853_animate takes host buffers");
+    if (ntimes < 2 || !t || !body_w0 || !snapshots) return fail(-12, "null data pointer / short time grid");
+    if (output_every < 1) return fail(-12, "output_every must be >= 1");
+    if (Np && (!w0_rows || !release_idx)) return fail(-12, "null data pointer");
+    RET_IF(pool_keep());
+    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    DevBodies B; RET_IF(resolve_bodies(bodies, B));
+    const size_t nb = B.nb, ntot = nb + Np;
+    int nout = (ntimes - 1) / output_every + 1;
+    if ((ntimes - 1) % output_every != 0) nout += 1;
+    Dop853Args a;
+    RET_IF(dop853_defaults(a, atol, rtol, nmax, 0.0, 1, 0.0, t[1] - t[0]));      // dop853_step's settings
+    // the lane of the last particle writes the bodies' end state (the reference's w[:nbodies] after the loop)
+    DevTmp dba, dw0, dri, dtg, dsn, dop, dob, dst;
+    CU(dba.put(nullptr, (size_t)ntimes * nb * 6 * sizeof(double), c.stream));
+    CU(cudaMemcpyAsync(dba.p, body_w0, nb * 6 * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    CU(dw0.put(w0_rows, Np * 6 * sizeof(double), c.stream));
+    CU(dri.put(release_idx, Np * sizeof(int32_t), c.stream));
+    CU(dtg.put(t, (size_t)ntimes * sizeof(double), c.stream));
+    const size_t sb = (size_t)nout * ntot * 6 * sizeof(double);
+    CU(dsn.put(nullptr, sb, c.stream));
+    CU(dop.put(nullptr, Np * 6 * sizeof(double), c.stream));
+    CU(dob.put(nullptr, nb * 6 * sizeof(double), c.stream));
+    const size_t nst = Np + 1;
+    CU(dst.put(nullptr, nst * sizeof(int32_t), c.stream));
+    cudaError_t e = KCALL(c, nbody_dop853_march, r.P, B, a, (double*)dba.p, nullptr, nullptr, Np, 0, (const double*)dtg.p,
+                          ntimes, output_every, (double*)dsn.p, nullptr, (double*)dob.p, 0, (int32_t*)dst.p + Np, c.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "nbody_dop853_march (bodies) launch");
+    g_launches++;
+    if (Np) {
+        e = KCALL(c, nbody_dop853_march, r.P, B, a, (double*)dba.p, (const double*)dw0.p, (const int32_t*)dri.p, Np, 1,
+                  (const double*)dtg.p, ntimes, output_every, (double*)dsn.p, (double*)dop.p, nullptr, 0,
+                  (int32_t*)dst.p, c.stream);
+        if (e != cudaSuccess) return cuda_fail(e, "nbody_dop853_march (particles) launch");
+        g_launches++;
+    }
+    std::vector<int32_t> hs(nst);
+    CU(cudaMemcpyAsync(snapshots, dsn.p, sb, cudaMemcpyDeviceToHost, c.stream));
+    if (Np && out_particles) CU(cudaMemcpyAsync(out_particles, dop.p, Np * 6 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    if (out_bodies) CU(cudaMemcpyAsync(out_bodies, dob.p, nb * 6 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    CU(cudaMemcpyAsync(hs.data(), dst.p, nst * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+    CU(cudaStreamSynchronize(c.stream));
+    int worst = 0;
+    for (size_t i = 0; i < nst; i++) { if (hs[i] < worst) worst = hs[i]; if (status && i < Np) status[i] = hs[i]; }
+    if (worst < 0) return fail(worst, "Integration failed with code " + std::to_string(worst));
+    return 0;
+}
+
 int gb_lyapunov_max(const gb_potential* pot, const gb_frame* fr, const double* w0_rows, const double* d0_vec, size_t N,
                     const double* t, int n_steps, double d0, int n_steps_per_pullback, int noffset_orbits, double atol,
                     double rtol, long nmax, double* LEs_raw, double* traj, int32_t* status, const gb_launch* opt) {

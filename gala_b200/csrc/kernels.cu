@@ -457,6 +457,17 @@ cudaError_t GB_ND_NAME(const DevPot& P, const DevBodies& B, const Dop853Args& a,
     return cudaGetLastError();
 }
 #if GB_PART == 6
+cudaError_t nbody_dop853_march(const DevPot& P, const DevBodies& B, const Dop853Args& a, double* body_all,
+                               const double* w0, const int32_t* ridx, size_t Np, int has_particle, const double* t,
+                               int ntimes, int output_every, double* snap, double* out_p, double* out_b,
+                               size_t body_writer, int32_t* status, cudaStream_t s) {
+    const size_t nthreads = has_particle ? Np : 1;
+    if (nthreads == 0) return cudaSuccess;
+    const int block = 64;
+    GB_SIG_SWITCH2(P.sig, (k_nbody_dop853_march<C><<<nblocks(nthreads, block), block, 0, s>>>(
+        P, B, a, body_all, w0, ridx, Np, has_particle, t, ntimes, output_every, snap, out_p, out_b, body_writer, status)));
+    return cudaGetLastError();
+}
 cudaError_t lyapunov(const DevPot& P, const DevFrame& F, const Dop853Args& a, const double* w0, const double* d0_vec,
                      size_t N, const double* t, int n_steps, double d0, int pullback, int noff, double* LEs, double* traj,
                      int32_t* status, cudaStream_t s) {

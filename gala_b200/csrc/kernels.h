@@ -76,6 +76,11 @@ struct Dop853Args {
                              const double* t1, size_t Np, const double* tgrid, int ntimes, double t0,      \
                              double tfinal, double* out_p, double* out_b, size_t body_writer,              \
                              double* traj, size_t ntot, int32_t* status, cudaStream_t s);                  \
+    cudaError_t nbody_dop853_march(const DevPot& P, const DevBodies& B, const Dop853Args& a,              \
+                                   double* body_all, const double* w0, const int32_t* ridx, size_t Np,     \
+                                   int has_particle, const double* t, int ntimes, int output_every,        \
+                                   double* snap, double* out_p, double* out_b, size_t body_writer,         \
+                                   int32_t* status, cudaStream_t s);                                       \
     cudaError_t lyapunov(const DevPot& P, const DevFrame& F, const Dop853Args& a, const double* w0,       \
                          const double* d0_vec, size_t N, const double* t, int n_steps, double d0,          \
                          int pullback, int noff, double* LEs, double* traj, int32_t* status,               \

@@ -247,3 +247,58 @@ k_nbody_dop853(const __grid_constant__ DevPot P, const __grid_constant__ DevBodi
     }
     if (status) status[p] = code;
 }
+
+
+// mockstream_dop853_animate with massive bodies (mockstream.pyx:306-440): the system is marched over the
+// caller's time grid interval by interval, every interval a fresh dop853_step call (initial step dt0), with
+// snapshots every `output_every` intervals.  Two launches of this kernel:
+//   has_particle = 0  one lane marches the bodies alone over the whole grid and writes their state at EVERY
+//                     grid time to body_all (ntimes, nb, 6) and at the snapshot times to snap;
+//   has_particle = 1  lane p starts at its release index ridx[p] from body_all[ridx[p]] and marches
+//                     [bodies, its particle]; snapshot rows before the release are NaN.
+// snap rows: (nout, nb + Np, 6).  The reference marches bodies and ALL released particles as one system with
+// one step size; here a lane's system is the bodies + one particle (deviation 1).
+template <class C>
+__global__ void __launch_bounds__(64)
+k_nbody_dop853_march(const __grid_constant__ DevPot P, const __grid_constant__ DevBodies B,
+                     const __grid_constant__ Dop853Args a, double* __restrict__ body_all,
+                     const double* __restrict__ w0, const int32_t* __restrict__ ridx, size_t Np, int has_particle,
+                     const double* __restrict__ t, int ntimes, int output_every, double* __restrict__ snap,
+                     double* __restrict__ out_p, double* __restrict__ out_b, size_t body_writer,
+                     int32_t* __restrict__ status) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (has_particle ? Np : 1)) return;
+    constexpr int NDIM = GB_ND_MAX;
+    const int nb = B.nb;
+    const size_t ntot = (size_t)nb + Np;
+    const int k0 = has_particle ? ridx[p] : 0;
+    const int nrun = 6 * (nb + (has_particle ? 1 : 0));
+    const bool wb = has_particle ? (p == body_writer) : true;
+    const double nan = CUDART_NAN;
+    double y[NDIM];
+    for (int i = 0; i < NDIM; i++) y[i] = 0.;
+    const double* bw = body_all + (size_t)k0 * nb * 6;
+    for (int i = 0; i < nb * 6; i++) y[i] = bw[i];
+    if (has_particle) for (int k = 0; k < 6; k++) y[nb * 6 + k] = w0[p * 6 + k];
+    NbodyRhs<C, NDIM> rhs{P, B, nrun / 6};
+    auto emit = [&](int, const double (&)[NDIM]) {};
+    auto store = [&](int jj, bool live) {
+        double* row = snap + (size_t)jj * ntot * 6;
+        if (!has_particle) for (int i = 0; i < nb * 6; i++) row[i] = y[i];
+        else for (int k = 0; k < 6; k++) row[((size_t)nb + p) * 6 + k] = live ? y[nb * 6 + k] : nan;
+    };
+    int code = 1, j = 0;
+    store(0, k0 == 0);
+    for (int i = 1; i < ntimes; i++) {
+        if (i > k0 && code > 0) {
+            int out_idx = 0, nstep, naccpt, nrejct, nfcn;
+            code = dop853_integrate<false, NDIM>(rhs, emit, a, t[i - 1], t[i], y, a.h0, nullptr, 0, out_idx, nstep, naccpt,
+                                                 nrejct, nfcn, nrun);
+            if (!has_particle) for (int q = 0; q < nb * 6; q++) body_all[(size_t)i * nb * 6 + q] = y[q];
+        }
+        if ((i % output_every) == 0 || i == ntimes - 1) { j++; store(j, i >= k0 && code > 0); }
+    }
+    if (has_particle && out_p) for (int k = 0; k < 6; k++) out_p[p * 6 + k] = y[nb * 6 + k];
+    if (wb && out_b) for (int i = 0; i < nb * 6; i++) out_b[i] = y[i];
+    if (status) status[p] = code;
+}

@@ -427,7 +427,7 @@ def mockstream_dop853_animate(nbody, t, stream_w0, nstream, output_every=1, outp
     """``mockstream.pyx:306-440``: march the stream over ``t`` interval by interval, storing a snapshot every
     ``output_every`` intervals (and the final state) in ``output_filename``.  Returns
     ``(nbody_w (nbodies,6), stream_w (Np,6))`` like the reference; the snapshot arrays are also kept on the
-    function object as ``mockstream_dop853_animate.last`` (dict of the two groups).  Massless bodies only."""
+    function object as ``mockstream_dop853_animate.last`` (dict of the two groups)."""
     import warnings
     t = np.ascontiguousarray(t, dtype=np.float64)
     stream_w0 = np.ascontiguousarray(stream_w0, dtype=np.float64)
@@ -437,8 +437,6 @@ def mockstream_dop853_animate(nbody, t, stream_w0, nstream, output_every=1, outp
         raise ValueError("nstream must have one entry per time")
     if stream_w0.shape != (int(nstream.sum()), 6):
         raise ValueError("stream_w0 must have shape (sum(nstream), 6)")
-    if nbody.n_massive:
-        raise NotImplementedError("snapshot output with massive bodies is not implemented on the B200 engine")
     H = nbody.H
     nbodies = nbody._c_w0.shape[0]
     Np = stream_w0.shape[0]
@@ -453,10 +451,22 @@ def mockstream_dop853_animate(nbody, t, stream_w0, nstream, output_every=1, outp
     status = np.empty(rows.shape[0], dtype=np.int32)
     opt = _opts(H)
     fr = H.frame.spec()
-    rc = _abi.lib().gb_mockstream_dop853_animate(H.potential.spec().ptr(), C.byref(fr), rows.ctypes.data, ridx.ctypes.data,
-                                                 rows.shape[0], t.ctypes.data, ntimes, float(atol), float(rtol), int(nmax),
-                                                 int(output_every), snap.ctypes.data, fin.ctypes.data, status.ctypes.data,
-                                                 C.byref(opt))
+    if nbody.n_massive:
+        # massive bodies: bodies-only march + one lane per particle = [bodies, particle] (csrc/nbody.cuh)
+        bs = _BodySpec(nbody.particle_potentials)
+        sw0 = np.ascontiguousarray(stream_w0)
+        pr = np.ascontiguousarray(ridx[nbodies:])
+        out_p = np.empty((Np, 6)); out_b = np.empty((nbodies, 6))
+        rc = _abi.lib().gb_nbody_dop853_animate(H.potential.spec().ptr(), bs.ptr(), np.ascontiguousarray(nbody._c_w0).ctypes.data,
+                                                sw0.ctypes.data, pr.ctypes.data, Np, t.ctypes.data, ntimes, float(atol),
+                                                float(rtol), int(nmax), int(output_every), snap.ctypes.data,
+                                                out_p.ctypes.data, out_b.ctypes.data, status.ctypes.data, C.byref(opt))
+        fin = np.vstack([out_b, out_p])
+    else:
+        rc = _abi.lib().gb_mockstream_dop853_animate(H.potential.spec().ptr(), C.byref(fr), rows.ctypes.data, ridx.ctypes.data,
+                                                     rows.shape[0], t.ctypes.data, ntimes, float(atol), float(rtol), int(nmax),
+                                                     int(output_every), snap.ctypes.data, fin.ctypes.data, status.ctypes.data,
+                                                     C.byref(opt))
     if rc in (-1, -2, -3, -4):
         if err_if_fail:
             _abi.check(rc)

@@ -263,6 +263,16 @@ int gb_nbody_dop853(const gb_potential* pot, const gb_bodies* bodies,
                     double* out_particles, double* out_bodies, size_t body_writer,
                     double* traj, int32_t* status, const gb_launch* opt);
 
+/* mockstream_dop853_animate with massive bodies: the bodies are marched alone over t (their states at the
+ * snapshot times fill snapshots[:, :n_bodies]); particle p then starts at release_idx[p] from the bodies' state
+ * there and is marched as [bodies, particle].  body_w0 (n_bodies, 6) at t[0]; snapshots (nout, n_bodies + Np, 6);
+ * out_bodies = the bodies' end state of the bodies-only march. */
+int gb_nbody_dop853_animate(const gb_potential* pot, const gb_bodies* bodies, const double* body_w0,
+                            const double* w0_rows, const int32_t* release_idx, size_t Np,
+                            const double* t, int ntimes, double atol, double rtol, long nmax, int output_every,
+                            double* snapshots, double* out_particles, double* out_bodies, int32_t* status,
+                            const gb_launch* opt);
+
 /* ---- chaos indicators ----------------------------------------------------------------
  * dop853_lyapunov_max(_dont_save) (dynamics/lyapunov/dop853_lyapunov.pyx:22-192) for N parent orbits at once
  * (the reference takes one per call): lane p integrates parent orbit p and its offset orbits

@@ -257,3 +257,56 @@ def test_nbody_reorder_sixteen_bodies(ref, integ):
             assert db.max() < 1e-8
     print(f"\n[nbody reorder, {sim.n_massive} massive of 16, {integ}] worst per-particle median over time = {worst:.2e}")
     assert worst < 1e-10
+
+
+def test_animate_with_self_gravity(ref, tmp_path):
+    """mockstream_dop853_animate (mockstream.pyx:306-440) with a massive progenitor: bodies marched alone
+    interval by interval, every particle marched as [bodies, particle] from its release index -- against
+    dop853_step calls of the compiled reference; then once through MockStreamGenerator.run(output_every=...)."""
+    from gala_b200.mockstream import mockstream_dop853_animate
+    pot = gb.MilkyWayPotential2022()
+    H = gb.Hamiltonian(pot)
+    pp = gb.PlummerPotential(m=5e8, b=0.3)
+    n_steps, oe = 30, 4
+    npart = np.where(np.arange(n_steps + 1) % 3 == 0, 1, 0).astype("i4")
+    t, w0, rel_t = _release(H, n_steps, npart)
+    nstream = np.zeros(n_steps + 1, dtype="i4")
+    np.add.at(nstream, np.round(rel_t).astype(int), 1)
+    nb = DirectNBody(PROG_W0, [pp], external_potential=pot)
+    fin_b, fin_s = mockstream_dop853_animate(nb, t, w0, nstream, output_every=oe, output_filename=str(tmp_path / "sg.hdf5"))
+    snaps = mockstream_dop853_animate.last
+    out_i = [i for i in range(n_steps + 1) if i % oe == 0 or i == n_steps]
+    assert snaps["stream"]["pos"].shape == (3, len(out_i), w0.shape[0])
+    # bodies-only march with the reference
+    body = PROG_W0[None, :].copy()
+    body_all = [body.copy()]
+    for i in range(1, n_steps + 1):
+        body, _, rc = ref.nbody_dop853(H, [pp], body, t1=t[i - 1], t2=t[i], dt0=1.0, mode=1)
+        assert rc >= 0
+        body_all.append(body.copy())
+    nb_snap = np.concatenate([snaps["nbody"]["pos"], snaps["nbody"]["vel"]])[:, :, 0]       # (6, nout)
+    for j, i in enumerate(out_i):
+        assert np.allclose(nb_snap[:, j], body_all[i][0], rtol=1e-12, atol=1e-14), i
+    assert np.allclose(fin_b[0], body_all[-1][0], rtol=1e-12, atol=1e-14)
+    w_snap = np.concatenate([snaps["stream"]["pos"], snaps["stream"]["vel"]])               # (6, nout, Np)
+    for p in range(w0.shape[0]):
+        k0 = int(round(rel_t[p]))
+        rows = np.vstack([body_all[k0], w0[p:p + 1]])
+        j = 0
+        for i in range(1, n_steps + 1):
+            if i > k0:
+                rows, _, rc = ref.nbody_dop853(H, [pp], rows, t1=t[i - 1], t2=t[i], dt0=1.0, mode=1)
+                assert rc >= 0
+            if i % oe == 0 or i == n_steps:
+                j += 1
+                if i < k0:
+                    assert np.all(np.isnan(w_snap[:, j, p]))
+                else:
+                    assert np.allclose(w_snap[:, j, p], rows[1], rtol=1e-11, atol=1e-13), (p, i)
+        assert np.allclose(fin_s[p], rows[1], rtol=1e-11, atol=1e-13)
+    gen = gb.MockStreamGenerator(gb.FardalStreamDF(gala_modified=True, random_state=np.random.RandomState(42)), H,
+                                 progenitor_potential=pp)
+    stream, prog = gen.run(PROG_W0, 5e8, dt=1.0, n_steps=n_steps, n_particles=1, release_every=3,
+                           output_every=oe, output_filename=str(tmp_path / "sg2.hdf5"))
+    assert stream.pos.shape == (3, 2 * 11) and np.all(np.isfinite(stream.pos))
+    assert mockstream_dop853_animate.last["nbody"]["pos"].shape == (3, len(out_i), 1)
