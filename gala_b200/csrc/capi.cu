@@ -62,8 +62,15 @@ int min_npar(int type) {
 // parameter vector, evaluated once per call in IEEE double.
 void gb_derive(int type, const double* p, double* d) {
     switch (type) {
-        case GB_POT_HERNQUIST: case GB_POT_KEPLER: case GB_POT_JAFFE:
+        case GB_POT_HERNQUIST: case GB_POT_KEPLER: case GB_POT_JAFFE: case GB_POT_KUZMIN:
             d[0] = p[0] * p[1]; break;
+        case GB_POT_SATOH:
+            d[0] = p[0] * p[1]; d[1] = p[3] * p[3]; break;
+        case GB_POT_NFW_FLATTENED:      // a = b = 1 (flattenednfw_* ignore them, builtin_potentials.cpp:925-962)
+            d[0] = p[0] * p[1]; d[1] = 1. / p[2]; d[2] = 1.; d[3] = 1.; d[4] = 1. / (p[5] * p[5]); break;
+        case GB_POT_NFW_TRIAXIAL:
+            d[0] = p[0] * p[1]; d[1] = 1. / p[2]; d[2] = 1. / (p[3] * p[3]); d[3] = 1. / (p[4] * p[4]);
+            d[4] = 1. / (p[5] * p[5]); break;
         case GB_POT_NFW_SPHERICAL:
             d[0] = p[0] * p[1]; d[1] = 1. / p[2]; break;
         case GB_POT_MIYAMOTONAGAI:

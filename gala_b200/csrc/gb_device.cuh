@@ -85,14 +85,15 @@ enum GbSig {
 
 // Number of host-derived constants per potential type (filled by capi.cu:gb_derive, read by the
 // fast build's accum() functions in potentials.cuh; the strict build ignores them):
-//   Hernquist/Kepler/Jaffe [G m] ; NFW spherical [G m, 1/r_s] ; MiyamotoNagai/Plummer/Isochrone [G m, b^2] ;
+//   Hernquist/Kepler/Jaffe/Kuzmin [G m] ; Satoh [G m, b^2] ; NFW flattened/triaxial [G m, 1/r_s, 1/a^2, 1/b^2, 1/c^2] ; NFW spherical [G m, 1/r_s] ; MiyamotoNagai/Plummer/Isochrone [G m, b^2] ;
 //   MN3 [G m1, G m2, G m3, b1^2, b2^2, b3^2] ; LongMuraliBar [G m, sin(alpha), cos(alpha), c^2] ;
 //   SCF [G m / r_s^2, 1 / r_s] ; PowerLawCutoff [G m, lgamma(a), 1/r_c^2, 1/r_c, 2a, ext offset of the gamma* fit], a = (3-alpha)/2 ;
 //   Logarithmic [v_c^2, r_h^2, 1/q1^2, 1/q2^2, 1/q3^2, sin(phi), cos(phi)].
 constexpr int gb_nderived(int type) {
-    return (type == GB_POT_HERNQUIST || type == GB_POT_KEPLER || type == GB_POT_JAFFE) ? 1
+    return (type == GB_POT_HERNQUIST || type == GB_POT_KEPLER || type == GB_POT_JAFFE || type == GB_POT_KUZMIN) ? 1
          : (type == GB_POT_NFW_SPHERICAL || type == GB_POT_MIYAMOTONAGAI || type == GB_POT_PLUMMER ||
-            type == GB_POT_ISOCHRONE) ? 2
+            type == GB_POT_ISOCHRONE || type == GB_POT_SATOH) ? 2
+         : (type == GB_POT_NFW_FLATTENED || type == GB_POT_NFW_TRIAXIAL) ? 5
          : (type == GB_POT_MN3) ? 6
          : (type == GB_POT_LONGMURALIBAR) ? 4
          : (type == GB_POT_SCF) ? 2

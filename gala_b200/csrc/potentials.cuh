@@ -227,6 +227,20 @@ struct PotNFWSpherical {
     }
 #endif
 };
+#if !GB_STRICT
+// flattened / triaxial NFW, fast build: d = [G m, 1/r_s, 1/a^2, 1/b^2, 1/c^2]; with m the ellipsoidal radius,
+// grad_i = G m [ln(1+m/r_s) - m/(m+r_s)] / m^3 * x_i / a_i^2 (the same expression as gb_nfw_fac)
+template <class Ctx> GB_DEV void gb_nfw_ellipsoidal_accum(const double* p, const double* d, Ctx& c) {
+    const double xi = c.x * d[2], yi = c.y * d[3], zi = c.z * d[4];
+    const double m2 = fma(c.x, xi, fma(c.y, yi, c.z * zi));
+    const double im = gb_rsqrt(m2);
+    const double m = m2 * im;
+    const double L = gb_log(fma(m, d[1], 1.0));
+    const double h = fma(-m, gb_rcp(m + p[2]), L);
+    const double f = (d[0] * h) * (im * (im * im));
+    c.gx = fma(f, xi, c.gx); c.gy = fma(f, yi, c.gy); c.gz = fma(f, zi, c.gz);
+}
+#endif
 struct PotNFWFlattened {
     GB_DEV static double u_of(const double* p, double x, double y, double z) {
         return sqrt(x * x + y * y + z * z / (p[5] * p[5])) / p[2];
@@ -237,7 +251,10 @@ struct PotNFWFlattened {
     }
     GB_DEV static double value(const double* p, double x, double y, double z) { return gb_nfw_value(p, u_of(p, x, y, z)); }
     GB_DEV static double density(const double*, double, double, double) { return CUDART_NAN; }  // nan_density (cybuiltin.pyx:303-311)
-    GB_ACCUM_VIA_GRADIENT
+    #if !GB_STRICT
+    static constexpr int USE = GB_USE_GEN;
+    template <class Ctx> GB_DEV static void accum(const double* p, const double* d, Ctx& c) { gb_nfw_ellipsoidal_accum(p, d, c); }
+#endif
 };
 struct PotNFWTriaxial {
     GB_DEV static double u_of(const double* p, double x, double y, double z) {
@@ -249,7 +266,10 @@ struct PotNFWTriaxial {
     }
     GB_DEV static double value(const double* p, double x, double y, double z) { return gb_nfw_value(p, u_of(p, x, y, z)); }
     GB_DEV static double density(const double*, double, double, double) { return CUDART_NAN; }
-    GB_ACCUM_VIA_GRADIENT
+    #if !GB_STRICT
+    static constexpr int USE = GB_USE_GEN;
+    template <class Ctx> GB_DEV static void accum(const double* p, const double* d, Ctx& c) { gb_nfw_ellipsoidal_accum(p, d, c); }
+#endif
 };
 
 // ---- Miyamoto-Nagai (builtin_potentials.cpp:1287-1332): [G, m, a, b] --------------------------
@@ -512,7 +532,18 @@ struct PotSatoh {
         const double A = p[1] * p[2] * p[3] * p[3] / (4 * GB_PI * S2 * sqrt(S2) * z2b2);
         return A * (1 / sqrt(z2b2) + 3 / p[2] * (1 - xyz2 / S2));
     }
-    GB_ACCUM_VIA_GRADIENT
+    #if !GB_STRICT
+    static constexpr int USE = GB_USE_DISC;
+    // d = [G m, b^2]: grad = G m S^-3 (x, y, z (1 + a / sqrt(z^2+b^2))), S^2 = r^2 + a (a + 2 sqrt(z^2+b^2))
+    template <class Ctx> GB_DEV static void accum(const double* p, const double* d, Ctx& c) {
+        const double s2 = c.z2 + d[1];
+        const double isq = gb_rsqrt(s2);
+        const double S2 = fma(p[2], fma(2., s2 * isq, p[2]), c.r2);
+        const double f = d[0] * gb_pow_m1p5(S2);
+        c.Fd += f;
+        c.Fdz = fma(f, fma(p[2], isq, 1.0), c.Fdz);
+    }
+#endif
 };
 
 // ---- Kuzmin disc (builtin_potentials.cpp:1235-1283): [G, m, a] ---------------------------------
@@ -532,7 +563,17 @@ struct PotKuzmin {
         if (z != 0.) return 0.;
         return p[1] * p[2] / (2 * GB_PI) * pow(x * x + y * y + p[2] * p[2], -1.5);
     }
-    GB_ACCUM_VIA_GRADIENT
+    #if !GB_STRICT
+    static constexpr int USE = GB_USE_DISC | GB_USE_GEN;
+    // d = [G m]: grad = G m S^-3 (x, y, sign(z) (a + |z|)), S^2 = R^2 + (a + |z|)^2
+    template <class Ctx> GB_DEV static void accum(const double* p, const double* d, Ctx& c) {
+        const double az = p[2] + fabs(c.z);
+        const double f = d[0] * gb_pow_m1p5(fma(az, az, c.R2));
+        const double zs = (c.z > 0) ? 1. : ((c.z < 0) ? -1. : 0.);
+        c.Fd += f;
+        c.gz = fma(f * zs, az, c.gz);          // the z-component is not proportional to z: general accumulator
+    }
+#endif
 };
 
 // ---- Logarithmic, triaxial, rotated by phi about z (builtin_potentials.cpp:1560-1625):
