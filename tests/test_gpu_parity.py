@@ -111,6 +111,8 @@ def test_gradient_energy_density(ref, name, strict):
     gtol = 2e-11 if name.startswith("scf") else 1e-12 if name.startswith("multipole") else (5e-15 if strict else 2e-14)
     if name in ("powerlawcutoff", "bovy2014"):
         gtol = 1e-13 if strict else 1e-12      # incomplete gamma function: series / continued fraction on both sides
+    if name in ("nfw_flat", "nfw_triax") and not strict:
+        gtol = 5e-14      # ln(1+u) - u/(1+u) cancels ~u/2 of its digits at small u in either form; rsqrt-based m here
     if name == "leesuto":
         gtol = 1e-11      # the reference's expanded polynomial form cancels ~3 digits (builtin_potentials.cpp:1518)
     assert np.max(np.sqrt(((g - g0) ** 2).sum(0)) / scale) < gtol
