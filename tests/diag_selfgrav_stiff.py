@@ -1,4 +1,4 @@
-"""C3 with progenitor self-gravity, DOP853: which stream particles end with the stiffness code -4 on the GPU,
+"""Diagnostic (test infrastructure, uses the oracle): C3 with progenitor self-gravity, DOP853: which stream particles end with the stiffness code -4 on the GPU,
 and does the compiled reference (lane by lane) end the same particles the same way?"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
