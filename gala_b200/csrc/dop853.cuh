@@ -30,7 +30,11 @@ GB_DEV double gb_pow_eighth(double err) {
 #if GB_STRICT
     return pow(err, 1.0 / 8.0);
 #else
-    return sqrt(sqrt(sqrt(err)));
+    // three square roots as x * rsqrt(x) (2 ulp each, no slow path); err == 0 stays 0
+    if (!(err > 0.0)) return 0.0;
+    const double s1 = err * gb_rsqrt(err);
+    const double s2 = s1 * gb_rsqrt(s1);
+    return s2 * gb_rsqrt(s2);
 #endif
 }
 
@@ -174,22 +178,39 @@ struct Dop853Lane {
             for (int i = 0; i < nn; i++) {
                 const double sk = atoli + rtoli * gb_max(fabs(y[i]), fabs(k5[i]));
                 double erri = k4[i] - bhh1 * k1[i] - bhh2 * k9[i] - bhh3 * k3[i];
+#if GB_STRICT
                 double sqr = erri / sk;
                 err2 += sqr * sqr;
                 erri = er1 * k1[i] + er6 * k6[i] + er7 * k7[i] + er8 * k8[i] + er9 * k9[i] + er10 * k10[i] +
                        er11 * k2[i] + er12 * k3[i];
                 sqr = erri / sk;
+#else
+                const double isk = gb_rcp(sk);          // one reciprocal for the two error components
+                double sqr = erri * isk;
+                err2 += sqr * sqr;
+                erri = er1 * k1[i] + er6 * k6[i] + er7 * k7[i] + er8 * k8[i] + er9 * k9[i] + er10 * k10[i] +
+                       er11 * k2[i] + er12 * k3[i];
+                sqr = erri * isk;
+#endif
                 err += sqr * sqr;
             }
             double deno = err + 0.01 * err2;
             if (deno <= 0.0) deno = 1.0;
+#if GB_STRICT
             err = fabs(h) * err * sqrt(1.0 / (deno * (double)nn));
+#else
+            err = fabs(h) * err * gb_rsqrt(deno * (double)nn);
+#endif
 
             // step-size controller (dop853.cpp:446-452), beta = 0 => pow(facold, beta) == 1
             const double fac11 = gb_pow_eighth(err);
             double fac = fac11;
             fac = gb_max(facc2, gb_min(facc1, fac / safe));
+#if GB_STRICT
             hnew = h / fac;
+#else
+            hnew = h * gb_rcp(fac);
+#endif
 
             if (err <= 1.0) {
                 // accepted
@@ -254,10 +275,17 @@ struct Dop853Lane {
                     }
                     // fill every requested time inside [x, x+h] (dop853.cpp:584-612; contd8 :869-904)
                     const double x0 = x, x1 = x0 + h;
+#if !GB_STRICT
+                    const double ih = 1.0 / h;            // one division per step, not one per output sample
+#endif
                     while (out_idx < ntout) {
                         const double t_out = tout[out_idx];
                         if ((x0 <= t_out && t_out <= x1) || (x1 <= t_out && t_out <= x0)) {
+#if GB_STRICT
                             const double s = (t_out - x0) / h;
+#else
+                            const double s = (t_out - x0) * ih;
+#endif
                             const double s1 = 1.0 - s;
                             double v[n];
 #pragma unroll(GB_NU)
@@ -280,7 +308,11 @@ struct Dop853Lane {
                 reject = 0;
             } else {
                 // rejected (dop853.cpp:638-645)
+#if GB_STRICT
                 hnew = h / gb_min(facc1, fac11 / safe);
+#else
+                hnew = h * gb_rcp(gb_min(facc1, fac11 / safe));
+#endif
                 reject = 1;
                 if (naccpt >= 1) nrejct = nrejct + 1;
                 last = 0;
