@@ -105,6 +105,7 @@ template <bool HEAVY> struct CompositeGeneric {
     // the adaptive integrator evaluates the gradient at 15-17 sites per step: ONE out-of-line copy of this
     // loop-and-switch per kernel instead of 17 inlined ones (hamiltonian.cuh: ham_rhs)
     static constexpr bool kOutOfLineInRhs = true;
+    static constexpr int kFixedStepMaxThreads = 256, kFixedStepMinBlocks = 1;   // __launch_bounds__ of k_leapfrog
     GB_DEV static void gradient(const DevPot& P, double t, double x, double y, double z,
                                 double& gx, double& gy, double& gz) {
 #if GB_STRICT
@@ -211,6 +212,7 @@ template <int OFF, int DOFF, int T0, int... Ts> struct SeqImpl<OFF, DOFF, T0, Ts
 };
 template <int... Ts> struct Seq {
     static constexpr bool kOutOfLineInRhs = false;
+    static constexpr int kFixedStepMaxThreads = 256, kFixedStepMinBlocks = 1;
     GB_DEV static void gradient(const DevPot& P, double t, double x, double y, double z,
                                 double& gx, double& gy, double& gz) {
 #if GB_STRICT
@@ -241,6 +243,11 @@ template <> struct Composite<SIG_LM10>       : Seq<GB_POT_MIYAMOTONAGAI, GB_POT_
 template <> struct Composite<SIG_BOVY2014>   : Seq<GB_POT_MIYAMOTONAGAI, GB_POT_POWERLAWCUTOFF, GB_POT_NFW_SPHERICAL> {};
 template <> struct Composite<SIG_SCF> {
     static constexpr bool kOutOfLineInRhs = true;
+#ifndef GB_SCF_MINBLOCKS
+#define GB_SCF_MAXTHREADS 256
+#define GB_SCF_MINBLOCKS 1
+#endif
+    static constexpr int kFixedStepMaxThreads = GB_SCF_MAXTHREADS, kFixedStepMinBlocks = GB_SCF_MINBLOCKS;
     GB_DEV static void gradient(const DevPot& P, double t, double x, double y, double z, double& gx, double& gy, double& gz) {
 #if !GB_STRICT
         if (P.cext_ok) { scf_fast_gradient(P, &P.drv[0], x, y, z, gx, gy, gz); return; }   // warp-uniform

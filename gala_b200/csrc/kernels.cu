@@ -96,7 +96,7 @@ __global__ void k_ham_gradient(const __grid_constant__ DevPot P, const __grid_co
 // out[k][j][i0..i0+31], never re-read by the kernel, so it should not occupy L2.
 // ------------------------------------------------------------------------------------------------
 template <class C, bool SAVE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(C::kFixedStepMaxThreads, C::kFixedStepMinBlocks)
 k_leapfrog(const __grid_constant__ DevPot P, const double* __restrict__ w0, size_t N,
            const double* __restrict__ t, int ntimes, double dt, double* __restrict__ out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -250,9 +250,9 @@ cudaError_t leapfrog(const DevPot& P, const double* w0, size_t N, const double* 
                      int save_all, double* out, int block, cudaStream_t s) {
     if (N == 0) return cudaSuccess;
     if (save_all) {
-        GB_SIG_SWITCH(P.sig, (k_leapfrog<C, true><<<nblocks(N, block), block, 0, s>>>(P, w0, N, t, ntimes, dt, out)));
+        GB_SIG_SWITCH(P.sig, (k_leapfrog<C, true><<<nblocks(N, block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads), block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads, 0, s>>>(P, w0, N, t, ntimes, dt, out)));
     } else {
-        GB_SIG_SWITCH(P.sig, (k_leapfrog<C, false><<<nblocks(N, block), block, 0, s>>>(P, w0, N, t, ntimes, dt, out)));
+        GB_SIG_SWITCH(P.sig, (k_leapfrog<C, false><<<nblocks(N, block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads), block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads, 0, s>>>(P, w0, N, t, ntimes, dt, out)));
     }
     return cudaGetLastError();
 }
