@@ -26,6 +26,10 @@
  *   -12      : invalid argument (shape etc; the Python shim raises ValueError)
  *   -13      : integrator does not support this frame (TypeError in the
  *              reference: leapfrog.pyx:64-68, ruth4.pyx:49-52)
+ *   -14      : not implemented in the reference either (Hessian of a rotated
+ *              potential: NotImplementedError, potential/potential/core.py:572-575)
+ * The N-body, snapshot and Lyapunov entry points (gb_nbody_*, gb_*_animate,
+ * gb_lyapunov_max) take HOST buffers only.
  */
 #ifndef GALA_B200_H
 #define GALA_B200_H
