@@ -81,7 +81,8 @@ class BaseStreamDF:
             potential.spec().ptr(), float(potential.G), prog_w.ctypes.data, prog_t.ctypes.data, prog_m.ctypes.data,
             len(prog_t), prog_idx.ctypes.data, sign.ctypes.data, None if draws is None else draws.ctypes.data, ncols,
             Np, int(self._kind), int(self._flags), out.ctypes.data, C.byref(opt)))
-        return out[:, :3].copy(), out[:, 3:].copy(), prog_t[prog_idx]
+        self._last_rows = out                # (Np, 6) rows as the integrate kernels take them: reused by run()
+        return out[:, :3], out[:, 3:], prog_t[prog_idx]
 
     def sample(self, prog_orbit, prog_mass, hamiltonian=None, release_every=1, n_particles=1):
         """``BaseStreamDF.sample`` (``df.pyx:125-238``): returns a ``MockStream`` of initial conditions."""
@@ -109,7 +110,9 @@ class BaseStreamDF:
         x, v, t1 = self._sample(H.potential, prog_x, prog_v, prog_t, prog_m, n_particles)
         _, sign = self._plan(prog_m, n_particles)
         lt = np.where(sign > 0, "t", "l").astype("U1")
-        return MockStream(pos=x.T, vel=v.T, release_time=t1, lead_trail=lt, frame=H.frame)
+        ms = MockStream(pos=x.T, vel=v.T, release_time=t1, lead_trail=lt, frame=H.frame)
+        ms._rows = self._last_rows
+        return ms
 
 
 class FardalStreamDF(BaseStreamDF):
@@ -390,7 +393,7 @@ def mockstream_dop853(nbody, time, stream_w0, stream_t1, tfinal, nstream, atol=1
     else:
         _abi.check(rc)
     Np = stream_w0.shape[0]
-    return out[Np:].copy(), out[:Np].copy()
+    return out[Np:], out[:Np]
 
 
 def _write_snapshots(filename, overwrite, groups, units_name):
@@ -528,7 +531,7 @@ def mockstream_leapfrog(nbody, full_time, spawn_time, stream_w0, stream_t1, tfin
                                                  rows.shape[0], float(tfinal), float(dt), out.ctypes.data,
                                                  C.byref(opt)))
     Np = stream_w0.shape[0]
-    return out[Np:].copy(), out[:Np].copy()
+    return out[Np:], out[:Np]
 
 
 def _scatter_isclose(orbit_t, unq_t1s, nstream):
@@ -606,7 +609,9 @@ class MockStreamGenerator:
         orbit_t = np.asarray(prog_orbit.t, dtype=np.float64)
         stream_w0 = self.df.sample(prog_orbit, prog_mass, hamiltonian=self.hamiltonian,
                                    release_every=release_every, n_particles=n_particles)
-        w0 = np.ascontiguousarray(np.vstack((stream_w0.pos, stream_w0.vel)).T)
+        w0 = getattr(stream_w0, "_rows", None)          # the sampler's (Np, 6) array: no re-assembly
+        if w0 is None:
+            w0 = np.ascontiguousarray(np.vstack((stream_w0.pos, stream_w0.vel)).T)
         unq_t1s, nstream = np.unique(stream_w0.release_time, return_counts=True)
         all_nstream = _scatter_isclose(orbit_t, unq_t1s, nstream)
         nstream_idx = np.where(all_nstream != 0)[0]
