@@ -132,8 +132,13 @@ class FardalStreamDF(BaseStreamDF):
         loc = np.array([2.0, 0.0, 0.3, 0.0])
         scale = np.array([0.5 if self._gala_modified else 0.4, 0.5,
                           0.5 if self._gala_modified else kvt_fardal, 0.5])
-        return np.ascontiguousarray(
-            self.random_state.normal(np.broadcast_to(loc, (Np, 4)), np.broadcast_to(scale, (Np, 4))), dtype=np.float64)
+        # normal(loc, scale) IS loc + scale * standard_normal() in numpy (legacy and Generator), so one
+        # standard_normal((Np, 4)) call consumes the bit stream like the reference's scalar draws and the
+        # in-place scale/shift reproduces their values bit for bit (tests/test_host_logic_cpu.py)
+        x = self.random_state.standard_normal((Np, 4))
+        x *= scale
+        x += loc
+        return x
 
 
 class StreaklineStreamDF(BaseStreamDF):
@@ -153,8 +158,10 @@ class LagrangeCloudStreamDF(BaseStreamDF):
         self.v_disp = float(strip(v_disp))
 
     def _draws(self, Np, potential):
-        return np.ascontiguousarray(self.random_state.normal(np.zeros((Np, 3)), np.full((Np, 3), self.v_disp)),
-                                    dtype=np.float64)
+        x = self.random_state.standard_normal((Np, 3))       # normal(0, v_disp) = 0 + v_disp * standard_normal()
+        x *= self.v_disp
+        x += 0.0
+        return x
 
 
 class ChenStreamDF(BaseStreamDF):

@@ -125,6 +125,9 @@ def test_rng_broadcast_draw_equals_scalar_draws():
         r = mk()
         b = np.array([[r.normal(loc[i, k], scale[i, k]) for k in range(4)] for i in range(50)])
         assert np.array_equal(a, b)
+        # what FardalStreamDF._draws does: standard_normal, then scale and shift in place
+        df = gb.FardalStreamDF(gala_modified=True, random_state=mk())
+        assert np.array_equal(df._draws(50, None), b)
 
 
 def test_chen_batched_draw_matches_per_particle_calls():
