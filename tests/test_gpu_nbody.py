@@ -310,3 +310,30 @@ def test_animate_with_self_gravity(ref, tmp_path):
                            output_every=oe, output_filename=str(tmp_path / "sg2.hdf5"))
     assert stream.pos.shape == (3, 2 * 11) and np.all(np.isfinite(stream.pos))
     assert mockstream_dop853_animate.last["nbody"]["pos"].shape == (3, len(out_i), 1)
+
+
+def test_one_burst_known_answer_of_the_reference():
+    """tests/dynamics/mockstream/test_mockstream_class.py:41-97 (test_one_burst), the reference's own
+    known-answer mock stream: NFW from v_c = 232.8 km/s at 8.2 kpc (r_s = 15), progenitor at [10,0,0] kpc with
+    [0,10,0] km/s, 1000 Fardal particles (gala_modified, default_rng(42)) released in one burst at the timestep
+    of minimum radius, Plummer self-gravity (2.5e4 Msun, b = 4 pc), dt = 1 Myr x 100, default DOPRI853.
+    Expected numbers are the ones hard-coded in the reference test (u.allclose default rtol 1e-5)."""
+    pot = gb.NFWPotential.from_circular_velocity(v_c=232.8 * KMS, r_s=15.0, r_ref=8.2)
+    H = gb.Hamiltonian(pot)
+    prog_w0 = gb.PhaseSpacePosition(pos=[10.0, 0.0, 0.0], vel=[0.0, 10.0 * KMS, 0.0])
+    orbit = H.integrate_orbit(prog_w0, dt=1.0, n_steps=100)
+    r = np.sqrt((np.asarray(orbit.pos).reshape(3, -1) ** 2).sum(0))
+    n_array = np.zeros(r.size, dtype=int)
+    n_array[r[0:150].argmin()] = 1000
+    df = gb.FardalStreamDF(gala_modified=True, random_state=np.random.default_rng(seed=42))
+    prog_pot = gb.PlummerPotential(m=2.5e4, b=0.004)
+    gen = gb.MockStreamGenerator(df, H, progenitor_potential=prog_pot)
+    stream, prog = gen.run(prog_w0, 2.5e4, n_particles=n_array, dt=1.0, n_steps=100, progress=False)
+    assert stream.pos.shape == (3, 2000)
+    got_s = np.concatenate([stream.pos[:, 0], stream.vel[:, 0]])
+    got_p = np.concatenate([prog.pos.ravel(), prog.vel.ravel()])
+    print(f"\n[test_one_burst] stream[0] = {got_s}\n                 prog      = {got_p}")
+    assert np.allclose(got_s[:3], [-10.07444187, -1.37424641, 0.06310397], rtol=1e-5, atol=0)
+    assert np.allclose(got_s[3:], [-0.05672946, -0.01837671, 0.00038504], rtol=1e-5, atol=0)
+    assert np.allclose(got_p[:3], [-9.72388107, -1.28632464, 0.0], rtol=1e-5, atol=1e-12)
+    assert np.allclose(got_p[3:], [-0.04714419, -0.016754, 0.0], rtol=1e-5, atol=1e-12)
