@@ -337,3 +337,31 @@ def test_one_burst_known_answer_of_the_reference():
     assert np.allclose(got_s[3:], [-0.05672946, -0.01837671, 0.00038504], rtol=1e-5, atol=0)
     assert np.allclose(got_p[:3], [-9.72388107, -1.28632464, 0.0], rtol=1e-5, atol=1e-12)
     assert np.allclose(got_p[3:], [-0.04714419, -0.016754, 0.0], rtol=1e-5, atol=1e-12)
+
+
+@pytest.mark.parametrize("integ", ["dopri853", "leapfrog", "ruth4"])
+def test_directnbody_integrate_like_the_reference(integ):
+    """tests/dynamics/nbody/test_nbody.py:20-146 (TestDirectNBody.test_directnbody_integrate), in the reference's
+    unit system (pc, 1e-5 Myr, 1e6 Msun): a test particle on a circular orbit 1 pc from a 1e6 Msun Hernquist
+    body.  With the body's mass switched off the particle's orbit changes by more than 50 pc within 1 Myr; the
+    massive body's own orbit does not change at all -- with and without an external NFW halo."""
+    from gala_b200.units import UnitSystem
+    usys = UnitSystem("pc, 1e-5 Myr, 1e6 Msun", gb.G_GALACTIC * 1e9 * 1e6 * 1e-10)
+    body_pot = gb.HernquistPotential(m=1.0, c=0.1, units=usys)
+    g1 = body_pot.gradient(np.array([[1.0], [0.0], [0.0]]))[0, 0]
+    vcirc = np.sqrt(1.0 * g1)
+    kms = gb.KMS_TO_KPC_MYR * 1e3 * 1e-5                       # km/s in pc per 1e-5 Myr
+    w0_2 = np.array([1e4, 0, 0, 0, 83 * kms, 0.0])
+    w0_1 = w0_2 + np.array([1.0, 0, 0, 0, vcirc, 0.0])
+    w0 = gb.PhaseSpacePosition.from_w(np.ascontiguousarray(np.vstack([w0_1, w0_2]).T))
+    t = np.arange(0, 1e5 + 1, 1.0)                             # dt = 1 unit, t2 = 1 Myr
+    ext = gb.NFWPotential(m=1e5, r_s=1e4, units=usys)           # NFW(m=1e11 Msun, r_s=10 kpc)
+    for external in (None, ext):
+        nb1 = DirectNBody(w0, [None, None], external_potential=external, units=usys)
+        nb2 = DirectNBody(w0, [None, body_pot], external_potential=external, units=usys)
+        o1 = nb1.integrate_orbit(t=t, Integrator=integ)
+        o2 = nb2.integrate_orbit(t=t, Integrator=integ)
+        dx0 = o1.pos[:, :, 0] - o2.pos[:, :, 0]
+        dx1 = o1.pos[:, :, 1] - o2.pos[:, :, 1]
+        assert np.abs(dx0).max() > 50.0
+        assert np.abs(dx1).max() < 1e-10
