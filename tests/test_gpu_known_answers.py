@@ -88,3 +88,36 @@ def test_against_sympy_closed_forms_gpu(name):
             H = pot.hessian(q)
             assert np.allclose(H[0, 0] + H[1, 1] + H[2, 2], lap(*q), rtol=1e-8, atol=1e-10 * np.abs(lap(*q)).max())
     pot.strict_math = False
+
+
+def test_bar_rotating_frame_jacobi_energy_gpu():
+    """tests/integration/test_bar_rotating_frame.py:171-219 (test_energy_conservation), the half that needs no
+    TimeInterpolatedPotential: LongMuraliBar + MW(v2) disk (m = 4.1e10) + halo + nucleus, static in a frame rotating
+    at 30 km/s/kpc, an orbit started at corotation, DOP853 atol = rtol = 1e-14, dt = 0.1 Myr over ~5 Gyr: the Jacobi
+    energy is conserved to < 1e-12."""
+    mw = gb.MilkyWayPotential(version="latest")
+    pot = gb.CCompositePotential()
+    pot["bar"] = gb.LongMuraliBarPotential(m=1e10, a=4.0, b=0.8, c=0.25, alpha=np.deg2rad(25.0))
+    pot["disk"] = gb.MN3ExponentialDiskPotential(m=4.1e10, h_R=mw["disk"].parameters["h_R"], h_z=mw["disk"].parameters["h_z"])
+    pot["halo"] = mw["halo"]
+    pot["nucleus"] = mw["nucleus"]
+    Omega = 30.0 * gb.KMS_TO_KPC_MYR                                  # rad / Myr
+    H = gb.Hamiltonian(pot, gb.ConstantRotatingFrame([0.0, 0.0, Omega]))
+
+    def om(r):
+        g = pot.gradient(np.array([[r], [0.0], [0.0]]))[0, 0]
+        return np.sqrt(g / r)
+    lo, hi = 2.0, 30.0
+    for _ in range(80):                                              # Omega_c(r) decreases outward
+        mid = 0.5 * (lo + hi)
+        lo, hi = (mid, hi) if om(mid) > Omega else (lo, mid)
+    r_c = 0.5 * (lo + hi)
+    w0 = np.array([r_c, 0, 0, 0, Omega * r_c, 0.0])
+    period = 2 * np.pi / Omega
+    t_end = np.arange(0, 5000.0, period / 200)[-1]
+    orb = H.integrate_orbit(w0, t1=0.0, t2=t_end, dt=0.1, Integrator="dopri853",
+                            Integrator_kwargs={"atol": 1e-14, "rtol": 1e-14})
+    E = orb.energy()
+    frac = np.abs((E[1:] - E[0]) / E[0])
+    print(f"\n[bar, rotating frame] corotation radius {r_c:.4f} kpc, {len(E)} outputs, max |dE_J/E_J| = {frac.max():.2e}")
+    assert frac.max() < 1e-12
