@@ -105,7 +105,9 @@ template <bool HEAVY> struct CompositeGeneric {
     // the adaptive integrator evaluates the gradient at 15-17 sites per step: ONE out-of-line copy of this
     // loop-and-switch per kernel instead of 17 inlined ones (hamiltonian.cuh: ham_rhs)
     static constexpr bool kOutOfLineInRhs = true;
-    static constexpr int kFixedStepMaxThreads = 256, kFixedStepMinBlocks = 1;   // __launch_bounds__ of k_leapfrog
+    // __launch_bounds__ of k_leapfrog: the analytic-only loop is capped at 128 registers (4 CTAs of 128 per SM);
+    // uncapped it grew from 124 to 140 registers as more fast accumulators were inlined (48 -> 59 ms for MW2022)
+    static constexpr int kFixedStepMaxThreads = HEAVY ? 256 : 128, kFixedStepMinBlocks = HEAVY ? 1 : 4;
     GB_DEV static void gradient(const DevPot& P, double t, double x, double y, double z,
                                 double& gx, double& gy, double& gz) {
 #if GB_STRICT

@@ -142,7 +142,7 @@ k_leapfrog(const __grid_constant__ DevPot P, const double* __restrict__ w0, size
 struct Ruth4Coef { double c[4], d[4]; };
 
 template <class C, bool ROT, bool SAVE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(C::kFixedStepMaxThreads, C::kFixedStepMinBlocks)
 k_ruth4(const __grid_constant__ DevPot P, const __grid_constant__ DevFrame F, const __grid_constant__ Ruth4Coef K,
         const double* __restrict__ w0, size_t N, int ntimes, double dt, double* __restrict__ out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -264,7 +264,7 @@ cudaError_t ruth4(const DevPot& P, const DevFrame& F, const double* w0, size_t N
     Ruth4Coef K;
     for (int k = 0; k < 4; k++) { K.c[k] = cs[k]; K.d[k] = ds[k]; }
     const bool rot = F.type != GB_FRAME_STATIC;
-#define GB_R4(ROT, SAVE) GB_SIG_SWITCH(P.sig, (k_ruth4<C, ROT, SAVE><<<nblocks(N, block), block, 0, s>>>(P, F, K, w0, N, ntimes, dt, out)))
+#define GB_R4(ROT, SAVE) GB_SIG_SWITCH(P.sig, (k_ruth4<C, ROT, SAVE><<<nblocks(N, block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads), block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads, 0, s>>>(P, F, K, w0, N, ntimes, dt, out)))
     if (rot) { if (save_all) { GB_R4(true, true); } else { GB_R4(true, false); } }
     else     { if (save_all) { GB_R4(false, true); } else { GB_R4(false, false); } }
 #undef GB_R4
@@ -408,7 +408,7 @@ cudaError_t nbody_leapfrog(const DevPot& P, const DevBodies& B, int scheme, cons
     const int hasp = Np > 0;
     const size_t nthreads = hasp ? Np : 1;
     if (block > 128 || block <= 0) block = 128;
-    Ruth4Coef rc;
+    NbodyRuth4Coef rc;
     for (int k = 0; k < 4; k++) { rc.cs[k] = cs ? cs[k] : 0.; rc.ds[k] = ds ? ds[k] : 0.; }
     GB_SIG_SWITCH2(P.sig, (k_nbody_leapfrog<C><<<nblocks(nthreads, block), block, 0, s>>>(
         P, B, rc, scheme, body_w0, group, w0, t1, Np, hasp, t0, tfinal, nsteps_fixed, dt, out_p, out_b, body_writer, traj, ntot)));

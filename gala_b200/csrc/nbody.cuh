@@ -52,14 +52,14 @@ GB_DEV void gb_nbody_grad_symplectic(const DevPot& P, const DevBodies& B, double
 // state body_w0[group[p]] and takes nsteps = int((tfinal - t1)/dt + 0.5) steps (mockstream.pyx:571) or
 // `nsteps_fixed` (leapfrog_integrate_nbody).  traj != null: every step is stored as rows of
 // (ntimes, ntot, 6) (leapfrog.pyx:249-252), the bodies by lane `body_writer`.
-struct Ruth4Coef { double cs[4], ds[4]; };   // ruth4.pyx:166-178, computed on the host
+struct NbodyRuth4Coef { double cs[4], ds[4]; };   // ruth4.pyx:166-178, computed on the host
 
 // scheme 0: leapfrog (above).  scheme 1: Ruth4 (c_ruth4_step_nbody, ruth4.pyx:116-136): no half-step
 // velocity; every point takes its four sub-stages in one go while the others stay where they are.
 template <class C>
 __global__ void __launch_bounds__(128)
 k_nbody_leapfrog(const __grid_constant__ DevPot P, const __grid_constant__ DevBodies B,
-                 const __grid_constant__ Ruth4Coef rc, int scheme,
+                 const __grid_constant__ NbodyRuth4Coef rc, int scheme,
                  const double* __restrict__ body_w0, const int32_t* __restrict__ group,
                  const double* __restrict__ w0, const double* __restrict__ t1, size_t Np, int has_particle,
                  double t0, double tfinal, int nsteps_fixed, double dt,
