@@ -12,6 +12,7 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/gala_b200.h"
@@ -145,7 +146,22 @@ void mp_pack(const double* params, int lmax, std::vector<double>& ext) {
 // PowerLawCutoff, fast build: Chebyshev fit of F(s) = gamma*(a, s^2) = P(a, s^2) / s^(2a) (Tricomi's entire
 // incomplete gamma function) on GB_PLC_NINT equal intervals of s in [0, GB_PLC_SMAX], degree GB_PLC_DEG.
 // F(s) = e^-x sum_n x^n / Gamma(a+n+1), x = s^2: all terms positive, summed in long double.
+void plc_fit(double a, std::vector<double>& ext);
+// The fit costs 1.4 ms of long-double arithmetic (more on a loaded host) and depends on `a` only: the last few are
+// kept, so repeated calls with the same bulge (every integrate_orbit of one potential) skip it.
 void plc_pack(double a, std::vector<double>& ext) {
+    static std::mutex mu;
+    static std::vector<std::pair<double, std::vector<double>>> memo;
+    std::lock_guard<std::mutex> g(mu);
+    for (const auto& e : memo)
+        if (e.first == a) { ext.insert(ext.end(), e.second.begin(), e.second.end()); return; }
+    std::vector<double> tab;
+    plc_fit(a, tab);
+    if (memo.size() >= 8) memo.erase(memo.begin());
+    memo.emplace_back(a, tab);
+    ext.insert(ext.end(), tab.begin(), tab.end());
+}
+void plc_fit(double a, std::vector<double>& ext) {
     const int D = GB_PLC_DEG + 1;
     const long double h = (long double)GB_PLC_SMAX / GB_PLC_NINT, pi = 3.14159265358979323846264338327950288L;
     auto F = [&](long double sx) {

@@ -16,8 +16,13 @@ for name, pot in cases:
     t = np.arange(1001.0)
     for _ in range(2):
         gb.leapfrog_integrate_hamiltonian(H, w0, t, save_all=0)
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    for _ in range(3):
-        gb.leapfrog_integrate_hamiltonian(H, w0, t, save_all=0)
-    torch.cuda.synchronize(); el = (time.perf_counter() - t0) / 3
-    print(f"{name:32s} leapfrog 3.03e6 x 1000: {el * 1e3:7.2f} ms  {3031040 * 1000 / el:.3e} orbit-steps/s")
+    torch.cuda.synchronize()
+    ev, wall = [], []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(); gb.leapfrog_integrate_hamiltonian(H, w0, t, save_all=0); e1.record()
+        torch.cuda.synchronize(); wall.append((time.perf_counter() - t0) * 1e3); ev.append(e0.elapsed_time(e1))
+    el = float(np.median(ev)) * 1e-3
+    print(f"{name:32s} leapfrog 3.03e6 x 1000: {el * 1e3:7.2f} ms (CUDA events, median of 5; min {min(ev):.2f} max {max(ev):.2f}; "
+          f"host wall median {np.median(wall):.2f})  {3031040 * 1000 / el:.3e} orbit-steps/s", flush=True)
