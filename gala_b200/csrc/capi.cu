@@ -102,9 +102,36 @@ static_assert(GB_CEXT == 2 * (GB_SCF_NMAX_CONST + 1) * ((GB_SCF_LMAX_CONST + 1) 
 struct Resolved {
     DevPot P;
     std::vector<double> ext;   // host copy of large parameter blocks (SCF coefficients)
-    double* d_ext = nullptr;   // device copy (owned)
-    ~Resolved() { if (d_ext) cudaFree(d_ext); }
+    double* d_ext = nullptr;   // device copy (owned by the table cache below)
 };
+
+// Device copies of the large parameter blocks, kept across calls: a cudaMalloc + cudaFree pair per call cost
+// 7-30 ms inside a process that holds tens of GB of torch allocations (measured on BovyMWPotential2014:
+// 40-66 ms per call around a 34 ms kernel).  Keyed on (device, contents); at most 16 entries, oldest evicted
+// (cudaFree waits for the device, so an evicted table cannot be in use).
+struct ExtEntry { int dev; std::vector<double> host; double* d; };
+cudaError_t ext_cache_get(const std::vector<double>& ext, double** out) {
+    static std::mutex mu;
+    static std::vector<ExtEntry> cache;
+    std::lock_guard<std::mutex> g(mu);
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    for (size_t i = 0; i < cache.size(); i++)
+        if (cache[i].dev == dev && cache[i].host.size() == ext.size() &&
+            memcmp(cache[i].host.data(), ext.data(), ext.size() * sizeof(double)) == 0) {
+            if (i + 1 != cache.size()) { ExtEntry t = std::move(cache[i]); cache.erase(cache.begin() + i); cache.push_back(std::move(t)); }
+            *out = cache.back().d;
+            return cudaSuccess;
+        }
+    if (cache.size() >= 16) { cudaFree(cache.front().d); cache.erase(cache.begin()); }
+    double* d = nullptr;
+    if ((e = cudaMalloc(&d, ext.size() * sizeof(double))) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(d, ext.data(), ext.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) { cudaFree(d); return e; }
+    cache.push_back(ExtEntry{dev, ext, d});
+    *out = d;
+    return cudaSuccess;
+}
 
 // SCF coefficients for the device (scf.cuh): (S,T) pairs in [l][m<=l][n] order with the spherical-
 // harmonic normalisation sqrt((2l+1)/(4 pi) (l-m)!/(l+m)!) (what gsl_sf_legendre_sphPlm and the
@@ -296,8 +323,7 @@ int resolve(const gb_potential* pot, Resolved& r, cudaStream_t stream) {
     }
 
     if (!r.ext.empty()) {
-        CU(cudaMalloc(&r.d_ext, r.ext.size() * sizeof(double)));
-        CU(cudaMemcpyAsync(r.d_ext, r.ext.data(), r.ext.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+        CU(ext_cache_get(r.ext, &r.d_ext));
         P.ext = r.d_ext;
     }
     return 0;
