@@ -110,10 +110,19 @@ struct Resolved {
 // 40-66 ms per call around a 34 ms kernel).  Keyed on (device, contents); at most 16 entries, oldest evicted
 // (cudaFree waits for the device, so an evicted table cannot be in use).
 struct ExtEntry { int dev; std::vector<double> host; double* d; };
+std::mutex g_ext_mu;
+std::vector<ExtEntry> g_ext_cache;
+void ext_cache_clear() {            // gb_release_scratch
+    std::lock_guard<std::mutex> g(g_ext_mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto& e : g_ext_cache) { cudaSetDevice(e.dev); cudaFree(e.d); }
+    g_ext_cache.clear();
+    cudaSetDevice(cur);
+}
 cudaError_t ext_cache_get(const std::vector<double>& ext, double** out) {
-    static std::mutex mu;
-    static std::vector<ExtEntry> cache;
-    std::lock_guard<std::mutex> g(mu);
+    std::vector<ExtEntry>& cache = g_ext_cache;
+    std::lock_guard<std::mutex> g(g_ext_mu);
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -124,7 +133,7 @@ cudaError_t ext_cache_get(const std::vector<double>& ext, double** out) {
             *out = cache.back().d;
             return cudaSuccess;
         }
-    if (cache.size() >= 16) { cudaFree(cache.front().d); cache.erase(cache.begin()); }
+    if (cache.size() >= 16) { cudaSetDevice(cache.front().dev); cudaFree(cache.front().d); cudaSetDevice(dev); cache.erase(cache.begin()); }
     double* d = nullptr;
     if ((e = cudaMalloc(&d, ext.size() * sizeof(double))) != cudaSuccess) return e;
     if ((e = cudaMemcpy(d, ext.data(), ext.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) { cudaFree(d); return e; }
@@ -529,6 +538,7 @@ int gb_release_scratch(void) {
         if (sc.dev != cur) cudaSetDevice(cur);
         sc.ptr = nullptr; sc.cap = 0; sc.dev = -1;
     }
+    ext_cache_clear();
     return 0;
 }
 

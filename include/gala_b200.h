@@ -301,7 +301,8 @@ double gb_fp64_peak_tflops(int reps);
 
 /* Frees the device staging / scratch buffers the library keeps cached between calls (HOST-mode staging
  * of inputs and outputs; the orbit-major dense-output scratch of gb_dop853, up to half of the free
- * device memory).  Safe to call at any time from the thread that made the calls. */
+ * device memory; the device copies of SCF / multipole coefficient blocks and of the PowerLawCutoff
+ * table, at most 16 small buffers).  Safe to call at any time from the thread that made the calls. */
 int gb_release_scratch(void);
 
 /* Diagnostic: y[i] = f(x[i]) with the math primitive the selected build (opt->strict_math) uses
