@@ -35,8 +35,15 @@ sys.path.insert(0, ROOT)
 SM_FILL = 148 * 2048          # resident threads of one B200 at full occupancy
 
 # algorithmic flops per orbit-step (source-level op counts)
-FLOPS = {"headline": 146, "c1": 46, "c4": 666, "c2": 3970, "c5": 3400, "c3": 146, "c3d": 0,
+FLOPS = {"headline": 146, "c1": 46, "c1x": 46, "c4": 666, "c2": 3970, "c5": 3400, "c3": 146, "c3d": 0,
          "c3sg": 2 * 146 + 20, "c3sgd": 0}      # self-gravity lane: progenitor + particle gradients + one Plummer term
+# workloads whose kernel is bound by the trajectory write, not by the FP64 pipe: the roofline is HBM GB/s against
+# MEASURED_PEAKS.json.  Algorithmic bytes per orbit-step = 48 (one (x, v) row written), plus
+# the 48-byte initial condition read once per orbit.
+HBM_BOUND = {"c1", "c1x"}
+# total orbits of the strong-scaling single-call measurement (one host array, one C-ABI call over all devices):
+# 8 x the per-GPU default, C5 at exactly the 10^7 orbits of BASELINE.json configs[4]
+TOTAL_ORBITS = {"headline": 8 * 10 * SM_FILL, "c4": 8 * 4 * SM_FILL, "c5": 10_000_000}
 
 
 def make_ic(N, seed, pot_gradient, rmin=4.0, rmax=50.0):
@@ -80,6 +87,15 @@ def workload(name, n_orbits):
         desc = f"C1: NFWPotential(m=1e11,r_s=12) leapfrog dt=1Myr 1000 steps save_all, {N} orbits/GPU"
         run = lambda w0, tt, out=None: gb.leapfrog_integrate_hamiltonian(H, w0, tt, save_all=1, out=out)[1]
         units = lambda N_, out: N_ * 1000
+    elif name == "c1x":
+        # the save_all path at a size that fills the GPU: the kernel writes 48 B per orbit-step and does 46 flops
+        # for it, so it is bound by HBM write bandwidth (north_star: "achieved HBM GB/s when trajectory output dominates")
+        H = gb.Hamiltonian(gb.NFWPotential(m=1e11, r_s=12.0))
+        t = np.arange(257, dtype=float)
+        N = n_orbits or (1 << 20)
+        desc = f"C1x: NFWPotential(m=1e11,r_s=12) leapfrog dt=1Myr 256 steps save_all, {N} orbits/GPU (C1 at GPU-filling size)"
+        run = lambda w0, tt, out=None: gb.leapfrog_integrate_hamiltonian(H, w0, tt, save_all=1, out=out)[1]
+        units = lambda N_, out: N_ * 256
     elif name == "c4":
         pot = gb.CCompositePotential()
         pot["bar"] = gb.LongMuraliBarPotential(m=1e10, a=4.0, b=0.8, c=0.25, alpha=np.deg2rad(25.0))
@@ -237,52 +253,179 @@ class ClockSampler:
                 "samples": len(sm), "how": self.how}
 
 
-def cpu_reference_rate(name, H, t, seconds_target=12.0, threads=None):
-    """Times the reference's CPU implementation (oracle/_ref/libgala_ref_fast.so; the plain-C port if the
-    compiled reference is absent) with all host threads on a bounded sample of the workload."""
+def _cpu_jobs(name, H, t, chk, n_jobs, per_job_seconds):
+    """Bounded samples of workload `name` for the CPU arm: a list of n_jobs callables, each integrating its own
+    sample with the reference's CPU code and returning the units it processed, in the SAME unit the GPU arm
+    reports (orbit-steps; DOP853: attempted internal steps; mock streams: particle-steps).  Also returns a
+    description of one sample."""
+    import gala_b200 as gb
+    pot = H.potential
+    grad = lambda q: chk.gradient(pot, q)
+
+    if name in ("headline", "c1", "c1x", "c4", "c5", "c2"):
+        if name == "c2":
+            def one(w0):
+                # attempted steps of the reference's own dop853() (nbatch=1 = the per-orbit control the GPU computes),
+                # observed through its right-hand-side calls: dense = 1 + 11 nstep + 4 naccpt, final = 1 + 11 nstep + naccpt
+                _, _, _, calls_d = chk.dop853_nfcn(H, w0, t, save_all=True, nbatch=1)
+                return calls_d
+            def steps_of(w0, calls_d):      # untimed: the second observation that separates nstep from naccpt
+                _, _, _, calls_f = chk.dop853_nfcn(H, w0, t, save_all=False, nbatch=1)
+                nacc = (calls_d - calls_f) // 3
+                return int(((calls_f - 1 - nacc) // 11).sum())
+        elif name == "c4":
+            one = lambda w0: chk.ruth4(H, w0, t, save_all=False) is None or w0.shape[1] * (len(t) - 1)
+        else:
+            sv = name in ("c1", "c1x")
+            one = lambda w0: chk.leapfrog(pot, w0, t, save_all=sv) is None or w0.shape[1] * (len(t) - 1)
+        probe_n = 16 if name == "c5" else 64
+        w_probe = make_ic(probe_n, 99, grad)
+        t0 = time.perf_counter(); one(w_probe); dt_probe = time.perf_counter() - t0
+        per_job = int(max(probe_n // 4, min(200_000, probe_n * per_job_seconds / max(dt_probe, 1e-4))))
+        w0s = [make_ic(per_job, 100 + k, grad) for k in range(n_jobs)]
+        if name == "c2":
+            def mk(w0):
+                def job():
+                    job.calls = one(w0)
+                    return 0
+                job.post = lambda: steps_of(w0, job.calls)
+                return job
+            return [mk(w) for w in w0s], f"{per_job} orbits x {len(t)} dense-output times"
+        return [(lambda w=w: one(w)) for w in w0s], f"{per_job} orbits x {len(t) - 1} steps"
+
+    if name in ("c3", "c3d", "c3sg", "c3sgd"):
+        # the reference's mock-stream loops (dynamics/mockstream/mockstream.pyx:442-620 leapfrog, :176-303 dop853):
+        # for every release time the rows [progenitor, its particles] are integrated from there to tfinal --
+        # fixed step: c_leapfrog_step_nbody over the rows; adaptive: ONE dop853 system of all rows (shared step).
+        # A sample = every `stride`-th release time (work per release time is linear in the remaining time, so a
+        # uniform subset is unbiased); units = particle-steps, as the GPU arm counts them.
+        from oracle import oracle
+        n_steps, n_part = 5000, 10
+        selfgrav = name in ("c3sg", "c3sgd")
+        pps = [gb.PlummerPotential(m=2.5e4, b=0.05) if selfgrav else None]
+        w_prog = np.array([13.0, 0.0, 20.0, 0.0, 130.0 * gb.KMS_TO_KPC_MYR, 50.0 * gb.KMS_TO_KPC_MYR]).reshape(6, 1)
+        tt = np.arange(n_steps + 1) * -1.0
+        prog = chk.leapfrog(pot, w_prog, tt, save_all=True)[:, ::-1, 0]      # (6, ntimes) from the earliest time on
+        tf = tt[::-1].copy()
+        # groups cost ~ (remaining steps) x 21 rows; probe one mid group to size the stride
+        def group_rows(i, rng):
+            x, v, _ = oracle.fardal_release_numpy(chk, pot, prog[:3, i:i + 1].T, prog[3:, i:i + 1].T, tf[i:i + 1],
+                                                  np.array([2.5e4]), np.array([n_part]), rng, gala_modified=True)
+            return np.vstack([prog[:, i], np.hstack([x, v])])
+        def run_group(i, rows):
+            nst = n_steps - i
+            if nst == 0:
+                return 0
+            if name in ("c3", "c3sg"):
+                chk.nbody_leapfrog(H, pps, rows, tf[i], nst, 1.0)
+            elif selfgrav:
+                chk.nbody_dop853(H, pps, rows, t1=tf[i], t2=tf[-1], dt0=1.0, mode=1)
+            else:
+                chk.dop853_step_rows(H, rows, tf[i], tf[-1], 1.0, group=False)
+            return 2 * n_part * nst
+        rng = np.random.RandomState(42)
+        rows_mid = group_rows(n_steps // 2, rng)
+        t0 = time.perf_counter(); run_group(n_steps // 2, rows_mid); dt_mid = time.perf_counter() - t0
+        n_groups = int(max(2, min(400, per_job_seconds / max(dt_mid, 1e-4))))
+        jobs = []
+        for k in range(n_jobs):
+            idx = np.linspace(0, n_steps - 1, n_groups, dtype=int) + (k % max(1, n_steps // n_groups // 2))
+            idx = np.clip(idx, 0, n_steps - 1)
+            rows = [group_rows(int(i), rng) for i in idx]
+            jobs.append(lambda idx=idx, rows=rows: sum(run_group(int(i), r) for i, r in zip(idx, rows)))
+        return jobs, f"{n_groups} of the {n_steps + 1} release times x {2 * n_part} particles (+ the progenitor row)"
+    raise ValueError(f"no CPU arm for workload {name}")
+
+
+def cpu_reference_rate(name, H, t, seconds_target=12.0, threads=None, one_thread=True):
+    """Times the reference's CPU implementation (oracle/_ref/libgala_ref_fast.so = the reference's own C++ built with
+    its shipped flags; the plain-C port if the compiled reference is absent) on a bounded sample of the workload:
+    with all host threads (`value`, `cores`) and on one thread (`value_1thread`; the reference itself is
+    single-threaded).  Unit = the GPU arm's."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import oracle
-    import gala_b200 as gb
     if oracle.have_ref("fast"):
         chk, kind = oracle.Ref("fast"), "reference"
     else:
         chk, kind = oracle.Port(), "port"
     threads = threads or os.cpu_count() or 1
-    pot = H.potential
-    # per-thread sample sized from a quick probe
-    probe_n = 64
-    w_probe = make_ic(probe_n, 99, lambda q: chk.gradient(pot, q))
 
-    def one(w0):
-        if name in ("headline", "c1"):
-            chk.leapfrog(pot, w0, t, save_all=(name == "c1")); return w0.shape[1] * (len(t) - 1)
-        if name == "c4":
-            chk.ruth4(H, w0, t, save_all=False); return w0.shape[1] * (len(t) - 1)
-        if name == "c2":
-            # reference default nbatch=100 couples the orbits of a batch; count output samples instead of
-            # internal steps is not comparable, so use nbatch=1 semantics == what the GPU computes
-            out, st, rc = chk.dop853(H, w0, t, save_all=True, nbatch=1); return None
-        raise ValueError(name)
-    t0 = time.perf_counter(); one(w_probe); dt_probe = time.perf_counter() - t0
-    per_thread = int(max(probe_n, min(200_000, probe_n * seconds_target / max(dt_probe, 1e-4))))
-    w0s = [make_ic(per_thread, 100 + k, lambda q: chk.gradient(pot, q)) for k in range(threads)]
-    best = None
-    for _ in range(2):
+    def timed(n_jobs, seconds, repeats):
+        jobs, what = _cpu_jobs(name, H, t, chk, n_jobs, seconds)
+        best, units = None, 0
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            if n_jobs == 1:
+                got = [jobs[0]()]
+            else:
+                with ThreadPoolExecutor(n_jobs) as ex:       # ctypes releases the GIL: real parallelism
+                    got = list(ex.map(lambda j: j(), jobs))
+            el = time.perf_counter() - t0
+            best = el if best is None else min(best, el)
+            units = sum(got)
+        if hasattr(jobs[0], "post"):                          # c2: step counts need a second (untimed) observation
+            units = sum(j.post() for j in jobs)
+        return units / best, best, what
+
+    v_all, el_all, what = timed(threads, seconds_target, 2)
+    flags = chk.build_flags() if kind == "reference" else "port -O2"
+    out = {"value": v_all, "unit": "orbit-steps/s", "cores": threads, "kind": kind, "sample_seconds": el_all,
+           "sample": f"{threads} threads x ({what}), best of 2, {flags}"}
+    if one_thread:
+        v_1, el_1, what1 = timed(1, max(2.0, seconds_target / 3.0), 1)
+        out["value_1thread"] = v_1
+        out["sample_1thread"] = f"1 thread x ({what1}), {el_1:.1f} s"
+    return out
+
+
+def config_of(desc, N, ntimes, world):
+    """The `config` object of the JSON line; identical on the GPU arm and on the reference arm."""
+    in_bytes = 48 * N
+    out_bytes = 48 * N * (ntimes if "save_all" in desc or "dense-output" in desc else 1)
+    big = max(in_bytes, out_bytes) > 126e6
+    return {"workload": desc, "orbits_per_gpu": N, "ntimes": int(ntimes),
+            "l2": f"inputs {in_bytes / 1e6:.0f} MB, outputs {out_bytes / 1e6:.0f} MB per launch" +
+                  (" > 126 MB L2" if big else " (compute-bound kernel: inputs read once per launch, state in registers)"),
+            "parallelism": f"orbit-index sharding x{world}, no collectives"}
+
+
+def measured_hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (driver-written, copy bandwidth)"
+    except Exception:
+        return 6500.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+
+
+def single_call_strong(args, gb, torch, H, t, run, world, name):
+    """Strong scaling through the drop-in API (north_star: "each GPU takes a contiguous slice of orbits and results
+    are gathered to the host"): ONE pinned host array of TOTAL_ORBITS[name] orbits, ONE call of the public function
+    with gb.set_devices(range(world)) -- the C ABI shards it (gb_launch.n_devices), every device copies its slice
+    in, integrates, copies its slice of the result straight into the one output array.  Runs on rank 0 only while
+    the other ranks wait on a CPU barrier (their GPUs are idle and are driven by rank 0's process here)."""
+    total = args.total_orbits or TOTAL_ORBITS.get(name)
+    if not total:
+        return {"skipped": f"single-call strong scaling is measured on the final-state workloads ({sorted(TOTAL_ORBITS)})"}
+    if gb._abi.device_count() < world:
+        return {"skipped": f"rank 0 sees {gb._abi.device_count()} devices, needs {world}"}
+    w0 = make_ic(total, 4242, lambda q: H.potential.gradient(q))
+    pin_in = gb.pinned_empty(w0.shape); pin_in[...] = w0
+    pin_out = gb.pinned_empty(w0.shape)
+    devs = list(range(world))
+    gb.set_devices(devs)
+    try:
+        for _ in range(3):
+            run(pin_in, t, pin_out)
         t0 = time.perf_counter()
-        with ThreadPoolExecutor(threads) as ex:       # ctypes releases the GIL: real parallelism
-            units = list(ex.map(one, w0s))
+        for _ in range(args.steps):
+            run(pin_in, t, pin_out)          # returns when every device has delivered its slice
         el = time.perf_counter() - t0
-        best = el if best is None else min(best, el)
-    if name == "c2":
-        # orbit-steps of the adaptive run: take the GPU definition (attempted steps) from a strict rerun is
-        # not available on the CPU side without instrumenting the reference; report orbits*outputs instead
-        total = threads * per_thread * len(t)
-        unit = "orbit-output-samples/s"
-    else:
-        total = sum(units); unit = "orbit-steps/s"
-    return {"value": total / best, "unit": unit, "cores": threads, "kind": kind, "sample_seconds": best,
-            "sample": f"{threads} threads x {per_thread} orbits x {len(t) - 1} steps, best of 2, "
-                      f"{chk.build_flags() if kind == 'reference' else 'port -O2'}"}
+    finally:
+        gb.set_devices(None)
+    nst = len(t) - 1
+    return {"value": total * nst * args.steps / el, "unit": "orbit-steps/s", "ms_per_call": el / args.steps * 1e3,
+            "orbits": int(total), "devices": devs, "scaling": "strong",
+            "h2d_bytes_per_call": int(pin_in.nbytes + t.nbytes), "d2h_bytes_per_call": int(pin_out.nbytes),
+            "what": "one pinned host (6,N) array in, one C-ABI call over all devices (gb_launch.n_devices), one (6,N) array out; wall clock on rank 0"}
 
 
 def main():
@@ -296,6 +439,8 @@ def main():
     ap.add_argument("--strict", action="store_true", help="use the strict-IEEE kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-single-call", action="store_true", help="skip the strong-scaling single-call measurement")
+    ap.add_argument("--total-orbits", type=int, default=0, help="orbits of the single-call measurement (0 = workload default)")
     ap.add_argument("--smi-clocks", action="store_true", help="sample clocks with an nvidia-smi child (A/B only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -317,7 +462,7 @@ def main():
         H, t, N, desc, run, units = workload(args.workload, args.orbits)
         vals = []
         for k in range(args.warmup + args.steps):
-            r = cpu_reference_rate(args.workload, H, t, seconds_target=4.0)
+            r = cpu_reference_rate(args.workload, H, t, seconds_target=4.0, one_thread=(k == args.warmup + args.steps - 1))
             if k >= args.warmup:
                 vals.append(r)
         v = float(np.mean([r["value"] for r in vals])) if vals else float("nan")
@@ -326,7 +471,7 @@ def main():
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": float(np.mean([r["sample_seconds"] for r in vals])) * 1e3 if vals else None,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": {"workload": desc},
+                "dtype": "f64", "data": "synthetic", "config": config_of(desc, N, len(t), args.gpus),
                 "cpu_baseline": cb,
                 "e2e": {"value": v, "unit": cb["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -338,8 +483,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")      # a barrier that does not put a spinning kernel on the GPUs
 
     H, t, N, desc, run, units = workload(args.workload, args.orbits)
     H.strict_math = args.strict
@@ -423,6 +570,19 @@ def main():
         e2e = {"value": ue.item() / te.item(), "unit": "orbit-steps/s",
                "h2d_bytes_per_step": int(w0_host.nbytes + t.nbytes), "d2h_bytes_per_step": int(np.asarray(out_h).nbytes)}
 
+    # strong scaling through ONE call over all devices, rank 0 only (the other ranks idle on a CPU barrier)
+    single = None
+    if not args.no_single_call and not args.no_e2e:
+        if world > 1:
+            dist.barrier(group=cpu_group)
+        if rank == 0:
+            try:
+                single = single_call_strong(args, gb, torch, H, t, run, world, args.workload)
+            except Exception as e:
+                single = {"error": f"{type(e).__name__}: {e}"}
+        if world > 1:
+            dist.barrier(group=cpu_group)
+
     if rank == 0:
         flops = FLOPS.get(args.workload, 0)
         per_launch_units = tot_units / max(args.steps, 1)
@@ -436,18 +596,22 @@ def main():
             "metric": "FP64 orbit-steps/sec", "value": value, "unit": "orbit-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "orbits_per_gpu": N, "ntimes": int(len(t)),
-                       "math": "strict" if args.strict else "fast",
-                       "l2": f"inputs {w0_host.nbytes / 1e6:.0f} MB per launch" +
-                             (" > 126 MB L2" if w0_host.nbytes > 126e6 else " (compute-bound kernel: inputs read once per 1000 steps)"),
-                       "parallelism": f"orbit-index sharding x{world}, no collectives"},
+            "config": config_of(desc, N, len(t), world), "math": "strict" if args.strict else "fast",
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf if peak_tf > 0 else None, "traffic": traffic,
                          "flops_per_orbit_step": flops,
                          "peak_source": "DFMA microbenchmark measured live (gala_b200/csrc/peak.cu); "
                                         "MEASURED_PEAKS.json has no FP64 entry"},
-            "clocks": clk, "gpu_launches": launches, "e2e": e2e,
+            "clocks": clk, "gpu_launches": launches, "e2e": e2e, "single_call": single,
         }
+        if args.workload in HBM_BOUND:
+            # trajectory output dominates: 48 B written per orbit-step (+ 48 B read per orbit), against the measured HBM peak
+            hbm_peak, hbm_src = measured_hbm_peak()
+            alg_bytes = 48.0 * per_launch_units + 48.0 * N
+            gbs = alg_bytes / mean_kern_s / 1e9
+            line["roofline"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                "traffic": traffic, "bytes_per_orbit_step": 48, "peak_source": hbm_src,
+                                "fp64_frac": achieved_tf / peak_tf if peak_tf > 0 else None}
         if not args.no_cpu_baseline and world == 1:
             try:
                 line["cpu_baseline"] = cpu_reference_rate(args.workload, H, t)

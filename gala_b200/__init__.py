@@ -6,6 +6,7 @@ Leapfrog / Ruth4 / DOPRI853, and ``MockStreamGenerator`` with ``FardalStreamDF``
 All arithmetic runs in hand-written CUDA kernels behind the C ABI of ``include/gala_b200.h``.
 """
 from . import _abi
+from ._abi import set_devices, get_devices
 from .units import galactic, dimensionless, G_GALACTIC, KMS_TO_KPC_MYR
 from .potential import *          # noqa: F401,F403
 from .frame import StaticFrame, ConstantRotatingFrame

@@ -43,7 +43,8 @@ class gb_frame(C.Structure):
 
 class gb_launch(C.Structure):
     _fields_ = [("mem", C.c_int32), ("device", C.c_int32), ("stream", C.c_void_p),
-                ("strict_math", C.c_int32), ("block_threads", C.c_int32)]
+                ("strict_math", C.c_int32), ("block_threads", C.c_int32),
+                ("n_devices", C.c_int32), ("_pad", C.c_int32), ("devices", c_int32_p)]
 
 
 class gb_bodies(C.Structure):
@@ -189,16 +190,64 @@ class Buf:
             self.ptr = arr.ctypes.data
 
 
-def launch_opts(device_mem: bool, strict: bool = False, stream=None, block: int = 0, device: int = -1):
+_devices = None      # process-wide default device list for host-buffer calls (set_devices)
+
+
+def set_devices(devices=None):
+    """Shard every host-buffer (numpy) call of the sharding entry points -- ``gb_leapfrog``, ``gb_ruth4``,
+    ``gb_dop853``, ``gb_mockstream_dop853 / _leapfrog``, potential / Hamiltonian evaluation -- over these CUDA
+    devices inside the C ABI (``gb_launch.n_devices``): contiguous orbit slices, one host thread per device, the
+    results land in the one output array.  ``"all"`` = every visible device; ``None`` / ``[]`` = the current device
+    only (default).  The environment variable ``GALA_B200_DEVICES`` ("all" or "0,1,2,3") sets the initial value."""
+    global _devices
+    if devices is None or (not isinstance(devices, str) and len(devices) == 0):
+        _devices = None
+    elif isinstance(devices, str) and devices.strip().lower() == "all":
+        n = device_count()
+        _devices = list(range(n)) if n > 1 else None
+    else:
+        if isinstance(devices, str):
+            devices = [int(x) for x in devices.split(",") if x.strip() != ""]
+        devs = [int(d) for d in devices]
+        if len(set(devs)) != len(devs) or any(d < 0 for d in devs):
+            raise ValueError("devices must be distinct non-negative CUDA ordinals")
+        _devices = devs
+    return _devices
+
+
+def get_devices():
+    return None if _devices is None else list(_devices)
+
+
+def launch_opts(device_mem: bool, strict: bool = False, stream=None, block: int = 0, device: int = -1,
+                devices=False):
+    """``devices``: list of CUDA ordinals to shard a host-buffer call over; ``None`` = the process default of
+    ``set_devices`` (what the wrappers of the sharding entry points pass); ``False`` = a single device (entry
+    points that run on one device reject a device list)."""
     o = gb_launch()
     o.mem = MEM_DEVICE if device_mem else MEM_HOST
     o.device = device
     o.stream = stream
     o.strict_math = 1 if strict else 0
     o.block_threads = block
+    if devices is None:
+        devices = _devices
+    if devices and not device_mem and len(devices) > 0:
+        arr = (C.c_int32 * len(devices))(*devices)
+        o._keep = arr                      # the struct only holds a pointer
+        o.n_devices = len(devices)
+        o.devices = C.cast(arr, c_int32_p)
     return o
 
 
 def as_f64(a, shape_ndim=None):
     """C-contiguous float64 view/copy of a numpy-like array (host path)."""
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+if os.environ.get("GALA_B200_DEVICES"):
+    try:
+        set_devices(os.environ["GALA_B200_DEVICES"])
+    except Exception as _e:            # a bad value must not make the package unimportable
+        import warnings
+        warnings.warn(f"GALA_B200_DEVICES ignored: {_e}")

@@ -12,6 +12,7 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -99,25 +100,36 @@ void gb_derive(int type, const double* p, double* d) {
 #define GB_SCF_LMAX_CONST 6
 static_assert(GB_CEXT == 2 * (GB_SCF_NMAX_CONST + 1) * ((GB_SCF_LMAX_CONST + 1) * (GB_SCF_LMAX_CONST + 2) / 2), "cext layout");
 
+void ext_cache_unpin(double* d);
 struct Resolved {
     DevPot P;
     std::vector<double> ext;   // host copy of large parameter blocks (SCF coefficients)
-    double* d_ext = nullptr;   // device copy (owned by the table cache below)
+    double* d_ext = nullptr;   // device copy (owned by the table cache below, pinned there while this object lives)
+    Resolved() = default;
+    Resolved(const Resolved&) = delete;
+    Resolved& operator=(const Resolved&) = delete;
+    ~Resolved() { if (d_ext) ext_cache_unpin(d_ext); }
 };
 
 // Device copies of the large parameter blocks, kept across calls: a cudaMalloc + cudaFree pair per call cost
 // 7-30 ms inside a process that holds tens of GB of torch allocations (measured on BovyMWPotential2014:
-// 40-66 ms per call around a 34 ms kernel).  Keyed on (device, contents); at most 16 entries, oldest evicted
-// (cudaFree waits for the device, so an evicted table cannot be in use).
-struct ExtEntry { int dev; std::vector<double> host; double* d; };
+// 40-66 ms per call around a 34 ms kernel).  Keyed on (device, contents); at most 16 unpinned entries, the
+// oldest unpinned one is evicted.  An entry is pinned from resolve() until the call that resolved it has
+// launched its kernels (Resolved's destructor), so a concurrent caller cannot free a table between another
+// thread's lookup and its launch; after the launch cudaFree's implicit device synchronisation protects it.
+struct ExtEntry { int dev; std::vector<double> host; double* d; int pins; };
 std::mutex g_ext_mu;
 std::vector<ExtEntry> g_ext_cache;
 void ext_cache_clear() {            // gb_release_scratch
     std::lock_guard<std::mutex> g(g_ext_mu);
     int cur = 0;
     cudaGetDevice(&cur);
-    for (auto& e : g_ext_cache) { cudaSetDevice(e.dev); cudaFree(e.d); }
-    g_ext_cache.clear();
+    std::vector<ExtEntry> keep;
+    for (auto& e : g_ext_cache) {
+        if (e.pins > 0) { keep.push_back(std::move(e)); continue; }     // in use by a call in flight on another thread
+        cudaSetDevice(e.dev); cudaFree(e.d);
+    }
+    g_ext_cache.swap(keep);
     cudaSetDevice(cur);
 }
 cudaError_t ext_cache_get(const std::vector<double>& ext, double** out) {
@@ -130,16 +142,27 @@ cudaError_t ext_cache_get(const std::vector<double>& ext, double** out) {
         if (cache[i].dev == dev && cache[i].host.size() == ext.size() &&
             memcmp(cache[i].host.data(), ext.data(), ext.size() * sizeof(double)) == 0) {
             if (i + 1 != cache.size()) { ExtEntry t = std::move(cache[i]); cache.erase(cache.begin() + i); cache.push_back(std::move(t)); }
+            cache.back().pins++;
             *out = cache.back().d;
             return cudaSuccess;
         }
-    if (cache.size() >= 16) { cudaSetDevice(cache.front().dev); cudaFree(cache.front().d); cudaSetDevice(dev); cache.erase(cache.begin()); }
+    if (cache.size() >= 16)
+        for (size_t i = 0; i < cache.size(); i++)
+            if (cache[i].pins == 0) {
+                cudaSetDevice(cache[i].dev); cudaFree(cache[i].d); cudaSetDevice(dev);
+                cache.erase(cache.begin() + i);
+                break;
+            }
     double* d = nullptr;
     if ((e = cudaMalloc(&d, ext.size() * sizeof(double))) != cudaSuccess) return e;
     if ((e = cudaMemcpy(d, ext.data(), ext.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) { cudaFree(d); return e; }
-    cache.push_back(ExtEntry{dev, ext, d});
+    cache.push_back(ExtEntry{dev, ext, d, 1});
     *out = d;
     return cudaSuccess;
+}
+void ext_cache_unpin(double* d) {
+    std::lock_guard<std::mutex> g(g_ext_mu);
+    for (auto& e : g_ext_cache) if (e.d == d) { if (e.pins > 0) e.pins--; return; }
 }
 
 // SCF coefficients for the device (scf.cuh): (S,T) pairs in [l][m<=l][n] order with the spherical-
@@ -266,6 +289,8 @@ int resolve(const gb_potential* pot, Resolved& r, cudaStream_t stream) {
         if (c.type_id == GB_POT_SCF) {
             nsmall = 5;
             const int nmax = (int)c.params[1], lmax = (int)c.params[2];
+            if (!(c.params[1] >= 0.) || !(c.params[2] >= 0.) || (double)nmax != c.params[1] || (double)lmax != c.params[2])
+                return fail(-12, "SCF: nmax and lmax must be non-negative integers");
             const int ncoef = (nmax + 1) * (lmax + 1) * (lmax + 1);
             if (c.n_params < 5 + 2 * ncoef) return fail(-12, "SCF: parameter vector shorter than 5 + 2*(nmax+1)(lmax+1)^2");
             if (lmax > 15 || nmax > 63) return fail(-11, "SCF: lmax <= 15 and nmax <= 63 supported");
@@ -349,33 +374,32 @@ int resolve_frame(const gb_frame* fr, DevFrame& F) {
 }
 
 // Device staging for GB_MEM_HOST calls.  A small grow-only cache per (device, slot) avoids paying
-// cudaMalloc/cudaFree on every call of a time-stepping loop written on the Python side.
+// cudaMalloc/cudaFree on every call of a time-stepping loop written on the Python side.  Each device has its
+// own slots and its own mutex, so the per-device worker threads of a multi-device call never share a buffer.
 struct Scratch {
     void* ptr = nullptr;
     size_t cap = 0;
-    int dev = -1;
 };
 constexpr int NSLOT = 16;
-std::mutex g_scratch_mu;
-Scratch g_scratch[NSLOT];
+constexpr int MAXDEV = 64;
+std::mutex g_scratch_mu[MAXDEV];
+Scratch g_scratch[MAXDEV][NSLOT];
 
 cudaError_t scratch_get(int slot, size_t bytes, void** out) {
     int dev;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    Scratch& s = g_scratch[slot];
-    if (s.ptr && (s.dev != dev || s.cap < bytes)) {
-        int cur = dev;
-        if (s.dev != dev) cudaSetDevice(s.dev);
+    if (dev < 0 || dev >= MAXDEV) return cudaErrorInvalidDevice;
+    Scratch& s = g_scratch[dev][slot];
+    if (s.ptr && s.cap < bytes) {
         cudaFree(s.ptr);
-        if (s.dev != cur) cudaSetDevice(cur);
         s.ptr = nullptr; s.cap = 0;
     }
     if (!s.ptr) {
         if (bytes == 0) bytes = 8;
         e = cudaMalloc(&s.ptr, bytes);
         if (e != cudaSuccess) { s.ptr = nullptr; return e; }
-        s.cap = bytes; s.dev = dev;
+        s.cap = bytes;
     }
     *out = s.ptr;
     return cudaSuccess;
@@ -386,10 +410,25 @@ struct Ctx {
     bool host = true;
     bool strict = false;
     int block = 0;
+    int dev = 0;         // the device this call runs on
+    int nsm = 148;
     int prev_dev = -1;
-    std::unique_lock<std::mutex> lock;   // held for HOST-staged calls (they share the scratch cache)
-    ~Ctx() { if (prev_dev >= 0) cudaSetDevice(prev_dev); }
+    std::unique_lock<std::mutex> lock;   // held while the call uses the device's scratch slots
+    void lock_scratch() { if (!lock.owns_lock()) lock = std::unique_lock<std::mutex>(g_scratch_mu[dev]); }
+    ~Ctx() { if (lock.owns_lock()) lock.unlock(); if (prev_dev >= 0) cudaSetDevice(prev_dev); }
 };
+
+int sm_count(int dev) {
+    static std::mutex mu;
+    static int tab[MAXDEV] = {0};
+    std::lock_guard<std::mutex> g(mu);
+    if (!tab[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        tab[dev] = n;
+    }
+    return tab[dev];
+}
 
 int open_ctx(const gb_launch* opt, Ctx& c) {
     int ndev = 0;
@@ -397,25 +436,52 @@ int open_ctx(const gb_launch* opt, Ctx& c) {
     if (e != cudaSuccess || ndev == 0)
         return fail(-10, std::string("no CUDA device available (this engine has no CPU fallback): ") +
                              (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    CU(cudaGetDevice(&c.dev));
+    if (opt && opt->n_devices > 0)
+        return fail(-12, "this entry point runs on one device (gb_launch.n_devices must be 0)");
     if (opt) {
         c.stream = (cudaStream_t)opt->stream;
         c.host = opt->mem == GB_MEM_HOST;
         c.strict = opt->strict_math != 0;
         c.block = opt->block_threads;
-        if (opt->device >= 0) {
-            int cur; CU(cudaGetDevice(&cur));
-            if (cur != opt->device) { c.prev_dev = cur; CU(cudaSetDevice(opt->device)); }
+        if (opt->device >= 0 && c.dev != opt->device) {
+            if (opt->device >= ndev) return fail(-12, "gb_launch.device is not a CUDA device ordinal of this process");
+            c.prev_dev = c.dev; CU(cudaSetDevice(opt->device)); c.dev = opt->device;
         }
     }
-    if (c.host) c.lock = std::unique_lock<std::mutex>(g_scratch_mu);
+    if (c.dev >= MAXDEV) return fail(-10, "device ordinal >= 64");
+    c.nsm = sm_count(c.dev);
+    if (c.host) c.lock_scratch();
     return 0;
 }
 
-// input staging: returns a device pointer for `p` (copying when the call is HOST-staged)
+// Fixed-step / evaluation kernels, thread = orbit: 128-thread CTAs unless that leaves SMs idle -- C1's 10^4
+// orbits are 79 CTAs of 128 on 148 SMs -- in which case the CTA shrinks (64, then 32 threads) until there are
+// at least two CTAs per SM or one warp per CTA.
+int pick_block(const Ctx& c, size_t N) {
+    if (c.block > 0) return c.block;
+    int block = 128;
+    while (block > 32 && (N + block - 1) / block < (size_t)2 * c.nsm) block >>= 1;
+    return block;
+}
+
+// input staging: returns a device pointer for `p` (copying when the call is HOST-staged).  The 2-D forms
+// move `rows` rows of n doubles between a host array whose rows are `pitch` doubles apart (one device's
+// slice [lo, lo+n) of a (rows, N) array: p already points at column lo, pitch = N) and a dense (rows, n)
+// device array.
 int stage_in(Ctx& c, int slot, const void* p, size_t bytes, const void** dptr) {
     if (!c.host) { *dptr = p; return 0; }
     void* d; CU(scratch_get(slot, bytes, &d));
     if (bytes) CU(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, c.stream));
+    *dptr = d;
+    return 0;
+}
+int stage_in_2d(Ctx& c, int slot, const double* p, size_t rows, size_t n, size_t pitch, const void** dptr) {
+    if (!c.host || pitch == n) return stage_in(c, slot, p, rows * n * sizeof(double), dptr);
+    void* d; CU(scratch_get(slot, rows * n * sizeof(double), &d));
+    if (rows && n)
+        CU(cudaMemcpy2DAsync(d, n * sizeof(double), p, pitch * sizeof(double), n * sizeof(double), rows,
+                             cudaMemcpyHostToDevice, c.stream));
     *dptr = d;
     return 0;
 }
@@ -429,11 +495,79 @@ int stage_out_copy(Ctx& c, void* host, const void* dev, size_t bytes) {
     CU(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c.stream));
     return 0;
 }
+int stage_out_copy_2d(Ctx& c, double* host, const void* dev, size_t rows, size_t n, size_t pitch) {
+    if (!c.host || !host || rows * n == 0) return 0;
+    if (pitch == n) return stage_out_copy(c, host, dev, rows * n * sizeof(double));
+    CU(cudaMemcpy2DAsync(host, pitch * sizeof(double), dev, n * sizeof(double), n * sizeof(double), rows,
+                         cudaMemcpyDeviceToHost, c.stream));
+    return 0;
+}
 int finish(Ctx& c) {
     // HOST-staged calls return results in caller memory, so they must complete before returning.
     // DEVICE calls stay asynchronous on the caller's stream (errors surface at the caller's sync).
     if (c.host) CU(cudaStreamSynchronize(c.stream));
     return 0;
+}
+
+// ---- several devices inside one HOST-mode call (gb_launch.n_devices) ------------------------
+// The orbit index is cut into contiguous slices, one per device; one host thread per device runs the ordinary
+// single-device path on its slice (that path already copies straight between the caller's arrays and device
+// memory with 2-D copies, so nothing is gathered afterwards).  Pinned caller arrays make those copies
+// asynchronous per device; with pageable arrays the driver stages them, still concurrently across threads.
+// No collective, no peer access: orbits never interact.
+bool multi_device(const gb_launch* opt) { return opt && opt->n_devices > 0; }
+
+int check_devices(const gb_launch* opt) {
+    if (opt->mem != GB_MEM_HOST) return fail(-12, "gb_launch.n_devices > 0 needs GB_MEM_HOST buffers (a device pointer belongs to one device)");
+    if (!opt->devices) return fail(-12, "gb_launch.devices is null");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(-10, std::string("no CUDA device available (this engine has no CPU fallback): ") +
+                             (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (opt->n_devices > MAXDEV) return fail(-12, "at most 64 devices per call");
+    for (int k = 0; k < opt->n_devices; k++) {
+        if (opt->devices[k] < 0 || opt->devices[k] >= ndev) return fail(-12, "gb_launch.devices holds an ordinal that is not a CUDA device of this process");
+        // GB_ALLOW_DUP_DEVICES (test hook): the slices of one device then run one after the other (they share the
+        // device's scratch mutex), which lets a single-GPU box exercise the slicing / pitched-copy logic
+        for (int j = 0; j < k; j++)
+            if (opt->devices[j] == opt->devices[k] && !getenv("GB_ALLOW_DUP_DEVICES"))
+                return fail(-12, "gb_launch.devices holds a device twice");
+    }
+    return 0;
+}
+
+// body(sub_opt, k, nd) -> rc, run on one thread per device; returns the most negative rc with its message.
+template <class Body>
+int run_on_devices(const gb_launch* opt, Body body) {
+    int rc0 = check_devices(opt);
+    if (rc0) return rc0;
+    const int nd = opt->n_devices;
+    std::vector<int> rc(nd, 0);
+    std::vector<std::string> msg(nd);
+    std::vector<std::thread> th;
+    th.reserve(nd);
+    for (int k = 0; k < nd; k++) {
+        gb_launch sub = *opt;
+        sub.n_devices = 0; sub.devices = nullptr; sub.device = opt->devices[k];
+        sub.stream = nullptr;            // the caller's stream belongs to one device; each device uses its default stream
+        th.emplace_back([&rc, &msg, &body, sub, k, nd]() {
+            rc[k] = body(&sub, k, nd);
+            if (rc[k]) msg[k] = g_err;   // g_err is thread-local: hand the text to the calling thread
+        });
+    }
+    for (auto& t : th) t.join();
+    int worst = 0, who = -1;
+    for (int k = 0; k < nd; k++) if (rc[k] < worst) { worst = rc[k]; who = k; }
+    if (who >= 0) return fail(worst, "device " + std::to_string(opt->devices[who]) + ": " + msg[who]);
+    return 0;
+}
+
+// contiguous slice k of nd of range(N): sizes differ by at most one (the rule of gala_b200/dist.py:shard_bounds)
+void slice_of(size_t N, int k, int nd, size_t* lo, size_t* n) {
+    const size_t base = N / nd, rem = N % nd;
+    *lo = (size_t)k * base + ((size_t)k < rem ? (size_t)k : rem);
+    *n = base + ((size_t)k < rem ? 1 : 0);
 }
 
 #define RET_IF(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
@@ -455,24 +589,33 @@ void ruth4_coeffs(double* cs, double* ds) {
 
 enum EvalKind { EV_GRAD, EV_ENERGY, EV_DENSITY };
 
-int eval_common(EvalKind kind, const gb_potential* pot, const double* q, double t, size_t N, double* out,
-                const gb_launch* opt) {
+int eval_impl(EvalKind kind, const gb_potential* pot, const double* q, double t, size_t N, size_t pitch, double* out,
+              const gb_launch* opt) {
     Ctx c; RET_IF(open_ctx(opt, c));
     if (N && (!q || !out)) return fail(-12, "null data pointer");
     Resolved r; RET_IF(resolve(pot, r, c.stream));
-    const int block = c.block > 0 ? c.block : 128;
-    const void* dq; RET_IF(stage_in(c, 0, q, 3 * N * sizeof(double), &dq));
-    const size_t ob = (kind == EV_GRAD ? 3 : 1) * N * sizeof(double);
-    void* dout; RET_IF(stage_out_alloc(c, 1, out, ob, &dout));
+    const int block = pick_block(c, N);
+    const void* dq; RET_IF(stage_in_2d(c, 0, q, 3, N, pitch, &dq));
+    const size_t orows = kind == EV_GRAD ? 3 : 1;
+    void* dout; RET_IF(stage_out_alloc(c, 1, out, orows * N * sizeof(double), &dout));
     cudaError_t e;
     if (kind == EV_GRAD) e = KCALL(c, eval_gradient, r.P, (const double*)dq, t, N, (double*)dout, block, c.stream);
     else if (kind == EV_ENERGY) e = KCALL(c, eval_energy, r.P, (const double*)dq, t, N, (double*)dout, block, c.stream);
     else e = KCALL(c, eval_density, r.P, (const double*)dq, t, N, (double*)dout, block, c.stream);
     if (e != cudaSuccess) return cuda_fail(e, "evaluation kernel launch");
     if (N) g_launches++;
-    RET_IF(stage_out_copy(c, out, dout, ob));
-    if (r.d_ext) CU(cudaStreamSynchronize(c.stream));   // d_ext is freed when r goes out of scope
+    RET_IF(stage_out_copy_2d(c, out, dout, orows, N, pitch));
     return finish(c);
+}
+
+int eval_common(EvalKind kind, const gb_potential* pot, const double* q, double t, size_t N, double* out,
+                const gb_launch* opt) {
+    if (!multi_device(opt)) return eval_impl(kind, pot, q, t, N, N, out, opt);
+    if (N && (!q || !out)) return fail(-12, "null data pointer");
+    return run_on_devices(opt, [=](const gb_launch* sub, int k, int nd) {
+        size_t lo, n; slice_of(N, k, nd, &lo, &n);
+        return n ? eval_impl(kind, pot, q + lo, t, n, N, out + lo, sub) : 0;
+    });
 }
 
 }  // namespace
@@ -514,7 +657,7 @@ int gb_hessian(const gb_potential* pot, const double* q, double t, size_t N, dou
         }
     }
     Resolved r; RET_IF(resolve(pot, r, c.stream));
-    const int block = c.block > 0 ? c.block : 128;
+    const int block = pick_block(c, N);
     const void* dq; RET_IF(stage_in(c, 0, q, 3 * N * sizeof(double), &dq));
     void* dout; RET_IF(stage_out_alloc(c, 1, hess, 9 * N * sizeof(double), &dout));
     cudaError_t e = KCALL(c, eval_hessian, r.P, (const double*)dq, N, (double*)dout, block, c.stream);
@@ -526,18 +669,23 @@ int gb_hessian(const gb_potential* pot, const double* q, double t, size_t N, dou
 }
 
 int gb_release_scratch(void) {
-    std::lock_guard<std::mutex> g(g_scratch_mu);
-    int cur = 0;
+    int cur = 0, ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); ndev = 0; }
     cudaGetDevice(&cur);
-    for (int k = 0; k < NSLOT; k++) {
-        Scratch& sc = g_scratch[k];
-        if (!sc.ptr) continue;
-        if (sc.dev != cur) cudaSetDevice(sc.dev);
+    for (int dev = 0; dev < ndev && dev < MAXDEV; dev++) {
+        std::lock_guard<std::mutex> g(g_scratch_mu[dev]);
+        bool any = false;
+        for (int k = 0; k < NSLOT; k++) any |= g_scratch[dev][k].ptr != nullptr;
+        if (!any) continue;
+        cudaSetDevice(dev);
         cudaDeviceSynchronize();
-        cudaFree(sc.ptr);
-        if (sc.dev != cur) cudaSetDevice(cur);
-        sc.ptr = nullptr; sc.cap = 0; sc.dev = -1;
+        for (int k = 0; k < NSLOT; k++) {
+            Scratch& sc = g_scratch[dev][k];
+            if (sc.ptr) cudaFree(sc.ptr);
+            sc.ptr = nullptr; sc.cap = 0;
+        }
     }
+    cudaSetDevice(cur);
     ext_cache_clear();
     return 0;
 }
@@ -555,50 +703,52 @@ int gb_math_probe(int which, const double* x, size_t N, double* y, const gb_laun
     return finish(c);
 }
 
-int gb_hamiltonian_energy(const gb_potential* pot, const gb_frame* fr, const double* w, double t, size_t N,
-                          double* out, const gb_launch* opt) {
+static int ham_eval_impl(bool grad, const gb_potential* pot, const gb_frame* fr, const double* w, double t, size_t N,
+                         size_t pitch, double* out, const gb_launch* opt) {
     Ctx c; RET_IF(open_ctx(opt, c));
     if (N && (!w || !out)) return fail(-12, "null data pointer");
     Resolved r; RET_IF(resolve(pot, r, c.stream));
     DevFrame F; RET_IF(resolve_frame(fr, F));
-    const int block = c.block > 0 ? c.block : 128;
-    const void* dw; RET_IF(stage_in(c, 0, w, 6 * N * sizeof(double), &dw));
-    void* dout; RET_IF(stage_out_alloc(c, 1, out, N * sizeof(double), &dout));
-    cudaError_t e = KCALL(c, ham_energy, r.P, F, (const double*)dw, t, N, (double*)dout, block, c.stream);
-    if (e != cudaSuccess) return cuda_fail(e, "ham_energy launch");
+    const int block = pick_block(c, N);
+    const size_t orows = grad ? 6 : 1;
+    const void* dw; RET_IF(stage_in_2d(c, 0, w, 6, N, pitch, &dw));
+    void* dout; RET_IF(stage_out_alloc(c, 1, out, orows * N * sizeof(double), &dout));
+    cudaError_t e = grad ? KCALL(c, ham_gradient, r.P, F, (const double*)dw, t, N, (double*)dout, block, c.stream)
+                         : KCALL(c, ham_energy, r.P, F, (const double*)dw, t, N, (double*)dout, block, c.stream);
+    if (e != cudaSuccess) return cuda_fail(e, grad ? "ham_gradient launch" : "ham_energy launch");
     if (N) g_launches++;
-    RET_IF(stage_out_copy(c, out, dout, N * sizeof(double)));
-    if (r.d_ext) CU(cudaStreamSynchronize(c.stream));
+    RET_IF(stage_out_copy_2d(c, out, dout, orows, N, pitch));
     return finish(c);
+}
+static int ham_eval(bool grad, const gb_potential* pot, const gb_frame* fr, const double* w, double t, size_t N,
+                    double* out, const gb_launch* opt) {
+    if (!multi_device(opt)) return ham_eval_impl(grad, pot, fr, w, t, N, N, out, opt);
+    if (N && (!w || !out)) return fail(-12, "null data pointer");
+    return run_on_devices(opt, [=](const gb_launch* sub, int k, int nd) {
+        size_t lo, n; slice_of(N, k, nd, &lo, &n);
+        return n ? ham_eval_impl(grad, pot, fr, w + lo, t, n, N, out + lo, sub) : 0;
+    });
+}
+
+int gb_hamiltonian_energy(const gb_potential* pot, const gb_frame* fr, const double* w, double t, size_t N,
+                          double* out, const gb_launch* opt) {
+    return ham_eval(false, pot, fr, w, t, N, out, opt);
 }
 
 int gb_hamiltonian_gradient(const gb_potential* pot, const gb_frame* fr, const double* w, double t, size_t N,
                             double* f, const gb_launch* opt) {
-    Ctx c; RET_IF(open_ctx(opt, c));
-    if (N && (!w || !f)) return fail(-12, "null data pointer");
-    Resolved r; RET_IF(resolve(pot, r, c.stream));
-    DevFrame F; RET_IF(resolve_frame(fr, F));
-    const int block = c.block > 0 ? c.block : 128;
-    const void* dw; RET_IF(stage_in(c, 0, w, 6 * N * sizeof(double), &dw));
-    void* dout; RET_IF(stage_out_alloc(c, 1, f, 6 * N * sizeof(double), &dout));
-    cudaError_t e = KCALL(c, ham_gradient, r.P, F, (const double*)dw, t, N, (double*)dout, block, c.stream);
-    if (e != cudaSuccess) return cuda_fail(e, "ham_gradient launch");
-    if (N) g_launches++;
-    RET_IF(stage_out_copy(c, f, dout, 6 * N * sizeof(double)));
-    if (r.d_ext) CU(cudaStreamSynchronize(c.stream));
-    return finish(c);
+    return ham_eval(true, pot, fr, w, t, N, f, opt);
 }
 
 // Two side streams per device for the chunked HOST pipeline (created once, never destroyed).
-// The streams and events are shared by every call on a device, so a call that uses them holds g_side_mu.
-std::mutex g_side_mu;
-struct SideStreams { cudaStream_t s[2] = {nullptr, nullptr}; cudaEvent_t ev[3] = {nullptr, nullptr, nullptr}; };
+// The streams and events are shared by every call on a device, so a call that uses them holds S->mu.
+struct SideStreams { std::mutex mu; cudaStream_t s[2] = {nullptr, nullptr}; cudaEvent_t ev[3] = {nullptr, nullptr, nullptr}; };
 static int side_streams(SideStreams** out) {
     static std::mutex mu;
-    static SideStreams tab[64];
+    static SideStreams tab[MAXDEV];
     int dev = 0;
     CU(cudaGetDevice(&dev));
-    if (dev >= 64) return fail(-10, "device ordinal >= 64");
+    if (dev >= MAXDEV) return fail(-10, "device ordinal >= 64");
     std::lock_guard<std::mutex> g(mu);
     SideStreams& S = tab[dev];
     if (!S.s[0]) {
@@ -609,18 +759,25 @@ static int side_streams(SideStreams** out) {
     return 0;
 }
 
+// dt < 0 sentinel is not usable (backward integrations have dt < 0), so the kernels take a flag: dt_from_t != 0
+// => the kernel itself forms dt = t[1] - t[0] from the device copy of the grid (DEVICE-mode calls: reading two
+// doubles back to the host would cost a stream synchronisation and break the "DEVICE calls stay asynchronous"
+// contract of the header; the subtraction is the same IEEE operation on either side).
 static cudaError_t launch_fixed(Ctx& c, bool is_ruth4, const DevPot& P, const DevFrame& F, const double* dw0, size_t n,
-                                const double* dt_dev, int ntimes, double dt, int save_all, double* dout, int block,
-                                cudaStream_t st) {
+                                const double* dt_dev, int ntimes, double dt, int dt_from_t, int save_all, double* dout,
+                                int block, cudaStream_t st) {
     if (!is_ruth4)
-        return KCALL(c, leapfrog, P, dw0, n, dt_dev, ntimes, dt, save_all, dout, block, st);
+        return KCALL(c, leapfrog, P, dw0, n, dt_dev, ntimes, dt, dt_from_t, save_all, dout, block, st);
     double cs[4], ds[4];
     ruth4_coeffs(cs, ds);
-    return KCALL(c, ruth4, P, F, dw0, n, dt_dev, ntimes, dt, cs, ds, save_all, dout, block, st);
+    return KCALL(c, ruth4, P, F, dw0, n, dt_dev, ntimes, dt, dt_from_t, cs, ds, save_all, dout, block, st);
 }
 
-static int fixed_step_common(bool is_ruth4, const gb_potential* pot, const gb_frame* fr, const double* w0, size_t N,
-                             const double* t, int ntimes, int save_all, double* w_out, const gb_launch* opt) {
+// One device's share of a fixed-step call: orbits [0, N) of arrays whose rows are `pitch` doubles apart on the
+// host side (pitch == N for a whole-array call; pitch = the full orbit count when w0 / w_out point at one
+// device's slice of the caller's (6, N_total) / (6, ntimes, N_total) arrays).
+static int fixed_step_impl(bool is_ruth4, const gb_potential* pot, const gb_frame* fr, const double* w0, size_t N,
+                           size_t pitch, const double* t, int ntimes, int save_all, double* w_out, const gb_launch* opt) {
     Ctx c; RET_IF(open_ctx(opt, c));
     if (ntimes < 2) return fail(-12, "the time grid needs at least 2 entries");
     if (!t || (N && (!w0 || !w_out))) return fail(-12, "null data pointer");
@@ -628,16 +785,9 @@ static int fixed_step_common(bool is_ruth4, const gb_potential* pot, const gb_fr
     if (!is_ruth4 && F.type != GB_FRAME_STATIC)
         return fail(-13, "Leapfrog integration is currently only supported for StaticFrame");
     Resolved r; RET_IF(resolve(pot, r, c.stream));
-    const int block = c.block > 0 ? c.block : 128;
-    // t is always read on the host for dt (it is tiny); the kernels take dt by value
-    double dt;
-    if (c.host) { dt = t[1] - t[0]; }
-    else {
-        double two[2];
-        CU(cudaMemcpyAsync(two, t, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
-        CU(cudaStreamSynchronize(c.stream));
-        dt = two[1] - two[0];
-    }
+    // HOST: dt from the caller's grid; DEVICE: the kernel reads it from the device grid (no synchronisation here)
+    const double dt = c.host ? t[1] - t[0] : 0.0;
+    const int dt_from_t = c.host ? 0 : 1;
     const void* dtg; RET_IF(stage_in(c, 2, t, (size_t)ntimes * sizeof(double), &dtg));
     const double* dt_dev = (const double*)dtg;
     const size_t rows = save_all ? (size_t)ntimes : 1;       // output rows per phase-space component
@@ -647,13 +797,14 @@ static int fixed_step_common(bool is_ruth4, const gb_potential* pot, const gb_fr
     // chunk of orbits a 2-D copy: 6 [x ntimes] rows of nb doubles with a pitch of N doubles).
     const size_t kPipeMin = 1 << 16;
     if (c.host && N >= kPipeMin && !getenv("GB_NO_PIPELINE")) {
-        std::lock_guard<std::mutex> side_lock(g_side_mu);
         SideStreams* S; RET_IF(side_streams(&S));
+        std::lock_guard<std::mutex> side_lock(S->mu);
         size_t nb = (N + 7) / 8;                                   // ~8 chunks
         const size_t cap = ((size_t)256 << 20) / (rows * 6 * sizeof(double));   // <= 256 MB of output per chunk
         if (nb > cap) nb = cap;
         if (nb < 16384) nb = 16384;
         nb = (nb + 127) & ~(size_t)127;
+        const int block = pick_block(c, nb);
         void *din[2], *dou[2];
         for (int k = 0; k < 2; k++) {
             CU(scratch_get(8 + k, 6 * nb * sizeof(double), &din[k]));
@@ -665,13 +816,13 @@ static int fixed_step_common(bool is_ruth4, const gb_potential* pot, const gb_fr
         for (size_t a0 = 0; a0 < N; a0 += nb, k ^= 1) {
             const size_t n = (N - a0 < nb) ? N - a0 : nb;
             cudaStream_t st = S->s[k];
-            CU(cudaMemcpy2DAsync(din[k], n * sizeof(double), w0 + a0, N * sizeof(double), n * sizeof(double), 6,
+            CU(cudaMemcpy2DAsync(din[k], n * sizeof(double), w0 + a0, pitch * sizeof(double), n * sizeof(double), 6,
                                  cudaMemcpyHostToDevice, st));
-            cudaError_t e = launch_fixed(c, is_ruth4, r.P, F, (const double*)din[k], n, dt_dev, ntimes, dt, save_all,
-                                         (double*)dou[k], block, st);
+            cudaError_t e = launch_fixed(c, is_ruth4, r.P, F, (const double*)din[k], n, dt_dev, ntimes, dt, dt_from_t,
+                                         save_all, (double*)dou[k], block, st);
             if (e != cudaSuccess) return cuda_fail(e, "integrator kernel launch");
             g_launches++;
-            CU(cudaMemcpy2DAsync(w_out + a0, N * sizeof(double), dou[k], n * sizeof(double), n * sizeof(double),
+            CU(cudaMemcpy2DAsync(w_out + a0, pitch * sizeof(double), dou[k], n * sizeof(double), n * sizeof(double),
                                  6 * rows, cudaMemcpyDeviceToHost, st));
         }
         for (int q = 0; q < 2; q++) {
@@ -681,16 +832,27 @@ static int fixed_step_common(bool is_ruth4, const gb_potential* pot, const gb_fr
         return finish(c);       // synchronises c.stream, which now depends on both side streams
     }
 
-    const void* dw0; RET_IF(stage_in(c, 0, w0, 6 * N * sizeof(double), &dw0));
-    const size_t ob = rows * 6 * N * sizeof(double);
-    void* dout; RET_IF(stage_out_alloc(c, 1, w_out, ob, &dout));
-    cudaError_t e = launch_fixed(c, is_ruth4, r.P, F, (const double*)dw0, N, dt_dev, ntimes, dt, save_all,
+    const int block = pick_block(c, N);
+    const void* dw0; RET_IF(stage_in_2d(c, 0, w0, 6, N, pitch, &dw0));
+    void* dout; RET_IF(stage_out_alloc(c, 1, w_out, rows * 6 * N * sizeof(double), &dout));
+    cudaError_t e = launch_fixed(c, is_ruth4, r.P, F, (const double*)dw0, N, dt_dev, ntimes, dt, dt_from_t, save_all,
                                  (double*)dout, block, c.stream);
     if (e != cudaSuccess) return cuda_fail(e, "integrator kernel launch");
     if (N) g_launches++;
-    RET_IF(stage_out_copy(c, w_out, dout, ob));
-    if (r.d_ext) CU(cudaStreamSynchronize(c.stream));
+    RET_IF(stage_out_copy_2d(c, w_out, dout, 6 * rows, N, pitch));
     return finish(c);
+}
+
+static int fixed_step_common(bool is_ruth4, const gb_potential* pot, const gb_frame* fr, const double* w0, size_t N,
+                             const double* t, int ntimes, int save_all, double* w_out, const gb_launch* opt) {
+    if (!multi_device(opt)) return fixed_step_impl(is_ruth4, pot, fr, w0, N, N, t, ntimes, save_all, w_out, opt);
+    if (ntimes < 2) return fail(-12, "the time grid needs at least 2 entries");
+    if (!t || (N && (!w0 || !w_out))) return fail(-12, "null data pointer");
+    return run_on_devices(opt, [=](const gb_launch* sub, int k, int nd) {
+        size_t lo, n; slice_of(N, k, nd, &lo, &n);
+        // an empty slice still validates the potential / frame on its device (same error codes as one device)
+        return fixed_step_impl(is_ruth4, pot, fr, w0 + lo, n, N, t, ntimes, save_all, w_out + lo, sub);
+    });
 }
 
 int gb_leapfrog(const gb_potential* pot, const gb_frame* fr, const double* w0, size_t N, const double* t,
@@ -764,9 +926,10 @@ struct AsyncBuf {
     ~AsyncBuf() { if (p) cudaFreeAsync(p, s); }
 };
 
-int gb_dop853(const gb_potential* pot, const gb_frame* fr, const double* w0, size_t N, const double* t, int ntimes,
-              double atol, double rtol, long nmax, double dt_max, long nstiff, int save_all, double* w_out,
-              int32_t* status, const gb_dop853_stats* stats, const gb_launch* opt) {
+// One device's share of a gb_dop853 call; `pitch` as in fixed_step_impl.
+static int dop853_impl(const gb_potential* pot, const gb_frame* fr, const double* w0, size_t N, size_t pitch,
+                       const double* t, int ntimes, double atol, double rtol, long nmax, double dt_max, long nstiff,
+                       int save_all, double* w_out, int32_t* status, const gb_dop853_stats* stats, const gb_launch* opt) {
     Ctx c; RET_IF(open_ctx(opt, c));
     if (ntimes < 2) return fail(-12, "the time grid needs at least 2 entries");
     if (!t || (N && (!w0 || !w_out))) return fail(-12, "null data pointer");
@@ -784,14 +947,14 @@ int gb_dop853(const gb_potential* pot, const gb_frame* fr, const double* w0, siz
     Dop853Args a;
     // dop853_helper passes uround = np.finfo(float).eps and h = t[1]-t[0] (dop853.pyx:157-182)
     RET_IF(dop853_defaults(a, atol, rtol, nmax, dt_max, nstiff, 2.220446049250313e-16, two[1] - two[0]));
-    const void* dw0; RET_IF(stage_in(c, 0, w0, 6 * N * sizeof(double), &dw0));
+    const void* dw0; RET_IF(stage_in_2d(c, 0, w0, 6, N, pitch, &dw0));
     const void* dtg; RET_IF(stage_in(c, 2, t, (size_t)ntimes * sizeof(double), &dtg));
-    const size_t ob = (save_all ? (size_t)ntimes : 1) * 6 * N * sizeof(double);
-    void* dout; RET_IF(stage_out_alloc(c, 1, w_out, ob, &dout));
+    const size_t orows = (save_all ? (size_t)ntimes : 1) * 6;
+    void* dout; RET_IF(stage_out_alloc(c, 1, w_out, orows * N * sizeof(double), &dout));
     // status + optional stats
     void* dstat;
     if (c.host || !status) {
-        if (!c.lock.owns_lock()) c.lock = std::unique_lock<std::mutex>(g_scratch_mu);
+        c.lock_scratch();
         CU(scratch_get(3, N * sizeof(int32_t), &dstat));
     } else dstat = status;
     int32_t* dst[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -815,8 +978,8 @@ int gb_dop853(const gb_potential* pot, const gb_frame* fr, const double* w0, siz
         // orbit does (~1000 sequential steps), so the work per resident lane must be several times
         // that, i.e. >> 38k orbits per launch.  Up to half of the free memory (counting what the
         // scratch cache already holds); the buffer stays cached until gb_release_scratch().
-        if (!c.lock.owns_lock()) c.lock = std::unique_lock<std::mutex>(g_scratch_mu);
-        size_t budget = (free_b + g_scratch[14].cap) / 2;
+        c.lock_scratch();
+        size_t budget = (free_b + g_scratch[c.dev][14].cap) / 2;
         if (const char* e = getenv("GB_D8_SCRATCH_MB")) budget = (size_t)atoll(e) << 20;
         chunk = budget / per_orbit;
         if (chunk < 64) chunk = 64;
@@ -835,11 +998,11 @@ int gb_dop853(const gb_potential* pot, const gb_frame* fr, const double* w0, siz
         if (chunk < 64) chunk = 64;
     }
     std::unique_lock<std::mutex> side_lock;
-    if (nstreams == 2) side_lock = std::unique_lock<std::mutex>(g_side_mu);
+    SideStreams* S = nullptr;
+    if (nstreams == 2) { RET_IF(side_streams(&S)); side_lock = std::unique_lock<std::mutex>(S->mu); }
     AsyncBuf queue[2], keys_in[2], keys_out[2], idx_in[2], perm[2], temp[2], scratch[2];
     size_t temp_bytes = 0;
     cudaStream_t st[2] = {c.stream, c.stream};
-    SideStreams* S = nullptr;
     if (N) {
         if (sorted) CU(gb_sort_pairs_bytes(chunk, &temp_bytes));
         for (int k = 0; k < nstreams; k++) {
@@ -855,7 +1018,6 @@ int gb_dop853(const gb_potential* pot, const gb_frame* fr, const double* w0, siz
             }
         }
         if (nstreams == 2) {
-            RET_IF(side_streams(&S));
             CU(cudaEventRecord(S->ev[2], c.stream));       // inputs staged, buffers allocated
             for (int k = 0; k < 2; k++) { st[k] = S->s[k]; CU(cudaStreamWaitEvent(st[k], S->ev[2], 0)); }
         }
@@ -895,7 +1057,7 @@ int gb_dop853(const gb_potential* pot, const gb_frame* fr, const double* w0, siz
             CU(cudaStreamWaitEvent(c.stream, S->ev[q], 0));
         }
     }
-    RET_IF(stage_out_copy(c, w_out, dout, ob));
+    RET_IF(stage_out_copy_2d(c, w_out, dout, orows, N, pitch));
     if (c.host) {
         if (status) RET_IF(stage_out_copy(c, status, dstat, N * sizeof(int32_t)));
         for (int k = 0; k < 4; k++) if (hst[k]) RET_IF(stage_out_copy(c, hst[k], dst[k], N * sizeof(int32_t)));
@@ -905,6 +1067,25 @@ int gb_dop853(const gb_potential* pot, const gb_frame* fr, const double* w0, siz
     RET_IF(finish(c));
     if (worst < 0) return fail(worst, "Integration failed with code " + std::to_string(worst));
     return 0;
+}
+
+int gb_dop853(const gb_potential* pot, const gb_frame* fr, const double* w0, size_t N, const double* t, int ntimes,
+              double atol, double rtol, long nmax, double dt_max, long nstiff, int save_all, double* w_out,
+              int32_t* status, const gb_dop853_stats* stats, const gb_launch* opt) {
+    if (!multi_device(opt))
+        return dop853_impl(pot, fr, w0, N, N, t, ntimes, atol, rtol, nmax, dt_max, nstiff, save_all, w_out, status, stats, opt);
+    if (ntimes < 2) return fail(-12, "the time grid needs at least 2 entries");
+    if (!t || (N && (!w0 || !w_out))) return fail(-12, "null data pointer");
+    return run_on_devices(opt, [=](const gb_launch* sub, int k, int nd) {
+        size_t lo, n; slice_of(N, k, nd, &lo, &n);
+        gb_dop853_stats st = {nullptr, nullptr, nullptr, nullptr};
+        if (stats) {
+            st.nstep = stats->nstep ? stats->nstep + lo : nullptr; st.naccpt = stats->naccpt ? stats->naccpt + lo : nullptr;
+            st.nrejct = stats->nrejct ? stats->nrejct + lo : nullptr; st.nfcn = stats->nfcn ? stats->nfcn + lo : nullptr;
+        }
+        return dop853_impl(pot, fr, w0 + lo, n, N, t, ntimes, atol, rtol, nmax, dt_max, nstiff, save_all, w_out + lo,
+                           status ? status + lo : nullptr, stats ? &st : nullptr, sub);
+    });
 }
 
 struct DevTmp {                      // stream-ordered device temporary with optional H2D fill
@@ -930,7 +1111,7 @@ int gb_stream_release(const gb_potential* pot, double G, const double* prog_w, c
     if (ncols < need[df_kind]) return fail(-12, "too few random deviates per particle for this DF");
     if (Np && (!prog_idx || !sign || !stream_w0 || (need[df_kind] && !draws))) return fail(-12, "null data pointer");
     Resolved r; RET_IF(resolve(pot, r, c.stream));
-    const int block = c.block > 0 ? c.block : 128;
+    const int block = pick_block(c, Np);
     const void *dpw, *dpt, *dpm, *dpi, *dsg, *dnr;
     RET_IF(stage_in(c, 0, prog_w, (size_t)ntimes * 6 * sizeof(double), &dpw));
     RET_IF(stage_in(c, 2, prog_t, (size_t)ntimes * sizeof(double), &dpt));
@@ -945,7 +1126,6 @@ int gb_stream_release(const gb_potential* pot, double G, const double* prog_w, c
     if (e != cudaSuccess) return cuda_fail(e, "stream release launch");
     if (Np) g_launches++;
     RET_IF(stage_out_copy(c, stream_w0, dout, Np * 6 * sizeof(double)));
-    if (r.d_ext) CU(cudaStreamSynchronize(c.stream));
     return finish(c);
 }
 
@@ -957,34 +1137,97 @@ int gb_fardal_release(const gb_potential* pot, double G, const double* prog_w, c
                              stream_w0, opt);
 }
 
-int gb_mockstream_dop853(const gb_potential* pot, const gb_frame* fr, const double* stream_w0, const double* t1,
-                         size_t Np, double tfinal, double dt0, double atol, double rtol, long nmax,
-                         double* stream_w, int32_t* status, const gb_launch* opt) {
+// Mock-stream particles over several devices: rows are dealt in groups of GB_DEAL consecutive particles,
+// group g to device g mod nd.  The caller's rows are ordered by release time (mockstream_generator.py:300-330),
+// i.e. by remaining work, so a contiguous split would give the first device all the long integrations; dealing
+// small groups round-robin gives every device the same mix (the C-ABI form of gala_b200/dist.py:deal_by_work).
+// A device's share is a 2-D copy: its groups are GB_DEAL rows wide and nd * GB_DEAL rows apart.
+#define GB_DEAL 128
+struct Deal {
+    int k = 0, nd = 1;
+    size_t Np = 0;          // particles of the whole call
+    size_t ngroups() const { return (Np + GB_DEAL - 1) / GB_DEAL; }
+    size_t my_groups() const { const size_t g = ngroups(); return g > (size_t)k ? (g - k + nd - 1) / nd : 0; }
+    bool has_tail() const { const size_t g = ngroups(); return my_groups() && (g - 1) % nd == (size_t)k && Np % GB_DEAL; }
+    size_t count() const {                                   // particles of this device
+        if (nd == 1) return Np;
+        const size_t mg = my_groups();
+        if (!mg) return 0;
+        return has_tail() ? (mg - 1) * GB_DEAL + Np % GB_DEAL : mg * GB_DEAL;
+    }
+};
+// copy this device's rows (elem bytes each) between the caller's array and a dense device array
+static int deal_copy(Ctx& c, const Deal& D, bool to_device, void* host, void* dev, size_t elem) {
+    const size_t n = D.count();
+    if (!n || !host) return 0;
+    const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    if (D.nd == 1) {
+        CU(cudaMemcpyAsync(to_device ? dev : host, to_device ? host : dev, n * elem, kind, c.stream));
+        return 0;
+    }
+    const size_t w = GB_DEAL * elem, hp = (size_t)D.nd * w;
+    char* h0 = (char*)host + (size_t)D.k * w;
+    const size_t full = D.has_tail() ? D.my_groups() - 1 : D.my_groups();
+    if (full) {
+        if (to_device) CU(cudaMemcpy2DAsync(dev, w, h0, hp, w, full, kind, c.stream));
+        else CU(cudaMemcpy2DAsync(h0, hp, dev, w, w, full, kind, c.stream));
+    }
+    if (D.has_tail()) {
+        const size_t tb = (D.Np % GB_DEAL) * elem;
+        char* ht = h0 + full * hp; char* dt_ = (char*)dev + full * w;
+        CU(cudaMemcpyAsync(to_device ? (void*)dt_ : (void*)ht, to_device ? (void*)ht : (void*)dt_, tb, kind, c.stream));
+    }
+    return 0;
+}
+
+static int mock_dop853_impl(const gb_potential* pot, const gb_frame* fr, const double* stream_w0, const double* t1,
+                            const Deal& D, double tfinal, double dt0, double atol, double rtol, long nmax,
+                            double* stream_w, int32_t* status, const gb_launch* opt) {
     Ctx c; RET_IF(open_ctx(opt, c));
-    if (Np && (!stream_w0 || !t1 || !stream_w)) return fail(-12, "null data pointer");
+    const size_t Np = D.count();
+    if (D.Np && (!stream_w0 || !t1 || !stream_w)) return fail(-12, "null data pointer");
     DevFrame F; RET_IF(resolve_frame(fr, F));
     Resolved r; RET_IF(resolve(pot, r, c.stream));
     const int block = c.block > 0 ? c.block : 64;
     Dop853Args a;
     // dop853_step (dop853.pyx:45-69): uround 0 -> 2.3e-16, hmax 0, nstiff hard-coded to 1
     RET_IF(dop853_defaults(a, atol, rtol, nmax, 0.0, 1, 0.0, dt0));
-    const void *dw0, *dt1;
-    RET_IF(stage_in(c, 0, stream_w0, Np * 6 * sizeof(double), &dw0));
-    RET_IF(stage_in(c, 2, t1, Np * sizeof(double), &dt1));
-    void* dout; RET_IF(stage_out_alloc(c, 1, stream_w, Np * 6 * sizeof(double), &dout));
-    void* dstat;
-    if (c.host || !status) CU(scratch_get(3, Np * sizeof(int32_t), &dstat)); else dstat = status;
+    const void *dw0 = stream_w0, *dt1 = t1;
+    void *dout = stream_w, *dstat = status;
+    if (c.host) {
+        void* p;
+        CU(scratch_get(0, Np * 6 * sizeof(double), &p)); dw0 = p;
+        RET_IF(deal_copy(c, D, true, (void*)stream_w0, p, 6 * sizeof(double)));
+        CU(scratch_get(2, Np * sizeof(double), &p)); dt1 = p;
+        RET_IF(deal_copy(c, D, true, (void*)t1, p, sizeof(double)));
+        CU(scratch_get(1, Np * 6 * sizeof(double), &dout));
+    }
+    if (c.host || !status) { c.lock_scratch(); CU(scratch_get(3, Np * sizeof(int32_t), &dstat)); }
     cudaError_t e = KCALL(c, mock_dop853, r.P, F, (const double*)dw0, (const double*)dt1, Np, tfinal, a,
                           (double*)dout, (int32_t*)dstat, block, c.stream);
     if (e != cudaSuccess) return cuda_fail(e, "mock_dop853 launch");
     if (Np) g_launches++;
-    RET_IF(stage_out_copy(c, stream_w, dout, Np * 6 * sizeof(double)));
-    if (c.host && status) RET_IF(stage_out_copy(c, status, dstat, Np * sizeof(int32_t)));
+    if (c.host) {
+        RET_IF(deal_copy(c, D, false, stream_w, dout, 6 * sizeof(double)));
+        RET_IF(deal_copy(c, D, false, status, dstat, sizeof(int32_t)));
+    }
     int worst = 0;
-    if (Np) RET_IF(worst_status(c, (const int32_t*)dstat, Np, c.host ? status : nullptr, &worst));
+    if (Np) RET_IF(worst_status(c, (const int32_t*)dstat, Np, nullptr, &worst));
     RET_IF(finish(c));
     if (worst < 0) return fail(worst, "Integration failed with code " + std::to_string(worst));
     return 0;
+}
+
+int gb_mockstream_dop853(const gb_potential* pot, const gb_frame* fr, const double* stream_w0, const double* t1,
+                         size_t Np, double tfinal, double dt0, double atol, double rtol, long nmax,
+                         double* stream_w, int32_t* status, const gb_launch* opt) {
+    Deal D; D.Np = Np;
+    if (!multi_device(opt))
+        return mock_dop853_impl(pot, fr, stream_w0, t1, D, tfinal, dt0, atol, rtol, nmax, stream_w, status, opt);
+    return run_on_devices(opt, [=](const gb_launch* sub, int k, int nd) {
+        Deal Dk = D; Dk.k = k; Dk.nd = nd;
+        return mock_dop853_impl(pot, fr, stream_w0, t1, Dk, tfinal, dt0, atol, rtol, nmax, stream_w, status, sub);
+    });
 }
 
 int gb_mockstream_dop853_animate(const gb_potential* pot, const gb_frame* fr, const double* w0_rows,
@@ -1029,24 +1272,40 @@ int gb_mockstream_dop853_animate(const gb_potential* pot, const gb_frame* fr, co
     return 0;
 }
 
-int gb_mockstream_leapfrog(const gb_potential* pot, const double* stream_w0, const double* t1, size_t Np,
-                           double tfinal, double dt, double* stream_w, const gb_launch* opt) {
+static int mock_leapfrog_impl(const gb_potential* pot, const double* stream_w0, const double* t1, const Deal& D,
+                              double tfinal, double dt, double* stream_w, const gb_launch* opt) {
     Ctx c; RET_IF(open_ctx(opt, c));
-    if (Np && (!stream_w0 || !t1 || !stream_w)) return fail(-12, "null data pointer");
+    const size_t Np = D.count();
+    if (D.Np && (!stream_w0 || !t1 || !stream_w)) return fail(-12, "null data pointer");
     if (dt == 0.0) return fail(-12, "dt must be non-zero");
     Resolved r; RET_IF(resolve(pot, r, c.stream));
-    const int block = c.block > 0 ? c.block : 128;
-    const void *dw0, *dt1;
-    RET_IF(stage_in(c, 0, stream_w0, Np * 6 * sizeof(double), &dw0));
-    RET_IF(stage_in(c, 2, t1, Np * sizeof(double), &dt1));
-    void* dout; RET_IF(stage_out_alloc(c, 1, stream_w, Np * 6 * sizeof(double), &dout));
+    const int block = pick_block(c, Np);
+    const void *dw0 = stream_w0, *dt1 = t1;
+    void* dout = stream_w;
+    if (c.host) {
+        void* p;
+        CU(scratch_get(0, Np * 6 * sizeof(double), &p)); dw0 = p;
+        RET_IF(deal_copy(c, D, true, (void*)stream_w0, p, 6 * sizeof(double)));
+        CU(scratch_get(2, Np * sizeof(double), &p)); dt1 = p;
+        RET_IF(deal_copy(c, D, true, (void*)t1, p, sizeof(double)));
+        CU(scratch_get(1, Np * 6 * sizeof(double), &dout));
+    }
     cudaError_t e = KCALL(c, mock_leapfrog, r.P, (const double*)dw0, (const double*)dt1, Np, tfinal, dt,
                           (double*)dout, block, c.stream);
     if (e != cudaSuccess) return cuda_fail(e, "mock_leapfrog launch");
     if (Np) g_launches++;
-    RET_IF(stage_out_copy(c, stream_w, dout, Np * 6 * sizeof(double)));
-    if (r.d_ext) CU(cudaStreamSynchronize(c.stream));
+    if (c.host) RET_IF(deal_copy(c, D, false, stream_w, dout, 6 * sizeof(double)));
     return finish(c);
+}
+
+int gb_mockstream_leapfrog(const gb_potential* pot, const double* stream_w0, const double* t1, size_t Np,
+                           double tfinal, double dt, double* stream_w, const gb_launch* opt) {
+    Deal D; D.Np = Np;
+    if (!multi_device(opt)) return mock_leapfrog_impl(pot, stream_w0, t1, D, tfinal, dt, stream_w, opt);
+    return run_on_devices(opt, [=](const gb_launch* sub, int k, int nd) {
+        Deal Dk = D; Dk.k = k; Dk.nd = nd;
+        return mock_leapfrog_impl(pot, stream_w0, t1, Dk, tfinal, dt, stream_w, sub);
+    });
 }
 
 // ---- massive bodies ------------------------------------------------------------------

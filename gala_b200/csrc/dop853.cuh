@@ -40,7 +40,13 @@ GB_DEV double gb_pow_eighth(double err) {
 
 // RHS functor interface: void operator()(double t, const double (&w)[6], double (&f)[6]) const
 //
-// OUT interface (DENSE only): void operator()(int idx, const double (&v)[6]) const
+// OUT interface (DENSE only), one of
+//   immediate: void operator()(int idx, const double (&v)[6]) const -- step() evaluates every requested time
+//              inside the accepted step itself (a per-lane loop) and hands the sample over;
+//   deferred:  static constexpr bool kDeferred = true; st(row, v) / ld(row) / stash(x0, h, ih) -- step() only
+//              deposits the eight dense-output coefficient vectors (row = 6 * k + component, k = 0..7 for
+//              rcont1..rcont8) and the step's (x, h); the caller evaluates the samples afterwards, outside the
+//              divergent accept branch (k_dop853_dyn: the whole warp shares the pending samples of its lanes).
 //
 // Dop853Lane holds everything dopcor keeps between attempted steps (dop853.cpp:333-366), so one
 // lane can be (re)initialised with a new orbit at any iteration of a persistent warp loop.
@@ -50,6 +56,8 @@ GB_DEV double gb_pow_eighth(double err) {
 #ifndef GB_D8_UNROLL_MAX
 #define GB_D8_UNROLL_MAX 12
 #endif
+template <class T, class = void> struct gb_is_deferred { static constexpr bool value = false; };
+template <class T> struct gb_is_deferred<T, decltype((void)T::kDeferred)> { static constexpr bool value = T::kDeferred; };
 template <bool DENSE, int NDIM = 6>
 struct Dop853Lane {
     static constexpr int n = NDIM;
@@ -231,7 +239,57 @@ struct Dop853Lane {
                     if (hlamb > 6.1) return -4;
                 }
 
-                if (DENSE) {
+                if constexpr (DENSE && gb_is_deferred<OUT>::value) {
+                    // dense-output preparation (dop853.cpp:492-582), deferred form: the coefficient vectors go to
+                    // the OUT object as they are formed (rcont5..8 as partial sums before the three extra stages,
+                    // completed afterwards), so none of them occupies registers across the extra RHS evaluations.
+                    // Same expressions in the same order as the immediate form below.
+#pragma unroll(GB_NU)
+                    for (int i = 0; i < nn; i++) {
+                        emit.st(i, y[i]);
+                        const double ydiff = k5[i] - y[i];
+                        emit.st(6 + i, ydiff);
+                        const double bspl = h * k1[i] - ydiff;
+                        emit.st(12 + i, bspl);
+                        emit.st(18 + i, ydiff - h * k4[i] - bspl);
+                        emit.st(24 + i, d41 * k1[i] + d46 * k6[i] + d47 * k7[i] + d48 * k8[i] + d49 * k9[i] + d410 * k10[i] +
+                                        d411 * k2[i] + d412 * k3[i]);
+                        emit.st(30 + i, d51 * k1[i] + d56 * k6[i] + d57 * k7[i] + d58 * k8[i] + d59 * k9[i] + d510 * k10[i] +
+                                        d511 * k2[i] + d512 * k3[i]);
+                        emit.st(36 + i, d61 * k1[i] + d66 * k6[i] + d67 * k7[i] + d68 * k8[i] + d69 * k9[i] + d610 * k10[i] +
+                                        d611 * k2[i] + d612 * k3[i]);
+                        emit.st(42 + i, d71 * k1[i] + d76 * k6[i] + d77 * k7[i] + d78 * k8[i] + d79 * k9[i] + d710 * k10[i] +
+                                        d711 * k2[i] + d712 * k3[i]);
+                    }
+#pragma unroll(GB_NU)
+                    for (int i = 0; i < nn; i++)
+                        yy1[i] = y[i] + h * (a141 * k1[i] + a147 * k7[i] + a148 * k8[i] + a149 * k9[i] + a1410 * k10[i] +
+                                             a1411 * k2[i] + a1412 * k3[i] + a1413 * k4[i]);
+                    rhs(x + c14 * h, yy1, k10);
+#pragma unroll(GB_NU)
+                    for (int i = 0; i < nn; i++)
+                        yy1[i] = y[i] + h * (a151 * k1[i] + a156 * k6[i] + a157 * k7[i] + a158 * k8[i] + a1511 * k2[i] +
+                                             a1512 * k3[i] + a1513 * k4[i] + a1514 * k10[i]);
+                    rhs(x + c15 * h, yy1, k2);
+#pragma unroll(GB_NU)
+                    for (int i = 0; i < nn; i++)
+                        yy1[i] = y[i] + h * (a161 * k1[i] + a166 * k6[i] + a167 * k7[i] + a168 * k8[i] + a169 * k9[i] +
+                                             a1613 * k4[i] + a1614 * k10[i] + a1615 * k2[i]);
+                    rhs(x + c16 * h, yy1, k3);
+                    nfcn += 3;
+#pragma unroll(GB_NU)
+                    for (int i = 0; i < nn; i++) {
+                        emit.st(24 + i, h * (emit.ld(24 + i) + d413 * k4[i] + d414 * k10[i] + d415 * k2[i] + d416 * k3[i]));
+                        emit.st(30 + i, h * (emit.ld(30 + i) + d513 * k4[i] + d514 * k10[i] + d515 * k2[i] + d516 * k3[i]));
+                        emit.st(36 + i, h * (emit.ld(36 + i) + d613 * k4[i] + d614 * k10[i] + d615 * k2[i] + d616 * k3[i]));
+                        emit.st(42 + i, h * (emit.ld(42 + i) + d713 * k4[i] + d714 * k10[i] + d715 * k2[i] + d716 * k3[i]));
+                    }
+#if GB_STRICT
+                    emit.stash(x, h, 0.0);
+#else
+                    emit.stash(x, h, 1.0 / h);            // one division per step, not one per output sample
+#endif
+                } else if constexpr (DENSE) {
                     // dense-output preparation (dop853.cpp:492-582)
 #pragma unroll(GB_NU)
                     for (int i = 0; i < nn; i++) {
@@ -362,17 +420,112 @@ GB_DEV int dop853_integrate(const RHS& rhs, const OUT& emit, const Dop853Args& a
 // fully coalesced reads and writes.  (Writing (6,ntimes,N) directly from per-lane cursors cost 8x
 // the algorithmic DRAM traffic in the first version.)
 // ------------------------------------------------------------------------------------------------
-// Register budget (A/B on B200, 303,104 MW2022 orbits, profiles/c2_ab_r1.txt): the dense kernel is fastest
-// with the full 255 registers (2 CTAs of 128 per SM: 34.1 ms; capped at 168 registers / 3 CTAs: 34.8 ms, at
-// 128 / 4 CTAs: 38.9 ms); the final-state kernel gains from 3 CTAs per SM (14.5 -> 13.3 ms).
+// Dense output is evaluated by the WARP, not by the lane that owns the step (round 2): in the first version every
+// lane looped over the caller's times inside its own accepted step, so a warp iterated max-over-lanes times
+// with mean-over-lanes useful work (22.8 of 32 lanes active per instruction over the whole kernel,
+// profiles/ncu_r1_dop853_mw2022_v2_benchsize.txt) and held rcont1..8 (48 doubles) in registers across three RHS
+// evaluations (230-255 registers, 8 warps per SM).  Now step() deposits the eight coefficient vectors in the
+// warp's shared-memory block ([row][lane], conflict-free for the writer and for readers of distinct or equal
+// owners), and after the step -- outside the accept branch, all 32 lanes converged -- the warp pools its lanes'
+// pending samples: sample s of the pool is evaluated by lane s mod 32 from the owner's column, so the loop runs
+// ceil(total / 32) times with every lane busy, and consecutive lanes write consecutive 48-byte records of the
+// same orbit row.  The numbers are the owner's: same coefficients, same (t - x0) / h, same Horner order.
+#ifndef GB_D8_DENSE_MINB
+#define GB_D8_DENSE_MINB 3       // CTAs of 128 threads per SM the dense kernel is compiled for (168 registers)
+#endif
+#define GB_WD_RC 0               // rcont[48][32]
+#define GB_WD_X0 1536            // x0[32]
+#define GB_WD_H 1568             // h[32]
+#define GB_WD_IH 1600            // 1/h[32] (fast build)
+#define GB_WD_ROW 1632           // row pointer[32] (as 64-bit words)
+#define GB_WD_BEG 1664           // int out_idx[32]
+#define GB_WD_PRE 1680           // int exclusive prefix of the sample counts[32]
+#define GB_WD_DOUBLES 1696       // 13,568 bytes per warp
+
+struct WarpDenseOut {
+    static constexpr bool kDeferred = true;
+    double* col;                 // this lane's column of the warp block
+    int* pending;                // set by stash(): this lane completed an accepted step in this iteration
+    GB_DEV void st(int row, double v) const { col[row * 32] = v; }
+    GB_DEV double ld(int row) const { return col[row * 32]; }
+    GB_DEV void stash(double x0, double h, double ih) const {
+        col[GB_WD_X0] = x0; col[GB_WD_H] = h; col[GB_WD_IH] = ih;
+        *pending = 1;
+    }
+};
+
+// All 32 lanes of the warp call this after every attempted step.  pending: this lane deposited a step.
+// Returns the number of samples of THIS lane that were written (its out_idx advances by that much).
+GB_DEV int warp_dense_flush(double* wb, unsigned lane, int pending, int out_idx, double* srow,
+                            const double* __restrict__ tout, int ntout) {
+    int cnt = 0;
+    if (pending) {
+        // every requested time inside [x, x+h] (dop853.cpp:584-612): the caller's grid is monotonic, stop at the first miss
+        const double x0 = wb[GB_WD_X0 + lane], x1 = x0 + wb[GB_WD_H + lane];
+        int e = out_idx;
+        while (e < ntout) {
+            const double t_out = tout[e];
+            if ((x0 <= t_out && t_out <= x1) || (x1 <= t_out && t_out <= x0)) e++;
+            else break;
+        }
+        cnt = e - out_idx;
+    }
+    if (!__any_sync(0xffffffffu, cnt > 0)) return 0;
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((int)lane >= d) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int* beg = reinterpret_cast<int*>(wb + GB_WD_BEG);
+    int* pre = reinterpret_cast<int*>(wb + GB_WD_PRE);
+    beg[lane] = out_idx;
+    pre[lane] = incl - cnt;
+    reinterpret_cast<double**>(wb + GB_WD_ROW)[lane] = srow;
+    __syncwarp();
+    for (int s0 = 0; s0 < total; s0 += 32) {
+        const int s = s0 + (int)lane;
+        if (s < total) {
+            // owner = the last lane whose exclusive prefix is <= s (lanes without samples share their successor's prefix)
+            int o = 0;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) if (pre[o + d] <= s) o += d;
+            const int idx = beg[o] + (s - pre[o]);
+            const double t_out = tout[idx];
+#if GB_STRICT
+            const double sg = (t_out - wb[GB_WD_X0 + o]) / wb[GB_WD_H + o];
+#else
+            const double sg = (t_out - wb[GB_WD_X0 + o]) * wb[GB_WD_IH + o];
+#endif
+            const double s1 = 1.0 - sg;
+            const double* rc = wb + GB_WD_RC + o;
+            double v[6];
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+                v[i] = rc[i * 32] + sg * (rc[(6 + i) * 32] + s1 * (rc[(12 + i) * 32] + sg * (rc[(18 + i) * 32] + s1 * (rc[(24 + i) * 32] +
+                       sg * (rc[(30 + i) * 32] + s1 * (rc[(36 + i) * 32] + sg * rc[(42 + i) * 32]))))));
+            double2* op = reinterpret_cast<double2*>(reinterpret_cast<double**>(wb + GB_WD_ROW)[o] + (size_t)idx * 6);
+            __stcs(op, make_double2(v[0], v[1])); __stcs(op + 1, make_double2(v[2], v[3])); __stcs(op + 2, make_double2(v[4], v[5]));
+        }
+    }
+    __syncwarp();            // the block is rewritten by the next step
+    return cnt;
+}
+
+// Register budget (A/B on B200, 303,104 MW2022 orbits): round 1, coefficients in registers: 255 registers /
+// 2 CTAs of 128 per SM 34.1 ms, capped at 168 / 3 CTAs 34.8 ms, at 128 / 4 CTAs 38.9 ms (profiles/c2_ab_r1.txt);
+// the final-state kernel gains from 3 CTAs per SM (14.5 -> 13.3 ms).  Round 2 (coefficients in shared memory):
+// see profiles/c2_ab_r2.txt.
 template <class C, bool ROT, bool DENSE>
-__global__ void __launch_bounds__(DENSE ? 256 : 128, DENSE ? 1 : 3)
+__global__ void __launch_bounds__(128, DENSE ? GB_D8_DENSE_MINB : 3)
 k_dop853_dyn(const __grid_constant__ DevPot P, const __grid_constant__ DevFrame F, const __grid_constant__ Dop853Args a,
              const double* __restrict__ w0, size_t N, const double* __restrict__ t, int ntimes,
              const uint32_t* __restrict__ perm, unsigned long long* __restrict__ queue,
              size_t orb0, size_t nslots, double* __restrict__ out, Dop853Stats st, int block_sync) {
     // This launch integrates the orbits [orb0, orb0 + nslots); perm (length nslots, global orbit
     // indices of that range in queue order) may be null = natural order.
+    extern __shared__ double gb_d8_smem[];       // DENSE: one GB_WD_DOUBLES block per warp
     auto rhs = [&](double tt, const double (&w)[6], double (&f)[6]) { ham_rhs<C, ROT>(P, F, tt, w, f); };
     Dop853Lane<DENSE> L;
     const unsigned lane = threadIdx.x & 31u;
@@ -380,10 +533,9 @@ k_dop853_dyn(const __grid_constant__ DevPot P, const __grid_constant__ DevFrame 
     bool active = false, drained = false;
     size_t orb = 0;          // orbit index (column of w0 / of the caller's output)
     double* srow = nullptr;  // DENSE: this orbit's [ntimes][6] block of the scratch array
-    auto emit = [&](int idx, const double (&v)[6]) {
-        double2* o = reinterpret_cast<double2*>(srow + (size_t)idx * 6);
-        __stcs(o, make_double2(v[0], v[1])); __stcs(o + 1, make_double2(v[2], v[3])); __stcs(o + 2, make_double2(v[4], v[5]));
-    };
+    double* wb = gb_d8_smem + (size_t)(threadIdx.x >> 5) * GB_WD_DOUBLES;
+    int pending = 0;
+    WarpDenseOut emit{wb + lane, &pending};
     while (true) {
         if (!drained) {
             const unsigned need = __ballot_sync(0xffffffffu, !active);
@@ -410,26 +562,33 @@ k_dop853_dyn(const __grid_constant__ DevPot P, const __grid_constant__ DevFrame 
         // (the L1.5 I-cache is 32 KB; unsynchronised warps each stream the whole loop body from L2).
         if (block_sync) { if (!__syncthreads_or(active)) break; }
         else if (!__any_sync(0xffffffffu, active)) break;
-        if (active) {
-            const int code = L.step(rhs, emit, a, t, ntimes);
-            if (code != 0) {
-                if (DENSE) {
-                    // a failed orbit leaves its remaining rows undefined in the reference (np.empty); use NaN
-                    const double nan = CUDART_NAN;
-                    for (int j = L.out_idx; j < ntimes; j++)
+        int code = 0;
+        pending = 0;
+        if (active) code = L.step(rhs, emit, a, t, ntimes);
+        if (DENSE) {
+            __syncwarp();
+            L.out_idx += warp_dense_flush(wb, lane, pending, L.out_idx, srow, t, ntimes);
+        }
+        if (active && code != 0) {
+            if (DENSE) {
+                // rows the integration did not reach.  code 1 (success): only the last requested time can be missing,
+                // when x + (xend - x) rounds an ulp short of xend -- the state there IS the final state (the reference
+                // leaves that row of its np.empty output unwritten).  code < 0: the reference leaves the remaining rows
+                // undefined as well; NaN here, and the per-orbit status says why.
+                const double nan = CUDART_NAN;
+                for (int j = L.out_idx; j < ntimes; j++)
 #pragma unroll
-                        for (int c = 0; c < 6; c++) srow[(size_t)j * 6 + c] = nan;
-                } else {
+                    for (int c = 0; c < 6; c++) srow[(size_t)j * 6 + c] = (code == 1) ? L.y[c] : nan;
+            } else {
 #pragma unroll
-                    for (int c = 0; c < 6; c++) out[c * N + orb] = L.y[c];
-                }
-                if (st.status) st.status[orb] = code;
-                if (st.nstep) st.nstep[orb] = L.nstep;
-                if (st.naccpt) st.naccpt[orb] = L.naccpt;
-                if (st.nrejct) st.nrejct[orb] = L.nrejct;
-                if (st.nfcn) st.nfcn[orb] = L.nfcn;
-                active = false;
+                for (int c = 0; c < 6; c++) out[c * N + orb] = L.y[c];
             }
+            if (st.status) st.status[orb] = code;
+            if (st.nstep) st.nstep[orb] = L.nstep;
+            if (st.naccpt) st.naccpt[orb] = L.naccpt;
+            if (st.nrejct) st.nrejct[orb] = L.nrejct;
+            if (st.nfcn) st.nfcn[orb] = L.nfcn;
+            active = false;
         }
     }
 }

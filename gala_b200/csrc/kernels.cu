@@ -98,9 +98,10 @@ __global__ void k_ham_gradient(const __grid_constant__ DevPot P, const __grid_co
 template <class C, bool SAVE>
 __global__ void __launch_bounds__(C::kFixedStepMaxThreads, C::kFixedStepMinBlocks)
 k_leapfrog(const __grid_constant__ DevPot P, const double* __restrict__ w0, size_t N,
-           const double* __restrict__ t, int ntimes, double dt, double* __restrict__ out) {
+           const double* __restrict__ t, int ntimes, double dt, int dt_from_t, double* __restrict__ out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
+    if (dt_from_t) dt = t[1] - t[0];       // DEVICE-mode calls: the grid lives on the device (capi.cu:launch_fixed)
     double x = w0[i], y = w0[N + i], z = w0[2 * N + i];
     double vx = w0[3 * N + i], vy = w0[4 * N + i], vz = w0[5 * N + i];
     const size_t TS = (size_t)ntimes * N;  // stride between phase-space components when SAVE
@@ -144,9 +145,11 @@ struct Ruth4Coef { double c[4], d[4]; };
 template <class C, bool ROT, bool SAVE>
 __global__ void __launch_bounds__(C::kFixedStepMaxThreads, C::kFixedStepMinBlocks)
 k_ruth4(const __grid_constant__ DevPot P, const __grid_constant__ DevFrame F, const __grid_constant__ Ruth4Coef K,
-        const double* __restrict__ w0, size_t N, int ntimes, double dt, double* __restrict__ out) {
+        const double* __restrict__ w0, size_t N, const double* __restrict__ t, int ntimes, double dt, int dt_from_t,
+        double* __restrict__ out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
+    if (dt_from_t) dt = t[1] - t[0];
     double x = w0[i], y = w0[N + i], z = w0[2 * N + i];
     double vx = w0[3 * N + i], vy = w0[4 * N + i], vz = w0[5 * N + i];
     const size_t TS = (size_t)ntimes * N;
@@ -247,24 +250,24 @@ cudaError_t ham_gradient(const DevPot& P, const DevFrame& F, const double* w, do
 }
 
 cudaError_t leapfrog(const DevPot& P, const double* w0, size_t N, const double* t, int ntimes, double dt,
-                     int save_all, double* out, int block, cudaStream_t s) {
+                     int dt_from_t, int save_all, double* out, int block, cudaStream_t s) {
     if (N == 0) return cudaSuccess;
     if (save_all) {
-        GB_SIG_SWITCH(P.sig, (k_leapfrog<C, true><<<nblocks(N, block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads), block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads, 0, s>>>(P, w0, N, t, ntimes, dt, out)));
+        GB_SIG_SWITCH(P.sig, (k_leapfrog<C, true><<<nblocks(N, block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads), block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads, 0, s>>>(P, w0, N, t, ntimes, dt, dt_from_t, out)));
     } else {
-        GB_SIG_SWITCH(P.sig, (k_leapfrog<C, false><<<nblocks(N, block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads), block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads, 0, s>>>(P, w0, N, t, ntimes, dt, out)));
+        GB_SIG_SWITCH(P.sig, (k_leapfrog<C, false><<<nblocks(N, block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads), block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads, 0, s>>>(P, w0, N, t, ntimes, dt, dt_from_t, out)));
     }
     return cudaGetLastError();
 }
 
 cudaError_t ruth4(const DevPot& P, const DevFrame& F, const double* w0, size_t N, const double* t, int ntimes,
-                  double dt, const double* cs, const double* ds, int save_all, double* out, int block,
+                  double dt, int dt_from_t, const double* cs, const double* ds, int save_all, double* out, int block,
                   cudaStream_t s) {
     if (N == 0) return cudaSuccess;
     Ruth4Coef K;
     for (int k = 0; k < 4; k++) { K.c[k] = cs[k]; K.d[k] = ds[k]; }
     const bool rot = F.type != GB_FRAME_STATIC;
-#define GB_R4(ROT, SAVE) GB_SIG_SWITCH(P.sig, (k_ruth4<C, ROT, SAVE><<<nblocks(N, block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads), block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads, 0, s>>>(P, F, K, w0, N, ntimes, dt, out)))
+#define GB_R4(ROT, SAVE) GB_SIG_SWITCH(P.sig, (k_ruth4<C, ROT, SAVE><<<nblocks(N, block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads), block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads, 0, s>>>(P, F, K, w0, N, t, ntimes, dt, dt_from_t, out)))
     if (rot) { if (save_all) { GB_R4(true, true); } else { GB_R4(true, false); } }
     else     { if (save_all) { GB_R4(false, true); } else { GB_R4(false, false); } }
 #undef GB_R4
@@ -290,13 +293,20 @@ static cudaError_t launch_d8(const DevPot& P, const DevFrame& F, const double* w
                              size_t orb0, size_t nslots, double* out, const Dop853Stats& st, int block, int nsm,
                              int block_sync, cudaStream_t s) {
     auto kern = k_dop853_dyn<C, GB_D8_ROT, DENSE>;
+    // DENSE: one block of dense-output coefficients per warp in shared memory (dop853.cuh: warp_dense_flush)
+    const size_t smem = DENSE ? (size_t)(block / 32) * GB_WD_DOUBLES * sizeof(double) : 0;
+    cudaError_t e = cudaSuccess;
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem);
     if (e != cudaSuccess) return e;
     const size_t want = (nslots + block - 1) / block;
     const size_t cap = (size_t)(per_sm > 0 ? per_sm : 1) * nsm;
-    kern<<<(unsigned)(want < cap ? want : cap), block, 0, s>>>(P, F, a, w0, N, t, ntimes, perm, queue, orb0, nslots,
-                                                                out, st, block_sync);
+    kern<<<(unsigned)(want < cap ? want : cap), block, smem, s>>>(P, F, a, w0, N, t, ntimes, perm, queue, orb0, nslots,
+                                                                   out, st, block_sync);
     return cudaGetLastError();
 }
 cudaError_t GB_D8_NAME(const DevPot& P, const DevFrame& F, const double* w0, size_t N, const double* t, int ntimes,
@@ -311,7 +321,7 @@ cudaError_t GB_D8_NAME(const DevPot& P, const DevFrame& F, const double* w0, siz
     e = cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
     if (const char* eb = getenv("GB_D8_BLOCK")) block = atoi(eb);
-    if (block > (save_all ? 256 : 128) || block <= 0 || (block & 31)) block = 64;      // __launch_bounds__ of k_dop853_dyn
+    if (block > 128 || block <= 0 || (block & 31)) block = 64;      // __launch_bounds__ of k_dop853_dyn
     const char* bs = getenv("GB_D8_BLOCKSYNC");
     const int block_sync = bs ? atoi(bs) : (block > 32);
     if (save_all) {

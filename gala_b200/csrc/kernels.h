@@ -37,10 +37,10 @@ struct Dop853Args {
     cudaError_t ham_gradient(const DevPot& P, const DevFrame& F, const double* w, double t, size_t N,     \
                              double* f, int block, cudaStream_t s);                                        \
     cudaError_t leapfrog(const DevPot& P, const double* w0, size_t N, const double* t, int ntimes,        \
-                         double dt, int save_all, double* out, int block, cudaStream_t s);                 \
+                         double dt, int dt_from_t, int save_all, double* out, int block, cudaStream_t s);  \
     cudaError_t ruth4(const DevPot& P, const DevFrame& F, const double* w0, size_t N, const double* t,    \
-                      int ntimes, double dt, const double* cs, const double* ds, int save_all,             \
-                      double* out, int block, cudaStream_t s);                                             \
+                      int ntimes, double dt, int dt_from_t, const double* cs, const double* ds,            \
+                      int save_all, double* out, int block, cudaStream_t s);                               \
     cudaError_t dop853_static(const DevPot& P, const DevFrame& F, const double* w0, size_t N,             \
                               const double* t, int ntimes, const Dop853Args& a, int save_all,              \
                               const uint32_t* perm, unsigned long long* queue, size_t orb0, size_t nslots, \

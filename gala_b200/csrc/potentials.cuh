@@ -38,7 +38,10 @@ template <int USE> struct FastCtx {
     }
     GB_DEV void finish(double& ox, double& oy, double& oz) const {
         double s = 0.;
-        if (USE & GB_USE_SIR) s = (USE & GB_USE_FS) ? fma(Sir, ir, Fs) : Sir * ir;
+        // generic loop (USE == GB_USE_ALL): no component may have touched Sir -- a lone Plummer / MiyamotoNagai / ...
+        // evaluated at r = 0, where ir is NaN (0 * inf in the rsqrt refinement) while the reference's value is finite
+        if (USE == GB_USE_ALL) s = (Sir != 0.) ? fma(Sir, ir, Fs) : Fs;
+        else if (USE & GB_USE_SIR) s = (USE & GB_USE_FS) ? fma(Sir, ir, Fs) : Sir * ir;
         else if (USE & GB_USE_FS) s = Fs;
         constexpr bool SPH = (USE & (GB_USE_SIR | GB_USE_FS)) != 0;
         double fxy, fz;

@@ -41,7 +41,8 @@ class Hamiltonian:
         N = buf.arr.shape[1]
         out = _alloc_like(buf, (rows, N) if rows > 1 else (N,))
         stream, dev = _stream_of(buf)
-        opt = _abi.launch_opts(buf.device, self.strict_math or self.potential.strict_math, stream, device=dev)
+        opt = _abi.launch_opts(buf.device, self.strict_math or self.potential.strict_math, stream, device=dev,
+                               devices=None)
         fr = self.frame.spec()
         fn = getattr(_abi.lib(), fn_name)
         _abi.check(fn(self.potential.spec().ptr(), C.byref(fr), buf.ptr, float(strip(t)), N, _abi.Buf(out).ptr,

@@ -124,7 +124,7 @@ def _opts(like, hamiltonian, block=0):
         stream = torch.cuda.current_stream(like.arr.device).cuda_stream
         dev = like.arr.device.index
     strict = bool(getattr(hamiltonian, "strict_math", False) or getattr(hamiltonian.potential, "strict_math", False))
-    return _abi.launch_opts(like.device, strict, stream, block=block, device=dev)
+    return _abi.launch_opts(like.device, strict, stream, block=block, device=dev, devices=None)
 
 
 def _check_c_enabled(hamiltonian):

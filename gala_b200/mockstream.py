@@ -27,8 +27,11 @@ __all__ = ["BaseStreamDF", "FardalStreamDF", "StreaklineStreamDF", "LagrangeClou
            "MockStreamGenerator", "DirectNBody", "mockstream_dop853", "mockstream_leapfrog", "mockstream_dop853_animate"]
 
 
-def _opts(H):
-    return _abi.launch_opts(False, bool(getattr(H, "strict_math", False) or H.potential.strict_math))
+def _opts(H, shard=False):
+    """``shard``: the entry point deals its particles over the devices of ``_abi.set_devices`` (test-particle mock
+    streams); the N-body / snapshot entry points run on one device."""
+    return _abi.launch_opts(False, bool(getattr(H, "strict_math", False) or H.potential.strict_math),
+                            devices=None if shard else False)
 
 
 class BaseStreamDF:
@@ -389,7 +392,7 @@ def mockstream_dop853(nbody, time, stream_w0, stream_t1, tfinal, nstream, atol=1
     t1 = np.concatenate([np.repeat(stream_t1, nstream), np.full(nbodies, stream_t1[last])])
     out = np.empty_like(rows)
     status = np.empty(rows.shape[0], dtype=np.int32)
-    opt = _opts(H)
+    opt = _opts(H, shard=True)
     fr = H.frame.spec()
     rc = _abi.lib().gb_mockstream_dop853(H.potential.spec().ptr(), C.byref(fr), rows.ctypes.data, t1.ctypes.data,
                                          rows.shape[0], float(tfinal), float(dt0), float(atol), float(rtol),
@@ -533,7 +536,7 @@ def mockstream_leapfrog(nbody, full_time, spawn_time, stream_w0, stream_t1, tfin
     rows = np.vstack([stream_w0, traj[:, idx, :].T])
     t1 = np.concatenate([np.repeat(stream_t1, nstream), np.full(nbodies, stream_t1[last])])
     out = np.empty_like(rows)
-    opt = _opts(H)
+    opt = _opts(H, shard=True)
     _abi.check(_abi.lib().gb_mockstream_leapfrog(H.potential.spec().ptr(), rows.ctypes.data, t1.ctypes.data,
                                                  rows.shape[0], float(tfinal), float(dt), out.ctypes.data,
                                                  C.byref(opt)))

@@ -129,7 +129,8 @@ class PotentialBase:
         N = buf.arr.shape[1]
         out = _alloc_like(buf, (out_rows, N) if out_rows > 1 else (N,))
         stream, dev = _stream_of(buf)
-        opt = _abi.launch_opts(buf.device, self.strict_math, stream, device=dev)
+        opt = _abi.launch_opts(buf.device, self.strict_math, stream, device=dev,
+                               devices=False if fn_name == "gb_hessian" else None)
         fn = getattr(_abi.lib(), fn_name)
         _abi.check(fn(self.spec().ptr(), buf.ptr, float(strip(t)), N, _abi.Buf(out).ptr, C.byref(opt)))
         if out_rows > 1:

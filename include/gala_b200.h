@@ -111,6 +111,15 @@ typedef struct {
     int32_t strict_math;      /* 1 = strict-IEEE kernels (reference operation order,
                                  no FMA contraction, libm pow/log); 0 = fast kernels */
     int32_t block_threads;    /* 0 = library default                                */
+    int32_t n_devices;        /* GB_MEM_HOST calls only: > 0 = shard the call over devices[0..n_devices-1]
+                                 (orbit-index sharding; no collective: every device takes a
+                                 contiguous slice of the orbit index -- block-cyclic groups of 128 particles for
+                                 the mock-stream integrators, whose work per particle is triangular in release
+                                 time -- copies its slice straight out of / into the caller's arrays and the call
+                                 returns when all devices are done).  0 = the single `device` above.  The result
+                                 is bit-identical to the single-device call: orbits never interact.            */
+    int32_t _pad;
+    const int32_t* devices;   /* CUDA device ordinals, n_devices entries                  */
 } gb_launch;
 
 /* Per-orbit DOP853 statistics (dopcor's nstep/naccpt/nrejct/nfcn,

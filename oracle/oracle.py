@@ -131,6 +131,22 @@ class _Lib:
                                 C.c_int(nbatch), out.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p))
         return out, status, rc
 
+    def dop853_nfcn(self, H, w0, t, atol=1e-10, rtol=1e-10, nmax=0, dt_max=0.0, nstiff=0, save_all=True, nbatch=1):
+        """As ``dop853`` plus, per orbit, the number of right-hand-side calls the reference's own ``dop853()`` made
+        (observed through a counting wrapper around ``Fwrapper_T``; = dopcor's ``nfcn`` for ``nbatch=1``).
+        Compiled-reference checker only."""
+        w0 = _f64(w0); t = _f64(t); N = w0.shape[1]
+        out = np.empty((6, t.size, N) if save_all else (6, N))
+        status = np.empty(N, dtype=np.int32)
+        nfcn = np.empty(N, dtype=np.int32)
+        fr = H.frame.spec()
+        rc = self._fn("dop853_nfcn")(H.potential.spec().ptr(), C.byref(fr), w0.ctypes.data_as(C.c_void_p), C.c_size_t(N),
+                                     t.ctypes.data_as(C.c_void_p), C.c_int(t.size), C.c_double(atol), C.c_double(rtol),
+                                     C.c_long(nmax), C.c_double(dt_max), C.c_long(nstiff), C.c_int(int(save_all)),
+                                     C.c_int(nbatch), out.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p),
+                                     nfcn.ctypes.data_as(C.c_void_p))
+        return out, status, rc, nfcn
+
     def dop853_step_rows(self, H, rows, t1, t2, dt0, atol=1e-10, rtol=1e-10, nmax=0, group=True):
         """rows (Np,6) integrated t1->t2 with dop853_step's settings; group=True: each row alone."""
         rows = _f64(rows).copy(); Np = rows.shape[0]

@@ -319,12 +319,36 @@ int ref_ruth4(const gb_potential *spec, const gb_frame *fr, const double *w0, si
     return 0;
 }
 
+// The reference's dopcor keeps nstep / naccpt / nrejct / nfcn as locals and its header only DECLARES
+// nfcnRead() ... nrejctRead() (dopri/dop853.h:252-255; no definition exists in dop853.cpp), so the step
+// statistics cannot be read from the unmodified sources.  What CAN be observed from outside is every call of
+// the right-hand side: this wrapper is handed to dop853() in place of Fwrapper_T, counts, and forwards.
+// With nbatch = 1 the count is dopcor's nfcn of that orbit: 2 + 11 nstep + naccpt (+ 3 naccpt with dense output).
+static thread_local long g_fcn_calls = 0;
+static void counting_Fwrapper_T(unsigned full_ndim, double t, double *w, double *f, CPotential *p, CFrameType *fr,
+                                unsigned norbits, unsigned na, void *args) {
+    g_fcn_calls++;
+    Fwrapper_T(full_ndim, t, w, f, p, fr, norbits, na, args);
+}
+
+int ref_dop853_nfcn(const gb_potential *spec, const gb_frame *fr, const double *w0, size_t N, const double *t,
+                    int ntimes, double atol, double rtol, long nmax, double dt_max, long nstiff, int save_all,
+                    int nbatch, double *w_out, int32_t *status, int32_t *nfcn);
+
 // dop853_integrate_hamiltonian (integrate/cyintegrators/dop853.pyx:196-250) calling
 // dop853_helper (:90-193) per batch of `nbatch` orbits.  status[i] = dop853 return code of the
 // batch orbit i belongs to.  Returns the most negative code, or 0.
 int ref_dop853(const gb_potential *spec, const gb_frame *fr, const double *w0, size_t N, const double *t,
                int ntimes, double atol, double rtol, long nmax, double dt_max, long nstiff, int save_all,
                int nbatch, double *w_out, int32_t *status) {
+    return ref_dop853_nfcn(spec, fr, w0, N, t, ntimes, atol, rtol, nmax, dt_max, nstiff, save_all, nbatch, w_out,
+                           status, NULL);
+}
+
+// nfcn (may be NULL): per orbit, the number of right-hand-side calls dop853() made for the batch it belongs to.
+int ref_dop853_nfcn(const gb_potential *spec, const gb_frame *fr, const double *w0, size_t N, const double *t,
+                    int ntimes, double atol, double rtol, long nmax, double dt_max, long nstiff, int save_all,
+                    int nbatch, double *w_out, int32_t *status, int32_t *nfcn) {
     RefPotential rp; if (!build(spec, rp)) return -11;
     RefFrame rf; build_frame(fr, rf);
     if (ntimes < 1) return -12;
@@ -337,7 +361,9 @@ int ref_dop853(const gb_potential *spec, const gb_frame *fr, const double *w0, s
             for (size_t i = 0; i < nb; i++) w[k * nb + i] = w0[k * N + i0 + i];
         Dop853DenseState *state = save_all ? dop853_dense_state_alloc(size, size) : NULL;
         double rt = rtol, at = atol;
-        int res = dop853(size, (FcnEqDiff)Fwrapper_T, rp.cp, &rf.cf, nb, 0, NULL, t[0], w.data(),
+        g_fcn_calls = 0;
+        int res = dop853(size, nfcn ? (FcnEqDiff)counting_Fwrapper_T : (FcnEqDiff)Fwrapper_T, rp.cp, &rf.cf, nb, 0, NULL,
+                         t[0], w.data(),
                          t[ntimes - 1], &rt, &at, 0, NULL, 0, NULL,
                          2.220446049250313e-16,  // np.finfo(float).eps (dop853.pyx:165)
                          0.0, 0.0, 0.0, 0.0, dt_max, t[1] - t[0], nmax, 1, nstiff,
@@ -346,6 +372,7 @@ int ref_dop853(const gb_potential *spec, const gb_frame *fr, const double *w0, s
         if (state) dop853_dense_state_free(state, size);
         if (res < worst) worst = res;
         for (size_t i = 0; i < nb; i++) if (status) status[i0 + i] = res;
+        for (size_t i = 0; i < nb; i++) if (nfcn) nfcn[i0 + i] = (int32_t)g_fcn_calls;
         if (save_all) {
             // wres[:, :, i:j] = wbatchout.transpose(1,0,2)   (dop853.pyx:242-243)
             for (int j = 0; j < ntimes; j++)

@@ -38,6 +38,26 @@ def make_ic(pot_gradient, N, seed, rmin=4.0, rmax=50.0):
     return np.ascontiguousarray(np.vstack([q, v]))
 
 
+def make_ic_survey(pot_gradient, N, seed, rmin=2.0, rmax=50.0):
+    """SURVEY.md section 8d's recipe verbatim: r = exp(U[ln 2, ln 50]) kpc with isotropic direction; speed =
+    f * v_circ(r), f ~ U[0.3, 1.0]; velocity direction ISOTROPIC.  Includes plunging orbits through the 70-pc
+    nucleus of MilkyWayPotential2022, on which two builds of the reference itself diverge (numerical chaos); the
+    parity assertions arbitrate those with the reference-vs-reference floor (``assert_within_floor``) instead of
+    leaving them out."""
+    rng = np.random.default_rng(seed)
+    r = np.exp(rng.uniform(np.log(rmin), np.log(rmax), N))
+    mu = rng.uniform(-1, 1, N); ph = rng.uniform(0, 2 * np.pi, N)
+    s = np.sqrt(1 - mu * mu)
+    q = r * np.vstack([s * np.cos(ph), s * np.sin(ph), mu])
+    mv = rng.uniform(-1, 1, N); pv = rng.uniform(0, 2 * np.pi, N)
+    sv = np.sqrt(1 - mv * mv)
+    vhat = np.vstack([sv * np.cos(pv), sv * np.sin(pv), mv])
+    g = pot_gradient(np.ascontiguousarray(q))
+    vc = np.sqrt(r * np.sqrt((g * g).sum(0)))
+    v = rng.uniform(0.3, 1.0, N) * vc * vhat
+    return np.ascontiguousarray(np.vstack([q, v]))
+
+
 def relnorm(a, b):
     """Per-orbit norm-relative difference of positions and of velocities: arrays (6, ..., N) -> (2, ..., N)."""
     dp = np.sqrt(((a[:3] - b[:3]) ** 2).sum(0)) / np.sqrt((b[:3] ** 2).sum(0))
@@ -69,8 +89,12 @@ def assert_within_floor(d, floor, abs_tol, label="", qs=(0.5, 0.9, 0.99, 1.0), f
     2000 orbits whose q50/q90/q99 agree to 10 %)."""
     dq = np.quantile(d, qs)
     fq = np.quantile(floor, qs) if floor is not None else np.zeros(len(qs))
-    print(f"\n[{label}] GPU-vs-ref q50/90/99/max = " + " ".join(f"{x:.2e}" for x in dq)
-          + (" | ref(-Ofast)-vs-ref(-O2) = " + " ".join(f"{x:.2e}" for x in fq) if floor is not None else ""))
+    line = (f"[{label}] GPU-vs-ref q50/90/99/max = " + " ".join(f"{x:.2e}" for x in dq)
+            + (" | ref(-Ofast)-vs-ref(-O2) = " + " ".join(f"{x:.2e}" for x in fq) if floor is not None else ""))
+    print("\n" + line)
+    if os.environ.get("GB_PARITY_LOG"):          # the GPU session copies this file into profiles/
+        with open(os.environ["GB_PARITY_LOG"], "a") as fh:
+            fh.write(line + "\n")
     for q, a, b in zip(qs, dq, fq):
         f = max_factor if (max_factor is not None and q == 1.0) else factor
         assert a <= max(abs_tol, f * b), f"{label}: q{q} = {a:.3e} exceeds max({abs_tol:.1e}, {f}x floor {b:.3e})"

@@ -35,7 +35,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_abi.gb_component) == 120
     assert ctypes.sizeof(_abi.gb_potential) == 16
     assert ctypes.sizeof(_abi.gb_frame) == 32
-    assert ctypes.sizeof(_abi.gb_launch) == 24
+    assert ctypes.sizeof(_abi.gb_launch) == 40
     assert ctypes.sizeof(_abi.gb_dop853_stats) == 32
 
 

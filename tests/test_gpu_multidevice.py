@@ -1,0 +1,136 @@
+"""`-m gpu`: one HOST-mode C-ABI call sharded over several devices (gb_launch.n_devices, SURVEY 8e / north_star
+"each GPU takes a contiguous slice of orbits and results are gathered to the host") must return the bits of the
+single-device call: orbits never interact, so slicing may not change a single result.
+
+Two layers: (1) on ANY box, the slicing / pitched-copy / block-cyclic-deal logic is exercised by listing device 0
+several times (test hook GB_ALLOW_DUP_DEVICES: the slices then run one after the other on that device);
+(2) with >= 2 GPUs the same comparisons run over really distinct devices.
+Reference entry being replaced: potential/hamiltonian/chamiltonian.pyx:315-356 (one call, whole w0)."""
+import os
+
+import numpy as np
+import pytest
+
+import gala_b200 as gb
+from gala_b200 import _abi
+from conftest import make_ic
+
+pytestmark = pytest.mark.gpu
+
+
+def device_lists():
+    out = [pytest.param([0, 0, 0], id="dev0x3-sliced")]
+    n = _abi.device_count()
+    if n >= 2:
+        out.append(pytest.param(list(range(min(n, 8))), id=f"{min(n, 8)}gpus"))
+    else:
+        out.append(pytest.param(None, id="multi-gpu", marks=pytest.mark.skip(reason="needs >= 2 GPUs")))
+    return out
+
+
+class use_devices:
+    def __init__(self, devs):
+        self.devs = devs
+
+    def __enter__(self):
+        os.environ["GB_ALLOW_DUP_DEVICES"] = "1"
+        _abi._devices = list(self.devs)
+
+    def __exit__(self, *a):
+        _abi._devices = None
+        os.environ.pop("GB_ALLOW_DUP_DEVICES", None)
+
+
+@pytest.fixture(scope="module")
+def mw():
+    return gb.Hamiltonian(gb.MilkyWayPotential2022())
+
+
+@pytest.mark.parametrize("devs", device_lists())
+@pytest.mark.parametrize("N,save_all", [(1003, 1), (1003, 0), (200_001, 0), (70_000, 1)])
+def test_leapfrog_sharded_bit_identical(mw, devs, N, save_all):
+    w0 = make_ic(lambda q: mw.potential.gradient(q), N, 11)
+    t = np.arange(41 if N > 5000 else 201, dtype=float)
+    _, ref = gb.leapfrog_integrate_hamiltonian(mw, w0, t, save_all=save_all)
+    with use_devices(devs):
+        _, got = gb.leapfrog_integrate_hamiltonian(mw, w0, t, save_all=save_all)
+    assert got.shape == ref.shape
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("devs", device_lists())
+def test_ruth4_rotating_sharded_bit_identical(devs):
+    pot = gb.CCompositePotential()
+    pot["bar"] = gb.LongMuraliBarPotential(m=1e10, a=4.0, b=0.8, c=0.25, alpha=0.4)
+    for k, v in gb.MilkyWayPotential2022().items():
+        pot[k] = v
+    H = gb.Hamiltonian(pot, gb.ConstantRotatingFrame([0.0, 0.0, 0.03]))
+    w0 = make_ic(lambda q: pot.gradient(q), 777, 12)
+    t = np.arange(101) * 0.5
+    _, ref = gb.ruth4_integrate_hamiltonian(H, w0, t, save_all=1, allow_rotating_frame=True)
+    with use_devices(devs):
+        _, got = gb.ruth4_integrate_hamiltonian(H, w0, t, save_all=1, allow_rotating_frame=True)
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("devs", device_lists())
+@pytest.mark.parametrize("save_all", [1, 0])
+def test_dop853_sharded_bit_identical(mw, devs, save_all):
+    N = 4099          # > 2048 per call: the single-device call sorts its queue; slices below 2048 do not -- same bits
+    w0 = make_ic(lambda q: mw.potential.gradient(q), N, 13)
+    t = np.linspace(0.0, 300.0, 61)
+    _, ref, sref = gb.dop853_integrate_hamiltonian(mw, w0, t, save_all=save_all, return_status=True)
+    with use_devices(devs):
+        _, got, sgot = gb.dop853_integrate_hamiltonian(mw, w0, t, save_all=save_all, return_status=True)
+    assert np.array_equal(got, ref)
+    for k in ("status", "nstep", "naccpt", "nrejct", "nfcn"):
+        assert np.array_equal(sgot[k], sref[k]), k
+
+
+@pytest.mark.parametrize("devs", device_lists())
+def test_evaluation_sharded_bit_identical(mw, devs):
+    rng = np.random.default_rng(3)
+    q = rng.normal(0, 15, (3, 2501))
+    w = np.vstack([q, rng.normal(0, 0.1, (3, 2501))])
+    pot = mw.potential
+    ref = [pot.gradient(q), pot.energy(q), pot.density(q), mw.energy(w), mw.gradient(w)]
+    with use_devices(devs):
+        got = [pot.gradient(q), pot.energy(q), pot.density(q), mw.energy(w), mw.gradient(w)]
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("devs", device_lists())
+@pytest.mark.parametrize("integ", ["leapfrog", "dopri853"])
+def test_mockstream_dealt_bit_identical(mw, devs, integ):
+    """The particle rows are dealt in groups of 128 (capi.cu:Deal): 2 x 3 x 301 = 1806 particles = 14 full groups
+    + a partial one, so every branch of the pitched copies runs."""
+    prog = gb.PhaseSpacePosition(pos=[13.0, 0.0, 20.0], vel=np.array([0.0, 130.0, 50.0]) * gb.KMS_TO_KPC_MYR)
+
+    def run():
+        gen = gb.MockStreamGenerator(gb.FardalStreamDF(gala_modified=True, random_state=np.random.RandomState(7)), mw)
+        stream, p = gen.run(prog, 2.5e4, dt=-1.0, n_steps=300, n_particles=3, release_every=1, Integrator=integ)
+        return stream.w(), p.w()
+
+    ref = run()
+    with use_devices(devs):
+        got = run()
+    assert got[0].shape == (6, 1806)
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+
+
+def test_device_list_validation(mw):
+    w0 = make_ic(lambda q: mw.potential.gradient(q), 64, 1)
+    t = np.arange(5.0)
+    _abi._devices = [0, 0]
+    try:
+        with pytest.raises(ValueError, match="twice"):
+            gb.leapfrog_integrate_hamiltonian(mw, w0, t)
+        _abi._devices = [4096]
+        with pytest.raises(ValueError, match="not a CUDA device"):
+            gb.leapfrog_integrate_hamiltonian(mw, w0, t)
+    finally:
+        _abi._devices = None
+    with pytest.raises(ValueError):
+        gb.set_devices([0, 0])
+    assert gb.set_devices(None) is None

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 import gala_b200 as gb
-from conftest import assert_within_floor, make_ic, relnorm
+from conftest import assert_within_floor, make_ic, make_ic_survey, relnorm
 
 pytestmark = pytest.mark.gpu
 
@@ -261,6 +261,60 @@ def test_leapfrog_short_span_all_orbits(ref, ref_fast):
         pot.strict_math = False
 
 
+# ---- SURVEY 8d's isotropic IC recipe verbatim (plunging orbits included) --------------------------------
+def test_survey_ic_leapfrog_short_span(ref, ref_fast):
+    """100 steps, every orbit of the SURVEY 8d recipe (isotropic velocities, r from 2 kpc, f from 0.3)."""
+    t = np.arange(101, dtype=float)
+    for name in ("nfw", "mw2022", "bar_mw2022"):
+        pot = POTS[name]
+        w0 = make_ic_survey(lambda q: ref.gradient(pot, q), 5000, seed=21)
+        w_ref = ref.leapfrog(pot, w0, t, save_all=False)
+        floor = relnorm(ref_fast.leapfrog(pot, w0, t, save_all=False), w_ref).max(0) if ref_fast else None
+        for strict in (True, False):
+            pot.strict_math = strict
+            _, w = gb.leapfrog_integrate_hamiltonian(gb.Hamiltonian(pot), w0, t, save_all=0)
+            assert_within_floor(relnorm(w, w_ref).max(0), floor, 1e-12, f"SURVEY-IC leapfrog 100 steps {name} strict={strict}")
+        pot.strict_math = False
+
+
+def test_survey_ic_leapfrog_long(ref, ref_fast):
+    """10^4 steps on the SURVEY 8d recipe (rmin = 4 kpc for both potentials, isotropic velocities): asserted with
+    the reference-vs-reference floor at every quantile; the strict build must also sit within 10x of the floor's
+    median (it is the same algorithm in the same operation order)."""
+    t = np.arange(10_001, dtype=float)
+    for name in ("nfw", "mw2022"):
+        pot = POTS[name]
+        w0 = make_ic_survey(lambda q: ref.gradient(pot, q), 2000, seed=22, rmin=4.0)
+        w_ref = ref.leapfrog(pot, w0, t, save_all=False)
+        floor = relnorm(ref_fast.leapfrog(pot, w0, t, save_all=False), w_ref).max(0) if ref_fast else None
+        for strict in (True, False):
+            pot.strict_math = strict
+            _, w = gb.leapfrog_integrate_hamiltonian(gb.Hamiltonian(pot), w0, t, save_all=0)
+            d = relnorm(w, w_ref).max(0)
+            assert_within_floor(d, floor, 1e-12, f"SURVEY-IC leapfrog 1e4 steps {name} strict={strict}", max_factor=100.0)
+        pot.strict_math = False
+
+
+def test_survey_ic_dop853_dense(ref, ref_fast):
+    """C2 slice on the SURVEY 8d recipe: DOP853 atol = rtol = 1e-10, 1000 output times."""
+    pot = POTS["mw2022"]
+    H = gb.Hamiltonian(pot)
+    w0 = make_ic_survey(lambda q: ref.gradient(pot, q), 1500, seed=23)
+    t = np.linspace(0, 1000, 1000)
+    w_ref, st_ref, rc = ref.dop853(H, w0, t, nbatch=1)
+    ok = st_ref == 1
+    assert ok.mean() > 0.95              # a radial plunge into the nucleus may make the reference itself give up
+    floor = relnorm(ref_fast.dop853(H, w0, t, nbatch=1)[0], w_ref).max(0).max(0)[ok] if ref_fast else None
+    for strict in (True, False):
+        H.strict_math = strict
+        _, w, stats = gb.dop853_integrate_hamiltonian(H, w0, t, return_status=True, err_if_fail=0)
+        if strict:
+            assert np.array_equal(stats["status"], st_ref)
+        d = relnorm(w, w_ref).max(0).max(0)[ok & (stats["status"] == 1)]
+        fl = floor if floor is None else floor[(stats["status"] == 1)[ok]]
+        assert_within_floor(d, fl, 1e-9, f"SURVEY-IC dop853 dense strict={strict}")
+
+
 @pytest.mark.parametrize("dt", [2.0, -2.0])
 def test_cyintegrators_setup(ref, dt):
     """The reference's own Cython-vs-Python integrator test setup
@@ -337,6 +391,43 @@ def test_c2_dop853_dense(ref, ref_fast, rotating):
     wb_ref, _, _ = ref.dop853(H, w0[:, :100], tb, nbatch=1)
     _, wb = gb.dop853_integrate_hamiltonian(H, w0[:, :100], tb)
     assert_within_floor(relnorm(wb, wb_ref).max(0).max(0), None if floor is None else floor[:100], 1e-9, "dop853 backward")
+
+
+@pytest.mark.parametrize("rotating", [False, True])
+def test_dop853_step_statistics_equal_reference(ref, rotating):
+    """The controller is the reference's, step for step: per orbit, the strict kernel attempts and accepts exactly as
+    many steps as the reference's own dop853() (run with nbatch=1) and calls the right-hand side exactly as often.
+    The reference keeps nstep/naccpt/nrejct/nfcn as locals of dopcor and only declares nfcnRead()... in its header
+    (dopri/dop853.h:252-255, no definition), so the oracle observes every RHS call through a counting wrapper
+    around Fwrapper_T: calls = 1 + 11 nstep + naccpt (+ 3 naccpt with dense output); dopcor's own nfcn, which the
+    kernel mirrors, books 2 for the start even when no hinit() call is made (dop853.cpp:361-366)."""
+    pot = POTS["mw2022"]
+    frame = gb.ConstantRotatingFrame([0.0, 0.0, 0.030681]) if rotating else gb.StaticFrame()
+    H = gb.Hamiltonian(pot, frame)
+    H.strict_math = True
+    N = 300 if rotating else 1200
+    w0 = make_ic(lambda q: ref.gradient(pot, q), N, seed=2)
+    t = np.linspace(0, 1000, 1000)
+    _, _, _, calls_dense = ref.dop853_nfcn(H, w0, t, save_all=True, nbatch=1)
+    _, _, _, calls_final = ref.dop853_nfcn(H, w0, t, save_all=False, nbatch=1)
+    naccpt_ref = (calls_dense - calls_final) // 3
+    nstep_ref = (calls_final - 1 - naccpt_ref) // 11
+    assert not ((calls_dense - calls_final) % 3).any() and not ((calls_final - 1 - naccpt_ref) % 11).any()
+    for save_all, calls in ((1, calls_dense), (0, calls_final)):
+        _, _, st = gb.dop853_integrate_hamiltonian(H, w0, t, save_all=save_all, return_status=True)
+        assert np.all(st["status"] == 1)
+        assert np.array_equal(st["nfcn"], calls + 1), f"save_all={save_all}: RHS call counts differ"
+        assert np.array_equal(st["nstep"], nstep_ref)
+        assert np.array_equal(st["naccpt"], naccpt_ref)
+        assert np.all(st["nrejct"] <= st["nstep"] - st["naccpt"])      # rejections before the first accepted step are not counted (dop853.cpp:642)
+    rej = 1.0 - naccpt_ref.sum() / nstep_ref.sum()
+    print(f"\n[dop853 step statistics rot={rotating}] identical for {N} orbits: nstep mean {nstep_ref.mean():.1f}, "
+          f"naccpt mean {naccpt_ref.mean():.1f}, rejected fraction {rej:.3f}")
+    # the fast build takes the same controller through rounding-level different arithmetic: the counts may differ by
+    # a step here and there, not systematically
+    H.strict_math = False
+    _, _, stf = gb.dop853_integrate_hamiltonian(H, w0, t, save_all=1, return_status=True)
+    assert abs(stf["nstep"].sum() / nstep_ref.sum() - 1.0) < 2e-3
 
 
 def test_dop853_failure_codes(ref):

@@ -407,3 +407,124 @@ def test_multipole_port_equals_reference_and_is_a_gradient(ref, port, inner):
     # on the z axis the theta and phi components are dropped (multipole.cpp:117-121, 281-283)
     qz = np.array([[0.0], [0.0], [5.0]])
     assert np.allclose(ref.gradient(pot, qz), port.gradient(pot, qz), rtol=1e-12, atol=1e-30)
+
+
+# ---- the GSL stand-ins of oracle/gsl_shim against scipy.special ----------------------
+def _shim():
+    import ctypes as C
+    from oracle import oracle
+    path = os.path.join(oracle._REF_DIR, "libgsl_shim_probe.so")
+    if not os.path.exists(path):
+        oracle.build()
+    return C.CDLL(path)
+
+
+def _shim_call(fn, ints, dbls):
+    import ctypes as C
+    n = len(dbls[-1])
+    out = np.empty(n)
+    args = [np.ascontiguousarray(a, dtype=np.int32) for a in ints] + [np.ascontiguousarray(a, dtype=np.float64) for a in dbls]
+    fn(*[a.ctypes.data_as(C.c_void_p) for a in args], C.c_int(n), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def test_gsl_shim_gegenbauer_matches_scipy():
+    """gsl_sf_gegenpoly_n(n, 2l + 3/2, xi) as bfe_helper.cpp:17,25,56-57 calls it: n <= 12, l <= 8, xi in [-1, 1]."""
+    from scipy.special import eval_gegenbauer
+    L = _shim()
+    xi = np.concatenate([np.linspace(-1, 1, 41), np.random.default_rng(0).uniform(-1, 1, 60)])
+    n, l, x = np.meshgrid(np.arange(13), np.arange(9), xi, indexing="ij")
+    n, l, x = n.ravel(), l.ravel(), x.ravel()
+    lam = 2.0 * l + 1.5
+    got = _shim_call(L.shim_gegenpoly_n, [n], [lam, x])
+    want = eval_gegenbauer(n, lam, x)
+    scale = np.maximum(np.abs(want), eval_gegenbauer(n, lam, 1.0) * 1e-3)     # relative to the polynomial's own size
+    assert np.max(np.abs(got - want) / scale) < 1e-13
+    # arbitrary-precision arbiter on a sub-sample: the three-term recurrence in exact rational arithmetic
+    from fractions import Fraction
+    for nn, ll, xx in [(12, 8, 0.3), (7, 3, -0.9), (10, 0, 0.999), (4, 6, -1.0)]:
+        lamf, xf = Fraction(2 * ll) + Fraction(3, 2), Fraction(xx)
+        c0, c1 = Fraction(1), 2 * lamf * xf
+        for k in range(2, nn + 1):
+            c0, c1 = c1, (2 * (k + lamf - 1) * xf * c1 - (k + 2 * lamf - 2) * c0) / k
+        g = _shim_call(L.shim_gegenpoly_n, [[nn]], [[float(lamf)], [xx]])[0]
+        assert abs(g - float(c1)) <= 1e-13 * abs(float(c1))
+
+
+def test_gsl_shim_legendre_matches_scipy():
+    """gsl_sf_legendre_Plm / sphPlm (bfe_helper.cpp:21,28,42,46,66; multipole.cpp:40-111) with the Condon-Shortley
+    phase, l <= 8 (and up to the multipole kernel's lmax = 15), x = cos(theta) over [-1, 1]."""
+    from scipy.special import lpmv, gammaln
+    L = _shim()
+    xs = np.concatenate([np.linspace(-1, 1, 41), np.random.default_rng(1).uniform(-1, 1, 60)])
+    ls, ms, x = [], [], []
+    for l in range(16):
+        for m in range(l + 1):
+            ls += [l] * xs.size; ms += [m] * xs.size; x += list(xs)
+    ls, ms, x = np.array(ls), np.array(ms), np.array(x)
+    want = lpmv(ms, ls, x)
+    got = _shim_call(L.shim_legendre_Plm, [ls, ms], [x])
+    # size of P_l^m over [-1,1] grows like (l+m)!/(l-m)!: compare relative to the per-(l,m) maximum
+    key = ls * 100 + ms
+    scale = np.zeros_like(want)
+    for k in np.unique(key):
+        sel = key == k
+        scale[sel] = np.abs(want[sel]).max()
+    lo = ls <= 8
+    assert np.max(np.abs(got - want)[lo] / scale[lo]) < 1e-13
+    assert np.max(np.abs(got - want) / scale) < 5e-13
+    norm = np.sqrt((2 * ls + 1) / (4 * np.pi) * np.exp(gammaln(ls - ms + 1) - gammaln(ls + ms + 1)))
+    got_s = _shim_call(L.shim_legendre_sphPlm, [ls, ms], [x])
+    assert np.max(np.abs(got_s - norm * want)[lo]) < 1e-13       # |Y_lm| <= sqrt((2l+1)/4pi) ~ O(1)
+    assert np.max(np.abs(got_s - norm * want)) < 5e-13
+    try:                                                             # scipy >= 1.15: the spherical harmonic itself
+        from scipy.special import sph_harm_y
+        th = np.arccos(np.clip(x, -1, 1))
+        y = sph_harm_y(ls, ms, th, np.zeros_like(th)).real
+        assert np.max(np.abs(got_s - y)) < 5e-13
+    except ImportError:
+        pass
+    # Gamma at the integer arguments of bfe_helper.cpp:72-74 / multipole.cpp:106-111
+    from scipy.special import gamma
+    k = np.arange(1.0, 35.0)
+    assert np.max(np.abs(_shim_call(L.shim_gamma, [], [k]) / gamma(k) - 1)) < 1e-14
+
+
+def test_multipole_closed_form_lmax5(ref):
+    """MultipolePotential through the reference's own multipole.cpp (compiled against the shim) equals the closed
+    form written with scipy: Phi = (G M / r_s) sum_lm s^-(l+1) [s^l inner] Y_lm(cos theta) (S_lm cos m phi +
+    T_lm sin m phi), s = r / r_s (multipole.cpp:50-66,182-224); gradient against 4th-order differences of that form."""
+    from scipy.special import lpmv, gammaln
+    rng = np.random.default_rng(55)
+    for inner in (False, True):
+        lmax = 5
+        kw = {}
+        for l in range(lmax + 1):
+            for m in range(l + 1):
+                kw[f"S{l}{m}"] = rng.normal()
+                if m:
+                    kw[f"T{l}{m}"] = rng.normal()
+        pot = gb.MultipolePotential(lmax=lmax, m=3e10, r_s=7.0, inner=inner, **kw)
+
+        def phi(q):
+            r = np.sqrt((q * q).sum(0)); s = r / 7.0
+            X = q[2] / r; az = np.arctan2(q[1], q[0])
+            out = np.zeros_like(r)
+            for l in range(lmax + 1):
+                for m in range(l + 1):
+                    nlm = np.sqrt((2 * l + 1) / (4 * np.pi) * np.exp(gammaln(l - m + 1) - gammaln(l + m + 1)))
+                    rad = s ** l if inner else s ** (-(l + 1.0))
+                    out += rad * nlm * lpmv(m, l, X) * (kw[f"S{l}{m}"] * np.cos(m * az) + kw.get(f"T{l}{m}", 0.0) * np.sin(m * az))
+            return pot.G * 3e10 / 7.0 * out
+
+        q = rng.normal(0, 6.0, (3, 400))
+        q = q[:, np.sqrt((q * q).sum(0)) > 1.0]
+        e = ref.energy(pot, q)
+        assert np.max(np.abs(e - phi(q)) / np.abs(phi(q)).max()) < 1e-13
+        g = ref.gradient(pot, q)
+        h = 1e-3
+        gfd = np.empty_like(g)
+        for k in range(3):
+            d = np.zeros((3, 1)); d[k] = h
+            gfd[k] = (-phi(q + 2 * d) + 8 * phi(q + d) - 8 * phi(q - d) + phi(q - 2 * d)) / (12 * h)
+        assert np.max(np.abs(g - gfd)) / np.abs(g).max() < 1e-8
