@@ -24,6 +24,12 @@ POT_STONE, POT_BURKERT, POT_SATOH, POT_KUZMIN, POT_LOGARITHMIC, POT_LEESUTO, POT
 FRAME_STATIC, FRAME_ROTATING_3D = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 
+# enum gb_extrema_row: rows of the (EXT_NSTAT, N) statistics array of gb_orbit_extrema / gb_integrate_extrema
+EXT_ROWS = ("n_peri", "peri_mean", "peri_min", "peri_max", "peri_t_first", "peri_t_last",
+            "n_apo", "apo_mean", "apo_min", "apo_max", "apo_t_first", "apo_t_last",
+            "E_first", "E_last", "dE_max", "abs_z_max")
+EXT_NSTAT = 16
+
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
 
@@ -100,6 +106,10 @@ SIGNATURES = {
     "gb_lyapunov_max": (C.c_int, [P(gb_potential), P(gb_frame), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
                                   C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_long, C.c_void_p,
                                   C.c_void_p, C.c_void_p, P(gb_launch)]),
+    "gb_orbit_extrema": (C.c_int, [P(gb_potential), P(gb_frame), C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int,
+                                   C.c_void_p, P(gb_launch)]),
+    "gb_integrate_extrema": (C.c_int, [P(gb_potential), P(gb_frame), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
+                                       C.c_int, C.c_void_p, C.c_void_p, P(gb_launch)]),
     "gb_last_error": (C.c_char_p, []),
     "gb_device_count": (C.c_int, []),
     "gb_launch_count": (C.c_long, []),

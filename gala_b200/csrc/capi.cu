@@ -864,6 +864,70 @@ int gb_ruth4(const gb_potential* pot, const gb_frame* fr, const double* w0, size
     return fixed_step_common(true, pot, fr, w0, N, t, ntimes, save_all, w_out, opt);
 }
 
+// ---- trajectory reductions (csrc/extrema.cuh) ------------------------------------------------
+int gb_orbit_extrema(const gb_potential* pot, const gb_frame* fr, const double* w, const double* t, int ntimes,
+                     size_t N, int with_energy, double* stats, const gb_launch* opt) {
+    Ctx c; RET_IF(open_ctx(opt, c));
+    if (ntimes < 1 || !t || (N && (!w || !stats))) return fail(-12, "null data pointer / empty time grid");
+    DevFrame F; RET_IF(resolve_frame(fr, F));
+    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    const int block = pick_block(c, N);
+    const void *dw, *dtg;
+    RET_IF(stage_in(c, 0, w, 6 * (size_t)ntimes * N * sizeof(double), &dw));
+    RET_IF(stage_in(c, 2, t, (size_t)ntimes * sizeof(double), &dtg));
+    void* dst; RET_IF(stage_out_alloc(c, 1, stats, GB_EXT_NSTAT * N * sizeof(double), &dst));
+    cudaError_t e = KCALL(c, trajectory_extrema, r.P, F, (const double*)dw, (const double*)dtg, ntimes, N, with_energy,
+                          (double*)dst, block, c.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "trajectory_extrema launch");
+    if (N) g_launches++;
+    RET_IF(stage_out_copy(c, stats, dst, GB_EXT_NSTAT * N * sizeof(double)));
+    return finish(c);
+}
+
+static int integrate_extrema_impl(const gb_potential* pot, const gb_frame* fr, int scheme, const double* w0, size_t N,
+                                  size_t pitch, const double* t, int ntimes, int with_energy, double* w_final,
+                                  double* stats, const gb_launch* opt) {
+    Ctx c; RET_IF(open_ctx(opt, c));
+    if (scheme != 0 && scheme != 1) return fail(-12, "scheme must be 0 (leapfrog) or 1 (ruth4)");
+    if (ntimes < 2) return fail(-12, "the time grid needs at least 2 entries");
+    if (!t || (N && (!w0 || !stats))) return fail(-12, "null data pointer");
+    DevFrame F; RET_IF(resolve_frame(fr, F));
+    if (scheme == 0 && F.type != GB_FRAME_STATIC)
+        return fail(-13, "Leapfrog integration is currently only supported for StaticFrame");
+    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    const double dt = c.host ? t[1] - t[0] : 0.0;
+    const int block = pick_block(c, N);
+    double cs[4], ds[4];
+    ruth4_coeffs(cs, ds);
+    const void *dw0, *dtg;
+    RET_IF(stage_in_2d(c, 0, w0, 6, N, pitch, &dw0));
+    RET_IF(stage_in(c, 2, t, (size_t)ntimes * sizeof(double), &dtg));
+    void *dst, *dfin = nullptr;
+    RET_IF(stage_out_alloc(c, 1, stats, GB_EXT_NSTAT * N * sizeof(double), &dst));
+    if (w_final) RET_IF(stage_out_alloc(c, 4, w_final, 6 * N * sizeof(double), &dfin));
+    cudaError_t e = KCALL(c, integrate_extrema, r.P, F, scheme, cs, ds, (const double*)dw0, N, (const double*)dtg, ntimes,
+                          dt, c.host ? 0 : 1, with_energy, (double*)dfin, (double*)dst, block, c.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "integrate_extrema launch");
+    if (N) g_launches++;
+    RET_IF(stage_out_copy_2d(c, stats, dst, GB_EXT_NSTAT, N, pitch));
+    if (w_final) RET_IF(stage_out_copy_2d(c, w_final, dfin, 6, N, pitch));
+    return finish(c);
+}
+
+int gb_integrate_extrema(const gb_potential* pot, const gb_frame* fr, int scheme, const double* w0, size_t N,
+                         const double* t, int ntimes, int with_energy, double* w_final, double* stats,
+                         const gb_launch* opt) {
+    if (!multi_device(opt))
+        return integrate_extrema_impl(pot, fr, scheme, w0, N, N, t, ntimes, with_energy, w_final, stats, opt);
+    if (ntimes < 2) return fail(-12, "the time grid needs at least 2 entries");
+    if (!t || (N && (!w0 || !stats))) return fail(-12, "null data pointer");
+    return run_on_devices(opt, [=](const gb_launch* sub, int k, int nd) {
+        size_t lo, n; slice_of(N, k, nd, &lo, &n);
+        return integrate_extrema_impl(pot, fr, scheme, w0 + lo, n, N, t, ntimes, with_energy,
+                                      w_final ? w_final + lo : nullptr, stats + lo, sub);
+    });
+}
+
 // dop853() front-end defaults (dopri/dop853.cpp:673-788)
 static int dop853_defaults(Dop853Args& a, double atol, double rtol, long nmax, double dt_max, long nstiff,
                            double uround, double h0) {

@@ -31,6 +31,9 @@ namespace GB_NS {
 #if GB_PART == 6
 #include "lyapunov.cuh"
 #endif
+#if GB_PART == 7
+#include "extrema.cuh"
+#endif
 
 #if GB_PART == 1
 // ------------------------------------------------------------------------------------------------
@@ -502,5 +505,31 @@ cudaError_t nbody_dop853(const DevPot& P, const DevBodies& B, const Dop853Args& 
 }
 #endif
 #endif  // GB_PART == 5 || 6
+
+#if GB_PART == 7
+cudaError_t trajectory_extrema(const DevPot& P, const DevFrame& F, const double* w, const double* t, int ntimes, size_t N,
+                               int with_energy, double* stats, int block, cudaStream_t s) {
+    if (N == 0) return cudaSuccess;
+    if (with_energy) {
+        GB_SIG_SWITCH(P.sig, (k_trajectory_extrema<C, true><<<nblocks(N, block), block, 0, s>>>(P, F, w, t, ntimes, N, stats)));
+    } else {
+        GB_SIG_SWITCH(P.sig, (k_trajectory_extrema<C, false><<<nblocks(N, block), block, 0, s>>>(P, F, w, t, ntimes, N, stats)));
+    }
+    return cudaGetLastError();
+}
+cudaError_t integrate_extrema(const DevPot& P, const DevFrame& F, int scheme, const double* cs, const double* ds,
+                              const double* w0, size_t N, const double* t, int ntimes, double dt, int dt_from_t,
+                              int with_energy, double* wfin, double* stats, int block, cudaStream_t s) {
+    if (N == 0) return cudaSuccess;
+    Ruth4CoefE K;
+    for (int k = 0; k < 4; k++) { K.c[k] = cs[k]; K.d[k] = ds[k]; }
+#define GB_IE(SCH, EN) GB_SIG_SWITCH(P.sig, (k_integrate_extrema<C, SCH, EN><<<nblocks(N, block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads), block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads, 0, s>>>(P, F, K, w0, N, t, ntimes, dt, dt_from_t, wfin, stats)))
+    const int sch = scheme == 0 ? 0 : (F.type == GB_FRAME_STATIC ? 1 : 2);
+    if (with_energy) { if (sch == 0) { GB_IE(0, true); } else if (sch == 1) { GB_IE(1, true); } else { GB_IE(2, true); } }
+    else             { if (sch == 0) { GB_IE(0, false); } else if (sch == 1) { GB_IE(1, false); } else { GB_IE(2, false); } }
+#undef GB_IE
+    return cudaGetLastError();
+}
+#endif  // GB_PART == 7
 
 }  // namespace GB_NS

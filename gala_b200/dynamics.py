@@ -84,6 +84,33 @@ class Orbit(PhaseSpacePosition):
         return Orbit(pos=self.pos[(slice(None),) + key], vel=self.vel[(slice(None),) + key], t=t,
                      hamiltonian=self.hamiltonian, frame=self.frame)
 
+    # -- pericentre / apocentre (dynamics/orbit.py:439-553), reduced on the GPU -------------------------------
+    def _extrema(self, kind, func, return_times, approximate):
+        from .integrate import orbit_extrema
+        if approximate:
+            raise NotImplementedError("approximate=True (no parabola refinement) is not part of the device reduction")
+        if self.hamiltonian is None or self.t is None:
+            raise ValueError("pericenter/apocenter need the orbit's hamiltonian and time grid")
+        if return_times and func is not None:
+            raise ValueError(f"Cannot return times if reducing {kind}centers using an input function. Pass `func=None` "
+                             "if you want to return all individual values and times.")
+        row = {np.mean: "mean", np.min: "min", np.max: "max", np.amin: "min", np.amax: "max"}.get(func)
+        if row is None:
+            raise NotImplementedError("the device reduction provides func=np.mean (default), np.min and np.max; for the "
+                                      "full list of extrema reduce the trajectory yourself")
+        w = self.w()
+        st = orbit_extrema(self.hamiltonian, w if w.ndim == 3 else w[:, :, None], self.t)
+        out = st[f"{kind}_{row}"]
+        return out[0] if w.ndim == 2 else out
+
+    def pericenter(self, return_times=False, func=np.mean, approximate=False):
+        """``Orbit.pericenter`` (``dynamics/orbit.py:439-493``) for ``func`` in (np.mean, np.min, np.max)."""
+        return self._extrema("peri", func, return_times, approximate)
+
+    def apocenter(self, return_times=False, func=np.mean, approximate=False):
+        """``Orbit.apocenter`` (``dynamics/orbit.py:495-553``) for ``func`` in (np.mean, np.min, np.max)."""
+        return self._extrema("apo", func, return_times, approximate)
+
     def energy(self, hamiltonian=None):
         """Hamiltonian value along the orbit, shape (ntimes[, norbits]) -- evaluated on the GPU."""
         H = hamiltonian or self.hamiltonian

@@ -1,5 +1,7 @@
 """Drop-in hook for a real gala installation (``gala`` is NOT importable in this image: astropy is
-absent; this module is exercised only through its duck-typed extractors).
+absent; this module is exercised through its duck-typed extractors and, for the patching
+itself, against a fake ``gala`` package tree with the reference's import structure,
+tests/test_host_logic_cpu.py::test_plugin_install_patches_the_names_gala_resolves).
 
 ``install()`` replaces the five Cython functions at the boundary with GPU-backed ones::
 
@@ -117,27 +119,54 @@ def _wrap_stream(fn):
     return inner
 
 
-def install():
-    """Swap gala's Cython boundary functions for the GPU-backed ones.  Raises ImportError if gala
-    itself cannot be imported."""
-    import gala.integrate.cyintegrators.leapfrog as lf
-    import gala.integrate.cyintegrators.ruth4 as r4
-    import gala.integrate.cyintegrators.dop853 as d8
-    import gala.potential.hamiltonian.chamiltonian as ch
-    lf.leapfrog_integrate_hamiltonian = _wrap(_integ.leapfrog_integrate_hamiltonian)
-    r4.ruth4_integrate_hamiltonian = _wrap(_integ.ruth4_integrate_hamiltonian)
-    d8.dop853_integrate_hamiltonian = _wrap(_integ.dop853_integrate_hamiltonian)
-    for name in ("leapfrog_integrate_hamiltonian", "ruth4_integrate_hamiltonian", "dop853_integrate_hamiltonian"):
-        if hasattr(ch, name):       # chamiltonian.pyx imports them lazily inside integrate_orbit
-            setattr(ch, name, _wrap(getattr(_integ, name)))
-    try:        # mock-stream boundary (dynamics/mockstream/mockstream.pyx:176-620)
-        import gala.dynamics.mockstream.mockstream as msx
-        import gala.dynamics.mockstream.mockstream_generator as msg
-        for name in ("mockstream_dop853", "mockstream_leapfrog", "mockstream_dop853_animate"):
-            w = _wrap_stream(getattr(_ms, name))
-            setattr(msx, name, w)
-            if hasattr(msg, name):
-                setattr(msg, name, w)
-    except ImportError:
-        pass
-    return True
+def _hook(installed, missing, modname, names, wrap):
+    """setattr(module, name, wrapped) for every name in ``names`` of an importable module."""
+    import importlib
+    try:
+        mod = importlib.import_module(modname)
+    except ImportError as e:
+        missing.append(f"{modname} ({e})")
+        return
+    for name, fn in names.items():
+        setattr(mod, name, wrap(fn))
+        installed.append(f"{modname}.{name}")
+
+
+def install(strict=True):
+    """Swap gala's Cython boundary functions for the GPU-backed ones.  Returns the list of hooks installed
+    (``"module.function"``).  Raises ImportError if gala itself cannot be imported, and -- with ``strict`` --
+    RuntimeError if a module the hot path resolves its functions through could not be patched.
+
+    Where the reference LOOKS THE NAMES UP decides what has to be patched:
+      * ``Hamiltonian.integrate_orbit`` does ``from ...integrate.cyintegrators import X`` at call time
+        (potential/hamiltonian/chamiltonian.pyx:324-336): that resolves ``X`` as an attribute of the PACKAGE
+        ``gala.integrate.cyintegrators``, whose ``__init__`` bound the Cython functions at import
+        (integrate/cyintegrators/__init__.py:1-3).  So the package attribute is the one that counts; the
+        submodules ``.leapfrog`` / ``.ruth4`` / ``.dop853`` are patched too for code that imports from them.
+      * ``MockStreamGenerator.run`` uses the names ``mockstream_generator`` imported from ``._mockstream`` at
+        import time (dynamics/mockstream/mockstream_generator.py:8-12; the extension module is
+        ``gala.dynamics.mockstream._mockstream``, setup.py:238-255), so both that module and the generator's own
+        namespace are patched, and ``gala.dynamics.mockstream`` re-exports ``mockstream_dop853`` (``__init__.py:1``)."""
+    import gala  # noqa: F401  (ImportError here = no gala to patch)
+    installed, missing = [], []
+    integ = {"leapfrog_integrate_hamiltonian": _integ.leapfrog_integrate_hamiltonian,
+             "ruth4_integrate_hamiltonian": _integ.ruth4_integrate_hamiltonian,
+             "dop853_integrate_hamiltonian": _integ.dop853_integrate_hamiltonian}
+    _hook(installed, missing, "gala.integrate.cyintegrators", integ, _wrap)
+    for sub, name in (("leapfrog", "leapfrog_integrate_hamiltonian"), ("ruth4", "ruth4_integrate_hamiltonian"),
+                      ("dop853", "dop853_integrate_hamiltonian")):
+        _hook(installed, missing, f"gala.integrate.cyintegrators.{sub}", {name: integ[name]}, _wrap)
+    stream = {n: getattr(_ms, n) for n in ("mockstream_dop853", "mockstream_leapfrog", "mockstream_dop853_animate")}
+    _hook(installed, missing, "gala.dynamics.mockstream._mockstream", stream, _wrap_stream)
+    _hook(installed, missing, "gala.dynamics.mockstream.mockstream_generator", stream, _wrap_stream)
+    _hook(installed, missing, "gala.dynamics.mockstream", {"mockstream_dop853": stream["mockstream_dop853"]}, _wrap_stream)
+    required = ("gala.integrate.cyintegrators.leapfrog_integrate_hamiltonian",
+                "gala.dynamics.mockstream.mockstream_generator.mockstream_dop853")
+    lacking = [r for r in required if r not in installed]
+    if missing:
+        import warnings
+        warnings.warn("gala_b200.gala_plugin.install(): not patched: " + "; ".join(missing), RuntimeWarning)
+    if strict and lacking:
+        raise RuntimeError("gala_b200.gala_plugin.install(): the hot path would still run gala's own code: "
+                           + ", ".join(lacking) + " could not be patched")
+    return installed

@@ -20,7 +20,7 @@ from .units import strip
 
 __all__ = ["pinned_empty", "parse_time_specification", "LeapfrogIntegrator", "Ruth4Integrator", "DOPRI853Integrator",
            "get_integrator", "leapfrog_integrate_hamiltonian", "ruth4_integrate_hamiltonian",
-           "dop853_integrate_hamiltonian"]
+           "dop853_integrate_hamiltonian", "integrate_extrema", "orbit_extrema"]
 
 
 def parse_time_specification(units=None, dt=None, n_steps=None, t1=None, t2=None, t=None):
@@ -206,6 +206,80 @@ def dop853_integrate_hamiltonian(hamiltonian, w0, t, atol=1e-10, rtol=1e-10, nma
         stats["status"] = status
         return res + (stats,)
     return res
+
+
+# ---- trajectory reductions on the device (include/gala_b200.h gb_*_extrema) ---------------
+def _stats_dict(stats):
+    return {name: stats[k] for k, name in enumerate(_abi.EXT_ROWS)}
+
+
+def integrate_extrema(hamiltonian, w0, t, Integrator="leapfrog", with_energy=False, return_final=False):
+    """Integrate ``w0`` (6,N) over the grid ``t`` with Leapfrog or Ruth4 and return, per orbit, the pericentre /
+    apocentre statistics of ``Orbit.pericenter`` / ``Orbit.apocenter`` (``dynamics/orbit.py:391-553``: local extrema
+    of r(t_j) refined by a parabola; count, mean, min, max, first and last time of each kind), ``max |z|`` and, with
+    ``with_energy``, E(t[0]), E(t[-1]) and max |E - E(t[0])| -- computed inside the integration kernel, so no
+    (6, ntimes, N) trajectory is stored or copied.  Returns a dict of (N,) arrays (keys ``_abi.EXT_ROWS``), plus the
+    final state (6,N) under ``"w_final"`` when asked for."""
+    _check_c_enabled(hamiltonian)
+    cls = get_integrator(Integrator)
+    if cls not in (LeapfrogIntegrator, Ruth4Integrator):
+        raise ValueError("integrate_extrema supports the fixed-step integrators (leapfrog, ruth4); for DOPRI853 reduce "
+                         "its dense output with orbit_extrema")
+    if cls is LeapfrogIntegrator and not isinstance(hamiltonian.frame, StaticFrame):
+        raise TypeError("Leapfrog integration is currently only supported for StaticFrame, "
+                        f"not {hamiltonian.frame.__class__.__name__}")
+    w = _prep_w0(w0)
+    th, tb = _prep_t(t, w)
+    N, ntimes = w.arr.shape[1], th.size
+    stats = _alloc(w, (_abi.EXT_NSTAT, N))
+    wfin = _alloc(w, (6, N)) if return_final else None
+    opt = _opts(w, hamiltonian)
+    fr = hamiltonian.frame.spec()
+    _abi.check(_abi.lib().gb_integrate_extrema(hamiltonian.potential.spec().ptr(), C.byref(fr),
+                                               0 if cls is LeapfrogIntegrator else 1, w.ptr, N, tb.ptr, ntimes,
+                                               int(bool(with_energy)), None if wfin is None else _abi.Buf(wfin).ptr,
+                                               _abi.Buf(stats).ptr, C.byref(opt)))
+    out = _stats_dict(stats)
+    if return_final:
+        out["w_final"] = wfin
+    return out
+
+
+def orbit_extrema(hamiltonian, w, t, with_energy=False):
+    """The same statistics for a trajectory that already exists: ``w`` (6, ntimes, N) host array or device tensor
+    (e.g. the dense output of ``dop853_integrate_hamiltonian`` left on the device)."""
+    _check_c_enabled(hamiltonian)
+    if _abi._is_torch_cuda(w):
+        import torch
+        if w.dtype != torch.float64 or w.ndim != 3 or w.shape[0] != 6:
+            raise ValueError("w must be a float64 tensor of shape (6, ntimes, N)")
+        buf = _abi.Buf(w.contiguous())
+    else:
+        a = np.ascontiguousarray(w, dtype=np.float64)
+        if a.ndim == 2:
+            a = a[:, :, None]
+        if a.ndim != 3 or a.shape[0] != 6:
+            raise ValueError(f"w must have shape (6, ntimes[, N]), got {a.shape}")
+        buf = _abi.Buf(np.ascontiguousarray(a))
+    th, tb = _prep_t(t, buf)
+    ntimes, N = buf.arr.shape[1], buf.arr.shape[2]
+    if th.size != ntimes:
+        raise ValueError("t must have one entry per saved sample")
+    stats = _alloc(buf, (_abi.EXT_NSTAT, N))
+    opt = _abi.launch_opts(buf.device, bool(getattr(hamiltonian, "strict_math", False) or hamiltonian.potential.strict_math),
+                           *( _stream_dev(buf) ))
+    fr = hamiltonian.frame.spec()
+    _abi.check(_abi.lib().gb_orbit_extrema(hamiltonian.potential.spec().ptr(), C.byref(fr), buf.ptr, tb.ptr, ntimes, N,
+                                           int(bool(with_energy)), _abi.Buf(stats).ptr, C.byref(opt)))
+    return _stats_dict(stats)
+
+
+def _stream_dev(buf):
+    """(stream, block, device) positional tail of launch_opts for a host / device buffer."""
+    if buf.device:
+        import torch
+        return torch.cuda.current_stream(buf.arr.device).cuda_stream, 0, buf.arr.device.index
+    return None, 0, -1
 
 
 # ---- integrator classes (names for Hamiltonian.integrate_orbit dispatch; integrate/__init__.py) ---

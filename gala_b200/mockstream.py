@@ -12,6 +12,7 @@ reference's order (``df.pyx:393-454``), so sampling is bit-reproducible; the GPU
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -25,6 +26,18 @@ from .units import strip
 
 __all__ = ["BaseStreamDF", "FardalStreamDF", "StreaklineStreamDF", "LagrangeCloudStreamDF", "ChenStreamDF",
            "MockStreamGenerator", "DirectNBody", "mockstream_dop853", "mockstream_leapfrog", "mockstream_dop853_animate"]
+
+
+_SIDE = {}
+
+
+def _side_stream(dev, k):
+    """Per-device pool of non-blocking torch streams for the stream pipeline (created once)."""
+    import torch
+    key = (dev.index, k)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
 
 
 def _opts(H, shard=False):
@@ -595,6 +608,183 @@ class MockStreamGenerator:
                            external_potential=self.hamiltonian.potential, frame=self.hamiltonian.frame,
                            units=self.hamiltonian.units)
 
+    # ---- the test-particle stream as one device-resident pipeline ------------------------------------------
+    def _run_pipelined(self, prog_w0, prog_mass, release_every, n_particles, Integrator, Integrator_kwargs, t):
+        """``run`` for the common case (no massive bodies, no snapshots), same numbers, different schedule.
+        The step-by-step form below costs host RNG (the reference's stream, 4 normals per Fardal particle) + two
+        single-lane progenitor orbits + release + the particle kernel one after the other (17.7 ms for C3,
+        profiles/bench_r1_final_c3.json).  Here everything stays on the device and overlaps:
+          * a worker thread draws the deviates chunk by chunk (numpy releases the GIL) while the progenitor
+            orbit runs; consecutive draws from the caller's RandomState / Generator are the same bit stream as
+            one big draw;
+          * particle rows are in release order = longest integration first, so chunk 0 (the earliest releases)
+            starts integrating while the deviates of the later chunks are still being drawn; every chunk has its
+            own stream (each is a fraction of one wave), the kernels overlap;
+          * the progenitor's second integration (the reference re-integrates the bodies forward from the
+            earliest state, mockstream.pyx:528-548 / :247-255 -- it decides the returned progenitor state) runs on a
+            side stream next to the particle kernels;
+          * one D2H of the (Np, 6) result at the end.
+        Returns (stream rows (Np,6) host, prog row (1,6) host, release_time, lead_trail)."""
+        import queue
+        import threading
+        import torch
+        H = self.hamiltonian
+        dev = torch.device("cuda", torch.cuda.current_device())
+        kw = {k: Integrator_kwargs[k] for k in ("atol", "rtol", "nmax", "dt_max", "err_if_fail") if k in Integrator_kwargs}
+        lf = Integrator is LeapfrogIntegrator
+        pw = prog_w0.w() if isinstance(prog_w0, PhaseSpacePosition) else np.asarray(prog_w0, dtype=np.float64)
+        pw = np.ascontiguousarray(np.asarray(pw, dtype=np.float64).reshape(6, 1))
+        backward = t[1] < t[0]
+        orbit_t = np.ascontiguousarray(t[::-1] if backward else t, dtype=np.float64)
+        ntimes = orbit_t.size
+        # ---- host bookkeeping that needs no GPU result (BaseStreamDF.sample / run, same code paths) ----------
+        prog_m = np.squeeze(np.asarray(strip(prog_mass), dtype=np.float64))
+        if prog_m.shape == ():
+            prog_m = np.full(ntimes, float(prog_m))
+        if np.iterable(n_particles):
+            npart = np.array(n_particles).astype("i4")
+            if len(npart) != ntimes:
+                raise ValueError("If passing in an array n_particles, its shape must match the number of "
+                                 "timesteps in the progenitor orbit.")
+        else:
+            npart = np.zeros(ntimes, dtype="i4")
+            npart[::release_every] = int(n_particles)
+        prog_idx, sign = self.df._plan(prog_m, npart)
+        Np = prog_idx.size
+        if Np == 0:
+            raise ValueError("no stream particles to integrate")
+        release_time = orbit_t[prog_idx]
+        lead_trail = np.where(sign > 0, "t", "l").astype("U1")
+        unq_t1s, nstream = np.unique(release_time, return_counts=True)
+        all_nstream = _scatter_isclose(orbit_t, unq_t1s, nstream)
+        nstream_idx = np.where(all_nstream != 0)[0]
+        if 0 not in nstream_idx:
+            nstream_idx = np.insert(nstream_idx, 0, 0)
+            unq_t1s = np.insert(unq_t1s, 0, orbit_t[0])
+        ns = all_nstream[nstream_idx]
+        if int(ns.sum()) != Np:
+            raise ValueError("stream_w0 must have shape (sum(nstream), 6)")
+        t1_rows = np.repeat(unq_t1s, ns)                  # what mockstream_* pair with the rows (== release_time)
+        groups = np.nonzero(ns)[0]
+        last = int(groups[-1])
+        tfinal = float(orbit_t[-1])
+        # fixed step: dt of the full grid (mockstream.pyx:500); adaptive: initial step = spacing of the release-time
+        # grid handed to mockstream_dop853 (time[1] - time[0], mockstream.pyx:228)
+        tgrid = orbit_t if lf else np.ascontiguousarray(orbit_t[nstream_idx])
+        dt0 = float(tgrid[1] - tgrid[0]) if tgrid.size > 1 else float(orbit_t[1] - orbit_t[0])
+        # ---- deviates: drawn on a worker thread, chunk by chunk, in the reference's order -------------------
+        nchunk = int(os.environ.get("GB_STREAM_CHUNKS", "8"))
+        nchunk = max(1, min(nchunk, (Np + 4095) // 4096))
+        bounds = [(Np * c) // nchunk for c in range(nchunk + 1)]
+        has_draws = type(self.df)._draws is not BaseStreamDF._draws
+        q = queue.Queue()
+
+        def draw_all():
+            try:
+                for c in range(nchunk):
+                    n = bounds[c + 1] - bounds[c]
+                    q.put(self.df._draws(n, H.potential) if has_draws else None)
+            except BaseException as e:           # surfaces on the main thread
+                q.put(e)
+        worker = threading.Thread(target=draw_all, daemon=True)
+        worker.start()
+        # ---- progenitor orbit (device-resident, asynchronous for the fixed-step integrator) -------------------
+        w0_dev = torch.as_tensor(pw, device=dev)
+        if lf:
+            _, traj = leapfrog_integrate_hamiltonian(H, w0_dev, t, save_all=1)
+        else:
+            _, traj = dop853_integrate_hamiltonian(H, w0_dev, t, nstiff=-1, save_all=1, **kw)
+        traj = traj[:, :, 0]                                                  # (6, ntimes)
+        if backward:
+            traj = torch.flip(traj, dims=[1])                                # earliest state first (run :237-250)
+        prog_rows = traj.t().contiguous()                                     # (ntimes, 6) = hstack([prog_x, prog_v])
+        up = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+        d_t, d_m, d_idx, d_sign, d_t1 = up(orbit_t), up(prog_m), up(prog_idx), up(sign), up(t1_rows)
+        rows0 = torch.empty((Np, 6), dtype=torch.float64, device=dev)
+        rows1 = torch.empty((Np + 1, 6), dtype=torch.float64, device=dev)    # + the progenitor row (nbodies = 1)
+        status = torch.empty((Np + 1,), dtype=torch.int32, device=dev)
+        main = torch.cuda.current_stream(dev)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        # ---- second progenitor integration on a side stream (it only feeds the returned progenitor state) -----
+        side = _side_stream(dev, 0)
+        side.wait_event(ready)
+        lib, pot = _abi.lib(), H.potential.spec().ptr()
+        fr = H.frame.spec()
+        strict = bool(getattr(H, "strict_math", False) or H.potential.strict_math)
+        with torch.cuda.stream(side):
+            nb0 = prog_rows[0].reshape(6, 1).contiguous()
+            if lf:
+                _, full = leapfrog_integrate_hamiltonian(H, nb0, orbit_t, save_all=1)
+                idx = int((unq_t1s[last] - orbit_t[0]) / (orbit_t[1] - orbit_t[0]) + 0.5)          # mockstream.pyx:548
+                body0 = full[:, idx, 0]
+            else:
+                akw = {k: v for k, v in Integrator_kwargs.items() if k in ("atol", "rtol", "nmax", "dt_max", "nstiff", "err_if_fail")}
+                akw.setdefault("nstiff", -1)
+                _, full = dop853_integrate_hamiltonian(H, nb0, np.ascontiguousarray(orbit_t[nstream_idx]), save_all=1, **akw)
+                body0 = full[:, last, 0]
+            prow = body0.reshape(1, 6).contiguous()
+            pt1 = torch.full((1,), float(unq_t1s[last]), dtype=torch.float64, device=dev)
+            self._mock_integrate(lib, pot, fr, lf, prow, pt1, 1, tfinal, dt0, Integrator_kwargs, rows1[Np:], status[Np:],
+                                 strict, side, dev)
+        done = [torch.cuda.Event()]
+        done[0].record(side)
+        # ---- chunks: deviates -> release -> integrate, each on its own stream ----------------------------------
+        for c in range(nchunk):
+            a, b = bounds[c], bounds[c + 1]
+            d = q.get()
+            if isinstance(d, BaseException):
+                raise d
+            st = _side_stream(dev, 1 + c % 4)
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                ncols = 0
+                d_dr = None
+                if d is not None:
+                    ncols = d.shape[1]
+                    d_dr = torch.as_tensor(d, device=dev)
+                opt = _abi.launch_opts(True, strict, st.cuda_stream, device=dev.index)
+                _abi.check(lib.gb_stream_release(pot, float(H.potential.G), prog_rows.data_ptr(), d_t.data_ptr(), d_m.data_ptr(),
+                                                 ntimes, d_idx[a:b].data_ptr(), d_sign[a:b].data_ptr(),
+                                                 None if d_dr is None else d_dr.data_ptr(), ncols, b - a, int(self.df._kind),
+                                                 int(self.df._flags), rows0[a:b].data_ptr(), C.byref(opt)))
+                self._mock_integrate(lib, pot, fr, lf, rows0[a:b], d_t1[a:b], b - a, tfinal, dt0, Integrator_kwargs,
+                                     rows1[a:b], status[a:b], strict, st, dev)
+                if d_dr is not None:
+                    d_dr.record_stream(st)
+            ev = torch.cuda.Event()
+            ev.record(st)
+            done.append(ev)
+        for ev in done:
+            main.wait_event(ev)
+        out = torch.empty((Np + 1, 6), dtype=torch.float64).pin_memory() if Np > 65536 else None
+        if out is not None:
+            out.copy_(rows1, non_blocking=True)
+            main.synchronize()
+            res = out.numpy()
+        else:
+            res = rows1.cpu().numpy()
+        worker.join()
+        if not lf and kw.get("err_if_fail", 1):
+            worst = int(status.min().item())
+            if worst < 0:
+                raise RuntimeError(f"Integration failed with code {worst}")
+        return res[:Np], res[Np:], release_time, lead_trail
+
+    @staticmethod
+    def _mock_integrate(lib, pot, fr, lf, rows, t1, n, tfinal, dt0, Integrator_kwargs, out, status, strict, st, dev):
+        opt = _abi.launch_opts(True, strict, st.cuda_stream, device=dev.index)
+        if lf:
+            _abi.check(lib.gb_mockstream_leapfrog(pot, rows.data_ptr(), t1.data_ptr(), n, float(tfinal),
+                                                  dt0, out.data_ptr(), C.byref(opt)))
+            return
+        kw = Integrator_kwargs
+        rc = lib.gb_mockstream_dop853(pot, C.byref(fr), rows.data_ptr(), t1.data_ptr(), n, float(tfinal),
+                                      dt0, float(kw.get("atol", 1e-10)), float(kw.get("rtol", 1e-10)),
+                                      int(kw.get("nmax", 0)), out.data_ptr(), status.data_ptr(), C.byref(opt))
+        if rc not in (-1, -2, -3, -4):          # per-particle failures are reported through `status`
+            _abi.check(rc)
+
     def run(self, prog_w0, prog_mass, nbody=None, release_every=1, n_particles=1, output_every=None,
             output_filename=None, check_filesize=True, overwrite=False, progress=False, Integrator=None,
             Integrator_kwargs=None, **time_spec):
@@ -603,6 +793,15 @@ class MockStreamGenerator:
         Integrator = get_integrator(Integrator or DOPRI853Integrator)
         units = self.hamiltonian.units
         t = parse_time_specification(units, **time_spec)
+        if (nbody is None and not self.self_gravity and output_every is None and output_filename is None
+                and Integrator in (LeapfrogIntegrator, DOPRI853Integrator) and isinstance(self.df, BaseStreamDF)
+                and isinstance(self.hamiltonian.frame, StaticFrame) and len(t) > 1 and _abi.get_devices() is None
+                and not os.environ.get("GB_NO_STREAM_PIPELINE")):
+            rows, prow, release_time, lead_trail = self._run_pipelined(prog_w0, prog_mass, release_every, n_particles,
+                                                                       Integrator, Integrator_kwargs, t)
+            stream = MockStream(pos=rows[:, :3].T, vel=rows[:, 3:].T, release_time=release_time, lead_trail=lead_trail,
+                                frame=self.hamiltonian.frame)
+            return stream, PhaseSpacePosition(pos=prow[:, :3].T, vel=prow[:, 3:].T, frame=self.hamiltonian.frame)
         prog_nbody = self._get_nbody(prog_w0, nbody)
         nbody_orbits = prog_nbody.integrate_orbit(t=t, Integrator=Integrator, Integrator_kwargs=Integrator_kwargs)
         if t[1] < t[0]:

@@ -298,6 +298,30 @@ int gb_lyapunov_max(const gb_potential* pot, const gb_frame* fr,
                     double atol, double rtol, long nmax,
                     double* LEs_raw, double* traj, int32_t* status, const gb_launch* opt);
 
+/* ---- trajectory reductions on the device -----------------------------------
+ * Orbit.pericenter / Orbit.apocenter (dynamics/orbit.py:391-553) and the energy drift without moving a
+ * (6, ntimes, N) trajectory over PCIe.  Per orbit, on the samples r_j = |q(t_j)| of the caller's grid: interior
+ * samples strictly above (below) both neighbours are apocentres (pericentres) -- scipy.signal.argrelmax as called at
+ * orbit.py:402-403 -- each refined to the vertex of the parabola through (t, r) at j-1, j, j+1 (orbit.py:413-422).
+ * stats is (GB_EXT_NSTAT, N), rows as enumerated below; means / minima / maxima are NaN for an orbit without such an
+ * extremum (np.mean of an empty array).  with_energy != 0 also evaluates the Hamiltonian (potential + frame energy)
+ * at every sample: E(t[0]), E(t[-1]) and max_j |E_j - E(t[0])|. */
+enum gb_extrema_row {
+    GB_EXT_N_PERI = 0, GB_EXT_PERI_MEAN, GB_EXT_PERI_MIN, GB_EXT_PERI_MAX, GB_EXT_PERI_T_FIRST, GB_EXT_PERI_T_LAST,
+    GB_EXT_N_APO = 6,  GB_EXT_APO_MEAN,  GB_EXT_APO_MIN,  GB_EXT_APO_MAX,  GB_EXT_APO_T_FIRST,  GB_EXT_APO_T_LAST,
+    GB_EXT_E_FIRST = 12, GB_EXT_E_LAST, GB_EXT_DE_MAX, GB_EXT_ABS_Z_MAX,
+    GB_EXT_NSTAT = 16
+};
+/* reduce a trajectory that already exists: w is (6, ntimes, N) (e.g. the dense output of gb_dop853 left in device
+ * memory); a decreasing grid is walked backwards, like the reference reverses the orbit (orbit.py:486,546). */
+int gb_orbit_extrema(const gb_potential* pot, const gb_frame* fr, const double* w, const double* t, int ntimes,
+                     size_t N, int with_energy, double* stats /* (GB_EXT_NSTAT, N) */, const gb_launch* opt);
+/* integrate like gb_leapfrog (scheme 0) / gb_ruth4 (scheme 1; rotating frame with gb_ruth4's semantics) and reduce on
+ * the fly: nothing of size ntimes is written.  w_final (6, N) may be NULL.  Shards over gb_launch.devices. */
+int gb_integrate_extrema(const gb_potential* pot, const gb_frame* fr, int scheme, const double* w0, size_t N,
+                         const double* t, int ntimes, int with_energy, double* w_final,
+                         double* stats /* (GB_EXT_NSTAT, N) */, const gb_launch* opt);
+
 /* ---- misc ------------------------------------------------------------------------ */
 const char* gb_last_error(void);
 int  gb_device_count(void);

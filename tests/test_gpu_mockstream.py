@@ -194,3 +194,33 @@ def test_mockstream_animate_snapshots(ref, tmp_path):
     with pytest.raises(NotImplementedError):
         gen.run(PROG_W0, 2.5e4, dt=1.0, n_steps=4, n_particles=1, output_every=2, output_filename=str(fn),
                 Integrator="leapfrog", overwrite=True)
+
+
+@pytest.mark.parametrize("integ", ["leapfrog", "dopri853"])
+@pytest.mark.parametrize("case", ["backward_every_step", "forward_release_every_3", "streakline"])
+def test_pipelined_run_equals_stepwise_run(monkeypatch, integ, case):
+    """MockStreamGenerator.run's device-resident pipeline (deviates drawn chunk by chunk on a worker thread, chunks
+    integrated on their own streams, the progenitor's second integration on a side stream) returns the bits of the
+    step-by-step form (GB_NO_STREAM_PIPELINE=1), for both integrators, both time directions and release_every > 1."""
+    H = gb.Hamiltonian(gb.MilkyWayPotential2022())
+    prog = gb.PhaseSpacePosition(pos=[13.0, 0.0, 20.0], vel=np.array([0.0, 130.0, 50.0]) * gb.KMS_TO_KPC_MYR)
+
+    def run():
+        if case == "streakline":
+            df = gb.StreaklineStreamDF()
+        else:
+            df = gb.FardalStreamDF(gala_modified=True, random_state=np.random.RandomState(5))
+        gen = gb.MockStreamGenerator(df, H)
+        if case == "forward_release_every_3":
+            s, p = gen.run(prog, 2.5e4, dt=1.0, n_steps=900, n_particles=7, release_every=3, Integrator=integ)
+        else:
+            s, p = gen.run(prog, 2.5e4, dt=-1.0, n_steps=1200, n_particles=6, release_every=1, Integrator=integ)
+        return s.w(), p.w(), s.release_time, s.lead_trail
+
+    monkeypatch.setenv("GB_STREAM_CHUNKS", "5")
+    got = run()
+    monkeypatch.setenv("GB_NO_STREAM_PIPELINE", "1")
+    want = run()
+    assert got[0].shape == want[0].shape and got[0].shape[1] > 4096
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)

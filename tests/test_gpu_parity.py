@@ -575,3 +575,29 @@ def test_hessian_errors_and_shift(ref):
     Hd = POTS["mw2022"].hessian(torch.as_tensor(q, device="cuda"))
     assert tuple(Hd.shape) == (3, 3, 64)
     assert np.allclose(Hd.cpu().numpy(), POTS["mw2022"].hessian(q), rtol=0, atol=0)
+
+
+def test_softened_potentials_finite_at_origin(ref):
+    """the fast build's shared context forms 1/r = rsqrt(r^2), NaN at r = 0; no component of these
+    potentials reads it, so the generic loop must not let it into the sum.  At the origin (and, for a shifted
+    component, at its own origin) fast == strict == the reference's finite value."""
+    cases = {
+        "plummer": gb.PlummerPotential(m=1e9, b=0.3),
+        "miyamoto": gb.MiyamotoNagaiPotential(m=5e10, a=3.0, b=0.3),
+        "isochrone": gb.IsochronePotential(m=1e10, b=1.0),
+        "satoh": gb.SatohPotential(m=5e10, a=3.0, b=0.3),
+        "logarithmic": gb.LogarithmicPotential(v_c=0.2, r_h=5.0, q1=1.0, q2=0.9, q3=0.8, phi=0.3),
+        "bar": gb.LongMuraliBarPotential(m=1e10, a=4.0, b=0.8, c=0.25, alpha=0.4),
+        "shifted_plummer_plus_disc": gb.CCompositePotential(
+            sat=gb.PlummerPotential(m=1e9, b=0.3, origin=[5.0, -2.0, 1.0]), disc=gb.MiyamotoNagaiPotential(m=5e10, a=3.0, b=0.3)),
+    }
+    q = np.array([[0.0, 5.0, 0.0, 1.0], [0.0, -2.0, 0.0, 1.0], [0.0, 1.0, 1e-300, 1.0]])
+    for name, pot in cases.items():
+        g_ref = ref.gradient(pot, q)
+        assert np.all(np.isfinite(g_ref)), name
+        for strict in (True, False):
+            pot.strict_math = strict
+            g = pot.gradient(q)
+            assert np.all(np.isfinite(g)), (name, strict, g)
+            assert np.max(np.abs(g - g_ref)) <= 1e-13 * max(np.abs(g_ref).max(), 1e-300), (name, strict)
+        pot.strict_math = False

@@ -216,3 +216,93 @@ def test_gala_plugin_adapts_nbody():
     ours = gp.adapt_nbody(nb)
     assert ours.n_massive == 1 and ours._c_w0.shape == (2, 6) and np.array_equal(ours._c_w0, nb._c_w0)
     assert ours.particle_potentials[1] is None
+
+
+def test_plugin_install_patches_the_names_gala_resolves(tmp_path, monkeypatch):
+    """A fake ``gala`` tree with the reference's import structure: the package ``gala.integrate.cyintegrators``
+    binds the three functions in its ``__init__`` (integrate/cyintegrators/__init__.py:1-3) and
+    ``integrate_orbit`` resolves them with ``from ...integrate.cyintegrators import X`` at call time
+    (chamiltonian.pyx:324-336); ``mockstream_generator`` imports its three functions from ``._mockstream`` at import
+    time (mockstream_generator.py:8-12).  After ``install()`` both lookups must find the GPU-backed wrappers."""
+    import importlib
+    import sys
+    import textwrap
+    root = tmp_path / "site"
+    files = {
+        "gala/__init__.py": "",
+        "gala/integrate/__init__.py": "",
+        "gala/integrate/cyintegrators/__init__.py": """
+            from .dop853 import dop853_integrate_hamiltonian
+            from .leapfrog import leapfrog_integrate_hamiltonian
+            from .ruth4 import ruth4_integrate_hamiltonian
+        """,
+        "gala/integrate/cyintegrators/leapfrog.py": "def leapfrog_integrate_hamiltonian(*a, **k):\n    return 'cython leapfrog'\n",
+        "gala/integrate/cyintegrators/ruth4.py": "def ruth4_integrate_hamiltonian(*a, **k):\n    return 'cython ruth4'\n",
+        "gala/integrate/cyintegrators/dop853.py": "def dop853_integrate_hamiltonian(*a, **k):\n    return 'cython dop853'\n",
+        "gala/potential/__init__.py": "",
+        "gala/potential/hamiltonian/__init__.py": "",
+        "gala/potential/hamiltonian/chamiltonian.py": """
+            def integrate_orbit_lookup(which):
+                # the reference's late import, verbatim in structure (chamiltonian.pyx:324-336)
+                if which == 'leapfrog':
+                    from ...integrate.cyintegrators import leapfrog_integrate_hamiltonian as f
+                elif which == 'ruth4':
+                    from ...integrate.cyintegrators import ruth4_integrate_hamiltonian as f
+                else:
+                    from ...integrate.cyintegrators import dop853_integrate_hamiltonian as f
+                return f
+        """,
+        "gala/dynamics/__init__.py": "",
+        "gala/dynamics/mockstream/__init__.py": """
+            from ._mockstream import mockstream_dop853
+            from .mockstream_generator import *
+        """,
+        "gala/dynamics/mockstream/_mockstream.py": """
+            def mockstream_dop853(*a, **k): return 'cython'
+            def mockstream_leapfrog(*a, **k): return 'cython'
+            def mockstream_dop853_animate(*a, **k): return 'cython'
+        """,
+        "gala/dynamics/mockstream/mockstream_generator.py": """
+            from ._mockstream import (mockstream_dop853, mockstream_dop853_animate, mockstream_leapfrog)
+            __all__ = ['run_lookup']
+            def run_lookup(which):
+                return {'dop853': mockstream_dop853, 'leapfrog': mockstream_leapfrog,
+                        'animate': mockstream_dop853_animate}[which]
+        """,
+    }
+    for rel, src in files.items():
+        f = root / rel
+        f.parent.mkdir(parents=True, exist_ok=True)
+        f.write_text(textwrap.dedent(src))
+    monkeypatch.syspath_prepend(str(root))
+    for m in [k for k in sys.modules if k == "gala" or k.startswith("gala.")]:
+        monkeypatch.delitem(sys.modules, m)
+    from gala_b200 import gala_plugin as gp
+    try:
+        ch = importlib.import_module("gala.potential.hamiltonian.chamiltonian")
+        gen = importlib.import_module("gala.dynamics.mockstream.mockstream_generator")
+        assert ch.integrate_orbit_lookup("leapfrog")() == "cython leapfrog"
+        hooks = gp.install()
+        for which in ("leapfrog", "ruth4", "dop853"):
+            f = ch.integrate_orbit_lookup(which)
+            assert f.__name__ == f"{which}_integrate_hamiltonian" and f.__module__ == gp.__name__, which
+        for which in ("dop853", "leapfrog", "animate"):
+            assert gen.run_lookup(which).__module__ == gp.__name__, which
+        import gala.dynamics.mockstream as msp
+        assert msp.mockstream_dop853.__module__ == gp.__name__
+        assert "gala.integrate.cyintegrators.leapfrog_integrate_hamiltonian" in hooks
+        assert "gala.dynamics.mockstream._mockstream.mockstream_leapfrog" in hooks and len(hooks) == 13
+        # a gala without the mock-stream extension: loud, not silent
+        (root / "gala/dynamics/mockstream/mockstream_generator.py").unlink()
+        (root / "gala/dynamics/mockstream/__init__.py").write_text("")
+        for m in [k for k in sys.modules if k.startswith("gala.dynamics")]:
+            del sys.modules[m]
+        importlib.invalidate_caches()
+        with pytest.warns(RuntimeWarning, match="not patched"):
+            with pytest.raises(RuntimeError, match="could not be patched"):
+                gp.install()
+        with pytest.warns(RuntimeWarning):
+            assert len(gp.install(strict=False)) == 10
+    finally:
+        for m in [k for k in sys.modules if k == "gala" or k.startswith("gala.")]:
+            del sys.modules[m]
