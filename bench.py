@@ -117,11 +117,21 @@ def workload(name, n_orbits):
         def run(w0, tt, out=None):
             res = gb.dop853_integrate_hamiltonian(H, w0, tt, save_all=1, return_status=True, out=out)
             stats["nstep"] = res[2]["nstep"]
+            stats["naccpt"] = res[2]["naccpt"]
             return res[1]
 
         def units(N_, out):
             ns = stats["nstep"]
             return int(ns.sum().item() if hasattr(ns, "cpu") else ns.sum())
+
+        def flops_of(N_, out):
+            # algorithmic flops of the steps actually taken: an accepted dense step costs 3970 (12 + 1 + 3 right-hand
+            # sides, stage sums, error norm, dense-output coefficients), a rejected one 2460 (12 right-hand sides, stage
+            # sums, error norm); SURVEY.md appendix C.  Round 1 charged 3970 to every attempted step.
+            ns, na = stats["nstep"], stats["naccpt"]
+            tot = lambda a: int(a.sum().item() if hasattr(a, "cpu") else a.sum())
+            return 3970.0 * tot(na) + 2460.0 * (tot(ns) - tot(na))
+        units.flops_of = flops_of
     elif name in ("c3", "c3d", "c3sg", "c3sgd"):
         # C3: 10^5-particle Fardal stream in MW2022 (tests/dynamics/mockstream/test_mockstream.py:676-678
         # progenitor); c3 = LeapfrogIntegrator (exact orbit-step count), c3d = DOPRI853 (reference default)
@@ -144,7 +154,7 @@ def workload(name, n_orbits):
                                          progenitor_potential=gb.PlummerPotential(m=2.5e4, b=0.05) if selfgrav else None)
             stream, _ = gen.run(prog, 2.5e4, dt=-1.0, n_steps=n_steps, n_particles=n_part, release_every=1,
                                 Integrator=integ, Integrator_kwargs={"err_if_fail": 0} if integ is gb.DOPRI853Integrator else None)
-            return stream.w()
+            return stream.pos          # the MockStream object IS the result (pos / vel views of the (Np, 6) rows, like the reference's)
 
         # fixed-step count: particle released at step k takes k steps (+ the progenitor orbit itself)
         units = lambda N_, out: 2 * n_part * (n_steps * (n_steps + 1) // 2) + n_steps
@@ -587,7 +597,8 @@ def main():
         flops = FLOPS.get(args.workload, 0)
         per_launch_units = tot_units / max(args.steps, 1)
         mean_kern_s = float(np.mean(kern_ms)) * 1e-3
-        achieved_tf = flops * per_launch_units / mean_kern_s / 1e12
+        per_launch_flops = units.flops_of(N, out) if hasattr(units, "flops_of") else flops * per_launch_units
+        achieved_tf = per_launch_flops / mean_kern_s / 1e12
         traffic = None
         tr_file = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tr_file):
@@ -599,7 +610,7 @@ def main():
             "config": config_of(desc, N, len(t), world), "math": "strict" if args.strict else "fast",
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf if peak_tf > 0 else None, "traffic": traffic,
-                         "flops_per_orbit_step": flops,
+                         "flops_per_orbit_step": flops if not hasattr(units, "flops_of") else per_launch_flops / max(per_launch_units, 1),
                          "peak_source": "DFMA microbenchmark measured live (gala_b200/csrc/peak.cu); "
                                         "MEASURED_PEAKS.json has no FP64 entry"},
             "clocks": clk, "gpu_launches": launches, "e2e": e2e, "single_call": single,

@@ -21,6 +21,7 @@ POT_NULL, POT_HERNQUIST, POT_NFW_SPHERICAL, POT_NFW_FLATTENED, POT_NFW_TRIAXIAL 
 POT_MIYAMOTONAGAI, POT_MN3, POT_LONGMURALIBAR, POT_SCF = 5, 6, 7, 8
 POT_KEPLER, POT_PLUMMER, POT_ISOCHRONE, POT_JAFFE, POT_MULTIPOLE = 9, 10, 11, 12, 13
 POT_STONE, POT_BURKERT, POT_SATOH, POT_KUZMIN, POT_LOGARITHMIC, POT_LEESUTO, POT_POWERLAWCUTOFF = 14, 15, 16, 17, 18, 19, 20
+POT_TIMEINTERP = 21
 FRAME_STATIC, FRAME_ROTATING_3D = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 

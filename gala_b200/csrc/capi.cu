@@ -29,6 +29,7 @@ int cuda_fail(cudaError_t e, const char* what) {
     return fail(-10, std::string(what) + ": " + cudaGetErrorString(e));
 }
 #define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(e__, #call); } while (0)
+#define RET_IF(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
 
 // expected parameter counts ([G, ...]) of each type for the compile-time signatures
 int expected_npar(int type) {
@@ -55,6 +56,7 @@ int min_npar(int type) {
         case GB_POT_NFW_SPHERICAL: return 3;
         case GB_POT_SCF: return 5;
         case GB_POT_MULTIPOLE: return 6;
+        case GB_POT_TIMEINTERP: return 7;
         default: return expected_npar(type);
     }
 }
@@ -245,6 +247,158 @@ void plc_fit(double a, std::vector<double>& ext) {
     }
 }
 
+// ---- TimeInterpolatedPotential (device side: csrc/timeinterp.cuh) -----------------------------
+// One table of cubic pieces y = y_i + dx (b_i + dx (c_i + dx d_i)) per interpolated element, in the form
+// gsl_spline_eval evaluates (time_interp.cpp:415-440 calls it per element).  The four interpolation types of
+// time_interpolated.py:44-60, from their published definitions:
+//   linear; cspline = natural cubic spline (second-derivative coefficients from the tridiagonal system, zero at
+//   both ends); akima = Akima (1970), non-periodic end extension, slope m_i when both weights vanish; steffen =
+//   Steffen (1990) monotone cubic with the end secants as end slopes.
+int ti_spline(int method, const std::vector<double>& x, const std::vector<double>& y, double* tab /* [n-1][4] */) {
+    const size_t n = x.size();
+    static const size_t min_size[4] = {2, 3, 5, 3};                 // GSL's minimum number of points per type
+    if (method < 0 || method > 3) return fail(-12, "TimeInterpolated: unknown interpolation method");
+    if (n < min_size[method]) return fail(-12, "TimeInterpolated: too few time knots for this interpolation method");
+    std::vector<double> b(n, 0.), c(n, 0.), d(n, 0.);
+    if (method == 0) {
+        for (size_t i = 0; i + 1 < n; i++) b[i] = (y[i + 1] - y[i]) / (x[i + 1] - x[i]);
+    } else if (method == 1) {
+        std::vector<double> cc(n, 0.);
+        const size_t m = n - 2;
+        std::vector<double> diag(m), off(m), g(m);
+        for (size_t i = 0; i < m; i++) {
+            const double h_i = x[i + 1] - x[i], h_ip1 = x[i + 2] - x[i + 1];
+            off[i] = h_ip1; diag[i] = 2.0 * (h_ip1 + h_i);
+            g[i] = 3.0 * ((y[i + 2] - y[i + 1]) / h_ip1 - (y[i + 1] - y[i]) / h_i);
+        }
+        for (size_t i = 1; i < m; i++) {
+            const double w = off[i - 1] / diag[i - 1];
+            diag[i] -= w * off[i - 1]; g[i] -= w * g[i - 1];
+        }
+        cc[m] = g[m - 1] / diag[m - 1];
+        for (size_t i = m - 1; i-- > 0;) cc[i + 1] = (g[i] - off[i] * cc[i + 2]) / diag[i];
+        for (size_t i = 0; i + 1 < n; i++) {
+            const double dx = x[i + 1] - x[i];
+            b[i] = (y[i + 1] - y[i]) / dx - dx * (cc[i + 1] + 2.0 * cc[i]) / 3.0;
+            c[i] = cc[i];
+            d[i] = (cc[i + 1] - cc[i]) / (3.0 * dx);
+        }
+    } else if (method == 2) {
+        std::vector<double> mm(n + 3);
+        double* m = mm.data() + 2;
+        for (size_t i = 0; i + 1 < n; i++) m[i] = (y[i + 1] - y[i]) / (x[i + 1] - x[i]);
+        m[-2] = 3.0 * m[0] - 2.0 * m[1];
+        m[-1] = 2.0 * m[0] - m[1];
+        m[n - 1] = 2.0 * m[n - 2] - m[n - 3];
+        m[n] = 3.0 * m[n - 2] - 2.0 * m[n - 3];
+        for (long i = 0; i + 1 < (long)n; i++) {
+            const double NE = fabs(m[i + 1] - m[i]) + fabs(m[i - 1] - m[i - 2]);
+            if (NE == 0.0) { b[i] = m[i]; continue; }
+            const double h_i = x[i + 1] - x[i];
+            const double NE_next = fabs(m[i + 2] - m[i + 1]) + fabs(m[i] - m[i - 1]);
+            const double alpha_i = fabs(m[i - 1] - m[i - 2]) / NE;
+            double tL = m[i];
+            if (NE_next != 0.0) { const double al = fabs(m[i] - m[i - 1]) / NE_next; tL = (1.0 - al) * m[i] + al * m[i + 1]; }
+            b[i] = (1.0 - alpha_i) * m[i - 1] + alpha_i * m[i];
+            c[i] = (3.0 * m[i] - 2.0 * b[i] - tL) / h_i;
+            d[i] = (b[i] + tL - 2.0 * m[i]) / (h_i * h_i);
+        }
+    } else {
+        std::vector<double> yp(n);
+        yp[0] = (y[1] - y[0]) / (x[1] - x[0]);
+        yp[n - 1] = (y[n - 1] - y[n - 2]) / (x[n - 1] - x[n - 2]);
+        auto sgn = [](double v) { return v > 0 ? 1. : (v < 0 ? -1. : 0.); };
+        for (size_t i = 1; i + 1 < n; i++) {
+            const double hi = x[i + 1] - x[i], hm = x[i] - x[i - 1];
+            const double si = (y[i + 1] - y[i]) / hi, sm = (y[i] - y[i - 1]) / hm;
+            const double pi = (sm * hi + si * hm) / (hm + hi);
+            yp[i] = (sgn(sm) + sgn(si)) * fmin(fabs(sm), fmin(fabs(si), 0.5 * fabs(pi)));
+        }
+        for (size_t i = 0; i + 1 < n; i++) {
+            const double hi = x[i + 1] - x[i], si = (y[i + 1] - y[i]) / hi;
+            d[i] = (yp[i] + yp[i + 1] - 2.0 * si) / (hi * hi);
+            c[i] = (3.0 * si - 2.0 * yp[i] - yp[i + 1]) / hi;
+            b[i] = yp[i];
+        }
+    }
+    for (size_t i = 0; i + 1 < n; i++) { tab[4 * i] = y[i]; tab[4 * i + 1] = b[i]; tab[4 * i + 2] = c[i]; tab[4 * i + 3] = d[i]; }
+    return 0;
+}
+// a constant element: every piece is (value, 0, 0, 0).  The reference decides "constant" the same way: all knot
+// values within 1e-15 of the first (time_interp.cpp:196-207,340-351).
+void ti_const(double v, size_t n, double* tab) {
+    for (size_t i = 0; i + 1 < n; i++) { tab[4 * i] = v; tab[4 * i + 1] = 0.; tab[4 * i + 2] = 0.; tab[4 * i + 3] = 0.; }
+}
+// rotation_matrix_to_axis_angle (time_interp.cpp:447-498)
+void ti_axis_angle(const double* M, double* axis, double* angle) {
+    const double trace = M[0] + M[4] + M[8];
+    *angle = acos((trace - 1.0) / 2.0);
+    if (fabs(*angle) < 1e-15) { axis[0] = 1.0; axis[1] = 0.0; axis[2] = 0.0; *angle = 0.0; }
+    else if (fabs(*angle - M_PI) < 1e-15) {
+        const double xx = (M[0] + 1.0) / 2.0, yy = (M[4] + 1.0) / 2.0, zz = (M[8] + 1.0) / 2.0;
+        const double xy = M[1] / 2.0, xz = M[2] / 2.0, yz = M[5] / 2.0;
+        if (xx > yy && xx > zz) { axis[0] = sqrt(xx); axis[1] = xy / axis[0]; axis[2] = xz / axis[0]; }
+        else if (yy > zz) { axis[1] = sqrt(yy); axis[0] = xy / axis[1]; axis[2] = yz / axis[1]; }
+        else { axis[2] = sqrt(zz); axis[0] = xz / axis[2]; axis[1] = yz / axis[2]; }
+    } else {
+        const double sa = sin(*angle);
+        axis[0] = (M[7] - M[5]) / (2.0 * sa); axis[1] = (M[2] - M[6]) / (2.0 * sa); axis[2] = (M[3] - M[1]) / (2.0 * sa);
+        const double norm = sqrt(axis[0] * axis[0] + axis[1] * axis[1] + axis[2] * axis[2]);
+        if (norm > 1e-15) { axis[0] /= norm; axis[1] /= norm; axis[2] /= norm; }
+    }
+}
+// params -> small parameters [G, wtype, method, n, nwp, rot_const, t_min, t_max] + ext block (timeinterp.cuh layout)
+int ti_pack(const gb_component& c, double* small, std::vector<double>& ext) {
+    const double* p = c.params;
+    if (c.n_params < 7) return fail(-12, "TimeInterpolated: parameter vector too short");
+    const int wtype = (int)p[1], method = (int)p[2], n = (int)p[3], nwp = (int)p[4], no = (int)p[5], nR = (int)p[6];
+    if (wtype <= GB_POT_NULL || wtype >= GB_POT_TIMEINTERP || wtype == GB_POT_SCF || wtype == GB_POT_MULTIPOLE)
+        return fail(-11, "TimeInterpolated: the wrapped potential must be one of the analytic builtin types");
+    if (n < 2 || nwp < 0 || nwp + 1 > 16 || (no != 1 && no != n) || (nR != 1 && nR != n))
+        return fail(-12, "TimeInterpolated: bad knot / parameter / origin / rotation counts");
+    if (nwp + 1 < min_npar(wtype)) return fail(-12, "TimeInterpolated: too few parameters for the wrapped type");
+    if (c.n_params != 7 + n + n * nwp + 3 * no + 9 * nR) return fail(-12, "TimeInterpolated: parameter vector length does not match its header");
+    if (c.do_shift_rotate) return fail(-12, "TimeInterpolated: origin and R travel inside the parameter vector, not in q0 / R");
+    const double* tk = p + 7;
+    const double* wv = tk + n;
+    const double* ov = wv + (size_t)n * nwp;
+    const double* Rv = ov + (size_t)3 * no;
+    std::vector<double> x(tk, tk + n), y(n);
+    for (int i = 0; i + 1 < n; i++) if (!(x[i + 1] > x[i])) return fail(-12, "TimeInterpolated: time knots must be strictly increasing");
+    const int nel = nwp + 1 + 3 + 4;
+    const size_t base = ext.size();
+    ext.insert(ext.end(), x.begin(), x.end());
+    ext.resize(base + n + (size_t)nel * (n - 1) * 4 + 9, 0.);
+    double* tab = ext.data() + base + n;
+    auto element = [&](int el, const double* vals, int stride, int count) -> int {
+        // vals[k * stride], k < count (count == 1: constant)
+        bool constant = count == 1;
+        if (!constant) { constant = true; for (int k = 1; k < count; k++) if (fabs(vals[(size_t)k * stride] - vals[0]) > 1e-15) { constant = false; break; } }
+        double* tb = tab + (size_t)el * (n - 1) * 4;
+        if (constant) { ti_const(vals[0], n, tb); return 0; }
+        for (int k = 0; k < n; k++) y[k] = vals[(size_t)k * stride];
+        return ti_spline(method, x, y, tb);
+    };
+    RET_IF(element(0, p, 0, 1));                                                    // G: always constant (cytimeinterp.pyx:196-201)
+    for (int k = 0; k < nwp; k++) RET_IF(element(1 + k, wv + k, nwp, n));
+    for (int k = 0; k < 3; k++) RET_IF(element(nwp + 1 + k, ov + k, 3, no));
+    // rotation: constant matrix, or splines through the axis-angle components (time_interp.cpp:325-392)
+    bool rconst = nR == 1;
+    if (!rconst) { rconst = true; for (int i = 1; i < nR && rconst; i++) for (int j = 0; j < 9; j++) if (fabs(Rv[i * 9 + j] - Rv[j]) > 1e-15) { rconst = false; break; } }
+    double* constR = tab + (size_t)nel * (n - 1) * 4;
+    for (int j = 0; j < 9; j++) constR[j] = Rv[j];
+    if (!rconst) {
+        std::vector<double> aa((size_t)4 * n);
+        for (int i = 0; i < n; i++) ti_axis_angle(Rv + 9 * i, &aa[4 * i], &aa[4 * i + 3]);
+        for (int k = 0; k < 4; k++) RET_IF(element(nwp + 4 + k, aa.data() + k, 4, n));
+    } else {
+        for (int k = 0; k < 4; k++) ti_const(0., n, tab + (size_t)(nwp + 4 + k) * (n - 1) * 4);
+    }
+    small[0] = p[0]; small[1] = wtype; small[2] = method; small[3] = n; small[4] = nwp; small[5] = rconst ? 1. : 0.;
+    small[6] = x[0]; small[7] = x[n - 1];
+    return 0;
+}
+
 bool sig_matches(const gb_potential* pot, std::initializer_list<int> types) {
     if ((size_t)pot->n_components != types.size()) return false;
     int i = 0;
@@ -259,7 +413,7 @@ bool sig_matches(const gb_potential* pot, std::initializer_list<int> types) {
 
 // Build the DevPot from the spec: the equivalent of CPotentialWrapper.init +
 // CCompositePotentialWrapper.__init__ (cpotential.pyx:57-102, ccompositepotential.pyx:27-70).
-int resolve(const gb_potential* pot, Resolved& r, cudaStream_t stream) {
+int resolve(const gb_potential* pot, Resolved& r, cudaStream_t stream, bool allow_time_dep = false) {
     if (!pot || !pot->comp) return fail(-12, "null potential spec");
     if (pot->n_dim != 3) return fail(-11, "only n_dim = 3 potentials are supported");
     if (pot->n_components < 1 || pot->n_components > GB_MAXC)
@@ -311,9 +465,19 @@ int resolve(const gb_potential* pot, Resolved& r, cudaStream_t stream) {
             d.eoff = (int)r.ext.size();
             plc_pack(0.5 * (3. - c.params[2]), r.ext);
         }
+        double ti_small[8];
+        if (c.type_id == GB_POT_TIMEINTERP) {
+            nsmall = 8;
+            // block = knots[n] | tables: the tables are read with 16-byte loads, so eoff + n must be even
+            if (c.n_params < 7) return fail(-12, "TimeInterpolated: parameter vector too short");
+            d.eoff = (int)r.ext.size();
+            if (((size_t)d.eoff + (size_t)(int)c.params[3]) & 1) { r.ext.push_back(0.); d.eoff = (int)r.ext.size(); }
+            RET_IF(ti_pack(c, ti_small, r.ext));
+            P.time_dep = 1;
+        }
         d.npar = nsmall;
         if (off + nsmall > GB_MAXP) return fail(-11, "too many potential parameters for the constant bank");
-        for (int k = 0; k < nsmall; k++) P.par[off + k] = c.params[k];
+        for (int k = 0; k < nsmall; k++) P.par[off + k] = (c.type_id == GB_POT_TIMEINTERP) ? ti_small[k] : c.params[k];
         off += nsmall;
         d.doff = doff;
         if (doff + gb_nderived(c.type_id) > GB_MAXD) return fail(-11, "too many potential components for the constant bank");
@@ -356,6 +520,8 @@ int resolve(const gb_potential* pot, Resolved& r, cudaStream_t stream) {
         }
     }
 
+    if (P.time_dep && !allow_time_dep)
+        return fail(-11, "this entry point does not evaluate time-dependent (TimeInterpolated) potentials");
     if (!r.ext.empty()) {
         CU(ext_cache_get(r.ext, &r.d_ext));
         P.ext = r.d_ext;
@@ -570,7 +736,6 @@ void slice_of(size_t N, int k, int nd, size_t* lo, size_t* n) {
     *n = base + ((size_t)k < rem ? 1 : 0);
 }
 
-#define RET_IF(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
 #define KCALL(c, fn, ...) ((c).strict ? gbk_strict::fn(__VA_ARGS__) : gbk_fast::fn(__VA_ARGS__))
 
 // Ruth4 coefficients exactly as the reference computes them (ruth4.pyx:65-78; numpy float pow ==
@@ -593,7 +758,7 @@ int eval_impl(EvalKind kind, const gb_potential* pot, const double* q, double t,
               const gb_launch* opt) {
     Ctx c; RET_IF(open_ctx(opt, c));
     if (N && (!q || !out)) return fail(-12, "null data pointer");
-    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    Resolved r; RET_IF(resolve(pot, r, c.stream, true));
     const int block = pick_block(c, N);
     const void* dq; RET_IF(stage_in_2d(c, 0, q, 3, N, pitch, &dq));
     const size_t orows = kind == EV_GRAD ? 3 : 1;
@@ -707,7 +872,7 @@ static int ham_eval_impl(bool grad, const gb_potential* pot, const gb_frame* fr,
                          size_t pitch, double* out, const gb_launch* opt) {
     Ctx c; RET_IF(open_ctx(opt, c));
     if (N && (!w || !out)) return fail(-12, "null data pointer");
-    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    Resolved r; RET_IF(resolve(pot, r, c.stream, true));
     DevFrame F; RET_IF(resolve_frame(fr, F));
     const int block = pick_block(c, N);
     const size_t orows = grad ? 6 : 1;
@@ -784,7 +949,7 @@ static int fixed_step_impl(bool is_ruth4, const gb_potential* pot, const gb_fram
     DevFrame F; RET_IF(resolve_frame(fr, F));
     if (!is_ruth4 && F.type != GB_FRAME_STATIC)
         return fail(-13, "Leapfrog integration is currently only supported for StaticFrame");
-    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    Resolved r; RET_IF(resolve(pot, r, c.stream, true));
     // HOST: dt from the caller's grid; DEVICE: the kernel reads it from the device grid (no synchronisation here)
     const double dt = c.host ? t[1] - t[0] : 0.0;
     const int dt_from_t = c.host ? 0 : 1;
@@ -870,7 +1035,7 @@ int gb_orbit_extrema(const gb_potential* pot, const gb_frame* fr, const double* 
     Ctx c; RET_IF(open_ctx(opt, c));
     if (ntimes < 1 || !t || (N && (!w || !stats))) return fail(-12, "null data pointer / empty time grid");
     DevFrame F; RET_IF(resolve_frame(fr, F));
-    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    Resolved r; RET_IF(resolve(pot, r, c.stream, true));
     const int block = pick_block(c, N);
     const void *dw, *dtg;
     RET_IF(stage_in(c, 0, w, 6 * (size_t)ntimes * N * sizeof(double), &dw));
@@ -894,7 +1059,7 @@ static int integrate_extrema_impl(const gb_potential* pot, const gb_frame* fr, i
     DevFrame F; RET_IF(resolve_frame(fr, F));
     if (scheme == 0 && F.type != GB_FRAME_STATIC)
         return fail(-13, "Leapfrog integration is currently only supported for StaticFrame");
-    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    Resolved r; RET_IF(resolve(pot, r, c.stream, true));
     const double dt = c.host ? t[1] - t[0] : 0.0;
     const int block = pick_block(c, N);
     double cs[4], ds[4];
@@ -1000,7 +1165,7 @@ static int dop853_impl(const gb_potential* pot, const gb_frame* fr, const double
     if (N >= 0xffffffffull) return fail(-12, "at most 2^32-2 orbits per call");
     RET_IF(pool_keep());
     DevFrame F; RET_IF(resolve_frame(fr, F));
-    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    Resolved r; RET_IF(resolve(pot, r, c.stream, true));
     const int block = c.block > 0 ? c.block : 128;     // 4 warps per CTA, step-synchronised (dop853.cuh)
     double two[2];
     if (c.host) { two[0] = t[0]; two[1] = t[1]; }
@@ -1035,9 +1200,12 @@ static int dop853_impl(const gb_potential* pot, const gb_frame* fr, const double
     // chunk x ntimes x 48 bytes, so the chunk is sized to a fraction of the free device memory.
     size_t chunk = N;
     if (save_all && N) {
-        size_t free_b = 0, total_b = 0;
-        CU(cudaMemGetInfo(&free_b, &total_b));
         const size_t per_orbit = (size_t)ntimes * 6 * sizeof(double);
+        c.lock_scratch();
+        size_t free_b = 0, total_b = 0;
+        // cudaMemGetInfo costs about a millisecond: only asked when the cached scratch cannot hold the whole call
+        if (g_scratch[c.dev][14].cap < N * per_orbit || getenv("GB_D8_SCRATCH_MB")) CU(cudaMemGetInfo(&free_b, &total_b));
+        else free_b = g_scratch[c.dev][14].cap;          // => budget >= cap: one chunk
         // As many orbits per persistent launch as memory allows: a launch cannot end before its longest
         // orbit does (~1000 sequential steps), so the work per resident lane must be several times
         // that, i.e. >> 38k orbits per launch.  Up to half of the free memory (counting what the
@@ -1086,9 +1254,15 @@ static int dop853_impl(const gb_potential* pot, const gb_frame* fr, const double
             for (int k = 0; k < 2; k++) { st[k] = S->s[k]; CU(cudaStreamWaitEvent(st[k], S->ev[2], 0)); }
         }
     }
+    // GB_D8_TIMING=1 (diagnostic): CUDA-event time of the sort, the persistent kernel and the transpose of every
+    // chunk, in place (ncu's per-kernel durations are serialised and cold-cache), printed to stderr
+    const bool timing = getenv("GB_D8_TIMING") != nullptr;
+    cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (timing) for (auto& e : tev) cudaEventCreate(&e);
     int k = 0;
     for (size_t orb0 = 0; orb0 < N; orb0 += chunk, k = (k + 1) % nstreams) {
         const size_t nc = (N - orb0 < chunk) ? N - orb0 : chunk;
+        if (timing) cudaEventRecord(tev[0], st[k]);
         CU(cudaMemsetAsync(queue[k].p, 0, sizeof(unsigned long long), st[k]));
         if (sorted) {
             cudaError_t e = KCALL(c, dyn_time_keys, r.P, (const double*)dw0, N, two[0], orb0, nc, (float*)keys_in[k].p,
@@ -1100,6 +1274,7 @@ static int dop853_impl(const gb_potential* pot, const gb_frame* fr, const double
         }
         double* kout = save_all ? (double*)scratch[k].get() : (double*)dout;
         const uint32_t* pp = sorted ? (const uint32_t*)perm[k].p : nullptr;
+        if (timing) cudaEventRecord(tev[1], st[k]);
         cudaError_t e = (F.type == GB_FRAME_STATIC)
             ? KCALL(c, dop853_static, r.P, F, (const double*)dw0, N, (const double*)dtg, ntimes, a, save_all, pp,
                     (unsigned long long*)queue[k].p, orb0, nc, kout, (int32_t*)dstat, dst[0], dst[1], dst[2], dst[3],
@@ -1109,12 +1284,21 @@ static int dop853_impl(const gb_potential* pot, const gb_frame* fr, const double
                     block, st[k]);
         if (e != cudaSuccess) return cuda_fail(e, "dop853 kernel launch");
         g_launches++;
+        if (timing) cudaEventRecord(tev[2], st[k]);
         if (save_all) {
             e = KCALL(c, dop853_transpose, (const double*)scratch[k].get(), orb0, nc, ntimes, N, (double*)dout, st[k]);
             if (e != cudaSuccess) return cuda_fail(e, "dop853 transpose launch");
             g_launches++;
         }
+        if (timing) {
+            cudaEventRecord(tev[3], st[k]);
+            cudaEventSynchronize(tev[3]);
+            float a = 0, b = 0, c2 = 0;
+            cudaEventElapsedTime(&a, tev[0], tev[1]); cudaEventElapsedTime(&b, tev[1], tev[2]); cudaEventElapsedTime(&c2, tev[2], tev[3]);
+            fprintf(stderr, "[gb_dop853 timing] chunk at %zu (%zu orbits): sort %.3f ms, kernel %.3f ms, transpose %.3f ms\n", orb0, nc, a, b, c2);
+        }
     }
+    if (timing) for (auto& e : tev) cudaEventDestroy(e);
     if (nstreams == 2) {
         for (int q = 0; q < 2; q++) {
             CU(cudaEventRecord(S->ev[q], S->s[q]));

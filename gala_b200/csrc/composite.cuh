@@ -12,6 +12,7 @@
 #include "potentials.cuh"
 #include "scf.cuh"
 #include "multipole.cuh"
+#include "timeinterp.cuh"
 
 template <int T> struct PotOf;
 template <> struct PotOf<GB_POT_NULL>          { using type = PotNull;          static constexpr int NP = 1; };
@@ -99,12 +100,38 @@ GB_DEV void gb_shift_rotate(const DevComp& c, double x, double y, double z, doub
     Z = c.R[6] * sx + c.R[7] * sy + c.R[8] * sz;
 }
 
+// ---- TimeInterpolated component (timeinterp.cuh; time_interp_wrapper.cpp:91-250): the wrapped analytic potential
+// evaluated with the parameter vector, origin and rotation interpolated at time t; NaN outside the knot range.
+GB_DEV void ti_gradient(const double* p, const double* e, double t, double x, double y, double z,
+                        double& gx, double& gy, double& gz) {
+    const TiView v = ti_view(p, e);
+    double wp[GB_TI_MAXPAR], o[3], R[9];
+    if (!ti_state(v, t, wp, o, R)) { gx = CUDART_NAN; gy = CUDART_NAN; gz = CUDART_NAN; return; }   // :148-155
+    double X, Y, Z, ax = 0., ay = 0., az = 0.;
+    ti_to_body(o, R, x, y, z, X, Y, Z);
+    gb_comp_gradient<false>(v.wtype, wp, nullptr, X, Y, Z, ax, ay, az);
+    // grad += R^T grad_body (time_interp_wrapper.cpp:186-201)
+    gx += R[0] * ax + R[3] * ay + R[6] * az;
+    gy += R[1] * ax + R[4] * ay + R[7] * az;
+    gz += R[2] * ax + R[5] * ay + R[8] * az;
+}
+template <int WHAT>     // 0 value, 1 density
+GB_DEV double ti_scalar(const double* p, const double* e, double t, double x, double y, double z) {
+    const TiView v = ti_view(p, e);
+    double wp[GB_TI_MAXPAR], o[3], R[9];
+    if (!ti_state(v, t, wp, o, R)) return CUDART_NAN;
+    double X, Y, Z;
+    ti_to_body(o, R, x, y, z, X, Y, Z);
+    return WHAT == 0 ? gb_comp_value<false>(v.wtype, wp, nullptr, X, Y, Z) : gb_comp_density<false>(v.wtype, wp, nullptr, X, Y, Z);
+}
+
 template <int SIG> struct Composite;
 
 template <bool HEAVY> struct CompositeGeneric {
     // the adaptive integrator evaluates the gradient at 15-17 sites per step: ONE out-of-line copy of this
     // loop-and-switch per kernel instead of 17 inlined ones (hamiltonian.cuh: ham_rhs)
     static constexpr bool kOutOfLineInRhs = true;
+    static constexpr bool kTimeDependent = true;      // may hold a TimeInterpolated component: the kernels pass real times
     // __launch_bounds__ of k_leapfrog: the analytic-only loop is capped at 128 registers (4 CTAs of 128 per SM);
     // uncapped it grew from 124 to 140 registers as more fast accumulators were inlined (48 -> 59 ms for MW2022)
     static constexpr int kFixedStepMaxThreads = HEAVY ? 256 : 128, kFixedStepMinBlocks = HEAVY ? 1 : 4;
@@ -116,6 +143,7 @@ template <bool HEAVY> struct CompositeGeneric {
             const DevComp& c = P.c[i];
             const double* p = &P.par[c.poff];
             const double* e = P.ext + c.eoff;
+            if (c.type == GB_POT_TIMEINTERP) { ti_gradient(p, e, t, x, y, z, gx, gy, gz); continue; }
             if (!c.shift) {
                 gb_comp_gradient<HEAVY>(c.type, p, e, x, y, z, gx, gy, gz);
             } else {
@@ -138,6 +166,7 @@ template <bool HEAVY> struct CompositeGeneric {
             const double* p = &P.par[c.poff];
             const double* d = &P.drv[c.doff];
             const double* e = P.ext + c.eoff;
+            if (c.type == GB_POT_TIMEINTERP) { ti_gradient(p, e, t, x, y, z, ctx.gx, ctx.gy, ctx.gz); continue; }
             if (!c.shift) {
                 gb_comp_accum<HEAVY>(c.type, p, d, e, ctx);
             } else {
@@ -160,6 +189,7 @@ template <bool HEAVY> struct CompositeGeneric {
         for (int i = 0; i < P.n; i++) {
             const DevComp& c = P.c[i];
             double X = x, Y = y, Z = z;
+            if (c.type == GB_POT_TIMEINTERP) { v = v + ti_scalar<0>(&P.par[c.poff], P.ext + c.eoff, t, x, y, z); continue; }
             if (c.shift) gb_shift_rotate(c, x, y, z, X, Y, Z);
             v = v + gb_comp_value<HEAVY>(c.type, &P.par[c.poff], P.ext + c.eoff, X, Y, Z);
         }
@@ -170,6 +200,7 @@ template <bool HEAVY> struct CompositeGeneric {
         for (int i = 0; i < P.n; i++) {
             const DevComp& c = P.c[i];
             double X = x, Y = y, Z = z;
+            if (c.type == GB_POT_TIMEINTERP) { v = v + ti_scalar<1>(&P.par[c.poff], P.ext + c.eoff, t, x, y, z); continue; }
             if (c.shift) gb_shift_rotate(c, x, y, z, X, Y, Z);
             v = v + gb_comp_density<HEAVY>(c.type, &P.par[c.poff], P.ext + c.eoff, X, Y, Z);
         }
@@ -214,6 +245,7 @@ template <int OFF, int DOFF, int T0, int... Ts> struct SeqImpl<OFF, DOFF, T0, Ts
 };
 template <int... Ts> struct Seq {
     static constexpr bool kOutOfLineInRhs = false;
+    static constexpr bool kTimeDependent = false;     // compile-time lists of static analytic potentials ignore t
     static constexpr int kFixedStepMaxThreads = 256, kFixedStepMinBlocks = 1;
     GB_DEV static void gradient(const DevPot& P, double t, double x, double y, double z,
                                 double& gx, double& gy, double& gz) {
@@ -245,6 +277,7 @@ template <> struct Composite<SIG_LM10>       : Seq<GB_POT_MIYAMOTONAGAI, GB_POT_
 template <> struct Composite<SIG_BOVY2014>   : Seq<GB_POT_MIYAMOTONAGAI, GB_POT_POWERLAWCUTOFF, GB_POT_NFW_SPHERICAL> {};
 template <> struct Composite<SIG_SCF> {
     static constexpr bool kOutOfLineInRhs = true;
+    static constexpr bool kTimeDependent = false;
 #ifndef GB_SCF_MINBLOCKS
 #define GB_SCF_MAXTHREADS 256
 #define GB_SCF_MINBLOCKS 1

@@ -240,18 +240,16 @@ struct Dop853Lane {
                 }
 
                 if constexpr (DENSE && gb_is_deferred<OUT>::value) {
-                    // dense-output preparation (dop853.cpp:492-582), deferred form: the coefficient vectors go to
-                    // the OUT object as they are formed (rcont5..8 as partial sums before the three extra stages,
-                    // completed afterwards), so none of them occupies registers across the extra RHS evaluations.
-                    // Same expressions in the same order as the immediate form below.
+                    // dense-output preparation (dop853.cpp:492-582), deferred form.  Register pressure peaks here
+                    // (y, k1, the new y and k1, k6..k9 for the three extra stages, the stage results, the gradient's
+                    // temporaries): at 168 registers the compiler spilled ~50 values per accepted step to local
+                    // memory, which no longer fits L1 next to the 160 KB of shared memory (long-scoreboard stalls,
+                    // profiles/ncu_r2_dop853.txt).  So the OUT object also serves as explicit spill space: rcont5..8
+                    // go there as partial sums before the extra stages, k6..k9 are parked in the rows that rcont1..4
+                    // take only at the very end, and the extra stages read them back.  Same expressions in the same
+                    // order as the immediate form below.
 #pragma unroll(GB_NU)
                     for (int i = 0; i < nn; i++) {
-                        emit.st(i, y[i]);
-                        const double ydiff = k5[i] - y[i];
-                        emit.st(6 + i, ydiff);
-                        const double bspl = h * k1[i] - ydiff;
-                        emit.st(12 + i, bspl);
-                        emit.st(18 + i, ydiff - h * k4[i] - bspl);
                         emit.st(24 + i, d41 * k1[i] + d46 * k6[i] + d47 * k7[i] + d48 * k8[i] + d49 * k9[i] + d410 * k10[i] +
                                         d411 * k2[i] + d412 * k3[i]);
                         emit.st(30 + i, d51 * k1[i] + d56 * k6[i] + d57 * k7[i] + d58 * k8[i] + d59 * k9[i] + d510 * k10[i] +
@@ -260,21 +258,22 @@ struct Dop853Lane {
                                         d611 * k2[i] + d612 * k3[i]);
                         emit.st(42 + i, d71 * k1[i] + d76 * k6[i] + d77 * k7[i] + d78 * k8[i] + d79 * k9[i] + d710 * k10[i] +
                                         d711 * k2[i] + d712 * k3[i]);
+                        emit.st(i, k6[i]); emit.st(6 + i, k7[i]); emit.st(12 + i, k8[i]); emit.st(18 + i, k9[i]);
                     }
 #pragma unroll(GB_NU)
                     for (int i = 0; i < nn; i++)
-                        yy1[i] = y[i] + h * (a141 * k1[i] + a147 * k7[i] + a148 * k8[i] + a149 * k9[i] + a1410 * k10[i] +
-                                             a1411 * k2[i] + a1412 * k3[i] + a1413 * k4[i]);
+                        yy1[i] = y[i] + h * (a141 * k1[i] + a147 * emit.ld(6 + i) + a148 * emit.ld(12 + i) + a149 * emit.ld(18 + i) +
+                                             a1410 * k10[i] + a1411 * k2[i] + a1412 * k3[i] + a1413 * k4[i]);
                     rhs(x + c14 * h, yy1, k10);
 #pragma unroll(GB_NU)
                     for (int i = 0; i < nn; i++)
-                        yy1[i] = y[i] + h * (a151 * k1[i] + a156 * k6[i] + a157 * k7[i] + a158 * k8[i] + a1511 * k2[i] +
-                                             a1512 * k3[i] + a1513 * k4[i] + a1514 * k10[i]);
+                        yy1[i] = y[i] + h * (a151 * k1[i] + a156 * emit.ld(i) + a157 * emit.ld(6 + i) + a158 * emit.ld(12 + i) +
+                                             a1511 * k2[i] + a1512 * k3[i] + a1513 * k4[i] + a1514 * k10[i]);
                     rhs(x + c15 * h, yy1, k2);
 #pragma unroll(GB_NU)
                     for (int i = 0; i < nn; i++)
-                        yy1[i] = y[i] + h * (a161 * k1[i] + a166 * k6[i] + a167 * k7[i] + a168 * k8[i] + a169 * k9[i] +
-                                             a1613 * k4[i] + a1614 * k10[i] + a1615 * k2[i]);
+                        yy1[i] = y[i] + h * (a161 * k1[i] + a166 * emit.ld(i) + a167 * emit.ld(6 + i) + a168 * emit.ld(12 + i) +
+                                             a169 * emit.ld(18 + i) + a1613 * k4[i] + a1614 * k10[i] + a1615 * k2[i]);
                     rhs(x + c16 * h, yy1, k3);
                     nfcn += 3;
 #pragma unroll(GB_NU)
@@ -283,6 +282,13 @@ struct Dop853Lane {
                         emit.st(30 + i, h * (emit.ld(30 + i) + d513 * k4[i] + d514 * k10[i] + d515 * k2[i] + d516 * k3[i]));
                         emit.st(36 + i, h * (emit.ld(36 + i) + d613 * k4[i] + d614 * k10[i] + d615 * k2[i] + d616 * k3[i]));
                         emit.st(42 + i, h * (emit.ld(42 + i) + d713 * k4[i] + d714 * k10[i] + d715 * k2[i] + d716 * k3[i]));
+                        // rcont1..4 last: their rows held k6..k9 until here
+                        emit.st(i, y[i]);
+                        const double ydiff = k5[i] - y[i];
+                        emit.st(6 + i, ydiff);
+                        const double bspl = h * k1[i] - ydiff;
+                        emit.st(12 + i, bspl);
+                        emit.st(18 + i, ydiff - h * k4[i] - bspl);
                     }
 #if GB_STRICT
                     emit.stash(x, h, 0.0);
@@ -431,7 +437,10 @@ GB_DEV int dop853_integrate(const RHS& rhs, const OUT& emit, const Dop853Args& a
 // ceil(total / 32) times with every lane busy, and consecutive lanes write consecutive 48-byte records of the
 // same orbit row.  The numbers are the owner's: same coefficients, same (t - x0) / h, same Horner order.
 #ifndef GB_D8_DENSE_MINB
-#define GB_D8_DENSE_MINB 3       // CTAs of 128 threads per SM the dense kernel is compiled for (168 registers)
+#define GB_D8_DENSE_MINB 3       // CTAs of GB_D8_MAXT threads per SM the dense kernel is compiled for (168 registers)
+#endif
+#ifndef GB_D8_MAXT
+#define GB_D8_MAXT 128           // largest CTA of k_dop853_dyn (A/B builds: 192 x 2, 384 x 1 keep 12 warps per SM)
 #endif
 #define GB_WD_RC 0               // rcont[48][32]
 #define GB_WD_X0 1536            // x0[32]
@@ -526,7 +535,7 @@ GB_DEV int warp_dense_flush(double* wb, unsigned lane, int pending, int out_idx,
 // the final-state kernel gains from 3 CTAs per SM (14.5 -> 13.3 ms).  Round 2 (coefficients in shared memory):
 // see profiles/c2_ab_r2.txt.
 template <class C, bool ROT, bool DENSE>
-__global__ void __launch_bounds__(128, DENSE ? GB_D8_DENSE_MINB : 3)
+__global__ void __launch_bounds__(GB_D8_MAXT, DENSE ? GB_D8_DENSE_MINB : (GB_D8_MAXT == 128 ? 3 : GB_D8_DENSE_MINB))
 k_dop853_dyn(const __grid_constant__ DevPot P, const __grid_constant__ DevFrame F, const __grid_constant__ Dop853Args a,
              const double* __restrict__ w0, size_t N, const double* __restrict__ t, int ntimes,
              const uint32_t* __restrict__ perm, unsigned long long* __restrict__ queue,

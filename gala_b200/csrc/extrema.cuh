@@ -129,14 +129,14 @@ k_integrate_extrema(const __grid_constant__ DevPot P, const __grid_constant__ De
     for (int j = 1; j < ntimes; j++) {
         if (SCHEME == 0) {
             x = x + hx * dt; y = y + hy * dt; z = z + hz * dt;
-            C::gradient(P, 0., x, y, z, gx, gy, gz);
+            C::gradient(P, C::kTimeDependent ? t[j] : 0., x, y, z, gx, gy, gz);
             if (ENERGY || j == ntimes - 1) { vx = hx - gx * dt / 2.; vy = hy - gy * dt / 2.; vz = hz - gz * dt / 2.; }
             hx = hx - gx * dt; hy = hy - gy * dt; hz = hz - gz * dt;
         } else {
 #pragma unroll
             for (int s = 0; s < 4; s++) {
                 if (s > 0) {
-                    C::gradient(P, 0., x, y, z, gx, gy, gz);
+                    C::gradient(P, C::kTimeDependent ? t[j] : 0., x, y, z, gx, gy, gz);
                     if (SCHEME == 1) {
                         vx = vx - K.d[s] * gx * dt; vy = vy - K.d[s] * gy * dt; vz = vz - K.d[s] * gz * dt;
                     } else {

@@ -37,7 +37,7 @@ struct DevPot {
     double par[GB_MAXP];
     double drv[GB_MAXD];       // per component: gb_nderived(type) doubles, see gb_derive() in capi.cu
     int32_t cext_ok;           // 1: cext holds the SCF coefficients of component 0 in the (10,6) padded layout
-    int32_t _pad2;
+    int32_t time_dep;          // 1: some component is a TimeInterpolated wrapper (the kernels then pass real times)
     double cext[GB_CEXT];      // constant-bank copy of a small `ext` block (scf.cuh: scf_fast_gradient)
     const double* ext;         // device-global parameters of "large" components (SCF coefficients)
 };

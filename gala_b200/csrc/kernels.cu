@@ -120,7 +120,7 @@ k_leapfrog(const __grid_constant__ DevPot P, const double* __restrict__ w0, size
 #pragma unroll 1
     for (int j = 1; j < ntimes; j++) {
         x = x + hx * dt; y = y + hy * dt; z = z + hz * dt;
-        C::gradient(P, 0., x, y, z, gx, gy, gz);
+        C::gradient(P, C::kTimeDependent ? t[j] : 0., x, y, z, gx, gy, gz);       // c_leapfrog_step(..., t[j], ...) leapfrog.pyx:106
         if (SAVE || j == ntimes - 1) { vx = hx - gx * dt / 2.; vy = hy - gy * dt / 2.; vz = hz - gz * dt / 2.; }
         hx = hx - gx * dt; hy = hy - gy * dt; hz = hz - gz * dt;
         if (SAVE) {
@@ -165,7 +165,7 @@ k_ruth4(const __grid_constant__ DevPot P, const __grid_constant__ DevFrame F, co
         for (int s = 0; s < 4; s++) {
             if (s > 0) {
                 double gx, gy, gz;
-                C::gradient(P, 0., x, y, z, gx, gy, gz);
+                C::gradient(P, C::kTimeDependent ? t[j] : 0., x, y, z, gx, gy, gz);   // c_ruth4_step(..., t[j], ...) ruth4.pyx:100
                 if (!ROT) {
                     vx = vx - K.d[s] * gx * dt; vy = vy - K.d[s] * gy * dt; vz = vz - K.d[s] * gz * dt;
                 } else {
@@ -324,7 +324,7 @@ cudaError_t GB_D8_NAME(const DevPot& P, const DevFrame& F, const double* w0, siz
     e = cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
     if (const char* eb = getenv("GB_D8_BLOCK")) block = atoi(eb);
-    if (block > 128 || block <= 0 || (block & 31)) block = 64;      // __launch_bounds__ of k_dop853_dyn
+    if (block > GB_D8_MAXT || block <= 0 || (block & 31)) block = 64;      // __launch_bounds__ of k_dop853_dyn
     const char* bs = getenv("GB_D8_BLOCKSYNC");
     const int block_sync = bs ? atoi(bs) : (block > 32);
     if (save_all) {

@@ -627,7 +627,11 @@ class MockStreamGenerator:
         Returns (stream rows (Np,6) host, prog row (1,6) host, release_time, lead_trail)."""
         import queue
         import threading
+        import time
         import torch
+        trace = [] if os.environ.get("GB_STREAM_TRACE") else None
+        t_start = time.perf_counter()
+        mark = (lambda what: trace.append((what, (time.perf_counter() - t_start) * 1e3))) if trace is not None else (lambda what: None)
         H = self.hamiltonian
         dev = torch.device("cuda", torch.cuda.current_device())
         kw = {k: Integrator_kwargs[k] for k in ("atol", "rtol", "nmax", "dt_max", "err_if_fail") if k in Integrator_kwargs}
@@ -653,6 +657,34 @@ class MockStreamGenerator:
         Np = prog_idx.size
         if Np == 0:
             raise ValueError("no stream particles to integrate")
+        # ---- deviates: drawn on a worker thread, piece by piece, in the reference's order; started first, it is the
+        # longest host-side item (4 legacy-gauss normals per Fardal particle: ~17 ns each) ---------------------------
+        # the adaptive particle call reads its status array back (it returns the worst code), so its kernel chunks
+        # cannot overlap one another: one kernel chunk there, the deviates still arrive in cache-sized pieces
+        npiece = max(1, min(int(os.environ.get("GB_STREAM_CHUNKS", "8")), (Np + 4095) // 4096))
+        bounds = [(Np * c) // npiece for c in range(npiece + 1)]
+        group = 1 if lf else npiece               # pieces per kernel chunk
+        has_draws = type(self.df)._draws is not BaseStreamDF._draws
+        q = queue.Queue()
+
+        def draw_all():
+            try:
+                for c in range(npiece):
+                    n = bounds[c + 1] - bounds[c]
+                    q.put(self.df._draws(n, H.potential) if has_draws else None)
+                    mark(f"draws {c} ready")
+            except BaseException as e:           # surfaces on the main thread
+                q.put(e)
+        worker = threading.Thread(target=draw_all, daemon=True)
+        worker.start()
+        # ---- progenitor orbit: launched before the rest of the host bookkeeping (asynchronous for the fixed-step
+        # integrator; the adaptive call returns when its status is back) -------------------------------------------
+        w0_dev = torch.as_tensor(pw, device=dev)
+        if lf:
+            _, traj = leapfrog_integrate_hamiltonian(H, w0_dev, t, save_all=1)
+        else:
+            _, traj = dop853_integrate_hamiltonian(H, w0_dev, t, nstiff=-1, save_all=1, **kw)
+        mark("progenitor issued")
         release_time = orbit_t[prog_idx]
         lead_trail = np.where(sign > 0, "t", "l").astype("U1")
         unq_t1s, nstream = np.unique(release_time, return_counts=True)
@@ -672,28 +704,7 @@ class MockStreamGenerator:
         # grid handed to mockstream_dop853 (time[1] - time[0], mockstream.pyx:228)
         tgrid = orbit_t if lf else np.ascontiguousarray(orbit_t[nstream_idx])
         dt0 = float(tgrid[1] - tgrid[0]) if tgrid.size > 1 else float(orbit_t[1] - orbit_t[0])
-        # ---- deviates: drawn on a worker thread, chunk by chunk, in the reference's order -------------------
-        nchunk = int(os.environ.get("GB_STREAM_CHUNKS", "8"))
-        nchunk = max(1, min(nchunk, (Np + 4095) // 4096))
-        bounds = [(Np * c) // nchunk for c in range(nchunk + 1)]
-        has_draws = type(self.df)._draws is not BaseStreamDF._draws
-        q = queue.Queue()
-
-        def draw_all():
-            try:
-                for c in range(nchunk):
-                    n = bounds[c + 1] - bounds[c]
-                    q.put(self.df._draws(n, H.potential) if has_draws else None)
-            except BaseException as e:           # surfaces on the main thread
-                q.put(e)
-        worker = threading.Thread(target=draw_all, daemon=True)
-        worker.start()
-        # ---- progenitor orbit (device-resident, asynchronous for the fixed-step integrator) -------------------
-        w0_dev = torch.as_tensor(pw, device=dev)
-        if lf:
-            _, traj = leapfrog_integrate_hamiltonian(H, w0_dev, t, save_all=1)
-        else:
-            _, traj = dop853_integrate_hamiltonian(H, w0_dev, t, nstiff=-1, save_all=1, **kw)
+        mark("host plan done")
         traj = traj[:, :, 0]                                                  # (6, ntimes)
         if backward:
             traj = torch.flip(traj, dims=[1])                                # earliest state first (run :237-250)
@@ -712,29 +723,55 @@ class MockStreamGenerator:
         lib, pot = _abi.lib(), H.potential.spec().ptr()
         fr = H.frame.spec()
         strict = bool(getattr(H, "strict_math", False) or H.potential.strict_math)
-        with torch.cuda.stream(side):
-            nb0 = prog_rows[0].reshape(6, 1).contiguous()
-            if lf:
-                _, full = leapfrog_integrate_hamiltonian(H, nb0, orbit_t, save_all=1)
-                idx = int((unq_t1s[last] - orbit_t[0]) / (orbit_t[1] - orbit_t[0]) + 0.5)          # mockstream.pyx:548
-                body0 = full[:, idx, 0]
-            else:
-                akw = {k: v for k, v in Integrator_kwargs.items() if k in ("atol", "rtol", "nmax", "dt_max", "nstiff", "err_if_fail")}
-                akw.setdefault("nstiff", -1)
-                _, full = dop853_integrate_hamiltonian(H, nb0, np.ascontiguousarray(orbit_t[nstream_idx]), save_all=1, **akw)
-                body0 = full[:, last, 0]
-            prow = body0.reshape(1, 6).contiguous()
-            pt1 = torch.full((1,), float(unq_t1s[last]), dtype=torch.float64, device=dev)
-            self._mock_integrate(lib, pot, fr, lf, prow, pt1, 1, tfinal, dt0, Integrator_kwargs, rows1[Np:], status[Np:],
-                                 strict, side, dev)
-        done = [torch.cuda.Event()]
-        done[0].record(side)
-        # ---- chunks: deviates -> release -> integrate, each on its own stream ----------------------------------
-        for c in range(nchunk):
-            a, b = bounds[c], bounds[c + 1]
+        def second_progenitor():
+            # the reference re-integrates the bodies forward from the earliest state (mockstream.pyx:528-548, :247-255);
+            # only the returned progenitor state depends on it
+            with torch.cuda.stream(side):
+                nb0 = prog_rows[0].reshape(6, 1).contiguous()
+                if lf:
+                    _, full = leapfrog_integrate_hamiltonian(H, nb0, orbit_t, save_all=1)
+                    idx = int((unq_t1s[last] - orbit_t[0]) / (orbit_t[1] - orbit_t[0]) + 0.5)          # mockstream.pyx:548
+                    body0 = full[:, idx, 0]
+                else:
+                    akw = {k: v for k, v in Integrator_kwargs.items() if k in ("atol", "rtol", "nmax", "dt_max", "nstiff", "err_if_fail")}
+                    akw.setdefault("nstiff", -1)
+                    _, full = dop853_integrate_hamiltonian(H, nb0, np.ascontiguousarray(orbit_t[nstream_idx]), save_all=1, **akw)
+                    body0 = full[:, last, 0]
+                prow = body0.reshape(1, 6).contiguous()
+                pt1 = torch.full((1,), float(unq_t1s[last]), dtype=torch.float64, device=dev)
+                self._mock_integrate(lib, pot, fr, lf, prow, pt1, 1, tfinal, dt0, Integrator_kwargs, rows1[Np:], status[Np:],
+                                     strict, side, dev)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                return ev
+        done = []
+        side_thread, side_result = None, {}
+        if lf:
+            done.append(second_progenitor())          # asynchronous launches
+        else:
+            # the adaptive calls block until their status is back: run this chain on its own host thread (ctypes and
+            # torch release the GIL) next to the particle call below
+            def side_main():
+                try:
+                    torch.cuda.set_device(dev)
+                    side_result["ev"] = second_progenitor()
+                except BaseException as e:
+                    side_result["err"] = e
+            side_thread = threading.Thread(target=side_main, daemon=True)
+            side_thread.start()
+        mark("progenitor + side stream issued")
+        # ---- kernel chunks: deviates -> release -> integrate, each on its own stream ------------------------------
+        pieces = []
+        for c in range(npiece):
             d = q.get()
             if isinstance(d, BaseException):
                 raise d
+            pieces.append(d)
+            if (c + 1) % group and c + 1 < npiece:
+                continue
+            a, b = bounds[c + 1 - len(pieces)], bounds[c + 1]
+            d = None if pieces[0] is None else (pieces[0] if len(pieces) == 1 else np.concatenate(pieces))
+            pieces = []
             st = _side_stream(dev, 1 + c % 4)
             st.wait_event(ready)
             with torch.cuda.stream(st):
@@ -755,9 +792,15 @@ class MockStreamGenerator:
             ev = torch.cuda.Event()
             ev.record(st)
             done.append(ev)
+            mark(f"chunk ending at piece {c} issued")
+        if side_thread is not None:
+            side_thread.join()
+            if "err" in side_result:
+                raise side_result["err"]
+            done.append(side_result["ev"])
         for ev in done:
             main.wait_event(ev)
-        out = torch.empty((Np + 1, 6), dtype=torch.float64).pin_memory() if Np > 65536 else None
+        out = torch.empty((Np + 1, 6), dtype=torch.float64, pin_memory=True) if Np > 65536 else None
         if out is not None:
             out.copy_(rows1, non_blocking=True)
             main.synchronize()
@@ -765,6 +808,10 @@ class MockStreamGenerator:
         else:
             res = rows1.cpu().numpy()
         worker.join()
+        mark("result on the host")
+        if trace is not None:
+            import sys
+            print("[stream pipeline ms] " + ", ".join(f"{w} {ms:.2f}" for w, ms in trace), file=sys.stderr)
         if not lf and kw.get("err_if_fail", 1):
             worst = int(status.min().item())
             if worst < 0:

@@ -23,7 +23,7 @@ __all__ = [
     "MN3ExponentialDiskPotential", "LongMuraliBarPotential", "SCFPotential", "MultipolePotential", "MilkyWayPotential",
     "MilkyWayPotential2022", "StonePotential", "BurkertPotential", "SatohPotential", "KuzminPotential",
     "LogarithmicPotential", "LeeSutoTriaxialNFWPotential", "PowerLawCutoffPotential", "LM10Potential",
-    "BovyMWPotential2014",
+    "BovyMWPotential2014", "TimeInterpolatedPotential",
 ]
 
 
@@ -435,6 +435,103 @@ class MultipolePotential(PotentialBase):
         n_coeffs = (self.lmax + 1) * (self.lmax + 2) // 2
         return np.concatenate([[self.lmax, n_coeffs, float(self.inner), self.parameters["m"], self.parameters["r_s"]],
                                np.array(list(self.coeffs.values()), dtype=np.float64)])
+
+
+class TimeInterpolatedPotential(PotentialBase):
+    """``TimeInterpolatedPotential`` (reference ``builtin/time_interpolated.py:29``): any analytic builtin potential
+    with parameters, origin and / or rotation given at ``time_knots`` and interpolated in between with one of GSL's
+    spline types -- ``'linear'``, ``'cspline'`` (default), ``'akima'``, ``'steffen'``.  A parameter is constant (scalar)
+    or time-varying (array of length ``n_knots``); ``origin`` is ``(3,)`` or ``(n_knots, 3)``; ``R`` is ``(3, 3)`` or
+    ``(n_knots, 3, 3)`` (interpolated through its axis-angle form, ``time_interp.cpp:325-405``).  Evaluation outside
+    ``[time_knots[0], time_knots[-1]]`` gives NaN, and ``integrate_orbit`` refuses such a time grid
+    (``time_interpolated.py:466-474``).
+
+    The C parameter rows are what the reference interpolates for classes with a parameter transform
+    (``_requires_c_param_precompute``, ``time_interpolated.py:271-330``), applied to every class: the wrapped
+    potential is instantiated at every knot and its ``c_parameters`` are the knot values.  The splines themselves are
+    built inside the C ABI (``GB_POT_TIMEINTERP``)."""
+    _type_id = _abi.POT_TIMEINTERP
+    _METHODS = {"linear": (0, 2), "cspline": (1, 3), "akima": (2, 5), "steffen": (3, 3)}
+    _UNSUPPORTED = ("NullPotential", "MultipolePotential", "SCFPotential", "CCompositePotential", "TimeInterpolatedPotential")
+
+    def __init__(self, potential_cls, time_knots, interpolation_method="cspline", units=galactic, origin=None, R=None,
+                 **kwargs):
+        if not (isinstance(potential_cls, type) and issubclass(potential_cls, PotentialBase)):
+            raise TypeError("potential_cls must be a gala_b200 potential class")
+        if potential_cls.__name__ in self._UNSUPPORTED or issubclass(potential_cls, CCompositePotential):
+            raise NotImplementedError(f"TimeInterpolatedPotential does not currently support {potential_cls.__name__}.")
+        if interpolation_method not in self._METHODS:
+            raise ValueError(f"Interpolation method '{interpolation_method}' is not recognized. Supported methods are: "
+                             f"{list(self._METHODS)}")
+        tk = np.ascontiguousarray(strip(time_knots), dtype=np.float64)
+        if tk.ndim != 1:
+            raise ValueError("time_knots must be one-dimensional")
+        n = tk.size
+        code, need = self._METHODS[interpolation_method]
+        if n < need:
+            raise ValueError(f"Interpolation method '{interpolation_method}' requires at least {need} time knots, but only "
+                             f"{n} were provided. Either provide more time knots or use 'linear' interpolation.")
+        if not np.all(np.diff(tk) > 0):
+            raise ValueError("time_knots must be monotonically increasing (and no duplicate times)")
+        self.potential_cls, self.time_knots, self.interpolation_method = potential_cls, tk, interpolation_method
+        self.units = units
+        self.G = units.G if units is not None else 1.0
+        self._interp_params = []
+        knot_kwargs = [dict() for _ in range(n)]
+        for k, v in kwargs.items():
+            a = np.asarray(strip(v), dtype=np.float64) if not isinstance(v, (bool, str)) else v
+            if isinstance(a, np.ndarray) and a.ndim >= 1 and k in getattr(potential_cls, "_param_names", ()):
+                if a.shape[0] != n:
+                    raise ValueError(f"Parameter '{k}' has shape {a.shape} but there are {n} time knots. For "
+                                     "time-interpolated parameters, the first dimension must match the number of time knots.")
+                self._interp_params.append(k)
+                for i in range(n):
+                    knot_kwargs[i][k] = a[i]
+            else:
+                for i in range(n):
+                    knot_kwargs[i][k] = v
+        knots = [potential_cls(units=units, **kw) for kw in knot_kwargs]
+        if len({p._type_id for p in knots}) != 1:
+            raise ValueError("the wrapped potential must resolve to the same C type at every time knot")
+        self._wrapped_type = knots[0]._type_id
+        self._rows = np.ascontiguousarray([p.c_parameters for p in knots], dtype=np.float64)      # (n_knots, n_wpar)
+        o = np.zeros((1, 3)) if origin is None else np.atleast_2d(np.asarray(strip(origin), dtype=np.float64))
+        if o.shape not in ((1, 3), (n, 3)):
+            raise ValueError(f"Origin array has wrong shape: expected (3,) or ({n}, 3)")
+        Rm = np.eye(3)[None] if R is None else np.asarray(R, dtype=np.float64)
+        Rm = Rm[None] if Rm.ndim == 2 else Rm
+        if Rm.shape not in ((1, 3, 3), (n, 3, 3)):
+            raise ValueError(f"Rotation matrices array has wrong shape {Rm.shape}")
+        self._origins, self._Rs = np.ascontiguousarray(o), np.ascontiguousarray(Rm)
+        self.origin, self.R = np.zeros(3), None          # they travel inside the parameter vector
+        self.parameters = OrderedDict(potential_cls=potential_cls, time_knots=tk, interpolation_method=interpolation_method,
+                                      **{k: kwargs[k] for k in kwargs})
+        self.c_parameters = np.concatenate([[self._wrapped_type, code, n, self._rows.shape[1], o.shape[0], Rm.shape[0]],
+                                            tk, self._rows.ravel(), o.ravel(), Rm.ravel()])
+        self._spec = None
+        self.strict_math = False
+
+    def _c_parameters(self):
+        return self.c_parameters
+
+    @property
+    def time_bounds(self):
+        return float(self.time_knots[0]), float(self.time_knots[-1])
+
+    def integrate_orbit(self, w0, Integrator=None, Integrator_kwargs=None, cython_if_possible=True, save_all=True,
+                        **time_spec):
+        from .integrate import parse_time_specification
+        t = parse_time_specification(self.units, **time_spec)
+        t_min, t_max = self.time_bounds
+        if np.any(t < t_min) or np.any(t > t_max):
+            raise ValueError("Integration times must be within the range of the Potential's interpolation range "
+                             f"that you defined: [{t_min}, {t_max}], your orbit integration range is [{min(t)}, {max(t)}]")
+        return super().integrate_orbit(w0, Integrator=Integrator, Integrator_kwargs=Integrator_kwargs,
+                                       cython_if_possible=cython_if_possible, save_all=save_all, t=t)
+
+    def __repr__(self):
+        return (f"<TimeInterpolatedPotential: {self.potential_cls.__name__} "
+                f"interpolation_method='{self.interpolation_method}')>")
 
 
 class CCompositePotential(PotentialBase, OrderedDict):

@@ -68,6 +68,17 @@ enum gb_pot_type {
     GB_POT_LOGARITHMIC      = 18, /* LogarithmicWrapper     :324  [G, v_c, r_h, q1, q2, q3, phi]         */
     GB_POT_LEESUTO          = 19, /* LeeSutoTriaxialNFWWrapper :336 [G, v_c, r_s, a, b, c]               */
     GB_POT_POWERLAWCUTOFF   = 20, /* PowerLawCutoffWrapper  :213  [G, m, alpha, r_c] (alpha < 3)         */
+    GB_POT_TIMEINTERP       = 21, /* TimeInterpolatedWrapper builtin/cytimeinterp.pyx:73 around one of the analytic types above:
+                                     [G, wrapped_type, method, n_knots, n_wpar, n_origin, n_R,
+                                      t_knots[n_knots], wpar[n_knots][n_wpar], origin[n_origin][3], R[n_R][9]]
+                                     method 0 linear, 1 cspline, 2 akima, 3 steffen (time_interpolated.py:44-60);
+                                     wpar rows = the wrapped potential's c_parameters (without G) at every knot, a
+                                     constant parameter repeated; n_origin / n_R = 1 (constant) or n_knots.  The
+                                     library builds the per-element splines and the axis-angle form of the rotation
+                                     (time_interp.cpp:181-405); evaluation outside [t_knots[0], t_knots[-1]] gives NaN
+                                     (time_interp_wrapper.cpp:103-106).  Supported by gb_gradient / gb_energy /
+                                     gb_density, the Hamiltonian entries, gb_leapfrog, gb_ruth4, gb_dop853 and
+                                     gb_integrate_extrema; other entry points return -11 for it.                   */
     GB_POT_NTYPES
 };
 

@@ -40,10 +40,22 @@ namespace {
 // Owns a CPotential built from a gb_potential spec.  Follows CPotentialWrapper.init
 // (potential/potential/cpotential.pyx:57-102) and the *Wrapper.__init__ bodies
 // (potential/potential/builtin/cybuiltin.pyx:126-376): one function-pointer set per type.
+struct RefPotential;
+#if GB_REF_HAVE_SCF
+// one TimeInterpolated component: the reference's TimeInterpState (opaque here) + the wrapped CPotential it points to
+struct RefTimeInterp {
+    void *state = nullptr;
+    RefPotential *wrapped = nullptr;
+    ~RefTimeInterp();
+};
+#endif
 struct RefPotential {
     CPotential *cp = nullptr;
     std::vector<std::vector<double>> pars, q0, R;
-    ~RefPotential() { if (cp) free_cpotential(cp); }
+#if GB_REF_HAVE_SCF
+    std::vector<RefTimeInterp *> ti;
+#endif
+    ~RefPotential();
 };
 
 #if GB_REF_HAVE_SCF
@@ -54,6 +66,20 @@ double scf_density5(double t, double *pars, double *q, int n_dim, void *) { retu
 // same for the multipole functions (builtin/multipole.h:3-5; cybuiltin.pyx:385-388)
 double mp_potential5(double t, double *pars, double *q, int n_dim, void *) { return mp_potential(t, pars, q, n_dim); }
 double mp_density5(double t, double *pars, double *q, int n_dim, void *) { return mp_density(t, pars, q, n_dim); }
+#endif
+
+#if GB_REF_HAVE_SCF
+}  // namespace
+// oracle/ref_timeinterp.cpp (compiled with USE_GSL == 1): restates TimeInterpolatedWrapper.__init__
+// (potential/potential/builtin/cytimeinterp.pyx:73-300) on the reference's own time_interp_* functions
+extern "C" void *gb_ref_ti_build(const double *params, int n_params, CPotential *wrapped);
+extern "C" void gb_ref_ti_free(void *state);
+extern "C" void gb_ref_ti_hook(CPotential *cp, int i, void *state);
+namespace {
+RefTimeInterp::~RefTimeInterp() { if (state) gb_ref_ti_free(state); delete wrapped; }
+RefPotential::~RefPotential() { if (cp) free_cpotential(cp); for (auto *t : ti) delete t; }
+#else
+RefPotential::~RefPotential() { if (cp) free_cpotential(cp); }
 #endif
 
 bool fill_component(CPotential *cp, int i, int type_id) {
@@ -136,6 +162,35 @@ bool build(const gb_potential *spec, RefPotential &out) {
     int all_null = 1;
     for (int i = 0; i < nc; i++) {
         const gb_component &c = spec->comp[i];
+#if GB_REF_HAVE_SCF
+        if (c.type_id == GB_POT_TIMEINTERP) {
+            // wrapped potential: a one-component CPotential of the wrapped type with the first knot's parameters
+            // (cytimeinterp.pyx:283 keeps wrapped_potential.cpotential only for its function pointers and state)
+            const int wtype = (int)c.params[1], n = (int)c.params[3], nwp = (int)c.params[4];
+            std::vector<double> wp(1 + nwp);
+            wp[0] = c.params[0];
+            for (int k = 0; k < nwp; k++) wp[1 + k] = c.params[7 + n + k];
+            gb_component wc;
+            memset(&wc, 0, sizeof(wc));
+            wc.type_id = wtype; wc.n_params = 1 + nwp; wc.params = wp.data(); wc.R[0] = wc.R[4] = wc.R[8] = 1.;
+            gb_potential wspec = {1, 3, &wc};
+            RefTimeInterp *t = new RefTimeInterp;
+            t->wrapped = new RefPotential;
+            out.ti.push_back(t);
+            if (!build(&wspec, *t->wrapped)) return false;
+            t->state = gb_ref_ti_build(c.params, c.n_params, t->wrapped->cp);
+            if (!t->state) return false;
+            all_null = 0;
+            // CPotentialWrapper.init([0.0], zeros, eye) (cytimeinterp.pyx:285-290): G placeholder, no shift/rotate
+            out.pars[i].assign(1, 0.); out.q0[i].assign(3, 0.); out.R[i].assign(9, 0.);
+            out.R[i][0] = out.R[i][4] = out.R[i][8] = 1.;
+            out.cp->n_params[i] = 1; out.cp->parameters[i] = out.pars[i].data();
+            out.cp->q0[i] = out.q0[i].data(); out.cp->R[i] = out.R[i].data();
+            out.cp->do_shift_rotate[i] = 0;
+            gb_ref_ti_hook(out.cp, i, t->state);
+            continue;
+        }
+#endif
         if (!fill_component(out.cp, i, c.type_id)) return false;
         if (c.type_id != GB_POT_NULL) all_null = 0;
         out.pars[i].assign(c.params, c.params + c.n_params);

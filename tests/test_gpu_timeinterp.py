@@ -1,0 +1,120 @@
+"""`-m gpu`: TimeInterpolatedPotential on the device (GB_POT_TIMEINTERP, csrc/timeinterp.cuh) against the
+reference's own time_interp.cpp / time_interp_wrapper.cpp (oracle; compiled against the GSL spline stand-in that
+tests/test_oracle_cpu.py pins to scipy and to the reference's docstring numbers).
+
+The reference's gradient wrapper indexes its scratch arrays orbit-major while the wrapped gradients are
+structure-of-arrays (time_interp_wrapper.cpp:186-201), so the oracle is only called with ONE point / ONE orbit at a
+time (N = 1, where both layouts coincide)."""
+import numpy as np
+import pytest
+from scipy.spatial.transform import Rotation
+
+import gala_b200 as gb
+from conftest import relnorm
+
+pytestmark = pytest.mark.gpu
+
+T = np.linspace(0.0, 600.0, 13)
+
+
+def _cases():
+    rng = np.random.default_rng(42)
+    grow = np.linspace(1.0, 1.8, T.size) * (1 + 0.05 * rng.normal(size=T.size))
+    Rs = np.array([Rotation.from_rotvec([0.1 * np.sin(a), 0.05, a]).as_matrix() for a in np.linspace(0, 1.9, T.size)])
+    orb = np.stack([8 * np.cos(T / 150), 8 * np.sin(T / 150), 0.5 * np.sin(T / 90)], axis=1)
+    out = {}
+    for method in ("linear", "cspline", "akima", "steffen"):
+        out[f"kepler_mass_{method}"] = gb.TimeInterpolatedPotential(gb.KeplerPotential, T, interpolation_method=method, m=1e10 * grow)
+        out[f"bar_rotating_{method}"] = gb.TimeInterpolatedPotential(gb.LongMuraliBarPotential, T, interpolation_method=method,
+                                                                     m=1e10, a=3.0, b=1.0, c=0.5, R=Rs)
+    out["hernquist_moving_growing"] = gb.TimeInterpolatedPotential(gb.HernquistPotential, T, m=5e10 * grow, c=1.5 * np.sqrt(grow), origin=orb)
+    out["mn3_growing"] = gb.TimeInterpolatedPotential(gb.MN3ExponentialDiskPotential, T, m=5e10 * grow, h_R=2.6, h_z=0.3)
+    out["nfw_triaxial_all"] = gb.TimeInterpolatedPotential(gb.NFWPotential, T, interpolation_method="steffen", m=6e11 * grow, r_s=16.0,
+                                                           a=1.0, b=0.9, c=0.8, origin=0.3 * orb, R=Rs)
+    out["logarithmic_const"] = gb.TimeInterpolatedPotential(gb.LogarithmicPotential, T, v_c=0.2, r_h=5.0, q1=1.0, q2=0.9, q3=0.8, phi=0.3)
+    comp = gb.CCompositePotential()
+    comp["halo"] = gb.NFWPotential(m=6e11, r_s=16.0)
+    comp["sat"] = gb.TimeInterpolatedPotential(gb.PlummerPotential, T, m=2e10 * grow, b=1.0, origin=2.5 * orb)
+    out["static_halo_plus_moving_satellite"] = comp
+    return out
+
+
+CASES = _cases()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("strict", [True, False])
+def test_evaluation_parity(ref, name, strict):
+    pot = CASES[name]
+    pot.strict_math = strict
+    rng = np.random.default_rng(1)
+    n = 40
+    q = rng.normal(0, 9.0, (3, n))
+    times = np.concatenate([rng.uniform(T[0], T[-1], n - 4), [T[0], T[-1], T[3], 0.5 * (T[5] + T[6])]])
+    for i in range(n):
+        qi = np.ascontiguousarray(q[:, i:i + 1])
+        g0, e0, d0 = ref.gradient(pot, qi, t=times[i]), ref.energy(pot, qi, t=times[i]), ref.density(pot, qi, t=times[i])
+        g, e = pot.gradient(qi, t=times[i]), pot.energy(qi, t=times[i])
+        assert np.max(np.abs(g - g0)) <= 2e-13 * np.abs(g0).max(), (name, i)
+        assert abs(e[0] - e0[0]) <= 2e-13 * abs(e0[0])
+        if np.isfinite(d0[0]):
+            d = pot.density(qi, t=times[i])
+            assert abs(d[0] - d0[0]) <= 1e-11 * max(abs(d0[0]), 1e-300)
+    # many points at one time == the same points one by one (the device has no N = 1 restriction)
+    gall = pot.gradient(q, t=times[0])
+    for i in range(0, n, 7):
+        assert np.array_equal(gall[:, i], pot.gradient(np.ascontiguousarray(q[:, i:i + 1]), t=times[0])[:, 0])
+    # outside the knot range: NaN (time_interp_wrapper.cpp:103-106,148-155)
+    assert np.isnan(pot.gradient(q, t=T[-1] + 1.0)).all() and np.isnan(pot.energy(q, t=T[0] - 1e-9)).all()
+    pot.strict_math = False
+
+
+def test_reference_docstring_numbers_on_the_gpu():
+    t = np.linspace(0, 100, 11)
+    pot = gb.TimeInterpolatedPotential(gb.KeplerPotential, t, m=np.linspace(1e10, 2e10, 11))
+    q = np.array([[1e-3], [0.0], [0.0]])
+    assert abs(pot.energy(q, t=0.0)[0] - (-44.98502151)) < 5e-9 and abs(pot.energy(q, t=50.0)[0] - (-67.47753227)) < 5e-9
+    Rs = np.array([Rotation.from_rotvec([0, 0, a]).as_matrix() for a in np.linspace(0, np.pi / 2, 11)])
+    bar = gb.TimeInterpolatedPotential(gb.LongMuraliBarPotential, np.linspace(0, 1000, 11), m=1e10, a=3.0, b=1.0, c=0.5, R=Rs)
+    q = np.array([[5.0], [0.0], [0.0]])
+    assert abs(bar.gradient(q, t=0.0)[0, 0] - 0.00207787) < 5e-9 and abs(bar.gradient(q, t=500.0)[0, 0] - 0.0015879) < 5e-8
+
+
+@pytest.mark.parametrize("name", ["static_halo_plus_moving_satellite", "bar_rotating_cspline", "hernquist_moving_growing"])
+def test_integration_parity(ref, name):
+    """Leapfrog, Ruth4 and DOP853 through a time-dependent potential: the step time t[j] (fixed step,
+    leapfrog.pyx:106, ruth4.pyx:100) / the stage time (DOP853) reaches the interpolation.  One orbit per oracle call."""
+    pot = CASES[name]
+    H = gb.Hamiltonian(pot)
+    rng = np.random.default_rng(3)
+    N = 12
+    w0 = np.vstack([rng.normal(0, 8.0, (3, N)), rng.normal(0, 0.08, (3, N))])
+    t = np.linspace(T[0], T[-1], 1201)
+    for strict in (True, False):
+        H.strict_math = strict
+        _, w_lf = gb.leapfrog_integrate_hamiltonian(H, w0, t, save_all=0)
+        _, w_r4 = gb.ruth4_integrate_hamiltonian(H, w0, t, save_all=0)
+        _, w_d8 = gb.dop853_integrate_hamiltonian(H, w0, t[::10].copy(), save_all=0)
+        for i in range(N):
+            wi = np.ascontiguousarray(w0[:, i:i + 1])
+            assert relnorm(w_lf[:, i:i + 1], ref.leapfrog(pot, wi, t, save_all=False)).max() < 1e-10
+            assert relnorm(w_r4[:, i:i + 1], ref.ruth4(H, wi, t, save_all=False)).max() < 1e-10
+            assert relnorm(w_d8[:, i:i + 1], ref.dop853(H, wi, t[::10].copy(), save_all=False, nbatch=1)[0]).max() < 1e-8
+    # the host class refuses a grid outside the knots; the raw boundary call integrates into NaN like the reference
+    if isinstance(pot, gb.TimeInterpolatedPotential):
+        with pytest.raises(ValueError):
+            pot.integrate_orbit(w0, dt=1.0, n_steps=int(T[-1]) + 10)
+    _, w_nan = gb.leapfrog_integrate_hamiltonian(H, w0, np.linspace(T[-1] - 5, T[-1] + 5, 11), save_all=0)
+    assert np.isnan(w_nan).all()
+    st = gb.integrate_extrema(H, w0, t, Integrator="leapfrog", return_final=True)
+    assert np.allclose(st["w_final"], w_lf, rtol=1e-9, atol=1e-12)
+
+
+def test_unsupported_entry_points_say_so():
+    pot = CASES["kepler_mass_cspline"]
+    with pytest.raises(gb._abi.GalaB200Error, match="time-dependent"):
+        pot.hessian(np.ones((3, 2)))
+    H = gb.Hamiltonian(pot)
+    prog = gb.PhaseSpacePosition(pos=[8.0, 0.0, 0.0], vel=[0.0, 0.07, 0.0])
+    with pytest.raises(gb._abi.GalaB200Error, match="time-dependent"):
+        gb.MockStreamGenerator(gb.StreaklineStreamDF(), H).run(prog, 1e4, dt=1.0, n_steps=50, Integrator="leapfrog")

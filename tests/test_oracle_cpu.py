@@ -528,3 +528,69 @@ def test_multipole_closed_form_lmax5(ref):
             d = np.zeros((3, 1)); d[k] = h
             gfd[k] = (-phi(q + 2 * d) + 8 * phi(q + d) - 8 * phi(q - d) + phi(q - 2 * d)) / (12 * h)
         assert np.max(np.abs(g - gfd)) / np.abs(g).max() < 1e-8
+
+
+# ---- GSL spline stand-in (oracle/gsl_shim/gsl/gsl_spline.h) and the reference's TimeInterpolatedPotential ----------
+def _shim_spline(kind, xk, yk, t):
+    import ctypes as C
+    L = _shim()
+    xk, yk, t = (np.ascontiguousarray(a, dtype=np.float64) for a in (xk, yk, t))
+    out = np.empty_like(t)
+    rc = L.shim_spline_eval(kind, xk.ctypes.data_as(C.c_void_p), yk.ctypes.data_as(C.c_void_p), xk.size,
+                            t.ctypes.data_as(C.c_void_p), t.size, out.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return out
+
+
+def test_gsl_shim_splines_match_scipy():
+    """linear / cspline (natural) / akima against scipy.interpolate on irregular knots; steffen against an independent
+    numpy statement of Steffen (1990) eqs. 2-11 plus its defining property (monotone between knots)."""
+    from scipy.interpolate import Akima1DInterpolator, CubicSpline
+    rng = np.random.default_rng(7)
+    for n in (5, 6, 12, 40):
+        xk = np.sort(rng.uniform(-50, 150, n)); yk = rng.normal(0, 3, n)
+        t = np.concatenate([np.linspace(xk[0], xk[-1], 801), xk])
+        scale = np.abs(yk).max()
+        assert np.max(np.abs(_shim_spline(0, xk, yk, t) - np.interp(t, xk, yk))) <= 1e-14 * scale
+        assert np.max(np.abs(_shim_spline(1, xk, yk, t) - CubicSpline(xk, yk, bc_type="natural")(t))) <= 1e-12 * scale
+        assert np.max(np.abs(_shim_spline(2, xk, yk, t) - Akima1DInterpolator(xk, yk)(t))) <= 1e-12 * scale
+        # Steffen: slopes at the knots, then the cubic Hermite form
+        h = np.diff(xk); s = np.diff(yk) / h
+        yp = np.empty(n); yp[0] = s[0]; yp[-1] = s[-1]
+        p = (s[:-1] * h[1:] + s[1:] * h[:-1]) / (h[:-1] + h[1:])
+        yp[1:-1] = (np.sign(s[:-1]) + np.sign(s[1:])) * np.minimum(np.minimum(np.abs(s[:-1]), np.abs(s[1:])), 0.5 * np.abs(p))
+        i = np.clip(np.searchsorted(xk, t, side="right") - 1, 0, n - 2)
+        u = (t - xk[i]) / h[i]
+        herm = ((2 * u ** 3 - 3 * u ** 2 + 1) * yk[i] + (u ** 3 - 2 * u ** 2 + u) * h[i] * yp[i]
+                + (-2 * u ** 3 + 3 * u ** 2) * yk[i + 1] + (u ** 3 - u ** 2) * h[i] * yp[i + 1])
+        got = _shim_spline(3, xk, yk, t)
+        assert np.max(np.abs(got - herm)) <= 1e-12 * scale
+        for k in range(n - 1):           # monotone on every interval
+            seg = got[:801][(t[:801] >= xk[k]) & (t[:801] <= xk[k + 1])]
+            d = np.diff(seg)
+            assert np.all(d * np.sign(yk[k + 1] - yk[k]) >= -1e-12 * scale)
+    assert np.isnan(_shim_spline(1, [0, 1, 2.0], [1, 2, 3.0], [-0.1, 2.1])).all()       # GSL_EDOM outside the knots
+
+
+def test_reference_time_interpolated_doctest_numbers(ref):
+    """The reference's own TimeInterpolatedPotential (time_interp.cpp / time_interp_wrapper.cpp compiled against the
+    spline stand-in, wired like cytimeinterp.pyx:157-300) reproduces the numbers of its class docstring
+    (time_interpolated.py:77-110): Kepler with a linearly growing mass, and a LongMuraliBar rotating by 90 deg in 1 Gyr."""
+    t = np.linspace(0, 100, 11)
+    pot = gb.TimeInterpolatedPotential(gb.KeplerPotential, t, m=np.linspace(1e10, 2e10, 11))
+    q = np.array([[1e-3], [0.0], [0.0]])
+    assert abs(ref.energy(pot, q, t=0.0)[0] - (-44.98502151)) < 5e-9
+    assert abs(ref.energy(pot, q, t=50.0)[0] - (-67.47753227)) < 5e-9
+    assert np.isnan(ref.energy(pot, q, t=100.5)[0]) and np.isnan(ref.gradient(pot, q, t=-1.0)).all()
+    from scipy.spatial.transform import Rotation
+    Rs = np.array([Rotation.from_rotvec([0, 0, a]).as_matrix() for a in np.linspace(0, np.pi / 2, 11)])
+    bar = gb.TimeInterpolatedPotential(gb.LongMuraliBarPotential, np.linspace(0, 1000, 11), m=1e10, a=3.0, b=1.0, c=0.5, R=Rs)
+    q = np.array([[5.0], [0.0], [0.0]])
+    assert abs(ref.gradient(bar, q, t=0.0)[0, 0] - 0.00207787) < 5e-9
+    assert abs(ref.gradient(bar, q, t=500.0)[0, 0] - 0.0015879) < 5e-8
+    with pytest.raises(ValueError):
+        gb.TimeInterpolatedPotential(gb.KeplerPotential, t[:4], interpolation_method="akima", m=np.ones(4))
+    with pytest.raises(NotImplementedError):
+        gb.TimeInterpolatedPotential(gb.NullPotential, t)
+    with pytest.raises(ValueError):
+        pot.integrate_orbit(np.ones(6), dt=1.0, n_steps=200)
