@@ -1,5 +1,7 @@
-"""Multi-GPU execution: orbits are independent, so the orbit index is cut into contiguous slices,
-one per rank (one process per GPU), with NO collective on the data path.
+"""Multi-GPU execution, one process per GPU: orbits are independent, so the orbit index is cut into contiguous
+slices, one per rank, with NO collective on the data path.  (The other form -- ONE process,
+one call, all devices -- lives inside the C ABI: ``gb_launch.n_devices``, ``gala_b200.set_devices``; it uses the same
+``shard_bounds`` rule for orbits and deals mock-stream particles in groups of 128 rows, ``capi.cu:Deal``.)
 ``torch.distributed`` is only plumbing: rank/world discovery and, when the caller wants the full
 result on every rank or on rank 0, a gather of the per-rank (6, [ntimes,] n_r) blocks.
 """
@@ -7,7 +9,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["shard_bounds", "shard", "gather_orbits", "integrate_sharded", "deal_by_work"]
+__all__ = ["shard_bounds", "shard", "gather_orbits", "integrate_sharded"]
 
 
 def shard_bounds(N: int, world: int):
@@ -26,13 +28,6 @@ def shard(w0, rank: int, world: int):
     """This rank's columns of a (6, N) array (a view; made contiguous by the integrators)."""
     lo, hi = shard_bounds(w0.shape[-1], world)[rank]
     return w0[..., lo:hi]
-
-
-def deal_by_work(work, world: int):
-    """Mock streams: particle p needs work[p] steps (triangular in release time).  Sort by work and
-    deal round-robin so every rank gets an equal share; returns a list of index arrays."""
-    order = np.argsort(-np.asarray(work), kind="stable")
-    return [np.sort(order[r::world]) for r in range(world)]
 
 
 def gather_orbits(local, N: int, dst=None, group=None):

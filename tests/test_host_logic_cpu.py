@@ -4,7 +4,7 @@ import pytest
 
 import gala_b200 as gb
 from gala_b200 import _abi
-from gala_b200.dist import deal_by_work, shard_bounds
+from gala_b200.dist import shard_bounds
 
 
 def test_parse_time_specification_matches_reference_semantics():
@@ -153,11 +153,6 @@ def test_shard_bounds_and_work_dealing():
     b = shard_bounds(10, 4)
     assert b == [(0, 3), (3, 6), (6, 8), (8, 10)]
     assert shard_bounds(0, 2) == [(0, 0), (0, 0)]
-    work = np.arange(100)[::-1]
-    parts = deal_by_work(work, 8)
-    assert sorted(np.concatenate(parts)) == list(range(100))
-    loads = [work[p].sum() for p in parts]
-    assert max(loads) - min(loads) <= 100
 
 
 def test_gala_plugin_extracts_duck_typed_gala_objects():
