@@ -20,4 +20,4 @@ from .mockstream import (BaseStreamDF, FardalStreamDF, StreaklineStreamDF, Lagra
 
 from .nonlinear import fast_lyapunov_max
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"

@@ -788,7 +788,7 @@ int eval_common(EvalKind kind, const gb_potential* pot, const double* q, double 
 extern "C" {
 
 const char* gb_last_error(void) { return g_err.c_str(); }
-const char* gb_version(void) { return "gala_b200 0.1 (sm_100a)"; }
+const char* gb_version(void) { return "gala_b200 0.2 (sm_100a)"; }
 long gb_launch_count(void) { return g_launches.load(); }
 int gb_device_count(void) {
     int n = 0;

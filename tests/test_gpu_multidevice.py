@@ -134,3 +134,19 @@ def test_device_list_validation(mw):
     with pytest.raises(ValueError):
         gb.set_devices([0, 0])
     assert gb.set_devices(None) is None
+    # a device list with device-memory buffers is refused (a device pointer belongs to one device), and entry points
+    # that run on one device say so instead of ignoring the list
+    import ctypes as C
+    import torch
+    wd = torch.as_tensor(w0, device="cuda")
+    out = torch.empty_like(wd)
+    td = torch.as_tensor(t, device="cuda")
+    opt = _abi.launch_opts(False, devices=[0])
+    opt.mem = _abi.MEM_DEVICE
+    fr = mw.frame.spec()
+    rc = _abi.lib().gb_leapfrog(mw.potential.spec().ptr(), C.byref(fr), wd.data_ptr(), 64, td.data_ptr(), 5, 0, out.data_ptr(), C.byref(opt))
+    assert rc == -12 and b"GB_MEM_HOST" in _abi.lib().gb_last_error()
+    opt = _abi.launch_opts(False, devices=[0])
+    h = np.empty((9, 64))
+    rc = _abi.lib().gb_hessian(mw.potential.spec().ptr(), np.ascontiguousarray(w0[:3]).ctypes.data, 0.0, 64, h.ctypes.data, C.byref(opt))
+    assert rc == -12 and b"one device" in _abi.lib().gb_last_error()
