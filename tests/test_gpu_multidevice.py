@@ -150,3 +150,20 @@ def test_device_list_validation(mw):
     h = np.empty((9, 64))
     rc = _abi.lib().gb_hessian(mw.potential.spec().ptr(), np.ascontiguousarray(w0[:3]).ctypes.data, 0.0, 64, h.ctypes.data, C.byref(opt))
     assert rc == -12 and b"one device" in _abi.lib().gb_last_error()
+
+
+@pytest.mark.parametrize("N", [0, 1, 2, 5])
+def test_fewer_orbits_than_devices(mw, N):
+    """Slices may be empty: N = 0, 1, 2 orbits over three (virtual) devices, and every output shape / value as on one."""
+    w0 = make_ic(lambda q: mw.potential.gradient(q), max(N, 1), 3)[:, :N]
+    w0 = np.ascontiguousarray(w0)
+    t = np.arange(21.0)
+    ref_lf = gb.leapfrog_integrate_hamiltonian(mw, w0, t, save_all=1)[1]
+    ref_d8 = gb.dop853_integrate_hamiltonian(mw, w0, t, save_all=0, return_status=True)
+    with use_devices([0, 0, 0]):
+        got_lf = gb.leapfrog_integrate_hamiltonian(mw, w0, t, save_all=1)[1]
+        got_d8 = gb.dop853_integrate_hamiltonian(mw, w0, t, save_all=0, return_status=True)
+        st = gb.integrate_extrema(mw, w0, t, Integrator="ruth4", return_final=True)
+    assert got_lf.shape == (6, 21, N) and np.array_equal(got_lf, ref_lf)
+    assert np.array_equal(got_d8[1], ref_d8[1]) and np.array_equal(got_d8[2]["nstep"], ref_d8[2]["nstep"])
+    assert st["w_final"].shape == (6, N) and st["n_peri"].shape == (N,)
