@@ -13,7 +13,7 @@ from .frame import StaticFrame, ConstantRotatingFrame
 from .dynamics import PhaseSpacePosition, Orbit, MockStream
 from .integrate import (pinned_empty, parse_time_specification, LeapfrogIntegrator, Ruth4Integrator, DOPRI853Integrator,
                         leapfrog_integrate_hamiltonian, ruth4_integrate_hamiltonian,
-                        dop853_integrate_hamiltonian, integrate_extrema, orbit_extrema)
+                        dop853_integrate_hamiltonian, integrate_extrema, orbit_extrema, orbit_extrema_list)
 from .hamiltonian import Hamiltonian
 from .mockstream import (BaseStreamDF, FardalStreamDF, StreaklineStreamDF, LagrangeCloudStreamDF, ChenStreamDF,
                          MockStreamGenerator, DirectNBody, mockstream_dop853, mockstream_leapfrog)

@@ -28,8 +28,9 @@ MEM_HOST, MEM_DEVICE = 0, 1
 # enum gb_extrema_row: rows of the (EXT_NSTAT, N) statistics array of gb_orbit_extrema / gb_integrate_extrema
 EXT_ROWS = ("n_peri", "peri_mean", "peri_min", "peri_max", "peri_t_first", "peri_t_last",
             "n_apo", "apo_mean", "apo_min", "apo_max", "apo_t_first", "apo_t_last",
-            "E_first", "E_last", "dE_max", "abs_z_max")
-EXT_NSTAT = 16
+            "E_first", "E_last", "dE_max", "abs_z_max",
+            "n_zmax", "zmax_mean", "zmax_min", "zmax_max", "zmax_t_first", "zmax_t_last")
+EXT_NSTAT = 22
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -109,6 +110,8 @@ SIGNATURES = {
                                   C.c_void_p, C.c_void_p, P(gb_launch)]),
     "gb_orbit_extrema": (C.c_int, [P(gb_potential), P(gb_frame), C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int,
                                    C.c_void_p, P(gb_launch)]),
+    "gb_orbit_extrema_list": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, P(gb_launch)]),
     "gb_integrate_extrema": (C.c_int, [P(gb_potential), P(gb_frame), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
                                        C.c_int, C.c_void_p, C.c_void_p, P(gb_launch)]),
     "gb_last_error": (C.c_char_p, []),

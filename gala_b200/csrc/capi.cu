@@ -1049,6 +1049,31 @@ int gb_orbit_extrema(const gb_potential* pot, const gb_frame* fr, const double* 
     return finish(c);
 }
 
+int gb_orbit_extrema_list(const double* w, const double* t, int ntimes, size_t N, int kind, int kmax, double* vals,
+                          double* times, int32_t* counts, const gb_launch* opt) {
+    Ctx c; RET_IF(open_ctx(opt, c));
+    if (ntimes < 1 || !t || (N && (!w || !counts))) return fail(-12, "null data pointer / empty time grid");
+    if (kind < 0 || kind > 2) return fail(-12, "kind must be 0 (pericentres), 1 (apocentres) or 2 (z heights)");
+    if (kmax < 0 || (kmax > 0 && N && (!vals || !times))) return fail(-12, "kmax > 0 needs the vals / times arrays");
+    const int block = pick_block(c, N);
+    const void *dw, *dtg;
+    RET_IF(stage_in(c, 0, w, 6 * (size_t)ntimes * N * sizeof(double), &dw));
+    RET_IF(stage_in(c, 2, t, (size_t)ntimes * sizeof(double), &dtg));
+    void *dv, *dt2, *dc;
+    const size_t lb = (size_t)kmax * N * sizeof(double);
+    RET_IF(stage_out_alloc(c, 1, vals, lb, &dv));
+    RET_IF(stage_out_alloc(c, 4, times, lb, &dt2));
+    RET_IF(stage_out_alloc(c, 5, counts, N * sizeof(int32_t), &dc));
+    cudaError_t e = KCALL(c, trajectory_extrema_list, (const double*)dw, (const double*)dtg, ntimes, N, kind, kmax,
+                          (double*)dv, (double*)dt2, (int32_t*)dc, block, c.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "trajectory_extrema_list launch");
+    if (N) g_launches++;
+    RET_IF(stage_out_copy(c, vals, dv, lb));
+    RET_IF(stage_out_copy(c, times, dt2, lb));
+    RET_IF(stage_out_copy(c, counts, dc, N * sizeof(int32_t)));
+    return finish(c);
+}
+
 static int integrate_extrema_impl(const gb_potential* pot, const gb_frame* fr, int scheme, const double* w0, size_t N,
                                   size_t pitch, const double* t, int ntimes, int with_energy, double* w_final,
                                   double* stats, const gb_launch* opt) {

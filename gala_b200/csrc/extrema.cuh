@@ -16,50 +16,97 @@
 
 // rows of the statistics array (GB_EXT_NSTAT, N): enum gb_extrema_row of include/gala_b200.h
 
+// the vertex of the parabola through (t_{j-1}, a), (t_j, b), (t_{j+1}, c), in coordinates centred on t_j
+GB_DEV void ext_parabola(double tm2, double tm1, double tj, double a, double b, double c, double& tv, double& val) {
+    const double da = tm2 - tm1, db = tj - tm1;
+    const double sb = (c - b) / db, sa = (a - b) / da;
+    const double c2 = (sb - sa) / (db - da);
+    const double c1 = sb - c2 * db;
+    const double tau = -c1 / (2. * c2);
+    tv = tm1 + tau;
+    val = b + tau * (c1 + c2 * tau);
+}
+
+// kinds: 0 pericentres (local minima of r), 1 apocentres (local maxima of r), 2 z-heights (local maxima of |z|,
+// Orbit.zmax, dynamics/orbit.py:600-656)
 struct ExtremaAcc {
-    double rm2, rm1, tm2, tm1;      // the two previous samples
+    double rm2, rm1, zm2, zm1, tm2, tm1;      // the two previous samples of r and |z|
     int seen;
-    double n[2], sum[2], mn[2], mx[2], tfirst[2], tlast[2];     // [0] pericentres, [1] apocentres
-    double zmax;
+    double n[3], sum[3], mn[3], mx[3], tfirst[3], tlast[3];
+    double zabs;
     GB_DEV void init() {
-        seen = 0; rm2 = rm1 = tm2 = tm1 = 0.;
-        for (int k = 0; k < 2; k++) { n[k] = 0.; sum[k] = 0.; mn[k] = CUDART_INF; mx[k] = -CUDART_INF; tfirst[k] = CUDART_NAN; tlast[k] = CUDART_NAN; }
-        zmax = 0.;
+        seen = 0; rm2 = rm1 = zm2 = zm1 = tm2 = tm1 = 0.;
+        for (int k = 0; k < 3; k++) { n[k] = 0.; sum[k] = 0.; mn[k] = CUDART_INF; mx[k] = -CUDART_INF; tfirst[k] = CUDART_NAN; tlast[k] = CUDART_NAN; }
+        zabs = 0.;
+    }
+    GB_DEV void add(int k, double tv, double val) {
+        if (n[k] == 0.) tfirst[k] = tv;
+        tlast[k] = tv;
+        n[k] += 1.; sum[k] += val; mn[k] = fmin(mn[k], val); mx[k] = fmax(mx[k], val);
     }
     // sample j: position (x, y, z) at time tj.  An extremum at sample j-1 is recognised when sample j arrives.
-    GB_DEV void push(double x, double y, double z, double tj) {
-        const double r = sqrt(x * x + y * y + z * z);
-        zmax = fmax(zmax, fabs(z));
+    // LIST (k_trajectory_extrema_list): hand every extremum of `kind` to `sink(value, time)` as well.
+    template <class Sink>
+    GB_DEV void push(double x, double y, double z, double tj, int kind, const Sink& sink) {
+        const double r = sqrt(x * x + y * y + z * z), az = fabs(z);
+        zabs = fmax(zabs, az);
         if (seen >= 2) {
             const bool is_max = (rm1 > rm2) && (rm1 > r);
             const bool is_min = (rm1 < rm2) && (rm1 < r);      // argrelmax(-r)
+            double tv, val;
             if (is_max || is_min) {
-                const double a = tm2 - tm1, b = tj - tm1;
-                const double sb = (r - rm1) / b, sa = (rm2 - rm1) / a;
-                const double c2 = (sb - sa) / (b - a);
-                const double c1 = sb - c2 * b;
-                const double tau = -c1 / (2. * c2);
-                const double val = rm1 + tau * (c1 + c2 * tau);
+                ext_parabola(tm2, tm1, tj, rm2, rm1, r, tv, val);
                 const int k = is_max ? 1 : 0;
-                if (n[k] == 0.) tfirst[k] = tm1 + tau;
-                tlast[k] = tm1 + tau;
-                n[k] += 1.; sum[k] += val; mn[k] = fmin(mn[k], val); mx[k] = fmax(mx[k], val);
+                add(k, tv, val);
+                if (kind == k) sink(val, tv);
+            }
+            if ((zm1 > zm2) && (zm1 > az)) {
+                ext_parabola(tm2, tm1, tj, zm2, zm1, az, tv, val);
+                add(2, tv, val);
+                if (kind == 2) sink(val, tv);
             }
         }
-        rm2 = rm1; tm2 = tm1; rm1 = r; tm1 = tj; seen++;
+        rm2 = rm1; zm2 = zm1; tm2 = tm1; rm1 = r; zm1 = az; tm1 = tj; seen++;
     }
+    GB_DEV void push(double x, double y, double z, double tj) { push(x, y, z, tj, -1, [](double, double) {}); }
     GB_DEV void store(double* __restrict__ st, size_t N, size_t i) const {
-        for (int k = 0; k < 2; k++) {
-            st[(6 * k + 0) * N + i] = n[k];
-            st[(6 * k + 1) * N + i] = n[k] > 0. ? sum[k] / n[k] : CUDART_NAN;     // np.mean of an empty array
-            st[(6 * k + 2) * N + i] = n[k] > 0. ? mn[k] : CUDART_NAN;
-            st[(6 * k + 3) * N + i] = n[k] > 0. ? mx[k] : CUDART_NAN;
-            st[(6 * k + 4) * N + i] = tfirst[k];
-            st[(6 * k + 5) * N + i] = tlast[k];
+        for (int k = 0; k < 3; k++) {
+            const int base = k < 2 ? 6 * k : 16;
+            st[(base + 0) * N + i] = n[k];
+            st[(base + 1) * N + i] = n[k] > 0. ? sum[k] / n[k] : CUDART_NAN;     // np.mean of an empty array
+            st[(base + 2) * N + i] = n[k] > 0. ? mn[k] : CUDART_NAN;
+            st[(base + 3) * N + i] = n[k] > 0. ? mx[k] : CUDART_NAN;
+            st[(base + 4) * N + i] = tfirst[k];
+            st[(base + 5) * N + i] = tlast[k];
         }
-        st[15 * N + i] = zmax;
+        st[15 * N + i] = zabs;
     }
 };
+
+// func=None of Orbit.pericenter / apocenter / zmax: every refined extremum of one kind, in time order.  vals / times
+// are (kmax, N) (extremum k of orbit i at [k * N + i], NaN beyond the orbit's count); counts (N) holds the true
+// number, which may exceed kmax -- the caller then repeats with a larger kmax.
+__global__ void k_trajectory_extrema_list(const double* __restrict__ w, const double* __restrict__ t, int ntimes, size_t N,
+                                          int kind, int kmax, double* __restrict__ vals, double* __restrict__ times,
+                                          int32_t* __restrict__ counts) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const size_t TS = (size_t)ntimes * N;
+    ExtremaAcc A; A.init();
+    int found = 0;
+    auto sink = [&](double val, double tv) {
+        if (found < kmax) { vals[(size_t)found * N + i] = val; times[(size_t)found * N + i] = tv; }
+        found++;
+    };
+    const bool rev = t[ntimes - 1] < t[0];
+    for (int jj = 0; jj < ntimes; jj++) {
+        const int j = rev ? ntimes - 1 - jj : jj;
+        const double* p = w + (size_t)j * N + i;
+        A.push(__ldcs(p), __ldcs(p + TS), __ldcs(p + 2 * TS), t[j], kind, sink);
+    }
+    for (int k = found; k < kmax; k++) { vals[(size_t)k * N + i] = CUDART_NAN; times[(size_t)k * N + i] = CUDART_NAN; }
+    counts[i] = found;
+}
 
 // An existing trajectory w (6, ntimes, N) in device memory (e.g. the dense output of gb_dop853): one pass, reads are
 // coalesced across orbits (consecutive threads = consecutive orbits of one row).  ENERGY: also the Hamiltonian

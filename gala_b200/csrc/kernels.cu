@@ -517,6 +517,12 @@ cudaError_t trajectory_extrema(const DevPot& P, const DevFrame& F, const double*
     }
     return cudaGetLastError();
 }
+cudaError_t trajectory_extrema_list(const double* w, const double* t, int ntimes, size_t N, int kind, int kmax,
+                                    double* vals, double* times, int32_t* counts, int block, cudaStream_t s) {
+    if (N == 0) return cudaSuccess;
+    k_trajectory_extrema_list<<<nblocks(N, block), block, 0, s>>>(w, t, ntimes, N, kind, kmax, vals, times, counts);
+    return cudaGetLastError();
+}
 cudaError_t integrate_extrema(const DevPot& P, const DevFrame& F, int scheme, const double* cs, const double* ds,
                               const double* w0, size_t N, const double* t, int ntimes, double dt, int dt_from_t,
                               int with_energy, double* wfin, double* stats, int block, cudaStream_t s) {

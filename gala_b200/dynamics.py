@@ -84,32 +84,53 @@ class Orbit(PhaseSpacePosition):
         return Orbit(pos=self.pos[(slice(None),) + key], vel=self.vel[(slice(None),) + key], t=t,
                      hamiltonian=self.hamiltonian, frame=self.frame)
 
-    # -- pericentre / apocentre (dynamics/orbit.py:439-553), reduced on the GPU -------------------------------
+    # -- pericentre / apocentre / zmax / eccentricity (dynamics/orbit.py:391-681), reduced on the GPU ----------------
     def _extrema(self, kind, func, return_times, approximate):
-        from .integrate import orbit_extrema
+        from .integrate import orbit_extrema, orbit_extrema_list
         if approximate:
             raise NotImplementedError("approximate=True (no parabola refinement) is not part of the device reduction")
-        if self.hamiltonian is None or self.t is None:
-            raise ValueError("pericenter/apocenter need the orbit's hamiltonian and time grid")
+        if self.t is None:
+            raise ValueError("pericenter / apocenter / zmax need the orbit's time grid")
         if return_times and func is not None:
-            raise ValueError(f"Cannot return times if reducing {kind}centers using an input function. Pass `func=None` "
-                             "if you want to return all individual values and times.")
-        row = {np.mean: "mean", np.min: "min", np.max: "max", np.amin: "min", np.amax: "max"}.get(func)
-        if row is None:
-            raise NotImplementedError("the device reduction provides func=np.mean (default), np.min and np.max; for the "
-                                      "full list of extrema reduce the trajectory yourself")
+            raise ValueError("Cannot return times if reducing using an input function. Pass `func=None` if you want to "
+                             "return all individual values and times.")
         w = self.w()
-        st = orbit_extrema(self.hamiltonian, w if w.ndim == 3 else w[:, :, None], self.t)
+        single = w.ndim == 2
+        w3 = w[:, :, None] if single else w
+        if func is None:             # every extremum (and its time): one array per orbit
+            vals, times = orbit_extrema_list(w3, self.t, kind)
+            if single:
+                return (vals[0], times[0]) if return_times else vals[0]
+            return (vals, times) if return_times else vals
+        row = {np.mean: "mean", np.min: "min", np.max: "max", np.amin: "min", np.amax: "max"}.get(func)
+        if row is None:              # any other reduction: applied to the list, like the reference applies func
+            vals, _ = orbit_extrema_list(w3, self.t, kind)
+            out = np.array([func(v) for v in vals])
+            return out[0] if single else out
+        if self.hamiltonian is None:
+            raise ValueError("the device reduction needs the orbit's hamiltonian")
+        st = orbit_extrema(self.hamiltonian, w3, self.t)
         out = st[f"{kind}_{row}"]
-        return out[0] if w.ndim == 2 else out
+        return out[0] if single else out
 
     def pericenter(self, return_times=False, func=np.mean, approximate=False):
-        """``Orbit.pericenter`` (``dynamics/orbit.py:439-493``) for ``func`` in (np.mean, np.min, np.max)."""
+        """``Orbit.pericenter`` (``dynamics/orbit.py:439-493``): mean (default) / min / max of the refined local minima of
+        r(t) straight from the device reduction; ``func=None`` all of them (with ``return_times`` also their times);
+        any other ``func`` is applied to the list."""
         return self._extrema("peri", func, return_times, approximate)
 
     def apocenter(self, return_times=False, func=np.mean, approximate=False):
-        """``Orbit.apocenter`` (``dynamics/orbit.py:495-553``) for ``func`` in (np.mean, np.min, np.max)."""
+        """``Orbit.apocenter`` (``dynamics/orbit.py:495-553``)."""
         return self._extrema("apo", func, return_times, approximate)
+
+    def zmax(self, return_times=False, func=np.mean, approximate=False):
+        """``Orbit.zmax`` (``dynamics/orbit.py:600-656``): refined local maxima of |z|."""
+        return self._extrema("zmax", func, return_times, approximate)
+
+    def eccentricity(self, **kw):
+        """``Orbit.eccentricity`` (``dynamics/orbit.py:658-681``): (r_apo - r_per) / (r_apo + r_per) of the means."""
+        ra, rp = self.apocenter(**kw), self.pericenter(**kw)
+        return (ra - rp) / (ra + rp)
 
     def energy(self, hamiltonian=None):
         """Hamiltonian value along the orbit, shape (ntimes[, norbits]) -- evaluated on the GPU."""

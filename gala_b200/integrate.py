@@ -20,7 +20,7 @@ from .units import strip
 
 __all__ = ["pinned_empty", "parse_time_specification", "LeapfrogIntegrator", "Ruth4Integrator", "DOPRI853Integrator",
            "get_integrator", "leapfrog_integrate_hamiltonian", "ruth4_integrate_hamiltonian",
-           "dop853_integrate_hamiltonian", "integrate_extrema", "orbit_extrema"]
+           "dop853_integrate_hamiltonian", "integrate_extrema", "orbit_extrema", "orbit_extrema_list"]
 
 
 def parse_time_specification(units=None, dt=None, n_steps=None, t1=None, t2=None, t=None):
@@ -272,6 +272,38 @@ def orbit_extrema(hamiltonian, w, t, with_energy=False):
     _abi.check(_abi.lib().gb_orbit_extrema(hamiltonian.potential.spec().ptr(), C.byref(fr), buf.ptr, tb.ptr, ntimes, N,
                                            int(bool(with_energy)), _abi.Buf(stats).ptr, C.byref(opt)))
     return _stats_dict(stats)
+
+
+def orbit_extrema_list(w, t, kind="peri"):
+    """Every refined extremum of one kind -- ``"peri"``, ``"apo"`` or ``"zmax"`` -- of every orbit of an existing trajectory
+    ``w`` (6, ntimes, N), i.e. ``func=None`` of ``Orbit.pericenter / apocenter / zmax`` (``dynamics/orbit.py:439-656``).
+    Returns ``(values, times)``: two lists with one array per orbit, in increasing time."""
+    k = {"peri": 0, "apo": 1, "zmax": 2}[kind]
+    if _abi._is_torch_cuda(w):
+        buf = _abi.Buf(w.contiguous())
+    else:
+        a = np.ascontiguousarray(w, dtype=np.float64)
+        buf = _abi.Buf(a if a.ndim == 3 else np.ascontiguousarray(a[:, :, None]))
+    if buf.arr.ndim != 3 or buf.arr.shape[0] != 6:
+        raise ValueError("w must have shape (6, ntimes[, N])")
+    th, tb = _prep_t(t, buf)
+    ntimes, N = buf.arr.shape[1], buf.arr.shape[2]
+    if th.size != ntimes:
+        raise ValueError("t must have one entry per saved sample")
+    kmax = 16
+    while True:
+        vals, times = _alloc(buf, (kmax, N)), _alloc(buf, (kmax, N))
+        counts = _alloc(buf, (N,), "i4")
+        opt = _abi.launch_opts(buf.device, False, *_stream_dev(buf))
+        _abi.check(_abi.lib().gb_orbit_extrema_list(buf.ptr, tb.ptr, ntimes, N, k, kmax, _abi.Buf(vals).ptr,
+                                                    _abi.Buf(times).ptr, _abi.Buf(counts).ptr, C.byref(opt)))
+        cmax = int(counts.max()) if N else 0
+        if cmax <= kmax:
+            break
+        kmax = cmax
+    if buf.device:
+        vals, times, counts = vals.cpu().numpy(), times.cpu().numpy(), counts.cpu().numpy()
+    return [vals[:counts[i], i].copy() for i in range(N)], [times[:counts[i], i].copy() for i in range(N)]
 
 
 def _stream_dev(buf):

@@ -321,12 +321,19 @@ enum gb_extrema_row {
     GB_EXT_N_PERI = 0, GB_EXT_PERI_MEAN, GB_EXT_PERI_MIN, GB_EXT_PERI_MAX, GB_EXT_PERI_T_FIRST, GB_EXT_PERI_T_LAST,
     GB_EXT_N_APO = 6,  GB_EXT_APO_MEAN,  GB_EXT_APO_MIN,  GB_EXT_APO_MAX,  GB_EXT_APO_T_FIRST,  GB_EXT_APO_T_LAST,
     GB_EXT_E_FIRST = 12, GB_EXT_E_LAST, GB_EXT_DE_MAX, GB_EXT_ABS_Z_MAX,
-    GB_EXT_NSTAT = 16
+    /* Orbit.zmax (dynamics/orbit.py:600-656): local maxima of |z|, refined the same way */
+    GB_EXT_N_ZMAX = 16, GB_EXT_ZMAX_MEAN, GB_EXT_ZMAX_MIN, GB_EXT_ZMAX_MAX, GB_EXT_ZMAX_T_FIRST, GB_EXT_ZMAX_T_LAST,
+    GB_EXT_NSTAT = 22
 };
 /* reduce a trajectory that already exists: w is (6, ntimes, N) (e.g. the dense output of gb_dop853 left in device
  * memory); a decreasing grid is walked backwards, like the reference reverses the orbit (orbit.py:486,546). */
 int gb_orbit_extrema(const gb_potential* pot, const gb_frame* fr, const double* w, const double* t, int ntimes,
                      size_t N, int with_energy, double* stats /* (GB_EXT_NSTAT, N) */, const gb_launch* opt);
+/* func=None of Orbit.pericenter / apocenter / zmax: every refined extremum of one kind (0 pericentres, 1 apocentres,
+ * 2 z-heights) of every orbit, in increasing time.  vals / times are (kmax, N), NaN beyond an orbit's count;
+ * counts (N) holds the true number per orbit (repeat with a larger kmax if any exceeds it). */
+int gb_orbit_extrema_list(const double* w, const double* t, int ntimes, size_t N, int kind, int kmax,
+                          double* vals, double* times, int32_t* counts, const gb_launch* opt);
 /* integrate like gb_leapfrog (scheme 0) / gb_ruth4 (scheme 1; rotating frame with gb_ruth4's semantics) and reduce on
  * the fly: nothing of size ntimes is written.  w_final (6, N) may be NULL.  Shards over gb_launch.devices. */
 int gb_integrate_extrema(const gb_potential* pot, const gb_frame* fr, int scheme, const double* w0, size_t N,

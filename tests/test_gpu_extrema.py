@@ -43,6 +43,14 @@ def check(stats, t, w, N):
             assert abs(stats[f"{kind}_t_first"][i] - tt[0]) <= 1e-5 * abs(t[1] - t[0])
             assert abs(stats[f"{kind}_t_last"][i] - tt[-1]) <= 1e-5 * abs(t[1] - t[0])
     assert np.allclose(stats["abs_z_max"], np.abs(w[2]).max(0), rtol=0, atol=0)
+    az = np.abs(w[2])
+    if t[-1] < t[0]:
+        az = az[::-1]
+    for i in range(N):                                   # Orbit.zmax: local maxima of |z| (orbit.py:600-656)
+        v, tt = reference_extrema(t, az[:, i], 1.0)
+        assert stats["n_zmax"][i] == len(v)
+        if len(v):
+            assert abs(stats["zmax_mean"][i] - v.mean()) <= 1e-8 * max(v.mean(), 1e-3) and abs(stats["zmax_max"][i] - v.max()) <= 1e-8 * max(v.max(), 1e-3)
 
 
 @pytest.mark.parametrize("integ", ["leapfrog", "ruth4"])
@@ -90,10 +98,24 @@ def test_orbit_extrema_of_existing_trajectory(backward):
     assert np.array_equal(peri, st["peri_mean"], equal_nan=True) and np.array_equal(apo, st["apo_max"], equal_nan=True)
     one = H.integrate_orbit(w0[:, 0], Integrator="dopri853", t=t)
     assert one.pericenter() == st["peri_mean"][0]
-    with pytest.raises(NotImplementedError):
-        orbit.pericenter(func=np.median)
     with pytest.raises(ValueError):
         orbit.pericenter(return_times=True)
+    # func=None: every extremum and its time (orbit.py:473-480), one array per orbit; other reductions apply to the list
+    r = np.sqrt((w[:3] ** 2).sum(0))
+    tt = t[::-1] if backward else t
+    rr = r[::-1] if backward else r
+    vals, times = orbit.apocenter(func=None, return_times=True)
+    for i in (0, 7, N - 1):
+        v, tv = reference_extrema(tt, rr[:, i], 1.0)
+        assert len(vals[i]) == len(v) and np.allclose(vals[i], v, rtol=1e-8) and np.allclose(times[i], tv, rtol=0, atol=1e-5 * abs(t[1] - t[0]))
+    v1, t1 = one.pericenter(func=None, return_times=True)
+    assert np.array_equal(v1, orbit.pericenter(func=None)[0]) and len(v1) == st["n_peri"][0]
+    assert np.allclose(orbit.pericenter(func=np.median), [np.median(v) if len(v) else np.nan for v in orbit.pericenter(func=None)], equal_nan=True)
+    ecc = orbit.eccentricity()
+    assert np.allclose(ecc, (st["apo_mean"] - st["peri_mean"]) / (st["apo_mean"] + st["peri_mean"]), equal_nan=True)
+    assert np.all((ecc[np.isfinite(ecc)] >= 0) & (ecc[np.isfinite(ecc)] < 1))
+    zm = orbit.zmax()
+    assert zm.shape == (N,) and np.array_equal(zm, st["zmax_mean"], equal_nan=True)
 
 
 def test_integrate_extrema_errors_and_devices():
