@@ -43,7 +43,10 @@ FLOPS = {"headline": 146, "c1": 46, "c1x": 46, "c4": 666, "c2": 3970, "c5": 3400
 HBM_BOUND = {"c1", "c1x"}
 # total orbits of the strong-scaling single-call measurement (one host array, one C-ABI call over all devices):
 # 8 x the per-GPU default, C5 at exactly the 10^7 orbits of BASELINE.json configs[4]
-TOTAL_ORBITS = {"headline": 8 * 10 * SM_FILL, "c4": 8 * 4 * SM_FILL, "c5": 10_000_000}
+TOTAL_ORBITS = {"headline": 8 * 10 * SM_FILL, "c4": 8 * 4 * SM_FILL, "c5": 10_000_000,
+                # trajectory-output workloads: the call is bound by the PCIe read-back, which every device does over
+                # its own link -- C1 at exactly BASELINE configs[0]'s 10^4 orbits, C1x and the C2 chunk at the 1-GPU sizes
+                "c1": 10_000, "c1x": 1 << 20, "c2": 148 * 256 * 8}
 
 
 def make_ic(N, seed, pot_gradient, rmin=4.0, rmax=50.0):
@@ -406,7 +409,7 @@ def measured_hbm_peak():
         return 6500.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
 
 
-def single_call_strong(args, gb, torch, H, t, run, world, name):
+def single_call_strong(args, gb, torch, H, t, run, units, world, name):
     """Strong scaling through the drop-in API (north_star: "each GPU takes a contiguous slice of orbits and results
     are gathered to the host"): ONE pinned host array of TOTAL_ORBITS[name] orbits, ONE call of the public function
     with gb.set_devices(range(world)) -- the C ABI shards it (gb_launch.n_devices), every device copies its slice
@@ -414,28 +417,33 @@ def single_call_strong(args, gb, torch, H, t, run, world, name):
     the other ranks wait on a CPU barrier (their GPUs are idle and are driven by rank 0's process here)."""
     total = args.total_orbits or TOTAL_ORBITS.get(name)
     if not total:
-        return {"skipped": f"single-call strong scaling is measured on the final-state workloads ({sorted(TOTAL_ORBITS)})"}
+        return {"skipped": f"the single-call leg is defined for {sorted(TOTAL_ORBITS)}"}
     if gb._abi.device_count() < world:
         return {"skipped": f"rank 0 sees {gb._abi.device_count()} devices, needs {world}"}
     w0 = make_ic(total, 4242, lambda q: H.potential.gradient(q))
     pin_in = gb.pinned_empty(w0.shape); pin_in[...] = w0
-    pin_out = gb.pinned_empty(w0.shape)
+    save_all = name in ("c1", "c1x", "c2")
+    pin_out = gb.pinned_empty((6, len(t), total) if save_all else w0.shape)
     devs = list(range(world))
     gb.set_devices(devs)
+    nunits = 0
+    steps = args.steps if not save_all else min(args.steps, 5)       # multi-GB read-backs: a few calls are enough
     try:
-        for _ in range(3):
-            run(pin_in, t, pin_out)
+        for _ in range(2 if save_all else 3):
+            out = run(pin_in, t, pin_out)
+            units(total, out)
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            run(pin_in, t, pin_out)          # returns when every device has delivered its slice
+        for _ in range(steps):
+            out = run(pin_in, t, pin_out)          # returns when every device has delivered its slice
+            nunits += units(total, out)
         el = time.perf_counter() - t0
     finally:
         gb.set_devices(None)
-    nst = len(t) - 1
-    return {"value": total * nst * args.steps / el, "unit": "orbit-steps/s", "ms_per_call": el / args.steps * 1e3,
+    return {"value": nunits / el, "unit": "orbit-steps/s", "ms_per_call": el / steps * 1e3,
             "orbits": int(total), "devices": devs, "scaling": "strong",
             "h2d_bytes_per_call": int(pin_in.nbytes + t.nbytes), "d2h_bytes_per_call": int(pin_out.nbytes),
-            "what": "one pinned host (6,N) array in, one C-ABI call over all devices (gb_launch.n_devices), one (6,N) array out; wall clock on rank 0"}
+            "what": "one pinned host (6,N) array in, one C-ABI call over all devices (gb_launch.n_devices), one "
+                    + ("(6,ntimes,N)" if save_all else "(6,N)") + " array out; wall clock on rank 0"}
 
 
 def main():
@@ -582,12 +590,12 @@ def main():
 
     # strong scaling through ONE call over all devices, rank 0 only (the other ranks idle on a CPU barrier)
     single = None
-    if not args.no_single_call and not args.no_e2e:
+    if not args.no_single_call:
         if world > 1:
             dist.barrier(group=cpu_group)
         if rank == 0:
             try:
-                single = single_call_strong(args, gb, torch, H, t, run, world, args.workload)
+                single = single_call_strong(args, gb, torch, H, t, run, units, world, args.workload)
             except Exception as e:
                 single = {"error": f"{type(e).__name__}: {e}"}
         if world > 1:
