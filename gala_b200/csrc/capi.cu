@@ -1041,8 +1041,9 @@ int gb_orbit_extrema(const gb_potential* pot, const gb_frame* fr, const double* 
     RET_IF(stage_in(c, 0, w, 6 * (size_t)ntimes * N * sizeof(double), &dw));
     RET_IF(stage_in(c, 2, t, (size_t)ntimes * sizeof(double), &dtg));
     void* dst; RET_IF(stage_out_alloc(c, 1, stats, GB_EXT_NSTAT * N * sizeof(double), &dst));
-    cudaError_t e = KCALL(c, trajectory_extrema, r.P, F, (const double*)dw, (const double*)dtg, ntimes, N, with_energy,
-                          (double*)dst, block, c.stream);
+    cudaError_t e = with_energy
+        ? KCALL(c, trajectory_extrema_e1, r.P, F, (const double*)dw, (const double*)dtg, ntimes, N, (double*)dst, block, c.stream)
+        : KCALL(c, trajectory_extrema_e0, r.P, F, (const double*)dw, (const double*)dtg, ntimes, N, (double*)dst, block, c.stream);
     if (e != cudaSuccess) return cuda_fail(e, "trajectory_extrema launch");
     if (N) g_launches++;
     RET_IF(stage_out_copy(c, stats, dst, GB_EXT_NSTAT * N * sizeof(double)));
@@ -1095,8 +1096,11 @@ static int integrate_extrema_impl(const gb_potential* pot, const gb_frame* fr, i
     void *dst, *dfin = nullptr;
     RET_IF(stage_out_alloc(c, 1, stats, GB_EXT_NSTAT * N * sizeof(double), &dst));
     if (w_final) RET_IF(stage_out_alloc(c, 4, w_final, 6 * N * sizeof(double), &dfin));
-    cudaError_t e = KCALL(c, integrate_extrema, r.P, F, scheme, cs, ds, (const double*)dw0, N, (const double*)dtg, ntimes,
-                          dt, c.host ? 0 : 1, with_energy, (double*)dfin, (double*)dst, block, c.stream);
+    cudaError_t e = with_energy
+        ? KCALL(c, integrate_extrema_e1, r.P, F, scheme, cs, ds, (const double*)dw0, N, (const double*)dtg, ntimes, dt,
+                c.host ? 0 : 1, (double*)dfin, (double*)dst, block, c.stream)
+        : KCALL(c, integrate_extrema_e0, r.P, F, scheme, cs, ds, (const double*)dw0, N, (const double*)dtg, ntimes, dt,
+                c.host ? 0 : 1, (double*)dfin, (double*)dst, block, c.stream);
     if (e != cudaSuccess) return cuda_fail(e, "integrate_extrema launch");
     if (N) g_launches++;
     RET_IF(stage_out_copy_2d(c, stats, dst, GB_EXT_NSTAT, N, pitch));

@@ -86,6 +86,7 @@ struct ExtremaAcc {
 // func=None of Orbit.pericenter / apocenter / zmax: every refined extremum of one kind, in time order.  vals / times
 // are (kmax, N) (extremum k of orbit i at [k * N + i], NaN beyond the orbit's count); counts (N) holds the true
 // number, which may exceed kmax -- the caller then repeats with a larger kmax.
+#if GB_PART == 7          // not a template: defined in one translation unit only
 __global__ void k_trajectory_extrema_list(const double* __restrict__ w, const double* __restrict__ t, int ntimes, size_t N,
                                           int kind, int kmax, double* __restrict__ vals, double* __restrict__ times,
                                           int32_t* __restrict__ counts) {
@@ -107,6 +108,7 @@ __global__ void k_trajectory_extrema_list(const double* __restrict__ w, const do
     for (int k = found; k < kmax; k++) { vals[(size_t)k * N + i] = CUDART_NAN; times[(size_t)k * N + i] = CUDART_NAN; }
     counts[i] = found;
 }
+#endif
 
 // An existing trajectory w (6, ntimes, N) in device memory (e.g. the dense output of gb_dop853): one pass, reads are
 // coalesced across orbits (consecutive threads = consecutive orbits of one row).  ENERGY: also the Hamiltonian

@@ -31,7 +31,7 @@ namespace GB_NS {
 #if GB_PART == 6
 #include "lyapunov.cuh"
 #endif
-#if GB_PART == 7
+#if GB_PART == 7 || GB_PART == 8
 #include "extrema.cuh"
 #endif
 
@@ -506,36 +506,42 @@ cudaError_t nbody_dop853(const DevPot& P, const DevBodies& B, const Dop853Args& 
 #endif
 #endif  // GB_PART == 5 || 6
 
+#if GB_PART == 7 || GB_PART == 8
+// part 7 = the reductions without the Hamiltonian (ENERGY = false) + the extremum lists; part 8 = with it: two
+// translation units so that the 11 signatures x 3 schemes compile side by side
 #if GB_PART == 7
-cudaError_t trajectory_extrema(const DevPot& P, const DevFrame& F, const double* w, const double* t, int ntimes, size_t N,
-                               int with_energy, double* stats, int block, cudaStream_t s) {
+#define GB_EXT_ENERGY false
+#define GB_EXT_SUFFIX(name) name##_e0
+#else
+#define GB_EXT_ENERGY true
+#define GB_EXT_SUFFIX(name) name##_e1
+#endif
+cudaError_t GB_EXT_SUFFIX(trajectory_extrema)(const DevPot& P, const DevFrame& F, const double* w, const double* t, int ntimes,
+                                              size_t N, double* stats, int block, cudaStream_t s) {
     if (N == 0) return cudaSuccess;
-    if (with_energy) {
-        GB_SIG_SWITCH(P.sig, (k_trajectory_extrema<C, true><<<nblocks(N, block), block, 0, s>>>(P, F, w, t, ntimes, N, stats)));
-    } else {
-        GB_SIG_SWITCH(P.sig, (k_trajectory_extrema<C, false><<<nblocks(N, block), block, 0, s>>>(P, F, w, t, ntimes, N, stats)));
-    }
+    GB_SIG_SWITCH(P.sig, (k_trajectory_extrema<C, GB_EXT_ENERGY><<<nblocks(N, block), block, 0, s>>>(P, F, w, t, ntimes, N, stats)));
     return cudaGetLastError();
 }
+#if GB_PART == 7
 cudaError_t trajectory_extrema_list(const double* w, const double* t, int ntimes, size_t N, int kind, int kmax,
                                     double* vals, double* times, int32_t* counts, int block, cudaStream_t s) {
     if (N == 0) return cudaSuccess;
     k_trajectory_extrema_list<<<nblocks(N, block), block, 0, s>>>(w, t, ntimes, N, kind, kmax, vals, times, counts);
     return cudaGetLastError();
 }
-cudaError_t integrate_extrema(const DevPot& P, const DevFrame& F, int scheme, const double* cs, const double* ds,
-                              const double* w0, size_t N, const double* t, int ntimes, double dt, int dt_from_t,
-                              int with_energy, double* wfin, double* stats, int block, cudaStream_t s) {
+#endif
+cudaError_t GB_EXT_SUFFIX(integrate_extrema)(const DevPot& P, const DevFrame& F, int scheme, const double* cs, const double* ds,
+                                             const double* w0, size_t N, const double* t, int ntimes, double dt, int dt_from_t,
+                                             double* wfin, double* stats, int block, cudaStream_t s) {
     if (N == 0) return cudaSuccess;
     Ruth4CoefE K;
     for (int k = 0; k < 4; k++) { K.c[k] = cs[k]; K.d[k] = ds[k]; }
-#define GB_IE(SCH, EN) GB_SIG_SWITCH(P.sig, (k_integrate_extrema<C, SCH, EN><<<nblocks(N, block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads), block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads, 0, s>>>(P, F, K, w0, N, t, ntimes, dt, dt_from_t, wfin, stats)))
+#define GB_IE(SCH) GB_SIG_SWITCH(P.sig, (k_integrate_extrema<C, SCH, GB_EXT_ENERGY><<<nblocks(N, block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads), block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads, 0, s>>>(P, F, K, w0, N, t, ntimes, dt, dt_from_t, wfin, stats)))
     const int sch = scheme == 0 ? 0 : (F.type == GB_FRAME_STATIC ? 1 : 2);
-    if (with_energy) { if (sch == 0) { GB_IE(0, true); } else if (sch == 1) { GB_IE(1, true); } else { GB_IE(2, true); } }
-    else             { if (sch == 0) { GB_IE(0, false); } else if (sch == 1) { GB_IE(1, false); } else { GB_IE(2, false); } }
+    if (sch == 0) { GB_IE(0); } else if (sch == 1) { GB_IE(1); } else { GB_IE(2); }
 #undef GB_IE
     return cudaGetLastError();
 }
-#endif  // GB_PART == 7
+#endif  // GB_PART == 7 || 8
 
 }  // namespace GB_NS

@@ -85,16 +85,21 @@ struct Dop853Args {
                          const double* d0_vec, size_t N, const double* t, int n_steps, double d0,          \
                          int pullback, int noff, double* LEs, double* traj, int32_t* status,               \
                          cudaStream_t s);                                                                  \
-    cudaError_t trajectory_extrema(const DevPot& P, const DevFrame& F, const double* w, const double* t,   \
-                                   int ntimes, size_t N, int with_energy, double* stats, int block,        \
-                                   cudaStream_t s);                                                        \
+    cudaError_t trajectory_extrema_e0(const DevPot& P, const DevFrame& F, const double* w, const double* t, \
+                                      int ntimes, size_t N, double* stats, int block, cudaStream_t s);      \
+    cudaError_t trajectory_extrema_e1(const DevPot& P, const DevFrame& F, const double* w, const double* t, \
+                                      int ntimes, size_t N, double* stats, int block, cudaStream_t s);      \
     cudaError_t trajectory_extrema_list(const double* w, const double* t, int ntimes, size_t N, int kind,  \
                                         int kmax, double* vals, double* times, int32_t* counts, int block,  \
                                         cudaStream_t s);                                                    \
-    cudaError_t integrate_extrema(const DevPot& P, const DevFrame& F, int scheme, const double* cs,        \
-                                  const double* ds, const double* w0, size_t N, const double* t,           \
-                                  int ntimes, double dt, int dt_from_t, int with_energy, double* wfin,     \
-                                  double* stats, int block, cudaStream_t s);                               \
+    cudaError_t integrate_extrema_e0(const DevPot& P, const DevFrame& F, int scheme, const double* cs,     \
+                                     const double* ds, const double* w0, size_t N, const double* t,        \
+                                     int ntimes, double dt, int dt_from_t, double* wfin, double* stats,     \
+                                     int block, cudaStream_t s);                                            \
+    cudaError_t integrate_extrema_e1(const DevPot& P, const DevFrame& F, int scheme, const double* cs,     \
+                                     const double* ds, const double* w0, size_t N, const double* t,        \
+                                     int ntimes, double dt, int dt_from_t, double* wfin, double* stats,     \
+                                     int block, cudaStream_t s);                                            \
     cudaError_t fardal_release(const DevPot& P, double G, const double* prog_w, const double* prog_t,     \
                                const double* prog_m, int ntimes, const int32_t* prog_idx,                  \
                                const double* sign, const double* normals, int ncols, size_t Np, int kind, \
