@@ -120,6 +120,8 @@ SIGNATURES = {
     "gb_version": (C.c_char_p, []),
     "gb_fp64_peak_tflops": (C.c_double, [C.c_int]),
     "gb_release_scratch": (C.c_int, []),
+    "gb_shard_bounds": (C.c_int, [C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "gb_deal_count": (C.c_long, [C.c_size_t, C.c_int, C.c_int]),
     "gb_math_probe": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, P(gb_launch)]),
 }
 

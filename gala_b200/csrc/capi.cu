@@ -1800,4 +1800,16 @@ int gb_lyapunov_max(const gb_potential* pot, const gb_frame* fr, const double* w
     return 0;
 }
 
+// ---- the partition of a multi-device call, for callers and tests (host-only arithmetic) -----------------
+int gb_shard_bounds(size_t N, int k, int nd, size_t* lo, size_t* n) {
+    if (nd < 1 || k < 0 || k >= nd || !lo || !n) return fail(-12, "gb_shard_bounds: need 0 <= k < nd and output pointers");
+    slice_of(N, k, nd, lo, n);
+    return 0;
+}
+long gb_deal_count(size_t Np, int k, int nd) {
+    if (nd < 1 || k < 0 || k >= nd) return fail(-12, "gb_deal_count: need 0 <= k < nd");
+    Deal D; D.Np = Np; D.k = k; D.nd = nd;
+    return (long)D.count();
+}
+
 }  // extern "C"

@@ -350,6 +350,12 @@ const char* gb_version(void);
  * denominator bench.py reports against (MEASURED_PEAKS.json carries no FP64 figure). */
 double gb_fp64_peak_tflops(int reps);
 
+/* The partition a multi-device call uses (no device needed): orbit slice [*lo, *lo + *n) of device k of nd for N
+ * orbits (contiguous, sizes differ by at most one), and the number of mock-stream particles of device k when Np rows
+ * are dealt in groups of 128 consecutive rows, group g to device g mod nd.  Return -12 for k outside [0, nd). */
+int gb_shard_bounds(size_t N, int k, int nd, size_t* lo, size_t* n);
+long gb_deal_count(size_t Np, int k, int nd);
+
 /* Frees the device staging / scratch buffers the library keeps cached between calls (HOST-mode staging
  * of inputs and outputs; the orbit-major dense-output scratch of gb_dop853, up to half of the free
  * device memory; the device copies of SCF / multipole coefficient blocks and of the PowerLawCutoff

@@ -83,3 +83,28 @@ def test_nbody_host_validation():
     assert nb.n_massive == 1
     with pytest.raises(TypeError):
         gb.MockStreamGenerator(gb.FardalStreamDF(), gb.Hamiltonian(gb.MilkyWayPotential2022()), progenitor_potential=3.0)
+
+
+def test_multi_device_partition_rules():
+    """Host-only arithmetic of a multi-device call (gb_launch.n_devices): contiguous orbit slices whose sizes differ by
+    at most one and tile [0, N) exactly (== gala_b200.dist.shard_bounds), and the block-cyclic deal of mock-stream rows
+    (groups of 128, group g to device g mod nd)."""
+    from gala_b200.dist import shard_bounds
+    L = _abi.lib()
+    lo, n = ctypes.c_size_t(), ctypes.c_size_t()
+    for N in (0, 1, 7, 8, 9, 1003, 10_000_000):
+        for nd in (1, 2, 3, 8):
+            got = []
+            for k in range(nd):
+                assert L.gb_shard_bounds(N, k, nd, ctypes.byref(lo), ctypes.byref(n)) == 0
+                got.append((lo.value, lo.value + n.value))
+            assert got == shard_bounds(N, nd)
+            assert got[0][0] == 0 and got[-1][1] == N and all(a[1] == b[0] for a, b in zip(got, got[1:]))
+    assert L.gb_shard_bounds(10, 3, 3, ctypes.byref(lo), ctypes.byref(n)) == -12
+    for Np in (0, 1, 127, 128, 129, 1806, 100_020):
+        for nd in (1, 2, 3, 8):
+            counts = [L.gb_deal_count(Np, k, nd) for k in range(nd)]
+            groups = [list(range(g * 128, min((g + 1) * 128, Np))) for g in range((Np + 127) // 128)]
+            want = [sum(len(gr) for g, gr in enumerate(groups) if g % nd == k) for k in range(nd)]
+            assert counts == want and sum(counts) == Np
+    assert L.gb_deal_count(10, -1, 2) == -12
