@@ -167,3 +167,40 @@ def test_fewer_orbits_than_devices(mw, N):
     assert got_lf.shape == (6, 21, N) and np.array_equal(got_lf, ref_lf)
     assert np.array_equal(got_d8[1], ref_d8[1]) and np.array_equal(got_d8[2]["nstep"], ref_d8[2]["nstep"])
     assert st["w_final"].shape == (6, N) and st["n_peri"].shape == (N,)
+
+
+def test_concurrent_callers_share_the_scratch_safely(mw):
+    """host-buffer and device-buffer calls from several threads at once (staging slots, side streams, the
+    cached coefficient tables and the DOP853 scratch are per device and locked / pinned per call): every thread gets
+    the bits a lone caller gets."""
+    import threading
+    import torch
+    S = np.zeros((3, 3, 3)); S[0, 0, 0] = 1.0; S[1, 0, 0] = 0.05; S[2, 2, 1] = 0.02
+    scf = gb.SCFPotential(m=1e11, r_s=10.0, Snlm=S, Tnlm=np.zeros((3, 3, 3)))
+    Hs = gb.Hamiltonian(scf)
+    w0 = make_ic(lambda q: mw.potential.gradient(q), 70_000, 5)
+    ws = np.ascontiguousarray(w0[:, :3000])
+    t = np.arange(31.0)
+    jobs = [
+        lambda: gb.leapfrog_integrate_hamiltonian(mw, w0, t, save_all=0)[1],                 # chunk pipeline, side streams
+        lambda: gb.dop853_integrate_hamiltonian(mw, ws, t, save_all=1)[1],                   # dense scratch, status slot
+        lambda: gb.leapfrog_integrate_hamiltonian(Hs, ws, t, save_all=0)[1],                 # cached SCF table
+        lambda: gb.dop853_integrate_hamiltonian(mw, torch.as_tensor(ws, device="cuda"), t, save_all=0)[1].cpu().numpy(),
+    ]
+    want = [j() for j in jobs]
+    got = [[None] * 3 for _ in jobs]
+    errs = []
+
+    def worker(k):
+        try:
+            for rep in range(3):
+                got[k][rep] = jobs[k]()
+        except BaseException as e:      # noqa: BLE001
+            errs.append(e)
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(len(jobs))]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errs, errs
+    for k in range(len(jobs)):
+        for rep in range(3):
+            assert np.array_equal(got[k][rep], want[k], equal_nan=True), (k, rep)
