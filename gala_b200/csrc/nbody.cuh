@@ -27,7 +27,7 @@ static __device__ __noinline__ void gb_body_gradient(const DevBodies& B, int b, 
         const double Y = R[3] * sx + R[4] * sy + R[5] * sz;
         const double Z = R[6] * sx + R[7] * sy + R[8] * sz;
         double ax = 0., ay = 0., az = 0.;
-        gb_comp_gradient(B.type[c], &B.par[B.poff[c]], nullptr, X, Y, Z, ax, ay, az);
+        gb_comp_gradient<false>(B.type[c], &B.par[B.poff[c]], nullptr, X, Y, Z, ax, ay, az);      // body potentials are analytic only (capi.cu:resolve_bodies): the switch without SCF / multipole saves 2 KB of stack per lane
         fx += R[0] * ax + R[3] * ay + R[6] * az;
         fy += R[1] * ax + R[4] * ay + R[7] * az;
         fz += R[2] * ax + R[5] * ay + R[8] * az;
