@@ -61,43 +61,6 @@ int min_npar(int type) {
     }
 }
 
-// Host-derived constants of one component for the fast build (layout: gb_nderived() in
-// gb_device.cuh; consumers: the accum() functions of potentials.cuh).  Pure functions of the
-// parameter vector, evaluated once per call in IEEE double.
-void gb_derive(int type, const double* p, double* d) {
-    switch (type) {
-        case GB_POT_HERNQUIST: case GB_POT_KEPLER: case GB_POT_JAFFE: case GB_POT_KUZMIN:
-            d[0] = p[0] * p[1]; break;
-        case GB_POT_SATOH:
-            d[0] = p[0] * p[1]; d[1] = p[3] * p[3]; break;
-        case GB_POT_NFW_FLATTENED:      // a = b = 1 (flattenednfw_* ignore them, builtin_potentials.cpp:925-962)
-            d[0] = p[0] * p[1]; d[1] = 1. / p[2]; d[2] = 1.; d[3] = 1.; d[4] = 1. / (p[5] * p[5]); break;
-        case GB_POT_NFW_TRIAXIAL:
-            d[0] = p[0] * p[1]; d[1] = 1. / p[2]; d[2] = 1. / (p[3] * p[3]); d[3] = 1. / (p[4] * p[4]);
-            d[4] = 1. / (p[5] * p[5]); break;
-        case GB_POT_NFW_SPHERICAL:
-            d[0] = p[0] * p[1]; d[1] = 1. / p[2]; break;
-        case GB_POT_MIYAMOTONAGAI:
-            d[0] = p[0] * p[1]; d[1] = p[3] * p[3]; break;
-        case GB_POT_PLUMMER: case GB_POT_ISOCHRONE:
-            d[0] = p[0] * p[1]; d[1] = p[2] * p[2]; break;
-        case GB_POT_MN3:
-            for (int i = 0; i < 3; i++) { d[i] = p[0] * p[1 + 3 * i]; d[3 + i] = p[3 + 3 * i] * p[3 + 3 * i]; }
-            break;
-        case GB_POT_LONGMURALIBAR:
-            d[0] = p[0] * p[1]; d[1] = sin(p[5]); d[2] = cos(p[5]); d[3] = p[4] * p[4]; break;
-        case GB_POT_SCF:
-            d[0] = p[0] * p[3] / (p[4] * p[4]); d[1] = 1. / p[4]; break;
-        case GB_POT_LOGARITHMIC:
-            d[0] = p[1] * p[1]; d[1] = p[2] * p[2]; d[2] = 1. / (p[3] * p[3]); d[3] = 1. / (p[4] * p[4]);
-            d[4] = 1. / (p[5] * p[5]); d[5] = sin(p[6]); d[6] = cos(p[6]); break;
-        case GB_POT_POWERLAWCUTOFF:
-            d[0] = p[0] * p[1]; d[1] = lgamma(0.5 * (3. - p[2])); d[2] = 1. / (p[3] * p[3]); d[3] = 1. / p[3];
-            d[4] = 3. - p[2]; d[5] = -1.; break;     // d[5] = offset of the fit in ext (resolve()); < 0: no fit, use the series
-        default: break;
-    }
-}
-
 #define GB_SCF_NMAX_CONST 10
 #define GB_SCF_LMAX_CONST 6
 static_assert(GB_CEXT == 2 * (GB_SCF_NMAX_CONST + 1) * ((GB_SCF_LMAX_CONST + 1) * (GB_SCF_LMAX_CONST + 2) / 2), "cext layout");
@@ -502,8 +465,9 @@ int resolve(const gb_potential* pot, Resolved& r, cudaStream_t stream, bool allo
     if (P.sig == SIG_GENERIC && !getenv("GB_FORCE_GENERIC_HEAVY")) {
         bool heavy = false;
         for (int i = 0; i < P.n; i++) heavy |= (P.c[i].type == GB_POT_SCF || P.c[i].type == GB_POT_MULTIPOLE);
-        if (!heavy) P.sig = SIG_GENERIC_LIGHT;
+        if (!heavy) P.sig = P.time_dep ? SIG_GENERIC_TI : SIG_GENERIC_LIGHT;
     }
+    if (P.time_dep && P.sig != SIG_GENERIC && P.sig != SIG_GENERIC_TI) P.sig = SIG_GENERIC_TI;   // GB_FORCE_GENERIC_HEAVY etc.
     if (P.sig == SIG_SCF && !getenv("GB_SCF_NO_CONST")) {
         // small expansions also go to the constant bank in the fixed (10,6) layout of scf_fast_gradient
         const double* p = pot->comp[0].params;

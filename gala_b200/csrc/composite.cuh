@@ -109,7 +109,16 @@ GB_DEV void ti_gradient(const double* p, const double* e, double t, double x, do
     if (!ti_state(v, t, wp, o, R)) { gx = CUDART_NAN; gy = CUDART_NAN; gz = CUDART_NAN; return; }   // :148-155
     double X, Y, Z, ax = 0., ay = 0., az = 0.;
     ti_to_body(o, R, x, y, z, X, Y, Z);
+#if GB_STRICT
     gb_comp_gradient<false>(v.wtype, wp, nullptr, X, Y, Z, ax, ay, az);
+#else
+    // fast build: the wrapped potential's fused accumulation, its derived constants formed from the interpolated parameters
+    double dl[8];
+    gb_derive(v.wtype, wp, dl);
+    FastCtx<GB_USE_ALL> c2(X, Y, Z);
+    gb_comp_accum<false>(v.wtype, wp, dl, nullptr, c2);
+    c2.finish(ax, ay, az);
+#endif
     // grad += R^T grad_body (time_interp_wrapper.cpp:186-201)
     gx += R[0] * ax + R[3] * ay + R[6] * az;
     gy += R[1] * ax + R[4] * ay + R[7] * az;
@@ -127,11 +136,11 @@ GB_DEV double ti_scalar(const double* p, const double* e, double t, double x, do
 
 template <int SIG> struct Composite;
 
-template <bool HEAVY> struct CompositeGeneric {
+template <bool HEAVY, bool TI> struct CompositeGeneric {
     // the adaptive integrator evaluates the gradient at 15-17 sites per step: ONE out-of-line copy of this
     // loop-and-switch per kernel instead of 17 inlined ones (hamiltonian.cuh: ham_rhs)
     static constexpr bool kOutOfLineInRhs = true;
-    static constexpr bool kTimeDependent = true;      // may hold a TimeInterpolated component: the kernels pass real times
+    static constexpr bool kTimeDependent = TI;        // may hold a TimeInterpolated component: the kernels pass real times
     // __launch_bounds__ of k_leapfrog: the analytic-only loop is capped at 128 registers (4 CTAs of 128 per SM);
     // uncapped it grew from 124 to 140 registers as more fast accumulators were inlined (48 -> 59 ms for MW2022)
     static constexpr int kFixedStepMaxThreads = HEAVY ? 256 : 128, kFixedStepMinBlocks = HEAVY ? 1 : 4;
@@ -143,7 +152,7 @@ template <bool HEAVY> struct CompositeGeneric {
             const DevComp& c = P.c[i];
             const double* p = &P.par[c.poff];
             const double* e = P.ext + c.eoff;
-            if (c.type == GB_POT_TIMEINTERP) { ti_gradient(p, e, t, x, y, z, gx, gy, gz); continue; }
+            if constexpr (TI) { if (c.type == GB_POT_TIMEINTERP) { ti_gradient(p, e, t, x, y, z, gx, gy, gz); continue; } }
             if (!c.shift) {
                 gb_comp_gradient<HEAVY>(c.type, p, e, x, y, z, gx, gy, gz);
             } else {
@@ -166,7 +175,7 @@ template <bool HEAVY> struct CompositeGeneric {
             const double* p = &P.par[c.poff];
             const double* d = &P.drv[c.doff];
             const double* e = P.ext + c.eoff;
-            if (c.type == GB_POT_TIMEINTERP) { ti_gradient(p, e, t, x, y, z, ctx.gx, ctx.gy, ctx.gz); continue; }
+            if constexpr (TI) { if (c.type == GB_POT_TIMEINTERP) { ti_gradient(p, e, t, x, y, z, ctx.gx, ctx.gy, ctx.gz); continue; } }
             if (!c.shift) {
                 gb_comp_accum<HEAVY>(c.type, p, d, e, ctx);
             } else {
@@ -189,7 +198,7 @@ template <bool HEAVY> struct CompositeGeneric {
         for (int i = 0; i < P.n; i++) {
             const DevComp& c = P.c[i];
             double X = x, Y = y, Z = z;
-            if (c.type == GB_POT_TIMEINTERP) { v = v + ti_scalar<0>(&P.par[c.poff], P.ext + c.eoff, t, x, y, z); continue; }
+            if constexpr (TI) { if (c.type == GB_POT_TIMEINTERP) { v = v + ti_scalar<0>(&P.par[c.poff], P.ext + c.eoff, t, x, y, z); continue; } }
             if (c.shift) gb_shift_rotate(c, x, y, z, X, Y, Z);
             v = v + gb_comp_value<HEAVY>(c.type, &P.par[c.poff], P.ext + c.eoff, X, Y, Z);
         }
@@ -200,15 +209,16 @@ template <bool HEAVY> struct CompositeGeneric {
         for (int i = 0; i < P.n; i++) {
             const DevComp& c = P.c[i];
             double X = x, Y = y, Z = z;
-            if (c.type == GB_POT_TIMEINTERP) { v = v + ti_scalar<1>(&P.par[c.poff], P.ext + c.eoff, t, x, y, z); continue; }
+            if constexpr (TI) { if (c.type == GB_POT_TIMEINTERP) { v = v + ti_scalar<1>(&P.par[c.poff], P.ext + c.eoff, t, x, y, z); continue; } }
             if (c.shift) gb_shift_rotate(c, x, y, z, X, Y, Z);
             v = v + gb_comp_density<HEAVY>(c.type, &P.par[c.poff], P.ext + c.eoff, X, Y, Z);
         }
         return v;
     }
 };
-template <> struct Composite<SIG_GENERIC> : CompositeGeneric<true> {};
-template <> struct Composite<SIG_GENERIC_LIGHT> : CompositeGeneric<false> {};
+template <> struct Composite<SIG_GENERIC> : CompositeGeneric<true, true> {};
+template <> struct Composite<SIG_GENERIC_LIGHT> : CompositeGeneric<false, false> {};
+template <> struct Composite<SIG_GENERIC_TI> : CompositeGeneric<false, true> {};
 
 // ---- compile-time component lists ------------------------------------------------------------
 template <int OFF, int DOFF, int... Ts> struct SeqImpl;

@@ -80,6 +80,8 @@ enum GbSig {
     SIG_LM10,           // [MiyamotoNagai, Hernquist, Logarithmic]               LM10Potential (special.py:26-87)
     SIG_BOVY2014,       // [MiyamotoNagai, PowerLawCutoff, SphericalNFW]         BovyMWPotential2014 (special.py:274-347)
     SIG_GENERIC_LIGHT,  // any list of analytic components (no SCF / multipole): the generic loop at their register budget
+    SIG_GENERIC_TI,     // analytic components of which at least one is a TimeInterpolated wrapper: the light loop + the
+                        // interpolation code and real step times (kept out of SIG_GENERIC_LIGHT: it cost that loop 10 %)
     SIG_COUNT
 };
 
@@ -101,6 +103,50 @@ constexpr int gb_nderived(int type) {
          : (type == GB_POT_LOGARITHMIC) ? 7
          : 0;
 }
+
+#ifdef __CUDACC__
+#define GB_HD __host__ __device__ inline
+#else
+#define GB_HD inline
+#endif
+#include <math.h>
+// Derived constants of one component for the fast build (layout: gb_nderived() above; consumers: the accum()
+// functions of potentials.cuh).  Pure functions of the parameter vector: evaluated once per call on the host
+// (capi.cu:resolve), and per evaluation on the device for a TimeInterpolated component, whose parameters change with t.
+GB_HD void gb_derive(int type, const double* p, double* d) {
+    switch (type) {
+        case GB_POT_HERNQUIST: case GB_POT_KEPLER: case GB_POT_JAFFE: case GB_POT_KUZMIN:
+            d[0] = p[0] * p[1]; break;
+        case GB_POT_SATOH:
+            d[0] = p[0] * p[1]; d[1] = p[3] * p[3]; break;
+        case GB_POT_NFW_FLATTENED:      // a = b = 1 (flattenednfw_* ignore them, builtin_potentials.cpp:925-962)
+            d[0] = p[0] * p[1]; d[1] = 1. / p[2]; d[2] = 1.; d[3] = 1.; d[4] = 1. / (p[5] * p[5]); break;
+        case GB_POT_NFW_TRIAXIAL:
+            d[0] = p[0] * p[1]; d[1] = 1. / p[2]; d[2] = 1. / (p[3] * p[3]); d[3] = 1. / (p[4] * p[4]);
+            d[4] = 1. / (p[5] * p[5]); break;
+        case GB_POT_NFW_SPHERICAL:
+            d[0] = p[0] * p[1]; d[1] = 1. / p[2]; break;
+        case GB_POT_MIYAMOTONAGAI:
+            d[0] = p[0] * p[1]; d[1] = p[3] * p[3]; break;
+        case GB_POT_PLUMMER: case GB_POT_ISOCHRONE:
+            d[0] = p[0] * p[1]; d[1] = p[2] * p[2]; break;
+        case GB_POT_MN3:
+            for (int i = 0; i < 3; i++) { d[i] = p[0] * p[1 + 3 * i]; d[3 + i] = p[3 + 3 * i] * p[3 + 3 * i]; }
+            break;
+        case GB_POT_LONGMURALIBAR:
+            d[0] = p[0] * p[1]; d[1] = sin(p[5]); d[2] = cos(p[5]); d[3] = p[4] * p[4]; break;
+        case GB_POT_SCF:
+            d[0] = p[0] * p[3] / (p[4] * p[4]); d[1] = 1. / p[4]; break;
+        case GB_POT_LOGARITHMIC:
+            d[0] = p[1] * p[1]; d[1] = p[2] * p[2]; d[2] = 1. / (p[3] * p[3]); d[3] = 1. / (p[4] * p[4]);
+            d[4] = 1. / (p[5] * p[5]); d[5] = sin(p[6]); d[6] = cos(p[6]); break;
+        case GB_POT_POWERLAWCUTOFF:
+            d[0] = p[0] * p[1]; d[1] = lgamma(0.5 * (3. - p[2])); d[2] = 1. / (p[3] * p[3]); d[3] = 1. / p[3];
+            d[4] = 3. - p[2]; d[5] = -1.; break;     // d[5] = offset of the fit in ext (resolve()); < 0: no fit, use the series
+        default: break;
+    }
+}
+
 
 #ifdef __CUDACC__
 #define GB_DEV __device__ __forceinline__

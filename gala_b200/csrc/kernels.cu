@@ -199,6 +199,13 @@ k_ruth4(const __grid_constant__ DevPot P, const __grid_constant__ DevFrame F, co
 // ------------------------------------------------------------------------------------------------
 static inline unsigned nblocks(size_t N, int block) { return (unsigned)((N + block - 1) / block); }
 
+// the TimeInterpolated signature exists only where time reaches the potential (evaluation, fixed-step integrators,
+// DOP853, extrema: parts 1-3, 7, 8); capi.cu:resolve refuses time-dependent potentials for the other entry points
+#if GB_PART == 1 || GB_PART == 2 || GB_PART == 3 || GB_PART == 7 || GB_PART == 8
+#define GB_SIG_CASE_TI(CALL) case SIG_GENERIC_TI: { using C = Composite<SIG_GENERIC_TI>; CALL; } break;
+#else
+#define GB_SIG_CASE_TI(CALL)
+#endif
 #define GB_SIG_SWITCH(sig, CALL)                                  \
     switch (sig) {                                                \
         case SIG_NFW:        { using C = Composite<SIG_NFW>;        CALL; } break; \
@@ -211,6 +218,7 @@ static inline unsigned nblocks(size_t N, int block) { return (unsigned)((N + blo
         case SIG_LM10:       { using C = Composite<SIG_LM10>;       CALL; } break; \
         case SIG_BOVY2014:   { using C = Composite<SIG_BOVY2014>;   CALL; } break; \
         case SIG_GENERIC_LIGHT: { using C = Composite<SIG_GENERIC_LIGHT>; CALL; } break; \
+        GB_SIG_CASE_TI(CALL) \
         default:             { using C = Composite<SIG_GENERIC>;    CALL; } break; \
     }
 

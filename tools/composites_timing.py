@@ -9,7 +9,10 @@ from bench import make_ic
 
 cases = [("mw2022", gb.MilkyWayPotential2022()), ("mw_v1", gb.MilkyWayPotential()), ("lm10", gb.LM10Potential()),
          ("bovy2014", gb.BovyMWPotential2014()),
-         ("plummer+nfw (light generic)", gb.PlummerPotential(m=1e10, b=1.0) + gb.NFWPotential(m=6e11, r_s=16.0))]
+         ("plummer+nfw (light generic)", gb.PlummerPotential(m=1e10, b=1.0) + gb.NFWPotential(m=6e11, r_s=16.0)),
+         ("nfw + time-interpolated plummer", gb.NFWPotential(m=6e11, r_s=16.0) + gb.TimeInterpolatedPotential(
+             gb.PlummerPotential, np.linspace(0.0, 1000.0, 41), m=1e10 * np.linspace(1.0, 2.0, 41), b=1.0,
+             origin=np.stack([8 * np.cos(np.linspace(0, 6, 41)), 8 * np.sin(np.linspace(0, 6, 41)), np.zeros(41)], axis=1)))]
 for name, pot in cases:
     H = gb.Hamiltonian(pot)
     w0 = torch.as_tensor(make_ic(3031040, 1, lambda q: pot.gradient(q)), device="cuda")
