@@ -176,3 +176,91 @@ def test_rotating_bar_inertial_vs_rotating_frame(ref):
     assert np.abs(o_rot.w() - ref_rot).max() < 1e-6 and np.abs(o_in.w() - ref_in).max() < 1e-6
     print(f"\n[rotating bar] corotation radius {r:.4f} kpc; max |dx| {np.abs(x_r - o_rot.pos).max():.2e} kpc, "
           f"max |dv| {np.abs(v_r - o_rot.vel).max():.2e} kpc/Myr over {t.size} samples / {knots.size} knots")
+
+
+# ---- the reference's own tests of this class (tests/potential/potential/test_time_interpolated.py), on the GPU ----------
+_ALL = ["KeplerPotential", "HernquistPotential", "PlummerPotential", "IsochronePotential", "JaffePotential", "NFWPotential",
+        "MiyamotoNagaiPotential", "MN3ExponentialDiskPotential", "LongMuraliBarPotential", "StonePotential", "BurkertPotential",
+        "SatohPotential", "KuzminPotential", "LogarithmicPotential", "LeeSutoTriaxialNFWPotential", "PowerLawCutoffPotential"]
+
+
+@pytest.mark.parametrize("name", _ALL)
+def test_all_builtin_potentials_time_interpolated(name):
+    """test_time_interpolated.py:438-496: every builtin class, first parameter x linspace(1, 4) over 32 knots, the others 1:
+    equal to the static potential at t = 0, different at t = 50."""
+    cls = getattr(gb, name)
+    names = list(cls._param_names)
+    knots = np.linspace(0, 100, 32)
+    const = {names[0]: 1e10 if names[0] == "m" else 1.0}
+    timed = {names[0]: const[names[0]] * np.linspace(1.0, 4, knots.size)}
+    for n in names[1:]:
+        const[n] = timed[n] = 1.0
+    if name == "MN3ExponentialDiskPotential":
+        const["h_R"] = timed["h_R"] = 5.0
+        const["h_z"] = timed["h_z"] = 0.5
+    elif name == "StonePotential":
+        const["r_c"] = timed["r_c"] = 1.0
+        const["r_h"] = timed["r_h"] = 10.0
+    elif name == "PowerLawCutoffPotential":
+        const["alpha"] = timed["alpha"] = 1.0
+    elif name == "LeeSutoTriaxialNFWPotential":
+        const.update(a=1.0, b=0.9, c=0.8); timed.update(a=1.0, b=0.9, c=0.8)      # the class requires a >= b >= c
+    static = cls(**const)
+    tip = gb.TimeInterpolatedPotential(cls, knots, **timed)
+    x = np.array([[1.0], [0.0], [0.0]])
+    e0, e_t0, e_t50 = static.energy(x)[0], tip.energy(x, t=0.0)[0], tip.energy(x, t=50.0)[0]
+    assert np.isclose(e0, e_t0, rtol=1e-12, atol=0.0) and not np.isclose(e0, e_t50, rtol=1e-5, atol=0.0)
+    g0, g_t0 = static.gradient(x), tip.gradient(x, t=0.0)
+    assert np.allclose(g0, g_t0, rtol=1e-12, atol=1e-300)
+
+
+def test_mn3_time_interpolated_like_the_reference():
+    """TestMN3TimeInterpolated (test_time_interpolated.py:533-700): constant parameters match the static MN3 at 1e-10,
+    the end knots of a varying mass match the static potentials of those masses, the extra keyword positive_density is
+    handed to the wrapped class, and a composite's gradient does not depend on the order of its components."""
+    knots = np.linspace(0, 5000.0, 6)
+    kw = dict(h_R=3.0, h_z=0.28)
+    static = gb.MN3ExponentialDiskPotential(m=5e10, **kw)
+    tip = gb.TimeInterpolatedPotential(gb.MN3ExponentialDiskPotential, knots, m=5e10, **kw)
+    xyz = np.array([[8.0, 0.0, 0.0], [4.0, 0.0, 0.5]]).T.copy()
+    for func in ("energy", "gradient", "density"):
+        np.testing.assert_allclose(getattr(tip, func)(xyz, t=2500.0), getattr(static, func)(xyz), rtol=1e-10)
+    masses = np.linspace(3e10, 7e10, knots.size)
+    tip = gb.TimeInterpolatedPotential(gb.MN3ExponentialDiskPotential, knots, m=masses, **kw)
+    x1 = np.array([[8.0], [0.0], [0.0]])
+    for t, m in ((knots[0], masses[0]), (knots[-1], masses[-1])):
+        np.testing.assert_allclose(tip.energy(x1, t=t), gb.MN3ExponentialDiskPotential(m=m, **kw).energy(x1), rtol=1e-10)
+    mid = tip.energy(x1, t=2500.0)[0]
+    lo, hi = tip.energy(x1, t=knots[0])[0], tip.energy(x1, t=knots[-1])[0]
+    assert min(lo, hi) < mid < max(lo, hi)
+    s2 = gb.MN3ExponentialDiskPotential(m=5e10, positive_density=False, **kw)
+    t2 = gb.TimeInterpolatedPotential(gb.MN3ExponentialDiskPotential, knots, m=5e10, positive_density=False, **kw)
+    np.testing.assert_allclose(t2.energy(xyz, t=100.0), s2.energy(xyz), rtol=1e-10)
+    assert not np.allclose(s2.energy(xyz), static.energy(xyz))
+    halo = gb.NFWPotential(m=6e11, r_s=16.0)
+    a, b = gb.CCompositePotential(), gb.CCompositePotential()
+    a["disk"], a["halo"] = tip, halo
+    b["halo"], b["disk"] = halo, tip
+    np.testing.assert_allclose(a.gradient(xyz, t=1234.0), b.gradient(xyz, t=1234.0), rtol=1e-13)
+    assert not np.allclose(a.energy(xyz, t=0.0), a.energy(xyz, t=4000.0))
+    orbit = tip.integrate_orbit(np.array([8.0, 0.0, 0.1, 0.0, 0.2, 0.0]), dt=1.0, n_steps=1000)
+    assert np.isfinite(orbit.pos).all()
+
+
+def test_interpolation_accuracy_and_bounds():
+    """test_time_interpolated.py:162-186,222-247: a linearly varying mass is reproduced exactly between the knots by every
+    spline type that reproduces straight lines; NaN outside the knot range, finite on its closed ends."""
+    knots = np.linspace(0, 10, 11)
+    m = 1e10 * (1 + 0.1 * knots)
+    x = np.array([[8.0], [0.0], [0.0]])
+    for method in ("linear", "cspline", "akima", "steffen"):
+        tip = gb.TimeInterpolatedPotential(gb.KeplerPotential, knots, interpolation_method=method, m=m)
+        for t in (0.0, 2.5, 7.25, 10.0):
+            want = gb.KeplerPotential(m=1e10 * (1 + 0.1 * t)).energy(x)[0]
+            assert np.isclose(tip.energy(x, t=t)[0], want, rtol=1e-13), (method, t)
+        assert np.isnan(tip.energy(x, t=-0.1)[0]) and np.isnan(tip.energy(x, t=10.1)[0])
+        assert np.isnan(tip.gradient(x, t=11.0)).all() and np.isnan(tip.density(x, t=-5.0)).all()
+    with pytest.raises(ValueError):
+        gb.TimeInterpolatedPotential(gb.KeplerPotential, knots, m=m[:5])          # test_mismatched_parameter_length
+    with pytest.raises(ValueError):
+        gb.TimeInterpolatedPotential(gb.KeplerPotential, knots[::-1].copy(), m=m)
