@@ -7,7 +7,7 @@ All arithmetic runs in hand-written CUDA kernels behind the C ABI of ``include/g
 """
 from . import _abi
 from ._abi import set_devices, get_devices
-from .units import galactic, dimensionless, G_GALACTIC, KMS_TO_KPC_MYR
+from .units import galactic, dimensionless, solarsystem, G_GALACTIC, KMS_TO_KPC_MYR
 from .potential import *          # noqa: F401,F403
 from .frame import StaticFrame, ConstantRotatingFrame
 from .dynamics import PhaseSpacePosition, Orbit, MockStream

@@ -21,6 +21,8 @@ class UnitSystem:
 
 galactic = UnitSystem("galactic (kpc, Myr, Msun, rad)", G_GALACTIC)
 dimensionless = UnitSystem("dimensionless", 1.0)
+# au, yr, Msun (reference units.py ``solarsystem``): G = 6.6743e-11 m^3 kg^-1 s^-2 x 1.988409870698051e30 kg x (365.25 d)^2 / au^3
+solarsystem = UnitSystem("solarsystem (au, yr, Msun, rad)", 39.476926408897626)
 
 
 def strip(x, units=galactic):

@@ -127,3 +127,30 @@ def test_integrate_extrema_errors_and_devices():
         gb.integrate_extrema(H, w0, t, Integrator="dopri853")
     st = gb.integrate_extrema(H, w0 * np.array([[8.0], [0.0], [1.0], [0.0], [0.2], [0.0]]), np.arange(400) * 1.0, Integrator="ruth4")
     assert st["n_apo"].shape == (4,)
+
+
+def test_reference_orbit_tests_kepler():
+    """The reference's own tests of these methods (tests/dynamics/test_orbit.py:352-446): Kepler m = 1 in solar-system
+    units -- a circular orbit has |e| < 1e-3; for v = 1.5 pi au/yr the mean apocentre / pericentre sit at the roots of
+    2 (E - Phi(r)) - L^2 / r^2 to 1 %, and the individual values scatter by < 1e-4."""
+    import scipy.optimize as so
+    pot = gb.KeplerPotential(m=1.0, units=gb.solarsystem)
+    H = gb.Hamiltonian(pot)
+    w = H.integrate_orbit(np.array([1.0, 0.0, 0.0, 0.0, 2 * np.pi, 0.0]), dt=0.01, n_steps=10000, Integrator="dopri853")
+    assert abs(w.eccentricity()) < 1e-3
+    w = H.integrate_orbit(np.array([1.0, 0.0, 0.0, 0.0, 1.5 * np.pi, 0.0]), dt=0.01, n_steps=10000, Integrator="dopri853")
+    apo, per, zmax = w.apocenter(), w.pericenter(), w.zmax()
+    assert np.shape(apo) == () and np.shape(per) == () and np.shape(zmax) == () and apo > per
+    E = np.mean(w.energy())
+    L = np.mean(np.sqrt((np.cross(w.pos.T, w.vel.T) ** 2).sum(1)))
+    f = lambda r: 2 * (E - pot.energy(np.array([[r], [0.0], [0.0]]))[0]) - L ** 2 / r ** 2
+    assert np.isclose(apo, so.brentq(f, 0.9, 1.0), rtol=1e-2) and np.isclose(per, so.brentq(f, 0.3, 0.5), rtol=1e-2)
+    apos, pers = w.apocenter(func=None), w.pericenter(func=None)
+    for v in (apos, pers):
+        d = np.std(v) / np.mean(v)
+        assert 0 < d < 1e-4
+    # several orbits at once
+    w0 = np.array([[1.0, 0, 0, 0, 1.5 * np.pi, 0], [1.1, 0, 0, 0, 1.5 * np.pi, 0]]).T
+    w2 = H.integrate_orbit(w0, dt=0.01, n_steps=10000)
+    per2, apo2, ecc2 = w2.pericenter(), w2.apocenter(), w2.eccentricity()
+    assert per2.shape == (2,) and np.all(apo2 > per2) and np.all((ecc2 > 0) & (ecc2 < 1))
