@@ -30,6 +30,11 @@
  *              potential: NotImplementedError, potential/potential/core.py:572-575)
  * The N-body, snapshot and Lyapunov entry points (gb_nbody_*, gb_*_animate,
  * gb_lyapunov_max) take HOST buffers only.
+ *
+ * Several GPUs: gb_launch.n_devices / devices shard ONE HOST-buffer call over the listed devices inside the
+ * library (gb_gradient / gb_energy / gb_density, gb_hamiltonian_*, gb_leapfrog, gb_ruth4, gb_dop853,
+ * gb_integrate_extrema, gb_mockstream_dop853 / _leapfrog); the other entry points run on one device and
+ * return -12 when handed a device list.  gb_shard_bounds / gb_deal_count tell the partition.
  */
 #ifndef GALA_B200_H
 #define GALA_B200_H
