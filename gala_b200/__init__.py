@@ -10,7 +10,7 @@ from ._abi import set_devices, get_devices
 from .units import galactic, dimensionless, solarsystem, G_GALACTIC, KMS_TO_KPC_MYR
 from .potential import *          # noqa: F401,F403
 from .frame import StaticFrame, ConstantRotatingFrame
-from .dynamics import PhaseSpacePosition, Orbit, MockStream
+from .dynamics import PhaseSpacePosition, Orbit, MockStream, peak_to_peak_period
 from .integrate import (pinned_empty, parse_time_specification, LeapfrogIntegrator, Ruth4Integrator, DOPRI853Integrator,
                         leapfrog_integrate_hamiltonian, ruth4_integrate_hamiltonian,
                         dop853_integrate_hamiltonian, integrate_extrema, orbit_extrema, orbit_extrema_list)

@@ -6,11 +6,30 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["PhaseSpacePosition", "Orbit", "MockStream"]
+__all__ = ["PhaseSpacePosition", "Orbit", "MockStream", "peak_to_peak_period"]
 
 
 def _is_torch(x):
     return type(x).__module__.startswith("torch")
+
+
+def peak_to_peak_period(t, f, amplitude_threshold=1e-2):
+    """``gala.dynamics.util.peak_to_peak_period`` (``dynamics/util.py:15-69``): the mean of the mean spacing of the
+    interior local maxima and of the interior local minima of f(t) (wrap-around comparison, end points dropped);
+    NaN when the oscillation is smaller than ``amplitude_threshold``."""
+    from scipy.signal import argrelmax, argrelmin
+    t = np.asarray(t, dtype=np.float64)
+    f = np.asarray(f, dtype=np.float64)
+    last = len(f) - 1
+    max_ix = argrelmax(f, mode="wrap")[0]
+    max_ix = max_ix[(max_ix != 0) & (max_ix != last)]
+    min_ix = argrelmin(f, mode="wrap")[0]
+    min_ix = min_ix[(min_ix != 0) & (min_ix != last)]
+    if len(max_ix) < 2 or len(min_ix) < 2:       # no interior peak pair or trough pair: the reference's means are NaN
+        return np.nan
+    if abs(np.mean(f[max_ix]) - np.mean(f[min_ix])) < amplitude_threshold:
+        return np.nan
+    return np.mean([np.mean(np.diff(t[max_ix])), np.mean(np.diff(t[min_ix]))])
 
 
 class PhaseSpacePosition:
@@ -49,6 +68,26 @@ class PhaseSpacePosition:
             key = (key,)
         return self.__class__(pos=self.pos[(slice(None),) + key], vel=self.vel[(slice(None),) + key],
                               frame=self.frame)
+
+    # -- the per-point quantities of ``dynamics/core.py:652-740`` (plain array arithmetic: numpy or torch) --------
+    def kinetic_energy(self):
+        """0.5 |v|^2 per unit mass (``dynamics/core.py:652-665``)."""
+        return 0.5 * (self.vel * self.vel).sum(0)
+
+    def potential_energy(self, potential, t=0.0):
+        """Phi(pos) per unit mass, evaluated on the device (``dynamics/core.py:667-686``)."""
+        flat = self.pos.reshape(self.pos.shape[0], -1)
+        return potential.energy(flat, t).reshape(self.shape)
+
+    def angular_momentum(self):
+        """q x p per unit mass, shape (3, ...) (``dynamics/core.py:708-740``)."""
+        x, y, z = self.pos
+        vx, vy, vz = self.vel
+        L = [y * vz - z * vy, z * vx - x * vz, x * vy - y * vx]
+        if _is_torch(self.pos):
+            import torch
+            return torch.stack(L, dim=0)
+        return np.stack(L, axis=0)
 
 
 class Orbit(PhaseSpacePosition):
@@ -131,6 +170,73 @@ class Orbit(PhaseSpacePosition):
         """``Orbit.eccentricity`` (``dynamics/orbit.py:658-681``): (r_apo - r_per) / (r_apo + r_per) of the means."""
         ra, rp = self.apocenter(**kw), self.pericenter(**kw)
         return (ra - rp) / (ra + rp)
+
+    def potential_energy(self, potential=None, t=0.0):
+        """``Orbit.potential_energy`` (``dynamics/orbit.py:339-359``): the orbit's own potential unless one is given."""
+        if potential is None:
+            if self.hamiltonian is None:
+                raise ValueError("To compute the potential energy, a potential object must be provided!")
+            potential = self.hamiltonian.potential
+        return super().potential_energy(potential, t)
+
+    # -- circulation / period estimates (dynamics/orbit.py:683-871, dynamics/util.py:15-69) --------------------------
+    def circulation(self):
+        """``Orbit.circulation`` (``dynamics/orbit.py:736-792``): 1 for every axis about which the angular momentum
+        never changes sign (nor drops below 1e-13) after the first sample; shape (3,) or (3, norbits).  A reduction
+        over the time axis -- a device-resident trajectory is reduced where it is."""
+        L = self.angular_momentum()
+        single = L.ndim == 2
+        if single:
+            L = L[..., None]
+        if _is_torch(L):
+            import torch
+            flip = (torch.sign(L[:, :1]) != torch.sign(L[:, 1:])) | (L[:, 1:].abs() < 1e-13)
+            circ = (~flip.any(dim=1)).to(torch.int64).cpu().numpy()
+        else:
+            flip = (np.sign(L[:, :1]) != np.sign(L[:, 1:])) | (np.abs(L[:, 1:]) < 1e-13)
+            circ = (~flip.any(axis=1)).astype(int)
+        return circ.reshape(3) if single else circ
+
+    def align_circulation_with_z(self, circulation=None):
+        """``Orbit.align_circulation_with_z`` (``dynamics/orbit.py:794-871``): tube orbits about x or y get that
+        axis exchanged with z (positions and velocities); z-tubes and boxes are returned unchanged."""
+        circ = self.circulation() if circulation is None else np.asarray(circulation)
+        circ = circ.reshape(3, -1)
+        single = self.pos.ndim == 2
+        pos = self.pos[..., None] if single else self.pos
+        vel = self.vel[..., None] if single else self.vel
+        if circ.shape[1] != pos.shape[2]:
+            raise ValueError("Shape of 'circulation' array should match the shape of the position/velocity (minus "
+                             "the time axis).")
+        new_pos, new_vel = (a.clone() if _is_torch(a) else a.copy() for a in (pos, vel))
+        for n in range(pos.shape[2]):
+            if circ[2, n] == 1 or not circ[:, n].any():
+                continue
+            if circ[:, n].sum() > 1:
+                import warnings
+                warnings.warn("Circulation about multiple axes - are you sure the orbit has been integrated for long "
+                              "enough?")
+            ax = 0 if circ[0, n] == 1 else 1
+            for new, old in ((new_pos, pos), (new_vel, vel)):
+                new[ax, :, n] = old[2, :, n]
+                new[2, :, n] = old[ax, :, n]
+        return Orbit(pos=new_pos.reshape(self.pos.shape), vel=new_vel.reshape(self.vel.shape), t=self.t,
+                     hamiltonian=self.hamiltonian, frame=self.frame)
+
+    def estimate_period(self, components=("x", "y", "z")):
+        """``Orbit.estimate_period`` (``dynamics/orbit.py:683-730``): mean peak-to-peak / trough-to-trough spacing of
+        every requested component (``peak_to_peak_period``, ``dynamics/util.py:15-69``) as a dict of (norbits,)
+        arrays.  Besides x, y, z the cylindrical ``rho`` and ``phi`` of ``orbit.cylindrical.estimate_period()``
+        can be asked for by name.  Host-side analysis (scipy ``argrelmax``), like the reference."""
+        if self.t is None:
+            raise ValueError("To compute the period, a time array is needed. Specify a time array when creating this "
+                             "object.")
+        pos = self.pos.cpu().numpy() if _is_torch(self.pos) else self.pos
+        t = np.asarray(self.t.cpu().numpy() if _is_torch(self.t) else self.t, dtype=np.float64)
+        pos = pos.reshape(3, pos.shape[1], -1)
+        series = {"x": pos[0], "y": pos[1], "z": pos[2], "rho": np.hypot(pos[0], pos[1]),
+                  "phi": np.arctan2(pos[1], pos[0])}
+        return {k: np.array([peak_to_peak_period(t, series[k][:, n]) for n in range(pos.shape[2])]) for k in components}
 
     def energy(self, hamiltonian=None):
         """Hamiltonian value along the orbit, shape (ntimes[, norbits]) -- evaluated on the GPU."""

@@ -159,6 +159,24 @@ class PotentialBase:
     def __call__(self, q, t=0.0):
         return self.energy(q, t)
 
+    def mass_enclosed(self, q, t=0.0):
+        """``PotentialBase.mass_enclosed`` (core.py:649-723): r^2 |dPhi/dr| / G from a centred difference of the
+        potential along the radius with the reference's step h = 1e-3, negative for a negative ``m`` parameter.
+        Two batched energy evaluations on the device; numpy in -> numpy out, torch.cuda in -> stays on the device."""
+        h = 1e-3
+        r = (q * q).sum(0) ** 0.5
+        eps = h * q / r
+        diff = self.energy(q + eps, t) - self.energy(q - eps, t)
+        m = getattr(self, "parameters", {}).get("m", None)
+        sgn = -1.0 if (m is not None and np.ndim(m) == 0 and m < 0) else 1.0
+        return sgn * abs(r * r * diff / self.G / (2.0 * h))
+
+    def circular_velocity(self, q, t=0.0):
+        """``PotentialBase.circular_velocity`` (core.py:725-784): sqrt(r |grad Phi . rhat|), one batched gradient."""
+        r = (q * q).sum(0) ** 0.5
+        dPhi_dr = (self.gradient(q, t) * q / r).sum(0)
+        return (r * abs(dPhi_dr)) ** 0.5
+
     # -- orbit integration (core.py:1150-1184 -> Hamiltonian.integrate_orbit) --------------------
     def integrate_orbit(self, w0, Integrator=None, Integrator_kwargs=None, cython_if_possible=True,
                         save_all=True, **time_spec):

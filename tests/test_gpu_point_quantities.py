@@ -1,0 +1,146 @@
+"""`-m gpu`: the per-point callers either side of the gradient / energy kernels -- ``PotentialBase.mass_enclosed``
+(core.py:649-723), ``circular_velocity`` (core.py:725-784), ``PhaseSpacePosition.kinetic_energy / potential_energy /
+angular_momentum`` (dynamics/core.py:652-740) -- against the compiled reference's ``c_potential`` / ``c_gradient`` put
+through the same numpy arithmetic the reference's Python does, and against closed forms."""
+import numpy as np
+import pytest
+
+import gala_b200 as gb
+from conftest import make_ic
+
+pytestmark = pytest.mark.gpu
+G = gb.G_GALACTIC
+
+
+def _pots():
+    return {
+        "hernquist": gb.HernquistPotential(m=1e11, c=10.0),
+        "nfw": gb.NFWPotential(m=6e11, r_s=16.0),
+        "plummer": gb.PlummerPotential(m=1e10, b=1.0),
+        "mw2022": gb.MilkyWayPotential2022(),
+        "lm10": gb.LM10Potential(),
+        "kepler_negative": gb.KeplerPotential(m=-2e10),
+    }
+
+
+@pytest.mark.parametrize("name", list(_pots()))
+def test_mass_enclosed_and_circular_velocity_match_reference_arithmetic(ref, name):
+    pot = _pots()[name]
+    pot.strict_math = True
+    q = make_ic(lambda x: gb.MilkyWayPotential2022().gradient(x), 500, seed=4)[:3].copy()
+    r = np.sqrt((q * q).sum(0))
+    # core.py:703-716 with the reference's own c_potential
+    h = 1e-3
+    eps = h * q / r
+    diff = ref.energy(pot, np.ascontiguousarray(q + eps)) - ref.energy(pot, np.ascontiguousarray(q - eps))
+    want_m = np.abs(r * r * diff / pot.G / (2.0 * h)) * (-1.0 if name == "kepler_negative" else 1.0)
+    got_m = pot.mass_enclosed(q)
+    # a difference of two potentials 2e-3 kpc apart: relative rounding of Phi (1e-16) is amplified by Phi / (h dPhi/dr)
+    assert np.allclose(got_m, want_m, rtol=1e-9, atol=0), np.abs(got_m / want_m - 1).max()
+    # core.py:773-777 with the reference's own c_gradient
+    want_v = np.sqrt(r * np.abs((ref.gradient(pot, q) * q / r).sum(0)))
+    got_v = pot.circular_velocity(q)
+    assert np.allclose(got_v, want_v, rtol=1e-13, atol=0), np.abs(got_v / want_v - 1).max()
+
+
+def test_closed_forms_and_device_arrays():
+    torch = pytest.importorskip("torch")
+    m, c = 1e11, 10.0
+    pot = gb.HernquistPotential(m=m, c=c)
+    rng = np.random.default_rng(42)
+    R = rng.uniform(4, 10, 128)                                   # tests/dynamics/test_dynamics_core.py:378-387
+    q = R[None] * np.array([1.0, 0, 0])[:, None]
+    vc = pot.circular_velocity(q)
+    assert np.allclose(vc, np.sqrt(G * m * R) / (R + c), rtol=1e-13)
+    assert np.allclose(pot.mass_enclosed(q), m * R ** 2 / (R + c) ** 2, rtol=1e-6)     # centred difference, h = 1e-3
+    # torch.cuda in -> torch.cuda out, same numbers
+    qd = torch.as_tensor(q, device="cuda")
+    vd = pot.circular_velocity(qd)
+    md = pot.mass_enclosed(qd)
+    assert vd.is_cuda and md.is_cuda
+    assert np.allclose(vd.cpu().numpy(), vc, rtol=1e-14) and np.allclose(md.cpu().numpy(), pot.mass_enclosed(q), rtol=1e-9)
+    # NFWPotential.from_circular_velocity (builtin/core.py:743-775): v_c is the circular velocity AT r_ref = r_s
+    nfw = gb.NFWPotential.from_circular_velocity(v_c=0.2, r_s=20.0)
+    assert np.allclose(nfw.circular_velocity(np.array([[20.0], [0.0], [0.0]])), 0.2, rtol=1e-12)
+
+
+def test_phase_space_point_quantities(ref):
+    pot = gb.MilkyWayPotential2022()
+    pot.strict_math = True
+    w0 = make_ic(lambda x: pot.gradient(x), 128, seed=1)
+    w = gb.PhaseSpacePosition.from_w(w0)
+    L = w.angular_momentum()                                       # tests/dynamics/test_dynamics_core.py:366-376
+    assert L.shape == (3, 128)
+    assert np.allclose(L, np.cross(w0[:3].T, w0[3:].T).T, rtol=0, atol=1e-15)
+    T = w.kinetic_energy()
+    assert np.allclose(T, 0.5 * (w0[3:] ** 2).sum(0), rtol=1e-15)
+    U = w.potential_energy(pot)
+    assert np.allclose(U, ref.energy(pot, w0[:3].copy()), rtol=1e-14)
+    # the docstring example of angular_momentum (dynamics/core.py:725-733): 1 au, 2 pi au / yr -> Lz = 6.28318531
+    one = gb.PhaseSpacePosition(pos=[1.0, 0, 0], vel=[0, 2 * np.pi, 0])
+    assert np.allclose(one.angular_momentum(), [0, 0, 6.28318531], atol=1e-8)
+    # along an orbit: T + U is the Hamiltonian of the static frame, conserved by leapfrog to the scheme's order
+    H = gb.Hamiltonian(pot)
+    orbit = H.integrate_orbit(w0, dt=0.5, n_steps=400)
+    E = orbit.kinetic_energy() + orbit.potential_energy()
+    assert E.shape == (401, 128)
+    assert np.allclose(E, orbit.energy(), rtol=1e-13)
+    drift = np.abs(E / E[0] - 1).max(0)                           # per orbit; the worst ones pass the 70-pc nucleus at dt = 0.5
+    assert np.median(drift) < 1e-3 and drift.max() < 5e-2
+    with pytest.raises(ValueError):
+        gb.Orbit(orbit.pos, orbit.vel).potential_energy()
+
+
+def test_circulation_known_orbits_of_the_reference():
+    """tests/dynamics/test_orbit.py:484-522 (Binney & Tremaine 2008 fig. 3.8 / 3.9): a loop and a box orbit of a
+    flattened logarithmic potential at E = -0.337; also with the trajectory left on the device."""
+    torch = pytest.importorskip("torch")
+    pot = gb.LogarithmicPotential(v_c=1.0, r_h=0.14, q1=1.0, q2=0.9, q3=1.0)
+    E = -0.337
+    ws = []
+    for x, vx in zip([0.5, 0.0], [0.0, 1.5]):
+        vy = np.sqrt(2 * (E - pot.energy(np.array([[x], [0.0], [0.0]]))))[0]
+        ws.append([x, 0.0, 0.0, vx, vy, 0.0])
+    ws = np.ascontiguousarray(np.array(ws).T)
+    H = gb.Hamiltonian(pot)
+    orbit = H.integrate_orbit(ws, dt=0.05, n_steps=10000)
+    c1 = orbit[:, 0].circulation()
+    assert c1.shape == (3,) and c1.sum() == 1
+    c2 = orbit[:, 1].circulation()
+    assert c2.shape == (3,) and c2.sum() == 0
+    circ = orbit.circulation()
+    assert circ.shape == (3, 2) and np.array_equal(circ.sum(axis=0), [1, 0])
+    dev = H.integrate_orbit(torch.as_tensor(ws, device="cuda"), dt=0.05, n_steps=10000)
+    assert dev.pos.is_cuda and np.array_equal(dev.circulation(), circ)
+    aligned = dev.align_circulation_with_z()
+    assert aligned.pos.is_cuda and np.array_equal(aligned.circulation(), circ)       # already a z-tube and a box
+
+
+def test_estimate_period_docstring_case_and_kepler(ref):
+    """dynamics/orbit.py:697-712: MilkyWayPotential2022, w0 = [8, 0, 0, 0, 0.18, 0], dt = 1, 4000 leapfrog steps.  The
+    periods are means of integer peak spacings: the GPU trajectory must give EXACTLY what the compiled reference's
+    trajectory gives (175.86038961038963, 175.88419913419915, cylindrical 120.96875 Myr with this repo's G; the
+    docstring prints 176.02 / 176.07 / 121.09 -- 0.1 % away, a different parameter / constant set than the source).
+    tests/dynamics/test_orbit.py:472-482: three copies of a Kepler orbit in solar-system units through DOPRI853 --
+    here also checked against Kepler's third law."""
+    from gala_b200.dynamics import peak_to_peak_period
+    pot = gb.MilkyWayPotential2022()
+    w0 = np.array([8.0, 0, 0, 0, 0.18, 0])
+    orbit = pot.integrate_orbit(w0, dt=1.0, n_steps=4000)
+    T = orbit.estimate_period(components=("x", "y", "rho"))
+    wr = ref.leapfrog(pot, w0.reshape(6, 1), np.arange(4001.0), save_all=True)[:, :, 0]
+    want = {"x": peak_to_peak_period(orbit.t, wr[0]), "y": peak_to_peak_period(orbit.t, wr[1]),
+            "rho": peak_to_peak_period(orbit.t, np.hypot(wr[0], wr[1]))}
+    for k in want:
+        assert T[k][0] == want[k], (k, T[k], want[k])
+    assert np.allclose([want["x"], want["y"], want["rho"]], [175.86038961038963, 175.88419913419915, 120.96875], rtol=1e-14)
+    assert np.allclose([want["x"], want["y"], want["rho"]], [176.02380952380952, 176.07034632034632, 121.09375], rtol=2e-3)
+    kep = gb.KeplerPotential(m=1.0, units=gb.solarsystem)
+    w0 = np.tile(np.array([1.0, 0, 0, 0, 1.5 * np.pi, 0])[:, None], (1, 3))
+    w = gb.Hamiltonian(kep).integrate_orbit(w0, dt=0.01, n_steps=10000, Integrator=gb.DOPRI853Integrator)
+    P = w.estimate_period()
+    GM = kep.G * 1.0
+    a = -GM / (2 * (0.5 * (1.5 * np.pi) ** 2 - GM))
+    want = 2 * np.pi * np.sqrt(a ** 3 / GM)
+    assert P["x"].shape == (3,) and np.allclose(P["x"], want, rtol=1e-3) and np.allclose(P["y"], want, rtol=1e-3)
+    assert np.all(np.isnan(P["z"]))

@@ -301,3 +301,61 @@ def test_plugin_install_patches_the_names_gala_resolves(tmp_path, monkeypatch):
     finally:
         for m in [k for k in sys.modules if k == "gala" or k.startswith("gala.")]:
             del sys.modules[m]
+
+
+# -- Orbit analysis helpers that are plain array reductions (no kernel involved): the reference's own tests -----------
+def test_estimate_period_like_the_reference():
+    """tests/dynamics/test_orbit.py:449-469: R(t) = 1 + 0.25 sin(2 pi t / T_R), phi = 2 pi t."""
+    import gala_b200 as gb
+    ntimes = 16384
+    for true_T_R in (1.0, 2.0, 4.123):
+        t = np.linspace(0, 10.0, ntimes)
+        R = 0.25 * np.sin(2 * np.pi / true_T_R * t) + 1.0
+        phi = (2 * np.pi * t) % (2 * np.pi)
+        pos = np.zeros((3, ntimes))
+        pos[0] = R * np.cos(phi)
+        pos[1] = R * np.sin(phi)
+        orb = gb.Orbit(pos, np.zeros_like(pos), t=t)
+        T = orb.estimate_period()
+        assert set(T) == {"x", "y", "z"} and T["x"].shape == (1,)
+        T = orb.estimate_period(components=("rho", "phi"))
+        assert np.allclose(T["rho"], true_T_R, rtol=1e-3)
+        assert np.allclose(T["phi"], 1.0, rtol=1e-3)
+    with pytest.raises(ValueError):
+        gb.Orbit(pos, np.zeros_like(pos)).estimate_period()
+
+
+def test_align_circulation_like_the_reference():
+    """tests/dynamics/test_orbit.py:525-574: loops about x, y, z and a box."""
+    import gala_b200 as gb
+    t = np.linspace(0, 100, 1024)
+    w = np.zeros((6, 1024, 4))
+    w[1, :, 0] = np.cos(t); w[2, :, 0] = np.sin(t); w[4, :, 0] = -np.sin(t); w[5, :, 0] = np.cos(t)
+    w[0, :, 1] = -np.cos(t); w[2, :, 1] = np.sin(t); w[3, :, 1] = np.sin(t); w[5, :, 1] = np.cos(t)
+    w[0, :, 2] = np.cos(t); w[1, :, 2] = np.sin(t); w[3, :, 2] = -np.sin(t); w[4, :, 2] = np.cos(t)
+    w[0, :, 3] = np.cos(t); w[1, :, 3] = -np.cos(0.5 * t); w[2, :, 3] = np.cos(0.25 * t)
+    w[3, :, 3] = -np.sin(t); w[4, :, 3] = 0.5 * np.sin(0.5 * t); w[5, :, 3] = -0.25 * np.sin(0.25 * t)
+    for i in range(4):
+        orb = gb.Orbit.from_w(w[..., i], t=t)
+        assert orb.circulation().shape == (3,)
+        circ = orb.align_circulation_with_z().circulation()
+        if i == 3:
+            assert circ.sum() == 0
+        else:
+            assert circ[2] == 1
+    orb = gb.Orbit.from_w(w, t=t)
+    circ = orb.circulation()
+    assert circ.shape == (3, 4)
+    assert np.array_equal(circ, np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]]))
+    new_orb = orb.align_circulation_with_z()
+    new_circ = new_orb.circulation()
+    assert np.all(new_circ[2, :3] == 1) and np.all(new_circ[:, 3] == 0)
+    # the exchanged axes carry the other one's samples, the box is untouched
+    assert np.array_equal(new_orb.pos[2, :, 0], w[0, :, 0]) and np.array_equal(new_orb.pos[0, :, 0], w[2, :, 0])
+    assert np.array_equal(new_orb.pos[:, :, 3], w[:3, :, 3])
+    with pytest.raises(ValueError):
+        orb.align_circulation_with_z(circulation=np.ones((3, 2), dtype=int))
+    # PhaseSpacePosition point quantities on plain arrays
+    L = gb.PhaseSpacePosition.from_w(w[:, 5]).angular_momentum()
+    assert L.shape == (3, 4) and np.allclose(L[0, 0], 1.0) and np.allclose(L[2, 2], 1.0)
+    assert np.allclose(gb.PhaseSpacePosition.from_w(w[:, 5]).kinetic_energy()[:3], 0.5)
