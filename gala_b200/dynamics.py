@@ -79,6 +79,44 @@ class PhaseSpacePosition:
         flat = self.pos.reshape(self.pos.shape[0], -1)
         return potential.energy(flat, t).reshape(self.shape)
 
+    def guiding_radius(self, potential, t=0.0, xtol=1e-12, maxiter=60):
+        """``PhaseSpacePosition.guiding_radius`` (``dynamics/core.py:742-764``, ``_guiding_radius_helper`` ``:951-967``):
+        the cylindrical radius R_g at which a circular orbit in the z = 0 plane has this point's |L_z|, i.e. the root of
+        |L_z| - R v_circ(R).  The reference runs one scipy ``root`` (hybr, xtol 1e-5) per point, each iteration a
+        single-point ``circular_velocity`` call; here ALL points take secant steps together, one batched device gradient
+        per iteration, started like the reference from the point's own R.  Points that do not converge give NaN."""
+        tor = _is_torch(self.pos)
+        flat_p = self.pos.reshape(3, -1)
+        Lz = abs(self.angular_momentum()[2].reshape(-1))
+        R0 = (flat_p[0] * flat_p[0] + flat_p[1] * flat_p[1]) ** 0.5
+        if tor:
+            import torch
+            zeros, where, isfinite = torch.zeros_like, torch.where, torch.isfinite
+        else:
+            zeros, where, isfinite = np.zeros_like, np.where, np.isfinite
+
+        def resid(R):
+            q = zeros(flat_p)
+            q[0] = R
+            return Lz - R * potential.circular_velocity(q, t)
+
+        Ra, Rb = R0, R0 * 1.05
+        fa, fb = resid(Ra), resid(Rb)
+        done = zeros(R0) != 0
+        for _ in range(maxiter):
+            denom = fb - fa
+            ok = denom != 0
+            Rn = Rb - where(ok, fb * (Rb - Ra) / where(ok, denom, denom + 1), zeros(R0))
+            Rn = where(Rn > 0, Rn, 0.5 * Rb)                      # the root is a radius: never step across R = 0
+            Rn = where(done, Rb, Rn)                              # converged points stay where they are
+            done = done | (abs(Rn - Rb) <= xtol * abs(Rn))
+            Ra, fa, Rb = Rb, fb, Rn
+            if bool(done.all()):
+                break
+            fb = resid(Rb)
+        out = where(done & isfinite(Rb), Rb, Rb * float("nan"))
+        return out.reshape(self.shape)
+
     def angular_momentum(self):
         """q x p per unit mass, shape (3, ...) (``dynamics/core.py:708-740``)."""
         x, y, z = self.pos

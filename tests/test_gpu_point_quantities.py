@@ -144,3 +144,32 @@ def test_estimate_period_docstring_case_and_kepler(ref):
     want = 2 * np.pi * np.sqrt(a ** 3 / GM)
     assert P["x"].shape == (3,) and np.allclose(P["x"], want, rtol=1e-3) and np.allclose(P["y"], want, rtol=1e-3)
     assert np.all(np.isnan(P["z"]))
+
+
+def test_guiding_radius_like_the_reference():
+    """tests/dynamics/test_dynamics_core.py:378-394 through the device gradient, numpy and torch.cuda; the root is
+    checked against brentq on the closed-form Hernquist circular velocity, and in MilkyWayPotential2022 by
+    substituting it back: R_g v_circ(R_g) = |L_z|."""
+    torch = pytest.importorskip("torch")
+    from scipy.optimize import brentq
+    m, c = 1e11, 10.0
+    p = gb.HernquistPotential(m=m, c=c)
+    rng = np.random.default_rng(42)
+    R = rng.uniform(4, 10, 128)
+    xyz = R[None] * np.array([1.0, 0, 0])[:, None]
+    vc = p.circular_velocity(xyz)
+    vxyz = np.zeros((3, R.size))
+    vxyz[1] = rng.normal(vc / gb.KMS_TO_KPC_MYR, 15.0) * gb.KMS_TO_KPC_MYR
+    w0 = gb.PhaseSpacePosition(xyz, vxyz)
+    Rg = w0.guiding_radius(p)
+    assert np.all(Rg > 0) and np.all(Rg < 25)
+    want = np.array([brentq(lambda x: L - x * np.sqrt(G * m * x) / (x + c), 1e-3, 1e3, xtol=1e-14, rtol=1e-14)
+                     for L in np.abs(R * vxyz[1])])
+    assert np.allclose(Rg, want, rtol=1e-10)
+    Rg_d = gb.PhaseSpacePosition(torch.as_tensor(xyz, device="cuda"), torch.as_tensor(vxyz, device="cuda")).guiding_radius(p)
+    assert Rg_d.is_cuda and np.allclose(Rg_d.cpu().numpy(), Rg, rtol=1e-12)
+    mw = gb.MilkyWayPotential2022()
+    w = gb.PhaseSpacePosition.from_w(make_ic(lambda x: mw.gradient(x), 300, seed=2))
+    Rg = w.guiding_radius(mw)
+    q = np.zeros((3, 300)); q[0] = Rg
+    assert np.allclose(Rg * mw.circular_velocity(q), np.abs(w.angular_momentum()[2]), rtol=1e-10)

@@ -359,3 +359,39 @@ def test_align_circulation_like_the_reference():
     L = gb.PhaseSpacePosition.from_w(w[:, 5]).angular_momentum()
     assert L.shape == (3, 4) and np.allclose(L[0, 0], 1.0) and np.allclose(L[2, 2], 1.0)
     assert np.allclose(gb.PhaseSpacePosition.from_w(w[:, 5]).kinetic_energy()[:3], 0.5)
+
+
+def test_guiding_radius_batched_secant_against_brentq():
+    """tests/dynamics/test_dynamics_core.py:378-394 (Hernquist m = 1e11, c = 10; R in [4, 10] kpc; v_y ~ N(v_c, 15 km/s)):
+    the batched secant iteration of PhaseSpacePosition.guiding_radius against one scipy brentq per point, with the
+    closed-form circular velocity standing in for the device call (the GPU version of this test is in
+    test_gpu_point_quantities.py)."""
+    from scipy.optimize import brentq
+    import gala_b200 as gb
+    m, c, G = 1e11, 10.0, gb.G_GALACTIC
+
+    class Hern:
+        calls = 0
+
+        def circular_velocity(self, q, t=0.0):
+            Hern.calls += 1
+            r = np.sqrt((q * q).sum(0))
+            return np.sqrt(G * m * r) / (r + c)
+
+    rng = np.random.default_rng(42)
+    R = rng.uniform(4, 10, 128)
+    xyz = R[None] * np.array([1.0, 0, 0])[:, None]
+    vc = Hern().circular_velocity(xyz)
+    vxyz = np.zeros((3, R.size))
+    vxyz[1] = rng.normal(vc / gb.KMS_TO_KPC_MYR, 15.0) * gb.KMS_TO_KPC_MYR
+    w0 = gb.PhaseSpacePosition(xyz, vxyz)
+    Hern.calls = 0
+    Rg = w0.guiding_radius(Hern())
+    assert Rg.shape == (128,) and np.all(Rg > 0) and np.all(Rg < 25)
+    assert Hern.calls < 20                                        # a handful of BATCHED evaluations, not 128 root solves
+    Lz = np.abs(R * vxyz[1])
+    want = np.array([brentq(lambda x: L - x * np.sqrt(G * m * x) / (x + c), 1e-3, 1e3, xtol=1e-14, rtol=1e-14) for L in Lz])
+    assert np.allclose(Rg, want, rtol=1e-10)
+    # a point with L_z = 0 has no guiding radius other than 0: NaN or ~0, never an exception
+    z = gb.PhaseSpacePosition([[5.0], [0.0], [0.0]], [[0.1], [0.0], [0.0]]).guiding_radius(Hern())
+    assert z.shape == (1,) and (np.isnan(z[0]) or z[0] < 1e-6)
