@@ -9,7 +9,8 @@ from . import _abi
 from ._abi import set_devices, get_devices
 from .units import galactic, dimensionless, solarsystem, G_GALACTIC, KMS_TO_KPC_MYR
 from .potential import *          # noqa: F401,F403
-from .frame import StaticFrame, ConstantRotatingFrame
+from .frame import (StaticFrame, ConstantRotatingFrame, static_to_constantrotating, constantrotating_to_static,
+                    static_to_static)
 from .dynamics import PhaseSpacePosition, Orbit, MockStream, peak_to_peak_period
 from .integrate import (pinned_empty, parse_time_specification, LeapfrogIntegrator, Ruth4Integrator, DOPRI853Integrator,
                         leapfrog_integrate_hamiltonian, ruth4_integrate_hamiltonian,

@@ -69,6 +69,22 @@ class PhaseSpacePosition:
         return self.__class__(pos=self.pos[(slice(None),) + key], vel=self.vel[(slice(None),) + key],
                               frame=self.frame)
 
+    def to_frame(self, frame, current_frame=None, **kwargs):
+        """``PhaseSpacePosition.to_frame`` (``dynamics/core.py:380-429``): static <-> constant-rotating; needs ``t=``."""
+        from . import frame as frame_trans
+        if self.frame is None and current_frame is None:
+            raise ValueError(f"If no frame was specified when this {self} was initialized, you must pass the current "
+                             "frame in via the current_frame argument to transform to a new frame.")
+        if current_frame is None:
+            current_frame = self.frame
+        name1 = current_frame.__class__.__name__.rstrip("Frame").lower()
+        name2 = frame.__class__.__name__.rstrip("Frame").lower()
+        func = getattr(frame_trans, f"{name1}_to_{name2}", None)
+        if func is None:
+            raise ValueError(f"Unsupported frame transformation: {current_frame} to {frame}")
+        pos, vel = func(current_frame, frame, self, **kwargs)
+        return PhaseSpacePosition(pos=pos, vel=vel, frame=frame)
+
     # -- the per-point quantities of ``dynamics/core.py:652-740`` (plain array arithmetic: numpy or torch) --------
     def kinetic_energy(self):
         """0.5 |v|^2 per unit mass (``dynamics/core.py:652-665``)."""
@@ -216,6 +232,17 @@ class Orbit(PhaseSpacePosition):
                 raise ValueError("To compute the potential energy, a potential object must be provided!")
             potential = self.hamiltonian.potential
         return super().potential_energy(potential, t)
+
+    def to_frame(self, frame, current_frame=None, **kwargs):
+        """``Orbit.to_frame`` (``dynamics/orbit.py:1256-1296``): the orbit's own time grid is the default ``t``."""
+        if current_frame is None:
+            current_frame = self.frame
+        if current_frame is not None and frame == current_frame and not kwargs:
+            return self
+        kw = dict(kwargs)
+        kw.setdefault("t", self.t)
+        psp = PhaseSpacePosition.to_frame(self, frame, current_frame, **kw)
+        return Orbit(pos=psp.pos, vel=psp.vel, t=self.t, hamiltonian=self.hamiltonian, frame=frame)
 
     # -- circulation / period estimates (dynamics/orbit.py:683-871, dynamics/util.py:15-69) --------------------------
     def circulation(self):

@@ -395,3 +395,40 @@ def test_guiding_radius_batched_secant_against_brentq():
     # a point with L_z = 0 has no guiding radius other than 0: NaN or ~0, never an exception
     z = gb.PhaseSpacePosition([[5.0], [0.0], [0.0]], [[0.1], [0.0], [0.0]]).guiding_radius(Hern())
     assert z.shape == (1,) and (np.isnan(z[0]) or z[0] < 1e-6)
+
+
+def test_frame_transform_like_the_reference():
+    """tests/dynamics/test_orbit.py:576-603 + the arithmetic of potential/frame/builtin/transformations.py:98-150
+    against scipy's Rotation: static -> rotating turns positions and velocities by -Omega t."""
+    from scipy.spatial.transform import Rotation
+    import gala_b200 as gb
+    static = gb.StaticFrame()
+    Om = np.array([0.53, 1.241, 0.9394])
+    rotating = gb.ConstantRotatingFrame(Omega=Om)
+    rng = np.random.default_rng(5)
+    x = rng.random((3, 10)); v = rng.random((3, 10))
+    t = np.linspace(0, 1, 10)
+    o = gb.Orbit(pos=x, vel=v, t=t)
+    with pytest.raises(ValueError):
+        o.to_frame(rotating)                                      # no frame specified at init
+    a = o.to_frame(rotating, current_frame=static, t=o.t)
+    b = o.to_frame(rotating, current_frame=static)
+    assert np.array_equal(a.pos, b.pos) and a.frame is rotating and isinstance(b, gb.Orbit)
+    o = gb.Orbit(pos=x, vel=v, t=t, frame=static)
+    assert np.array_equal(o.to_frame(rotating).pos, a.pos) and np.array_equal(o.to_frame(rotating, t=o.t).vel, a.vel)
+    assert o.to_frame(static) is o
+    for j in range(10):
+        Rm = Rotation.from_rotvec(-Om * t[j]).as_matrix()
+        assert np.allclose(a.pos[:, j], Rm @ x[:, j], atol=1e-15) and np.allclose(a.vel[:, j], Rm @ v[:, j], atol=1e-15)
+    back = a.to_frame(static)
+    assert np.allclose(back.pos, x, atol=1e-15) and np.allclose(back.vel, v, atol=1e-15)
+    # several orbits: the angle follows the time axis; a PhaseSpacePosition needs t
+    x3 = rng.random((3, 10, 4)); v3 = rng.random((3, 10, 4))
+    o3 = gb.Orbit(pos=x3, vel=v3, t=t, frame=static).to_frame(rotating)
+    for n in range(4):
+        assert np.allclose(o3.pos[:, :, n], gb.Orbit(pos=x3[:, :, n], vel=v3[:, :, n], t=t, frame=static).to_frame(rotating).pos)
+    p = gb.PhaseSpacePosition(x, v, frame=static)
+    with pytest.raises(ValueError):
+        p.to_frame(rotating)
+    assert np.allclose(p.to_frame(rotating, t=t).pos, a.pos) and np.allclose(p.to_frame(rotating, t=0.5).pos[:, 0],
+                                                                            Rotation.from_rotvec(-Om * 0.5).as_matrix() @ x[:, 0])
