@@ -11,7 +11,7 @@ from .units import galactic, dimensionless, solarsystem, G_GALACTIC, KMS_TO_KPC_
 from .potential import *          # noqa: F401,F403
 from .frame import (StaticFrame, ConstantRotatingFrame, static_to_constantrotating, constantrotating_to_static,
                     static_to_static)
-from .dynamics import PhaseSpacePosition, Orbit, MockStream, peak_to_peak_period
+from .dynamics import PhaseSpacePosition, Orbit, MockStream, peak_to_peak_period, estimate_dt_n_steps, combine
 from .integrate import (pinned_empty, parse_time_specification, LeapfrogIntegrator, Ruth4Integrator, DOPRI853Integrator,
                         leapfrog_integrate_hamiltonian, ruth4_integrate_hamiltonian,
                         dop853_integrate_hamiltonian, integrate_extrema, orbit_extrema, orbit_extrema_list)
@@ -19,6 +19,6 @@ from .hamiltonian import Hamiltonian
 from .mockstream import (BaseStreamDF, FardalStreamDF, StreaklineStreamDF, LagrangeCloudStreamDF, ChenStreamDF,
                          MockStreamGenerator, DirectNBody, mockstream_dop853, mockstream_leapfrog)
 
-from .nonlinear import fast_lyapunov_max
+from .nonlinear import fast_lyapunov_max, surface_of_section
 
 __version__ = "0.2.0"

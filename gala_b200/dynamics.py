@@ -6,7 +6,8 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["PhaseSpacePosition", "Orbit", "MockStream", "peak_to_peak_period"]
+__all__ = ["PhaseSpacePosition", "Orbit", "MockStream", "peak_to_peak_period", "estimate_dt_n_steps",
+           "combine"]
 
 
 def _is_torch(x):
@@ -292,7 +293,7 @@ class Orbit(PhaseSpacePosition):
         """``Orbit.estimate_period`` (``dynamics/orbit.py:683-730``): mean peak-to-peak / trough-to-trough spacing of
         every requested component (``peak_to_peak_period``, ``dynamics/util.py:15-69``) as a dict of (norbits,)
         arrays.  Besides x, y, z the cylindrical ``rho`` and ``phi`` of ``orbit.cylindrical.estimate_period()``
-        can be asked for by name.  Host-side analysis (scipy ``argrelmax``), like the reference."""
+        and the spherical ``r`` of ``orbit.physicsspherical`` can be asked for by name.  Host-side analysis (scipy ``argrelmax``), like the reference."""
         if self.t is None:
             raise ValueError("To compute the period, a time array is needed. Specify a time array when creating this "
                              "object.")
@@ -300,7 +301,7 @@ class Orbit(PhaseSpacePosition):
         t = np.asarray(self.t.cpu().numpy() if _is_torch(self.t) else self.t, dtype=np.float64)
         pos = pos.reshape(3, pos.shape[1], -1)
         series = {"x": pos[0], "y": pos[1], "z": pos[2], "rho": np.hypot(pos[0], pos[1]),
-                  "phi": np.arctan2(pos[1], pos[0])}
+                  "phi": np.arctan2(pos[1], pos[0]), "r": np.sqrt((pos * pos).sum(0))}
         return {k: np.array([peak_to_peak_period(t, series[k][:, n]) for n in range(pos.shape[2])]) for k in components}
 
     def energy(self, hamiltonian=None):
@@ -320,3 +321,87 @@ class MockStream(PhaseSpacePosition):
         super().__init__(pos, vel, frame=frame)
         self.release_time = release_time
         self.lead_trail = lead_trail
+
+
+def _autodetermine_initial_dt(w0, H, dE_threshold=1e-9, **integrate_kwargs):
+    """``dynamics/util.py:72-93``: the largest dt of logspace(1, -3, 8) whose 1000-time-unit test orbit keeps
+    |E_last - E_first| / |E_first| below the threshold (the smallest one if none does)."""
+    if w0.shape and w0.shape[0] > 1:
+        raise ValueError("Only one set of initial conditions may be passed in at a time.")
+    if dE_threshold is None:
+        return 1.0
+    for dt in np.logspace(-3, 1, 8)[::-1]:
+        orbit = H.integrate_orbit(w0, dt=dt, n_steps=round(1000 / dt), **integrate_kwargs)
+        E = orbit.energy()
+        if abs(float((E[-1] - E[0]) / E[0])) < dE_threshold:
+            break
+    return float(dt)
+
+
+def estimate_dt_n_steps(w0, hamiltonian, n_periods, n_steps_per_period, dE_threshold=1e-9, func=np.nanmax,
+                        **integrate_kwargs):
+    """``gala.dynamics.util.estimate_dt_n_steps`` (``dynamics/util.py:96-207``): a test orbit (10000 time units at
+    the dt of ``_autodetermine_initial_dt``) gives the periods -- cylindrical ones after aligning a tube orbit with
+    z, Cartesian ones for a box -- ``func`` picks one, and (dt, n_steps) sample ``n_periods`` of it with
+    ``n_steps_per_period`` steps each.  Every integration runs on the device; the period analysis is host-side."""
+    from .hamiltonian import Hamiltonian
+    if not isinstance(w0, PhaseSpacePosition):
+        w0 = PhaseSpacePosition.from_w(np.asarray(w0, dtype=np.float64))
+    H = hamiltonian if isinstance(hamiltonian, Hamiltonian) else Hamiltonian(hamiltonian)
+    dt = _autodetermine_initial_dt(w0, H, dE_threshold=dE_threshold, **integrate_kwargs)
+    orbit = H.integrate_orbit(w0, dt=dt, n_steps=round(10000 / dt), **integrate_kwargs)
+    circ = orbit.circulation()
+    if np.any(circ):
+        orbit = orbit.align_circulation_with_z(circulation=circ)
+        names = ("rho", "phi", "z")
+    else:
+        names = ("x", "y", "z")
+    per = orbit.estimate_period(components=names)
+    T = func(np.array([per[k][0] for k in names]))
+    if np.isnan(T):
+        raise RuntimeError("Failed to find period.")
+    dt = float(T) / float(n_steps_per_period)
+    n_steps = round(n_periods * float(T) / dt)
+    if dt == 0.0 or dt < 1e-13:
+        raise ValueError("Timestep is zero or very small!")
+    return dt, n_steps
+
+
+def combine(objs):
+    """``gala.dynamics.combine`` (``dynamics/util.py:209-350``): several PhaseSpacePosition objects -> one with the
+    points side by side, several Orbit objects on the same time grid -> one with the orbits side by side (the way a
+    batch of initial conditions or of results is assembled for one device call).  Same type, ndim, frame and -- for
+    orbits -- hamiltonian and time array are required; numpy or torch arrays."""
+    if isinstance(objs, PhaseSpacePosition) or not np.iterable(objs) or len(objs) < 1:
+        raise ValueError("You must pass a non-empty iterable to combine.")
+    if len(objs) == 1:
+        return objs[0]
+    first = objs[0]
+    if first.__class__ not in (PhaseSpacePosition, Orbit):
+        raise TypeError("Objects must be either PhaseSpacePosition or Orbit instances.")
+    for obj in objs:
+        if obj.__class__ != first.__class__:
+            raise TypeError("All objects must have the same type.")
+        if obj.ndim != first.ndim:
+            raise ValueError("All objects must have the same ndim.")
+        if obj.frame != first.frame:
+            raise ValueError("All objects must have the same frame.")
+        if isinstance(obj, Orbit):
+            if obj.hamiltonian is not first.hamiltonian:
+                raise ValueError("All objects must have the same potential.")
+            if obj.t is not None and first.t is not None and not (
+                    len(obj.t) == len(first.t) and bool(abs(obj.t - first.t).max() <= 1e-13)):
+                raise ValueError("All orbits must have the same time array.")
+    axis = 1 if first.__class__ is PhaseSpacePosition else 2
+
+    def cat(arrs):
+        arrs = [a[..., None] if a.ndim == axis else a for a in arrs]
+        if _is_torch(arrs[0]):
+            import torch
+            return torch.cat(arrs, dim=axis)
+        return np.concatenate(arrs, axis=axis)
+
+    pos, vel = cat([o.pos for o in objs]), cat([o.vel for o in objs])
+    if first.__class__ is PhaseSpacePosition:
+        return PhaseSpacePosition(pos=pos, vel=vel, frame=first.frame)
+    return Orbit(pos=pos, vel=vel, t=first.t, hamiltonian=first.hamiltonian, frame=first.frame)

@@ -12,7 +12,7 @@ from .dynamics import Orbit, PhaseSpacePosition
 from .hamiltonian import Hamiltonian
 from .units import strip
 
-__all__ = ["fast_lyapunov_max"]
+__all__ = ["fast_lyapunov_max", "surface_of_section"]
 
 
 def fast_lyapunov_max(w0, hamiltonian, dt, n_steps, d0=1e-5, n_steps_per_pullback=10, noffset_orbits=2, t1=0.0,
@@ -69,3 +69,25 @@ def fast_lyapunov_max(w0, hamiltonian, dt, n_steps, d0=1e-5, n_steps_per_pullbac
     else:
         ww = ww.reshape(6, nst, -1)
     return LEs, Orbit.from_w(np.ascontiguousarray(ww), t=t, hamiltonian=H)
+
+
+def surface_of_section(orbit, constant_idx, constant_val=0.0):
+    """``gala.dynamics.nonlinear.surface_of_section`` (``dynamics/nonlinear.py:293-340``): the samples of the orbit
+    closest to the plane ``w[constant_idx] = constant_val`` (local minima of the squared distance) that cross it with
+    positive conjugate momentum, as an ``Orbit`` of those samples.  One orbit per call like the reference; for an
+    orbit array a list with one section per orbit is returned (the sections have different lengths).  Host-side
+    analysis of a trajectory (a device-resident one is copied to the host first)."""
+    from scipy.signal import argrelmin
+    w = orbit.w()
+    if type(w).__module__.startswith("torch"):
+        w = w.cpu().numpy()
+    ndim = w.shape[0] // 2
+
+    def one(wn):
+        cross = argrelmin((wn[constant_idx] - constant_val) ** 2)[0]
+        cross = cross[wn[constant_idx + ndim][cross] > 0.0]
+        return Orbit(pos=wn[:ndim, cross], vel=wn[ndim:, cross])
+
+    if w.ndim == 2:
+        return one(w)
+    return [one(w[:, :, n]) for n in range(w.shape[2])]

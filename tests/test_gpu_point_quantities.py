@@ -207,3 +207,36 @@ def test_rotating_frame_orbit_transforms_back_to_the_static_one():
     o_d = gb.Hamiltonian(pot, rotating).integrate_orbit(torch.as_tensor(w0, device="cuda"), t=t, Integrator=gb.DOPRI853Integrator)
     back_d = o_d.to_frame(static)
     assert back_d.pos.is_cuda and np.allclose(back_d.pos.cpu().numpy(), back.pos, rtol=0, atol=1e-12)
+
+
+def test_estimate_dt_n_steps_like_the_reference():
+    """tests/dynamics/test_dynamics_util.py:34-48: NFW from v_c = 1 at r_s = 10, w0 = [10, 0, 0, 0, 0.9, 0]; the
+    recommended (dt, n_steps) covers exactly the requested 128 radial periods."""
+    nperiods = 128
+    pot = gb.NFWPotential.from_circular_velocity(v_c=1.0, r_s=10.0)
+    w0 = [10.0, 0.0, 0.0, 0.0, 0.9, 0.0]
+    H = gb.Hamiltonian(pot)
+    dt, n_steps = gb.estimate_dt_n_steps(w0, H, n_periods=nperiods, n_steps_per_period=256, func=np.nanmin)
+    assert n_steps == nperiods * 256
+    orbit = H.integrate_orbit(np.array(w0), dt=dt, n_steps=n_steps)
+    T = orbit.estimate_period(components=("r",))["r"]
+    assert int(np.squeeze(np.round(orbit.t.max() / T))) == nperiods
+    # a potential instead of a Hamiltonian, and no energy criterion (dt = 1 test orbit)
+    dt2, n2 = gb.estimate_dt_n_steps(w0, pot, n_periods=4, n_steps_per_period=100, dE_threshold=None, func=np.nanmin)
+    assert n2 == 400 and abs(dt2 * 100 / (dt * 256) - 1) < 2e-2          # the same period from either test orbit
+
+
+def test_surface_of_section_like_the_reference():
+    """tests/dynamics/test_nonlinear.py:312-320: triaxial logarithmic potential, one orbit, section y = 0 with
+    p_y > 0; every recorded sample is the closest one to the plane on its crossing."""
+    pot = gb.LogarithmicPotential(v_c=1.0, r_h=1.0, q1=1.0, q2=0.9, q3=0.8)
+    w0 = np.array([0.0, 0.8, 0.0, 1.0, 0.0, 0.0])
+    H = gb.Hamiltonian(pot)
+    orbit = H.integrate_orbit(w0, dt=0.02, n_steps=100_000)
+    sos = gb.surface_of_section(orbit, constant_idx=1)
+    n = sos.pos.shape[1]
+    assert sos.pos.shape == (3, n) and n > 100
+    assert np.all(sos.vel[1] > 0) and np.abs(sos.pos[1]).max() < 0.02 * np.abs(orbit.vel[1]).max()
+    many = H.integrate_orbit(np.stack([w0, w0 * np.array([1, 1.1, 1, 1, 1, 1])], axis=1), dt=0.02, n_steps=20_000)
+    secs = gb.surface_of_section(many, constant_idx=1)
+    assert len(secs) == 2 and np.array_equal(secs[0].pos, gb.surface_of_section(many[:, 0], constant_idx=1).pos)

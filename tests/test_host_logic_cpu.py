@@ -432,3 +432,40 @@ def test_frame_transform_like_the_reference():
         p.to_frame(rotating)
     assert np.allclose(p.to_frame(rotating, t=t).pos, a.pos) and np.allclose(p.to_frame(rotating, t=0.5).pos[:, 0],
                                                                             Rotation.from_rotvec(-Om * 0.5).as_matrix() @ x[:, 0])
+
+
+def test_combine_like_the_reference():
+    """tests/dynamics/test_dynamics_util.py:51-122 (TestCombine), without the unit bookkeeping."""
+    import gala_b200 as gb
+    rng = np.random.default_rng(8)
+    static = gb.StaticFrame()
+    x, v = rng.random(3), rng.random(3)
+    p1 = gb.PhaseSpacePosition(pos=x, vel=v)
+    p2 = gb.PhaseSpacePosition(pos=x, vel=v, frame=static)
+    x, v = rng.random((3, 5)), rng.random((3, 5))
+    p3 = gb.PhaseSpacePosition(pos=x, vel=v)
+    x, v = rng.random((2, 5)), rng.random((2, 5))
+    p5 = gb.PhaseSpacePosition(pos=x, vel=v)
+    psps = [p1, p2, p3, p5]
+    x, v = rng.random((3, 8)), rng.random((3, 8))
+    o1 = gb.Orbit(pos=x, vel=v)
+    o2 = gb.Orbit(pos=x, vel=v, t=np.arange(8.0))
+    o3 = gb.Orbit(pos=x, vel=v, t=np.arange(8.0), frame=static)
+    x3, v3 = rng.random((3, 8, 2)), rng.random((3, 8, 2))
+    o5 = gb.Orbit(pos=x3, vel=v3, t=np.arange(8.0))
+    orbs = [o1, o2, o3, o5]
+    for bad, exc in (([], ValueError), (p1, ValueError), ([p1, o1], TypeError), ([5, 5, 5], TypeError), (psps, ValueError),
+                     (orbs, ValueError), ([o2, gb.Orbit(pos=x, vel=v, t=np.arange(8.0) + 1e-3)], ValueError)):
+        with pytest.raises(exc):
+            gb.combine(bad)
+    assert gb.combine([p3]) is p3
+    for psp in psps:
+        new = gb.combine([psp] * 3)
+        n = psp.pos.shape[1] if psp.pos.ndim > 1 else 1
+        assert new.ndim == psp.ndim and new.pos.shape == (psp.ndim, 3 * n) and new.frame == psp.frame
+    for orb in orbs:
+        new = gb.combine([orb] * 4)
+        assert new.pos.shape == (3, 8, 4 * orb.norbits) and new.frame == orb.frame and new.hamiltonian is orb.hamiltonian
+        assert np.array_equal(new.pos[:, :, -1], orb.pos.reshape(3, 8, -1)[:, :, -1])
+    w0 = gb.combine((p3, gb.PhaseSpacePosition(pos=p3.pos + 1.0, vel=p3.vel)))     # tests/dynamics/nbody/test_nbody.py:38
+    assert w0.w().shape == (6, 10) and np.array_equal(w0.pos[:, 5:], p3.pos + 1.0)
