@@ -62,12 +62,49 @@ def extract_potential(pot):
         for k, v in pot.items():
             out[k] = extract_potential(v)
         return out
+    if wrapper == "TimeInterpolatedWrapper":
+        return _extract_time_interpolated(pot)
     if wrapper not in WRAPPER_TO_TYPE:
         raise TypeError(f"potential wrapper {wrapper} is not supported by the B200 engine")
     origin = getattr(pot, "origin", np.zeros(3))
     origin = getattr(origin, "value", origin)
     return _Extracted(WRAPPER_TO_TYPE[wrapper], pot.G, pot.c_parameters, origin, getattr(pot, "_R", None),
                       getattr(pot, "units", None))
+
+
+def _value(x):
+    return np.asarray(getattr(x, "value", x), dtype=np.float64)
+
+
+def _extract_time_interpolated(pot):
+    """gala ``TimeInterpolatedPotential`` -> ``gala_b200.TimeInterpolatedPotential``.  gala keeps the tables inside
+    the Cython wrapper (cytimeinterp.pyx:71-130), out of reach from Python; what it builds them FROM is public:
+    ``parameters['potential_cls' | 'time_knots' | 'interpolation_method' | <name>]``, ``_potential_param_names``,
+    ``_interp_params``, ``_extra_wrapped_kwargs``, ``origin`` and ``R`` (time_interpolated.py:59-260).  The wrapped
+    potential is instantiated by gala at every knot exactly as ``_setup_wrapper`` does for classes with derived C
+    parameters (:267-285), and its ``c_parameters`` row is what the device interpolates."""
+    P = pot.parameters
+    wcls = P["potential_cls"]
+    tk = _value(P["time_knots"])
+    names = list(pot._potential_param_names)
+    interp = set(pot._interp_params)
+    extra = dict(getattr(pot, "_extra_wrapped_kwargs", {}) or {})
+    rows, wtype = [], None
+    for i in range(len(tk) if interp else 1):
+        knot = wcls(units=pot.units, **{k: (P[k][i] if k in interp else P[k]) for k in names}, **extra)
+        wname = type(knot.c_instance).__name__
+        if wname not in WRAPPER_TO_TYPE:
+            raise TypeError(f"potential wrapper {wname} inside a TimeInterpolatedPotential is not supported by the B200 engine")
+        if wtype not in (None, WRAPPER_TO_TYPE[wname]):
+            raise TypeError("the wrapped potential resolves to different C types at different time knots")
+        wtype = WRAPPER_TO_TYPE[wname]
+        rows.append(_value(knot.c_parameters))
+    origin = getattr(pot, "origin", None)
+    R = getattr(pot, "R", None)
+    from .potential import TimeInterpolatedPotential
+    return TimeInterpolatedPotential.from_tables(wtype, pot.G, tk, np.array(rows), None if origin is None else _value(origin),
+                                                 None if R is None else _value(R), str(P["interpolation_method"]),
+                                                 getattr(pot, "units", None))
 
 
 def extract_frame(frame):

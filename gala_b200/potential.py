@@ -529,6 +529,42 @@ class TimeInterpolatedPotential(PotentialBase):
         self._spec = None
         self.strict_math = False
 
+    @classmethod
+    def from_tables(cls, wrapped_type, G, time_knots, rows, origins=None, Rs=None, interpolation_method="cspline",
+                    units=galactic):
+        """Build the device parameter vector from tables that already exist: ``rows`` (n_knots, n_wpar) = the wrapped
+        potential's C parameter vector at every knot (one row if nothing varies), ``origins`` (1 | n_knots, 3), ``Rs``
+        (1 | n_knots, 3, 3).  Used by ``gala_plugin`` for a gala ``TimeInterpolatedPotential``, whose knot potentials
+        gala itself instantiates (time_interpolated.py:161-260)."""
+        self = cls.__new__(cls)
+        if interpolation_method not in cls._METHODS:
+            raise ValueError(f"Interpolation method '{interpolation_method}' is not recognized. Supported methods are: "
+                             f"{list(cls._METHODS)}")
+        tk = np.ascontiguousarray(time_knots, dtype=np.float64)
+        n = tk.size
+        code, need = cls._METHODS[interpolation_method]
+        if tk.ndim != 1 or n < need or not np.all(np.diff(tk) > 0):
+            raise ValueError("time_knots must be one-dimensional, strictly increasing and long enough for the method")
+        rows = np.atleast_2d(np.asarray(rows, dtype=np.float64))
+        if rows.shape[0] == 1:
+            rows = np.repeat(rows, n, axis=0)
+        o = np.zeros((1, 3)) if origins is None else np.atleast_2d(np.asarray(origins, dtype=np.float64))
+        Rm = np.eye(3)[None] if Rs is None else np.asarray(Rs, dtype=np.float64)
+        Rm = Rm[None] if Rm.ndim == 2 else Rm
+        if rows.shape[0] != n or o.shape not in ((1, 3), (n, 3)) or Rm.shape not in ((1, 3, 3), (n, 3, 3)):
+            raise ValueError("tables must have one row per time knot (or a single constant row)")
+        self.potential_cls, self.time_knots, self.interpolation_method = None, tk, interpolation_method
+        self.units, self.G = units, float(G)
+        self._interp_params, self._wrapped_type = [], int(wrapped_type)
+        self._rows, self._origins, self._Rs = np.ascontiguousarray(rows), np.ascontiguousarray(o), np.ascontiguousarray(Rm)
+        self.origin, self.R = np.zeros(3), None
+        self.parameters = OrderedDict(time_knots=tk, interpolation_method=interpolation_method)
+        self.c_parameters = np.concatenate([[self._wrapped_type, code, n, rows.shape[1], o.shape[0], Rm.shape[0]],
+                                            tk, rows.ravel(), o.ravel(), Rm.ravel()])
+        self._spec = None
+        self.strict_math = False
+        return self
+
     def _c_parameters(self):
         return self.c_parameters
 
@@ -548,7 +584,7 @@ class TimeInterpolatedPotential(PotentialBase):
                                        cython_if_possible=cython_if_possible, save_all=save_all, t=t)
 
     def __repr__(self):
-        return (f"<TimeInterpolatedPotential: {self.potential_cls.__name__} "
+        return (f"<TimeInterpolatedPotential: {getattr(self.potential_cls, '__name__', f'C type {self._wrapped_type}')} "
                 f"interpolation_method='{self.interpolation_method}')>")
 
 

@@ -469,3 +469,59 @@ def test_combine_like_the_reference():
         assert np.array_equal(new.pos[:, :, -1], orb.pos.reshape(3, 8, -1)[:, :, -1])
     w0 = gb.combine((p3, gb.PhaseSpacePosition(pos=p3.pos + 1.0, vel=p3.vel)))     # tests/dynamics/nbody/test_nbody.py:38
     assert w0.w().shape == (6, 10) and np.array_equal(w0.pos[:, 5:], p3.pos + 1.0)
+
+
+def test_gala_plugin_extracts_time_interpolated_potentials():
+    """A gala TimeInterpolatedPotential seen through its public attributes (time_interpolated.py:59-260) becomes the
+    same device parameter vector as the native class built from the same inputs -- incl. a class with derived C
+    parameters (MN3), a moving origin and rotation matrices.  Stand-ins with gala's attribute names are used."""
+    from gala_b200 import gala_plugin as gp
+    T = np.linspace(0.0, 400.0, 9)
+    grow = 1.0 + 0.3 * T / 400.0
+    orb = np.stack([10 * np.cos(T / 100), 10 * np.sin(T / 100), 0 * T], axis=1)
+    ang = 0.04 * T
+    R = np.array([[[np.cos(a), -np.sin(a), 0.0], [np.sin(a), np.cos(a), 0.0], [0.0, 0.0, 1.0]] for a in ang])
+
+    def gala_like_class(native_cls, wrapper_name):
+        W = type(wrapper_name, (), {})
+
+        class K:                                     # what gala's potential_cls(units=..., **params) returns
+            def __init__(self, units=None, **kw):
+                self.c_parameters = native_cls(**kw).c_parameters
+                self.c_instance = W()
+        return K
+
+    def gala_like_ti(native_cls, wrapper_name, method, origin=None, R=None, **params):
+        names = [k for k in params]
+        interp = [k for k in names if np.ndim(params[k]) >= 1]
+        P = dict(potential_cls=gala_like_class(native_cls, wrapper_name), time_knots=T, interpolation_method=method, **params)
+        return type("FakeTI", (), {"c_instance": type("TimeInterpolatedWrapper", (), {})(), "parameters": P,
+                                   "_potential_param_names": names, "_interp_params": interp, "_extra_wrapped_kwargs": {},
+                                   "origin": origin, "R": R, "G": gb.G_GALACTIC, "units": None})()
+
+    cases = [
+        (gb.HernquistPotential, "HernquistWrapper", "cspline", dict(m=5e10 * grow, c=1.5), dict(origin=orb)),
+        (gb.MN3ExponentialDiskPotential, "MN3ExponentialDiskWrapper", "akima", dict(m=5e10 * grow, h_R=2.6, h_z=0.3), {}),
+        (gb.LongMuraliBarPotential, "LongMuraliBarWrapper", "linear", dict(m=1e10, a=4.0, b=0.8, c=0.25, alpha=0.0), dict(R=R)),
+    ]
+    for native_cls, wname, method, params, where in cases:
+        got = gp.extract_potential(gala_like_ti(native_cls, wname, method, **where, **params))
+        want = gb.TimeInterpolatedPotential(native_cls, T, interpolation_method=method, **params, **where)
+        assert isinstance(got, gb.TimeInterpolatedPotential)
+        assert np.array_equal(got.c_parameters, want.c_parameters), wname
+        assert got._components()[0][0] == want._components()[0][0] == gb._abi.POT_TIMEINTERP
+        assert got.time_bounds == (0.0, 400.0)
+    # inside a composite, next to a static component
+    from collections import OrderedDict
+
+    class FakeComposite(OrderedDict):
+        c_instance = type("CCompositePotentialWrapper", (), {})()
+    comp = FakeComposite()
+    comp["halo"] = type("FakePot", (), {"c_instance": type("SphericalNFWWrapper", (), {})(), "G": gb.G_GALACTIC,
+                                        "c_parameters": np.array([6e11, 16.0, 1.0, 1.0, 1.0]), "origin": np.zeros(3),
+                                        "_R": None, "units": None})()
+    comp["bar"] = gala_like_ti(*cases[2][:3], **cases[2][4], **cases[2][3])
+    out = gp.extract_potential(comp)
+    assert [c[0] for c in out._components()] == [gb._abi.POT_NFW_SPHERICAL, gb._abi.POT_TIMEINTERP]
+    with pytest.raises(TypeError):
+        gp.extract_potential(gala_like_ti(gb.HernquistPotential, "CylSplineWrapper", "linear", m=1e10, c=1.0))
