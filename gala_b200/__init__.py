@@ -20,5 +20,7 @@ from .mockstream import (BaseStreamDF, FardalStreamDF, StreaklineStreamDF, Lagra
                          MockStreamGenerator, DirectNBody, mockstream_dop853, mockstream_leapfrog)
 
 from .nonlinear import fast_lyapunov_max, surface_of_section
+from . import io
+from .io import load, save
 
 __version__ = "0.2.0"

@@ -159,6 +159,11 @@ class PotentialBase:
     def __call__(self, q, t=0.0):
         return self.energy(q, t)
 
+    def save(self, f):
+        """``PotentialBase.save`` (core.py:1186-1200): write the YAML specification (``gala_b200.io.save``)."""
+        from .io import save
+        save(self, f)
+
     def mass_enclosed(self, q, t=0.0):
         """``PotentialBase.mass_enclosed`` (core.py:649-723): r^2 |dPhi/dr| / G from a centred difference of the
         potential along the radius with the reference's step h = 1e-3, negative for a negative ``m`` parameter.
@@ -634,6 +639,7 @@ class MilkyWayPotential(CCompositePotential):
 
     def __init__(self, units=galactic, disk=None, halo=None, bulge=None, nucleus=None, version="v1"):
         super().__init__()
+        self.version = version
         if version in ("v2", "latest"):
             _setup_mwp_2022(self, units, disk, halo, bulge, nucleus)
         else:
