@@ -894,12 +894,44 @@ static int side_streams(SideStreams** out) {
 // contract of the header; the subtraction is the same IEEE operation on either side).
 static cudaError_t launch_fixed(Ctx& c, bool is_ruth4, const DevPot& P, const DevFrame& F, const double* dw0, size_t n,
                                 const double* dt_dev, int ntimes, double dt, int dt_from_t, int save_all, double* dout,
-                                int block, cudaStream_t st) {
+                                const void* ti_tab, int block, cudaStream_t st) {
     if (!is_ruth4)
-        return KCALL(c, leapfrog, P, dw0, n, dt_dev, ntimes, dt, dt_from_t, save_all, dout, block, st);
+        return KCALL(c, leapfrog, P, dw0, n, dt_dev, ntimes, dt, dt_from_t, save_all, dout, ti_tab, block, st);
     double cs[4], ds[4];
     ruth4_coeffs(cs, ds);
-    return KCALL(c, ruth4, P, F, dw0, n, dt_dev, ntimes, dt, dt_from_t, cs, ds, save_all, dout, block, st);
+    return KCALL(c, ruth4, P, F, dw0, n, dt_dev, ntimes, dt, dt_from_t, cs, ds, save_all, dout, ti_tab, block, st);
+}
+
+// Time-dependent composites in the fixed-step integrators: the state of every TimeInterpolated component at every
+// time of the grid is tabulated once on the device (k_ti_table) -- every lane evaluates at the same t[j].  The table
+// is a stream-ordered allocation (a few hundred KB), so DEVICE-mode calls stay asynchronous.
+struct TiTable {
+    void* p = nullptr;
+    cudaStream_t s = nullptr;
+    ~TiTable() { if (p) cudaFreeAsync(p, s); }
+};
+static int make_ti_table(Ctx& c, const DevPot& P, const double* dt_dev, int ntimes, TiTable& tab) {
+    if (!P.time_dep) return 0;
+    const size_t nb = KCALL(c, ti_table_bytes, P, ntimes);
+    tab.s = c.stream;
+    {   // keep freed table memory in the device's default pool instead of returning it to the OS at every synchronise
+        static std::mutex mu;
+        static bool done[MAXDEV] = {false};
+        std::lock_guard<std::mutex> g(mu);
+        if (!done[c.dev]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, c.dev) == cudaSuccess) {
+                uint64_t keep = (uint64_t)64 << 20;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            done[c.dev] = true;
+        }
+    }
+    CU(cudaMallocAsync(&tab.p, nb ? nb : 8, c.stream));
+    cudaError_t e = KCALL(c, ti_table, P, dt_dev, ntimes, tab.p, c.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "TimeInterpolated state table launch");
+    g_launches++;
+    return 0;
 }
 
 // One device's share of a fixed-step call: orbits [0, N) of arrays whose rows are `pitch` doubles apart on the
@@ -920,6 +952,7 @@ static int fixed_step_impl(bool is_ruth4, const gb_potential* pot, const gb_fram
     const void* dtg; RET_IF(stage_in(c, 2, t, (size_t)ntimes * sizeof(double), &dtg));
     const double* dt_dev = (const double*)dtg;
     const size_t rows = save_all ? (size_t)ntimes : 1;       // output rows per phase-space component
+    TiTable ti; RET_IF(make_ti_table(c, r.P, dt_dev, ntimes, ti));     // freed (stream-ordered) when the call returns
 
     // HOST buffers, many orbits: orbit-index chunks pipelined over two streams, so the H2D copy of
     // chunk k+1 and the D2H copy of chunk k-1 overlap the kernel of chunk k (the (6,N) layout makes a
@@ -948,7 +981,7 @@ static int fixed_step_impl(bool is_ruth4, const gb_potential* pot, const gb_fram
             CU(cudaMemcpy2DAsync(din[k], n * sizeof(double), w0 + a0, pitch * sizeof(double), n * sizeof(double), 6,
                                  cudaMemcpyHostToDevice, st));
             cudaError_t e = launch_fixed(c, is_ruth4, r.P, F, (const double*)din[k], n, dt_dev, ntimes, dt, dt_from_t,
-                                         save_all, (double*)dou[k], block, st);
+                                         save_all, (double*)dou[k], ti.p, block, st);
             if (e != cudaSuccess) return cuda_fail(e, "integrator kernel launch");
             g_launches++;
             CU(cudaMemcpy2DAsync(w_out + a0, pitch * sizeof(double), dou[k], n * sizeof(double), n * sizeof(double),
@@ -965,7 +998,7 @@ static int fixed_step_impl(bool is_ruth4, const gb_potential* pot, const gb_fram
     const void* dw0; RET_IF(stage_in_2d(c, 0, w0, 6, N, pitch, &dw0));
     void* dout; RET_IF(stage_out_alloc(c, 1, w_out, rows * 6 * N * sizeof(double), &dout));
     cudaError_t e = launch_fixed(c, is_ruth4, r.P, F, (const double*)dw0, N, dt_dev, ntimes, dt, dt_from_t, save_all,
-                                 (double*)dout, block, c.stream);
+                                 (double*)dout, ti.p, block, c.stream);
     if (e != cudaSuccess) return cuda_fail(e, "integrator kernel launch");
     if (N) g_launches++;
     RET_IF(stage_out_copy_2d(c, w_out, dout, 6 * rows, N, pitch));

@@ -124,6 +124,53 @@ GB_DEV void ti_gradient(const double* p, const double* e, double t, double x, do
     gy += R[1] * ax + R[4] * ay + R[7] * az;
     gz += R[2] * ax + R[5] * ay + R[8] * az;
 }
+// ---- per-step state table (fixed-step integrators): every lane of leapfrog / Ruth4 evaluates the TimeInterpolated
+// components at the SAME time t[j], so the interval search, the cubics, the axis-angle -> matrix conversion and
+// (fast build) the derived constants are formed ONCE per step and component by a small pre-pass kernel
+// (kernels.cu: k_ti_table, one thread per (step, component)) and read back by every lane with warp-uniform loads --
+// the same functions on the same inputs as the per-lane path of ti_gradient (which DOP853, with its per-lane stage
+// times, keeps), so the results are bit-identical to it.  Row j of the table holds P.n states (only the
+// TimeInterpolated components' entries are written / read).
+struct TiState {
+    double wp[GB_TI_MAXPAR];
+    double o[3], R[9];
+    double dl[8];
+    int ok, wtype;
+};
+GB_DEV void ti_fill_state(const DevPot& P, int i, double t, TiState& s) {
+    const DevComp& c = P.c[i];
+    const TiView v = ti_view(&P.par[c.poff], P.ext + c.eoff);
+    double wp[GB_TI_MAXPAR], o[3], R[9], dl[8];
+    for (int k = 0; k < GB_TI_MAXPAR; k++) wp[k] = 0.;
+    for (int k = 0; k < 8; k++) dl[k] = 0.;
+    for (int k = 0; k < 3; k++) o[k] = 0.;
+    for (int k = 0; k < 9; k++) R[k] = 0.;
+    const bool ok = ti_state(v, t, wp, o, R);
+#if !GB_STRICT
+    if (ok) gb_derive(v.wtype, wp, dl);
+#endif
+    for (int k = 0; k < GB_TI_MAXPAR; k++) s.wp[k] = wp[k];
+    for (int k = 0; k < 3; k++) s.o[k] = o[k];
+    for (int k = 0; k < 9; k++) s.R[k] = R[k];
+    for (int k = 0; k < 8; k++) s.dl[k] = dl[k];
+    s.ok = ok ? 1 : 0;
+    s.wtype = v.wtype;
+}
+GB_DEV void ti_gradient_state(const TiState& s, double x, double y, double z, double& gx, double& gy, double& gz) {
+    if (!s.ok) { gx = CUDART_NAN; gy = CUDART_NAN; gz = CUDART_NAN; return; }
+    double X, Y, Z, ax = 0., ay = 0., az = 0.;
+    ti_to_body(s.o, s.R, x, y, z, X, Y, Z);
+#if GB_STRICT
+    gb_comp_gradient<false>(s.wtype, s.wp, nullptr, X, Y, Z, ax, ay, az);
+#else
+    FastCtx<GB_USE_ALL> c2(X, Y, Z);
+    gb_comp_accum<false>(s.wtype, s.wp, s.dl, nullptr, c2);
+    c2.finish(ax, ay, az);
+#endif
+    gx += s.R[0] * ax + s.R[3] * ay + s.R[6] * az;
+    gy += s.R[1] * ax + s.R[4] * ay + s.R[7] * az;
+    gz += s.R[2] * ax + s.R[5] * ay + s.R[8] * az;
+}
 template <int WHAT>     // 0 value, 1 density
 GB_DEV double ti_scalar(const double* p, const double* e, double t, double x, double y, double z) {
     const TiView v = ti_view(p, e);
@@ -146,13 +193,29 @@ template <bool HEAVY, bool TI> struct CompositeGeneric {
     static constexpr int kFixedStepMaxThreads = HEAVY ? 256 : 128, kFixedStepMinBlocks = HEAVY ? 1 : 4;
     GB_DEV static void gradient(const DevPot& P, double t, double x, double y, double z,
                                 double& gx, double& gy, double& gz) {
+        gradient_t<false>(P, t, nullptr, x, y, z, gx, gy, gz);
+    }
+    // the fixed-step integrators: `row` = the TimeInterpolated components' states at this step's time (k_ti_table)
+    GB_DEV static void gradient_row(const DevPot& P, const TiState* __restrict__ row, double x, double y, double z,
+                                    double& gx, double& gy, double& gz) {
+        gradient_t<true>(P, 0., row, x, y, z, gx, gy, gz);
+    }
+    template <bool CTA_STATE>
+    GB_DEV static void gradient_t(const DevPot& P, double t, const TiState* __restrict__ row, double x, double y, double z,
+                                  double& gx, double& gy, double& gz) {
 #if GB_STRICT
         gx = 0.; gy = 0.; gz = 0.;
         for (int i = 0; i < P.n; i++) {
             const DevComp& c = P.c[i];
             const double* p = &P.par[c.poff];
             const double* e = P.ext + c.eoff;
-            if constexpr (TI) { if (c.type == GB_POT_TIMEINTERP) { ti_gradient(p, e, t, x, y, z, gx, gy, gz); continue; } }
+            if constexpr (TI) {
+                if (c.type == GB_POT_TIMEINTERP) {
+                    if constexpr (CTA_STATE) ti_gradient_state(row[i], x, y, z, gx, gy, gz);
+                    else ti_gradient(p, e, t, x, y, z, gx, gy, gz);
+                    continue;
+                }
+            }
             if (!c.shift) {
                 gb_comp_gradient<HEAVY>(c.type, p, e, x, y, z, gx, gy, gz);
             } else {
@@ -175,7 +238,13 @@ template <bool HEAVY, bool TI> struct CompositeGeneric {
             const double* p = &P.par[c.poff];
             const double* d = &P.drv[c.doff];
             const double* e = P.ext + c.eoff;
-            if constexpr (TI) { if (c.type == GB_POT_TIMEINTERP) { ti_gradient(p, e, t, x, y, z, ctx.gx, ctx.gy, ctx.gz); continue; } }
+            if constexpr (TI) {
+                if (c.type == GB_POT_TIMEINTERP) {
+                    if constexpr (CTA_STATE) ti_gradient_state(row[i], x, y, z, ctx.gx, ctx.gy, ctx.gz);
+                    else ti_gradient(p, e, t, x, y, z, ctx.gx, ctx.gy, ctx.gz);
+                    continue;
+                }
+            }
             if (!c.shift) {
                 gb_comp_accum<HEAVY>(c.type, p, d, e, ctx);
             } else {

@@ -101,7 +101,8 @@ __global__ void k_ham_gradient(const __grid_constant__ DevPot P, const __grid_co
 template <class C, bool SAVE>
 __global__ void __launch_bounds__(C::kFixedStepMaxThreads, C::kFixedStepMinBlocks)
 k_leapfrog(const __grid_constant__ DevPot P, const double* __restrict__ w0, size_t N,
-           const double* __restrict__ t, int ntimes, double dt, int dt_from_t, double* __restrict__ out) {
+           const double* __restrict__ t, int ntimes, double dt, int dt_from_t, double* __restrict__ out,
+           const TiState* __restrict__ ti_tab) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     if (dt_from_t) dt = t[1] - t[0];       // DEVICE-mode calls: the grid lives on the device (capi.cu:launch_fixed)
@@ -113,14 +114,17 @@ k_leapfrog(const __grid_constant__ DevPot P, const double* __restrict__ w0, size
         __stcs(out + 3 * TS + i, vx); __stcs(out + 4 * TS + i, vy); __stcs(out + 5 * TS + i, vz);
     }
     double gx, gy, gz;
-    C::gradient(P, t[0], x, y, z, gx, gy, gz);
+    // time-dependent composites: row j of ti_tab = the TimeInterpolated components at t[j] (k_ti_table below)
+    if constexpr (C::kTimeDependent) C::gradient_row(P, ti_tab, x, y, z, gx, gy, gz);
+    else C::gradient(P, t[0], x, y, z, gx, gy, gz);
     double hx = vx - gx * dt / 2., hy = vy - gy * dt / 2., hz = vz - gz * dt / 2.;
     // The synchronised velocity is only formed where it is read: every step when SAVE, else on the
     // last step (same expression, same operands as c_leapfrog_step, leapfrog.pyx:35-51).
 #pragma unroll 1
     for (int j = 1; j < ntimes; j++) {
         x = x + hx * dt; y = y + hy * dt; z = z + hz * dt;
-        C::gradient(P, C::kTimeDependent ? t[j] : 0., x, y, z, gx, gy, gz);       // c_leapfrog_step(..., t[j], ...) leapfrog.pyx:106
+        if constexpr (C::kTimeDependent) C::gradient_row(P, ti_tab + (size_t)j * P.n, x, y, z, gx, gy, gz);
+        else C::gradient(P, 0., x, y, z, gx, gy, gz);                             // c_leapfrog_step(..., t[j], ...) leapfrog.pyx:106
         if (SAVE || j == ntimes - 1) { vx = hx - gx * dt / 2.; vy = hy - gy * dt / 2.; vz = hz - gz * dt / 2.; }
         hx = hx - gx * dt; hy = hy - gy * dt; hz = hz - gz * dt;
         if (SAVE) {
@@ -149,7 +153,7 @@ template <class C, bool ROT, bool SAVE>
 __global__ void __launch_bounds__(C::kFixedStepMaxThreads, C::kFixedStepMinBlocks)
 k_ruth4(const __grid_constant__ DevPot P, const __grid_constant__ DevFrame F, const __grid_constant__ Ruth4Coef K,
         const double* __restrict__ w0, size_t N, const double* __restrict__ t, int ntimes, double dt, int dt_from_t,
-        double* __restrict__ out) {
+        double* __restrict__ out, const TiState* __restrict__ ti_tab) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     if (dt_from_t) dt = t[1] - t[0];
@@ -165,7 +169,8 @@ k_ruth4(const __grid_constant__ DevPot P, const __grid_constant__ DevFrame F, co
         for (int s = 0; s < 4; s++) {
             if (s > 0) {
                 double gx, gy, gz;
-                C::gradient(P, C::kTimeDependent ? t[j] : 0., x, y, z, gx, gy, gz);   // c_ruth4_step(..., t[j], ...) ruth4.pyx:100
+                if constexpr (C::kTimeDependent) C::gradient_row(P, ti_tab + (size_t)j * P.n, x, y, z, gx, gy, gz);
+                else C::gradient(P, 0., x, y, z, gx, gy, gz);                        // c_ruth4_step(..., t[j], ...) ruth4.pyx:100
                 if (!ROT) {
                     vx = vx - K.d[s] * gx * dt; vy = vy - K.d[s] * gy * dt; vz = vz - K.d[s] * gz * dt;
                 } else {
@@ -188,6 +193,14 @@ k_ruth4(const __grid_constant__ DevPot P, const __grid_constant__ DevFrame F, co
         out[i] = x; out[N + i] = y; out[2 * N + i] = z;
         out[3 * N + i] = vx; out[4 * N + i] = vy; out[5 * N + i] = vz;
     }
+}
+
+// State of every TimeInterpolated component at every time of the grid: thread = (step j, component i).
+__global__ void k_ti_table(const __grid_constant__ DevPot P, const double* __restrict__ t, int ntimes, TiState* __restrict__ tab) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (size_t)ntimes * P.n) return;
+    const int j = (int)(k / P.n), i = (int)(k % P.n);
+    if (P.c[i].type == GB_POT_TIMEINTERP) ti_fill_state(P, i, t[j], tab[k]);
 }
 
 #endif  // GB_PART == 1
@@ -260,25 +273,35 @@ cudaError_t ham_gradient(const DevPot& P, const DevFrame& F, const double* w, do
     return cudaGetLastError();
 }
 
+size_t ti_table_bytes(const DevPot& P, int ntimes) { return (size_t)ntimes * P.n * sizeof(TiState); }
+
+cudaError_t ti_table(const DevPot& P, const double* t, int ntimes, void* tab, cudaStream_t s) {
+    const size_t n = (size_t)ntimes * P.n;
+    if (n == 0) return cudaSuccess;
+    k_ti_table<<<nblocks(n, 128), 128, 0, s>>>(P, t, ntimes, (TiState*)tab);
+    return cudaGetLastError();
+}
+
 cudaError_t leapfrog(const DevPot& P, const double* w0, size_t N, const double* t, int ntimes, double dt,
-                     int dt_from_t, int save_all, double* out, int block, cudaStream_t s) {
+                     int dt_from_t, int save_all, double* out, const void* ti_tab, int block, cudaStream_t s) {
     if (N == 0) return cudaSuccess;
     if (save_all) {
-        GB_SIG_SWITCH(P.sig, (k_leapfrog<C, true><<<nblocks(N, block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads), block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads, 0, s>>>(P, w0, N, t, ntimes, dt, dt_from_t, out)));
+        GB_SIG_SWITCH(P.sig, (k_leapfrog<C, true><<<nblocks(N, block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads), block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads, 0, s>>>(P, w0, N, t, ntimes, dt, dt_from_t, out, (const TiState*)ti_tab)));
     } else {
-        GB_SIG_SWITCH(P.sig, (k_leapfrog<C, false><<<nblocks(N, block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads), block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads, 0, s>>>(P, w0, N, t, ntimes, dt, dt_from_t, out)));
+        GB_SIG_SWITCH(P.sig, (k_leapfrog<C, false><<<nblocks(N, block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads), block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads, 0, s>>>(P, w0, N, t, ntimes, dt, dt_from_t, out, (const TiState*)ti_tab)));
     }
     return cudaGetLastError();
 }
 
 cudaError_t ruth4(const DevPot& P, const DevFrame& F, const double* w0, size_t N, const double* t, int ntimes,
-                  double dt, int dt_from_t, const double* cs, const double* ds, int save_all, double* out, int block,
+                  double dt, int dt_from_t, const double* cs, const double* ds, int save_all, double* out,
+                  const void* ti_tab, int block,
                   cudaStream_t s) {
     if (N == 0) return cudaSuccess;
     Ruth4Coef K;
     for (int k = 0; k < 4; k++) { K.c[k] = cs[k]; K.d[k] = ds[k]; }
     const bool rot = F.type != GB_FRAME_STATIC;
-#define GB_R4(ROT, SAVE) GB_SIG_SWITCH(P.sig, (k_ruth4<C, ROT, SAVE><<<nblocks(N, block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads), block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads, 0, s>>>(P, F, K, w0, N, t, ntimes, dt, dt_from_t, out)))
+#define GB_R4(ROT, SAVE) GB_SIG_SWITCH(P.sig, (k_ruth4<C, ROT, SAVE><<<nblocks(N, block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads), block < C::kFixedStepMaxThreads ? block : C::kFixedStepMaxThreads, 0, s>>>(P, F, K, w0, N, t, ntimes, dt, dt_from_t, out, (const TiState*)ti_tab)))
     if (rot) { if (save_all) { GB_R4(true, true); } else { GB_R4(true, false); } }
     else     { if (save_all) { GB_R4(false, true); } else { GB_R4(false, false); } }
 #undef GB_R4

@@ -36,11 +36,15 @@ struct Dop853Args {
                            double* out, int block, cudaStream_t s);                                        \
     cudaError_t ham_gradient(const DevPot& P, const DevFrame& F, const double* w, double t, size_t N,     \
                              double* f, int block, cudaStream_t s);                                        \
+    /* time-dependent composites: the TimeInterpolated components' state at every grid time (ti_tab) */    \
+    size_t ti_table_bytes(const DevPot& P, int ntimes);                                                    \
+    cudaError_t ti_table(const DevPot& P, const double* t, int ntimes, void* tab, cudaStream_t s);        \
     cudaError_t leapfrog(const DevPot& P, const double* w0, size_t N, const double* t, int ntimes,        \
-                         double dt, int dt_from_t, int save_all, double* out, int block, cudaStream_t s);  \
+                         double dt, int dt_from_t, int save_all, double* out, const void* ti_tab,          \
+                         int block, cudaStream_t s);                                                       \
     cudaError_t ruth4(const DevPot& P, const DevFrame& F, const double* w0, size_t N, const double* t,    \
                       int ntimes, double dt, int dt_from_t, const double* cs, const double* ds,            \
-                      int save_all, double* out, int block, cudaStream_t s);                               \
+                      int save_all, double* out, const void* ti_tab, int block, cudaStream_t s);           \
     cudaError_t dop853_static(const DevPot& P, const DevFrame& F, const double* w0, size_t N,             \
                               const double* t, int ntimes, const Dop853Args& a, int save_all,              \
                               const uint32_t* perm, unsigned long long* queue, size_t orb0, size_t nslots, \
