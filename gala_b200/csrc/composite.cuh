@@ -129,14 +129,19 @@ GB_DEV void ti_gradient(const double* p, const double* e, double t, double x, do
 // (fast build) the derived constants are formed ONCE per step and component by a small pre-pass kernel
 // (kernels.cu: k_ti_table, one thread per (step, component)) and read back by every lane with warp-uniform loads --
 // the same functions on the same inputs as the per-lane path of ti_gradient (which DOP853, with its per-lane stage
-// times, keeps), so the results are bit-identical to it.  Row j of the table holds P.n states (only the
-// TimeInterpolated components' entries are written / read).
+// times, keeps), so the results are bit-identical to it.  Row j of the table holds one state per TimeInterpolated
+// component, in component order (ti_count(P) states).
 struct TiState {
     double wp[GB_TI_MAXPAR];
     double o[3], R[9];
     double dl[8];
     int ok, wtype;
 };
+GB_HD int ti_count(const DevPot& P) {
+    int n = 0;
+    for (int i = 0; i < P.n; i++) n += (P.c[i].type == GB_POT_TIMEINTERP);
+    return n;
+}
 GB_DEV void ti_fill_state(const DevPot& P, int i, double t, TiState& s) {
     const DevComp& c = P.c[i];
     const TiView v = ti_view(&P.par[c.poff], P.ext + c.eoff);
@@ -203,6 +208,7 @@ template <bool HEAVY, bool TI> struct CompositeGeneric {
     template <bool CTA_STATE>
     GB_DEV static void gradient_t(const DevPot& P, double t, const TiState* __restrict__ row, double x, double y, double z,
                                   double& gx, double& gy, double& gz) {
+        [[maybe_unused]] int k_ti = 0;          // rank of the next TimeInterpolated component = its slot in `row`
 #if GB_STRICT
         gx = 0.; gy = 0.; gz = 0.;
         for (int i = 0; i < P.n; i++) {
@@ -211,7 +217,7 @@ template <bool HEAVY, bool TI> struct CompositeGeneric {
             const double* e = P.ext + c.eoff;
             if constexpr (TI) {
                 if (c.type == GB_POT_TIMEINTERP) {
-                    if constexpr (CTA_STATE) ti_gradient_state(row[i], x, y, z, gx, gy, gz);
+                    if constexpr (CTA_STATE) ti_gradient_state(row[k_ti++], x, y, z, gx, gy, gz);
                     else ti_gradient(p, e, t, x, y, z, gx, gy, gz);
                     continue;
                 }
@@ -240,7 +246,7 @@ template <bool HEAVY, bool TI> struct CompositeGeneric {
             const double* e = P.ext + c.eoff;
             if constexpr (TI) {
                 if (c.type == GB_POT_TIMEINTERP) {
-                    if constexpr (CTA_STATE) ti_gradient_state(row[i], x, y, z, ctx.gx, ctx.gy, ctx.gz);
+                    if constexpr (CTA_STATE) ti_gradient_state(row[k_ti++], x, y, z, ctx.gx, ctx.gy, ctx.gz);
                     else ti_gradient(p, e, t, x, y, z, ctx.gx, ctx.gy, ctx.gz);
                     continue;
                 }

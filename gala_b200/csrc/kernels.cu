@@ -115,6 +115,7 @@ k_leapfrog(const __grid_constant__ DevPot P, const double* __restrict__ w0, size
     }
     double gx, gy, gz;
     // time-dependent composites: row j of ti_tab = the TimeInterpolated components at t[j] (k_ti_table below)
+    const int nti = C::kTimeDependent ? ti_count(P) : 0;
     if constexpr (C::kTimeDependent) C::gradient_row(P, ti_tab, x, y, z, gx, gy, gz);
     else C::gradient(P, t[0], x, y, z, gx, gy, gz);
     double hx = vx - gx * dt / 2., hy = vy - gy * dt / 2., hz = vz - gz * dt / 2.;
@@ -123,7 +124,7 @@ k_leapfrog(const __grid_constant__ DevPot P, const double* __restrict__ w0, size
 #pragma unroll 1
     for (int j = 1; j < ntimes; j++) {
         x = x + hx * dt; y = y + hy * dt; z = z + hz * dt;
-        if constexpr (C::kTimeDependent) C::gradient_row(P, ti_tab + (size_t)j * P.n, x, y, z, gx, gy, gz);
+        if constexpr (C::kTimeDependent) C::gradient_row(P, ti_tab + (size_t)j * nti, x, y, z, gx, gy, gz);
         else C::gradient(P, 0., x, y, z, gx, gy, gz);                             // c_leapfrog_step(..., t[j], ...) leapfrog.pyx:106
         if (SAVE || j == ntimes - 1) { vx = hx - gx * dt / 2.; vy = hy - gy * dt / 2.; vz = hz - gz * dt / 2.; }
         hx = hx - gx * dt; hy = hy - gy * dt; hz = hz - gz * dt;
@@ -164,12 +165,13 @@ k_ruth4(const __grid_constant__ DevPot P, const __grid_constant__ DevFrame F, co
         __stcs(out + i, x); __stcs(out + TS + i, y); __stcs(out + 2 * TS + i, z);
         __stcs(out + 3 * TS + i, vx); __stcs(out + 4 * TS + i, vy); __stcs(out + 5 * TS + i, vz);
     }
+    const int nti = C::kTimeDependent ? ti_count(P) : 0;
     for (int j = 1; j < ntimes; j++) {
 #pragma unroll
         for (int s = 0; s < 4; s++) {
             if (s > 0) {
                 double gx, gy, gz;
-                if constexpr (C::kTimeDependent) C::gradient_row(P, ti_tab + (size_t)j * P.n, x, y, z, gx, gy, gz);
+                if constexpr (C::kTimeDependent) C::gradient_row(P, ti_tab + (size_t)j * nti, x, y, z, gx, gy, gz);
                 else C::gradient(P, 0., x, y, z, gx, gy, gz);                        // c_ruth4_step(..., t[j], ...) ruth4.pyx:100
                 if (!ROT) {
                     vx = vx - K.d[s] * gx * dt; vy = vy - K.d[s] * gy * dt; vz = vz - K.d[s] * gz * dt;
@@ -195,12 +197,16 @@ k_ruth4(const __grid_constant__ DevPot P, const __grid_constant__ DevFrame F, co
     }
 }
 
-// State of every TimeInterpolated component at every time of the grid: thread = (step j, component i).
+// State of every TimeInterpolated component at every time of the grid: thread = (step j, component i); row j holds
+// the TimeInterpolated components only, in component order.
 __global__ void k_ti_table(const __grid_constant__ DevPot P, const double* __restrict__ t, int ntimes, TiState* __restrict__ tab) {
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= (size_t)ntimes * P.n) return;
     const int j = (int)(k / P.n), i = (int)(k % P.n);
-    if (P.c[i].type == GB_POT_TIMEINTERP) ti_fill_state(P, i, t[j], tab[k]);
+    if (P.c[i].type != GB_POT_TIMEINTERP) return;
+    int rank = 0;
+    for (int q = 0; q < i; q++) rank += (P.c[q].type == GB_POT_TIMEINTERP);
+    ti_fill_state(P, i, t[j], tab[(size_t)j * ti_count(P) + rank]);
 }
 
 #endif  // GB_PART == 1
@@ -273,7 +279,7 @@ cudaError_t ham_gradient(const DevPot& P, const DevFrame& F, const double* w, do
     return cudaGetLastError();
 }
 
-size_t ti_table_bytes(const DevPot& P, int ntimes) { return (size_t)ntimes * P.n * sizeof(TiState); }
+size_t ti_table_bytes(const DevPot& P, int ntimes) { return (size_t)ntimes * ti_count(P) * sizeof(TiState); }
 
 cudaError_t ti_table(const DevPot& P, const double* t, int ntimes, void* tab, cudaStream_t s) {
     const size_t n = (size_t)ntimes * P.n;

@@ -36,6 +36,14 @@ def _cases():
     comp["halo"] = gb.NFWPotential(m=6e11, r_s=16.0)
     comp["sat"] = gb.TimeInterpolatedPotential(gb.PlummerPotential, T, m=2e10 * grow, b=1.0, origin=2.5 * orb)
     out["static_halo_plus_moving_satellite"] = comp
+    # TimeInterpolated, static, TimeInterpolated: the fixed-step kernels read the k-th TimeInterpolated component from
+    # slot k of the per-step state row (kernels.cu: k_ti_table), not from its component index
+    comp2 = gb.CCompositePotential()
+    comp2["bar"] = gb.TimeInterpolatedPotential(gb.LongMuraliBarPotential, T, m=1e10, a=3.0, b=1.0, c=0.5, R=Rs)
+    comp2["halo"] = gb.NFWPotential(m=6e11, r_s=16.0)
+    comp2["sat"] = gb.TimeInterpolatedPotential(gb.HernquistPotential, T, interpolation_method="akima", m=3e10 * grow, c=1.2, origin=2.0 * orb)
+    comp2["disk"] = gb.MiyamotoNagaiPotential(m=6e10, a=3.0, b=0.3)
+    out["two_interpolated_around_static_ones"] = comp2
     return out
 
 
