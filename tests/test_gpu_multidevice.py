@@ -204,3 +204,27 @@ def test_concurrent_callers_share_the_scratch_safely(mw):
     for k in range(len(jobs)):
         for rep in range(3):
             assert np.array_equal(got[k][rep], want[k], equal_nan=True), (k, rep)
+
+
+@pytest.mark.parametrize("devs", device_lists())
+def test_time_interpolated_composite_sharded_bit_identical(devs):
+    """A time-dependent composite: every device builds its own per-step state table (capi.cu: make_ti_table) and its
+    own spline tables; the pipelined HOST path (N >= 65536) and the plain one must both return the single-device bits,
+    for leapfrog, Ruth4 and DOPRI853."""
+    T = np.linspace(0.0, 400.0, 9)
+    grow = 1.0 + 0.3 * T / 400.0
+    orb = np.stack([8 * np.cos(T / 150), 8 * np.sin(T / 150), 0.5 * np.sin(T / 90)], axis=1)
+    pot = gb.CCompositePotential()
+    pot["halo"] = gb.NFWPotential(m=6e11, r_s=16.0)
+    pot["sat"] = gb.TimeInterpolatedPotential(gb.PlummerPotential, T, m=2e10 * grow, b=1.0, origin=orb)
+    H = gb.Hamiltonian(pot)
+    t = np.linspace(0.0, 400.0, 81)
+    for N in (1003, 70_001):
+        w0 = make_ic(lambda q: gb.MilkyWayPotential2022().gradient(q), N, 13)
+        one = [gb.leapfrog_integrate_hamiltonian(H, w0, t, save_all=0)[1], gb.ruth4_integrate_hamiltonian(H, w0, t, save_all=0)[1],
+               gb.dop853_integrate_hamiltonian(H, w0[:, :2000], t[::8].copy(), save_all=0)[1]]
+        with use_devices(devs):
+            many = [gb.leapfrog_integrate_hamiltonian(H, w0, t, save_all=0)[1], gb.ruth4_integrate_hamiltonian(H, w0, t, save_all=0)[1],
+                    gb.dop853_integrate_hamiltonian(H, w0[:, :2000], t[::8].copy(), save_all=0)[1]]
+        for a, b in zip(one, many):
+            assert np.isfinite(a).all() and np.array_equal(a, b)
