@@ -1384,7 +1384,7 @@ int gb_stream_release(const gb_potential* pot, double G, const double* prog_w, c
     static const int need[4] = {4, 0, 3, 6};
     if (ncols < need[df_kind]) return fail(-12, "too few random deviates per particle for this DF");
     if (Np && (!prog_idx || !sign || !stream_w0 || (need[df_kind] && !draws))) return fail(-12, "null data pointer");
-    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    Resolved r; RET_IF(resolve(pot, r, c.stream, true));
     const int block = pick_block(c, Np);
     const void *dpw, *dpt, *dpm, *dpi, *dsg, *dnr;
     RET_IF(stage_in(c, 0, prog_w, (size_t)ntimes * 6 * sizeof(double), &dpw));
@@ -1461,7 +1461,7 @@ static int mock_dop853_impl(const gb_potential* pot, const gb_frame* fr, const d
     const size_t Np = D.count();
     if (D.Np && (!stream_w0 || !t1 || !stream_w)) return fail(-12, "null data pointer");
     DevFrame F; RET_IF(resolve_frame(fr, F));
-    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    Resolved r; RET_IF(resolve(pot, r, c.stream, true));
     const int block = c.block > 0 ? c.block : 64;
     Dop853Args a;
     // dop853_step (dop853.pyx:45-69): uround 0 -> 2.3e-16, hmax 0, nstiff hard-coded to 1
@@ -1515,7 +1515,7 @@ int gb_mockstream_dop853_animate(const gb_potential* pot, const gb_frame* fr, co
     if (Np && (!w0_rows || !release_idx || !snapshots || !final_w)) return fail(-12, "null data pointer");
     RET_IF(pool_keep());
     DevFrame F; RET_IF(resolve_frame(fr, F));
-    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    Resolved r; RET_IF(resolve(pot, r, c.stream, true));
     int nout = (ntimes - 1) / output_every + 1;
     if ((ntimes - 1) % output_every != 0) nout += 1;                  // mockstream.pyx:360-363
     Dop853Args a;
@@ -1552,7 +1552,7 @@ static int mock_leapfrog_impl(const gb_potential* pot, const double* stream_w0, 
     const size_t Np = D.count();
     if (D.Np && (!stream_w0 || !t1 || !stream_w)) return fail(-12, "null data pointer");
     if (dt == 0.0) return fail(-12, "dt must be non-zero");
-    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    Resolved r; RET_IF(resolve(pot, r, c.stream, true));
     const int block = pick_block(c, Np);
     const void *dw0 = stream_w0, *dt1 = t1;
     void* dout = stream_w;

@@ -219,8 +219,9 @@ __global__ void k_ti_table(const __grid_constant__ DevPot P, const double* __res
 static inline unsigned nblocks(size_t N, int block) { return (unsigned)((N + block - 1) / block); }
 
 // the TimeInterpolated signature exists only where time reaches the potential (evaluation, fixed-step integrators,
-// DOP853, extrema: parts 1-3, 7, 8); capi.cu:resolve refuses time-dependent potentials for the other entry points
-#if GB_PART == 1 || GB_PART == 2 || GB_PART == 3 || GB_PART == 7 || GB_PART == 8
+// DOP853, mock streams without massive bodies, extrema: parts 1-4, 7, 8); capi.cu:resolve refuses time-dependent
+// potentials for the other entry points (Hessians, massive bodies, Lyapunov)
+#if GB_PART == 1 || GB_PART == 2 || GB_PART == 3 || GB_PART == 4 || GB_PART == 7 || GB_PART == 8
 #define GB_SIG_CASE_TI(CALL) case SIG_GENERIC_TI: { using C = Composite<SIG_GENERIC_TI>; CALL; } break;
 #else
 #define GB_SIG_CASE_TI(CALL)

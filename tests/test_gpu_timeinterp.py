@@ -272,3 +272,109 @@ def test_interpolation_accuracy_and_bounds():
         gb.TimeInterpolatedPotential(gb.KeplerPotential, knots, m=m[:5])          # test_mismatched_parameter_length
     with pytest.raises(ValueError):
         gb.TimeInterpolatedPotential(gb.KeplerPotential, knots[::-1].copy(), m=m)
+
+
+def _time_dependent_galaxy(kind):
+    """a static halo and disc + (bar) a bar turning in the inertial frame through rotation matrices at the knots, or
+    (satellite) an infalling, growing Hernquist satellite on a moving origin -- knots cover a backward integration from 0"""
+    Tk = np.linspace(-200.0, 10.0, 43)
+    pot = gb.CCompositePotential()
+    pot["halo"] = gb.NFWPotential(m=6e11, r_s=16.0)
+    pot["disk"] = gb.MiyamotoNagaiPotential(m=6e10, a=3.0, b=0.3)
+    if kind == "bar":
+        Rk = np.array([Rotation.from_rotvec([0.0, 0.0, -0.04 * a]).as_matrix() for a in Tk])
+        pot["bar"] = gb.TimeInterpolatedPotential(gb.LongMuraliBarPotential, Tk, m=1e10, a=4.0, b=0.8, c=0.25, R=Rk)
+    else:
+        track = np.stack([60.0 + 0.2 * Tk, -20.0 - 0.15 * Tk, 10.0 + 0.05 * Tk], axis=1)
+        pot["lmc"] = gb.TimeInterpolatedPotential(gb.HernquistPotential, Tk, m=1.5e11 * np.linspace(0.6, 1.0, Tk.size), c=10.0,
+                                                  origin=track)
+    return pot
+
+
+@pytest.mark.parametrize("kind,integ", [("satellite", "dopri853"), ("satellite", "leapfrog"), ("bar", "leapfrog")])
+def test_mock_stream_in_a_time_dependent_potential(ref, kind, integ):
+    """MockStreamGenerator in a galaxy with an infalling satellite / a bar turning in the inertial frame (the uses the
+    reference's TimeInterpolatedPotential was written for): the release (c_d2_dr2 at the release time, df.pyx:61-92),
+    the progenitor orbit and every particle's integration (mockstream.pyx:176-303, 442-620) see the potential at their
+    own time.  Same checks as test_gpu_mockstream.py's parity tests, against the compiled reference."""
+    from gala_b200.mockstream import DirectNBody
+    KMS = gb.KMS_TO_KPC_MYR
+    PROG_W0 = np.array([13.0, 0.0, 20.0, 0.0, 130.0 * KMS, 50.0 * KMS])
+    pot = _time_dependent_galaxy(kind)
+    H = gb.Hamiltonian(pot)
+    n_steps, npart = 120, 3
+    mk = lambda: np.random.RandomState(7)                                    # noqa: E731
+    gen = gb.MockStreamGenerator(gb.FardalStreamDF(gala_modified=True, random_state=mk()), H)
+    stream, prog = gen.run(PROG_W0, 2.5e4, dt=-1.0, n_steps=n_steps, n_particles=npart, Integrator=integ)
+    assert stream.pos.shape == (3, 2 * npart * (n_steps + 1)) and np.isfinite(stream.pos).all()
+    t = gb.parse_time_specification(None, dt=-1.0, n_steps=n_steps)
+    orb = DirectNBody(PROG_W0, [None], external_potential=pot).integrate_orbit(t=t, Integrator=integ)
+    prog_orb = gb.Orbit(pos=orb.pos[:, ::-1, 0], vel=orb.vel[:, ::-1, 0], t=t[::-1], hamiltonian=H)
+    s0 = gb.FardalStreamDF(gala_modified=True, random_state=mk()).sample(prog_orb, 2.5e4, n_particles=npart)
+    # release against the reference's own potential evaluations at the release times (strict kernels, like
+    # test_gpu_mockstream.py::test_fardal_release_parity: the second difference of Phi with h = 1e-2 amplifies rounding)
+    from oracle import oracle
+    pm = np.full(n_steps + 1, 2.5e4)
+    x0, v0, t10 = oracle.fardal_release_numpy(ref, pot, prog_orb.pos.T, prog_orb.vel.T, prog_orb.t, pm,
+                                              np.full(n_steps + 1, npart, dtype="i4"), mk(), gala_modified=True)
+    pot.strict_math = True
+    ss = gb.FardalStreamDF(gala_modified=True, random_state=mk()).sample(prog_orb, 2.5e4, n_particles=npart)
+    pot.strict_math = False
+    assert np.array_equal(s0.release_time, t10) and np.array_equal(ss.release_time, t10)
+    off = np.sqrt(((x0 - prog_orb.pos.T[np.searchsorted(prog_orb.t, t10)]) ** 2).sum(1))
+    e_pos, e_vel = np.max(np.abs(ss.pos.T - x0) / off[:, None]), np.max(np.abs(ss.vel.T - v0)) / np.abs(v0).max()
+    f_pos = np.max(np.abs(s0.pos.T - x0) / off[:, None])
+    print(f"\n[release, time-dependent {kind}] strict: offsets {e_pos:.1e}, velocities {e_vel:.1e}; fast: offsets {f_pos:.1e}")
+    assert e_pos < 5e-9 and e_vel < 1e-10 and f_pos < 1e-7
+    w0 = np.vstack([s0.pos, s0.vel])
+    tf = prog_orb.t[-1]
+    out = np.empty_like(w0)
+    for t1 in np.unique(s0.release_time):
+        m = s0.release_time == t1
+        if integ == "dopri853":
+            rows, st, rc = ref.dop853_step_rows(H, np.ascontiguousarray(w0[:, m].T), t1, tf, prog_orb.t[1] - prog_orb.t[0], group=True)
+            assert rc >= 0
+            out[:, m] = rows.T
+        else:
+            # one particle per oracle call: the reference's time_interp_gradient back-rotates a batch with AoS indices on
+            # SoA arrays (time_interp_wrapper.cpp:189-201, SURVEY 8f-3) and is only self-consistent for N = 1
+            k = int((tf - t1) / 1.0 + 0.5)
+            for i in np.flatnonzero(m):
+                out[:, i] = w0[:, i] if k == 0 else ref.leapfrog(pot, np.ascontiguousarray(w0[:, i:i + 1]), t1 + np.arange(k + 1) * 1.0,
+                                                                 save_all=False)[:, 0]
+    d = relnorm(np.vstack([stream.pos, stream.vel]), out)
+    print(f"[mock stream, time-dependent {kind}, {integ}] median={np.median(d):.2e} max={d.max():.2e}")
+    assert d.max() < (1e-9 if integ == "dopri853" else 1e-11)
+    # the time-dependent component matters: the same run without it ends somewhere else
+    static = gb.CCompositePotential(halo=pot["halo"], disk=pot["disk"])
+    s_static, _ = gb.MockStreamGenerator(gb.FardalStreamDF(gala_modified=True, random_state=mk()), gb.Hamiltonian(static)).run(
+        PROG_W0, 2.5e4, dt=-1.0, n_steps=n_steps, n_particles=npart, Integrator=integ)
+    assert np.abs(s_static.pos - stream.pos).max() > 1e-3
+    # massive bodies in a time-dependent field stay with the reference's CPU path: the library says so
+    gen_sg = gb.MockStreamGenerator(gb.FardalStreamDF(random_state=mk()), H, progenitor_potential=gb.PlummerPotential(m=2.5e4, b=0.004))
+    with pytest.raises(gb._abi.GalaB200Error, match="time-dependent"):
+        gen_sg.run(PROG_W0, 2.5e4, dt=-1.0, n_steps=20, n_particles=1, Integrator=integ)
+
+
+def test_turning_bar_trips_the_stiffness_test_like_the_reference(ref):
+    """A quirk carried over on purpose: ``dop853_step`` hands ``nstiff = 1`` to ``dop853`` whatever its caller asked for
+    (dop853.pyx:64), so the stiffness test runs after every accepted step of a stream particle, and a bar turning
+    through interpolated rotation matrices makes it fire (code -4) for some release times -- in the reference's own
+    C++ as on the device.  ``err_if_fail`` then raises the reference's RuntimeError."""
+    KMS = gb.KMS_TO_KPC_MYR
+    PROG_W0 = np.array([13.0, 0.0, 20.0, 0.0, 130.0 * KMS, 50.0 * KMS])
+    pot = _time_dependent_galaxy("bar")
+    H = gb.Hamiltonian(pot)
+    gen = gb.MockStreamGenerator(gb.FardalStreamDF(gala_modified=True, random_state=np.random.RandomState(7)), H)
+    with pytest.raises(RuntimeError, match="Integration failed with code -4"):
+        gen.run(PROG_W0, 2.5e4, dt=-1.0, n_steps=120, n_particles=3)
+    # the reference on the same particles
+    t = gb.parse_time_specification(None, dt=-1.0, n_steps=120)
+    from gala_b200.mockstream import DirectNBody
+    orb = DirectNBody(PROG_W0, [None], external_potential=pot).integrate_orbit(t=t, Integrator="dopri853")
+    prog_orb = gb.Orbit(pos=orb.pos[:, ::-1, 0], vel=orb.vel[:, ::-1, 0], t=t[::-1], hamiltonian=H)
+    s0 = gb.FardalStreamDF(gala_modified=True, random_state=np.random.RandomState(7)).sample(prog_orb, 2.5e4, n_particles=3)
+    w0 = np.vstack([s0.pos, s0.vel])
+    codes = [ref.dop853_step_rows(H, np.ascontiguousarray(w0[:, s0.release_time == t1].T), t1, 0.0, 1.0, group=True)[2]
+             for t1 in np.unique(s0.release_time)]
+    assert min(codes) == -4
