@@ -132,8 +132,15 @@ def test_unsupported_entry_points_say_so():
         pot.hessian(np.ones((3, 2)))
     H = gb.Hamiltonian(pot)
     prog = gb.PhaseSpacePosition(pos=[8.0, 0.0, 0.0], vel=[0.0, 0.07, 0.0])
+    # mock streams without massive bodies ARE supported (test_mock_stream_in_a_time_dependent_potential); massive
+    # bodies and the Lyapunov kernel are not
+    stream, _ = gb.MockStreamGenerator(gb.StreaklineStreamDF(), H).run(prog, 1e4, dt=1.0, n_steps=50, Integrator="leapfrog")
+    assert np.isfinite(stream.pos).all()
     with pytest.raises(gb._abi.GalaB200Error, match="time-dependent"):
-        gb.MockStreamGenerator(gb.StreaklineStreamDF(), H).run(prog, 1e4, dt=1.0, n_steps=50, Integrator="leapfrog")
+        gb.MockStreamGenerator(gb.StreaklineStreamDF(), H, progenitor_potential=gb.PlummerPotential(m=1e4, b=0.01)).run(
+            prog, 1e4, dt=1.0, n_steps=50, Integrator="leapfrog")
+    with pytest.raises(gb._abi.GalaB200Error, match="time-dependent"):
+        gb.fast_lyapunov_max(np.array([8.0, 0.0, 0.0, 0.0, 0.07, 0.0]), H, dt=1.0, n_steps=100, return_orbit=False)
 
 
 def test_rotating_bar_inertial_vs_rotating_frame(ref):

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU session 31: state table compacted to the TimeInterpolated components (rank mapping), full suite, timings
-OUT=gpurun_out/r2s31; mkdir -p $OUT
+OUT=gpurun_out/${GB_SESSION:-r2s31}; mkdir -p $OUT
 export GB_PARITY_LOG=$PWD/$OUT/parity_stats.txt
 timeout 1200 python -m pytest tests -m gpu -q -x > $OUT/pytest.log 2>&1; echo "pytest exit $?" >> $OUT/pytest.log; tail -4 $OUT/pytest.log
 unset GB_PARITY_LOG
