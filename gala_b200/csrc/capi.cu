@@ -785,11 +785,11 @@ int gb_hessian(const gb_potential* pot, const double* q, double t, size_t N, dou
                     return fail(-14, "Computing Hessian matrices for rotated potentials is currently not supported.");
         }
     }
-    Resolved r; RET_IF(resolve(pot, r, c.stream));
+    Resolved r; RET_IF(resolve(pot, r, c.stream, true));
     const int block = pick_block(c, N);
     const void* dq; RET_IF(stage_in(c, 0, q, 3 * N * sizeof(double), &dq));
     void* dout; RET_IF(stage_out_alloc(c, 1, hess, 9 * N * sizeof(double), &dout));
-    cudaError_t e = KCALL(c, eval_hessian, r.P, (const double*)dq, N, (double*)dout, block, c.stream);
+    cudaError_t e = KCALL(c, eval_hessian, r.P, (const double*)dq, t, N, (double*)dout, block, c.stream);
     if (e != cudaSuccess) return cuda_fail(e, "hessian kernel launch");
     if (N) g_launches++;
     RET_IF(stage_out_copy(c, hess, dout, 9 * N * sizeof(double)));

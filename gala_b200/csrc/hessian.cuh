@@ -170,13 +170,33 @@ GB_DEV void gb_grad_t(int type, const double* p, const T& x, const T& y, const T
 
 // hess (3,3,N): H[i][j][n] = d^2 Phi / dq_i dq_j at point n (CPotentialWrapper.hessian, cpotential.pyx:164-182,
 // returned by PotentialBase.hessian as (n_dim, n_dim, N), core.py:535-600)
-__global__ void k_eval_hessian(const __grid_constant__ DevPot P, const double* __restrict__ q, size_t N,
+// A TimeInterpolated component (time_interp_hessian, time_interp_wrapper.cpp:254-318): the wrapped potential's
+// Hessian at the interpolated parameters in body coordinates X = R (q - o), turned back as R^T H R -- here the dual
+// parts simply ride through the two linear maps; NaN outside the knots.
+__global__ void k_eval_hessian(const __grid_constant__ DevPot P, const double* __restrict__ q, double t, size_t N,
                                double* __restrict__ hess) {
     const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     Dual3 g[3] = {mk(0, 0, 0, 0), mk(0, 0, 0, 0), mk(0, 0, 0, 0)};
     for (int i = 0; i < P.n; i++) {
         const DevComp& c = P.c[i];
+        if (c.type == GB_POT_TIMEINTERP) {
+            const TiView v = ti_view(&P.par[c.poff], P.ext + c.eoff);
+            double wp[GB_TI_MAXPAR], o[3], R[9];
+            if (!ti_state(v, t, wp, o, R)) {
+                for (int k = 0; k < 3; k++) g[k] = mk(CUDART_NAN, CUDART_NAN, CUDART_NAN, CUDART_NAN);
+                continue;
+            }
+            const Dual3 sx = mk(q[n] - o[0], 1, 0, 0), sy = mk(q[N + n] - o[1], 0, 1, 0), sz = mk(q[2 * N + n] - o[2], 0, 0, 1);
+            const Dual3 X = R[0] * sx + R[1] * sy + R[2] * sz, Y = R[3] * sx + R[4] * sy + R[5] * sz,
+                        Z = R[6] * sx + R[7] * sy + R[8] * sz;
+            Dual3 b[3] = {mk(0, 0, 0, 0), mk(0, 0, 0, 0), mk(0, 0, 0, 0)};
+            gb_grad_t<Dual3>(v.wtype, wp, X, Y, Z, b[0], b[1], b[2]);
+            g[0] = g[0] + (R[0] * b[0] + R[3] * b[1] + R[6] * b[2]);
+            g[1] = g[1] + (R[1] * b[0] + R[4] * b[1] + R[7] * b[2]);
+            g[2] = g[2] + (R[2] * b[0] + R[5] * b[1] + R[8] * b[2]);
+            continue;
+        }
         const double sx = c.shift ? c.q0[0] : 0., sy = c.shift ? c.q0[1] : 0., sz = c.shift ? c.q0[2] : 0.;
         const Dual3 x = mk(q[n] - sx, 1, 0, 0), y = mk(q[N + n] - sy, 0, 1, 0), z = mk(q[2 * N + n] - sz, 0, 0, 1);
         gb_grad_t<Dual3>(c.type, &P.par[c.poff], x, y, z, g[0], g[1], g[2]);

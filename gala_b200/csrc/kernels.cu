@@ -220,7 +220,7 @@ static inline unsigned nblocks(size_t N, int block) { return (unsigned)((N + blo
 
 // the TimeInterpolated signature exists only where time reaches the potential (evaluation, fixed-step integrators,
 // DOP853, mock streams without massive bodies, extrema: parts 1-4, 7, 8); capi.cu:resolve refuses time-dependent
-// potentials for the other entry points (Hessians, massive bodies, Lyapunov)
+// potentials for the other entry points (massive bodies, Lyapunov)
 #if GB_PART == 1 || GB_PART == 2 || GB_PART == 3 || GB_PART == 4 || GB_PART == 7 || GB_PART == 8
 #define GB_SIG_CASE_TI(CALL) case SIG_GENERIC_TI: { using C = Composite<SIG_GENERIC_TI>; CALL; } break;
 #else
@@ -434,9 +434,9 @@ cudaError_t fardal_release(const DevPot& P, double G, const double* prog_w, cons
     return cudaGetLastError();
 }
 
-cudaError_t eval_hessian(const DevPot& P, const double* q, size_t N, double* hess, int block, cudaStream_t s) {
+cudaError_t eval_hessian(const DevPot& P, const double* q, double t, size_t N, double* hess, int block, cudaStream_t s) {
     if (N == 0) return cudaSuccess;
-    k_eval_hessian<<<nblocks(N, block), block, 0, s>>>(P, q, N, hess);
+    k_eval_hessian<<<nblocks(N, block), block, 0, s>>>(P, q, t, N, hess);
     return cudaGetLastError();
 }
 #endif  // GB_PART == 4

@@ -30,8 +30,8 @@ struct Dop853Args {
                             int block, cudaStream_t s);                                                    \
     cudaError_t eval_density(const DevPot& P, const double* q, double t, size_t N, double* out,           \
                              int block, cudaStream_t s);                                                   \
-    cudaError_t eval_hessian(const DevPot& P, const double* q, size_t N, double* hess, int block,        \
-                             cudaStream_t s);                                                              \
+    cudaError_t eval_hessian(const DevPot& P, const double* q, double t, size_t N, double* hess,         \
+                             int block, cudaStream_t s);                                                   \
     cudaError_t ham_energy(const DevPot& P, const DevFrame& F, const double* w, double t, size_t N,       \
                            double* out, int block, cudaStream_t s);                                        \
     cudaError_t ham_gradient(const DevPot& P, const DevFrame& F, const double* w, double t, size_t N,     \

@@ -573,6 +573,14 @@ class TimeInterpolatedPotential(PotentialBase):
     def _c_parameters(self):
         return self.c_parameters
 
+    def hessian(self, q, t=0.0):
+        """``time_interp_hessian`` (time_interp_wrapper.cpp:254-318) at time t.  With rotation matrices the reference's
+        ``PotentialBase.hessian`` refuses (core.py:581-589), and so does this class; the C ABI itself returns
+        R^T H R like the reference's C function (``gb_hessian``)."""
+        if self._Rs.shape[0] > 1 or not np.array_equal(self._Rs[0], np.eye(3)):
+            raise NotImplementedError("Computing Hessian matrices for rotated potentials is currently not supported.")
+        return super().hessian(q, t)
+
     @property
     def time_bounds(self):
         return float(self.time_knots[0]), float(self.time_knots[-1])

@@ -82,10 +82,10 @@ enum gb_pot_type {
                                      library builds the per-element splines and the axis-angle form of the rotation
                                      (time_interp.cpp:181-405); evaluation outside [t_knots[0], t_knots[-1]] gives NaN
                                      (time_interp_wrapper.cpp:103-106).  Supported by gb_gradient / gb_energy /
-                                     gb_density, the Hamiltonian entries, gb_leapfrog, gb_ruth4, gb_dop853,
+                                     gb_density / gb_hessian, the Hamiltonian entries, gb_leapfrog, gb_ruth4, gb_dop853,
                                      gb_integrate_extrema, gb_stream_release and the mock-stream entries without
                                      massive bodies (gb_mockstream_dop853[_animate], gb_mockstream_leapfrog); the
-                                     Hessian, N-body and Lyapunov entry points return -11 for it.                  */
+                                     N-body and Lyapunov entry points return -11 for it.                           */
     GB_POT_NTYPES
 };
 
