@@ -20,7 +20,7 @@ from .mockstream import (BaseStreamDF, FardalStreamDF, StreaklineStreamDF, Lagra
                          MockStreamGenerator, DirectNBody, mockstream_dop853, mockstream_leapfrog)
 
 from .nonlinear import fast_lyapunov_max, surface_of_section
-from . import io
-from .io import load, save
+from . import potential_io as io        # gala's name for it (gala.potential.potential.io); the file is not called io.py so that it can never shadow the standard library's
+from .potential_io import load, save
 
 __version__ = "0.2.0"

@@ -160,8 +160,8 @@ class PotentialBase:
         return self.energy(q, t)
 
     def save(self, f):
-        """``PotentialBase.save`` (core.py:1186-1200): write the YAML specification (``gala_b200.io.save``)."""
-        from .io import save
+        """``PotentialBase.save`` (core.py:1186-1200): write the YAML specification (``gala_b200.io.save``, potential_io.py)."""
+        from .potential_io import save
         save(self, f)
 
     def mass_enclosed(self, q, t=0.0):
