@@ -138,7 +138,20 @@ def fam_timeinterp():
         H = gb.Hamiltonian(comp)
         finite(comp.gradient(w0[:3].copy(), t=100.0), comp.energy(w0[:3].copy(), t=100.0))
         finite(gb.leapfrog_integrate_hamiltonian(H, w0, t, save_all=0)[1])
+        finite(gb.ruth4_integrate_hamiltonian(H, w0, t, save_all=1)[1])
         finite(gb.dop853_integrate_hamiltonian(H, w0, t[::8].copy())[1])
+        finite(gb.PotentialBase.hessian(comp, w0[:3].copy(), 100.0))
+    # a stream in a galaxy with an infalling, growing satellite (release + particles at their own times)
+    Tk = np.linspace(-200.0, 10.0, 43)
+    track = np.stack([60.0 + 0.2 * Tk, -20.0 - 0.15 * Tk, 10.0 + 0.05 * Tk], axis=1)
+    gal = gb.CCompositePotential()
+    gal["halo"] = gb.NFWPotential(m=6e11, r_s=16.0)
+    gal["lmc"] = gb.TimeInterpolatedPotential(gb.HernquistPotential, Tk, m=1.5e11 * np.linspace(0.6, 1.0, Tk.size), c=10.0, origin=track)
+    prog = gb.PhaseSpacePosition(pos=[13.0, 0.0, 20.0], vel=[0.0, 130.0 * KMS, 50.0 * KMS])
+    for integ in ("dopri853", "leapfrog"):
+        gen = gb.MockStreamGenerator(gb.FardalStreamDF(random_state=np.random.default_rng(1)), gb.Hamiltonian(gal))
+        stream, p = gen.run(prog, 2.5e4, dt=-1.0, n_steps=100, n_particles=2, Integrator=integ)
+        finite(stream.pos, stream.vel, p.pos)
 
 
 def fam_nbody():
