@@ -594,3 +594,53 @@ def test_reference_time_interpolated_doctest_numbers(ref):
         gb.TimeInterpolatedPotential(gb.NullPotential, t)
     with pytest.raises(ValueError):
         pot.integrate_orbit(np.ones(6), dt=1.0, n_steps=200)
+
+
+def test_reference_time_interpolated_quirks_are_what_the_gpu_tests_assume(ref):
+    """Three properties of the reference's own C/C++ that the GPU tests lean on, pinned here on the CPU so that a change of
+    the reference (or of how the oracle drives it) is noticed where it is cheap:
+    (1) ``time_interp_gradient`` back-rotates a batch with AoS indices on SoA arrays (time_interp_wrapper.cpp:189-201):
+        a multi-point call with a rotating component differs from per-point calls -- the GPU tests call it per point;
+    (2) ``time_interp_hessian`` zeroes its output before accumulating (:303-312): the Hessian of a composite is the last
+        TimeInterpolated component's plus what follows it;
+    (3) ``dop853_step`` runs the stiffness test after every accepted step (nstiff = 1, dop853.pyx:64): a stream particle
+        in a potential with a turning bar can stop with code -4, while the same call in the static part does not."""
+    from scipy.spatial.transform import Rotation
+    Tk = np.linspace(-200.0, 10.0, 43)
+    Rk = np.array([Rotation.from_rotvec([0.0, 0.0, -0.04 * a]).as_matrix() for a in Tk])
+    halo = gb.NFWPotential(m=6e11, r_s=16.0)
+    disk = gb.MiyamotoNagaiPotential(m=6e10, a=3.0, b=0.3)
+    bar = gb.TimeInterpolatedPotential(gb.LongMuraliBarPotential, Tk, m=1e10, a=4.0, b=0.8, c=0.25, R=Rk)
+    gal = gb.CCompositePotential(halo=halo, disk=disk, bar=bar)
+    q = np.ascontiguousarray(np.random.default_rng(2).normal(0, 6.0, (3, 6)))
+    # (1)
+    batch = ref.gradient(bar, q, -50.0)
+    single = np.concatenate([ref.gradient(bar, np.ascontiguousarray(q[:, i:i + 1]), -50.0) for i in range(6)], axis=1)
+    assert np.abs(batch - single).max() > 1e-3 * np.abs(single).max()           # not even the first point survives the batch
+    h = 1e-5                                       # the per-point gradient IS the derivative of the reference's potential
+    for j in range(3):
+        dq = np.zeros((3, 1)); dq[j] = h
+        num = (ref.energy(bar, q[:, :1] + dq, -50.0) - ref.energy(bar, q[:, :1] - dq, -50.0)) / (2 * h)
+        assert np.isclose(num[0], single[j, 0], rtol=1e-6)
+    # (2)
+    Hc = ref.hessian(gal, q, -50.0)
+    assert np.allclose(Hc, ref.hessian(bar, q, -50.0), rtol=1e-13, atol=0)
+    assert np.abs(Hc - sum(ref.hessian(p, q, -50.0) for p in (halo, disk, bar))).max() > 0.1 * np.abs(Hc).max()
+    # (3)
+    KMS = gb.KMS_TO_KPC_MYR
+    H_bar, H_static = gb.Hamiltonian(gal), gb.Hamiltonian(gb.CCompositePotential(halo=halo, disk=disk))
+    w0 = np.array([13.0, 0.0, 20.0, 0.0, 130.0 * KMS, 50.0 * KMS]).reshape(6, 1)
+    t = -np.arange(121.0)
+    back, _, rc = ref.dop853(H_bar, w0, t, nbatch=1)
+    assert rc == 0
+    px, pv, pt = back[:3, ::-1, 0].T.copy(), back[3:, ::-1, 0].T.copy(), t[::-1].copy()
+    x0, v0, t10 = oracle.fardal_release_numpy(ref, gal, px, pv, pt, np.full(121, 2.5e4), np.full(121, 3, dtype="i4"),
+                                              np.random.RandomState(7), gala_modified=True)
+    rows = np.hstack([x0, v0])
+    codes_bar, codes_static = [], []
+    for t1 in np.unique(t10):
+        grp = np.ascontiguousarray(rows[t10 == t1])
+        codes_bar.append(ref.dop853_step_rows(H_bar, grp, t1, 0.0, 1.0, group=True)[2])
+        codes_static.append(ref.dop853_step_rows(H_static, grp, t1, 0.0, 1.0, group=True)[2])
+    assert min(codes_static) >= 0 and min(codes_bar) == -4 and set(codes_bar) <= {0, 1, -4}
+    print(f"\n[reference dop853_step in a turning bar] {codes_bar.count(-4)} of {len(codes_bar)} release times stop with code -4")
